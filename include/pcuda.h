@@ -1,0 +1,175 @@
+/*
+ * pcuda.h — C-ABI of libpcuda.so: the B200 (sm_100a) kernels behind PointCloudUDA's
+ * adversarial-adaptation hot path.
+ *
+ * The reference (sulaimanvesal/PointCloudUDA) has no FFI of its own: the boundary is three
+ * Python-level call sites.  Each entry point below names the reference code it replaces
+ * (paths relative to the reference's src/):
+ *
+ *   pcuda_entropy_fwd / _bwd      inline expressions  train_mscmrseg.py:222,265
+ *                                                     train_mmwhs.py:213-217,224-225,240-243
+ *   pcuda_chamfer_fwd / _bwd      utils/loss.py:40-76  (batch_NN_loss, batch_pairwise_dist)
+ *   pcuda_pointmlp_fwd / _bwd     networks/PointNetCls.py:38-44 (STN3d trunk), :84-88 (STNkd
+ *                                 trunk), :143-163 (PointNetfeat trunk + global max-pool)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter is documented "host";
+ *   - the caller allocates inputs, outputs and workspaces and keeps them alive until the
+ *     stream has passed the launch; the library owns no device memory;
+ *   - launches are asynchronous on `stream`; no entry point synchronises, allocates or frees,
+ *     so all of them are legal under CUDA-graph stream capture;
+ *   - return value: 0 on success; a negative PCUDA_E* code for a rejected argument;
+ *     a positive value is a cudaError_t from the launch.  Nothing throws or exits.
+ *     pcuda_last_error_string() gives a thread-local description of the last failure.
+ */
+#ifndef PCUDA_H_
+#define PCUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCUDA_VERSION 100 /* major*100 + minor */
+
+typedef void* pcuda_stream_t; /* a cudaStream_t */
+
+enum {
+  PCUDA_OK = 0,
+  PCUDA_E_NULL = -1,        /* required pointer is NULL */
+  PCUDA_E_SHAPE = -2,       /* negative / inconsistent extent */
+  PCUDA_E_UNSUPPORTED = -3, /* valid request this build has no kernel for */
+  PCUDA_E_ALIGN = -4,       /* pointer not aligned as documented */
+  PCUDA_E_WORKSPACE = -5    /* workspace too small */
+};
+
+enum { PCUDA_ACT_SIGMOID = 0, PCUDA_ACT_SOFTMAX = 1 };
+
+int pcuda_version(void);
+const char* pcuda_last_error_string(void);
+const char* pcuda_error_name(int code);
+/* SM count of the current device (cached); used by callers to size benchmarks. */
+int pcuda_sm_count(void);
+/* Benchmark-only knob for A/B-ing kernel variants (key, value); not part of the reference-facing
+ * contract.  Keys: 0 = entropy fast-log (0/1), 1 = chamfer rows*1000+threads, 2 = force fp32 MLP. */
+int pcuda_tune(int key, int value);
+
+/* ------------------------------------------------------------------------------------------
+ * Entropy / self-information map.
+ *   p = sigmoid(z)            (PCUDA_ACT_SIGMOID, train_mscmrseg.py:222)
+ *   p = softmax(z, dim=C)     (PCUDA_ACT_SOFTMAX, train_mmwhs.py:213,240)
+ *   m = ((-1*p) * log(p + smooth)) * inv_norm     inv_norm = 1 or 1/ln(C) (train_mmwhs.py:224)
+ *   mean_out = mean_{b,hw} sum_c m                (train_mmwhs.py:225,243), optional
+ * z, m, p: contiguous [B, C, HW] fp32 (NCHW with H*W flattened).  p and mean_out may be NULL.
+ * ws: PCUDA_ENTROPY_WS_BYTES bytes, zero-filled once by the caller at allocation; the kernel
+ *     leaves it zeroed again.  Required only when mean_out != NULL.
+ * C in [1, 16].
+ */
+#define PCUDA_ENTROPY_WS_BYTES 16
+int pcuda_entropy_fwd(const float* z, float* m, float* p, float* mean_out, void* ws, int B,
+                      int C, int64_t HW, int activation, float inv_norm, float smooth,
+                      pcuda_stream_t stream);
+
+/* Backward of the above w.r.t. z.
+ *   grad_m   [B,C,HW]  upstream gradient of the map           (may be NULL = zeros)
+ *   grad_p   [B,C,HW]  upstream gradient of p (D1 branch)     (may be NULL)
+ *   grad_mean  device scalar, upstream gradient of mean_out   (may be NULL)
+ *   grad_z   [B,C,HW]  output
+ */
+int pcuda_entropy_bwd(const float* z, const float* grad_m, const float* grad_p,
+                      const float* grad_mean, float* grad_z, int B, int C, int64_t HW,
+                      int activation, float inv_norm, float smooth, pcuda_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Chamfer / nearest-neighbour loss  (utils/loss.py:40-76).
+ *   P[b,i,j] = fl(fl(|x_i|^2 + |y_j|^2) - 2 * x_i.y_j)   with every dot product evaluated as
+ *              fmaf(a2,b2, fmaf(a1,b1, a0*b0))            (what bmm with K=3 computes)
+ *   d        = sqrtf(P + 1e-5f)
+ *   d1[b,i], i1[b,i] = min / first arg-min over j         (loss.py:68-69)
+ *   d2[b,j], i2[b,j] = min / first arg-min over i         (loss.py:71-72)
+ *   loss     = sum_b (sum_i d1)/N /B + sum_b (sum_j d2)/N /B      (loss.py:73-75; the
+ *              reference divides both terms by x.size(1) = N)
+ * x [B,N,3], y [B,M,3] contiguous fp32.  i1/i2 are int64 (torch.min index dtype).
+ * ws: pcuda_chamfer_ws_bytes(B,N,M) bytes; zero-filled once by the caller at allocation, left
+ *     zeroed by every call.  loss may be NULL (then ws may be NULL too).
+ */
+size_t pcuda_chamfer_ws_bytes(int B, int N, int M);
+int pcuda_chamfer_fwd(const float* x, const float* y, int B, int N, int M, float* d1,
+                      int64_t* i1, float* d2, int64_t* i2, float* loss, void* ws,
+                      pcuda_stream_t stream);
+
+/* Backward through fixed indices:
+ *   grad_x[b,i] = G/(N*B) * [ (x_i - y_{i1(i)})/d1_i + sum_{j: i2(j)=i} (x_i - y_j)/d2_j ]
+ *   grad_y[b,j] = G/(N*B) * [ (y_j - x_{i2(j)})/d2_j + sum_{i: i1(i)=j} (y_j - x_i)/d1_i ]
+ * G = *grad_loss (device scalar).  grad_x / grad_y may each be NULL.
+ * The many-to-one sums are accumulated in 64-bit fixed point (2^-40 resolution), so the result
+ * is independent of scheduling order.
+ * ws: pcuda_chamfer_bwd_ws_bytes(B,N,M) bytes, any contents.
+ */
+size_t pcuda_chamfer_bwd_ws_bytes(int B, int N, int M);
+int pcuda_chamfer_bwd(const float* x, const float* y, const float* d1, const int64_t* i1,
+                      const float* d2, const int64_t* i2, const float* grad_loss, int B, int N,
+                      int M, float* grad_x, float* grad_y, void* ws, pcuda_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PointNet shared MLP (+ global max-pool): a stack of L layers
+ *     y_l = W_l a_{l-1} + b_l ; z_l = BatchNorm1d(y_l) ; a_l = relu_l ? max(z_l,0) : z_l
+ * applied independently to each of the B*N points (Conv1d with kernel_size 1,
+ * networks/PointNetCls.py:41-43, :84-86, :143-161), followed — when pool != 0 — by
+ * max over the N points of each cloud (:44, :87, :162).
+ *
+ * BatchNorm1d semantics (train != 0): per-channel mean and biased variance over all B*N
+ * columns; running_mean/var updated with `momentum` and the unbiased variance, exactly as
+ * torch.nn.BatchNorm1d does.  train == 0 normalises with running_mean/var and updates nothing.
+ */
+typedef struct pcuda_mlp_layer {
+  int32_t cin, cout;
+  int32_t relu;          /* apply ReLU after BN */
+  int32_t reserved;
+  const float* weight;   /* [cout, cin] */
+  const float* bias;     /* [cout] or NULL */
+  const float* gamma;    /* [cout] (BN weight) */
+  const float* beta;     /* [cout] (BN bias) */
+  float* running_mean;   /* [cout] or NULL */
+  float* running_var;    /* [cout] or NULL */
+  float* save_mean;      /* [cout]  fwd: out, bwd: in */
+  float* save_invstd;    /* [cout]  fwd: out, bwd: in */
+  float* y;              /* [B*N, cout] pre-BN activations, point-major. fwd: out (saved for
+                            bwd), bwd: in.  May be NULL for the LAST layer when pool != 0 —
+                            the pooled layer is never materialised. */
+  float* grad_weight;    /* bwd out [cout, cin]  (NULL: skip weight/bias/BN-param gradients) */
+  float* grad_bias;      /* bwd out [cout] (train-mode BN cancels the bias: exact zeros) */
+  float* grad_gamma;     /* bwd out [cout] */
+  float* grad_beta;      /* bwd out [cout] */
+} pcuda_mlp_layer_t;
+
+enum { PCUDA_MLP_FP32 = 0, PCUDA_MLP_BF16 = 1 };
+
+/* x: [B, C0, N] fp32 addressed as x[b*sxb + c*sxc + n*sxn] (element strides) — the reference
+ *    passes a transposed view (train_mscmrseg.py:232), so strides are explicit.
+ * out: pool ? [B, C_L] : [B, C_L, N] contiguous.
+ * pool_arg: [B, C_L] int32, index n of the selected point (first on ties); required iff pool.
+ * precision: PCUDA_MLP_FP32 (CUDA-core reference path) or PCUDA_MLP_BF16 (tcgen05 tensor-core
+ *    path for layers with cin >= 64: bf16 operands, fp32 accumulate).
+ * ws: pcuda_pointmlp_ws_bytes(...) bytes, any contents.
+ */
+size_t pcuda_pointmlp_ws_bytes(int B, int N, int L, const pcuda_mlp_layer_t* layers /*host*/,
+                               int pool, int backward);
+int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N,
+                       int L, const pcuda_mlp_layer_t* layers /*host*/, int pool, int train,
+                       float momentum, float eps, int precision, float* out, int32_t* pool_arg,
+                       void* ws, pcuda_stream_t stream);
+
+/* grad_out: pool ? [B, C_L] : [B, C_L, N].  grad_x: [B, C0, N] contiguous or NULL.
+ * Uses layers[l].y / save_mean / save_invstd written by the matching forward call. */
+int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N,
+                       int L, const pcuda_mlp_layer_t* layers /*host*/, int pool, int train,
+                       float eps, int precision, const float* out, const int32_t* pool_arg,
+                       const float* grad_out, float* grad_x, void* ws, pcuda_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCUDA_H_ */

@@ -1,0 +1,468 @@
+// Chamfer / nearest-neighbour loss: tiled all-pairs search (forward) and index scatter (backward).
+//
+// Replaces utils/loss.py:40-76 (batch_NN_loss + batch_pairwise_dist) of the reference, which
+// materialises >= 8 [B,N,N] fp32 temporaries through six K=3 bmm calls.  Here nothing of size
+// N x N ever exists: each thread owns R query points in registers, candidate points stream
+// through shared memory as packed (x, y, z, |p|^2) float4 broadcast reads, and only
+// (distance, index) per point reaches HBM.
+//
+// Bit-exactness contract: the arg-min the reference returns is
+//     argmin_j sqrtf( fl( fl(rx_i + ry_j) - 2*zz_ij ) + 1e-5f ),   first index on ties,
+// with every dot product the K=3 chain fmaf(a2,b2, fmaf(a1,b1, a0*b0)).  The kernel evaluates
+// exactly that expression with explicit round-to-nearest intrinsics (no contraction, no
+// reassociation).  sqrt is applied lazily: f(P) = sqrtf(P + 1e-5f) is monotone non-decreasing
+// in P, so the running minimum is tracked on P and f is evaluated only when a strictly smaller P
+// arrives — then the index moves only if f also strictly decreased (distinct P can round to the
+// same distance, and the reference then keeps the EARLIER index).
+//
+// Roofline: FP32 issue rate, not HBM — algorithmic HBM bytes are 12*B*(N+M) in and
+// 12*B*(N+M) out, the work is 2*B*N*M ordered pair evaluations at 5 FP32 ops + compare each.
+#include "pcuda_common.cuh"
+
+namespace pcuda {
+namespace {
+
+constexpr int kTileJ = 1024;           // candidate points per shared-memory tile (16 KB)
+constexpr float kEps = 0.00001f;       // loss.py:68,71
+constexpr double kFixScale = 1099511627776.0;  // 2^40, backward fixed-point accumulators
+
+struct FwdWs {
+  unsigned int ticket;
+  unsigned int pad;
+  double partial[1];  // [2][B][tiles]
+};
+
+__device__ __forceinline__ float norm3(float a0, float a1, float a2) {
+  return __fmaf_rn(a2, a2, __fmaf_rn(a1, a1, __fmul_rn(a0, a0)));
+}
+
+// One launch covers both directions: blockIdx.z == 0 searches y for every x_i (d1,i1),
+// blockIdx.z == 1 searches x for every y_j (d2,i2).
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+chamfer_nn_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M,
+                  float* __restrict__ d1, int64_t* __restrict__ i1, float* __restrict__ d2,
+                  int64_t* __restrict__ i2, FwdWs* __restrict__ ws, float* __restrict__ loss,
+                  int tiles_x, int tiles_y, int B) {
+  __shared__ float4 tile[kTileJ];
+  __shared__ double warp_part[THREADS / 32];
+
+  const int dir = blockIdx.z;
+  const int b = blockIdx.y;
+  const int nq = dir == 0 ? N : M;  // queries (rows)
+  const int nc = dir == 0 ? M : N;  // candidates (columns)
+  const int tiles_q = dir == 0 ? tiles_x : tiles_y;
+  const bool active_block = static_cast<int>(blockIdx.x) < tiles_q;
+
+  const float* __restrict__ qbase = (dir == 0 ? x : y) + static_cast<int64_t>(b) * nq * 3;
+  const float* __restrict__ cbase = (dir == 0 ? y : x) + static_cast<int64_t>(b) * nc * 3;
+  float* __restrict__ dout = (dir == 0 ? d1 : d2) + static_cast<int64_t>(b) * nq;
+  int64_t* __restrict__ iout = (dir == 0 ? i1 : i2) + static_cast<int64_t>(b) * nq;
+
+  double my_sum = 0.0;
+  if (active_block) {
+    float q0[R], q1[R], q2[R], rq[R], bestP[R], bestD[R];
+    int bestI[R];
+    const int row0 = blockIdx.x * (THREADS * R) + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r * THREADS;
+      const int rr = row < nq ? row : nq - 1;  // clamp: out-of-range rows compute but never store
+      q0[r] = __ldg(qbase + rr * 3 + 0);
+      q1[r] = __ldg(qbase + rr * 3 + 1);
+      q2[r] = __ldg(qbase + rr * 3 + 2);
+      rq[r] = norm3(q0[r], q1[r], q2[r]);
+      bestP[r] = INFINITY;
+      bestD[r] = INFINITY;
+      bestI[r] = 0;
+    }
+
+    for (int j0 = 0; j0 < nc; j0 += kTileJ) {
+      const int tj = min(kTileJ, nc - j0);
+      __syncthreads();
+      for (int t = threadIdx.x; t < tj; t += THREADS) {
+        const float c0 = __ldg(cbase + (j0 + t) * 3 + 0);
+        const float c1 = __ldg(cbase + (j0 + t) * 3 + 1);
+        const float c2 = __ldg(cbase + (j0 + t) * 3 + 2);
+        tile[t] = make_float4(c0, c1, c2, norm3(c0, c1, c2));
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int t = 0; t < tj; ++t) {
+        const float4 c = tile[t];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float zz = __fmaf_rn(q2[r], c.z, __fmaf_rn(q1[r], c.y, __fmul_rn(q0[r], c.x)));
+          // direction 0: rx_i + ry_j ; direction 1: ry_j + rx_i — fp32 addition commutes.
+          const float P = __fmaf_rn(-2.0f, zz, __fadd_rn(rq[r], c.w));
+          if (P < bestP[r]) {
+            bestP[r] = P;
+            const float d = __fsqrt_rn(__fadd_rn(P, kEps));
+            if (d < bestD[r]) {
+              bestD[r] = d;
+              bestI[r] = j0 + t;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r * THREADS;
+      if (row < nq) {
+        dout[row] = bestD[r];
+        iout[row] = bestI[r];
+        my_sum += static_cast<double>(bestD[r]);
+      }
+    }
+  }
+
+  if (loss == nullptr) return;
+  // ---- deterministic loss reduction: per-block partial -> fixed-order final sum by last block
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double w = warp_sum(my_sum);
+  if (lane == 0) warp_part[wid] = w;
+  __syncthreads();
+  __shared__ bool is_last;
+  const int tiles_max = gridDim.x;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) s += warp_part[i];
+    ws->partial[(static_cast<int64_t>(dir) * B + b) * tiles_max + blockIdx.x] = s;
+    __threadfence();
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    is_last = atomicAdd(&ws->ticket, 1u) == total - 1;
+  }
+  __syncthreads();
+  if (is_last && wid == 0) {
+    __threadfence();
+    // loss = sum_b (sum_i d1)/N /B + sum_b (sum_j d2)/N /B      (loss.py:73-75)
+    double acc = 0.0;
+    const int64_t n_part = static_cast<int64_t>(2) * B * tiles_max;
+    const volatile double* part = ws->partial;
+    for (int64_t k = lane; k < n_part; k += 32) acc += part[k];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      *loss = static_cast<float>(acc / (static_cast<double>(N) * static_cast<double>(B)));
+      ws->ticket = 0u;
+      __threadfence();
+    }
+  }
+}
+
+
+// ---- v2: packed FP32 (FFMA2 / FADD2 / FMUL2, new on sm_100) -----------------------------------
+// Two candidate columns ride in the two halves of every 64-bit register operand, so the five
+// IEEE-rounded FP32 operations of a pair evaluation cost 2.5 issue slots instead of 5; the
+// per-component rounding is identical to the scalar instructions, so indices stay bit-exact.
+// The (rare) "new minimum" handling is hoisted behind ONE warp-level branch per column pair.
+// Shared-memory tile layout: A[jp] = (x_j, x_j+1, y_j, y_j+1), B[jp] = (z_j, z_j+1, r_j, r_j+1).
+__device__ __forceinline__ void nn_update(float P, int j, float& bestP, float& bestD, int& bestI) {
+  if (P < bestP) {
+    bestP = P;
+    const float d = __fsqrt_rn(__fadd_rn(P, kEps));
+    if (d < bestD) {
+      bestD = d;
+      bestI = j;
+    }
+  }
+}
+
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+chamfer_nn2_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M,
+                   float* __restrict__ d1, int64_t* __restrict__ i1, float* __restrict__ d2,
+                   int64_t* __restrict__ i2, FwdWs* __restrict__ ws, float* __restrict__ loss,
+                   int tiles_x, int tiles_y, int B) {
+  __shared__ float4 tileA[kTileJ / 2];
+  __shared__ float4 tileB[kTileJ / 2];
+  __shared__ double warp_part[THREADS / 32];
+
+  const int dir = blockIdx.z;
+  const int b = blockIdx.y;
+  const int nq = dir == 0 ? N : M;
+  const int nc = dir == 0 ? M : N;
+  const int tiles_q = dir == 0 ? tiles_x : tiles_y;
+  const bool active_block = static_cast<int>(blockIdx.x) < tiles_q;
+
+  const float* __restrict__ qbase = (dir == 0 ? x : y) + static_cast<int64_t>(b) * nq * 3;
+  const float* __restrict__ cbase = (dir == 0 ? y : x) + static_cast<int64_t>(b) * nc * 3;
+  float* __restrict__ dout = (dir == 0 ? d1 : d2) + static_cast<int64_t>(b) * nq;
+  int64_t* __restrict__ iout = (dir == 0 ? i1 : i2) + static_cast<int64_t>(b) * nq;
+
+  double my_sum = 0.0;
+  if (active_block) {
+    float2 q0[R], q1[R], q2[R], rq[R];
+    float bestP[R], bestD[R];
+    int bestI[R];
+    const int row0 = blockIdx.x * (THREADS * R) + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r * THREADS;
+      const int rr = row < nq ? row : nq - 1;
+      const float a0 = __ldg(qbase + rr * 3 + 0);
+      const float a1 = __ldg(qbase + rr * 3 + 1);
+      const float a2 = __ldg(qbase + rr * 3 + 2);
+      const float n = norm3(a0, a1, a2);
+      q0[r] = make_float2(a0, a0);
+      q1[r] = make_float2(a1, a1);
+      q2[r] = make_float2(a2, a2);
+      rq[r] = make_float2(n, n);
+      bestP[r] = INFINITY;
+      bestD[r] = INFINITY;
+      bestI[r] = 0;
+    }
+    const float2 neg2 = make_float2(-2.0f, -2.0f);
+
+    for (int j0 = 0; j0 < nc; j0 += kTileJ) {
+      const int tj = min(kTileJ, nc - j0);
+      const int npair = (tj + 1) >> 1;
+      __syncthreads();
+      for (int t = threadIdx.x; t < npair; t += THREADS) {
+        const int ja = j0 + 2 * t;
+        const bool has_b = (2 * t + 1) < tj;
+        const float xa = __ldg(cbase + ja * 3 + 0), ya = __ldg(cbase + ja * 3 + 1), za = __ldg(cbase + ja * 3 + 2);
+        // odd tail: a sentinel column whose P is +inf can never be selected
+        const float xb = has_b ? __ldg(cbase + ja * 3 + 3) : 0.0f;
+        const float yb = has_b ? __ldg(cbase + ja * 3 + 4) : 0.0f;
+        const float zb = has_b ? __ldg(cbase + ja * 3 + 5) : 0.0f;
+        const float ra = norm3(xa, ya, za);
+        const float rb = has_b ? norm3(xb, yb, zb) : INFINITY;
+        tileA[t] = make_float4(xa, xb, ya, yb);
+        tileB[t] = make_float4(za, zb, ra, rb);
+      }
+      __syncthreads();
+#pragma unroll 2
+      for (int t = 0; t < npair; ++t) {
+        const float4 A = tileA[t];
+        const float4 Bv = tileB[t];
+        const float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w);
+        const float2 cz = make_float2(Bv.x, Bv.y), cr = make_float2(Bv.z, Bv.w);
+        float2 P[R];
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float2 zz = __ffma2_rn(q2[r], cz, __ffma2_rn(q1[r], cy, __fmul2_rn(q0[r], cx)));
+          P[r] = __ffma2_rn(neg2, zz, __fadd2_rn(rq[r], cr));
+          any = any || (P[r].x < bestP[r]) || (P[r].y < bestP[r]);
+        }
+        if (any) {
+          const int j = j0 + 2 * t;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            nn_update(P[r].x, j, bestP[r], bestD[r], bestI[r]);
+            nn_update(P[r].y, j + 1, bestP[r], bestD[r], bestI[r]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r * THREADS;
+      if (row < nq) {
+        dout[row] = bestD[r];
+        iout[row] = bestI[r];
+        my_sum += static_cast<double>(bestD[r]);
+      }
+    }
+  }
+
+  if (loss == nullptr) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double w = warp_sum(my_sum);
+  if (lane == 0) warp_part[wid] = w;
+  __syncthreads();
+  __shared__ bool is_last;
+  const int tiles_max = gridDim.x;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) s += warp_part[i];
+    ws->partial[(static_cast<int64_t>(dir) * B + b) * tiles_max + blockIdx.x] = s;
+    __threadfence();
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    is_last = atomicAdd(&ws->ticket, 1u) == total - 1;
+  }
+  __syncthreads();
+  if (is_last && wid == 0) {
+    __threadfence();
+    double acc = 0.0;
+    const int64_t n_part = static_cast<int64_t>(2) * B * tiles_max;
+    const volatile double* part = ws->partial;
+    for (int64_t k = lane; k < n_part; k += 32) acc += part[k];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      *loss = static_cast<float>(acc / (static_cast<double>(N) * static_cast<double>(B)));
+      ws->ticket = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// ---- backward ---------------------------------------------------------------------------------
+// Pass 1 (scatter): many-to-one terms, accumulated as 64-bit fixed point so the sum is exact
+// and order-independent.  Pass 2 (finalise): one-to-one term + conversion + scale.
+__global__ void chamfer_bwd_scatter(const float* __restrict__ q, const float* __restrict__ c,
+                                    const float* __restrict__ dq, const int64_t* __restrict__ iq,
+                                    int nq, int nc, int B, long long* __restrict__ acc_c) {
+  // for every query point (b,i) with nearest candidate j: acc_c[b,j] += (c_j - q_i)/d_i
+  const int64_t total = static_cast<int64_t>(B) * nq;
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = g / nq;
+    const int64_t j = iq[g];
+    const float d = dq[g];
+    const float* qp = q + g * 3;
+    const float* cp = c + (b * nc + j) * 3;
+    long long* a = acc_c + (b * nc + j) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float u = __fdiv_rn(__fsub_rn(cp[k], qp[k]), d);
+      atomicAdd(reinterpret_cast<unsigned long long*>(a + k),
+                static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(u) * kFixScale)));
+    }
+  }
+}
+
+__global__ void chamfer_bwd_finalize(const float* __restrict__ q, const float* __restrict__ c,
+                                     const float* __restrict__ dq, const int64_t* __restrict__ iq,
+                                     const long long* __restrict__ acc_q,
+                                     const float* __restrict__ grad_loss, int nq, int nc, int B,
+                                     double inv_nb, float* __restrict__ grad_q) {
+  const int64_t total = static_cast<int64_t>(B) * nq;
+  const double scale = static_cast<double>(__ldg(grad_loss)) * inv_nb;
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t b = g / nq;
+    const int64_t j = iq[g];
+    const float d = dq[g];
+    const float* qp = q + g * 3;
+    const float* cp = c + (b * nc + j) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float u = __fdiv_rn(__fsub_rn(qp[k], cp[k]), d);
+      const double many = static_cast<double>(acc_q[g * 3 + k]) * (1.0 / kFixScale);
+      grad_q[g * 3 + k] = static_cast<float>(scale * (static_cast<double>(u) + many));
+    }
+  }
+}
+
+struct Plan {
+  int R, threads, tiles_x, tiles_y;
+};
+
+Plan make_plan(int B, int N, int M) {
+  // Fill the machine: prefer 4 rows/thread (amortises each shared-memory broadcast over 4 pair
+  // evaluations) but fall back to fewer rows / smaller blocks while the grid would be < 2 waves.
+  const int64_t target = static_cast<int64_t>(sm_count()) * 8;
+  const int forced = tuning(TUNE_CHAMFER_ROWS);
+  const int cand[5][2] = {{8, 128}, {4, 128}, {2, 128}, {1, 128}, {1, 64}};
+  Plan p{1, 64, 0, 0};
+  for (int k = (forced > 0 ? 0 : 1); k < 5; ++k) {
+    const int R = cand[k][0], T = cand[k][1];
+    const int tx = (N + R * T - 1) / (R * T), ty = (M + R * T - 1) / (R * T);
+    p = Plan{R, T, tx, ty};
+    if (forced > 0) {
+      if (forced % 100000 == R * 1000 + T) break;
+      continue;
+    }
+    if (static_cast<int64_t>(B) * (tx + ty) >= target) break;
+  }
+  return p;
+}
+
+}  // namespace
+}  // namespace pcuda
+
+using namespace pcuda;
+
+extern "C" size_t pcuda_chamfer_ws_bytes(int B, int N, int M) {
+  if (B <= 0 || N <= 0 || M <= 0) return 16;
+  // worst case one partial per 64 rows per direction
+  const int64_t tiles = (static_cast<int64_t>(N > M ? N : M) + 63) / 64;
+  return 16 + sizeof(double) * 2 * static_cast<size_t>(B) * static_cast<size_t>(tiles);
+}
+
+extern "C" int pcuda_chamfer_fwd(const float* x, const float* y, int B, int N, int M, float* d1,
+                                 int64_t* i1, float* d2, int64_t* i2, float* loss, void* ws,
+                                 pcuda_stream_t stream) {
+  PCUDA_REQUIRE(B >= 0 && N >= 0 && M >= 0, PCUDA_E_SHAPE, "chamfer_fwd: bad shape B=%d N=%d M=%d", B, N, M);
+  PCUDA_REQUIRE(B <= 65535, PCUDA_E_UNSUPPORTED, "chamfer_fwd: B=%d > 65535", B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0 || N == 0 || M == 0) {
+    // torch: min over an empty dimension raises; an empty batch gives 0/0 = NaN.  Surface the
+    // degenerate case as an argument error instead of launching.
+    PCUDA_REQUIRE(B == 0 && N > 0 && M > 0, PCUDA_E_SHAPE, "chamfer_fwd: empty point cloud (N=%d, M=%d)", N, M);
+    if (loss) {
+      const float nanv = __builtin_nanf("");
+      cudaMemcpyAsync(loss, &nanv, sizeof(float), cudaMemcpyHostToDevice, st);
+    }
+    return 0;
+  }
+  PCUDA_REQUIRE(x && y && d1 && i1 && d2 && i2, PCUDA_E_NULL, "chamfer_fwd: NULL tensor");
+  PCUDA_REQUIRE(!loss || ws, PCUDA_E_NULL, "chamfer_fwd: loss needs ws");
+  const Plan p = make_plan(B, N, M);
+  const dim3 grid(p.tiles_x > p.tiles_y ? p.tiles_x : p.tiles_y, B, 2);
+  FwdWs* w = static_cast<FwdWs*>(ws);
+#define PCUDA_LAUNCH_NN(RR, TT)                                                              \
+  chamfer_nn_kernel<RR, TT><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,        \
+                                                 p.tiles_x, p.tiles_y, B)
+#define PCUDA_LAUNCH_NN2(RR, TT)                                                             \
+  chamfer_nn2_kernel<RR, TT><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,       \
+                                                  p.tiles_x, p.tiles_y, B)
+  // tuning value >= 100000 selects the scalar (v1) kernel for A/B runs
+  const bool scalar_variant = tuning(TUNE_CHAMFER_ROWS) >= 100000;
+  if (scalar_variant) {
+    if (p.R >= 4) PCUDA_LAUNCH_NN(4, 128);
+    else if (p.R == 2) PCUDA_LAUNCH_NN(2, 128);
+    else if (p.threads == 128) PCUDA_LAUNCH_NN(1, 128);
+    else PCUDA_LAUNCH_NN(1, 64);
+  } else {
+    if (p.R == 8) PCUDA_LAUNCH_NN2(8, 128);
+    else if (p.R == 4) PCUDA_LAUNCH_NN2(4, 128);
+    else if (p.R == 2) PCUDA_LAUNCH_NN2(2, 128);
+    else if (p.threads == 128) PCUDA_LAUNCH_NN2(1, 128);
+    else PCUDA_LAUNCH_NN2(1, 64);
+  }
+#undef PCUDA_LAUNCH_NN
+#undef PCUDA_LAUNCH_NN2
+  return check_launch("chamfer_nn_kernel");
+}
+
+extern "C" size_t pcuda_chamfer_bwd_ws_bytes(int B, int N, int M) {
+  if (B <= 0) return 0;
+  return sizeof(long long) * 3 * static_cast<size_t>(B) * (static_cast<size_t>(N > 0 ? N : 0) + static_cast<size_t>(M > 0 ? M : 0));
+}
+
+extern "C" int pcuda_chamfer_bwd(const float* x, const float* y, const float* d1,
+                                 const int64_t* i1, const float* d2, const int64_t* i2,
+                                 const float* grad_loss, int B, int N, int M, float* grad_x,
+                                 float* grad_y, void* ws, pcuda_stream_t stream) {
+  PCUDA_REQUIRE(B >= 0 && N >= 0 && M >= 0, PCUDA_E_SHAPE, "chamfer_bwd: bad shape B=%d N=%d M=%d", B, N, M);
+  if (B == 0 || N == 0 || M == 0) return 0;
+  if (!grad_x && !grad_y) return 0;
+  PCUDA_REQUIRE(x && y && d1 && i1 && d2 && i2 && grad_loss && ws, PCUDA_E_NULL, "chamfer_bwd: NULL tensor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long* acc_x = static_cast<long long*>(ws);
+  long long* acc_y = acc_x + static_cast<size_t>(B) * N * 3;
+  const double inv_nb = 1.0 / (static_cast<double>(N) * static_cast<double>(B));
+  const int threads = 256;
+  auto blocks = [&](int64_t n) {
+    int64_t g = (n + threads - 1) / threads;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+    return static_cast<int>(g < cap ? g : cap);
+  };
+  if (grad_x) {
+    cudaMemsetAsync(acc_x, 0, sizeof(long long) * 3 * static_cast<size_t>(B) * N, st);
+    // y_j -> nearest x_i contributes to grad_x[i2(j)]
+    chamfer_bwd_scatter<<<blocks(static_cast<int64_t>(B) * M), threads, 0, st>>>(y, x, d2, i2, M, N, B, acc_x);
+    chamfer_bwd_finalize<<<blocks(static_cast<int64_t>(B) * N), threads, 0, st>>>(x, y, d1, i1, acc_x, grad_loss, N, M, B, inv_nb, grad_x);
+  }
+  if (grad_y) {
+    cudaMemsetAsync(acc_y, 0, sizeof(long long) * 3 * static_cast<size_t>(B) * M, st);
+    chamfer_bwd_scatter<<<blocks(static_cast<int64_t>(B) * N), threads, 0, st>>>(x, y, d1, i1, N, M, B, acc_y);
+    chamfer_bwd_finalize<<<blocks(static_cast<int64_t>(B) * M), threads, 0, st>>>(y, x, d2, i2, acc_y, grad_loss, M, N, B, inv_nb, grad_y);
+  }
+  return check_launch("chamfer_bwd");
+}
