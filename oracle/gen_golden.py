@@ -150,9 +150,10 @@ def gen_entropy():
 POINTNET_CASES = {
     # name: (spec kwargs, B, N, seed)
     "default_b4_n64": (dict(), 4, 64, 31),
-    "default_b2_n300": (dict(), 2, 300, 32),
-    "ft_b3_n48": (dict(feature_transform=True), 3, 48, 33),
-    "ft_ext_b3_n40": (dict(feature_transform=True, ext=True), 3, 40, 34),
+    "default_b6_n300": (dict(), 6, 300, 32),
+    "ft_b5_n48": (dict(feature_transform=True), 5, 48, 33),
+    "ft_ext_b4_n40": (dict(feature_transform=True, ext=True), 4, 40, 34),
+    "default_b2_n50": (dict(), 2, 50, 36),   # smallest batch the reference can run (B==1 crashes)
     "nostn_b4_n32": (dict(sample_transform=False), 4, 32, 35),
 }
 
