@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py — adversarial-step throughput of the PointCloudUDA hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+One "step" = the hot-path work of one train_epoch iteration (pointcloududa_b200/step.py):
+entropy map fwd+bwd / fwd, Chamfer fwd+bwd / fwd, D4 (PointNetCls) 3x fwd + 3x bwd, BCE, D4 gradient
+all-reduce (N > 1) and SGD step — on synthetic slices / clouds of the reference's shapes.
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the definition of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "uda_adversarial_steps_per_s"
+UNIT = "steps/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: MS-CMRSeg step on 1xB200 (per-rank batch under weak scaling)
+    "cfg2": dict(B=8, C=4, H=224, W=224, N=300, activation="sigmoid", normalize=False, return_prob=False),
+    # configs[2] per-rank shard is B=4; the full single-GPU batch:
+    "cfg3": dict(B=32, C=5, H=256, W=256, N=1024, activation="softmax", normalize=True, return_prob=True),
+    # configs[4] per-rank shard (32 of 256 samples)
+    "cfg5_rank": dict(B=32, C=5, H=256, W=256, N=4096, activation="softmax", normalize=True, return_prob=True),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_host_inputs(w: dict, rank: int, pinned: bool):
+    import torch
+    from pointcloududa_b200.synth import synth_clouds, synth_logits
+    B, C, H, W, N = w["B"], w["C"], w["H"], w["W"], w["N"]
+    seed = 1234 + 97 * rank
+    xS, yA = synth_clouds(B, N, seed=seed + 1, mode="near")
+    xT, yB = synth_clouds(B, N, seed=seed + 2, mode="uniform")
+    host = {
+        "oS": synth_logits(B, C, H, W, seed=seed + 3), "oT": synth_logits(B, C, H, W, seed=seed + 4),
+        "grad_mapT": synth_logits(B, C, H, W, seed=seed + 5, std=1.0),
+        "vertS": xS, "vertT": xT, "vertexA": yA, "vertexB": yB,
+    }
+    if pinned:
+        host = {k: v.pin_memory() for k, v in host.items()}
+    return host
+
+
+def cpu_step(w: dict, host_np: dict, params, spec):
+    """The same step on the host cores with the oracle port (reference restatement)."""
+    import numpy as np
+    import oracle
+    act, norm = w["activation"], w["normalize"]
+    # P1
+    o = oracle.chamfer_fwd(host_np["vertS"], host_np["vertexA"])
+    oracle.chamfer_bwd64(host_np["vertS"], host_np["vertexA"], o["d1"], o["i1"], o["d2"], o["i2"])
+    # P2
+    oracle.entropy_fwd(host_np["oT"], act, norm, want_p=w["return_prob"], want_mean=True)
+    oracle.entropy_bwd64(host_np["oT"], host_np["grad_mapT"], None, 0.0, act, norm)
+    oracle.chamfer_fwd(host_np["vertT"], host_np["vertexB"])
+    losses = []
+    for pts in (host_np["vertT"], host_np["vertS"], host_np["vertT"]):
+        x = np.ascontiguousarray(pts.transpose(0, 2, 1))
+        logit, _, _, cache = oracle.pointnet_forward(params, x, spec)
+        dlogit = ((1.0 / (1.0 + np.exp(-logit))) - 1.0) / logit.shape[0]
+        oracle.pointnet_backward(dlogit.astype(np.float32), cache)
+        losses.append(float(logit.mean()))
+    # P3 entropy of the source logits (forward only)
+    oracle.entropy_fwd(host_np["oS"], act, norm, want_p=w["return_prob"])
+    return losses
+
+
+def run_cpu_baseline(w: dict, budget_s: float, min_steps: int = 2, max_steps: int = 50):
+    import numpy as np
+    import oracle
+    host = make_host_inputs(w, 0, pinned=False)
+    host_np = {k: v.numpy() for k, v in host.items()}
+    spec = oracle.PointNetSpec()
+    params = oracle.make_params(spec, 0)
+    cores = os.cpu_count() or 1
+    oracle.set_num_threads(cores)
+    cpu_step(w, host_np, params, spec)  # warm-up
+    ts = []
+    t_start = time.perf_counter()
+    while len(ts) < max_steps and (len(ts) < min_steps or time.perf_counter() - t_start < budget_s):
+        t0 = time.perf_counter()
+        cpu_step(w, host_np, params, spec)
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return {"value": 1.0 / med, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(ts)} full steps of the same workload (oracle port: C+OpenMP entropy/Chamfer, numpy/BLAS PointNet), median",
+            "ms_per_step": med * 1e3}
+
+
+# ------------------------------------------------------------------------------------------------
+def time_op(fn, iters: int, flush):
+    import torch
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.mean(ts)
+
+
+def op_breakdown(step, w: dict, flush, pk: dict):
+    """Per-op device time at this workload (cold L2) and the roofline of the dominant one."""
+    import torch
+    from pointcloududa_b200 import ops
+    from pointcloududa_b200.utils.loss import batch_NN_loss, entropy_map
+    I = step.inputs
+    B, C, H, W, N = w["B"], w["C"], w["H"], w["W"], w["N"]
+    elems = B * C * H * W
+    act, norm, rp = w["activation"], w["normalize"], w["return_prob"]
+    out = {}
+    t = time_op(lambda: entropy_map(I["oS"], act, norm, return_prob=rp), 10, flush)
+    out["entropy_fwd"] = dict(ms=t, bytes=(8 + (4 if rp else 0)) * elems)
+    zr = I["oT"].detach().requires_grad_(True)
+    mm = entropy_map(zr, act, norm)
+    t = time_op(lambda: torch.autograd.grad(mm, zr, I["grad_mapT"], retain_graph=True), 10, flush)
+    out["entropy_bwd"] = dict(ms=t, bytes=12 * elems)
+    t = time_op(lambda: ops.chamfer_nn(I["vertS"], I["vertexA"]), 10, flush)
+    out["chamfer_fwd"] = dict(ms=t, pairs=2 * B * N * N, bytes=2 * 24 * B * N)
+    xr = I["vertS"].detach().requires_grad_(True)
+    loss = batch_NN_loss(x=xr, y=I["vertexA"])
+    t = time_op(lambda: torch.autograd.grad(loss, xr, retain_graph=True), 10, flush)
+    out["chamfer_bwd"] = dict(ms=t, bytes=B * N * 2 * 36)
+    d4 = step.d4
+    pts = I["vertS"].transpose(2, 1)
+    with torch.no_grad():
+        t = time_op(lambda: d4.feat(pts), 10, flush)
+    mac_pp = 278912 if not (w.get("feature_transform") or w.get("ext")) else None
+    out["d4_feat_fwd"] = dict(ms=t, flops=2 * 278912 * B * N if mac_pp else None)
+    for k, v in out.items():
+        if v.get("bytes"):
+            v["gbs"] = v["bytes"] / v["ms"] / 1e6
+        if v.get("flops"):
+            v["tflops"] = v["flops"] / v["ms"] / 1e9
+        if v.get("pairs"):
+            v["gpairs_s"] = v["pairs"] / v["ms"] / 1e6
+    dom = max(out, key=lambda k: out[k]["ms"])
+    d = out[dom]
+    if dom.startswith("d4"):
+        roof = {"bound": "tensor", "achieved": d["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": d["tflops"] / pk["tensor"], "traffic": None}
+    else:
+        roof = {"bound": "hbm", "achieved": d["gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                "frac": d["gbs"] / pk["hbm"], "traffic": None}
+    roof["kernel"] = dom
+    roof["launch_ms"] = d["ms"]
+    roof["peak_source"] = pk["source"]
+    roof["note"] = ("op-level duration (CUDA events, cold L2) of the dominant hot-path op at this workload; "
+                    "cfg2-sized ops are launch-latency-bound, see `large` for the roofline-sized shapes")
+    return out, roof
+
+
+def large_shape_rooflines(flush, pk: dict):
+    """Roofline-sized shapes (cfg-5 per-rank shard / cfg-4) where % of peak is meaningful."""
+    import torch
+    from pointcloududa_b200 import ops
+    from pointcloududa_b200.synth import synth_clouds
+    from pointcloududa_b200.utils.loss import entropy_map
+    dev = flush.device
+    res = {}
+    z = torch.randn(32, 5, 256, 256, device=dev) * 3
+    g = torch.randn_like(z)
+    nb = z.numel() * 4
+    t = time_op(lambda: entropy_map(z, "softmax", True), 10, flush)
+    res["entropy_fwd_B32_C5_256x256"] = dict(ms=t, gbs=2 * nb / t / 1e6, frac_hbm=2 * nb / t / 1e6 / pk["hbm"])
+    zr = z.clone().requires_grad_(True)
+    mm = entropy_map(zr, "softmax", True)
+    t = time_op(lambda: torch.autograd.grad(mm, zr, g, retain_graph=True), 10, flush)
+    res["entropy_bwd_B32_C5_256x256"] = dict(ms=t, gbs=3 * nb / t / 1e6, frac_hbm=3 * nb / t / 1e6 / pk["hbm"])
+    del z, g, zr, mm
+    for B, N in ((64, 4096), (64, 16384)):
+        x, y = synth_clouds(B, N, seed=5, mode="near")
+        x, y = x.to(dev), y.to(dev)
+        t = time_op(lambda: ops.chamfer_nn(x, y), 5, flush)
+        res[f"chamfer_fwd_B{B}_N{N}"] = dict(ms=t, tpairs_s=2.0 * B * N * N / t / 1e9)
+    from pointcloududa_b200.networks.PointNetCls import PointNetCls
+    net = PointNetCls().to(dev).train()
+    pts = torch.rand(32, 4096, 3, device=dev).transpose(2, 1)
+    with torch.no_grad():
+        t = time_op(lambda: net.feat(pts), 5, flush)
+    fl = 2 * 278912 * 32 * 4096
+    res["d4_feat_fwd_B32_N4096"] = dict(ms=t, tflops=fl / t / 1e9, frac_tensor=fl / t / 1e9 / pk["tensor"])
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pointcloududa_b200 import dist as pdist
+    from pointcloududa_b200 import ops
+    from pointcloududa_b200.step import RESULT_FIELDS, AdversarialStep, StepConfig
+
+    rank, local, world = pdist.init_from_env("nccl")
+    if world != args.gpus:
+        if rank == 0:
+            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    w = dict(WORKLOADS[args.workload])
+    pk = peaks()
+    cfg = StepConfig(B=w["B"], C=w["C"], H=w["H"], W=w["W"], N=w["N"], activation=w["activation"],
+                     normalize=w["normalize"], return_prob=w["return_prob"], precision=args.precision)
+    step = AdversarialStep(cfg, dev, seed=0)
+    host = make_host_inputs(w, rank, pinned=True)
+    h2d_bytes = step.load_inputs(host, non_blocking=False)
+    result_host = torch.empty(len(RESULT_FIELDS), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+    # launches per step, counted on an eager step (a graph replays exactly these)
+    step.run(); torch.cuda.synchronize()
+    l0 = ops.launch_count(); step.run(); torch.cuda.synchronize()
+    launches_per_step = ops.launch_count() - l0
+
+    use_graph = world == 1 and not args.no_graph
+    if use_graph:
+        step.capture(warmup=2)
+    for _ in range(max(args.warmup, 3)):
+        step.run()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- device-resident timing: K steps, per-step CUDA events, L2 flushed between steps ---------
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in ev:
+        flush.fill_(1.0)
+        e0.record(); step.run(); e1.record()
+    barrier()
+    t_dev = sum(e0.elapsed_time(e1) for e0, e1 in ev) / 1e3
+
+    # ---- end-to-end: pinned host -> device inputs, step, device -> host result, per step --------
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in ev2:
+        flush.fill_(1.0)
+        e0.record()
+        step.load_inputs(host, non_blocking=True)
+        r = step.run()
+        result_host.copy_(r, non_blocking=True)
+        e1.record()
+    barrier()
+    t_e2e = sum(e0.elapsed_time(e1) for e0, e1 in ev2) / 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    last = {k: float(v) for k, v in zip(RESULT_FIELDS, result_host.tolist())}
+
+    tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = tt.tolist()
+
+    line = None
+    if rank == 0:
+        breakdown, roof = op_breakdown(step, w, flush, pk)
+        large = None
+        if not args.skip_large:
+            try:
+                large = large_shape_rooflines(flush, pk)
+            except Exception as e:  # never lose the headline line to an auxiliary measurement
+                large = {"error": repr(e)}
+        cpu = None
+        if world == 1 and not args.skip_cpu:
+            try:
+                cpu = run_cpu_baseline(w, budget_s=args.cpu_budget)
+            except Exception as e:
+                cpu = {"error": repr(e)}
+        line = {
+            "metric": METRIC, "value": world * args.steps / t_dev, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f32+bf16",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: MS-CMRSeg adversarial step, per-rank batch {w['B']}, "
+                                   f"{w['C']}x{w['H']}x{w['W']} logits, {w['N']}-pt clouds"
+                       if args.workload == "cfg2" else args.workload,
+                       "per_rank": w, "global_batch": w["B"] * world, "parallelism": f"dp{world} (batch-sharded, D4 grad all-reduce)",
+                       "l2": "flushed between steps (256 MiB write) outside the per-step CUDA-event intervals",
+                       "cuda_graph": bool(use_graph), "mlp_precision": args.precision},
+            "e2e": {"value": world * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": result_host.numel() * 4, "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "samples_per_s": world * w["B"] * args.steps / t_dev,
+            "roofline": roof, "ops": breakdown, "large": large, "cpu_baseline": cpu, "clocks": clocks,
+            "last_step": last,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def run_reference(args):
+    """Reference arm for this tier: the reference's CPU path (oracle port; the Python reference
+    cannot travel to the GPU box) on the host cores, same workload / metric / unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = dict(WORKLOADS[args.workload])
+    steps = max(1, min(args.steps, 10))
+    cpu = run_cpu_baseline(w, budget_s=60.0, min_steps=steps, max_steps=steps)
+    v = cpu["value"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "per_rank": w},
+        "cpu_baseline": {**cpu, "value": v},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-large", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,8 @@ int pcuda_sm_count(void);
 /* Benchmark-only knob for A/B-ing kernel variants (key, value); not part of the reference-facing
  * contract.  Keys: 0 = entropy fast-log (0/1), 1 = chamfer rows*1000+threads, 2 = force fp32 MLP. */
 int pcuda_tune(int key, int value);
+/* Number of kernels this library has launched in this process (monotone; for bench accounting). */
+uint64_t pcuda_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Entropy / self-information map.

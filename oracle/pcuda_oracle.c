@@ -52,9 +52,9 @@ void oracle_set_num_threads(int n) {
 void oracle_entropy_fwd(const float* z, float* m, float* p, float* mean_out, int B, int C,
                         int64_t HW, int activation, float norm, float smooth) {
   double total = 0.0;
-#pragma omp parallel for reduction(+ : total) schedule(static)
-  for (int64_t bp = 0; bp < (int64_t)B * HW; ++bp) {
-    const int64_t b = bp / HW, px = bp % HW;
+#pragma omp parallel for reduction(+ : total) schedule(static) collapse(2)
+  for (int64_t b = 0; b < (int64_t)B; ++b)
+  for (int64_t px = 0; px < HW; ++px) {
     const float* zp = z + b * C * HW + px;
     float mx = -INFINITY, sum = 0.0f;
     if (activation == 1) {
@@ -84,9 +84,9 @@ void oracle_entropy_bwd(const float* z, const float* grad_m, const float* grad_p
   const double k = norm != 0.0f ? 1.0 / (double)norm : 1.0;
   const double gs = (double)grad_mean / ((double)B * (double)HW);
   const double s = (double)smooth;
-#pragma omp parallel for schedule(static)
-  for (int64_t bp = 0; bp < (int64_t)B * HW; ++bp) {
-    const int64_t b = bp / HW, px = bp % HW;
+#pragma omp parallel for schedule(static) collapse(2)
+  for (int64_t b = 0; b < (int64_t)B; ++b)
+  for (int64_t px = 0; px < HW; ++px) {
     const int64_t base = b * C * HW + px;
     double pr[64], t[64];
     double mx = -INFINITY, sum = 0.0, dot = 0.0;
@@ -138,28 +138,38 @@ void oracle_pairwise_dist(const float* x, const float* y, int N, int M, float* P
   }
 }
 
-/* nearest neighbour of every q_i among c_j: torch.min(dim) returns the FIRST minimal index */
+/* nearest neighbour of every q_i among c_j: torch.min(dim) returns the FIRST minimal index.
+ * The distance row is evaluated into a buffer (vectorisable: fmaf and sqrtf are IEEE per lane),
+ * then scanned in ascending j with a strict '<'. */
 static void nn_search(const float* q, const float* c, int nq, int nc, float* d, int64_t* idx) {
-  float* rc = (float*)malloc(sizeof(float) * (size_t)nc);
-  for (int j = 0; j < nc; ++j) rc[j] = dot3(c + 3 * j, c + 3 * j);
+  float* c0 = (float*)malloc(sizeof(float) * (size_t)nc * 5);
+  float *c1 = c0 + nc, *c2 = c1 + nc, *rc = c2 + nc, *row = rc + nc;
+  for (int j = 0; j < nc; ++j) {
+    c0[j] = c[3 * j]; c1[j] = c[3 * j + 1]; c2[j] = c[3 * j + 2];
+    rc[j] = dot3(c + 3 * j, c + 3 * j);
+  }
   for (int i = 0; i < nq; ++i) {
+    const float q0 = q[3 * i], q1 = q[3 * i + 1], q2 = q[3 * i + 2];
     const float rq = dot3(q + 3 * i, q + 3 * i);
+#pragma omp simd
+    for (int j = 0; j < nc; ++j) {
+      const float zz = fmaf(q2, c2[j], fmaf(q1, c1[j], q0 * c0[j]));
+      const float t = rq + rc[j];
+      const float P = t - 2.0f * zz;
+      row[j] = sqrtf(P + 0.00001f);
+    }
     float best = INFINITY;
     int64_t bi = 0;
     for (int j = 0; j < nc; ++j) {
-      const float zz = dot3(q + 3 * i, c + 3 * j);
-      const float t = rq + rc[j];
-      const float P = t - 2.0f * zz;
-      const float dist = sqrtf(P + 0.00001f);
-      if (dist < best) {
-        best = dist;
+      if (row[j] < best) {
+        best = row[j];
         bi = j;
       }
     }
     d[i] = best;
     idx[i] = bi;
   }
-  free(rc);
+  free(c0);
 }
 
 /* x [B,N,3], y [B,M,3] -> d1,i1 [B,N]; d2,i2 [B,M]; loss scalar (loss.py:73-75) */

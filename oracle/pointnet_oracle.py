@@ -122,22 +122,32 @@ def _bn_bwd(dz, cache):
     return dy, dgamma, dbeta
 
 
-def _conv_bn(x, W, b, gamma, beta, relu, dt):
-    """x [B,Cin,N] -> relu?(bn(W x + b)) [B,Cout,N]   (Conv1d k=1 + BatchNorm1d, :41-43,:143-161)"""
+def _conv_bn(x2, W, b, gamma, beta, relu, dt):
+    """x2 [Cin, B*N] -> relu?(bn(W x + b)) [Cout, B*N]  (Conv1d k=1 + BatchNorm1d, :41-43,:143-161).
+    The k=1 convolution over [B,C,N] is one GEMM over the B*N columns."""
     W2 = W.reshape(W.shape[0], -1).astype(dt)
-    y = np.matmul(W2[None], x) + b.astype(dt)[None, :, None]
-    z, bnc = _bn_fwd(y, gamma.astype(dt), beta.astype(dt), (0, 2), dt)
+    y = W2 @ x2 + b.astype(dt)[:, None]
+    mean = y.mean(axis=1, keepdims=True, dtype=dt)
+    var = ((y - mean) ** 2).mean(axis=1, keepdims=True, dtype=dt)
+    invstd = 1.0 / np.sqrt(var + dt(BN_EPS))
+    yhat = (y - mean) * invstd
+    g = gamma.astype(dt)[:, None]
+    z = yhat * g + beta.astype(dt)[:, None]
     a = np.maximum(z, 0) if relu else z
-    return a, (x, W2, bnc, relu, z)
+    return a, (x2, W2, (yhat, invstd, g, (1,), mean.reshape(-1), var.reshape(-1)), relu, z)
 
 
 def _conv_bn_bwd(da, cache):
-    x, W2, bnc, relu, z = cache
+    x2, W2, bnc, relu, z = cache
+    yhat, invstd, g = bnc[0], bnc[1], bnc[2]
     dz = da * (z > 0) if relu else da
-    dy, dgamma, dbeta = _bn_bwd(dz, bnc)
-    dW = np.einsum("bon,bcn->oc", dy, x)
-    db = dy.sum(axis=(0, 2))
-    dx = np.matmul(W2.T[None], dy)
+    dgamma = (dz * yhat).sum(axis=1)
+    dbeta = dz.sum(axis=1)
+    dyhat = dz * g
+    dy = invstd * (dyhat - dyhat.mean(axis=1, keepdims=True) - yhat * (dyhat * yhat).mean(axis=1, keepdims=True))
+    dW = dy @ x2.T
+    db = dy.sum(axis=1)
+    dx = W2.T @ dy
     return dx, {"weight": dW, "bias": db, "gamma": dgamma, "beta": dbeta}
 
 
@@ -175,33 +185,38 @@ def stack_forward(x, layers, pool: bool, dtype=np.float32):
     Returns (out, cache); out is [B,C_L] when pool else [B,C_L,N].  cache['stats'] holds the
     per-layer batch mean / biased var (for running-stat checks)."""
     dt = dtype
-    a = x.astype(dt)
+    B, C0, N = x.shape
+    a = np.ascontiguousarray(x.astype(dt).transpose(1, 0, 2)).reshape(C0, B * N)
     caches, stats = [], []
     for L in layers:
         a, c = _conv_bn(a, L["weight"], L["bias"], L["gamma"], L["beta"], bool(L["relu"]), dt)
         caches.append(c)
         stats.append((c[2][4], c[2][5]))
+    a3 = a.reshape(a.shape[0], B, N).transpose(1, 0, 2)  # [B, C, N]
     arg = None
     if pool:
-        arg = a.argmax(axis=2)  # first maximal index, like torch.max(x, 2)
-        out = np.take_along_axis(a, arg[:, :, None], axis=2)[:, :, 0]
+        arg = a3.argmax(axis=2)  # first maximal index, like torch.max(x, 2)
+        out = np.take_along_axis(a3, arg[:, :, None], axis=2)[:, :, 0]
     else:
-        out = a
-    return out, {"caches": caches, "arg": arg, "shape": a.shape, "stats": stats, "pool": pool}
+        out = np.ascontiguousarray(a3)
+    return out, {"caches": caches, "arg": arg, "shape": a3.shape, "stats": stats, "pool": pool}
 
 
 def stack_backward(dout, cache):
     """Returns (dx [B,C0,N], [per-layer dict(weight,bias,gamma,beta)])."""
+    B, C, N = cache["shape"]
     if cache["pool"]:
-        da = np.zeros(cache["shape"], dout.dtype)
-        np.put_along_axis(da, cache["arg"][:, :, None], dout[:, :, None], axis=2)
+        da3 = np.zeros(cache["shape"], dout.dtype)
+        np.put_along_axis(da3, cache["arg"][:, :, None], dout[:, :, None], axis=2)
     else:
-        da = dout
+        da3 = dout
+    da = np.ascontiguousarray(da3.transpose(1, 0, 2)).reshape(C, B * N)
     grads = []
     for c in reversed(cache["caches"]):
         da, g = _conv_bn_bwd(da, c)
         grads.append(g)
-    return da, grads[::-1]
+    dx = np.ascontiguousarray(da.reshape(da.shape[0], B, N).transpose(1, 0, 2))
+    return dx, grads[::-1]
 
 
 def _stn_layers(params, prefix):

@@ -1,0 +1,88 @@
+"""ctypes binding of libpcuda.so (the C-ABI declared in include/pcuda.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, an exception
+is raised — nothing in this package computes the hot path any other way.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libpcuda.so"
+_lib = None
+
+
+class PcudaError(RuntimeError):
+    pass
+
+
+class MlpLayer(ctypes.Structure):
+    """pcuda_mlp_layer_t (include/pcuda.h)."""
+    _fields_ = [
+        ("cin", c_int32), ("cout", c_int32), ("relu", c_int32), ("reserved", c_int32),
+        ("weight", c_void_p), ("bias", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+        ("running_mean", c_void_p), ("running_var", c_void_p),
+        ("save_mean", c_void_p), ("save_invstd", c_void_p), ("y", c_void_p),
+        ("grad_weight", c_void_p), ("grad_bias", c_void_p), ("grad_gamma", c_void_p),
+        ("grad_beta", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/pcuda.h declares
+SIGNATURES = {
+    "pcuda_version": (c_int, []),
+    "pcuda_last_error_string": (c_char_p, []),
+    "pcuda_error_name": (c_char_p, [c_int]),
+    "pcuda_sm_count": (c_int, []),
+    "pcuda_tune": (c_int, [c_int, c_int]),
+    "pcuda_launch_count": (ctypes.c_uint64, []),
+    "pcuda_entropy_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                  c_int64, c_int, c_float, c_float, c_void_p]),
+    "pcuda_entropy_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                  c_int64, c_int, c_float, c_float, c_void_p]),
+    "pcuda_chamfer_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pcuda_chamfer_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcuda_chamfer_bwd_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pcuda_chamfer_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "pcuda_pointmlp_ws_bytes": (c_size_t, [c_int, c_int, c_int, POINTER(MlpLayer), c_int, c_int]),
+    "pcuda_pointmlp_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
+                                   POINTER(MlpLayer), c_int, c_int, c_float, c_float, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcuda_pointmlp_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
+                                   POINTER(MlpLayer), c_int, c_int, c_float, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise PcudaError(
+                f"{_LIB_PATH} not found: build it with `python -m pointcloududa_b200.build` "
+                "(nvcc, sm_100a). pointcloududa_b200 has no CPU or PyTorch fallback.")
+        L = ctypes.CDLL(str(_LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError here = stale library
+            fn.restype = res
+            fn.argtypes = args
+        if L.pcuda_version() // 100 != 1:
+            raise PcudaError(f"libpcuda version {L.pcuda_version()} does not match this package")
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        L = lib()
+        msg = L.pcuda_last_error_string().decode(errors="replace")
+        name = L.pcuda_error_name(rc).decode(errors="replace")
+        raise PcudaError(f"{what} failed: {name} ({rc}): {msg}")

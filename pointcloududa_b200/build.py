@@ -76,7 +76,7 @@ def build_oracle(force: bool = False) -> Path:
     src = ORACLE / "pcuda_oracle.c"
     out = ORACLE / "libpcuda_oracle.so"
     if force or _stale(out, [src]):
-        cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-fopenmp", "-mavx2", "-mfma",
+        cmd = ["gcc", "-O3", "-std=c11", "-fPIC", "-shared", "-fopenmp", "-mavx2", "-mfma",
                "-ffp-contract=off", "-fno-fast-math", "-o", str(out), str(src), "-lm"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -53,6 +53,9 @@ int sm_count() {
   return g_sm_count[dev];
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n)); }
+
 static std::atomic<int> g_tune[TUNE_NKEYS];
 int tuning(int key) { return (key >= 0 && key < TUNE_NKEYS) ? g_tune[key].load() : 0; }
 
@@ -77,6 +80,8 @@ const char* pcuda_error_name(int code) {
 }
 
 int pcuda_sm_count(void) { return pcuda::sm_count(); }
+
+uint64_t pcuda_launch_count(void) { return pcuda::g_launches.load(); }
 
 // Tuning knobs for benchmarking kernel variants; not part of the reference-facing contract.
 int pcuda_tune(int key, int value) {

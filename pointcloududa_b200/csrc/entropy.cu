@@ -320,7 +320,7 @@ int launch_fwd_vec4(const FwdArgs& a, int64_t n_quads, int64_t qpi) {
   const int grid = grid_for(k, n_quads);
   k<<<grid, kThreads, 0, a.st>>>(a.z, a.m, a.p, a.mean_out, a.ws, n_quads, qpi, a.HW, a.inv_norm,
                                  a.smooth, 1.0 / (static_cast<double>(a.B) * a.HW));
-  return check_launch("entropy_fwd_vec4");
+  count_launch(); return check_launch("entropy_fwd_vec4");
 }
 
 template <int ACT, int C, bool FAST>
@@ -358,7 +358,7 @@ int launch_bwd_vec4(const BwdArgs& a, int64_t n_quads, int64_t qpi) {
   const int grid = grid_for(k, n_quads);
   k<<<grid, kThreads, 0, a.st>>>(a.z, a.gm, a.gp, a.gmean, a.gz, n_quads, qpi, a.HW, a.inv_norm,
                                  a.smooth, static_cast<float>(1.0 / (static_cast<double>(a.B) * a.HW)));
-  return check_launch("entropy_bwd_vec4");
+  count_launch(); return check_launch("entropy_bwd_vec4");
 }
 
 template <int ACT, int C, bool FAST>
@@ -424,7 +424,7 @@ extern "C" int pcuda_entropy_fwd(const float* z, float* m, float* p, float* mean
         auto go = [&](auto k) {
           const int grid = grid_for(k, n / 4);
           k<<<grid, kThreads, 0, f.st>>>(z, m, p, mean_out, f.ws, n / 4, n / 4, n, inv_norm, smooth, invc);
-          return check_launch("entropy_fwd_vec4(sigmoid)");
+          count_launch(); return check_launch("entropy_fwd_vec4(sigmoid)");
         };
         if (wp && wm) return go(entropy_fwd_vec4<PCUDA_ACT_SIGMOID, 1, true, true, F>);
         if (wp) return go(entropy_fwd_vec4<PCUDA_ACT_SIGMOID, 1, true, false, F>);
@@ -443,7 +443,7 @@ extern "C" int pcuda_entropy_fwd(const float* z, float* m, float* p, float* mean
   auto go = [&](auto k) {
     const int grid = grid_for(k, n_pix);
     k<<<grid, kThreads, 0, a.st>>>(z, m, p, mean_out, a.ws, n_pix, C, HW, inv_norm, smooth, invc);
-    return check_launch("entropy_fwd_generic");
+    count_launch(); return check_launch("entropy_fwd_generic");
   };
   if (activation == PCUDA_ACT_SOFTMAX)
     return fast ? go(entropy_fwd_generic<PCUDA_ACT_SOFTMAX, true>) : go(entropy_fwd_generic<PCUDA_ACT_SOFTMAX, false>);
@@ -472,7 +472,7 @@ extern "C" int pcuda_entropy_bwd(const float* z, const float* grad_m, const floa
         auto go = [&](auto k) {
           const int grid = grid_for(k, n / 4);
           k<<<grid, kThreads, 0, a.st>>>(z, grad_m, grad_p, grad_mean, grad_z, n / 4, n / 4, n, inv_norm, smooth, invc);
-          return check_launch("entropy_bwd_vec4(sigmoid)");
+          count_launch(); return check_launch("entropy_bwd_vec4(sigmoid)");
         };
         const bool gm = grad_m != nullptr, gp = grad_p != nullptr;
         if (gm && gp) return go(entropy_bwd_vec4<PCUDA_ACT_SIGMOID, 1, true, true, F>);
@@ -490,7 +490,7 @@ extern "C" int pcuda_entropy_bwd(const float* z, const float* grad_m, const floa
   auto go = [&](auto k) {
     const int grid = grid_for(k, n_pix);
     k<<<grid, kThreads, 0, a.st>>>(z, grad_m, grad_p, grad_mean, grad_z, n_pix, C, HW, inv_norm, smooth, invc);
-    return check_launch("entropy_bwd_generic");
+    count_launch(); return check_launch("entropy_bwd_generic");
   };
   if (activation == PCUDA_ACT_SOFTMAX)
     return fast ? go(entropy_bwd_generic<PCUDA_ACT_SOFTMAX, true>) : go(entropy_bwd_generic<PCUDA_ACT_SOFTMAX, false>);

@@ -16,6 +16,7 @@ namespace pcuda {
 void set_error(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);  // returns cudaGetLastError() as a positive code (0 = ok)
+void count_launch(int n = 1);        // bench accounting: kernels launched by this library
 int sm_count();
 int tuning(int key);
 

@@ -1,0 +1,371 @@
+"""Drop-in for the reference's `src/networks/PointNetCls.py` (point-cloud discriminator D4).
+
+Same classes, constructor signatures, forward signatures and state_dict keys as the reference
+(STN3d :11-63, STNkd :66-102, PointNetfeat :104-168, PointNetCls :170-214), so
+`PointNetCls()` / `PointNetCls(feature_transform=args.ft, ext=args.extd4, cvinit=args.cvinit)`
+(train_mscmrseg.py:425, train_mmwhs.py:451), `.train()`, `requires_grad` toggling, SGD over
+`.parameters()` and `load_state_dict` of reference checkpoints all keep working.
+
+What changes is the execution: every "shared MLP" — a run of Conv1d(k=1)+BatchNorm1d(+ReLU)
+layers, optionally ending in the global max-pool — is one call into libpcuda
+(`pcuda_pointmlp_fwd/_bwd`, csrc/pointmlp*.cu).  The nn.Conv1d / nn.BatchNorm1d submodules remain
+as parameter and buffer containers only.  The tiny FC heads ([B,1024] -> ...) stay in PyTorch so
+Dropout draws from torch's Philox stream exactly like the reference.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+from .._lib import MlpLayer, PcudaError, check
+
+PRECISIONS = {"fp32": 0, "bf16": 1}
+DEFAULT_PRECISION = "bf16"
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class _SharedMLP(torch.autograd.Function):
+    """y = [max_n] relu?(bn(conv1x1(...relu(bn(conv1x1(x)))))) on libpcuda."""
+
+    @staticmethod
+    def forward(ctx, x, pool: bool, train: bool, precision: int, relus: Tuple[bool, ...],
+                momenta: Tuple[float, ...], eps: float, buffers: Tuple[torch.Tensor, ...], *params):
+        # params: (weight, bias, gamma, beta) per layer; buffers: (running_mean, running_var) per layer
+        if not x.is_cuda:
+            raise PcudaError("PointNetCls runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if x.dtype != torch.float32 or x.dim() != 3:
+            raise PcudaError(f"expected a float32 [B, C, N] tensor, got {x.dtype} {tuple(x.shape)}")
+        L = len(relus)
+        B, C0, N = x.shape
+        dev = x.device
+        M = B * N
+        lay = (MlpLayer * L)()
+        keep = []  # tensors referenced by raw pointers
+        ys, means, invstds = [], [], []
+        for l in range(L):
+            w, b, g, be = params[4 * l: 4 * l + 4]
+            rm, rv = buffers[2 * l], buffers[2 * l + 1]
+            cout, cin = w.shape[0], w.shape[1]
+            w2 = w.detach().reshape(cout, cin).contiguous()
+            b2 = None if b is None else b.detach().contiguous()
+            g2, be2 = g.detach().contiguous(), be.detach().contiguous()
+            mean = torch.empty(cout, dtype=torch.float32, device=dev)
+            invstd = torch.empty(cout, dtype=torch.float32, device=dev)
+            last_pooled = pool and l == L - 1
+            y = None if last_pooled else torch.empty((M, cout), dtype=torch.float32, device=dev)
+            keep += [w2, b2, g2, be2]
+            ys.append(y); means.append(mean); invstds.append(invstd)
+            lay[l].cin, lay[l].cout, lay[l].relu = cin, cout, int(relus[l])
+            lay[l].weight, lay[l].bias, lay[l].gamma, lay[l].beta = _ptr(w2), _ptr(b2), _ptr(g2), _ptr(be2)
+            lay[l].running_mean, lay[l].running_var = _ptr(rm), _ptr(rv)
+            lay[l].save_mean, lay[l].save_invstd, lay[l].y = _ptr(mean), _ptr(invstd), _ptr(y)
+        if len(set(momenta)) != 1:
+            raise PcudaError("all BatchNorm layers of one shared MLP must use the same momentum")
+        c_last = lay[L - 1].cout
+        out = torch.empty((B, c_last) if pool else (B, c_last, N), dtype=torch.float32, device=dev)
+        arg = torch.empty((B, c_last), dtype=torch.int32, device=dev) if pool else None
+        Lb = _lib.lib()
+        with torch.cuda.device(dev):
+            ws = torch.empty(max(Lb.pcuda_pointmlp_ws_bytes(B, N, L, lay, int(pool), 0), 16), dtype=torch.uint8, device=dev)
+            check(Lb.pcuda_pointmlp_fwd(_ptr(x), x.stride(0), x.stride(1), x.stride(2), B, N, L, lay, int(pool),
+                                        int(train), float(momenta[0]), float(eps), precision, _ptr(out), _ptr(arg),
+                                        _ptr(ws), torch.cuda.current_stream().cuda_stream), "pcuda_pointmlp_fwd")
+        ctx.cfg = (pool, train, precision, relus, eps, B, N, L)
+        ctx.save_for_backward(x)
+        ctx.keep = keep
+        ctx.saved = (ys, means, invstds, out if pool else None, arg)
+        ctx.param_shapes = [None if p is None else p.shape for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        pool, train, precision, relus, eps, B, N, L = ctx.cfg
+        (x,) = ctx.saved_tensors
+        keep = ctx.keep
+        ys, means, invstds, out, arg = ctx.saved
+        dev = x.device
+        need_x = ctx.needs_input_grad[0]
+        needs_p = ctx.needs_input_grad[8:]
+        lay = (MlpLayer * L)()
+        grads: List[Optional[torch.Tensor]] = []
+        for l in range(L):
+            w2, b2, g2, be2 = keep[4 * l: 4 * l + 4]
+            cout, cin = w2.shape
+            lay[l].cin, lay[l].cout, lay[l].relu = cin, cout, int(relus[l])
+            lay[l].weight, lay[l].bias, lay[l].gamma, lay[l].beta = _ptr(w2), _ptr(b2), _ptr(g2), _ptr(be2)
+            lay[l].save_mean, lay[l].save_invstd, lay[l].y = _ptr(means[l]), _ptr(invstds[l]), _ptr(ys[l])
+            want = any(needs_p[4 * l: 4 * l + 4])
+            if want:
+                gw = torch.empty((cout, cin), dtype=torch.float32, device=dev)
+                gb = torch.empty(cout, dtype=torch.float32, device=dev) if b2 is not None else None
+                gg = torch.empty(cout, dtype=torch.float32, device=dev)
+                gbe = torch.empty(cout, dtype=torch.float32, device=dev)
+                lay[l].grad_weight, lay[l].grad_bias = _ptr(gw), _ptr(gb)
+                lay[l].grad_gamma, lay[l].grad_beta = _ptr(gg), _ptr(gbe)
+                grads += [gw.reshape(ctx.param_shapes[4 * l]), gb, gg, gbe]
+            else:
+                grads += [None, None, None, None]
+        gx = torch.empty((B, x.shape[1], N), dtype=torch.float32, device=dev) if need_x else None
+        go = grad_out.contiguous()
+        Lb = _lib.lib()
+        with torch.cuda.device(dev):
+            ws = torch.empty(max(Lb.pcuda_pointmlp_ws_bytes(B, N, L, lay, int(pool), 1), 16), dtype=torch.uint8, device=dev)
+            check(Lb.pcuda_pointmlp_bwd(_ptr(x), x.stride(0), x.stride(1), x.stride(2), B, N, L, lay, int(pool),
+                                        int(train), float(eps), precision, _ptr(out), _ptr(arg), _ptr(go), _ptr(gx),
+                                        _ptr(ws), torch.cuda.current_stream().cuda_stream), "pcuda_pointmlp_bwd")
+        for i, need in enumerate(needs_p):
+            if not need:
+                grads[i] = None
+        return (gx, None, None, None, None, None, None, None, *grads)
+
+
+def shared_mlp(x: torch.Tensor, convs: Sequence[nn.Conv1d], bns: Sequence[nn.BatchNorm1d],
+               relus: Sequence[bool], pool: bool, precision: str = DEFAULT_PRECISION) -> torch.Tensor:
+    """Run Conv1d(k=1)+BatchNorm1d(+ReLU) layers [+ max over points] as one fused op."""
+    params, buffers, momenta = [], [], []
+    eps = bns[0].eps
+    train = bns[0].training or not bns[0].track_running_stats
+    for conv, bn in zip(convs, bns):
+        if conv.kernel_size != (1,) or conv.stride != (1,) or conv.padding != (0,):
+            raise PcudaError("the fused shared MLP supports kernel_size=1, stride=1 only "
+                             "(the only configuration the reference ever instantiates)")
+        if bn.momentum is None:
+            raise PcudaError("BatchNorm1d(momentum=None) (cumulative average) is not supported")
+        if bn.eps != eps or (bn.training or not bn.track_running_stats) != train:
+            raise PcudaError("all BatchNorm layers of one shared MLP must share eps and mode")
+        params += [conv.weight, conv.bias, bn.weight, bn.bias]
+        buffers += [bn.running_mean, bn.running_var]
+        momenta.append(float(bn.momentum))
+    out = _SharedMLP.apply(x, bool(pool), bool(train), PRECISIONS[precision], tuple(bool(r) for r in relus),
+                           tuple(momenta), float(eps), tuple(buffers), *params)
+    if train:
+        for bn in bns:
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+    return out
+
+
+def _check_batch(batchsize: int) -> None:
+    if batchsize < 2:
+        # the reference switches to InstanceNorm1d for B == 1 (PointNetCls.py:49-55, :210-211), a
+        # branch that raises inside torch >= 2 ("running_mean should contain 1 elements not 512")
+        raise PcudaError("PointNetCls needs a batch of at least 2 clouds per call (the reference's "
+                         "B == 1 InstanceNorm branch is broken on torch >= 2; keep >= 2 per rank)")
+
+
+class STN3d(nn.Module):
+    """Spatial transformer network: computes the 3x3 input transform (reference :11-63)."""
+
+    def __init__(self, dim=3, precision=DEFAULT_PRECISION):
+        super(STN3d, self).__init__()
+        self.conv1 = torch.nn.Conv1d(dim, 64, 1)
+        self.conv2 = torch.nn.Conv1d(64, 128, 1)
+        self.conv3 = torch.nn.Conv1d(128, 1024, 1)
+        self.fc1 = nn.Linear(1024, 512)
+        self.fc2 = nn.Linear(512, 256)
+        self.fc3 = nn.Linear(256, 9)
+        self.relu = nn.ReLU()
+
+        self.bn1 = nn.BatchNorm1d(64)
+        self.bn2 = nn.BatchNorm1d(128)
+        self.bn3 = nn.BatchNorm1d(1024)
+        self.bn4 = nn.BatchNorm1d(512)
+        self.bn5 = nn.BatchNorm1d(256)
+        # unused (B == 1 branch), kept so state_dict keys match reference checkpoints
+        self.in1 = nn.InstanceNorm1d(64, track_running_stats=True)
+        self.in2 = nn.InstanceNorm1d(128, track_running_stats=True)
+        self.in3 = nn.InstanceNorm1d(1024, track_running_stats=True)
+        self.in4 = nn.InstanceNorm1d(512, track_running_stats=True)
+        self.in5 = nn.InstanceNorm1d(256, track_running_stats=True)
+        self._precision = precision
+
+    def forward(self, x):
+        batchsize = x.size()[0]
+        _check_batch(batchsize)
+        x = shared_mlp(x, [self.conv1, self.conv2, self.conv3], [self.bn1, self.bn2, self.bn3],
+                       [True, True, True], pool=True, precision=self._precision)     # :41-45
+        x = F.relu(self.bn4(self.fc1(x)))
+        x = F.relu(self.bn5(self.fc2(x)))
+        x = self.fc3(x)
+        iden = torch.eye(3, dtype=x.dtype, device=x.device).reshape(1, 9)
+        x = x + iden
+        return x.view(-1, 3, 3)
+
+
+class STNkd(nn.Module):
+    """Feature transformer (reference :66-102)."""
+
+    def __init__(self, k=64, precision=DEFAULT_PRECISION):
+        super(STNkd, self).__init__()
+        self.conv1 = torch.nn.Conv1d(k, 64, 1)
+        self.conv2 = torch.nn.Conv1d(64, 128, 1)
+        self.conv3 = torch.nn.Conv1d(128, 1024, 1)
+        self.fc1 = nn.Linear(1024, 512)
+        self.fc2 = nn.Linear(512, 256)
+        self.fc3 = nn.Linear(256, k * k)
+        self.relu = nn.ReLU()
+
+        self.bn1 = nn.BatchNorm1d(64)
+        self.bn2 = nn.BatchNorm1d(128)
+        self.bn3 = nn.BatchNorm1d(1024)
+        self.bn4 = nn.BatchNorm1d(512)
+        self.bn5 = nn.BatchNorm1d(256)
+
+        self.k = k
+        self._precision = precision
+
+    def forward(self, x):
+        x = shared_mlp(x, [self.conv1, self.conv2, self.conv3], [self.bn1, self.bn2, self.bn3],
+                       [True, True, True], pool=True, precision=self._precision)     # :82-86
+        x = F.relu(self.bn4(self.fc1(x)))
+        x = F.relu(self.bn5(self.fc2(x)))
+        x = self.fc3(x)
+        iden = torch.eye(self.k, dtype=x.dtype, device=x.device).reshape(1, self.k * self.k)
+        x = x + iden
+        return x.view(-1, self.k, self.k)
+
+
+class PointNetfeat(nn.Module):
+    """Trunk: input transform, shared MLP 3->64->128->1024 (+ext widening), global max-pool
+    (reference :104-168)."""
+
+    def __init__(self, global_feat=True, feature_transform=False, sample_transform=True, kernel_size=1,
+                 stride=1, in_channel=3, dim=3, ext=False, precision=DEFAULT_PRECISION):
+        super(PointNetfeat, self).__init__()
+        self.stn = STN3d(dim=dim, precision=precision)
+        self._ext = ext
+        if self._ext:
+            self.conv1 = torch.nn.Conv1d(in_channel, 8, kernel_size, stride, kernel_size // 2)
+            self.bn1 = nn.BatchNorm1d(8)
+            self.conv1_1 = torch.nn.Conv1d(8, 64, kernel_size, stride, kernel_size // 2)
+            self.bn1_1 = nn.BatchNorm1d(64)
+            self.conv2 = torch.nn.Conv1d(64, 128, kernel_size, stride, kernel_size // 2)
+            self.bn2 = nn.BatchNorm1d(128)
+            self.conv2_1 = torch.nn.Conv1d(128, 256, kernel_size, stride, kernel_size // 2)
+            self.bn2_1 = nn.BatchNorm1d(256)
+            self.conv3 = torch.nn.Conv1d(256, 512, kernel_size, stride, kernel_size // 2)
+            self.bn3 = nn.BatchNorm1d(512)
+            self.conv3_1 = torch.nn.Conv1d(512, 1024, kernel_size, stride, kernel_size // 2)
+            self.bn3_1 = nn.BatchNorm1d(1024)
+        else:
+            self.conv1 = torch.nn.Conv1d(in_channel, 64, kernel_size, stride, kernel_size // 2)
+            self.conv2 = torch.nn.Conv1d(64, 128, kernel_size, stride, kernel_size // 2)
+            self.conv3 = torch.nn.Conv1d(128, 1024, kernel_size, stride, kernel_size // 2)
+            self.bn1 = nn.BatchNorm1d(64)
+            self.bn2 = nn.BatchNorm1d(128)
+            self.bn3 = nn.BatchNorm1d(1024)
+        self.global_feat = global_feat
+        self.feature_transform = feature_transform
+        self._sample_transform = sample_transform
+        if self.feature_transform:
+            self.fstn = STNkd(k=64, precision=precision)
+        self._precision = precision
+
+    def _stacks(self):
+        if self._ext:
+            pre = ([self.conv1, self.conv1_1], [self.bn1, self.bn1_1], [True, True])
+            post = ([self.conv2, self.conv2_1, self.conv3, self.conv3_1],
+                    [self.bn2, self.bn2_1, self.bn3, self.bn3_1], [True, True, False, True])
+        else:
+            pre = ([self.conv1], [self.bn1], [True])
+            post = ([self.conv2, self.conv3], [self.bn2, self.bn3], [True, False])   # no ReLU after bn3 (:159)
+        return pre, post
+
+    def forward(self, x):
+        n_pts = x.size()[2]
+        _check_batch(x.size()[0])
+        trans = None
+        if self._sample_transform:
+            trans = self.stn(x)
+            x = x.transpose(2, 1)
+            x = torch.bmm(x, trans)                                                # :140-142
+            x = x.transpose(2, 1)
+        (pc, pb, pr), (qc, qb, qr) = self._stacks()
+        pointfeat = None
+        if self.feature_transform or not self.global_feat:
+            # the 64-wide point features are needed as a tensor: run the trunk as two stacks
+            x = shared_mlp(x, pc, pb, pr, pool=False, precision=self._precision)
+            if self.feature_transform:
+                trans_feat = self.fstn(x)
+                x = x.transpose(2, 1)
+                x = torch.bmm(x, trans_feat)                                       # :147-151
+                x = x.transpose(2, 1)
+            else:
+                trans_feat = None
+            pointfeat = x
+            x = shared_mlp(x, qc, qb, qr, pool=True, precision=self._precision)
+        else:
+            trans_feat = None
+            x = shared_mlp(x, pc + qc, pb + qb, pr + qr, pool=True, precision=self._precision)  # :143-162
+        x = x.view(-1, 1024)
+        if self.global_feat:
+            return x, trans, trans_feat
+        else:
+            x = x.view(-1, 1024, 1).repeat(1, 1, n_pts)
+            return torch.cat([x, pointfeat], 1), trans, trans_feat
+
+
+class PointNetCls(nn.Module):
+    """Point-cloud discriminator: PointNetfeat + FC 1024->512->256->1 (reference :170-214).
+
+    `precision` is the only addition to the reference signature: 'bf16' runs the wide 1x1-conv
+    layers on the tcgen05 tensor cores (bf16 operands, fp32 accumulation), 'fp32' keeps everything
+    on the FP32 CUDA-core kernels."""
+
+    def __init__(self, feature_transform=False, sample_transform=True, kernel_size=1, stride=1, in_channel=3,
+                 dim=3, ext=False, drop=0.3, heinit=False, cvinit=False, precision=DEFAULT_PRECISION):
+        super(PointNetCls, self).__init__()
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        if kernel_size != 1 or stride != 1:
+            raise PcudaError("PointNetCls: only kernel_size=1, stride=1 is supported (all the reference uses)")
+        self.feature_transform = feature_transform
+        self.feat = PointNetfeat(global_feat=True, feature_transform=feature_transform,
+                                 sample_transform=sample_transform, kernel_size=kernel_size, stride=stride,
+                                 in_channel=in_channel, dim=dim, ext=ext, precision=precision)
+        self.fc1 = nn.Linear(1024, 512)
+        self.fc2 = nn.Linear(512, 256)
+        self.fc3 = nn.Linear(256, 1)
+        self.dropout = nn.Dropout(p=drop)
+        self.bn1 = nn.BatchNorm1d(512)
+        self.bn2 = nn.BatchNorm1d(256)
+        self.in1 = nn.InstanceNorm1d(512, track_running_stats=True)
+        self.in2 = nn.InstanceNorm1d(256, track_running_stats=True)
+        self.relu = nn.ReLU()
+        if heinit or cvinit:
+            self._initialize_weights(heinit=heinit)
+
+    def _initialize_weights(self, heinit=False):
+        # The reference only re-initialises nn.Conv2d modules (:188-202) and this network has none,
+        # so heinit / cvinit leave torch's default init untouched — reproduced here on purpose.
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                std = float(np.sqrt(2 / float(np.prod(m.weight.size()[1:])))) if heinit else 0.02
+                m.weight.data.normal_(0.0, std)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+
+    def forward(self, x):
+        x, trans, trans_feat = self.feat(x)
+        batchsize = x.size()[0]
+        _check_batch(batchsize)
+        x = F.relu(self.bn1(self.fc1(x)))                                          # :208
+        x = F.relu(self.bn2(self.dropout(self.fc2(x))))                            # :209
+        x = self.fc3(x)
+        return x, trans, trans_feat
+
+
+def feature_transform_regularizer(trans):
+    """||T T^T - I|| regulariser (reference :217-224; unused by the train scripts)."""
+    d = trans.size()[1]
+    I = torch.eye(d, device=trans.device, dtype=trans.dtype)[None, :, :]
+    return torch.mean(torch.norm(torch.bmm(trans, trans.transpose(2, 1)) - I, dim=(1, 2)))

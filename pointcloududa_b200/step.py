@@ -1,0 +1,172 @@
+"""The hot-path work of ONE adversarial train step, with the backbone outputs given as inputs.
+
+Mirrors the non-backbone part of `train_epoch` (train_mscmrseg.py:183-330, train_mmwhs.py:187-360;
+SURVEY.md §3.1 / §8d "one adversarial step"):
+
+  P1  Chamfer(vertS, vertexA) forward + backward into the predicted source cloud        (:206,:213)
+  P2  entropy map of the target logits, forward + backward (upstream gradient = what D2 would
+      send back, supplied as an input because the D2/D1 conv stacks are out of scope)     (:222,:246)
+      Chamfer(vertT, vertexB) forward only (logged)                                       (:230-231)
+      D4(vertT^T) with FROZEN parameters -> BCE vs 1 -> backward into the cloud           (:232-233,:246)
+  P3  entropy map of the detached source logits (forward only)                            (:265)
+      D4(vertS.detach()^T) -> BCE vs 1 -> backward (parameter gradients)                  (:284-288)
+  P4  D4(vertT.detach()^T) -> BCE vs 0 -> backward (parameter gradients)                  (:314-319)
+  P5  [multi-GPU: all-reduce of D4's gradients]  SGD(momentum .99, wd 5e-4) step          (:329-330,:450-455)
+
+The U-Net, D1/D2 and host-side bookkeeping are excluded.  All scalar results are kept on the
+device and returned as one small tensor so a caller pays a single device->host read per step.
+The whole step is CUDA-graph capturable (`AdversarialStep.capture()`): no host synchronisation,
+no allocation outside torch's graph pool, every libpcuda launch on the capture stream.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import dist as pdist
+from .networks.PointNetCls import PointNetCls
+from .utils.loss import batch_NN_loss, entropy_map
+
+RESULT_FIELDS = ("chamfer_source", "chamfer_target", "entropy_mean_target", "adv_point_loss",
+                 "d4_loss_source", "d4_loss_target", "d4_acc_source", "d4_acc_target")
+
+
+@dataclass
+class StepConfig:
+    B: int
+    C: int
+    H: int
+    W: int
+    N: int
+    activation: str = "sigmoid"   # MS-CMRSeg: sigmoid, no /log C;  MM-WHS -softmax: softmax, /log C
+    normalize: bool = False
+    return_prob: bool = False     # MM-WHS: D1 consumes pred (train_mmwhs.py:267)
+    dr: float = 0.01              # args.dr weight of the adversarial terms
+    lr_dis: float = 2.5e-5
+    precision: str = "bf16"
+    feature_transform: bool = False
+    ext: bool = False
+
+
+class AdversarialStep:
+    """Owns D4, its optimiser, static input buffers and (optionally) a captured CUDA graph."""
+
+    def __init__(self, cfg: StepConfig, device: torch.device, seed: int = 0):
+        self.cfg = cfg
+        self.device = device
+        torch.manual_seed(seed)
+        self.d4 = PointNetCls(feature_transform=cfg.feature_transform, ext=cfg.ext,
+                              precision=cfg.precision).to(device).train()
+        # optim_dis4 of the reference: SGD, momentum .99, weight decay 5e-4 (train_mscmrseg.py:450-455)
+        self.opt = torch.optim.SGD(self.d4.parameters(), lr=cfg.lr_dis, momentum=0.99, weight_decay=0.0005)
+        self.bucket = pdist.GradBucket(self.d4.parameters())
+        B, C, H, W, N = cfg.B, cfg.C, cfg.H, cfg.W, cfg.N
+        f32 = dict(dtype=torch.float32, device=device)
+        self.inputs: Dict[str, torch.Tensor] = {
+            "oS": torch.zeros(B, C, H, W, **f32), "oT": torch.zeros(B, C, H, W, **f32),
+            "grad_mapT": torch.zeros(B, C, H, W, **f32),
+            "vertS": torch.zeros(B, N, 3, **f32), "vertT": torch.zeros(B, N, 3, **f32),
+            "vertexA": torch.zeros(B, N, 3, **f32), "vertexB": torch.zeros(B, N, 3, **f32),
+        }
+        self.result = torch.zeros(len(RESULT_FIELDS), **f32)
+        self.grad_oT = torch.zeros(B, C, H, W, **f32)
+        self.grad_vertS = torch.zeros(B, N, 3, **f32)
+        self.grad_vertT = torch.zeros(B, N, 3, **f32)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._ones = torch.ones(B, 1, **f32)
+        self._zeros = torch.zeros(B, 1, **f32)
+
+    # -- inputs -----------------------------------------------------------------------------------
+    def load_inputs(self, host: Dict[str, torch.Tensor], non_blocking: bool = True) -> int:
+        """Host (pinned) -> device copy of one step's inputs. Returns bytes copied."""
+        n = 0
+        for k, dst in self.inputs.items():
+            dst.copy_(host[k], non_blocking=non_blocking)
+            n += dst.numel() * dst.element_size()
+        return n
+
+    def _set_requires_grad(self, flag: bool) -> None:
+        for p in self.d4.parameters():
+            p.requires_grad = flag
+
+    # -- the step -----------------------------------------------------------------------------------
+    def _body(self) -> None:
+        cfg, I = self.cfg, self.inputs
+        res = []
+        # P0: zero D4's gradients (they live in the flat bucket), freeze D4
+        self.bucket.zero()
+        self._set_requires_grad(False)
+
+        # P1: source Chamfer, forward + backward into the predicted cloud
+        vertS = I["vertS"].detach().requires_grad_(True)
+        loss_seg3 = batch_NN_loss(x=vertS, y=I["vertexA"])
+        (gS,) = torch.autograd.grad(loss_seg3, vertS)
+        self.grad_vertS.copy_(gS)
+        res.append(loss_seg3.detach())
+
+        # P2: fool the discriminators
+        oT = I["oT"].detach().requires_grad_(True)
+        outs = entropy_map(oT, activation=cfg.activation, normalize=cfg.normalize,
+                           return_prob=cfg.return_prob, return_mean=True)
+        mapT, ent_mean = outs[0], outs[-1]
+        (gO,) = torch.autograd.grad(mapT, oT, I["grad_mapT"])
+        self.grad_oT.copy_(gO)
+        vertT = I["vertT"].detach().requires_grad_(True)
+        with torch.no_grad():
+            loss_vert_target = batch_NN_loss(x=vertT, y=I["vertexB"])
+        D_out4 = self.d4(vertT.transpose(2, 1))[0]
+        loss_adv_point = cfg.dr * F.binary_cross_entropy_with_logits(D_out4, self._ones)
+        (gT,) = torch.autograd.grad(loss_adv_point, vertT)
+        self.grad_vertT.copy_(gT)
+        res += [loss_vert_target.detach(), ent_mean.detach(), loss_adv_point.detach()]
+
+        # P3: discriminators on the source domain (label 1)
+        self._set_requires_grad(True)
+        self.bucket.attach()
+        with torch.no_grad():
+            entropy_map(I["oS"], activation=cfg.activation, normalize=cfg.normalize,
+                        return_prob=cfg.return_prob)
+        D_out4 = self.d4(I["vertS"].transpose(2, 1))[0]
+        loss_D_same4 = F.binary_cross_entropy_with_logits(D_out4, self._ones)
+        loss_D_same4.backward()
+        acc_s = (torch.sigmoid(D_out4.detach()) >= 0.5).float().mean()
+
+        # P4: discriminators on the target domain (label 0)
+        D_out4 = self.d4(I["vertT"].transpose(2, 1))[0]
+        loss_D_diff_4 = F.binary_cross_entropy_with_logits(D_out4, self._zeros)
+        loss_D_diff_4.backward()
+        acc_t = 1.0 - (torch.sigmoid(D_out4.detach()) >= 0.5).float().mean()
+        res += [loss_D_same4.detach(), loss_D_diff_4.detach(), acc_s, acc_t]
+
+        # P5: gradient all-reduce (one bucket) + SGD step
+        self.bucket.gather_grads()
+        self.bucket.allreduce_mean()
+        self.opt.step()
+        self.result.copy_(torch.stack([r.reshape(()).float() for r in res]))
+
+    def run(self) -> torch.Tensor:
+        """One step on the current stream (eager launches or graph replay). Returns the device-side
+        result vector (RESULT_FIELDS)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+        return self.result
+
+    def capture(self, warmup: int = 3) -> None:
+        """Capture the step into a CUDA graph (single-GPU; with NCCL in the step the eager path is
+        used so the collective stays on NCCL's own stream ordering)."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body()
+        self.graph = g

@@ -1,0 +1,444 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle, the committed
+golden vectors produced by the reference, and plain-torch restatements executed on the same GPU.
+
+Tolerances (north_star): Chamfer arg-min indices bit-exact; entropy maps / losses / gradients
+1e-5 relative in fp32 — applied as |a-b| <= 1e-5*|b| + 5e-7 element-wise for the map (SURVEY.md §7:
+the reference itself misses a pure relative 1e-5 on 3-12% of confident pixels) and max-norm
+relative elsewhere; 1e-2 for the bf16 tensor-core MLP.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from conftest import max_rel
+from oracle.gen_golden import POINTNET_CASES, sample_index
+from pointcloududa_b200 import ops
+from pointcloududa_b200.synth import synth_clouds, synth_logits
+from pointcloududa_b200.utils.loss import batch_NN_loss, entropy_map
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def test_native_library_is_the_path():
+    """The .so is loaded and kernels are actually launched (no silent fallback)."""
+    before = ops.launch_count()
+    z = torch.zeros(1, 4, 8, 8, device=DEV)
+    entropy_map(z)
+    torch.cuda.synchronize()
+    assert ops.launch_count() == before + 1
+
+
+# ================================================================ entropy ==========================
+ENT_CASES = ["sigmoid_c4", "softmax_c5_norm", "sigmoid_c5_norm", "softmax_c4_confident",
+             "softmax_zero", "sigmoid_zero", "sigmoid_saturated"]
+
+
+def _ent_close(m, ref):
+    return np.all(np.abs(m - ref) <= 1e-5 * np.abs(ref) + 5e-7)
+
+
+@pytest.mark.parametrize("fast", [0, 1])
+@pytest.mark.parametrize("case", ENT_CASES)
+def test_entropy_vs_reference_golden(golden_entropy, case, fast):
+    g = golden_entropy[case]
+    ops.tune(0, fast)
+    try:
+        z = torch.from_numpy(g["z"]).to(DEV).requires_grad_(True)
+        m, p, mean = entropy_map(z, activation=str(g["act"]), normalize=bool(g["norm"]),
+                                 return_prob=True, return_mean=True)
+        assert _ent_close(m.detach().cpu().numpy(), g["m"])
+        assert np.all(np.abs(p.detach().cpu().numpy() - g["p"]) <= 1e-5 * np.abs(g["p"]) + 1e-9)
+        assert abs(mean.item() - float(g["mean"])) <= 1e-5 * abs(float(g["mean"])) + 1e-7
+        gm = torch.from_numpy(g["grad_m"]).to(DEV)
+        gp = torch.from_numpy(g["grad_p"]).to(DEV)
+        total = (m * gm).sum() + (p * gp).sum() + float(g["grad_mean"]) * mean
+        total.backward()
+        gz = z.grad.cpu().numpy()
+        truth = oracle.entropy_bwd64(g["z"], g["grad_m"], g["grad_p"], float(g["grad_mean"]),
+                                     str(g["act"]), bool(g["norm"]))
+        scale = np.abs(truth).max()
+        err_new = np.abs(gz - truth).max()
+        err_ref = np.abs(g["grad_z"] - truth).max()
+        assert err_new <= 1e-5 * scale + 1e-8
+        assert err_new <= 4 * err_ref + 1e-6 * scale + 1e-8   # no worse than the reference's own fp32 noise
+    finally:
+        ops.tune(0, 0)
+
+
+@pytest.mark.parametrize("shape,act,norm", [
+    ((8, 4, 224, 224), "sigmoid", False),     # cfg-1/2
+    ((4, 5, 256, 256), "softmax", True),      # cfg-3 / cfg-5 slice shape
+    ((3, 5, 7, 9), "softmax", True),          # HW % 4 != 0 -> generic path
+    ((2, 9, 16, 16), "softmax", True),        # C > 8 -> generic path
+    ((2, 16, 5, 5), "sigmoid", True),
+    ((2, 2, 32, 32), "softmax", False),
+    ((5, 3, 1, 1), "softmax", True),          # ragged: a single pixel
+])
+def test_entropy_vs_oracle(shape, act, norm):
+    z = synth_logits(*shape, seed=100 + shape[1])
+    m_o, p_o, mean_o = oracle.entropy_fwd(z.numpy(), act, norm, want_p=True, want_mean=True)
+    zc = z.to(DEV).requires_grad_(True)
+    m, p, mean = entropy_map(zc, activation=act, normalize=norm, return_prob=True, return_mean=True)
+    assert _ent_close(m.detach().cpu().numpy(), m_o)
+    assert np.all(np.abs(p.detach().cpu().numpy() - p_o) <= 1e-5 * np.abs(p_o) + 1e-9)
+    assert abs(mean.item() - float(mean_o)) <= 1e-5 * abs(float(mean_o)) + 1e-7
+    g = torch.Generator().manual_seed(5)
+    gm = torch.randn(shape, generator=g)
+    (m * gm.to(DEV)).sum().backward()
+    truth = oracle.entropy_bwd64(z.numpy(), gm.numpy(), None, 0.0, act, norm)
+    assert np.abs(zc.grad.cpu().numpy() - truth).max() <= 1e-5 * np.abs(truth).max() + 1e-8
+
+
+def test_entropy_vs_torch_expression_on_gpu():
+    """The reference's inline expression, executed by torch on this GPU (train_mmwhs.py:213,224-225)."""
+    z = synth_logits(4, 5, 64, 64, seed=7).to(DEV)
+    zt = z.clone().requires_grad_(True)
+    pred = F.softmax(zt, dim=1)
+    umap = -1.0 * pred * torch.log(pred + 1e-7) / math.log(5)
+    temp = torch.mean(torch.sum(umap, dim=1))
+    zc = z.clone().requires_grad_(True)
+    m, p, mean = entropy_map(zc, "softmax", True, return_prob=True, return_mean=True)
+    assert torch.all((m - umap).abs() <= 1e-5 * umap.abs() + 5e-7)
+    assert abs(mean.item() - temp.item()) <= 1e-5 * abs(temp.item())
+    w = torch.randn_like(z)
+    ((umap * w).sum() + 0.3 * temp).backward()
+    ((m * w).sum() + 0.3 * mean).backward()
+    assert max_rel(zc.grad.cpu().numpy(), zt.grad.cpu().numpy()) < 2e-5
+
+
+def test_entropy_mean_workspace_is_reusable_and_deterministic():
+    z = synth_logits(2, 5, 64, 64, seed=8).to(DEV)
+    vals = [entropy_map(z, "softmax", True, return_mean=True)[1].item() for _ in range(5)]
+    assert len(set(vals)) == 1
+
+
+def test_entropy_empty_and_errors():
+    z = torch.zeros(0, 4, 8, 8, device=DEV)
+    assert entropy_map(z).shape == z.shape
+    with pytest.raises(ops.PcudaError):
+        entropy_map(torch.zeros(1, 17, 4, 4, device=DEV), "softmax")
+    with pytest.raises(ValueError):
+        entropy_map(torch.zeros(1, 4, 4, 4, device=DEV), "tanh")
+    with pytest.raises(ops.PcudaError):
+        entropy_map(torch.zeros(1, 4, 4, 4, device=DEV, dtype=torch.float16))
+
+
+# ================================================================ Chamfer ==========================
+CH_CASES = ["near_b3_n64", "near_b2_n300", "uniform_b2_n257", "identical_dups_b2_n128",
+            "zero_gt_b2_n96", "shifted_b2_n80"]
+# (tuning value) kernel variants: packed-FP32 R=1/64thr, 1, 2, 4, 8 rows; scalar R=4, R=1
+VARIANTS = [0, 1064, 1128, 2128, 4128, 8128, 104128, 101064]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("case", CH_CASES)
+def test_chamfer_golden_bit_exact(golden_chamfer, case, variant):
+    g = golden_chamfer[case]
+    ops.tune(1, variant)
+    try:
+        x = torch.from_numpy(g["x"]).to(DEV)
+        y = torch.from_numpy(g["y"]).to(DEV)
+        loss, d1, i1, d2, i2 = ops.chamfer_nn(x, y)
+        assert np.array_equal(i1.cpu().numpy(), g["i1"])
+        assert np.array_equal(i2.cpu().numpy(), g["i2"])
+        o = oracle.chamfer_fwd(g["x"], g["y"])
+        # distances bit-exact against the IEEE-sqrt oracle
+        assert np.array_equal(d1.cpu().numpy().view(np.int32), o["d1"].view(np.int32))
+        assert np.array_equal(d2.cpu().numpy().view(np.int32), o["d2"].view(np.int32))
+        assert abs(loss.item() - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    finally:
+        ops.tune(1, 0)
+
+
+def _torch_reference_nn(x, y):
+    """utils/loss.py:47-72 restated with torch ops, to run on the GPU (cuBLAS bmm with K=3)."""
+    def pairwise(a, b):
+        aa = torch.bmm(a, a.transpose(2, 1))
+        bb = torch.bmm(b, b.transpose(2, 1))
+        ab = torch.bmm(a, b.transpose(2, 1))
+        ra = aa.diagonal(dim1=1, dim2=2).unsqueeze(1).expand_as(aa)
+        rb = bb.diagonal(dim1=1, dim2=2).unsqueeze(1).expand_as(bb)
+        return ra.transpose(2, 1) + rb - 2 * ab
+    d1, i1 = torch.sqrt(pairwise(x, y) + 0.00001).min(dim=2)
+    d2, i2 = torch.sqrt(pairwise(y, x) + 0.00001).min(dim=2)
+    n = x.shape[1]
+    loss = (d1.sum(1) / n).sum() / x.shape[0] + (d2.sum(1) / n).sum() / x.shape[0]
+    return loss, d1, i1, d2, i2
+
+
+@pytest.mark.parametrize("B,N,mode", [(8, 300, "near"), (4, 1024, "near"), (4, 1024, "uniform"), (2, 2048, "near")])
+def test_chamfer_vs_reference_executed_on_this_gpu(B, N, mode):
+    """Ground truth #1 of SURVEY.md §8c: the reference expression run by torch/cuBLAS on this B200."""
+    x, y = synth_clouds(B, N, seed=40 + N, mode=mode)
+    x, y = x.to(DEV), y.to(DEV)
+    loss_r, d1r, i1r, d2r, i2r = _torch_reference_nn(x, y)
+    loss, d1, i1, d2, i2 = ops.chamfer_nn(x, y)
+    assert torch.equal(i1, i1r), f"{(i1 != i1r).sum().item()} i1 mismatches"
+    assert torch.equal(i2, i2r), f"{(i2 != i2r).sum().item()} i2 mismatches"
+    assert torch.equal(d1, d1r) and torch.equal(d2, d2r)
+    assert abs(loss.item() - loss_r.item()) <= 2e-6 * abs(loss_r.item())
+
+
+@pytest.mark.parametrize("B,N,mode", [(8, 300, "near"), (4, 1024, "uniform"), (2, 4096, "near"), (3, 1, "near"),
+                                      (2, 1025, "near"), (2, 2049, "uniform")])
+def test_chamfer_vs_oracle(B, N, mode):
+    x, y = synth_clouds(B, N, seed=60 + N, mode=mode)
+    o = oracle.chamfer_fwd(x.numpy(), y.numpy())
+    loss, d1, i1, d2, i2 = ops.chamfer_nn(x.to(DEV), y.to(DEV))
+    assert np.array_equal(i1.cpu().numpy(), o["i1"]) and np.array_equal(i2.cpu().numpy(), o["i2"])
+    assert np.array_equal(d1.cpu().numpy().view(np.int32), o["d1"].view(np.int32))
+    assert np.array_equal(d2.cpu().numpy().view(np.int32), o["d2"].view(np.int32))
+    assert abs(loss.item() - float(o["loss"])) <= 2e-6 * abs(float(o["loss"]))
+
+
+def test_chamfer_unequal_sizes_kernel_level():
+    """The kernel supports N != M (the reference-facing shim rejects it like the reference)."""
+    x, _ = synth_clouds(3, 200, seed=71, mode="uniform")
+    _, y = synth_clouds(3, 333, seed=72, mode="uniform")
+    o = oracle.chamfer_fwd(x.numpy(), y.numpy())
+    loss, d1, i1, d2, i2 = ops.chamfer_nn(x.to(DEV), y.to(DEV))
+    assert np.array_equal(i1.cpu().numpy(), o["i1"]) and np.array_equal(i2.cpu().numpy(), o["i2"])
+    with pytest.raises(RuntimeError):
+        batch_NN_loss(x=x.to(DEV), y=y.to(DEV))
+
+
+def test_chamfer_full_size_properties():
+    """cfg-4 top size (B=64, N=16384: 34.4 G ordered pairs) through size-independent properties and
+    an oracle check on a row subset."""
+    B, N = 64, 16384
+    x, y = synth_clouds(B, N, seed=81, mode="near")
+    xg, yg = x.to(DEV), y.to(DEV)
+    loss, d1, i1, d2, i2 = ops.chamfer_nn(xg, yg)
+    # (1) symmetry: swapping the arguments swaps the two directions bit for bit
+    loss_s, e1, j1, e2, j2 = ops.chamfer_nn(yg, xg)
+    assert torch.equal(d1, e2) and torch.equal(i1, j2) and torch.equal(d2, e1) and torch.equal(i2, j1)
+    # (2) the reported minimum is attained at the reported index (re-evaluate that one pair)
+    bsel = torch.arange(B, device=DEV)[:, None].expand(B, N)
+    ysel = yg[bsel, i1]
+    diff = (xg - ysel).double().pow(2).sum(-1).add(1e-5).sqrt()
+    assert torch.all((diff - d1.double()).abs() <= 2e-3)   # expansion-formula cancellation bound
+    # (3) identical clouds: every distance is sqrt(1e-5) and the match index is never later than i
+    loss_i, f1, k1, f2, k2 = ops.chamfer_nn(yg, yg)
+    assert torch.all(f1 == f1[0, 0]) and abs(f1[0, 0].item() - math.sqrt(1e-5)) < 1e-6
+    assert torch.all(k1 <= torch.arange(N, device=DEV)[None, :])
+    # (4) oracle on a row subset of 4 clouds: 48 query rows against all 16384 candidates
+    rows = torch.randperm(N, generator=torch.Generator().manual_seed(3))[:48]
+    for b in (0, 17, 32, 63):
+        o = oracle.chamfer_fwd(x[b:b + 1, rows].numpy(), y[b:b + 1].numpy())
+        assert np.array_equal(i1[b, rows.to(DEV)].cpu().numpy(), o["i1"][0])
+        assert np.array_equal(d1[b, rows.to(DEV)].cpu().numpy().view(np.int32), o["d1"][0].view(np.int32))
+    # (5) loss is the mean of the per-point distances
+    want = (d1.double().sum() + d2.double().sum()).item() / (N * B)
+    assert abs(loss.item() - want) <= 1e-6 * want
+
+
+@pytest.mark.parametrize("case", ["near_b3_n64", "near_b2_n300", "uniform_b2_n257", "identical_dups_b2_n128"])
+def test_chamfer_backward(golden_chamfer, case):
+    g = golden_chamfer[case]
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    y = torch.from_numpy(g["y"]).to(DEV).requires_grad_(True)
+    loss = batch_NN_loss(x=x, y=y)
+    (loss * 1.5).backward()
+    o = oracle.chamfer_fwd(g["x"], g["y"])
+    tx, ty = oracle.chamfer_bwd64(g["x"], g["y"], o["d1"], o["i1"], o["d2"], o["i2"], 1.5, want_y=True)
+    assert max_rel(x.grad.cpu().numpy(), tx) < 2e-6
+    assert max_rel(y.grad.cpu().numpy(), ty) < 2e-6
+    # closer to the exact derivative than the reference's autograd result is
+    err_new = np.abs(x.grad.cpu().numpy() / 1.5 - tx / 1.5).max()
+    err_ref = np.abs(g["grad_x"] - tx / 1.5).max()
+    assert err_new <= err_ref + 1e-9
+    assert max_rel(x.grad.cpu().numpy() / 1.5, g["grad_x"]) < 5e-3
+
+
+def test_chamfer_backward_deterministic_and_no_grad():
+    x, y = synth_clouds(4, 512, seed=91, mode="near")
+    grads = []
+    for _ in range(3):
+        xg = x.to(DEV).requires_grad_(True)
+        batch_NN_loss(x=xg, y=y.to(DEV)).backward()
+        grads.append(xg.grad.clone())
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[1], grads[2])
+    with torch.no_grad():                                  # validation path, train_mscmrseg.py:66-73
+        l = batch_NN_loss(x=x.to(DEV), y=y.to(DEV))
+    assert not l.requires_grad and l.dim() == 0
+
+
+# ================================================================ PointNet shared MLP ===============
+def _torch_stack(x, layers, pool, train, dtype):
+    """Plain-torch restatement of a Conv1d(k=1)+BatchNorm1d(+ReLU) stack (+max over points)."""
+    a = x.to(dtype)
+    for Ld in layers:
+        a = F.conv1d(a, Ld["weight"].to(dtype).reshape(Ld["weight"].shape[0], -1, 1), Ld["bias"].to(dtype))
+        a = F.batch_norm(a, Ld["rm"].to(dtype), Ld["rv"].to(dtype), Ld["gamma"].to(dtype), Ld["beta"].to(dtype),
+                         training=train, momentum=0.1, eps=1e-5)
+        if Ld["relu"]:
+            a = F.relu(a)
+    return a.max(dim=2)[0] if pool else a
+
+
+def _run_stack_case(chans, relus, B, N, pool, seed, train=True, precision="fp32", zero_gamma=False, tol=2e-5, gtol=2e-4):
+    from pointcloududa_b200.networks.PointNetCls import shared_mlp
+    import torch.nn as nn
+    rs = np.random.RandomState(seed)
+    convs, bns, layers = [], [], []
+    for l in range(len(chans) - 1):
+        conv = nn.Conv1d(chans[l], chans[l + 1], 1).to(DEV)
+        bn = nn.BatchNorm1d(chans[l + 1]).to(DEV)
+        with torch.no_grad():
+            bn.weight.copy_(torch.from_numpy(1.0 + 0.5 * rs.standard_normal(chans[l + 1])).float())
+            bn.bias.copy_(torch.from_numpy(0.2 * rs.standard_normal(chans[l + 1])).float())
+            if zero_gamma:
+                bn.weight[::7] = 0.0
+            bn.running_mean.copy_(torch.from_numpy(0.1 * rs.standard_normal(chans[l + 1])).float())
+            bn.running_var.copy_(torch.from_numpy(rs.uniform(0.5, 1.5, chans[l + 1])).float())
+        bn.train(train)
+        convs.append(conv); bns.append(bn)
+    scale = torch.from_numpy(rs.uniform(0.3, 1.0, size=(B, 1, chans[0]))).float()
+    pts = (torch.from_numpy(rs.rand(B, N, chans[0])).float() * scale).to(DEV)
+    x = pts.transpose(2, 1).requires_grad_(True)            # the transposed VIEW the reference passes
+    ref_layers = [dict(weight=c.weight.detach().double(), bias=c.bias.detach().double(),
+                       gamma=b.weight.detach().double(), beta=b.bias.detach().double(),
+                       rm=b.running_mean.clone().double(), rv=b.running_var.clone().double(), relu=r)
+                  for c, b, r in zip(convs, bns, relus)]
+    for Ld in ref_layers:
+        for k in ("weight", "bias", "gamma", "beta"):
+            Ld[k].requires_grad_(True)
+    xr = pts.transpose(2, 1).double().detach().requires_grad_(True)
+    out_r = _torch_stack(xr, ref_layers, pool, train, torch.float64)
+    w = torch.from_numpy(rs.standard_normal(tuple(out_r.shape))).to(DEV)
+    (out_r * w).sum().backward()
+
+    out = shared_mlp(x, convs, bns, relus, pool=pool, precision=precision)
+    assert out.shape == out_r.shape
+    assert max_rel(out.detach().cpu().numpy(), out_r.detach().cpu().numpy()) < tol
+    (out * w.float()).sum().backward()
+    assert max_rel(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < gtol
+    for c, b, Ld in zip(convs, bns, ref_layers):
+        assert max_rel(c.weight.grad.cpu().numpy().reshape(Ld["weight"].shape), Ld["weight"].grad.cpu().numpy()) < gtol
+        assert max_rel(b.weight.grad.cpu().numpy(), Ld["gamma"].grad.cpu().numpy()) < gtol
+        assert max_rel(b.bias.grad.cpu().numpy(), Ld["beta"].grad.cpu().numpy()) < gtol
+        if train:   # train-mode BN cancels the conv bias: the gradient is exactly zero
+            assert c.bias.grad.abs().max().item() == 0.0
+        else:
+            assert max_rel(c.bias.grad.cpu().numpy(), Ld["bias"].grad.cpu().numpy()) < gtol
+        if train:   # running statistics updated exactly like nn.BatchNorm1d
+            assert max_rel(b.running_mean.cpu().numpy(), Ld["rm"].cpu().numpy()) < 1e-5
+            assert max_rel(b.running_var.cpu().numpy(), Ld["rv"].cpu().numpy()) < 1e-5
+            assert int(b.num_batches_tracked.item()) == 1
+    return out
+
+
+@pytest.mark.parametrize("B,N", [(4, 64), (8, 300), (2, 50), (3, 129), (2, 1)])
+def test_shared_mlp_pooled_default_stack(B, N):
+    _run_stack_case([3, 64, 128, 1024], [True, True, True], B, N, pool=True, seed=B * 1000 + N)   # STN3d trunk
+    _run_stack_case([3, 64, 128, 1024], [True, True, False], B, N, pool=True, seed=B * 1000 + N + 1)  # main trunk
+
+
+def test_shared_mlp_other_stacks():
+    _run_stack_case([3, 64], [True], 4, 100, pool=False, seed=1)                              # ft: pre stack, dense out
+    _run_stack_case([3, 8, 64], [True, True], 4, 100, pool=False, seed=2)                     # ft+ext pre stack
+    _run_stack_case([64, 128, 1024], [True, False], 4, 100, pool=True, seed=3)                # ft: post stack
+    _run_stack_case([64, 64, 128, 1024], [True, True, True], 3, 70, pool=True, seed=4)        # STNkd trunk
+    _run_stack_case([3, 8, 64, 128, 256, 512, 1024], [True, True, True, True, False, True], 3, 40, pool=True,
+                    seed=5, gtol=5e-4)                                                        # ext trunk
+    _run_stack_case([3, 1024], [False], 4, 33, pool=True, seed=6)                             # single pooled layer
+
+
+def test_shared_mlp_zero_and_negative_gamma():
+    _run_stack_case([3, 64, 128, 1024], [True, True, False], 4, 64, pool=True, seed=11, zero_gamma=True)
+
+
+def test_shared_mlp_eval_mode():
+    _run_stack_case([3, 64, 128, 1024], [True, True, False], 4, 64, pool=True, seed=12, train=False)
+    _run_stack_case([3, 64], [True], 4, 64, pool=False, seed=13, train=False)
+
+
+def _load_params(net, params):
+    sd = net.state_dict()
+    for k, v in params.items():
+        sd[k] = torch.from_numpy(v.copy())
+    net.load_state_dict(sd)
+
+
+@pytest.mark.parametrize("case", list(POINTNET_CASES))
+def test_pointnetcls_vs_reference_golden(golden_pointnet, case):
+    """Whole discriminator (fp32 path) against the reference's own outputs and gradients."""
+    from pointcloududa_b200.networks.PointNetCls import PointNetCls
+    from test_oracle_golden import POINTNET_TOL
+    g = golden_pointnet[case]
+    kw, B, N, seed = POINTNET_CASES[case]
+    tol, gtol = POINTNET_TOL[case]
+    net = PointNetCls(drop=0.0, precision="fp32", **kw)
+    _load_params(net, oracle.make_params(oracle.PointNetSpec(**kw), seed))
+    net.to(DEV).train()
+    x = torch.from_numpy(g["pts"]).to(DEV).transpose(2, 1).requires_grad_(True)
+    logit, trans, trans_feat = net(x)
+    assert logit.shape == (B, 1)
+    assert max_rel(logit.detach().cpu().numpy(), g["logit"]) < 4 * tol
+    if "trans" in g:
+        assert max_rel(trans.detach().cpu().numpy(), g["trans"]) < 4 * tol
+    else:
+        assert trans is None
+    if "trans_feat_sum" in g:
+        assert max_rel(trans_feat.detach().sum(dim=(1, 2)).cpu().numpy(), g["trans_feat_sum"]) < 4 * tol
+    else:
+        assert trans_feat is None
+    loss = F.binary_cross_entropy_with_logits(logit, torch.ones_like(logit))
+    assert abs(loss.item() - float(g["loss"])) < 4 * tol * max(abs(float(g["loss"])), 1.0)
+    if gtol is None:
+        return
+    loss.backward()
+    assert max_rel(x.grad.cpu().numpy(), g["grad_x"]) < 2 * gtol
+    for k, p in net.named_parameters():
+        if f"gsample/{k}" not in g:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0
+            continue
+        mine = p.grad.detach().cpu().numpy().reshape(-1)
+        gs = g[f"gsample/{k}"]
+        norm_ref = float(g[f"gnorm/{k}"])
+        idx = sample_index(mine.size, k)
+        scale = max(np.abs(gs).max(), norm_ref / np.sqrt(mine.size), 1e-12)
+        leaf = k.rsplit(".", 2)[-2]
+        if k.endswith(".bias") and (leaf.startswith("conv") or leaf in ("fc1", "fc2")):
+            assert np.abs(mine).max() < 1e-3, k
+        else:
+            assert np.abs(mine[idx] - gs).max() <= 2 * gtol * scale + 2 * gtol * 1e-3, k
+    for k, v in net.state_dict().items():
+        if f"buf/{k}" in g:
+            assert max_rel(v.cpu().numpy(), g[f"buf/{k}"]) < 1e-4, k
+
+
+def test_pointnetcls_frozen_parameters_dgrad_only():
+    """Phase P2 of the train loop (train_mscmrseg.py:184-198,232-246): D4's parameters are frozen,
+    the gradient flows into the cloud only, and BN running stats still update."""
+    from pointcloududa_b200.networks.PointNetCls import PointNetCls
+    net = PointNetCls(drop=0.0, precision="fp32").to(DEV).train()
+    for p in net.parameters():
+        p.requires_grad = False
+    pts = torch.rand(4, 300, 3, device=DEV, requires_grad=True)
+    rm0 = net.feat.bn3.running_mean.clone()
+    out = net(pts.transpose(2, 1))[0]
+    F.binary_cross_entropy_with_logits(out, torch.ones_like(out)).backward()
+    assert pts.grad is not None and torch.isfinite(pts.grad).all() and pts.grad.abs().max() > 0
+    assert all(p.grad is None for p in net.parameters())
+    assert not torch.equal(rm0, net.feat.bn3.running_mean)
+    assert int(net.feat.bn3.num_batches_tracked.item()) == 1
+
+
+def test_pointnetcls_batch_of_one_raises():
+    from pointcloududa_b200.networks.PointNetCls import PointNetCls
+    net = PointNetCls().to(DEV)
+    with pytest.raises(ops.PcudaError):
+        net(torch.rand(1, 3, 64, device=DEV))
