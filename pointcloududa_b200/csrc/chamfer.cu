@@ -354,8 +354,9 @@ struct Plan {
 
 Plan make_plan(int B, int N, int M) {
   // Fill the machine: prefer 4 rows/thread (amortises each shared-memory broadcast over 4 pair
-  // evaluations) but fall back to fewer rows / smaller blocks while the grid would be < 2 waves.
-  const int64_t target = static_cast<int64_t>(sm_count()) * 8;
+  // evaluations) but fall back to fewer rows / smaller blocks while the grid would be < 4 CTAs per SM
+  // (measured on B200: R=4 wins from B*N >= 64*4096, R=1 below 32*1024).
+  const int64_t target = static_cast<int64_t>(sm_count()) * 4;
   const int forced = tuning(TUNE_CHAMFER_ROWS);
   const int cand[5][2] = {{8, 128}, {4, 128}, {2, 128}, {1, 128}, {1, 64}};
   Plan p{1, 64, 0, 0};

@@ -162,7 +162,8 @@ template <bool POOL>
 __global__ void __launch_bounds__(kThreads)
 mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias, int Cout,
                int N, int tiles_per_sample, float* __restrict__ y_out, double* __restrict__ stats,
-               const float* __restrict__ gamma, unsigned long long* __restrict__ keys) {
+               const float* __restrict__ pivot, const float* __restrict__ gamma,
+               unsigned long long* __restrict__ keys) {
   __shared__ Tiles t;
   __shared__ float ssum[TN], ssq[TN];
   __shared__ unsigned long long skey[TN];
@@ -204,14 +205,18 @@ mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
     if (c >= Cout) continue;
     const float bj = bias ? bias[c] : 0.f;
     const float g = POOL ? gamma[c] : 0.f;
+    // statistics are accumulated on (y - pivot_c), pivot_c = y of point 0: E[y^2]-E[y]^2 on raw
+    // values loses |mean|^2/var digits in fp32, centred sums do not (torch uses Welford)
+    const float pv = pivot[c];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int n = n0 + ty * 4 + i;
       if (n >= N) continue;
       const float v = acc[i][j] + bj;
       acc[i][j] = v;
-      cs[j] += v;
-      cq[j] = fmaf(v, v, cq[j]);
+      const float vc = v - pv;
+      cs[j] += vc;
+      cq[j] = fmaf(vc, vc, cq[j]);
       if (POOL) {
         // track max of sign(gamma)*y; gamma == 0 -> every n ties and the first index wins
         const float vv = g > 0.f ? v : (g < 0.f ? -v : 0.f);
@@ -250,26 +255,45 @@ mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, double count, float eps,
-                                   float momentum, int train, float* __restrict__ save_mean,
-                                   float* __restrict__ save_invstd, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (train) {
-    const double mean = stats[c] / count;
-    double var = stats[C + c] / count - mean * mean;
-    var = var > 0.0 ? var : 0.0;
-    save_mean[c] = static_cast<float>(mean);
-    save_invstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
-    if (running_var) {
-      const double unbiased = var * (count / (count - 1.0));
-      running_var[c] = (1.0f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+// One block.  Phase 1 (if stats != nullptr): finalise BatchNorm of layer l-1 from its centred sums.
+// Phase 2 (if W_next != nullptr): pivot of layer l = its pre-BN output at global point 0, which
+// needs layer l-1's finalised parameters — hence the same kernel, separated by a block barrier.
+__global__ void __launch_bounds__(1024)
+bn_finalize_pivot_kernel(const double* __restrict__ stats, const float* __restrict__ pivot_prev, int C,
+                         double count, float eps, float momentum, int train, float* __restrict__ save_mean,
+                         float* __restrict__ save_invstd, float* __restrict__ running_mean,
+                         float* __restrict__ running_var, ActSrc src_next, const float* __restrict__ W_next,
+                         const float* __restrict__ bias_next, int C_next, float* __restrict__ pivot_next) {
+  if (stats != nullptr) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (train) {
+        const double d = stats[c] / count;
+        const double mean = static_cast<double>(pivot_prev[c]) + d;
+        double var = stats[C + c] / count - d * d;
+        var = var > 0.0 ? var : 0.0;
+        save_mean[c] = static_cast<float>(mean);
+        save_invstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+        if (running_var) {
+          const double unbiased = var * (count / (count - 1.0));
+          running_var[c] = (1.0f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+        }
+      } else {
+        save_mean[c] = running_mean[c];
+        save_invstd[c] = static_cast<float>(1.0 / sqrt(static_cast<double>(running_var[c]) + static_cast<double>(eps)));
+      }
     }
-  } else {
-    save_mean[c] = running_mean[c];
-    save_invstd[c] = static_cast<float>(1.0 / sqrt(static_cast<double>(running_var[c]) + static_cast<double>(eps)));
+  }
+  if (W_next == nullptr) return;
+  __threadfence_block();
+  __syncthreads();
+  const int K = src_next.C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < C_next; c += nwarps) {
+    float dot = 0.f;
+    for (int k = lane; k < K; k += 32) dot = fmaf(W_next[static_cast<int64_t>(c) * K + k], load_act1(src_next, 0, k), dot);
+    dot = warp_sum(dot);
+    if (lane == 0) pivot_next[c] = dot + (bias_next ? bias_next[c] : 0.f);
   }
 }
 
@@ -306,37 +330,54 @@ __global__ void dense_out_kernel(ActSrc src, int B, float* __restrict__ out) {
 }
 
 // ---- backward: pooled last layer ---------------------------------------------------------------
-// One thread per output channel c; loops over the B clouds (deterministic order).
-__global__ void pool_bwd_stats_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias,
-                                      const float* __restrict__ mean, const float* __restrict__ invstd,
-                                      const float* __restrict__ gamma, int relu, int train,
-                                      const float* __restrict__ out, const int32_t* __restrict__ arg,
-                                      const float* __restrict__ grad_out, int B, int N, int C, double count,
-                                      float* __restrict__ coef, float* __restrict__ alpha, float* __restrict__ kappa,
-                                      float* __restrict__ grad_gamma, float* __restrict__ grad_beta) {
+// One warp per (cloud, channel): masked upstream gradient and yhat at the selected point.
+__global__ void pool_sel_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias,
+                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                const float* __restrict__ gamma, int relu, const float* __restrict__ out,
+                                const int32_t* __restrict__ arg, const float* __restrict__ grad_out, int B, int N,
+                                int C, float* __restrict__ coef, float* __restrict__ gsel, float* __restrict__ gyh) {
+  const int64_t w = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= static_cast<int64_t>(B) * C) return;
+  const int c = static_cast<int>(w % C);
+  const int64_t b = w / C;
+  const int K = src.C;
+  float g = grad_out[w];
+  if (relu && !(out[w] > 0.f)) g = 0.f;
+  float yhat = 0.f;
+  if (g != 0.f) {
+    const int64_t m = b * N + arg[w];
+    float dot = 0.f;
+    for (int k = lane; k < K; k += 32) dot = fmaf(W[static_cast<int64_t>(c) * K + k], load_act1(src, m, k), dot);
+    dot = warp_sum(dot);
+    yhat = (dot + (bias ? bias[c] : 0.f) - mean[c]) * invstd[c];
+  }
+  if (lane == 0) {
+    coef[w] = gamma[c] * invstd[c] * g;
+    gsel[w] = g;
+    gyh[w] = g * yhat;
+  }
+}
+
+// One thread per channel: fixed-order sums over the B clouds.
+__global__ void pool_coef_kernel(const float* __restrict__ gsel, const float* __restrict__ gyh,
+                                 const float* __restrict__ invstd, const float* __restrict__ gamma, int B, int C,
+                                 double count, int train, float* __restrict__ alpha, float* __restrict__ kappa,
+                                 float* __restrict__ grad_gamma, float* __restrict__ grad_beta,
+                                 float* __restrict__ grad_bias) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const int K = src.C;
-  const float sc = gamma[c] * invstd[c];
-  const float bc = bias ? bias[c] : 0.f;
   double dbeta = 0.0, dgamma = 0.0;
   for (int b = 0; b < B; ++b) {
-    float g = grad_out[static_cast<int64_t>(b) * C + c];
-    if (relu && !(out[static_cast<int64_t>(b) * C + c] > 0.f)) g = 0.f;
-    coef[static_cast<int64_t>(b) * C + c] = sc * g;
-    if (g != 0.f) {
-      const int64_t m = static_cast<int64_t>(b) * N + arg[static_cast<int64_t>(b) * C + c];
-      float dot = 0.f;
-      for (int k = 0; k < K; ++k) dot = fmaf(W[static_cast<int64_t>(c) * K + k], load_act1(src, m, k), dot);
-      const float yhat = (dot + bc - mean[c]) * invstd[c];
-      dbeta += static_cast<double>(g);
-      dgamma += static_cast<double>(g) * static_cast<double>(yhat);
-    }
+    dbeta += static_cast<double>(gsel[static_cast<int64_t>(b) * C + c]);
+    dgamma += static_cast<double>(gyh[static_cast<int64_t>(b) * C + c]);
   }
+  const double sc = static_cast<double>(gamma[c]) * static_cast<double>(invstd[c]);
   if (grad_gamma) grad_gamma[c] = static_cast<float>(dgamma);
   if (grad_beta) grad_beta[c] = static_cast<float>(dbeta);
-  alpha[c] = train ? static_cast<float>(static_cast<double>(sc) * dbeta / count) : 0.f;
-  kappa[c] = train ? static_cast<float>(static_cast<double>(sc) * static_cast<double>(invstd[c]) * dgamma / count) : 0.f;
+  if (grad_bias) grad_bias[c] = train ? 0.f : static_cast<float>(sc * dbeta);
+  alpha[c] = train ? static_cast<float>(sc * dbeta / count) : 0.f;
+  kappa[c] = train ? static_cast<float>(sc * static_cast<double>(invstd[c]) * dgamma / count) : 0.f;
 }
 
 // column sums of an activation: partial[s, k] over the s-th slice of points
@@ -443,13 +484,15 @@ __global__ void pool_u_kernel(const float* __restrict__ W, const float* __restri
 __global__ void pool_dw_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ coef,
                                const int32_t* __restrict__ arg, const float* __restrict__ kappa,
                                const float* __restrict__ abar, const float* __restrict__ Ghat, int B, int N,
-                               int C, float* __restrict__ dW) {
+                               int C, int train, float* __restrict__ dW) {
   const int K = src.C;
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<int64_t>(C) * K) return;
   const int c = static_cast<int>(i / K), k = static_cast<int>(i % K);
   double s = 0.0;
-  const float ab = abar[k];
+  // train: sum_b coef = M*alpha, which folds the rank-one BN term into a centring of a[sel];
+  // eval: there is no BN correction at all
+  const float ab = train ? abar[k] : 0.f;
   for (int b = 0; b < B; ++b) {
     const float cf = coef[static_cast<int64_t>(b) * C + c];
     if (cf != 0.f) {
@@ -700,6 +743,7 @@ Shape make_shape(int B, int N, int L, const pcuda_mlp_layer_t* layers, int pool)
 size_t fwd_ws_bytes(const Shape& s) {
   size_t b = align_up(sizeof(double) * 2 * s.sumC);
   if (s.pool) b += align_up(sizeof(unsigned long long) * static_cast<size_t>(s.B) * s.Clast);
+  b += align_up(sizeof(float) * (static_cast<size_t>(s.sumC) + 4));  // pivots
   return b;
 }
 
@@ -710,7 +754,7 @@ size_t bwd_ws_bytes(const Shape& s) {
   b += align_up(sizeof(float) * static_cast<size_t>(s.S) * s.maxWW);  // contraction partials
   if (s.pool) {
     const size_t K = s.Kpool;
-    b += align_up(sizeof(float) * static_cast<size_t>(s.B) * s.Clast);  // coef
+    b += 3 * align_up(sizeof(float) * static_cast<size_t>(s.B) * s.Clast);  // coef, gsel, gyh
     b += align_up(sizeof(double) * s.S * K);                            // colsum partials
     b += align_up(sizeof(double) * K * K);                              // G
     b += 2 * align_up(sizeof(float) * K * K);                           // Ghat, Q
@@ -774,25 +818,38 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
   Carver cv(ws);
   double* stats = cv.take<double>(2 * static_cast<size_t>(s.sumC));
   unsigned long long* keys = pool ? cv.take<unsigned long long>(static_cast<size_t>(B) * s.Clast) : nullptr;
+  float* pivots = cv.take<float>(static_cast<size_t>(s.sumC) + 4);
   cudaMemsetAsync(stats, 0, sizeof(double) * 2 * s.sumC, st);
   if (pool) cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * static_cast<size_t>(B) * s.Clast, st);
 
   const int tps = (N + TM - 1) / TM;
   double* st_l = stats;
+  float* piv_l = pivots;
   int launches = 0;
+  // pivot of layer 0 (no BN to finalise yet)
+  bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, 0, 1.0, eps, momentum, train, nullptr, nullptr, nullptr, nullptr,
+                                               input_src(x, sxb, sxc, sxn, N, layers[0].cin), layers[0].weight, layers[0].bias,
+                                               layers[0].cout, piv_l);
+  launches += 1;
   for (int l = 0; l < L; ++l) {
     const pcuda_mlp_layer_t& y = layers[l];
     const ActSrc src = l == 0 ? input_src(x, sxb, sxc, sxn, N, y.cin) : layer_src(layers[l - 1], N);
     const dim3 grid(B * tps, (y.cout + TN - 1) / TN);
     const bool is_pool = pool && l == L - 1;
     if (is_pool)
-      mlp_fwd_kernel<true><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, y.gamma, keys);
+      mlp_fwd_kernel<true><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, keys);
     else
-      mlp_fwd_kernel<false><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, y.gamma, nullptr);
-    bn_finalize_kernel<<<(y.cout + 127) / 128, 128, 0, st>>>(st_l, y.cout, static_cast<double>(s.M), eps, momentum, train,
-                                                            y.save_mean, y.save_invstd, y.running_mean, y.running_var);
+      mlp_fwd_kernel<false><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, nullptr);
+    // finalise this layer's BN; if a dense layer follows, compute its pivot in the same launch
+    const bool has_next = l + 1 < L;
+    bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(st_l, piv_l, y.cout, static_cast<double>(s.M), eps, momentum, train,
+                                                 y.save_mean, y.save_invstd, y.running_mean, y.running_var,
+                                                 has_next ? layer_src(y, N) : ActSrc{}, has_next ? layers[l + 1].weight : nullptr,
+                                                 has_next ? layers[l + 1].bias : nullptr, has_next ? layers[l + 1].cout : 0,
+                                                 piv_l + y.cout);
     launches += 2;
     st_l += 2 * y.cout;
+    piv_l += y.cout;
   }
   const pcuda_mlp_layer_t& last = layers[L - 1];
   if (pool) {
@@ -827,11 +884,13 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
   float* alpha = cv.take<float>(s.sumC);
   float* kappa = cv.take<float>(s.sumC);
   float* partial = cv.take<float>(static_cast<size_t>(s.S) * s.maxWW);
-  float *coef = nullptr, *Ghat = nullptr, *Q = nullptr, *abar = nullptr, *u = nullptr;
+  float *coef = nullptr, *gsel = nullptr, *gyh = nullptr, *Ghat = nullptr, *Q = nullptr, *abar = nullptr, *u = nullptr;
   double *colsum = nullptr, *G = nullptr;
   if (pool) {
     const size_t K = s.Kpool;
     coef = cv.take<float>(static_cast<size_t>(B) * s.Clast);
+    gsel = cv.take<float>(static_cast<size_t>(B) * s.Clast);
+    gyh = cv.take<float>(static_cast<size_t>(B) * s.Clast);
     colsum = cv.take<double>(s.S * K);
     G = cv.take<double>(K * K);
     Ghat = cv.take<float>(K * K);
@@ -866,10 +925,15 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     const ActSrc src = src_of(L - 2);
     float* al = alpha + off[L - 1];
     float* ka = kappa + off[L - 1];
-    pool_bwd_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(src, last.weight, last.bias, last.save_mean, last.save_invstd,
-                                                           last.gamma, last.relu, train, out, pool_arg, grad_out, B, N, C, count,
-                                                           coef, al, ka, last.grad_weight ? last.grad_gamma : nullptr,
-                                                           last.grad_weight ? last.grad_beta : nullptr);
+    const int64_t bc = static_cast<int64_t>(B) * C;
+    pool_sel_kernel<<<static_cast<int>((bc * 32 + 255) / 256), 256, 0, st>>>(src, last.weight, last.bias, last.save_mean,
+                                                                            last.save_invstd, last.gamma, last.relu, out, pool_arg,
+                                                                            grad_out, B, N, C, coef, gsel, gyh);
+    const bool want_last = last.grad_weight != nullptr;
+    pool_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(gsel, gyh, last.save_invstd, last.gamma, B, C, count, train, al, ka,
+                                                      want_last ? last.grad_gamma : nullptr, want_last ? last.grad_beta : nullptr,
+                                                      want_last ? last.grad_bias : nullptr);
+    launches += 1;
     act_colsum_kernel<<<dim3(s.S, (K + 127) / 128), 128, 0, st>>>(src, s.M, chunk, colsum);
     point_contract_kernel<1><<<dim3(s.S, (K + TM - 1) / TM, (K + TN - 1) / TN), kThreads, 0, st>>>(DySrc{}, src, src, s.M, chunk, K, K, partial);
     const int64_t kk = static_cast<int64_t>(K) * K;
@@ -880,8 +944,7 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     launches += 7;
     if (last.grad_weight) {
       const int64_t ck = static_cast<int64_t>(C) * K;
-      pool_dw_kernel<<<static_cast<int>((ck + 255) / 256), 256, 0, st>>>(src, last.weight, coef, pool_arg, ka, abar, Ghat, B, N, C, last.grad_weight);
-      if (last.grad_bias) cudaMemsetAsync(last.grad_bias, 0, sizeof(float) * C, st);  // train-mode BN: exactly 0
+      pool_dw_kernel<<<static_cast<int>((ck + 255) / 256), 256, 0, st>>>(src, last.weight, coef, pool_arg, ka, abar, Ghat, B, N, C, train, last.grad_weight);
       launches += 1;
     }
     if (L >= 2 || grad_x) {

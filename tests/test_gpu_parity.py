@@ -285,7 +285,7 @@ def _torch_stack(x, layers, pool, train, dtype):
                          training=train, momentum=0.1, eps=1e-5)
         if Ld["relu"]:
             a = F.relu(a)
-    return a.max(dim=2)[0] if pool else a
+    return (a.max(dim=2)[0] if pool else a), a
 
 
 def _run_stack_case(chans, relus, B, N, pool, seed, train=True, precision="fp32", zero_gamma=False, tol=2e-5, gtol=2e-4):
@@ -316,8 +316,15 @@ def _run_stack_case(chans, relus, B, N, pool, seed, train=True, precision="fp32"
         for k in ("weight", "bias", "gamma", "beta"):
             Ld[k].requires_grad_(True)
     xr = pts.transpose(2, 1).double().detach().requires_grad_(True)
-    out_r = _torch_stack(xr, ref_layers, pool, train, torch.float64)
+    out_r, pre = _torch_stack(xr, ref_layers, pool, train, torch.float64)
     w = torch.from_numpy(rs.standard_normal(tuple(out_r.shape))).to(DEV)
+    if pool and N > 1:
+        # A (cloud, channel) whose two largest values are closer than fp32 can resolve may select
+        # a different point in fp32 than in this fp64 reference (either choice is a valid
+        # torch.max result at that precision); keep such pairs out of the gradient comparison.
+        top2 = pre.detach().topk(2, dim=2)[0]
+        ambiguous = (top2[..., 0] - top2[..., 1]) < 1e-4 * (1.0 + top2[..., 0].abs())
+        w = torch.where(ambiguous, torch.zeros_like(w), w)
     (out_r * w).sum().backward()
 
     out = shared_mlp(x, convs, bns, relus, pool=pool, precision=precision)
@@ -327,8 +334,12 @@ def _run_stack_case(chans, relus, B, N, pool, seed, train=True, precision="fp32"
     assert max_rel(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < gtol
     for c, b, Ld in zip(convs, bns, ref_layers):
         assert max_rel(c.weight.grad.cpu().numpy().reshape(Ld["weight"].shape), Ld["weight"].grad.cpu().numpy()) < gtol
-        assert max_rel(b.weight.grad.cpu().numpy(), Ld["gamma"].grad.cpu().numpy()) < gtol
-        assert max_rel(b.bias.grad.cpu().numpy(), Ld["beta"].grad.cpu().numpy()) < gtol
+        # gamma/beta gradients can be mathematically zero (a BN without ReLU feeding another
+        # train-mode BN): compare on the scale of the layer's weight gradient
+        gscale = Ld["weight"].grad.abs().max().item()
+        for mine, ref in ((b.weight.grad, Ld["gamma"].grad), (b.bias.grad, Ld["beta"].grad)):
+            err = (mine.double() - ref).abs().max().item()
+            assert err <= gtol * max(ref.abs().max().item(), 1e-2 * gscale), (err, ref.abs().max().item(), gscale)
         if train:   # train-mode BN cancels the conv bias: the gradient is exactly zero
             assert c.bias.grad.abs().max().item() == 0.0
         else:
