@@ -23,7 +23,8 @@
 #include <algorithm>
 #include <vector>
 
-#include "pcuda_common.cuh"
+#include "pointmlp_common.cuh"
+#include "pointmlp_tc.cuh"
 
 namespace pcuda {
 namespace {
@@ -33,88 +34,6 @@ constexpr int TN = 64;   // tile cols
 constexpr int TK = 16;   // contraction chunk
 constexpr int LD = 68;   // padded leading dimension of the smem tiles
 constexpr int kThreads = 256;
-
-// a_l[m, k] = relu?((y[m,k] - mean_k) * invstd_k * gamma_k + beta_k), or raw x for the network input
-struct ActSrc {
-  const float* y;  // [M, C] or nullptr -> raw input
-  const float* mean;
-  const float* invstd;
-  const float* gamma;
-  const float* beta;
-  int relu;
-  const float* x;  // raw input, x[b*sxb + c*sxc + n*sxn]
-  int64_t sxb, sxc, sxn;
-  int N;
-  int C;
-};
-
-__device__ __forceinline__ float bn_act(float y, float mean, float invstd, float gamma, float beta, int relu) {
-  const float z = fmaf(y - mean, invstd * gamma, beta);
-  return relu ? fmaxf(z, 0.0f) : z;
-}
-
-// 4 consecutive channels k..k+3 of point m (zero beyond C). k % 4 == 0.
-__device__ __forceinline__ float4 load_act4(const ActSrc& s, int64_t m, int k) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (s.y != nullptr) {
-    if (k + 3 < s.C) {
-      const float4 yy = *reinterpret_cast<const float4*>(s.y + m * s.C + k);
-      const float4 mu = *reinterpret_cast<const float4*>(s.mean + k);
-      const float4 is = *reinterpret_cast<const float4*>(s.invstd + k);
-      const float4 ga = *reinterpret_cast<const float4*>(s.gamma + k);
-      const float4 be = *reinterpret_cast<const float4*>(s.beta + k);
-      v.x = bn_act(yy.x, mu.x, is.x, ga.x, be.x, s.relu);
-      v.y = bn_act(yy.y, mu.y, is.y, ga.y, be.y, s.relu);
-      v.z = bn_act(yy.z, mu.z, is.z, ga.z, be.z, s.relu);
-      v.w = bn_act(yy.w, mu.w, is.w, ga.w, be.w, s.relu);
-    } else {
-      float* pv = &v.x;
-      for (int i = 0; i < 4 && k + i < s.C; ++i)
-        pv[i] = bn_act(s.y[m * s.C + k + i], s.mean[k + i], s.invstd[k + i], s.gamma[k + i], s.beta[k + i], s.relu);
-    }
-  } else {
-    const int64_t b = m / s.N, n = m - b * s.N;
-    const float* px = s.x + b * s.sxb + n * s.sxn;
-    float* pv = &v.x;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (k + i < s.C) pv[i] = __ldg(px + (k + i) * s.sxc);
-  }
-  return v;
-}
-
-__device__ __forceinline__ float load_act1(const ActSrc& s, int64_t m, int k) {
-  if (s.y != nullptr) return bn_act(s.y[m * s.C + k], s.mean[k], s.invstd[k], s.gamma[k], s.beta[k], s.relu);
-  const int64_t b = m / s.N, n = m - b * s.N;
-  return __ldg(s.x + b * s.sxb + n * s.sxn + k * s.sxc);
-}
-
-// dy_l[m, c] = s_c*dz[m,c] - alpha_c - kappa_c*(y[m,c] - mean_c)   (train-mode BN backward; in
-// eval mode alpha = kappa = 0).  s_c = gamma_c * invstd_c.
-struct DySrc {
-  const float* dz;  // [M, C]
-  const float* y;   // [M, C]
-  const float* mean;
-  const float* invstd;
-  const float* gamma;
-  const float* alpha;
-  const float* kappa;
-  int C;
-};
-
-__device__ __forceinline__ float4 load_dy4(const DySrc& s, int64_t m, int c) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  float* pv = &v.x;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int cc = c + i;
-    if (cc < s.C) {
-      const float sc = s.gamma[cc] * s.invstd[cc];
-      pv[i] = fmaf(sc, s.dz[m * s.C + cc], -s.alpha[cc]) - s.kappa[cc] * (s.y[m * s.C + cc] - s.mean[cc]);
-    }
-  }
-  return v;
-}
 
 // ---- shared 64x64x16 FP32 micro-kernel ---------------------------------------------------------
 struct Tiles {
@@ -151,10 +70,6 @@ __device__ __forceinline__ void stage_cols(float (&S)[TK][LD], F f4, int k0) {
   *reinterpret_cast<float4*>(&S[kk][c4]) = v;
 }
 
-__device__ __forceinline__ unsigned long long pool_key(float v, int n) {
-  return (static_cast<unsigned long long>(float_to_ordered(v)) << 32) |
-         static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<unsigned int>(n));
-}
 
 // ---- forward layer -------------------------------------------------------------------------------
 // grid (B * tiles_per_sample, ceil(Cout/64)).  Tiles never straddle two clouds.
@@ -380,15 +295,33 @@ __global__ void pool_coef_kernel(const float* __restrict__ gsel, const float* __
   kappa[c] = train ? static_cast<float>(sc * static_cast<double>(invstd[c]) * dgamma / count) : 0.f;
 }
 
-// column sums of an activation: partial[s, k] over the s-th slice of points
-__global__ void act_colsum_kernel(ActSrc src, int64_t M, int64_t chunk, double* __restrict__ partial) {
-  const int k = blockIdx.y * blockDim.x + threadIdx.x;
-  if (k >= src.C) return;
+// column sums of an activation: partial[s, k] over the s-th slice of points.
+// grid (S, ceil(K/32)), 256 threads: lane = channel, the 8 warps interleave the rows of the slice
+__global__ void __launch_bounds__(256)
+act_colsum_kernel(ActSrc src, int64_t M, int64_t chunk, double* __restrict__ partial) {
+  __shared__ double part[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.y * 32 + lane;
   const int64_t m0 = blockIdx.x * chunk;
   const int64_t m1 = m0 + chunk < M ? m0 + chunk : M;
   double s = 0.0;
-  for (int64_t m = m0; m < m1; ++m) s += static_cast<double>(load_act1(src, m, k));
-  partial[static_cast<int64_t>(blockIdx.x) * src.C + k] = s;
+  if (k < src.C) {
+    float f = 0.f;
+    int cnt = 0;
+    for (int64_t m = m0 + warp; m < m1; m += 8) {
+      f += load_act1(src, m, k);
+      if (++cnt == 32) { s += static_cast<double>(f); f = 0.f; cnt = 0; }
+    }
+    s += static_cast<double>(f);
+  }
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && k < src.C) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    partial[static_cast<int64_t>(blockIdx.x) * src.C + k] = t;
+  }
 }
 
 // OUT[s, r, c] = sum_{m in slice s} P[m, r] * R[m, c]   (contraction over points; 64x64 tile / CTA)
@@ -444,40 +377,109 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int64_
   out[i] = static_cast<TOut>(s);
 }
 
-// abar[k] = (sum_s colsum_partial[s,k]) / M ;  Ghat[k,k'] = G[k,k'] - M abar_k abar_k'
-__global__ void gram_center_kernel(const double* __restrict__ colsum_partial, int S, const double* __restrict__ G,
-                                   int K, double count, float* __restrict__ abar, float* __restrict__ Ghat) {
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= static_cast<int64_t>(K) * K) return;
-  const int k = static_cast<int>(i / K), k2 = static_cast<int>(i % K);
-  double a = 0.0, b = 0.0;
-  for (int s = 0; s < S; ++s) { a += colsum_partial[static_cast<int64_t>(s) * K + k]; b += colsum_partial[static_cast<int64_t>(s) * K + k2]; }
-  a /= count; b /= count;
-  Ghat[i] = static_cast<float>(G[i] - count * a * b);
-  if (k2 == 0) abar[k] = static_cast<float>(a);
-}
-
-// Q[k,k'] = sum_c kappa_c W[c,k] W[c,k']
-__global__ void pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, int C, int K,
-                              float* __restrict__ Q) {
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= static_cast<int64_t>(K) * K) return;
-  const int k = static_cast<int>(i / K), k2 = static_cast<int>(i % K);
-  double s = 0.0;
-  for (int c = 0; c < C; ++c)
-    s += static_cast<double>(kappa[c] * W[static_cast<int64_t>(c) * K + k]) * static_cast<double>(W[static_cast<int64_t>(c) * K + k2]);
-  Q[i] = static_cast<float>(s);
-}
-
-// u'[k] = sum_c alpha_c W[c,k] - sum_k' Q[k,k'] abar_k'
-__global__ void pool_u_kernel(const float* __restrict__ W, const float* __restrict__ alpha, const float* __restrict__ Q,
-                              const float* __restrict__ abar, int C, int K, float* __restrict__ u) {
+// abar[k] = (sum_s colsum_partial[s,k]) / M   (fixed order)
+__global__ void abar_kernel(const double* __restrict__ colsum_partial, int S, int K, double count,
+                            float* __restrict__ abar, double* __restrict__ abar_d) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
+  double a = 0.0;
+  for (int s = 0; s < S; ++s) a += colsum_partial[static_cast<int64_t>(s) * K + k];
+  a /= count;
+  abar[k] = static_cast<float>(a);
+  abar_d[k] = a;
+}
+
+// Ghat[k,k'] = G[k,k'] - M abar_k abar_k'
+__global__ void gram_center_kernel(const double* __restrict__ abar_d, const double* __restrict__ G, int K,
+                                   double count, float* __restrict__ Ghat) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(K) * K) return;
+  const int k = static_cast<int>(i / K), k2 = static_cast<int>(i % K);
+  Ghat[i] = static_cast<float>(G[i] - count * abar_d[k] * abar_d[k2]);
+}
+
+// Q[k,k'] = sum_c kappa_c W[c,k] W[c,k'].  grid (K/32, K/32), 256 threads, each 2x2 outputs;
+// the 32 x 32 output tile walks over all C channels in chunks of 32 staged in shared memory.
+__global__ void __launch_bounds__(256)
+pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, int C, int K, float* __restrict__ Q) {
+  __shared__ float Wa[32][33], Wb[32][33];
+  const int k0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lr = threadIdx.x >> 5, lc = threadIdx.x & 31;   // loader: 8 rows x 32 columns per pass
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    __syncthreads();
+#pragma unroll
+    for (int r = lr; r < 32; r += 8) {
+      const int c = c0 + r;
+      const float kp = c < C ? kappa[c] : 0.f;
+      Wa[r][lc] = (c < C && k0 + lc < K) ? kp * W[static_cast<int64_t>(c) * K + k0 + lc] : 0.f;
+      Wb[r][lc] = (c < C && j0 + lc < K) ? W[static_cast<int64_t>(c) * K + j0 + lc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const float a0 = Wa[r][ty * 2], a1 = Wa[r][ty * 2 + 1], b0 = Wb[r][tx * 2], b1 = Wb[r][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = k0 + ty * 2 + i, k2 = j0 + tx * 2 + j;
+      if (k < K && k2 < K) Q[static_cast<int64_t>(k) * K + k2] = acc[i][j];
+    }
+}
+
+// u'[k] = sum_c alpha_c W[c,k] - sum_k' Q[k',k] abar_k'.  grid K/32, 256 threads: lane = k, the 8 warps
+// interleave the summation index; partial sums are combined in a fixed order.
+__global__ void __launch_bounds__(256)
+pool_u_kernel(const float* __restrict__ W, const float* __restrict__ alpha, const float* __restrict__ Q,
+              const float* __restrict__ abar, int C, int K, float* __restrict__ u) {
+  __shared__ double part[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int c = 0; c < C; ++c) s += static_cast<double>(alpha[c]) * static_cast<double>(W[static_cast<int64_t>(c) * K + k]);
-  for (int k2 = 0; k2 < K; ++k2) s -= static_cast<double>(Q[static_cast<int64_t>(k2) * K + k]) * static_cast<double>(abar[k2]);
-  u[k] = static_cast<float>(s);
+  if (k < K) {
+    for (int c = warp; c < C; c += 8) s += static_cast<double>(alpha[c]) * static_cast<double>(W[static_cast<int64_t>(c) * K + k]);
+    for (int k2 = warp; k2 < K; k2 += 8) s -= static_cast<double>(Q[static_cast<int64_t>(k2) * K + k]) * static_cast<double>(abar[k2]);
+  }
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && k < K) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    u[k] = static_cast<float>(t);
+  }
+}
+
+// Inverted index of the max-pool selection of one cloud: for every point the ascending list of
+// channels whose arg-max it is (channels with a zero coefficient are left out).
+//   head[b*N + n] = first such channel or -1 (head must be pre-filled with -1); next[b*C + c] = next or -1
+__global__ void __launch_bounds__(1024)
+pool_invert_kernel(const int32_t* __restrict__ arg, const float* __restrict__ coef, int C, int N,
+                   int* __restrict__ head, int* __restrict__ next) {
+  extern __shared__ int sarg[];
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    sarg[c] = coef[static_cast<int64_t>(b) * C + c] != 0.f ? arg[static_cast<int64_t>(b) * C + c] : -1;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int a = sarg[c];
+    int nx = -1;
+    if (a >= 0) {
+      for (int c2 = c + 1; c2 < C; ++c2)
+        if (sarg[c2] == a) { nx = c2; break; }
+      bool is_head = true;
+      for (int c2 = c - 1; c2 >= 0; --c2)
+        if (sarg[c2] == a) { is_head = false; break; }
+      if (is_head) head[static_cast<int64_t>(b) * N + a] = c;
+    }
+    next[static_cast<int64_t>(b) * C + c] = nx;
+  }
 }
 
 // dW[c,k] = sum_b coef[b,c] (a[(b,sel),k] - abar_k) - kappa_c sum_k' W[c,k'] Ghat[k',k]
@@ -504,18 +506,6 @@ __global__ void pool_dw_kernel(ActSrc src, const float* __restrict__ W, const fl
   for (int k2 = 0; k2 < K; ++k2) t += static_cast<double>(W[static_cast<int64_t>(c) * K + k2]) * static_cast<double>(Ghat[static_cast<int64_t>(k2) * K + k]);
   dW[i] = static_cast<float>(s - static_cast<double>(kappa[c]) * t);
 }
-
-// Epilogue shared by the two dgrad kernels: val -> (ReLU mask of the producing layer) -> store
-// dz_prev + accumulate that layer's dbeta / dgamma sums; or, for the network input, store grad_x.
-struct DgradOut {
-  float* dz_prev;        // [M, Cp] or nullptr
-  const float* y_prev;   // [M, Cp] pre-BN of the previous layer (mask + yhat)
-  const float* mean; const float* invstd; const float* gamma; const float* beta;
-  int relu;
-  double* sums;          // [2*Cp]: dbeta, dgamma of the previous layer
-  float* grad_x;         // [B, Cp, N] when the previous "layer" is the input
-  int Cp;
-};
 
 __device__ __forceinline__ void dgrad_epilogue(const DgradOut& o, float (&acc)[4][4], int b, int n0, int N,
                                                int c0, int ty, int tx, float* ssum, float* ssq) {
@@ -722,7 +712,7 @@ struct Shape {
   int64_t M;
   int sumC = 0, maxC = 0, Clast = 0, Kpool = 0;
   int64_t maxWW = 0;  // largest cout*cin among layers handled by the generic wgrad
-  int S;
+  int S;              // upper bound of point-range splits of any contraction over points
 };
 
 Shape make_shape(int B, int N, int L, const pcuda_mlp_layer_t* layers, int pool) {
@@ -736,14 +726,15 @@ Shape make_shape(int B, int N, int L, const pcuda_mlp_layer_t* layers, int pool)
   s.Clast = layers[L - 1].cout;
   s.Kpool = layers[L - 1].cin;
   if (pool) s.maxWW = std::max<int64_t>(s.maxWW, static_cast<int64_t>(s.Kpool) * s.Kpool);
-  s.S = splits_for(s.M);
+  s.S = std::max(splits_for(s.M), sm_count());
   return s;
 }
 
 size_t fwd_ws_bytes(const Shape& s) {
-  size_t b = align_up(sizeof(double) * 2 * s.sumC);
+  size_t b = align_up(sizeof(double) * 2 * s.sumC);                    // stats
+  b += align_up(sizeof(float) * (static_cast<size_t>(s.sumC) + 4));    // zero vector (pivot of bias-free layers)
   if (s.pool) b += align_up(sizeof(unsigned long long) * static_cast<size_t>(s.B) * s.Clast);
-  b += align_up(sizeof(float) * (static_cast<size_t>(s.sumC) + 4));  // pivots
+  b += align_up(sizeof(float) * (static_cast<size_t>(s.sumC) + 4));    // pivots
   return b;
 }
 
@@ -759,6 +750,9 @@ size_t bwd_ws_bytes(const Shape& s) {
     b += align_up(sizeof(double) * K * K);                              // G
     b += 2 * align_up(sizeof(float) * K * K);                           // Ghat, Q
     b += 2 * align_up(sizeof(float) * K);                               // abar, u
+    b += align_up(sizeof(double) * K);                                  // abar (double)
+    b += align_up(sizeof(int) * static_cast<size_t>(s.M));              // head
+    b += align_up(sizeof(int) * static_cast<size_t>(s.B) * s.Clast);    // next
   }
   b += 2 * align_up(sizeof(float) * static_cast<size_t>(s.M) * s.maxC);  // dz ping-pong
   return b;
@@ -789,6 +783,14 @@ ActSrc layer_src(const pcuda_mlp_layer_t& y, int N) {
   return ActSrc{y.y, y.save_mean, y.save_invstd, y.gamma, y.beta, y.relu, nullptr, 0, 0, 0, N, y.cout};
 }
 
+// Which pieces run on the tensor cores.  TUNE_MLP_TC_MASK bits switch single pieces back to the
+// FP32 kernels (A/B runs, fault isolation): 1 forward, 2 pooled dgrad, 4 dense dgrad, 8 wgrad, 16 Gram.
+enum TcPiece { TC_FWD = 1, TC_POOL_DGRAD = 2, TC_DGRAD = 4, TC_WGRAD = 8, TC_GRAM = 16 };
+bool tc_on(int precision, int piece) {
+  if (precision != PCUDA_MLP_BF16 || tuning(TUNE_MLP_FORCE_FP32)) return false;
+  return (tuning(TUNE_MLP_TC_MASK) & piece) == 0;
+}
+
 }  // namespace
 }  // namespace pcuda
 
@@ -817,37 +819,50 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Carver cv(ws);
   double* stats = cv.take<double>(2 * static_cast<size_t>(s.sumC));
+  float* zeros = cv.take<float>(static_cast<size_t>(s.sumC) + 4);
   unsigned long long* keys = pool ? cv.take<unsigned long long>(static_cast<size_t>(B) * s.Clast) : nullptr;
+  const size_t zero_span = cv.off;   // stats, zeros and keys are contiguous: one memset
   float* pivots = cv.take<float>(static_cast<size_t>(s.sumC) + 4);
-  cudaMemsetAsync(stats, 0, sizeof(double) * 2 * s.sumC, st);
-  if (pool) cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * static_cast<size_t>(B) * s.Clast, st);
+  cudaMemsetAsync(stats, 0, zero_span, st);
 
+  const bool tcf = tc_on(precision, TC_FWD);
+  auto layer_tc = [&](int l) { return tcf && tc::supports(layers[l].cin); };
   const int tps = (N + TM - 1) / TM;
   double* st_l = stats;
   float* piv_l = pivots;
   int launches = 0;
-  // pivot of layer 0 (no BN to finalise yet)
-  bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, 0, 1.0, eps, momentum, train, nullptr, nullptr, nullptr, nullptr,
-                                               input_src(x, sxb, sxc, sxn, N, layers[0].cin), layers[0].weight, layers[0].bias,
-                                               layers[0].cout, piv_l);
-  launches += 1;
+  if (!layer_tc(0)) {
+    // pivot of layer 0 (no BN to finalise yet)
+    bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, 0, 1.0, eps, momentum, train, nullptr, nullptr, nullptr, nullptr,
+                                                 input_src(x, sxb, sxc, sxn, N, layers[0].cin), layers[0].weight, layers[0].bias,
+                                                 layers[0].cout, piv_l);
+    launches += 1;
+  }
   for (int l = 0; l < L; ++l) {
     const pcuda_mlp_layer_t& y = layers[l];
     const ActSrc src = l == 0 ? input_src(x, sxb, sxc, sxn, N, y.cin) : layer_src(layers[l - 1], N);
-    const dim3 grid(B * tps, (y.cout + TN - 1) / TN);
     const bool is_pool = pool && l == L - 1;
-    if (is_pool)
-      mlp_fwd_kernel<true><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, keys);
-    else
-      mlp_fwd_kernel<false><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, nullptr);
-    // finalise this layer's BN; if a dense layer follows, compute its pivot in the same launch
-    const bool has_next = l + 1 < L;
-    bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(st_l, piv_l, y.cout, static_cast<double>(s.M), eps, momentum, train,
+    const float* pivot_used = piv_l;
+    if (layer_tc(l)) {
+      // tensor-core layer: statistics are accumulated bias-free, i.e. centred on pivot = bias
+      if (int rc = tc::fwd_layer(src, y, is_pool, B, N, st_l, keys, st)) return rc;
+      pivot_used = y.bias ? y.bias : zeros;
+    } else {
+      const dim3 grid(B * tps, (y.cout + TN - 1) / TN);
+      if (is_pool)
+        mlp_fwd_kernel<true><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, keys);
+      else
+        mlp_fwd_kernel<false><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, nullptr);
+      launches += 1;
+    }
+    // finalise this layer's BN; if an FP32 layer follows, compute its pivot in the same launch
+    const bool next_piv = l + 1 < L && !layer_tc(l + 1);
+    bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(st_l, pivot_used, y.cout, static_cast<double>(s.M), eps, momentum, train,
                                                  y.save_mean, y.save_invstd, y.running_mean, y.running_var,
-                                                 has_next ? layer_src(y, N) : ActSrc{}, has_next ? layers[l + 1].weight : nullptr,
-                                                 has_next ? layers[l + 1].bias : nullptr, has_next ? layers[l + 1].cout : 0,
+                                                 next_piv ? layer_src(y, N) : ActSrc{}, next_piv ? layers[l + 1].weight : nullptr,
+                                                 next_piv ? layers[l + 1].bias : nullptr, next_piv ? layers[l + 1].cout : 0,
                                                  piv_l + y.cout);
-    launches += 2;
+    launches += 1;
     st_l += 2 * y.cout;
     piv_l += y.cout;
   }
@@ -885,7 +900,8 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
   float* kappa = cv.take<float>(s.sumC);
   float* partial = cv.take<float>(static_cast<size_t>(s.S) * s.maxWW);
   float *coef = nullptr, *gsel = nullptr, *gyh = nullptr, *Ghat = nullptr, *Q = nullptr, *abar = nullptr, *u = nullptr;
-  double *colsum = nullptr, *G = nullptr;
+  double *colsum = nullptr, *G = nullptr, *abar_d = nullptr;
+  int *head = nullptr, *next = nullptr;
   if (pool) {
     const size_t K = s.Kpool;
     coef = cv.take<float>(static_cast<size_t>(B) * s.Clast);
@@ -897,13 +913,17 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     Q = cv.take<float>(K * K);
     abar = cv.take<float>(K);
     u = cv.take<float>(K);
+    abar_d = cv.take<double>(K);
+    head = cv.take<int>(static_cast<size_t>(s.M));
+    next = cv.take<int>(static_cast<size_t>(B) * s.Clast);
   }
   float* dzbuf[2] = {cv.take<float>(static_cast<size_t>(s.M) * s.maxC), cv.take<float>(static_cast<size_t>(s.M) * s.maxC)};
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * s.sumC, st);
 
   std::vector<int> off(L + 1, 0);
   for (int l = 0; l < L; ++l) off[l + 1] = off[l] + layers[l].cout;
-  const int64_t chunk = (s.M + s.S - 1) / s.S;
+  const int S32 = splits_for(s.M);                       // FP32 contraction kernels
+  const int64_t chunk32 = (s.M + S32 - 1) / S32;
   auto src_of = [&](int l) { return l < 0 ? input_src(x, sxb, sxc, sxn, N, layers[0].cin) : layer_src(layers[l], N); };
   auto dgrad_out = [&](int lp, float* dzp) {  // epilogue target: previous layer lp (or input if lp < 0)
     DgradOut o{};
@@ -926,6 +946,7 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     float* al = alpha + off[L - 1];
     float* ka = kappa + off[L - 1];
     const int64_t bc = static_cast<int64_t>(B) * C;
+    const int64_t kk = static_cast<int64_t>(K) * K;
     pool_sel_kernel<<<static_cast<int>((bc * 32 + 255) / 256), 256, 0, st>>>(src, last.weight, last.bias, last.save_mean,
                                                                             last.save_invstd, last.gamma, last.relu, out, pool_arg,
                                                                             grad_out, B, N, C, coef, gsel, gyh);
@@ -933,15 +954,23 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     pool_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(gsel, gyh, last.save_invstd, last.gamma, B, C, count, train, al, ka,
                                                       want_last ? last.grad_gamma : nullptr, want_last ? last.grad_beta : nullptr,
                                                       want_last ? last.grad_bias : nullptr);
-    launches += 1;
-    act_colsum_kernel<<<dim3(s.S, (K + 127) / 128), 128, 0, st>>>(src, s.M, chunk, colsum);
-    point_contract_kernel<1><<<dim3(s.S, (K + TM - 1) / TM, (K + TN - 1) / TN), kThreads, 0, st>>>(DySrc{}, src, src, s.M, chunk, K, K, partial);
-    const int64_t kk = static_cast<int64_t>(K) * K;
-    reduce_partials_kernel<double><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(partial, kk, s.S, G);
-    gram_center_kernel<<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(colsum, s.S, G, K, count, abar, Ghat);
-    pool_q_kernel<<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(last.weight, ka, C, K, Q);
-    pool_u_kernel<<<(K + 127) / 128, 128, 0, st>>>(last.weight, al, Q, abar, C, K, u);
-    launches += 7;
+    launches += 2;
+    // centred Gram matrix of the pooled layer's input (train-mode BN correction terms only)
+    int Sg = S32;
+    if (tc_on(precision, TC_GRAM) && tc::pt_supports(K, K, true)) {
+      Sg = tc::pt_splits(s.M, (K + 127) / 128);
+      if (int rc = tc::gram(src, s.M, Sg, partial, colsum, st)) return rc;
+    } else {
+      act_colsum_kernel<<<dim3(S32, (K + 31) / 32), 256, 0, st>>>(src, s.M, chunk32, colsum);
+      point_contract_kernel<1><<<dim3(S32, (K + TM - 1) / TM, (K + TN - 1) / TN), kThreads, 0, st>>>(DySrc{}, src, src, s.M, chunk32, K, K, partial);
+      launches += 2;
+    }
+    reduce_partials_kernel<double><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(partial, kk, Sg, G);
+    abar_kernel<<<(K + 127) / 128, 128, 0, st>>>(colsum, Sg, K, count, abar, abar_d);
+    gram_center_kernel<<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(abar_d, G, K, count, Ghat);
+    pool_q_kernel<<<dim3((K + 31) / 32, (K + 31) / 32), 256, 0, st>>>(last.weight, ka, C, K, Q);
+    pool_u_kernel<<<(K + 31) / 32, 256, 0, st>>>(last.weight, al, Q, abar, C, K, u);
+    launches += 5;
     if (last.grad_weight) {
       const int64_t ck = static_cast<int64_t>(C) * K;
       pool_dw_kernel<<<static_cast<int>((ck + 255) / 256), 256, 0, st>>>(src, last.weight, coef, pool_arg, ka, abar, Ghat, B, N, C, train, last.grad_weight);
@@ -949,8 +978,15 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     }
     if (L >= 2 || grad_x) {
       const DgradOut o = dgrad_out(L - 2, dzbuf[cur]);
-      pool_dgrad_kernel<<<dim3(B * tps, (K + TN - 1) / TN), kThreads, 0, st>>>(src, Q, u, last.weight, coef, pool_arg, C, N, tps, o);
-      launches += 1;
+      if (tc_on(precision, TC_POOL_DGRAD) && tc::supports(K)) {
+        cudaMemsetAsync(head, 0xFF, sizeof(int) * static_cast<size_t>(s.M), st);
+        pool_invert_kernel<<<B, 1024, sizeof(int) * C, st>>>(pool_arg, coef, C, N, head, next);
+        launches += 1;
+        if (int rc = tc::pool_dgrad(src, Q, u, last.weight, coef, head, next, C, B, N, o, st)) return rc;
+      } else {
+        pool_dgrad_kernel<<<dim3(B * tps, (K + TN - 1) / TN), kThreads, 0, st>>>(src, Q, u, last.weight, coef, pool_arg, C, N, tps, o);
+        launches += 1;
+      }
     }
     top = L - 2;
   } else {
@@ -973,15 +1009,26 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     launches += 1;
     const DySrc dys{dzbuf[cur], y.y, y.save_mean, y.save_invstd, y.gamma, al, ka, C};
     if (want_w) {
-      point_contract_kernel<0><<<dim3(s.S, (C + TM - 1) / TM, (Kp + TN - 1) / TN), kThreads, 0, st>>>(dys, ActSrc{}, src_of(l - 1), s.M, chunk, C, Kp, partial);
       const int64_t ck = static_cast<int64_t>(C) * Kp;
-      reduce_partials_kernel<float><<<static_cast<int>((ck + 255) / 256), 256, 0, st>>>(partial, ck, s.S, y.grad_weight);
-      launches += 2;
+      int Sw = S32;
+      if (tc_on(precision, TC_WGRAD) && tc::pt_supports(C, Kp, false)) {
+        Sw = tc::pt_splits(s.M, (C + 127) / 128);
+        if (int rc = tc::wgrad_layer(dys, src_of(l - 1), s.M, Sw, partial, st)) return rc;
+      } else {
+        point_contract_kernel<0><<<dim3(S32, (C + TM - 1) / TM, (Kp + TN - 1) / TN), kThreads, 0, st>>>(dys, ActSrc{}, src_of(l - 1), s.M, chunk32, C, Kp, partial);
+        launches += 1;
+      }
+      reduce_partials_kernel<float><<<static_cast<int>((ck + 255) / 256), 256, 0, st>>>(partial, ck, Sw, y.grad_weight);
+      launches += 1;
     }
     if (l > 0 || grad_x) {
       const DgradOut o = dgrad_out(l - 1, dzbuf[cur ^ 1]);
-      dense_dgrad_kernel<<<dim3(B * tps, (Kp + TN - 1) / TN), kThreads, 0, st>>>(dys, y.weight, N, tps, o);
-      launches += 1;
+      if (tc_on(precision, TC_DGRAD) && tc::supports(C) && Kp >= 64 && (C % 8) == 0) {
+        if (int rc = tc::dgrad_layer(dys, y.weight, B, N, o, st)) return rc;
+      } else {
+        dense_dgrad_kernel<<<dim3(B * tps, (Kp + TN - 1) / TN), kThreads, 0, st>>>(dys, y.weight, N, tps, o);
+        launches += 1;
+      }
       cur ^= 1;
     }
   }

@@ -1,0 +1,110 @@
+// Shared between pointmlp.cu (FP32 CUDA-core kernels) and pointmlp_tc.cu (tcgen05 kernels):
+// how an activation / a pre-BN gradient is addressed and re-materialised on load.
+#pragma once
+#include "pcuda_common.cuh"
+
+namespace pcuda {
+
+// a_l[m, k] = relu?((y[m,k] - mean_k) * invstd_k * gamma_k + beta_k), or raw x for the network input
+struct ActSrc {
+  const float* y;  // [M, C] or nullptr -> raw input
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  const float* beta;
+  int relu;
+  const float* x;  // raw input, x[b*sxb + c*sxc + n*sxn]
+  int64_t sxb, sxc, sxn;
+  int N;
+  int C;
+};
+
+__device__ __forceinline__ float bn_act(float y, float mean, float invstd, float gamma, float beta, int relu) {
+  const float z = fmaf(y - mean, invstd * gamma, beta);
+  return relu ? fmaxf(z, 0.0f) : z;
+}
+
+// 4 consecutive channels k..k+3 of point m (zero beyond C). k % 4 == 0.
+__device__ __forceinline__ float4 load_act4(const ActSrc& s, int64_t m, int k) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s.y != nullptr) {
+    if (k + 3 < s.C) {
+      const float4 yy = *reinterpret_cast<const float4*>(s.y + m * s.C + k);
+      const float4 mu = *reinterpret_cast<const float4*>(s.mean + k);
+      const float4 is = *reinterpret_cast<const float4*>(s.invstd + k);
+      const float4 ga = *reinterpret_cast<const float4*>(s.gamma + k);
+      const float4 be = *reinterpret_cast<const float4*>(s.beta + k);
+      v.x = bn_act(yy.x, mu.x, is.x, ga.x, be.x, s.relu);
+      v.y = bn_act(yy.y, mu.y, is.y, ga.y, be.y, s.relu);
+      v.z = bn_act(yy.z, mu.z, is.z, ga.z, be.z, s.relu);
+      v.w = bn_act(yy.w, mu.w, is.w, ga.w, be.w, s.relu);
+    } else {
+      float* pv = &v.x;
+      for (int i = 0; i < 4 && k + i < s.C; ++i)
+        pv[i] = bn_act(s.y[m * s.C + k + i], s.mean[k + i], s.invstd[k + i], s.gamma[k + i], s.beta[k + i], s.relu);
+    }
+  } else {
+    const int64_t b = m / s.N, n = m - b * s.N;
+    const float* px = s.x + b * s.sxb + n * s.sxn;
+    float* pv = &v.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (k + i < s.C) pv[i] = __ldg(px + (k + i) * s.sxc);
+  }
+  return v;
+}
+
+__device__ __forceinline__ float load_act1(const ActSrc& s, int64_t m, int k) {
+  if (s.y != nullptr) return bn_act(s.y[m * s.C + k], s.mean[k], s.invstd[k], s.gamma[k], s.beta[k], s.relu);
+  const int64_t b = m / s.N, n = m - b * s.N;
+  return __ldg(s.x + b * s.sxb + n * s.sxn + k * s.sxc);
+}
+
+// dy_l[m, c] = s_c*dz[m,c] - alpha_c - kappa_c*(y[m,c] - mean_c)   (train-mode BN backward; in
+// eval mode alpha = kappa = 0).  s_c = gamma_c * invstd_c.
+struct DySrc {
+  const float* dz;  // [M, C]
+  const float* y;   // [M, C]
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  const float* alpha;
+  const float* kappa;
+  int C;
+};
+
+__device__ __forceinline__ float4 load_dy4(const DySrc& s, int64_t m, int c) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* pv = &v.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cc = c + i;
+    if (cc < s.C) {
+      const float sc = s.gamma[cc] * s.invstd[cc];
+      pv[i] = fmaf(sc, s.dz[m * s.C + cc], -s.alpha[cc]) - s.kappa[cc] * (s.y[m * s.C + cc] - s.mean[cc]);
+    }
+  }
+  return v;
+}
+
+
+// Target of a dgrad epilogue: val -> (ReLU mask of the producing layer) -> store
+// dz_prev + accumulate that layer's dbeta / dgamma sums; or, for the network input, store grad_x.
+struct DgradOut {
+  float* dz_prev;        // [M, Cp] or nullptr
+  const float* y_prev;   // [M, Cp] pre-BN of the previous layer (mask + yhat)
+  const float* mean; const float* invstd; const float* gamma; const float* beta;
+  int relu;
+  double* sums;          // [2*Cp]: dbeta, dgamma of the previous layer
+  float* grad_x;         // [B, Cp, N] when the previous "layer" is the input
+  int Cp;
+};
+
+// Order-preserving (value, first-index) key for the fused global max-pool: larger value wins,
+// then the smaller point index.
+__device__ __forceinline__ unsigned long long pool_key(float v, int n) {
+  return (static_cast<unsigned long long>(float_to_ordered(v)) << 32) |
+         static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<unsigned int>(n));
+}
+
+}  // namespace pcuda

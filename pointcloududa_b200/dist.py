@@ -61,6 +61,13 @@ class GradBucket:
     def zero(self) -> None:
         self.flat.zero_()
 
+    def accumulate(self, grads: Sequence[Optional[torch.Tensor]]) -> None:
+        """bucket += grads (as returned by torch.autograd.grad over self.params; None = zero)."""
+        vs = [v for v, g in zip(self.views, grads) if g is not None]
+        gs = [g.reshape(v.shape) for v, g in zip(self.views, grads) if g is not None]
+        if vs:
+            torch._foreach_add_(vs, gs)
+
     def gather_grads(self) -> None:
         """Copy .grad tensors that are not already views of the bucket into it."""
         for p, v in zip(self.params, self.views):

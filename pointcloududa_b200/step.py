@@ -62,6 +62,7 @@ class AdversarialStep:
                               precision=cfg.precision).to(device).train()
         # optim_dis4 of the reference: SGD, momentum .99, weight decay 5e-4 (train_mscmrseg.py:450-455)
         self.opt = torch.optim.SGD(self.d4.parameters(), lr=cfg.lr_dis, momentum=0.99, weight_decay=0.0005)
+        self._pnames = [n for n, _ in self.d4.named_parameters()]
         self.bucket = pdist.GradBucket(self.d4.parameters())
         B, C, H, W, N = cfg.B, cfg.C, cfg.H, cfg.W, cfg.N
         f32 = dict(dtype=torch.float32, device=device)
@@ -91,6 +92,11 @@ class AdversarialStep:
     def _set_requires_grad(self, flag: bool) -> None:
         for p in self.d4.parameters():
             p.requires_grad = flag
+
+    def _d4_fresh(self, x: torch.Tensor):
+        leaves = [p.detach().requires_grad_(True) for p in self.bucket.params]
+        out = torch.func.functional_call(self.d4, dict(zip(self._pnames, leaves)), (x,))[0]
+        return out, leaves
 
     # -- the step -----------------------------------------------------------------------------------
     def _body(self) -> None:
@@ -123,26 +129,28 @@ class AdversarialStep:
         self.grad_vertT.copy_(gT)
         res += [loss_vert_target.detach(), ent_mean.detach(), loss_adv_point.detach()]
 
-        # P3: discriminators on the source domain (label 1)
+        # P3: discriminators on the source domain (label 1).  D4 runs on fresh leaf views of its
+        # parameters (functional_call): their gradient-accumulator nodes are created on the stream
+        # the step runs on, so the step is legal under CUDA-graph capture on a side stream, and
+        # the gradients are summed straight into the flat bucket.
         self._set_requires_grad(True)
-        self.bucket.attach()
         with torch.no_grad():
             entropy_map(I["oS"], activation=cfg.activation, normalize=cfg.normalize,
                         return_prob=cfg.return_prob)
-        D_out4 = self.d4(I["vertS"].transpose(2, 1))[0]
+        D_out4, leaves = self._d4_fresh(I["vertS"].transpose(2, 1))
         loss_D_same4 = F.binary_cross_entropy_with_logits(D_out4, self._ones)
-        loss_D_same4.backward()
+        self.bucket.accumulate(torch.autograd.grad(loss_D_same4, leaves, allow_unused=True))
         acc_s = (torch.sigmoid(D_out4.detach()) >= 0.5).float().mean()
 
         # P4: discriminators on the target domain (label 0)
-        D_out4 = self.d4(I["vertT"].transpose(2, 1))[0]
+        D_out4, leaves = self._d4_fresh(I["vertT"].transpose(2, 1))
         loss_D_diff_4 = F.binary_cross_entropy_with_logits(D_out4, self._zeros)
-        loss_D_diff_4.backward()
+        self.bucket.accumulate(torch.autograd.grad(loss_D_diff_4, leaves, allow_unused=True))
         acc_t = 1.0 - (torch.sigmoid(D_out4.detach()) >= 0.5).float().mean()
         res += [loss_D_same4.detach(), loss_D_diff_4.detach(), acc_s, acc_t]
 
         # P5: gradient all-reduce (one bucket) + SGD step
-        self.bucket.gather_grads()
+        self.bucket.attach()
         self.bucket.allreduce_mean()
         self.opt.step()
         self.result.copy_(torch.stack([r.reshape(()).float() for r in res]))
