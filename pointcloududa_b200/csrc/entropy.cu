@@ -29,29 +29,53 @@ struct MeanWs {
 };
 static_assert(sizeof(MeanWs) == PCUDA_ENTROPY_WS_BYTES, "workspace layout");
 
-// log(t) for t in (0, 2].  FAST: lg2.approx (abs err 2^-22 in log2 on (0.5,2), rel 2^-22 outside)
-// with a degree-6 log1p polynomial on |t-1| < 1/16, where the approx's absolute error would
-// dominate the (tiny) map value.  Max rel. error ~3e-6 at the seam, <2e-7 elsewhere.
+// Two arithmetic flavours, selected per call (pcuda_tune key 0):
+//   FAST (default)  MUFU-based: ex2.approx / lg2.approx / rcp.approx.  exp and the reciprocal are
+//                   within ~2 ulp; lg2.approx has an ABSOLUTE error of 2^-22 in log2 on [0.5, 2],
+//                   i.e. <= 1.7e-7 on a map entry — inside the 1e-5*|m| + 5e-7 parity band
+//                   (the reference itself is 1.6e-7 off fp64) at ~11 instructions
+//                   per element, which leaves the kernel HBM-bound.
+//   precise         libdevice expf/logf and IEEE reciprocal (~45 instructions per element,
+//                   issue-bound on B200); kept as the cross-check.
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
 template <bool FAST>
 __device__ __forceinline__ float pc_log(float t) {
-  if constexpr (!FAST) {
-    return logf(t);
-  } else {
-    float u = t - 1.0f;  // exact for t in [0.5, 2]
-    float poly = fmaf(u, -1.0f / 6.0f, 0.2f);
-    poly = fmaf(u, poly, -0.25f);
-    poly = fmaf(u, poly, 1.0f / 3.0f);
-    poly = fmaf(u, poly, -0.5f);
-    poly = fmaf(u, poly, 1.0f);
-    poly *= u;
-    float l = __log2f(t) * 0.6931471805599453f;
-    return (fabsf(u) < 0.0625f) ? poly : l;
-  }
+  if constexpr (!FAST) return logf(t);
+  else return mufu_lg2(t) * kLn2;
 }
-
+// exp(x - mx): softmax numerator
+template <bool FAST>
+__device__ __forceinline__ float pc_exp_sub(float x, float mx) {
+  if constexpr (!FAST) return expf(x - mx);
+  else return mufu_ex2((x - mx) * kLog2e);
+}
+template <bool FAST>
+__device__ __forceinline__ float pc_rcp(float x) {
+  if constexpr (!FAST) return __frcp_rn(x);
+  else return mufu_rcp(x);
+}
+template <bool FAST>
 __device__ __forceinline__ float pc_sigmoid(float z) {
-  // 1/(1+exp(-z)) as ATen evaluates it; expf overflow -> inf -> 0 is the reference behaviour too.
-  return __frcp_rn(1.0f + expf(-z));
+  // 1/(1+exp(-z)) as ATen evaluates it; exp overflow -> inf -> 0 is the reference behaviour too.
+  if constexpr (!FAST) return __frcp_rn(1.0f + expf(-z));
+  else return mufu_rcp(1.0f + mufu_ex2(-z * kLog2e));
 }
 
 // Finalise the mean-entropy scalar: every block adds its partial, the last one to take a ticket
@@ -89,10 +113,13 @@ entropy_fwd_vec4(const float* __restrict__ z, float* __restrict__ m, float* __re
                  int64_t quads_per_img, int64_t HW, float inv_norm, float smooth,
                  double inv_count) {
   float local = 0.0f;
-  for (int64_t q = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; q < n_quads;
-       q += static_cast<int64_t>(gridDim.x) * kThreads) {
-    const int64_t b = q / quads_per_img;
-    const int64_t r = q - b * quads_per_img;
+  // (image, quad-in-image) advance incrementally: no 64-bit division inside the streaming loop
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  int64_t q = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x;
+  int64_t b = q / quads_per_img;
+  int64_t r = q - b * quads_per_img;
+  for (; q < n_quads; q += stride, r += stride) {
+    while (r >= quads_per_img) { r -= quads_per_img; ++b; }
     const int64_t base = b * C * HW + r * 4;
     float4 v[C];
 #pragma unroll
@@ -108,12 +135,12 @@ entropy_fwd_vec4(const float* __restrict__ z, float* __restrict__ m, float* __re
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        v[c].x = expf(v[c].x - mx.x); v[c].y = expf(v[c].y - mx.y);
-        v[c].z = expf(v[c].z - mx.z); v[c].w = expf(v[c].w - mx.w);
+        v[c].x = pc_exp_sub<FAST>(v[c].x, mx.x); v[c].y = pc_exp_sub<FAST>(v[c].y, mx.y);
+        v[c].z = pc_exp_sub<FAST>(v[c].z, mx.z); v[c].w = pc_exp_sub<FAST>(v[c].w, mx.w);
         s.x += v[c].x; s.y += v[c].y; s.z += v[c].z; s.w += v[c].w;
       }
       // ATen divides exp by the sum; a correctly rounded reciprocal + multiply is within 1 ulp.
-      const float4 inv = make_float4(__frcp_rn(s.x), __frcp_rn(s.y), __frcp_rn(s.z), __frcp_rn(s.w));
+      const float4 inv = make_float4(pc_rcp<FAST>(s.x), pc_rcp<FAST>(s.y), pc_rcp<FAST>(s.z), pc_rcp<FAST>(s.w));
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         v[c].x *= inv.x; v[c].y *= inv.y; v[c].z *= inv.z; v[c].w *= inv.w;
@@ -121,8 +148,8 @@ entropy_fwd_vec4(const float* __restrict__ z, float* __restrict__ m, float* __re
     } else {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        v[c].x = pc_sigmoid(v[c].x); v[c].y = pc_sigmoid(v[c].y);
-        v[c].z = pc_sigmoid(v[c].z); v[c].w = pc_sigmoid(v[c].w);
+        v[c].x = pc_sigmoid<FAST>(v[c].x); v[c].y = pc_sigmoid<FAST>(v[c].y);
+        v[c].z = pc_sigmoid<FAST>(v[c].z); v[c].w = pc_sigmoid<FAST>(v[c].w);
       }
     }
 #pragma unroll
@@ -156,12 +183,12 @@ entropy_fwd_generic(const float* __restrict__ z, float* __restrict__ m, float* _
     if (ACT == PCUDA_ACT_SOFTMAX) {
       for (int c = 0; c < C; ++c) mx = fmaxf(mx, z[base + c * HW]);
       float s = 0.0f;
-      for (int c = 0; c < C; ++c) s += expf(z[base + c * HW] - mx);
-      inv = __frcp_rn(s);
+      for (int c = 0; c < C; ++c) s += pc_exp_sub<FAST>(z[base + c * HW], mx);
+      inv = pc_rcp<FAST>(s);
     }
     for (int c = 0; c < C; ++c) {
       const float zz = z[base + c * HW];
-      const float p = (ACT == PCUDA_ACT_SOFTMAX) ? expf(zz - mx) * inv : pc_sigmoid(zz);
+      const float p = (ACT == PCUDA_ACT_SOFTMAX) ? pc_exp_sub<FAST>(zz, mx) * inv : pc_sigmoid<FAST>(zz);
       if (p_out) p_out[base + c * HW] = p;
       const float e = (-p) * pc_log<FAST>(p + smooth) * inv_norm;
       m[base + c * HW] = e;
@@ -177,7 +204,7 @@ entropy_fwd_generic(const float* __restrict__ z, float* __restrict__ m, float* _
 template <bool FAST>
 __device__ __forceinline__ float entropy_t(float p, float g, float inv_norm, float smooth) {
   const float ps = p + smooth;
-  return -inv_norm * g * (pc_log<FAST>(ps) + __fdividef(p, ps));
+  return -inv_norm * g * (pc_log<FAST>(ps) + p * pc_rcp<FAST>(ps));
 }
 
 template <int ACT, int C, bool HAS_GM, bool HAS_GP, bool FAST>
@@ -187,10 +214,13 @@ entropy_bwd_vec4(const float* __restrict__ z, const float* __restrict__ grad_m,
                  float* __restrict__ grad_z, int64_t n_quads, int64_t quads_per_img, int64_t HW,
                  float inv_norm, float smooth, float inv_count) {
   const float gs = grad_mean ? __ldg(grad_mean) * inv_count : 0.0f;
-  for (int64_t q = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; q < n_quads;
-       q += static_cast<int64_t>(gridDim.x) * kThreads) {
-    const int64_t b = q / quads_per_img;
-    const int64_t r = q - b * quads_per_img;
+  // (image, quad-in-image) advance incrementally: no 64-bit division inside the streaming loop
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  int64_t q = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x;
+  int64_t b = q / quads_per_img;
+  int64_t r = q - b * quads_per_img;
+  for (; q < n_quads; q += stride, r += stride) {
+    while (r >= quads_per_img) { r -= quads_per_img; ++b; }
     const int64_t base = b * C * HW + r * 4;
     float4 v[C];
 #pragma unroll
@@ -205,11 +235,11 @@ entropy_bwd_vec4(const float* __restrict__ z, const float* __restrict__ grad_m,
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        v[c].x = expf(v[c].x - mx.x); v[c].y = expf(v[c].y - mx.y);
-        v[c].z = expf(v[c].z - mx.z); v[c].w = expf(v[c].w - mx.w);
+        v[c].x = pc_exp_sub<FAST>(v[c].x, mx.x); v[c].y = pc_exp_sub<FAST>(v[c].y, mx.y);
+        v[c].z = pc_exp_sub<FAST>(v[c].z, mx.z); v[c].w = pc_exp_sub<FAST>(v[c].w, mx.w);
         s.x += v[c].x; s.y += v[c].y; s.z += v[c].z; s.w += v[c].w;
       }
-      const float4 inv = make_float4(__frcp_rn(s.x), __frcp_rn(s.y), __frcp_rn(s.z), __frcp_rn(s.w));
+      const float4 inv = make_float4(pc_rcp<FAST>(s.x), pc_rcp<FAST>(s.y), pc_rcp<FAST>(s.z), pc_rcp<FAST>(s.w));
       float4 dot = make_float4(0.f, 0.f, 0.f, 0.f);
       float4 t[C];
 #pragma unroll
@@ -250,10 +280,10 @@ entropy_bwd_vec4(const float* __restrict__ z, const float* __restrict__ grad_m,
         if constexpr (HAS_GP) gp = ld_stream4(grad_p + base + c * HW);
         float4 o;
         float p;
-        p = pc_sigmoid(v[c].x); o.x = (entropy_t<FAST>(p, g.x, inv_norm, smooth) + gp.x) * p * (1.0f - p);
-        p = pc_sigmoid(v[c].y); o.y = (entropy_t<FAST>(p, g.y, inv_norm, smooth) + gp.y) * p * (1.0f - p);
-        p = pc_sigmoid(v[c].z); o.z = (entropy_t<FAST>(p, g.z, inv_norm, smooth) + gp.z) * p * (1.0f - p);
-        p = pc_sigmoid(v[c].w); o.w = (entropy_t<FAST>(p, g.w, inv_norm, smooth) + gp.w) * p * (1.0f - p);
+        p = pc_sigmoid<FAST>(v[c].x); o.x = (entropy_t<FAST>(p, g.x, inv_norm, smooth) + gp.x) * p * (1.0f - p);
+        p = pc_sigmoid<FAST>(v[c].y); o.y = (entropy_t<FAST>(p, g.y, inv_norm, smooth) + gp.y) * p * (1.0f - p);
+        p = pc_sigmoid<FAST>(v[c].z); o.z = (entropy_t<FAST>(p, g.z, inv_norm, smooth) + gp.z) * p * (1.0f - p);
+        p = pc_sigmoid<FAST>(v[c].w); o.w = (entropy_t<FAST>(p, g.w, inv_norm, smooth) + gp.w) * p * (1.0f - p);
         st_stream4(grad_z + base + c * HW, o);
       }
     }
@@ -275,10 +305,10 @@ entropy_bwd_generic(const float* __restrict__ z, const float* __restrict__ grad_
     if (ACT == PCUDA_ACT_SOFTMAX) {
       for (int c = 0; c < C; ++c) mx = fmaxf(mx, z[base + c * HW]);
       float s = 0.0f;
-      for (int c = 0; c < C; ++c) s += expf(z[base + c * HW] - mx);
-      inv = __frcp_rn(s);
+      for (int c = 0; c < C; ++c) s += pc_exp_sub<FAST>(z[base + c * HW], mx);
+      inv = pc_rcp<FAST>(s);
       for (int c = 0; c < C; ++c) {
-        const float p = expf(z[base + c * HW] - mx) * inv;
+        const float p = pc_exp_sub<FAST>(z[base + c * HW], mx) * inv;
         const float g = gs + (grad_m ? grad_m[base + c * HW] : 0.0f);
         float t = entropy_t<FAST>(p, g, inv_norm, smooth);
         if (grad_p) t += grad_p[base + c * HW];
@@ -287,7 +317,7 @@ entropy_bwd_generic(const float* __restrict__ z, const float* __restrict__ grad_
     }
     for (int c = 0; c < C; ++c) {
       const float zz = z[base + c * HW];
-      const float p = (ACT == PCUDA_ACT_SOFTMAX) ? expf(zz - mx) * inv : pc_sigmoid(zz);
+      const float p = (ACT == PCUDA_ACT_SOFTMAX) ? pc_exp_sub<FAST>(zz, mx) * inv : pc_sigmoid<FAST>(zz);
       const float g = gs + (grad_m ? grad_m[base + c * HW] : 0.0f);
       float t = entropy_t<FAST>(p, g, inv_norm, smooth);
       if (grad_p) t += grad_p[base + c * HW];
@@ -408,7 +438,7 @@ extern "C" int pcuda_entropy_fwd(const float* z, float* m, float* p, float* mean
   }
   PCUDA_REQUIRE(z && m, PCUDA_E_NULL, "entropy_fwd: z/m is NULL");
   FwdArgs a{z, m, p, mean_out, static_cast<MeanWs*>(ws), B, C, HW, inv_norm, smooth, static_cast<cudaStream_t>(stream)};
-  const bool fast = tuning(TUNE_ENTROPY_FAST_LOG) != 0;
+  const bool fast = tuning(TUNE_ENTROPY_PRECISE) == 0;
   const bool ptr_ok = aligned16(z) && aligned16(m) && (!p || aligned16(p));
   int rc = -100;
   if (activation == PCUDA_ACT_SIGMOID) {
@@ -461,7 +491,7 @@ extern "C" int pcuda_entropy_bwd(const float* z, const float* grad_m, const floa
   if (n_pix == 0) return 0;
   PCUDA_REQUIRE(z && grad_z, PCUDA_E_NULL, "entropy_bwd: z/grad_z is NULL");
   BwdArgs a{z, grad_m, grad_p, grad_mean, grad_z, B, C, HW, inv_norm, smooth, static_cast<cudaStream_t>(stream)};
-  const bool fast = tuning(TUNE_ENTROPY_FAST_LOG) != 0;
+  const bool fast = tuning(TUNE_ENTROPY_PRECISE) == 0;
   const bool ptr_ok = aligned16(z) && aligned16(grad_z) && (!grad_m || aligned16(grad_m)) && (!grad_p || aligned16(grad_p));
   const float invc = static_cast<float>(1.0 / static_cast<double>(n_pix));
   if (activation == PCUDA_ACT_SIGMOID) {

@@ -286,7 +286,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const WsParams p) {
       if (MODE != FWD_POOL || b < 0) return;
       for (int cb = 0; cb < p.CB; ++cb) {
         const int r = row_base + cb * 128 + q * 32 + lane;
-        if (r < p.R) atomicMax(&p.keys[static_cast<int64_t>(b) * p.R + r], pool_key(best[cb], besti[cb]));
+        if (r < p.R) {
+          // the running maximum is over the bias-free accumulator times sign(gamma); the key holds
+          // sign(gamma) * (y + bias), what pool_finalize_kernel expects
+          const float gm = p.gamma[r];
+          const float sg = gm > 0.f ? 1.f : (gm < 0.f ? -1.f : 0.f);
+          const float bv = p.bias ? p.bias[r] : 0.f;
+          atomicMax(&p.keys[static_cast<int64_t>(b) * p.R + r], pool_key(best[cb] + sg * bv, besti[cb]));
+        }
         best[cb] = -INFINITY; besti[cb] = 0;
       }
     };

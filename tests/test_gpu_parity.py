@@ -279,17 +279,41 @@ def test_chamfer_backward_deterministic_and_no_grad():
 def _torch_stack(x, layers, pool, train, dtype):
     """Plain-torch restatement of a Conv1d(k=1)+BatchNorm1d(+ReLU) stack (+max over points)."""
     a = x.to(dtype)
+    margin = float("inf")      # smallest |BN output| entering a ReLU: how close any unit is to switching
     for Ld in layers:
         a = F.conv1d(a, Ld["weight"].to(dtype).reshape(Ld["weight"].shape[0], -1, 1), Ld["bias"].to(dtype))
         a = F.batch_norm(a, Ld["rm"].to(dtype), Ld["rv"].to(dtype), Ld["gamma"].to(dtype), Ld["beta"].to(dtype),
                          training=train, momentum=0.1, eps=1e-5)
         if Ld["relu"]:
+            nz = a.detach().abs()
+            nz = nz[:, Ld["gamma"].detach() != 0]          # gamma == 0 channels are constant: no switch possible
+            if nz.numel():
+                margin = min(margin, nz.min().item())
             a = F.relu(a)
+    _torch_stack.margin = margin
     return (a.max(dim=2)[0] if pool else a), a
 
 
 def _run_stack_case(chans, relus, B, N, pool, seed, train=True, precision="fp32", zero_gamma=False, tol=2e-5, gtol=2e-4,
                     check_grads=True):
+    """Compare against an fp64 torch evaluation.  A ReLU whose input is within fp32 rounding of 0
+    may switch between the two evaluations, which changes gradients discontinuously; instances
+    are therefore drawn (deterministically: seed, seed+7919, ...) until no ReLU input of the
+    fp64 evaluation is that close to 0."""
+    for attempt in range(40):
+        try:
+            return _run_stack_instance(chans, relus, B, N, pool, seed + 7919 * attempt, train, precision, zero_gamma,
+                                       tol, gtol, check_grads)
+        except _NearSwitch:
+            continue
+    raise AssertionError("no switch-free instance found")
+
+
+class _NearSwitch(Exception):
+    pass
+
+
+def _run_stack_instance(chans, relus, B, N, pool, seed, train, precision, zero_gamma, tol, gtol, check_grads):
     from pointcloududa_b200.networks.PointNetCls import shared_mlp
     import torch.nn as nn
     rs = np.random.RandomState(seed)
@@ -318,6 +342,8 @@ def _run_stack_case(chans, relus, B, N, pool, seed, train=True, precision="fp32"
             Ld[k].requires_grad_(True)
     xr = pts.transpose(2, 1).double().detach().requires_grad_(True)
     out_r, pre = _torch_stack(xr, ref_layers, pool, train, torch.float64)
+    if check_grads and _torch_stack.margin < 4e-6:
+        raise _NearSwitch()
     w = torch.from_numpy(rs.standard_normal(tuple(out_r.shape))).to(DEV)
     if pool and N > 1:
         # A (cloud, channel) whose two largest values are closer than fp32 can resolve may select
@@ -335,14 +361,7 @@ def _run_stack_case(chans, relus, B, N, pool, seed, train=True, precision="fp32"
     if not check_grads:
         assert torch.isfinite(x.grad).all()
         return out
-    # A ReLU whose pre-activation is within rounding of 0 may legitimately switch between this fp32
-    # evaluation and the fp64 reference; that moves the gradient of ONE point by O(1/width).  So:
-    # almost every element within gtol, and the whole tensor within a small L2 error.
-    gx, gxr = x.grad.double().cpu(), xr.grad.cpu()
-    scale = gxr.abs().max().item()
-    frac_bad = ((gx - gxr).abs() > gtol * scale).double().mean().item()
-    assert frac_bad <= 2e-3, frac_bad
-    assert ((gx - gxr).norm() / gxr.norm()).item() < 25 * gtol
+    assert max_rel(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < gtol
     for c, b, Ld in zip(convs, bns, ref_layers):
         assert max_rel(c.weight.grad.cpu().numpy().reshape(Ld["weight"].shape), Ld["weight"].grad.cpu().numpy()) < gtol
         # gamma/beta gradients can be mathematically zero (a BN without ReLU feeding another
