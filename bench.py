@@ -291,7 +291,7 @@ def run_ours(args):
     l0 = ops.launch_count(); step.run(); torch.cuda.synchronize()
     launches_per_step = ops.launch_count() - l0
 
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph
     if use_graph:
         step.capture(warmup=2)
     for _ in range(max(args.warmup, 3)):

@@ -52,8 +52,11 @@ const char* pcuda_last_error_string(void);
 const char* pcuda_error_name(int code);
 /* SM count of the current device (cached); used by callers to size benchmarks. */
 int pcuda_sm_count(void);
-/* Benchmark-only knob for A/B-ing kernel variants (key, value); not part of the reference-facing
- * contract.  Keys: 0 = entropy fast-log (0/1), 1 = chamfer rows*1000+threads, 2 = force fp32 MLP. */
+/* Benchmark / fault-isolation knob for A/B-ing kernel variants (key, value); not part of the
+ * reference-facing contract.  Keys: 0 = entropy arithmetic (0 MUFU fast path, 1 libdevice precise),
+ * 1 = chamfer rows*1000+threads (+100000: scalar variant), 2 = force the FP32 MLP kernels,
+ * 3 = bit mask of MLP pieces switched from tcgen05 back to FP32 (1 forward, 2 pooled dgrad,
+ * 4 dense dgrad, 8 wgrad, 16 Gram). */
 int pcuda_tune(int key, int value);
 /* Number of kernels this library has launched in this process (monotone; for bench accounting). */
 uint64_t pcuda_launch_count(void);

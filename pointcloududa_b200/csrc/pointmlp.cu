@@ -398,24 +398,32 @@ __global__ void gram_center_kernel(const double* __restrict__ abar_d, const doub
   Ghat[i] = static_cast<float>(G[i] - count * abar_d[k] * abar_d[k2]);
 }
 
-// Q[k,k'] = sum_c kappa_c W[c,k] W[c,k'].  grid (K/32, K/32), 256 threads, each 2x2 outputs;
-// the 32 x 32 output tile walks over all C channels in chunks of 32 staged in shared memory.
+// Q[k,k'] = sum_c kappa_c W[c,k] W[c,k'].  grid (K/32, K/32, CS), 256 threads, each 2x2 outputs; slice z
+// of the channels goes to partial[z] (reduced in a fixed order by reduce_partials_kernel).  The 32 x 32
+// output tile walks over its channels in chunks of 32 staged in shared memory.
+constexpr int kPoolQSplits = 8;
 __global__ void __launch_bounds__(256)
-pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, int C, int K, float* __restrict__ Q) {
+pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, int C, int K, float* __restrict__ partial) {
   __shared__ float Wa[32][33], Wb[32][33];
   const int k0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const int per = (C + gridDim.z - 1) / gridDim.z;
+  const int cbeg = blockIdx.z * per, cend = min(C, cbeg + per);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int lr = threadIdx.x >> 5, lc = threadIdx.x & 31;   // loader: 8 rows x 32 columns per pass
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int c0 = 0; c0 < C; c0 += 32) {
+  for (int c0 = cbeg; c0 < cend; c0 += 32) {
+    float ra[4], rb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + lr + 8 * i;
+      const bool ok = c < cend;
+      const float kp = ok ? kappa[c] : 0.f;
+      ra[i] = (ok && k0 + lc < K) ? kp * W[static_cast<int64_t>(c) * K + k0 + lc] : 0.f;
+      rb[i] = (ok && j0 + lc < K) ? W[static_cast<int64_t>(c) * K + j0 + lc] : 0.f;
+    }
     __syncthreads();
 #pragma unroll
-    for (int r = lr; r < 32; r += 8) {
-      const int c = c0 + r;
-      const float kp = c < C ? kappa[c] : 0.f;
-      Wa[r][lc] = (c < C && k0 + lc < K) ? kp * W[static_cast<int64_t>(c) * K + k0 + lc] : 0.f;
-      Wb[r][lc] = (c < C && j0 + lc < K) ? W[static_cast<int64_t>(c) * K + j0 + lc] : 0.f;
-    }
+    for (int i = 0; i < 4; ++i) { Wa[lr + 8 * i][lc] = ra[i]; Wb[lr + 8 * i][lc] = rb[i]; }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 32; ++r) {
@@ -424,6 +432,7 @@ pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, int 
       acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
     }
   }
+  float* Q = partial + static_cast<int64_t>(blockIdx.z) * K * K;
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -433,52 +442,78 @@ pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, int 
     }
 }
 
-// u'[k] = sum_c alpha_c W[c,k] - sum_k' Q[k',k] abar_k'.  grid K/32, 256 threads: lane = k, the 8 warps
+// u'[k] = sum_c alpha_c W[c,k] - sum_k' Q[k',k] abar_k'.  grid K/32, 1024 threads: lane = k, the 32 warps
 // interleave the summation index; partial sums are combined in a fixed order.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 pool_u_kernel(const float* __restrict__ W, const float* __restrict__ alpha, const float* __restrict__ Q,
               const float* __restrict__ abar, int C, int K, float* __restrict__ u) {
-  __shared__ double part[8][33];
+  __shared__ double part[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
   double s = 0.0;
   if (k < K) {
-    for (int c = warp; c < C; c += 8) s += static_cast<double>(alpha[c]) * static_cast<double>(W[static_cast<int64_t>(c) * K + k]);
-    for (int k2 = warp; k2 < K; k2 += 8) s -= static_cast<double>(Q[static_cast<int64_t>(k2) * K + k]) * static_cast<double>(abar[k2]);
+    float f = 0.f;
+#pragma unroll 8
+    for (int c = warp; c < C; c += 32) f = fmaf(alpha[c], W[static_cast<int64_t>(c) * K + k], f);
+    s = static_cast<double>(f);
+    f = 0.f;
+#pragma unroll 8
+    for (int k2 = warp; k2 < K; k2 += 32) f = fmaf(Q[static_cast<int64_t>(k2) * K + k], abar[k2], f);
+    s -= static_cast<double>(f);
   }
   part[warp][lane] = s;
   __syncthreads();
   if (warp == 0 && k < K) {
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    for (int w = 0; w < 32; ++w) t += part[w][lane];
     u[k] = static_cast<float>(t);
   }
 }
 
-// Inverted index of the max-pool selection of one cloud: for every point the ascending list of
-// channels whose arg-max it is (channels with a zero coefficient are left out).
-//   head[b*N + n] = first such channel or -1 (head must be pre-filled with -1); next[b*C + c] = next or -1
+// Sparse part of the pooled layer's dgrad, aggregated per selected point:
+//   srows[b, h, :] = sum_{c : arg[b,c] == n, coef != 0} coef[b,c] * W[c, :]     (ascending c: deterministic)
+//   head[b*N + n]  = h = the lowest such channel          (head must be pre-filled with -1)
+// grid (B, parts), 1024 threads; dynamic smem: C + N ints.  A warp owns a head channel, finds the other
+// channels selecting the same point with ballots over the shared-memory copy of arg, and sums their rows.
 __global__ void __launch_bounds__(1024)
-pool_invert_kernel(const int32_t* __restrict__ arg, const float* __restrict__ coef, int C, int N,
-                   int* __restrict__ head, int* __restrict__ next) {
-  extern __shared__ int sarg[];
+pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ coef, const float* __restrict__ W,
+                   int C, int N, int K, int* __restrict__ head, float* __restrict__ srows) {
+  extern __shared__ int sm_i[];
+  int* sarg = sm_i;
+  int* first = sm_i + C;
   const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c = threadIdx.x; c < C; c += blockDim.x)
     sarg[c] = coef[static_cast<int64_t>(b) * C + c] != 0.f ? arg[static_cast<int64_t>(b) * C + c] : -1;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) first[n] = 0x7fffffff;
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    if (sarg[c] >= 0) atomicMin(&first[sarg[c]], c);
+  __syncthreads();
+  const int stride = 32 * gridDim.y;
+  for (int c = blockIdx.y * 32 + warp; c < C; c += stride) {
     const int a = sarg[c];
-    int nx = -1;
-    if (a >= 0) {
-      for (int c2 = c + 1; c2 < C; ++c2)
-        if (sarg[c2] == a) { nx = c2; break; }
-      bool is_head = true;
-      for (int c2 = c - 1; c2 >= 0; --c2)
-        if (sarg[c2] == a) { is_head = false; break; }
-      if (is_head) head[static_cast<int64_t>(b) * N + a] = c;
+    if (a < 0 || first[a] != c) continue;      // warp-uniform
+    if (lane == 0) head[static_cast<int64_t>(b) * N + a] = c;
+    float acc[16];
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.f;
+    for (int c0 = c & ~31; c0 < C; c0 += 32) {
+      const int cc = c0 + lane;
+      unsigned mask = __ballot_sync(0xffffffffu, cc >= c && cc < C && sarg[cc] == a);
+      while (mask) {
+        const int c2 = c0 + __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float cf = coef[static_cast<int64_t>(b) * C + c2];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj)
+          if (lane + 32 * jj < K) acc[jj] = fmaf(cf, W[static_cast<int64_t>(c2) * K + lane + 32 * jj], acc[jj]);
+      }
     }
-    next[static_cast<int64_t>(b) * C + c] = nx;
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj)
+      if (lane + 32 * jj < K) srows[(static_cast<int64_t>(b) * C + c) * K + lane + 32 * jj] = acc[jj];
   }
 }
 
@@ -701,7 +736,7 @@ struct Carver {
 };
 
 int splits_for(int64_t M) {
-  int64_t s = (M + 1023) / 1024;
+  int64_t s = (M + 127) / 128;
   const int64_t cap = 2 * static_cast<int64_t>(sm_count());
   if (s > cap) s = cap;
   return static_cast<int>(s < 1 ? 1 : s);
@@ -730,32 +765,85 @@ Shape make_shape(int B, int N, int L, const pcuda_mlp_layer_t* layers, int pool)
   return s;
 }
 
-size_t fwd_ws_bytes(const Shape& s) {
-  size_t b = align_up(sizeof(double) * 2 * s.sumC);                    // stats
-  b += align_up(sizeof(float) * (static_cast<size_t>(s.sumC) + 4));    // zero vector (pivot of bias-free layers)
-  if (s.pool) b += align_up(sizeof(unsigned long long) * static_cast<size_t>(s.B) * s.Clast);
-  b += align_up(sizeof(float) * (static_cast<size_t>(s.sumC) + 4));    // pivots
-  return b;
+// Workspace layouts are produced by ONE routine per direction, used both to size the workspace
+// (base == nullptr) and to carve it.
+struct FwdWs {
+  double* stats; float* zeros; unsigned long long* keys; size_t zero_span; float* pivots;
+  uint8_t* apack[16]; uint8_t* wpack[16];
+  size_t bytes;
+};
+
+FwdWs carve_fwd(const Shape& s, const pcuda_mlp_layer_t* layers, void* base) {
+  FwdWs w{};
+  Carver cv(base);
+  w.stats = cv.take<double>(2 * static_cast<size_t>(s.sumC));
+  w.zeros = cv.take<float>(static_cast<size_t>(s.sumC) + 4);   // pivot of bias-free layers
+  w.keys = s.pool ? cv.take<unsigned long long>(static_cast<size_t>(s.B) * s.Clast) : nullptr;
+  w.zero_span = cv.off;                                          // stats, zeros and keys: one memset
+  w.pivots = cv.take<float>(static_cast<size_t>(s.sumC) + 4);
+  const tc::Tiling tl = tc::make_tiling(s.B, s.N);
+  for (int l = 0; l < s.L; ++l) {
+    if (!tc::supports(layers[l].cin)) continue;
+    w.apack[l] = cv.take<uint8_t>(tc::act_pack_bytes(tl, layers[l].cin));
+    w.wpack[l] = cv.take<uint8_t>(tc::w_pack_bytes(layers[l].cout, layers[l].cin));
+  }
+  w.bytes = cv.off;
+  return w;
 }
 
-size_t bwd_ws_bytes(const Shape& s) {
-  size_t b = 0;
-  b += align_up(sizeof(double) * 2 * s.sumC);                       // sums
-  b += 2 * align_up(sizeof(float) * s.sumC);                        // alpha, kappa
-  b += align_up(sizeof(float) * static_cast<size_t>(s.S) * s.maxWW);  // contraction partials
+struct BwdWs {
+  double* sums; float* alpha; float* kappa; float* partial;
+  float *coef, *gsel, *gyh, *Ghat, *Q, *abar, *u, *srows;
+  double *colsum, *G, *abar_d;
+  int* head;
+  float* dzbuf[2];
+  uint8_t* apack[17];   // apack[l + 1] = packed activation a_l; index 0 = the raw network input
+  uint8_t* dypack; uint8_t* wtpack; uint8_t* qpack;
+  size_t bytes;
+};
+
+BwdWs carve_bwd(const Shape& s, const pcuda_mlp_layer_t* layers, void* base) {
+  BwdWs w{};
+  Carver cv(base);
+  w.sums = cv.take<double>(2 * static_cast<size_t>(s.sumC));
+  w.alpha = cv.take<float>(s.sumC);
+  w.kappa = cv.take<float>(s.sumC);
+  w.partial = cv.take<float>(static_cast<size_t>(s.S) * s.maxWW);
+  const tc::Tiling tl = tc::make_tiling(s.B, s.N);
   if (s.pool) {
     const size_t K = s.Kpool;
-    b += 3 * align_up(sizeof(float) * static_cast<size_t>(s.B) * s.Clast);  // coef, gsel, gyh
-    b += align_up(sizeof(double) * s.S * K);                            // colsum partials
-    b += align_up(sizeof(double) * K * K);                              // G
-    b += 2 * align_up(sizeof(float) * K * K);                           // Ghat, Q
-    b += 2 * align_up(sizeof(float) * K);                               // abar, u
-    b += align_up(sizeof(double) * K);                                  // abar (double)
-    b += align_up(sizeof(int) * static_cast<size_t>(s.M));              // head
-    b += align_up(sizeof(int) * static_cast<size_t>(s.B) * s.Clast);    // next
+    w.coef = cv.take<float>(static_cast<size_t>(s.B) * s.Clast);
+    w.gsel = cv.take<float>(static_cast<size_t>(s.B) * s.Clast);
+    w.gyh = cv.take<float>(static_cast<size_t>(s.B) * s.Clast);
+    w.colsum = cv.take<double>(s.S * K);
+    w.G = cv.take<double>(K * K);
+    w.Ghat = cv.take<float>(K * K);
+    w.Q = cv.take<float>(K * K);
+    w.abar = cv.take<float>(K);
+    w.u = cv.take<float>(K);
+    w.abar_d = cv.take<double>(K);
+    w.head = cv.take<int>(static_cast<size_t>(s.M));
+    w.srows = cv.take<float>(static_cast<size_t>(s.B) * s.Clast * K);
+    if (tc::supports(static_cast<int>(K))) w.qpack = cv.take<uint8_t>(tc::w_pack_bytes(static_cast<int>(K), static_cast<int>(K)));
   }
-  b += 2 * align_up(sizeof(float) * static_cast<size_t>(s.M) * s.maxC);  // dz ping-pong
-  return b;
+  w.dzbuf[0] = cv.take<float>(static_cast<size_t>(s.M) * s.maxC);
+  w.dzbuf[1] = cv.take<float>(static_cast<size_t>(s.M) * s.maxC);
+  size_t dy_max = 0, wt_max = 0;
+  for (int l = -1; l <= s.L - 2; ++l) {
+    const int C = l < 0 ? layers[0].cin : layers[l].cout;
+    if (tc::supports(C)) w.apack[l + 1] = cv.take<uint8_t>(tc::act_pack_bytes(tl, C));
+  }
+  for (int l = 0; l < s.L; ++l) {
+    if (s.pool && l == s.L - 1) continue;
+    if (tc::supports(layers[l].cout)) {
+      dy_max = std::max(dy_max, tc::act_pack_bytes(tl, layers[l].cout));
+      wt_max = std::max(wt_max, tc::w_pack_bytes(layers[l].cin, layers[l].cout));
+    }
+  }
+  if (dy_max) w.dypack = cv.take<uint8_t>(dy_max);
+  if (wt_max) w.wtpack = cv.take<uint8_t>(wt_max);
+  w.bytes = cv.off;
+  return w;
 }
 
 int validate(const char* who, int B, int N, int L, const pcuda_mlp_layer_t* layers, int pool) {
@@ -800,7 +888,7 @@ extern "C" size_t pcuda_pointmlp_ws_bytes(int B, int N, int L, const pcuda_mlp_l
                                           int backward) {
   if (B < 1 || N < 1 || L < 1 || !layers) return 0;
   const Shape s = make_shape(B, N, L, layers, pool);
-  return backward ? bwd_ws_bytes(s) : fwd_ws_bytes(s);
+  return backward ? carve_bwd(s, layers, nullptr).bytes : carve_fwd(s, layers, nullptr).bytes;
 }
 
 extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
@@ -817,20 +905,20 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
     for (int l = 0; l < L; ++l)
       PCUDA_REQUIRE(layers[l].running_mean && layers[l].running_var, PCUDA_E_NULL, "pointmlp_fwd: eval mode needs running stats (layer %d)", l);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  Carver cv(ws);
-  double* stats = cv.take<double>(2 * static_cast<size_t>(s.sumC));
-  float* zeros = cv.take<float>(static_cast<size_t>(s.sumC) + 4);
-  unsigned long long* keys = pool ? cv.take<unsigned long long>(static_cast<size_t>(B) * s.Clast) : nullptr;
-  const size_t zero_span = cv.off;   // stats, zeros and keys are contiguous: one memset
-  float* pivots = cv.take<float>(static_cast<size_t>(s.sumC) + 4);
-  cudaMemsetAsync(stats, 0, zero_span, st);
+  const FwdWs w = carve_fwd(s, layers, ws);
+  cudaMemsetAsync(w.stats, 0, w.zero_span, st);
 
   const bool tcf = tc_on(precision, TC_FWD);
-  auto layer_tc = [&](int l) { return tcf && tc::supports(layers[l].cin); };
+  auto layer_tc = [&](int l) { return tcf && tc::fwd_fits(layers[l].cout, layers[l].cin); };
+  const tc::Tiling tl = tc::make_tiling(B, N);
   const int tps = (N + TM - 1) / TM;
-  double* st_l = stats;
-  float* piv_l = pivots;
+  double* st_l = w.stats;
+  float* piv_l = w.pivots;
   int launches = 0;
+  // bf16 copies of the tensor-core layers' weights
+  for (int l = 0; l < L; ++l)
+    if (layer_tc(l))
+      if (int rc = tc::pack_w(layers[l].weight, layers[l].cout, layers[l].cin, false, w.wpack[l], st)) return rc;
   if (!layer_tc(0)) {
     // pivot of layer 0 (no BN to finalise yet)
     bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, 0, 1.0, eps, momentum, train, nullptr, nullptr, nullptr, nullptr,
@@ -844,13 +932,15 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
     const bool is_pool = pool && l == L - 1;
     const float* pivot_used = piv_l;
     if (layer_tc(l)) {
-      // tensor-core layer: statistics are accumulated bias-free, i.e. centred on pivot = bias
-      if (int rc = tc::fwd_layer(src, y, is_pool, B, N, st_l, keys, st)) return rc;
-      pivot_used = y.bias ? y.bias : zeros;
+      // tensor-core layer: one pass packs a_{l-1} = relu?(bn(y_{l-1})) as bf16 slabs, the GEMM streams them.
+      // Statistics are accumulated bias-free, i.e. centred on pivot = bias.
+      if (int rc = tc::pack_act(src, tl, w.apack[l], st)) return rc;
+      if (int rc = tc::fwd_layer(tl, w.apack[l], w.wpack[l], y, is_pool, st_l, w.keys, st)) return rc;
+      pivot_used = y.bias ? y.bias : w.zeros;
     } else {
       const dim3 grid(B * tps, (y.cout + TN - 1) / TN);
       if (is_pool)
-        mlp_fwd_kernel<true><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, keys);
+        mlp_fwd_kernel<true><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, w.keys);
       else
         mlp_fwd_kernel<false><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, nullptr);
       launches += 1;
@@ -869,7 +959,7 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
   const pcuda_mlp_layer_t& last = layers[L - 1];
   if (pool) {
     const int64_t n = static_cast<int64_t>(B) * s.Clast;
-    pool_finalize_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(keys, last.save_mean, last.save_invstd, last.gamma,
+    pool_finalize_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(w.keys, last.save_mean, last.save_invstd, last.gamma,
                                                                             last.beta, last.relu, B, s.Clast, out, pool_arg);
   } else {
     const dim3 grid((N + 31) / 32, (s.Clast + 31) / 32, B);
@@ -892,32 +982,13 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const double count = static_cast<double>(s.M);
   const int tps = (N + TM - 1) / TM;
+  const tc::Tiling tl = tc::make_tiling(B, N);
   int launches = 0;
 
-  Carver cv(ws);
-  double* sums = cv.take<double>(2 * static_cast<size_t>(s.sumC));
-  float* alpha = cv.take<float>(s.sumC);
-  float* kappa = cv.take<float>(s.sumC);
-  float* partial = cv.take<float>(static_cast<size_t>(s.S) * s.maxWW);
-  float *coef = nullptr, *gsel = nullptr, *gyh = nullptr, *Ghat = nullptr, *Q = nullptr, *abar = nullptr, *u = nullptr;
-  double *colsum = nullptr, *G = nullptr, *abar_d = nullptr;
-  int *head = nullptr, *next = nullptr;
-  if (pool) {
-    const size_t K = s.Kpool;
-    coef = cv.take<float>(static_cast<size_t>(B) * s.Clast);
-    gsel = cv.take<float>(static_cast<size_t>(B) * s.Clast);
-    gyh = cv.take<float>(static_cast<size_t>(B) * s.Clast);
-    colsum = cv.take<double>(s.S * K);
-    G = cv.take<double>(K * K);
-    Ghat = cv.take<float>(K * K);
-    Q = cv.take<float>(K * K);
-    abar = cv.take<float>(K);
-    u = cv.take<float>(K);
-    abar_d = cv.take<double>(K);
-    head = cv.take<int>(static_cast<size_t>(s.M));
-    next = cv.take<int>(static_cast<size_t>(B) * s.Clast);
-  }
-  float* dzbuf[2] = {cv.take<float>(static_cast<size_t>(s.M) * s.maxC), cv.take<float>(static_cast<size_t>(s.M) * s.maxC)};
+  const BwdWs w = carve_bwd(s, layers, ws);
+  double* sums = w.sums;
+  float *alpha = w.alpha, *kappa = w.kappa, *partial = w.partial;
+  float* const* dzbuf = w.dzbuf;
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * s.sumC, st);
 
   std::vector<int> off(L + 1, 0);
@@ -937,54 +1008,75 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     return o;
   };
 
+  // bf16 copies of the activations the tensor-core pieces stream: a_l for l = -1 (input) .. L-2
+  const bool any_tc = precision == PCUDA_MLP_BF16 && !tuning(TUNE_MLP_FORCE_FP32) && (tuning(TUNE_MLP_TC_MASK) & 30) != 30;
+  const uint8_t* apack[17] = {};
+  if (any_tc)
+    for (int l = -1; l <= L - 2; ++l)
+      if (w.apack[l + 1] != nullptr && (l >= 0 || layers[0].grad_weight != nullptr)) {
+        if (int rc = tc::pack_act(src_of(l), tl, w.apack[l + 1], st)) return rc;
+        apack[l + 1] = w.apack[l + 1];
+      }
+
   int cur = 0;      // dzbuf[cur] holds dz of layer `top`
   int top = L - 1;  // highest layer whose dz is dense and stored
   const pcuda_mlp_layer_t& last = layers[L - 1];
   if (pool) {
     const int C = last.cout, K = last.cin;
     const ActSrc src = src_of(L - 2);
+    const uint8_t* a_in = apack[L - 1];
     float* al = alpha + off[L - 1];
     float* ka = kappa + off[L - 1];
     const int64_t bc = static_cast<int64_t>(B) * C;
     const int64_t kk = static_cast<int64_t>(K) * K;
     pool_sel_kernel<<<static_cast<int>((bc * 32 + 255) / 256), 256, 0, st>>>(src, last.weight, last.bias, last.save_mean,
                                                                             last.save_invstd, last.gamma, last.relu, out, pool_arg,
-                                                                            grad_out, B, N, C, coef, gsel, gyh);
+                                                                            grad_out, B, N, C, w.coef, w.gsel, w.gyh);
     const bool want_last = last.grad_weight != nullptr;
-    pool_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(gsel, gyh, last.save_invstd, last.gamma, B, C, count, train, al, ka,
+    pool_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(w.gsel, w.gyh, last.save_invstd, last.gamma, B, C, count, train, al, ka,
                                                       want_last ? last.grad_gamma : nullptr, want_last ? last.grad_beta : nullptr,
                                                       want_last ? last.grad_bias : nullptr);
     launches += 2;
     // centred Gram matrix of the pooled layer's input (train-mode BN correction terms only)
     int Sg = S32;
-    if (tc_on(precision, TC_GRAM) && tc::pt_supports(K, K, true)) {
-      Sg = tc::pt_splits(s.M, (K + 127) / 128);
-      if (int rc = tc::gram(src, s.M, Sg, partial, colsum, st)) return rc;
+    act_colsum_kernel<<<dim3(S32, (K + 31) / 32), 256, 0, st>>>(src, s.M, chunk32, w.colsum);
+    launches += 1;
+    if (tc_on(precision, TC_GRAM) && a_in && tc::pt_supports(K, K, true)) {
+      Sg = tc::pt_splits(tl, (K + 127) / 128);
+      if (int rc = tc::gram(tl, a_in, K, Sg, partial, st)) return rc;
     } else {
-      act_colsum_kernel<<<dim3(S32, (K + 31) / 32), 256, 0, st>>>(src, s.M, chunk32, colsum);
       point_contract_kernel<1><<<dim3(S32, (K + TM - 1) / TM, (K + TN - 1) / TN), kThreads, 0, st>>>(DySrc{}, src, src, s.M, chunk32, K, K, partial);
-      launches += 2;
+      launches += 1;
     }
-    reduce_partials_kernel<double><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(partial, kk, Sg, G);
-    abar_kernel<<<(K + 127) / 128, 128, 0, st>>>(colsum, Sg, K, count, abar, abar_d);
-    gram_center_kernel<<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(abar_d, G, K, count, Ghat);
-    pool_q_kernel<<<dim3((K + 31) / 32, (K + 31) / 32), 256, 0, st>>>(last.weight, ka, C, K, Q);
-    pool_u_kernel<<<(K + 31) / 32, 256, 0, st>>>(last.weight, al, Q, abar, C, K, u);
-    launches += 5;
+    reduce_partials_kernel<double><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(partial, kk, Sg, w.G);
+    abar_kernel<<<(K + 127) / 128, 128, 0, st>>>(w.colsum, S32, K, count, w.abar, w.abar_d);
+    gram_center_kernel<<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(w.abar_d, w.G, K, count, w.Ghat);
+    pool_q_kernel<<<dim3((K + 31) / 32, (K + 31) / 32, kPoolQSplits), 256, 0, st>>>(last.weight, ka, C, K, partial);
+    reduce_partials_kernel<float><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(partial, kk, kPoolQSplits, w.Q);
+    pool_u_kernel<<<(K + 31) / 32, 1024, 0, st>>>(last.weight, al, w.Q, w.abar, C, K, w.u);
+    launches += 6;
     if (last.grad_weight) {
       const int64_t ck = static_cast<int64_t>(C) * K;
-      pool_dw_kernel<<<static_cast<int>((ck + 255) / 256), 256, 0, st>>>(src, last.weight, coef, pool_arg, ka, abar, Ghat, B, N, C, train, last.grad_weight);
+      pool_dw_kernel<<<static_cast<int>((ck + 255) / 256), 256, 0, st>>>(src, last.weight, w.coef, pool_arg, ka, w.abar, w.Ghat, B, N, C, train, last.grad_weight);
       launches += 1;
     }
     if (L >= 2 || grad_x) {
       const DgradOut o = dgrad_out(L - 2, dzbuf[cur]);
-      if (tc_on(precision, TC_POOL_DGRAD) && tc::supports(K)) {
-        cudaMemsetAsync(head, 0xFF, sizeof(int) * static_cast<size_t>(s.M), st);
-        pool_invert_kernel<<<B, 1024, sizeof(int) * C, st>>>(pool_arg, coef, C, N, head, next);
+      const size_t sparse_smem = sizeof(int) * (static_cast<size_t>(C) + N);
+      if (tc_on(precision, TC_POOL_DGRAD) && a_in && w.qpack && tc::pool_dgrad_fits(K) && sparse_smem <= 200 * 1024 && K <= 512) {
+        static bool attr_done = false;
+        if (!attr_done) {
+          cudaFuncSetAttribute(pool_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          attr_done = true;
+        }
+        cudaMemsetAsync(w.head, 0xFF, sizeof(int) * static_cast<size_t>(s.M), st);
+        const int parts = std::max(1, std::min(8, 2 * sm_count() / std::max(1, B)));
+        pool_sparse_kernel<<<dim3(B, parts), 1024, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, w.head, w.srows);
         launches += 1;
-        if (int rc = tc::pool_dgrad(src, Q, u, last.weight, coef, head, next, C, B, N, o, st)) return rc;
+        if (int rc = tc::pack_w(w.Q, K, K, false, w.qpack, st)) return rc;
+        if (int rc = tc::pool_dgrad(tl, a_in, K, w.qpack, w.u, w.head, w.srows, C, o, st)) return rc;
       } else {
-        pool_dgrad_kernel<<<dim3(B * tps, (K + TN - 1) / TN), kThreads, 0, st>>>(src, Q, u, last.weight, coef, pool_arg, C, N, tps, o);
+        pool_dgrad_kernel<<<dim3(B * tps, (K + TN - 1) / TN), kThreads, 0, st>>>(src, w.Q, w.u, last.weight, w.coef, pool_arg, C, N, tps, o);
         launches += 1;
       }
     }
@@ -1008,12 +1100,19 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
                                                         want_w ? y.grad_bias : nullptr);
     launches += 1;
     const DySrc dys{dzbuf[cur], y.y, y.save_mean, y.save_invstd, y.gamma, al, ka, C};
+    const bool need_dgrad = l > 0 || grad_x != nullptr;
+    const bool wgrad_tc = want_w && tc_on(precision, TC_WGRAD) && w.dypack && apack[l] && tc::pt_supports(C, Kp, false);
+    const bool dgrad_side = l - 1 >= 0 && (Kp % 64) == 0 && apack[l] != nullptr;
+    const bool dgrad_tc = need_dgrad && tc_on(precision, TC_DGRAD) && w.dypack && w.wtpack && (Kp % 8) == 0 &&
+                          tc::dgrad_fits(Kp, C, dgrad_side);
+    if (wgrad_tc || dgrad_tc)
+      if (int rc = tc::pack_dy(dys, tl, w.dypack, st)) return rc;      // dy_l as bf16 slabs, once for both GEMMs
     if (want_w) {
       const int64_t ck = static_cast<int64_t>(C) * Kp;
       int Sw = S32;
-      if (tc_on(precision, TC_WGRAD) && tc::pt_supports(C, Kp, false)) {
-        Sw = tc::pt_splits(s.M, (C + 127) / 128);
-        if (int rc = tc::wgrad_layer(dys, src_of(l - 1), s.M, Sw, partial, st)) return rc;
+      if (wgrad_tc) {
+        Sw = tc::pt_splits(tl, (C + 127) / 128);
+        if (int rc = tc::wgrad_layer(tl, w.dypack, C, apack[l], Kp, Sw, partial, st)) return rc;
       } else {
         point_contract_kernel<0><<<dim3(S32, (C + TM - 1) / TM, (Kp + TN - 1) / TN), kThreads, 0, st>>>(dys, ActSrc{}, src_of(l - 1), s.M, chunk32, C, Kp, partial);
         launches += 1;
@@ -1021,10 +1120,13 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
       reduce_partials_kernel<float><<<static_cast<int>((ck + 255) / 256), 256, 0, st>>>(partial, ck, Sw, y.grad_weight);
       launches += 1;
     }
-    if (l > 0 || grad_x) {
+    if (need_dgrad) {
       const DgradOut o = dgrad_out(l - 1, dzbuf[cur ^ 1]);
-      if (tc_on(precision, TC_DGRAD) && tc::supports(C) && Kp >= 64 && (C % 8) == 0) {
-        if (int rc = tc::dgrad_layer(dys, y.weight, B, N, o, st)) return rc;
+      if (dgrad_tc) {
+        // A[r = channel of layer l-1, k = channel of layer l] = W_l[k, r]
+        if (int rc = tc::pack_w(y.weight, Kp, C, true, w.wtpack, st)) return rc;
+        const uint8_t* side = dgrad_side ? apack[l] : nullptr;
+        if (int rc = tc::dgrad_layer(tl, w.dypack, C, w.wtpack, side, o, st)) return rc;
       } else {
         dense_dgrad_kernel<<<dim3(B * tps, (Kp + TN - 1) / TN), kThreads, 0, st>>>(dys, y.weight, N, tps, o);
         launches += 1;

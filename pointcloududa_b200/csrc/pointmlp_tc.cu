@@ -1,32 +1,39 @@
 // PointNet shared MLP on the Blackwell tensor cores (tcgen05.mma, accumulators in TMEM).
 //
-// Two kernels cover every wide (cin >= 64) contraction of the Conv1d(k=1)+BatchNorm1d(+ReLU) stacks of
-// networks/PointNetCls.py:41-44,:84-87,:143-162 and of their backward:
+// Every wide (cin >= 64) contraction of the Conv1d(k=1)+BatchNorm1d(+ReLU) stacks of
+// networks/PointNetCls.py:41-44,:84-87,:143-162 — forward and backward — runs through two GEMM
+// kernels whose operands arrive by 1-D bulk copies (cp.async.bulk -> mbarrier complete_tx):
+//
+//   pack_*_kernel   one HBM pass per operand: fp32 tensor -> (BatchNorm + ReLU | BN-backward
+//                   transform) -> bf16, written in the 128-byte-swizzled "slab" format the
+//                   tensor core reads (tc_common.cuh), tile by tile (256 points, never straddling
+//                   a cloud; rows past the end of a cloud are zero).  A slab is 32 KB contiguous,
+//                   so the GEMM kernels fetch it with ONE bulk-copy instruction: no tensor maps,
+//                   no per-thread loads, the transform is paid once per tensor instead of once
+//                   per consumer CTA.
 //
 //   ws_kernel  "weight-stationary":  D[r, m] = sum_k A[r, k] * Bop[m, k]
 //        TMEM lane r = an output channel, TMEM column m = a point of the current 256-point tile.
-//        A (weights, 128 rows per block) is converted to bf16 once per CTA and stays in shared
-//        memory; Bop tiles are produced by 4 warps straight from the fp32 tensors in HBM with the
-//        previous layer's BatchNorm + ReLU (or the BN-backward transform) folded into the load, so
-//        no normalised / activated / bf16 copy of an activation ever exists in HBM.
+//        A (packed weights, 128 rows per block) is fetched once per CTA; Bop slabs stream through
+//        a shared-memory ring.  Because a thread of the epilogue owns a channel and walks over
+//        points, every per-channel reduction is thread-local (no shuffles, no shared atomics).
 //          FWD_DENSE   y = W a            epilogue: store y (pre-BN), per-channel sum / sum^2
 //          FWD_POOL    y = W a            epilogue: per-(cloud,channel) max + first arg-max, sums;
 //                                         the [B*N, 1024] activation is never written
-//          DGRAD       da = dy W          epilogue: ReLU mask of the producing layer, store dz,
-//                                         dbeta / dgamma sums of that layer
-//          POOL_DGRAD  da = S - u - a Q   (low-rank backward of the pooled layer, see pointmlp.cu)
-//        Because a thread owns a channel and walks over points, every per-channel reduction
-//        (BN statistics, max-pool, dbeta/dgamma) is thread-local: no shuffles, no shared atomics.
+//          DGRAD       da = dy W          epilogue: ReLU mask of the producing layer (from its
+//                                         packed activation), store dz, dbeta / dgamma sums
+//          POOL_DGRAD  da = S - u - a Q   (low-rank backward of the pooled layer, see pointmlp.cu);
+//                                         the streamed operand doubles as the mask source
 //
 //   pt_kernel  "point-contraction":  D[c, k] = sum_m P[m, c] * R[m, k]      (wgrad, Gram matrix)
-//        both operands stream (MN-major reads of the same slab format), the accumulator stays in
-//        TMEM over the CTA's whole point range and is written once.
+//        MN-major reads of the same slabs; the accumulator stays in TMEM over the CTA's tiles.
 //
-// Warp roles (ws_kernel, 288 threads): warps 0-3 producers, warps 4-7 epilogue (TMEM lane
-// quarter = warp % 4), warp 8 = TMEM allocation + the single MMA-issuing thread.
-// Pipelines: smem ring full/empty mbarriers (producers <-> MMA), TMEM accumulator full/empty
-// mbarriers (MMA <-> epilogue); two 256-column accumulators so the epilogue of one overlaps the
-// MMAs of the other.
+// Warp roles (ws_kernel, 384 threads): warp 0 = bulk-copy producer (one lane), warp 1 = TMEM
+// allocation + the single MMA-issuing thread, warps 4-11 = epilogue (TMEM lane quarter = warp % 4,
+// the two warps of a quarter take alternate 32-column chunks).
+// Pipelines: smem ring full/empty mbarriers (producer <-> MMA [<-> epilogue]), TMEM accumulator
+// full/empty mbarriers (MMA <-> epilogue); two 256-column accumulators so the epilogue of one
+// overlaps the MMAs of the other.
 #include <algorithm>
 
 #include "pointmlp_common.cuh"
@@ -39,59 +46,17 @@ namespace {
 
 constexpr int kNT = 256;                 // points per tile (UMMA N)
 constexpr int kSlabA = 128 * 128;        // bytes of one A slab: 128 rows x 64 bf16
-constexpr int kSlabB = kNT * 128;        // bytes of one B slab: 256 rows x 64 bf16
-constexpr int kProducers = 128;
-constexpr int kWsThreads = 288;
+constexpr int kSlabB = kNT * 128;        // bytes of one activation slab: 256 rows x 64 bf16
+constexpr int kThreads = 384;          // ws_kernel: warp 0 producer, 1 MMA, 4-11 epilogue
+constexpr int kPtThreads = 256;
 constexpr int kMaxK = 512;
 constexpr uint32_t kTmemCols = 512;
+constexpr int kSmemBudget = 227 * 1024;
 
-enum Mode { FWD_DENSE = 0, FWD_POOL = 1, DGRAD = 2, POOL_DGRAD = 3 };
-
-struct WsParams {
-  int B, N, tpc, n_tiles;   // tiles never straddle clouds: tile t -> cloud t / tpc, points (t % tpc) * 256 ...
-  int K;                    // contraction length (multiple of 64, <= 512)
-  int R;                    // output rows (TMEM lanes): Cout (forward), channels of the previous layer (dgrad)
-  int CB, G, nstage;        // row blocks per CTA (1|2), row groups, ring depth
-  ActSrc act;               // FWD_*, POOL_DGRAD: Bop = act(prev layer)
-  DySrc dy;                 // DGRAD: Bop = dy of this layer
-  const float* A;           // FWD_*: W [R, K];  POOL_DGRAD: Q [R, K] (symmetric);  DGRAD: W [K, R] (read transposed)
-  // forward epilogue
-  const float* bias; const float* gamma; float* y_out; double* stats; unsigned long long* keys;
-  // dgrad epilogues
-  DgradOut out;
-  const float* u;           // POOL_DGRAD: [R]
-  const float* coef;        // POOL_DGRAD: [B, Cpool]
-  const int* head;          // POOL_DGRAD: [B*N] first channel whose arg-max is this point, or -1
-  const int* next;          // POOL_DGRAD: [B, Cpool] next channel selecting the same point, or -1
-  const float* Wpool;       // POOL_DGRAD: [Cpool, K]
-  int Cpool;
-};
-
-// per-contraction-channel constants of the producer transform, in shared memory
-//   ActSrc : a  = relu?(y * p0 + p1)                 p0 = invstd*gamma, p1 = beta - mean*p0
-//   DySrc  : dy = dz * p0 + (y * p1 + p2)            p0 = gamma*invstd, p1 = -kappa, p2 = kappa*mean - alpha
-struct ProducerConsts {
+// ================================= operand packing =================================================
+struct PackConsts {
   float p0[kMaxK], p1[kMaxK], p2[kMaxK];
 };
-
-template <int MODE>
-__device__ __forceinline__ void init_consts(const WsParams& p, ProducerConsts& pc) {
-  for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
-    if (MODE == DGRAD) {
-      const float sc = p.dy.gamma[k] * p.dy.invstd[k];
-      pc.p0[k] = sc;
-      pc.p1[k] = -p.dy.kappa[k];
-      pc.p2[k] = p.dy.kappa[k] * p.dy.mean[k] - p.dy.alpha[k];
-    } else if (p.act.y != nullptr) {
-      const float sc = p.act.invstd[k] * p.act.gamma[k];
-      pc.p0[k] = sc;
-      pc.p1[k] = p.act.beta[k] - p.act.mean[k] * sc;
-      pc.p2[k] = 0.f;
-    } else {
-      pc.p0[k] = 1.f; pc.p1[k] = 0.f; pc.p2[k] = 0.f;
-    }
-  }
-}
 
 __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
@@ -99,153 +64,225 @@ __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// One 256-row x 64-channel slab of the streamed operand, produced by the 128 producer threads.
-// Thread -> fixed 16-byte chunk column (8 channels) and 16 rows; rows past the end of the cloud are zero.
-template <int MODE>
-__device__ __forceinline__ void produce_slab(const WsParams& p, const ProducerConsts& pc, uint8_t* stage, int b,
-                                             int n0, int slab, int ptid) {
-  const int c = ptid & 7, rg = ptid >> 3;
-  const int k0 = slab * 64 + c * 8;
-  const int N = p.N;
-  float q0[8], q1[8], q2[8];
+// a = relu?(y * p0 + p1)  (or the raw network input), p0 = invstd*gamma, p1 = beta - mean*p0
+// one thread = one 16-byte chunk (8 channels of one point)
+__global__ void __launch_bounds__(256) pack_act_kernel(ActSrc src, Tiling tl, uint8_t* __restrict__ out) {
+  __shared__ PackConsts pc;
+  const int C = src.C;
+  for (int k = threadIdx.x; k < C; k += blockDim.x) {
+    if (src.y != nullptr) {
+      const float sc = src.invstd[k] * src.gamma[k];
+      pc.p0[k] = sc;
+      pc.p1[k] = src.beta[k] - src.mean[k] * sc;
+    } else { pc.p0[k] = 1.f; pc.p1[k] = 0.f; }
+  }
+  __syncthreads();
+  const int cpr = C >> 3, KS = C >> 6;                       // chunks per row, slabs per tile
+  const int64_t total = static_cast<int64_t>(tl.n_tiles) * kNT * cpr;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int chunk = static_cast<int>(i % cpr);
+    const int64_t rowid = i / cpr;
+    const int row = static_cast<int>(rowid % kNT);
+    const int tile = static_cast<int>(rowid / kNT);
+    const int b = tile / tl.tpc, n = (tile - b * tl.tpc) * kNT + row;
+    const int k0 = chunk * 8;
+    float a[8];
+    if (n < tl.N) {
+      float v[8];
+      if (src.y != nullptr) ld8(src.y + (static_cast<int64_t>(b) * tl.N + n) * C + k0, v);
+      else {
+        const float* px = src.x + static_cast<int64_t>(b) * src.sxb + static_cast<int64_t>(n) * src.sxn;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { q0[i] = pc.p0[k0 + i]; q1[i] = pc.p1[k0 + i]; q2[i] = pc.p2[k0 + i]; }
-  const int64_t mbase = static_cast<int64_t>(b) * N + n0;
-  constexpr int RB = 4;  // rows in flight per thread
-#pragma unroll 1
-  for (int i0 = 0; i0 < 16; i0 += RB) {
-    float v[RB][8], w[RB][8];
-#pragma unroll
-    for (int j = 0; j < RB; ++j) {
-      const int r = rg + 16 * (i0 + j);
-      const bool ok = n0 + r < N;
-      if (MODE == DGRAD) {
-        if (ok) {
-          ld8(p.dy.dz + (mbase + r) * p.K + k0, v[j]);
-          ld8(p.dy.y + (mbase + r) * p.K + k0, w[j]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { v[j][e] = 0.f; w[j][e] = 0.f; }
-        }
-      } else if (p.act.y != nullptr) {
-        if (ok) ld8(p.act.y + (mbase + r) * p.K + k0, v[j]);
-        else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
-        }
-      } else {
-        // raw network input x[b, k, n] with explicit strides (the reference passes transposed views)
-        const float* px = p.act.x + static_cast<int64_t>(b) * p.act.sxb + static_cast<int64_t>(n0 + r) * p.act.sxn;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[j][e] = ok ? __ldg(px + static_cast<int64_t>(k0 + e) * p.act.sxc) : 0.f;
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(px + static_cast<int64_t>(k0 + e) * src.sxc);
       }
-    }
-#pragma unroll
-    for (int j = 0; j < RB; ++j) {
-      const int r = rg + 16 * (i0 + j);
-      const bool ok = n0 + r < N;
-      float a[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float t;
-        if (MODE == DGRAD) t = fmaf(v[j][e], q0[e], fmaf(w[j][e], q1[e], q2[e]));
-        else {
-          t = fmaf(v[j][e], q0[e], q1[e]);
-          if (p.act.relu) t = fmaxf(t, 0.f);
-        }
-        a[e] = ok ? t : 0.f;
+        const float t = fmaf(v[e], pc.p0[k0 + e], pc.p1[k0 + e]);
+        a[e] = src.relu ? fmaxf(t, 0.f) : t;
       }
-      *reinterpret_cast<uint4*>(stage + slab_off(r, c)) = pack8(a);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = 0.f;
     }
+    uint8_t* dst = out + (static_cast<int64_t>(tile) * KS + (chunk >> 3)) * kSlabB + slab_off(row, chunk & 7);
+    *reinterpret_cast<uint4*>(dst) = pack8(a);
   }
 }
 
-// The stationary operand: 128 rows (TMEM lanes) x K, bf16, written once per CTA.
-//   K-major  (FWD_*, POOL_DGRAD): slab s = rows x channels [64 s, 64 s + 64);  A[r, k] = src[(r0 + r) * K + k]
-//   MN-major (DGRAD)            : group g (64 lanes) = K contraction rows x 64 lanes; A[r, k] = src[k * R + r0 + r]
-template <int MODE>
-__device__ __forceinline__ void load_A(const WsParams& p, uint8_t* abase, int r0) {
-  const int K = p.K, R = p.R;
-  if (MODE != DGRAD) {
-    const int chunks = 128 * (K / 8);
-    for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
-      const int r = i / (K / 8), kc = i - r * (K / 8);
-      const int k = kc * 8;
-      float a[8];
-      if (r0 + r < R) ld8(p.A + static_cast<int64_t>(r0 + r) * K + k, a);
+// dy = dz * p0 + (y * p1 + p2),  p0 = gamma*invstd, p1 = -kappa, p2 = kappa*mean - alpha
+__global__ void __launch_bounds__(256) pack_dy_kernel(DySrc dys, Tiling tl, uint8_t* __restrict__ out) {
+  __shared__ PackConsts pc;
+  const int C = dys.C;
+  for (int k = threadIdx.x; k < C; k += blockDim.x) {
+    pc.p0[k] = dys.gamma[k] * dys.invstd[k];
+    pc.p1[k] = -dys.kappa[k];
+    pc.p2[k] = dys.kappa[k] * dys.mean[k] - dys.alpha[k];
+  }
+  __syncthreads();
+  const int cpr = C >> 3, KS = C >> 6;
+  const int64_t total = static_cast<int64_t>(tl.n_tiles) * kNT * cpr;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int chunk = static_cast<int>(i % cpr);
+    const int64_t rowid = i / cpr;
+    const int row = static_cast<int>(rowid % kNT);
+    const int tile = static_cast<int>(rowid / kNT);
+    const int b = tile / tl.tpc, n = (tile - b * tl.tpc) * kNT + row;
+    const int k0 = chunk * 8;
+    float a[8];
+    if (n < tl.N) {
+      float v[8], w[8];
+      const int64_t m = static_cast<int64_t>(b) * tl.N + n;
+      ld8(dys.dz + m * C + k0, v);
+      ld8(dys.y + m * C + k0, w);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = fmaf(v[e], pc.p0[k0 + e], fmaf(w[e], pc.p1[k0 + e], pc.p2[k0 + e]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = 0.f;
+    }
+    uint8_t* dst = out + (static_cast<int64_t>(tile) * KS + (chunk >> 3)) * kSlabB + slab_off(row, chunk & 7);
+    *reinterpret_cast<uint4*>(dst) = pack8(a);
+  }
+}
+
+// Stationary operand: 128-row blocks of a [R, K] matrix.
+//   transposed == 0 (K-major)  A[r, k] = W[r*K + k]   block rb: KS slabs of 128 rows x 64 k
+//   transposed == 1 (MN-major) A[r, k] = W[k*R + r]   block rb: 2 groups (64 lanes each) of K rows x 64 lanes
+// Either way a block occupies (K/64) * 16 KB = K * 256 bytes.
+__global__ void __launch_bounds__(256) pack_w_kernel(const float* __restrict__ W, int R, int K, int transposed,
+                                                     uint8_t* __restrict__ out) {
+  const int rblocks = (R + 127) / 128;
+  const int64_t total = static_cast<int64_t>(rblocks) * 128 * (K >> 3);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float a[8];
+    uint8_t* dst;
+    if (!transposed) {
+      const int chunk = static_cast<int>(i % (K >> 3));
+      const int64_t rid = i / (K >> 3);
+      const int row = static_cast<int>(rid % 128), rb = static_cast<int>(rid / 128);
+      const int r = rb * 128 + row, k0 = chunk * 8;
+      if (r < R) ld8(W + static_cast<int64_t>(r) * K + k0, a);
       else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) a[e] = 0.f;
       }
-      *reinterpret_cast<uint4*>(abase + (k >> 6) * kSlabA + slab_off(r, kc & 7)) = pack8(a);
-    }
-  } else {
-    // A^T view of W [K, R]: contraction row k, lanes r0 .. r0+127 -> two 64-lane groups of K rows each
-    const int chunks = K * 16;
-    for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
-      const int k = i >> 4, lc = i & 15;  // lc: 8-lane chunk within the 128 lanes
-      const int r = lc * 8;
-      float a[8];
+      dst = out + static_cast<int64_t>(rb) * K * 256 + (chunk >> 3) * kSlabA + slab_off(row, chunk & 7);
+    } else {
+      const int lc = static_cast<int>(i % 16);               // 8-lane chunk inside the 128-lane block
+      const int64_t rid = i / 16;
+      const int k = static_cast<int>(rid % K), rb = static_cast<int>(rid / K);
+      const int r0 = rb * 128 + lc * 8;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) a[e] = (r0 + r + e < R) ? __ldg(p.A + static_cast<int64_t>(k) * R + r0 + r + e) : 0.f;
-      *reinterpret_cast<uint4*>(abase + (lc >> 3) * (K * 128) + slab_off(k, lc & 7)) = pack8(a);
+      for (int e = 0; e < 8; ++e) a[e] = (r0 + e < R) ? __ldg(W + static_cast<int64_t>(k) * R + r0 + e) : 0.f;
+      dst = out + static_cast<int64_t>(rb) * K * 256 + (lc >> 3) * (K * 128) + slab_off(k, lc & 7);
     }
+    *reinterpret_cast<uint4*>(dst) = pack8(a);
   }
 }
 
+// ================================= weight-stationary GEMM ==========================================
+enum Mode { FWD_DENSE = 0, FWD_POOL = 1, DGRAD = 2, POOL_DGRAD = 3 };
+
+struct WsParams {
+  Tiling tl;
+  int K;                    // contraction length (multiple of 64, <= 512)
+  int R;                    // output rows (TMEM lanes): Cout (forward), channels of the previous layer (dgrad)
+  int CB, G, nstage;        // row blocks per CTA (1|2), row groups, ring depth
+  int side_slabs;           // DGRAD: slabs per tile of the previous layer's packed activation (0: none)
+  const uint8_t* A;         // packed stationary operand (pack_w_kernel)
+  const uint8_t* Bop;       // packed streamed operand: [n_tiles][K/64] slabs
+  const uint8_t* side;      // DGRAD: packed activation of the previous layer: [n_tiles][side_slabs] slabs
+  // forward epilogue
+  const float* bias; const float* gamma; float* y_out; double* stats; unsigned long long* keys;
+  // dgrad epilogues
+  DgradOut out;
+  const float* u;           // POOL_DGRAD: [R]
+  const int* head;          // POOL_DGRAD: [B*N] lowest channel whose arg-max is this point, or -1
+  const float* srows;       // POOL_DGRAD: [B, Cpool, K] row at (b, head) = sum over the channels selecting that point
+  int Cpool;
+};
+
 struct __align__(8) WsBarriers {
-  uint64_t full[8], empty[8], acc_full[2], acc_empty[2];
+  uint64_t full[8], empty[8], acc_full[2], acc_empty[2], a_full, side_full, side_empty;
   uint32_t tmem_base;
   uint32_t pad;
 };
 
+__device__ __forceinline__ float bf16_at(const uint8_t* slab, int row, int ch) {
+  // element (row, ch) of a 64-channel slab
+  const __nv_bfloat16 h = *reinterpret_cast<const __nv_bfloat16*>(slab + slab_off(row, ch >> 3) + (ch & 7) * 2);
+  return __bfloat162float(h);
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const WsParams p) {
+__global__ void __launch_bounds__(kThreads, 1) ws_kernel(const WsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int KS = p.K >> 6;
-  uint8_t* a_smem = smem;                                   // CB * KS slabs of 16 KB
-  uint8_t* b_smem = a_smem + p.CB * KS * kSlabA;            // nstage slabs of 32 KB
-  ProducerConsts* pc = reinterpret_cast<ProducerConsts*>(b_smem + p.nstage * kSlabB);
-  WsBarriers* bars = reinterpret_cast<WsBarriers*>(pc + 1);
+  uint8_t* a_smem = smem;                                       // CB * KS slabs of 16 KB
+  uint8_t* b_smem = a_smem + p.CB * KS * kSlabA;                // nstage slabs of 32 KB
+  uint8_t* side_smem = b_smem + p.nstage * kSlabB;              // side_slabs slabs of 32 KB
+  WsBarriers* bars = reinterpret_cast<WsBarriers*>(side_smem + p.side_slabs * kSlabB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x % p.G;                           // row group of this CTA
-  const int P = gridDim.x / p.G, j = blockIdx.x / p.G;      // CTAs per group, index inside the group
-  const int t_begin = static_cast<int>(static_cast<int64_t>(p.n_tiles) * j / P);
-  const int t_end = static_cast<int>(static_cast<int64_t>(p.n_tiles) * (j + 1) / P);
+  const int g = blockIdx.x % p.G;                               // row group of this CTA
+  const int P = gridDim.x / p.G, j = blockIdx.x / p.G;          // CTAs per group, index inside the group
+  const int t_begin = static_cast<int>(static_cast<int64_t>(p.tl.n_tiles) * j / P);
+  const int t_end = static_cast<int>(static_cast<int64_t>(p.tl.n_tiles) * (j + 1) / P);
   const int row_base = g * p.CB * 128;
+  constexpr bool kEpiReadsB = MODE == POOL_DGRAD;               // the streamed slabs double as mask source
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.nstage; ++s) { mbar_init(smem_u32(&bars->full[s]), kProducers); mbar_init(smem_u32(&bars->empty[s]), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->acc_full[s]), 1); mbar_init(smem_u32(&bars->acc_empty[s]), 128); }
+    for (int s = 0; s < p.nstage; ++s) {
+      mbar_init(smem_u32(&bars->full[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), kEpiReadsB ? 9 : 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->acc_full[s]), 1); mbar_init(smem_u32(&bars->acc_empty[s]), 8); }
+    mbar_init(smem_u32(&bars->a_full), 1);
+    mbar_init(smem_u32(&bars->side_full), 1);
+    mbar_init(smem_u32(&bars->side_empty), 8);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
-  init_consts<MODE>(p, *pc);
-  for (int cb = 0; cb < p.CB; ++cb) load_A<MODE>(p, a_smem + cb * KS * kSlabA, row_base + cb * 128);
-  fence_proxy_async();
+  if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp < 4) {
-    // ================================ producers ===================================================
-    uint32_t it = 0;
-    for (int t = t_begin; t < t_end; ++t) {
-      const int b = t / p.tpc, n0 = (t - b * p.tpc) * kNT;
-      for (int s = 0; s < KS; ++s, ++it) {
-        const uint32_t stage = it % p.nstage, ph = (it / p.nstage) & 1u;
-        mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1u);
-        produce_slab<MODE>(p, *pc, b_smem + stage * kSlabB, b, n0, s, threadIdx.x);
-        fence_proxy_async();
-        mbar_arrive(smem_u32(&bars->full[stage]));
+  if (warp == 0) {
+    // ================================ producer (one lane) =========================================
+    if (lane == 0) {
+      const uint32_t a_bytes = static_cast<uint32_t>(p.CB * KS * kSlabA);
+      mbar_arrive_expect_tx(smem_u32(&bars->a_full), a_bytes);
+      const uint8_t* a_src = p.A + static_cast<int64_t>(row_base / 128) * KS * kSlabA;
+      for (uint32_t off = 0; off < a_bytes; off += kSlabA)
+        bulk_g2s(smem_u32(a_smem + off), a_src + off, kSlabA, smem_u32(&bars->a_full));
+      uint32_t it = 0, tc = 0;
+      for (int t = t_begin; t < t_end; ++t, ++tc) {
+        for (int s = 0; s < KS; ++s, ++it) {
+          const uint32_t stage = it % p.nstage, ph = (it / p.nstage) & 1u;
+          mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1u);
+          mbar_arrive_expect_tx(smem_u32(&bars->full[stage]), kSlabB);
+          bulk_g2s(smem_u32(b_smem + stage * kSlabB), p.Bop + (static_cast<int64_t>(t) * KS + s) * kSlabB, kSlabB,
+                   smem_u32(&bars->full[stage]));
+        }
+        if (MODE == DGRAD && p.side_slabs > 0) {
+          mbar_wait(smem_u32(&bars->side_empty), (tc & 1u) ^ 1u);
+          mbar_arrive_expect_tx(smem_u32(&bars->side_full), static_cast<uint32_t>(p.side_slabs) * kSlabB);
+          for (int s = 0; s < p.side_slabs; ++s)
+            bulk_g2s(smem_u32(side_smem + s * kSlabB), p.side + (static_cast<int64_t>(t) * p.side_slabs + s) * kSlabB, kSlabB,
+                     smem_u32(&bars->side_full));
+        }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 1) {
     // ================================ MMA issuer ==================================================
     const uint32_t idesc = make_idesc(128, kNT, MODE == DGRAD ? 1 : 0, 0);
+    mbar_wait(smem_u32(&bars->a_full), 0);
+    tc_fence_after();
     uint32_t it = 0, ac = 0;
     for (int t = t_begin; t < t_end; ++t, it += KS) {
       for (int cb = 0; cb < p.CB; ++cb, ++ac) {
@@ -261,7 +298,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const WsParams p) {
             const uint32_t b_addr = smem_u32(b_smem + stage * kSlabB);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              uint64_t adesc, bdesc = make_sdesc(b_addr + kk * 32, 16, 1024);
+              uint64_t adesc;
+              const uint64_t bdesc = make_sdesc(b_addr + kk * 32, 16, 1024);
               if (MODE == DGRAD) adesc = make_sdesc(a_cb + (s * 64 + kk * 16) * 128, p.K * 128, 1024);
               else adesc = make_sdesc(a_cb + s * kSlabA + kk * 32, 16, 1024);
               umma_bf16(tmem + slot * kNT, adesc, bdesc, idesc, (s | kk) != 0);
@@ -273,35 +311,42 @@ __global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const WsParams p) {
         }
       }
     }
-  } else {
-    // ================================ epilogue ====================================================
-    const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+  } else if (warp >= 4) {
+    // ================================ epilogue (8 warps) ==========================================
+    // TMEM lane quarter = warp % 4; the two warps of a quarter split the 32-column chunks of a tile
+    // (even / odd), so every SM sub-partition holds two epilogue warps to hide each other's latency.
+    // All per-channel state lives in scalar registers (nothing is indexed dynamically).
+    const int q = warp & 3, half = (warp - 4) >> 2;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    uint32_t ac = 0;
-    double S[2] = {0.0, 0.0}, Q[2] = {0.0, 0.0};
-    float best[2] = {-INFINITY, -INFINITY};
-    int besti[2] = {0, 0};
+    uint32_t ac = 0, it = 0, tc = 0;
+    double S0 = 0.0, S1 = 0.0, Q0 = 0.0, Q1 = 0.0;
+    float best0 = -INFINITY, best1 = -INFINITY;
+    int besti0 = 0, besti1 = 0;
     int cur_b = -1;
-    auto flush_pool = [&](int b) {
-      if (MODE != FWD_POOL || b < 0) return;
-      for (int cb = 0; cb < p.CB; ++cb) {
-        const int r = row_base + cb * 128 + q * 32 + lane;
-        if (r < p.R) {
-          // the running maximum is over the bias-free accumulator times sign(gamma); the key holds
-          // sign(gamma) * (y + bias), what pool_finalize_kernel expects
-          const float gm = p.gamma[r];
-          const float sg = gm > 0.f ? 1.f : (gm < 0.f ? -1.f : 0.f);
-          const float bv = p.bias ? p.bias[r] : 0.f;
-          atomicMax(&p.keys[static_cast<int64_t>(b) * p.R + r], pool_key(best[cb] + sg * bv, besti[cb]));
-        }
-        best[cb] = -INFINITY; besti[cb] = 0;
+    auto flush_one = [&](int b, int cb, float bv_, int bi_) {
+      const int r = row_base + cb * 128 + q * 32 + lane;
+      if (r < p.R && bv_ > -INFINITY) {
+        // the running maximum is over the bias-free accumulator times sign(gamma); the key holds
+        // sign(gamma) * (y + bias), what pool_finalize_kernel expects
+        const float gm = p.gamma[r];
+        const float sg = gm > 0.f ? 1.f : (gm < 0.f ? -1.f : 0.f);
+        const float bs = p.bias ? p.bias[r] : 0.f;
+        atomicMax(&p.keys[static_cast<int64_t>(b) * p.R + r], pool_key(bv_ + sg * bs, bi_));
       }
     };
-    for (int t = t_begin; t < t_end; ++t) {
-      const int b = t / p.tpc, n0 = (t - b * p.tpc) * kNT;
-      const int nvalid = min(kNT, p.N - n0);
-      const int64_t m0 = static_cast<int64_t>(b) * p.N + n0;
-      if (b != cur_b) { flush_pool(cur_b); cur_b = b; }
+    for (int t = t_begin; t < t_end; ++t, it += KS, ++tc) {
+      const int b = t / p.tl.tpc, n0 = (t - b * p.tl.tpc) * kNT;
+      const int nvalid = min(kNT, p.tl.N - n0);
+      const int64_t m0 = static_cast<int64_t>(b) * p.tl.N + n0;
+      if (MODE == FWD_POOL && b != cur_b) {
+        if (cur_b >= 0) {
+          flush_one(cur_b, 0, best0, besti0);
+          if (p.CB == 2) flush_one(cur_b, 1, best1, besti1);
+        }
+        best0 = best1 = -INFINITY; besti0 = besti1 = 0;
+      }
+      cur_b = b;
+      if (MODE == DGRAD && p.side_slabs > 0) mbar_wait(smem_u32(&bars->side_full), tc & 1u);
 #pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
         if (cb >= p.CB) break;
@@ -309,20 +354,29 @@ __global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const WsParams p) {
         ++ac;
         const int r = row_base + cb * 128 + q * 32 + lane;   // this thread's output channel
         const bool rok = r < p.R;
-        mbar_wait(smem_u32(&bars->acc_full[slot]), aph);
-        tc_fence_after();
-        float s_t = 0.f, q_t = 0.f;
         // per-channel constants
         float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
         if (rok) {
           if (MODE == FWD_DENSE) e0 = p.bias ? p.bias[r] : 0.f;
           if (MODE == FWD_POOL) { const float gm = p.gamma[r]; e0 = gm > 0.f ? 1.f : (gm < 0.f ? -1.f : 0.f); }
-          if (MODE == DGRAD || MODE == POOL_DGRAD) {
-            if (p.out.grad_x == nullptr) { e0 = p.out.mean[r]; e1 = p.out.invstd[r]; e2 = p.out.gamma[r]; e3 = p.out.beta[r]; }
+          if ((MODE == DGRAD || MODE == POOL_DGRAD) && p.out.grad_x == nullptr) {
+            e0 = p.out.mean[r]; e1 = p.out.invstd[r]; e2 = p.out.gamma[r]; e3 = p.out.beta[r];
           }
         }
         const float uk = (MODE == POOL_DGRAD && rok) ? p.u[r] : 0.f;
-        for (int ch = 0; ch * 32 < nvalid; ++ch) {
+        // where this thread's mask / yhat source lives in shared memory (packed activation of the
+        // layer that produced the operand): POOL_DGRAD -> the streamed slabs, DGRAD -> the side buffer
+        const uint8_t* act_slab = nullptr;
+        if (MODE == POOL_DGRAD && rok) act_slab = b_smem + ((it + (r >> 6)) % p.nstage) * kSlabB;
+        if (MODE == DGRAD && p.side_slabs > 0 && rok) act_slab = side_smem + (r >> 6) * kSlabB;
+        const float inv_g = e2 != 0.f ? 1.0f / e2 : 0.f;
+        const bool to_x = p.out.grad_x != nullptr;
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};   // 4-way split sums: ILP for one warp
+        float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int bi[4] = {0, 0, 0, 0};
+        mbar_wait(smem_u32(&bars->acc_full[slot]), aph);
+        tc_fence_after();
+        for (int ch = half; ch * 32 < nvalid; ch += 2) {
           float v[32];
           tmem_ld32(tmem + lane_addr + slot * kNT + ch * 32, v);
           const int ncol = min(32, nvalid - ch * 32);
@@ -333,8 +387,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const WsParams p) {
               for (int i = 0; i < 32; ++i) {
                 if (i < ncol) {
                   yp[static_cast<int64_t>(i) * p.R] = v[i] + e0;
-                  s_t += v[i];
-                  q_t = fmaf(v[i], v[i], q_t);
+                  sa[i & 3] += v[i];
+                  qa[i & 3] = fmaf(v[i], v[i], qa[i & 3]);
                 }
               }
             }
@@ -342,40 +396,47 @@ __global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const WsParams p) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if (i < ncol) {
-                s_t += v[i];
-                q_t = fmaf(v[i], v[i], q_t);
+                sa[i & 3] += v[i];
+                qa[i & 3] = fmaf(v[i], v[i], qa[i & 3]);
                 const float vv = v[i] * e0;     // sign(gamma) * y: BN is monotone per channel
-                if (vv > best[cb]) { best[cb] = vv; besti[cb] = n0 + ch * 32 + i; }
+                if (vv > bv[i & 3]) { bv[i & 3] = vv; bi[i & 3] = n0 + ch * 32 + i; }
               }
             }
           } else {
             // dgrad epilogues
             int hv = -1;
             if (MODE == POOL_DGRAD) hv = (lane < ncol) ? __ldg(p.head + m0 + ch * 32 + lane) : -1;
-            const bool to_x = p.out.grad_x != nullptr;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if (i < ncol) {
                 float val = v[i];
+                const int col = ch * 32 + i;
                 if (MODE == POOL_DGRAD) {
+                  const int h = __shfl_sync(0xffffffffu, hv, i);
                   float sp = 0.f;
-                  int c = __shfl_sync(0xffffffffu, hv, i);
-                  while (c >= 0) {       // warp-uniform: every lane walks the same list
-                    if (rok) sp = fmaf(__ldg(p.coef + static_cast<int64_t>(b) * p.Cpool + c), __ldg(p.Wpool + static_cast<int64_t>(c) * p.K + r), sp);
-                    c = __ldg(p.next + static_cast<int64_t>(b) * p.Cpool + c);
-                  }
+                  if (h >= 0 && rok) sp = __ldg(p.srows + (static_cast<int64_t>(b) * p.Cpool + h) * p.K + r);
                   val = sp - uk - val;
                 }
                 if (rok) {
-                  const int64_t m = m0 + ch * 32 + i;
+                  const int64_t m = m0 + col;
                   if (to_x) {
-                    p.out.grad_x[(static_cast<int64_t>(b) * p.R + r) * p.N + n0 + ch * 32 + i] = val;
+                    p.out.grad_x[(static_cast<int64_t>(b) * p.R + r) * p.tl.N + n0 + col] = val;
                   } else {
-                    const float yh = (__ldg(p.out.y_prev + m * p.R + r) - e0) * e1;
-                    if (p.out.relu && !(fmaf(yh, e2, e3) > 0.f)) val = 0.f;
+                    float yh;
+                    bool on = true;
+                    if (act_slab != nullptr && e2 != 0.f) {
+                      // a = relu?(gamma*yhat + beta) in bf16: mask = a > 0, yhat = (a - beta) / gamma
+                      const float a = bf16_at(act_slab, col, r & 63);
+                      if (p.out.relu) on = a > 0.f;
+                      yh = (a - e3) * inv_g;
+                    } else {
+                      yh = (__ldg(p.out.y_prev + m * p.R + r) - e0) * e1;
+                      if (p.out.relu) on = fmaf(yh, e2, e3) > 0.f;
+                    }
+                    if (!on) val = 0.f;
                     p.out.dz_prev[m * p.R + r] = val;
-                    s_t += val;
-                    q_t = fmaf(val, yh, q_t);
+                    sa[i & 3] += val;
+                    qa[i & 3] = fmaf(val, yh, qa[i & 3]);
                   }
                 }
               }
@@ -383,48 +444,66 @@ __global__ void __launch_bounds__(kWsThreads, 1) ws_kernel(const WsParams p) {
           }
         }
         tc_fence_before();
-        mbar_arrive(smem_u32(&bars->acc_empty[slot]));
-        S[cb] += static_cast<double>(s_t);
-        Q[cb] += static_cast<double>(q_t);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[slot]));
+        const double s_t = static_cast<double>((sa[0] + sa[1]) + (sa[2] + sa[3]));
+        const double q_t = static_cast<double>((qa[0] + qa[1]) + (qa[2] + qa[3]));
+        if (cb == 0) { S0 += s_t; Q0 += q_t; } else { S1 += s_t; Q1 += q_t; }
+        if (MODE == FWD_POOL) {
+          // merge the 4 interleaved trackers, then into the cloud's running best: larger value, then lower index
+          float mv = bv[0]; int mi = bi[0];
+#pragma unroll
+          for (int k = 1; k < 4; ++k)
+            if (bv[k] > mv || (bv[k] == mv && bi[k] < mi)) { mv = bv[k]; mi = bi[k]; }
+          if (cb == 0) { if (mv > best0) { best0 = mv; besti0 = mi; } }
+          else { if (mv > best1) { best1 = mv; besti1 = mi; } }
+        }
+      }
+      if (kEpiReadsB) {
+        __syncwarp();
+        if (lane == 0)
+          for (int s = 0; s < KS; ++s) mbar_arrive(smem_u32(&bars->empty[(it + s) % p.nstage]));
+      }
+      if (MODE == DGRAD && p.side_slabs > 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->side_empty));
       }
     }
-    flush_pool(cur_b);
-    for (int cb = 0; cb < p.CB; ++cb) {
+    if (MODE == FWD_POOL && cur_b >= 0) {
+      flush_one(cur_b, 0, best0, besti0);
+      if (p.CB == 2) flush_one(cur_b, 1, best1, besti1);
+    }
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      if (cb >= p.CB) break;
       const int r = row_base + cb * 128 + q * 32 + lane;
       if (r >= p.R) continue;
+      const double Sv = cb == 0 ? S0 : S1, Qv = cb == 0 ? Q0 : Q1;
       if (MODE == FWD_DENSE || MODE == FWD_POOL) {
-        if (p.stats) { atomicAdd(&p.stats[r], S[cb]); atomicAdd(&p.stats[p.R + r], Q[cb]); }
+        if (p.stats) { atomicAdd(&p.stats[r], Sv); atomicAdd(&p.stats[p.R + r], Qv); }
       } else if (p.out.grad_x == nullptr) {
-        atomicAdd(&p.out.sums[r], S[cb]);
-        atomicAdd(&p.out.sums[p.R + r], Q[cb]);
+        atomicAdd(&p.out.sums[r], Sv);
+        atomicAdd(&p.out.sums[p.R + r], Qv);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, kTmemCols);
+  if (warp == 1) tmem_dealloc(tmem, kTmemCols);
 }
 
-// ---- point-contraction kernel (wgrad / Gram) ----------------------------------------------------
-//   D[c, k] = sum_{m in range} Pm[m, c] * Rm[m, k]     c: 128-lane block, k: Kr columns (<= 256)
-// GRAM: Pm = Rm = act (CPb = Kr = K <= 128 per block);  WGRAD: Pm = dy (this layer), Rm = act (previous layer)
-constexpr int kPT = 128;          // points per stage
-constexpr int kPtThreads = 288;   // warps 0-7 producers, warp 8 MMA (+ all of 0-3 for the final epilogue)
-
+// ================================= point-contraction GEMM ==========================================
+//   D[c, k] = sum_{m} P[m, c] * R[m, k]     c: one 128-lane block per blockIdx.y, k: Kr columns (<= 256)
+// WGRAD: P = packed dy of this layer, R = packed activation of the previous layer;  GRAM: P == R.
 struct PtParams {
-  int64_t M;
-  int S;                    // point-range splits
+  Tiling tl;
+  int S;                    // tile-range splits (gridDim.x)
   int C, Kr;                // rows of D (channels of P), columns of D (channels of R)
-  int gram;                 // 1: P == R == act
-  DySrc dy;                 // WGRAD
-  ActSrc act;               // R operand (and P for GRAM)
+  int gram;
+  int nstage;
+  const uint8_t* P;         // [n_tiles][C/64] slabs (unused for GRAM)
+  const uint8_t* Rm;        // [n_tiles][Kr/64] slabs
   float* partial;           // [S, C, Kr]
-  double* colsum;           // GRAM: [S, Kr] column sums of the bf16-rounded activation
-};
-
-struct PtConsts {
-  float d0[kMaxK], d1[kMaxK], d2[kMaxK];   // dy transform (per P channel)
-  float a0[kMaxK], a1[kMaxK];              // act transform (per R channel)
 };
 
 struct __align__(8) PtBarriers {
@@ -435,185 +514,81 @@ struct __align__(8) PtBarriers {
 __global__ void __launch_bounds__(kPtThreads, 1) pt_kernel(const PtParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int GR = p.Kr >> 6;                       // 64-channel groups of R
-  const int GP = p.gram ? 0 : 2;                  // 64-channel groups of P per 128-lane block (GRAM reuses R)
-  const int stage_bytes = (GP + GR) * kPT * 128;
-  const int nstage = 2;
-  PtConsts* pc = reinterpret_cast<PtConsts*>(smem + nstage * stage_bytes);
-  PtBarriers* bars = reinterpret_cast<PtBarriers*>(pc + 1);
-  float* csum = reinterpret_cast<float*>(bars + 1);   // [16][Kr] per-row-group column sums (GRAM)
+  const int GR = p.Kr >> 6;                       // slabs per tile of R
+  const int PC = p.C >> 6;                        // slabs per tile of P
+  const int cblk = blockIdx.y;
+  const int GP = p.gram ? 0 : min(2, PC - cblk * 2);   // P slabs this CTA needs per tile
+  const int stage_stride = ((p.gram ? 0 : 2) + GR) * kSlabB;
+  PtBarriers* bars = reinterpret_cast<PtBarriers*>(smem + p.nstage * stage_stride);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cblk = blockIdx.y;                    // 128-row block of D
   const int s = blockIdx.x;
-  const int64_t chunk = ((p.M + p.S - 1) / p.S + kPT - 1) / kPT * kPT;
-  const int64_t m_begin = s * chunk, m_end = min(p.M, m_begin + chunk);
-  const int n_steps = m_end > m_begin ? static_cast<int>((m_end - m_begin + kPT - 1) / kPT) : 0;
+  const int t_begin = static_cast<int>(static_cast<int64_t>(p.tl.n_tiles) * s / p.S);
+  const int t_end = static_cast<int>(static_cast<int64_t>(p.tl.n_tiles) * (s + 1) / p.S);
+  const int n_steps = t_end - t_begin;
   const uint32_t ncols = p.Kr <= 32 ? 32u : (p.Kr <= 64 ? 64u : (p.Kr <= 128 ? 128u : 256u));
+  const int p_off = p.gram ? 0 : 2;               // R slabs start after the (up to) two P slabs
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < nstage; ++i) { mbar_init(smem_u32(&bars->full[i]), 256); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    for (int i = 0; i < p.nstage; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
     mbar_init(smem_u32(&bars->done), 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(&bars->tmem_base), ncols);
-  for (int k = threadIdx.x; k < p.Kr; k += blockDim.x) {
-    if (p.act.y != nullptr) {
-      const float sc = p.act.invstd[k] * p.act.gamma[k];
-      pc->a0[k] = sc; pc->a1[k] = p.act.beta[k] - p.act.mean[k] * sc;
-    } else { pc->a0[k] = 1.f; pc->a1[k] = 0.f; }
-  }
-  if (!p.gram)
-    for (int k = threadIdx.x; k < 128; k += blockDim.x) {
-      const int c = cblk * 128 + k;
-      if (c < p.C) {
-        pc->d0[k] = p.dy.gamma[c] * p.dy.invstd[c];
-        pc->d1[k] = -p.dy.kappa[c];
-        pc->d2[k] = p.dy.kappa[c] * p.dy.mean[c] - p.dy.alpha[c];
-      } else { pc->d0[k] = 0.f; pc->d1[k] = 0.f; pc->d2[k] = 0.f; }
-    }
+  if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), ncols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp < 8) {
-    // producers: 256 threads; thread -> chunk column cc (8 channels), rows rg + 32*i
-    const int ptid = threadIdx.x;
-    const int cc = ptid & 7, rg = ptid >> 3;       // rg in [0, 32)
-    float colacc[4][8];                            // GRAM: up to 4 R groups... (Kr <= 256)
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) colacc[a][e] = 0.f;
-    for (int it = 0; it < n_steps; ++it) {
-      const uint32_t stage = it & 1u, ph = (it >> 1) & 1u;
-      mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1u);
-      uint8_t* sb = smem + stage * stage_bytes;
-      const int64_t mt = m_begin + static_cast<int64_t>(it) * kPT;
-      // P groups (dy of this layer's channels cblk*128 ..)
-      for (int gidx = 0; gidx < GP; ++gidx) {
-        const int kl = gidx * 64 + cc * 8;          // local channel in the 128-block
-        const int c0 = cblk * 128 + kl;
-        float q0[8], q1[8], q2[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { q0[e] = pc->d0[kl + e]; q1[e] = pc->d1[kl + e]; q2[e] = pc->d2[kl + e]; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = rg + 32 * i;
-          const int64_t m = mt + r;
-          float a[8];
-          if (m < m_end && c0 < p.C) {
-            float v[8], w[8];
-            ld8(p.dy.dz + m * p.C + c0, v);
-            ld8(p.dy.y + m * p.C + c0, w);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) a[e] = fmaf(v[e], q0[e], fmaf(w[e], q1[e], q2[e]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) a[e] = 0.f;
-          }
-          *reinterpret_cast<uint4*>(sb + gidx * (kPT * 128) + slab_off(r, cc)) = pack8(a);
-        }
-      }
-      // R groups (activation of the previous layer)
-#pragma unroll
-      for (int gidx = 0; gidx < 4; ++gidx) {
-        if (gidx >= GR) break;
-        const int k0 = gidx * 64 + cc * 8;
-        float q0[8], q1[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { q0[e] = pc->a0[k0 + e]; q1[e] = pc->a1[k0 + e]; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = rg + 32 * i;
-          const int64_t m = mt + r;
-          float a[8];
-          if (m < m_end) {
-            if (p.act.y != nullptr) {
-              float v[8];
-              ld8(p.act.y + m * p.Kr + k0, v);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float t = fmaf(v[e], q0[e], q1[e]);
-                a[e] = p.act.relu ? fmaxf(t, 0.f) : t;
-              }
-            } else {
-              const int64_t b = m / p.act.N, n = m - b * p.act.N;
-              const float* px = p.act.x + b * p.act.sxb + n * p.act.sxn;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a[e] = __ldg(px + static_cast<int64_t>(k0 + e) * p.act.sxc);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) a[e] = 0.f;
-          }
-          const uint4 pk = pack8(a);
-          *reinterpret_cast<uint4*>(sb + (GP + gidx) * (kPT * 128) + slab_off(r, cc)) = pk;
-          if (p.gram) {
-            // column sums of exactly what the tensor core will see
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(h[e]);
-              colacc[gidx][2 * e] += f.x;
-              colacc[gidx][2 * e + 1] += f.y;
-            }
-          }
-        }
-      }
-      fence_proxy_async();
-      mbar_arrive(smem_u32(&bars->full[stage]));
-    }
-    if (p.gram) {
-      // reduce the 32 row groups in a fixed order: csum[rg][k] -> thread k sums over rg
-#pragma unroll
-      for (int gidx = 0; gidx < 4; ++gidx) {
-        if (gidx >= GR) break;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) csum[rg * p.Kr + gidx * 64 + cc * 8 + e] = colacc[gidx][e];
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int k = ptid; k < p.Kr; k += 256) {
-        double acc = 0.0;
-        for (int r2 = 0; r2 < 32; ++r2) acc += static_cast<double>(csum[r2 * p.Kr + k]);
-        p.colsum[static_cast<int64_t>(s) * p.Kr + k] = acc;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_steps; ++i) {
+        const uint32_t stage = i % p.nstage, ph = (i / p.nstage) & 1u;
+        const int t = t_begin + i;
+        mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1u);
+        mbar_arrive_expect_tx(smem_u32(&bars->full[stage]), static_cast<uint32_t>((GP + GR) * kSlabB));
+        uint8_t* sb = smem + stage * stage_stride;
+        for (int gi = 0; gi < GP; ++gi)
+          bulk_g2s(smem_u32(sb + gi * kSlabB), p.P + (static_cast<int64_t>(t) * PC + cblk * 2 + gi) * kSlabB, kSlabB,
+                   smem_u32(&bars->full[stage]));
+        for (int gi = 0; gi < GR; ++gi)
+          bulk_g2s(smem_u32(sb + (p_off + gi) * kSlabB), p.Rm + (static_cast<int64_t>(t) * GR + gi) * kSlabB, kSlabB,
+                   smem_u32(&bars->full[stage]));
       }
     }
-  } else {
-    // MMA issuer
+  } else if (warp == 1) {
     const uint32_t idesc = make_idesc(128, p.Kr, 1, 1);
-    for (int it = 0; it < n_steps; ++it) {
-      const uint32_t stage = it & 1u, ph = (it >> 1) & 1u;
+    for (int i = 0; i < n_steps; ++i) {
+      const uint32_t stage = i % p.nstage, ph = (i / p.nstage) & 1u;
       mbar_wait(smem_u32(&bars->full[stage]), ph);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t sb = smem_u32(smem + stage * stage_bytes);
-        const uint32_t pa = p.gram ? sb + (cblk * 2) * (kPT * 128) : sb;   // GRAM: lanes = R groups 2*cblk, 2*cblk+1
-        const uint32_t ra = sb + GP * (kPT * 128);
+        const uint32_t sb = smem_u32(smem + stage * stage_stride);
+        const uint32_t pa = p.gram ? sb + (cblk * 2) * kSlabB : sb;   // GRAM: the lanes are R's channel groups 2*cblk, 2*cblk+1
+        const uint32_t ra = sb + p_off * kSlabB;
 #pragma unroll
-        for (int kk = 0; kk < kPT / 16; ++kk) {
-          const uint64_t adesc = make_sdesc(pa + kk * 2048, kPT * 128, 1024);
-          const uint64_t bdesc = make_sdesc(ra + kk * 2048, kPT * 128, 1024);
-          umma_bf16(tmem, adesc, bdesc, idesc, (it | kk) != 0);
+        for (int kk = 0; kk < kNT / 16; ++kk) {
+          const uint64_t adesc = make_sdesc(pa + kk * 2048, kSlabB, 1024);
+          const uint64_t bdesc = make_sdesc(ra + kk * 2048, kSlabB, 1024);
+          umma_bf16(tmem, adesc, bdesc, idesc, (i | kk) != 0);
         }
         umma_commit(smem_u32(&bars->empty[stage]));
-        if (it == n_steps - 1) umma_commit(smem_u32(&bars->done));
+        if (i == n_steps - 1) umma_commit(smem_u32(&bars->done));
       }
       __syncwarp();
     }
-  }
-  // final epilogue: warps 0-3 read the accumulator (lane quarter = warp) and write the partial
-  if (warp < 4) {
+  } else if (warp >= 4) {
+    // final epilogue: lane quarter = warp % 4, write this split's partial
+    const int q = warp & 3;
     float* outp = p.partial + (static_cast<int64_t>(s) * p.C) * p.Kr;
-    const int c = cblk * 128 + warp * 32 + lane;
+    const int c = cblk * 128 + q * 32 + lane;
     if (n_steps > 0) {
       mbar_wait(smem_u32(&bars->done), 0);
       tc_fence_after();
     }
     for (int ch = 0; ch * 32 < p.Kr; ++ch) {
       float v[32];
-      if (n_steps > 0) tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + ch * 32, v);
+      if (n_steps > 0) tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + ch * 32, v);
       else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -627,29 +602,29 @@ __global__ void __launch_bounds__(kPtThreads, 1) pt_kernel(const PtParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, ncols);
+  if (warp == 1) tmem_dealloc(tmem, ncols);
 }
 
-// ---- host side ----------------------------------------------------------------------------------
-constexpr int kSmemBudget = 227 * 1024;
-
+// ================================= host side =======================================================
 struct WsPlan {
   int CB, G, nstage, grid;
   size_t smem;
   bool ok;
 };
 
-WsPlan plan_ws(int R, int K, int n_tiles) {
+WsPlan plan_ws(int mode, int R, int K, int n_tiles, int side_slabs) {
   WsPlan pl{};
   const int KS = K / 64;
   const int rblocks = (R + 127) / 128;
-  const size_t fixed = 1024 + sizeof(ProducerConsts) + sizeof(WsBarriers) + 64;
+  const size_t fixed = 1024 + sizeof(WsBarriers) + 64 + static_cast<size_t>(side_slabs) * kSlabB;
   pl.CB = (rblocks >= 2 && (rblocks % 2) == 0 && K <= 128) ? 2 : 1;
   for (;;) {
     const size_t a = static_cast<size_t>(pl.CB) * KS * kSlabA;
-    const int ns = static_cast<int>((kSmemBudget - fixed - a) / kSlabB);
+    const int ns = a + fixed < static_cast<size_t>(kSmemBudget) ? static_cast<int>((kSmemBudget - fixed - a) / kSlabB) : 0;
     pl.nstage = std::min(8, ns);
-    const int need = pl.CB == 2 ? 2 * KS : 2;   // CB == 2 keeps a whole tile resident while the next is produced
+    // CB == 2 and POOL_DGRAD keep a whole tile resident (second row block / epilogue reads) while the next streams in
+    const bool hold = pl.CB == 2 || mode == POOL_DGRAD;
+    const int need = hold ? KS + 1 : std::min(2, KS + 1);
     if (pl.nstage >= need) break;
     if (pl.CB == 2) { pl.CB = 1; continue; }
     pl.ok = false;
@@ -665,8 +640,8 @@ WsPlan plan_ws(int R, int K, int n_tiles) {
 
 template <int MODE>
 int launch_ws(WsParams& p, cudaStream_t st, const char* what) {
-  const WsPlan pl = plan_ws(p.R, p.K, p.n_tiles);
-  if (!pl.ok) return fail(PCUDA_E_UNSUPPORTED, "%s: K=%d does not fit the tensor-core kernel", what, p.K);
+  const WsPlan pl = plan_ws(MODE, p.R, p.K, p.tl.n_tiles, p.side_slabs);
+  if (!pl.ok) return fail(PCUDA_E_UNSUPPORTED, "%s: K=%d R=%d does not fit the tensor-core kernel", what, p.K, p.R);
   p.CB = pl.CB; p.G = pl.G; p.nstage = pl.nstage;
   static bool attr_done[4] = {false, false, false, false};
   if (!attr_done[MODE]) {
@@ -674,60 +649,93 @@ int launch_ws(WsParams& p, cudaStream_t st, const char* what) {
     if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
     attr_done[MODE] = true;
   }
-  ws_kernel<MODE><<<pl.grid, kWsThreads, pl.smem, st>>>(p);
+  ws_kernel<MODE><<<pl.grid, kThreads, pl.smem, st>>>(p);
   count_launch();
   return check_launch(what);
 }
 
-WsParams base_params(int B, int N, int K, int R) {
-  WsParams p{};
-  p.B = B; p.N = N; p.tpc = (N + kNT - 1) / kNT; p.n_tiles = B * p.tpc; p.K = K; p.R = R;
-  return p;
+int pack_grid(int64_t units) {
+  const int64_t blocks = (units + 255) / 256;
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(blocks, static_cast<int64_t>(sm_count()) * 8)));
 }
 
 }  // namespace
 
+bool fwd_fits(int cout, int cin) { return supports(cin) && plan_ws(FWD_POOL, cout, cin, 1, 0).ok; }
+bool dgrad_fits(int Kp, int C, bool with_side) {
+  return supports(C) && Kp >= 64 && plan_ws(DGRAD, Kp, C, 1, with_side ? Kp / 64 : 0).ok;
+}
+bool pool_dgrad_fits(int K) { return supports(K) && plan_ws(POOL_DGRAD, K, K, 1, 0).ok; }
+
+Tiling make_tiling(int B, int N) {
+  Tiling t{};
+  t.B = B; t.N = N; t.tpc = (N + kNT - 1) / kNT; t.n_tiles = B * t.tpc;
+  return t;
+}
+
 bool supports(int cin) { return cin >= 64 && cin <= kMaxK && (cin % 64) == 0; }
 
-int fwd_layer(const ActSrc& src, const pcuda_mlp_layer_t& L, bool pool, int B, int N, double* stats,
-              unsigned long long* keys, cudaStream_t st) {
-  WsParams p = base_params(B, N, L.cin, L.cout);
-  p.act = src; p.A = L.weight; p.bias = L.bias; p.gamma = L.gamma; p.y_out = L.y; p.stats = stats; p.keys = keys;
+size_t act_pack_bytes(const Tiling& tl, int C) { return static_cast<size_t>(tl.n_tiles) * (C / 64) * kSlabB; }
+size_t w_pack_bytes(int R, int K) { return static_cast<size_t>((R + 127) / 128) * K * 256; }
+
+int pack_act(const ActSrc& src, const Tiling& tl, uint8_t* out, cudaStream_t st) {
+  pack_act_kernel<<<pack_grid(static_cast<int64_t>(tl.n_tiles) * kNT * (src.C / 8)), 256, 0, st>>>(src, tl, out);
+  count_launch();
+  return check_launch("tc::pack_act");
+}
+int pack_dy(const DySrc& dys, const Tiling& tl, uint8_t* out, cudaStream_t st) {
+  pack_dy_kernel<<<pack_grid(static_cast<int64_t>(tl.n_tiles) * kNT * (dys.C / 8)), 256, 0, st>>>(dys, tl, out);
+  count_launch();
+  return check_launch("tc::pack_dy");
+}
+int pack_w(const float* W, int R, int K, bool transposed, uint8_t* out, cudaStream_t st) {
+  pack_w_kernel<<<pack_grid(static_cast<int64_t>((R + 127) / 128) * 128 * (K / 8)), 256, 0, st>>>(W, R, K, transposed ? 1 : 0, out);
+  count_launch();
+  return check_launch("tc::pack_w");
+}
+
+int fwd_layer(const Tiling& tl, const uint8_t* a_pack, const uint8_t* w_pack, const pcuda_mlp_layer_t& L, bool pool,
+              double* stats, unsigned long long* keys, cudaStream_t st) {
+  WsParams p{};
+  p.tl = tl; p.K = L.cin; p.R = L.cout; p.A = w_pack; p.Bop = a_pack;
+  p.bias = L.bias; p.gamma = L.gamma; p.y_out = L.y; p.stats = stats; p.keys = keys;
   return pool ? launch_ws<FWD_POOL>(p, st, "tc::fwd_layer(pool)") : launch_ws<FWD_DENSE>(p, st, "tc::fwd_layer");
 }
 
-int dgrad_layer(const DySrc& dys, const float* W, int B, int N, const DgradOut& out, cudaStream_t st) {
-  WsParams p = base_params(B, N, dys.C, out.Cp);
-  p.dy = dys; p.A = W; p.out = out;
+int dgrad_layer(const Tiling& tl, const uint8_t* dy_pack, int C, const uint8_t* wt_pack, const uint8_t* aprev_pack,
+                const DgradOut& out, cudaStream_t st) {
+  WsParams p{};
+  p.tl = tl; p.K = C; p.R = out.Cp; p.A = wt_pack; p.Bop = dy_pack; p.out = out;
+  p.side = aprev_pack;
+  p.side_slabs = (aprev_pack != nullptr && out.grad_x == nullptr) ? out.Cp / 64 : 0;
   return launch_ws<DGRAD>(p, st, "tc::dgrad_layer");
 }
 
-int pool_dgrad(const ActSrc& src, const float* Q, const float* u, const float* Wpool, const float* coef,
-               const int* head, const int* next, int Cpool, int B, int N, const DgradOut& out, cudaStream_t st) {
-  WsParams p = base_params(B, N, src.C, src.C);
-  p.act = src; p.A = Q; p.u = u; p.Wpool = Wpool; p.coef = coef; p.head = head; p.next = next; p.Cpool = Cpool;
+int pool_dgrad(const Tiling& tl, const uint8_t* a_pack, int K, const uint8_t* q_pack, const float* u, const int* head,
+               const float* srows, int Cpool, const DgradOut& out, cudaStream_t st) {
+  WsParams p{};
+  p.tl = tl; p.K = K; p.R = K; p.A = q_pack; p.Bop = a_pack; p.u = u; p.head = head; p.srows = srows; p.Cpool = Cpool;
   p.out = out;
   return launch_ws<POOL_DGRAD>(p, st, "tc::pool_dgrad");
 }
 
-int pt_splits(int64_t M, int rblocks) {
-  const int64_t steps = (M + kPT - 1) / kPT;
-  int64_t S = std::max<int64_t>(1, sm_count() / std::max(1, rblocks));
-  if (S > steps) S = steps;
-  return static_cast<int>(S);
+int pt_splits(const Tiling& tl, int rblocks) {
+  return std::max(1, std::min(tl.n_tiles, sm_count() / std::max(1, rblocks)));
 }
 
 bool pt_supports(int C, int Kr, bool gram) {
   if (Kr % 64 != 0 || Kr < 64 || Kr > 256) return false;
-  if (gram) return C == Kr && Kr <= 256;
-  return C >= 64 && (C % 8) == 0;
+  if (gram) return C == Kr;
+  return C >= 64 && (C % 64) == 0 && C <= kMaxK;
 }
 
 static int launch_pt(PtParams& p, cudaStream_t st, const char* what) {
   const int GR = p.Kr / 64, GP = p.gram ? 0 : 2;
-  const size_t smem = 1024 + 2 * static_cast<size_t>(GP + GR) * kPT * 128 + sizeof(PtConsts) + sizeof(PtBarriers) +
-                      (p.gram ? sizeof(float) * 32 * p.Kr : 0) + 64;
-  if (smem > static_cast<size_t>(kSmemBudget)) return fail(PCUDA_E_UNSUPPORTED, "%s: Kr=%d does not fit", what, p.Kr);
+  const size_t stage = static_cast<size_t>(GP + GR) * kSlabB;
+  const size_t fixed = 1024 + sizeof(PtBarriers) + 64;
+  const int ns = static_cast<int>((kSmemBudget - fixed) / stage);
+  if (ns < 1) return fail(PCUDA_E_UNSUPPORTED, "%s: Kr=%d does not fit", what, p.Kr);
+  p.nstage = std::min(4, ns);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(pt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
@@ -735,20 +743,21 @@ static int launch_pt(PtParams& p, cudaStream_t st, const char* what) {
     attr_done = true;
   }
   const dim3 grid(p.S, (p.C + 127) / 128);
-  pt_kernel<<<grid, kPtThreads, smem, st>>>(p);
+  pt_kernel<<<grid, kPtThreads, fixed + p.nstage * stage, st>>>(p);
   count_launch();
   return check_launch(what);
 }
 
-int wgrad_layer(const DySrc& dys, const ActSrc& prev, int64_t M, int S, float* partial, cudaStream_t st) {
+int wgrad_layer(const Tiling& tl, const uint8_t* dy_pack, int C, const uint8_t* aprev_pack, int Kr, int S, float* partial,
+                cudaStream_t st) {
   PtParams p{};
-  p.M = M; p.S = S; p.C = dys.C; p.Kr = prev.C; p.gram = 0; p.dy = dys; p.act = prev; p.partial = partial;
+  p.tl = tl; p.S = S; p.C = C; p.Kr = Kr; p.gram = 0; p.P = dy_pack; p.Rm = aprev_pack; p.partial = partial;
   return launch_pt(p, st, "tc::wgrad_layer");
 }
 
-int gram(const ActSrc& act, int64_t M, int S, float* partial, double* colsum, cudaStream_t st) {
+int gram(const Tiling& tl, const uint8_t* a_pack, int K, int S, float* partial, cudaStream_t st) {
   PtParams p{};
-  p.M = M; p.S = S; p.C = act.C; p.Kr = act.C; p.gram = 1; p.act = act; p.partial = partial; p.colsum = colsum;
+  p.tl = tl; p.S = S; p.C = K; p.Kr = K; p.gram = 1; p.Rm = a_pack; p.partial = partial;
   return launch_pt(p, st, "tc::gram");
 }
 

@@ -47,6 +47,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     else if (now - t0 > 4000000000ll) __trap();
   }
 }
+// arm the barrier with one arrival of this thread plus `bytes` of expected bulk-copy traffic
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit (UBLKCP): `bytes` (multiple of 16) from
+// 16-byte-aligned `src` to 16-byte-aligned shared `dst`, completing on `bar` (complete_tx)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -77,6 +77,8 @@ class AdversarialStep:
         self.grad_vertS = torch.zeros(B, N, 3, **f32)
         self.grad_vertT = torch.zeros(B, N, 3, **f32)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_post: Optional[torch.cuda.CUDAGraph] = None
+        self._res = []
         self._ones = torch.ones(B, 1, **f32)
         self._zeros = torch.zeros(B, 1, **f32)
 
@@ -99,7 +101,7 @@ class AdversarialStep:
         return out, leaves
 
     # -- the step -----------------------------------------------------------------------------------
-    def _body(self) -> None:
+    def _pre(self) -> None:
         cfg, I = self.cfg, self.inputs
         res = []
         # P0: zero D4's gradients (they live in the flat bucket), freeze D4
@@ -149,24 +151,38 @@ class AdversarialStep:
         acc_t = 1.0 - (torch.sigmoid(D_out4.detach()) >= 0.5).float().mean()
         res += [loss_D_same4.detach(), loss_D_diff_4.detach(), acc_s, acc_t]
 
-        # P5: gradient all-reduce (one bucket) + SGD step
+        self._res = res
+
+    def _post(self) -> None:
+        # P5 (after the gradient all-reduce): SGD step of D4, scalars of the step into one small tensor
         self.bucket.attach()
-        self.bucket.allreduce_mean()
         self.opt.step()
-        self.result.copy_(torch.stack([r.reshape(()).float() for r in res]))
+        self.result.copy_(torch.stack([r.reshape(()).float() for r in self._res]))
+
+    def _body(self) -> None:
+        self._pre()
+        self.bucket.allreduce_mean()
+        self._post()
 
     def run(self) -> torch.Tensor:
         """One step on the current stream (eager launches or graph replay). Returns the device-side
         result vector (RESULT_FIELDS)."""
         if self.graph is not None:
             self.graph.replay()
+            if self.graph_post is not None:
+                # multi-GPU: the one NCCL call of the step sits between the two captured halves
+                self.bucket.allreduce_mean()
+                self.graph_post.replay()
         else:
             self._body()
         return self.result
 
     def capture(self, warmup: int = 3) -> None:
-        """Capture the step into a CUDA graph (single-GPU; with NCCL in the step the eager path is
-        used so the collective stays on NCCL's own stream ordering)."""
+        """Capture the step into CUDA graphs.  Single GPU: one graph.  With a process group the step
+        is captured as two graphs around the gradient all-reduce, which stays an ordinary NCCL call
+        on the same stream."""
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -175,6 +191,15 @@ class AdversarialStep:
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._body()
-        self.graph = g
+        if not multi:
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph, self.graph_post = g, None
+            return
+        pool = torch.cuda.graph_pool_handle()
+        with torch.cuda.graph(g, pool=pool):
+            self._pre()
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, pool=pool):
+            self._post()
+        self.graph, self.graph_post = g, g2

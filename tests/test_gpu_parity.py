@@ -280,13 +280,15 @@ def _torch_stack(x, layers, pool, train, dtype):
     """Plain-torch restatement of a Conv1d(k=1)+BatchNorm1d(+ReLU) stack (+max over points)."""
     a = x.to(dtype)
     margin = float("inf")      # smallest |BN output| entering a ReLU: how close any unit is to switching
-    for Ld in layers:
+    for li, Ld in enumerate(layers):
         a = F.conv1d(a, Ld["weight"].to(dtype).reshape(Ld["weight"].shape[0], -1, 1), Ld["bias"].to(dtype))
         a = F.batch_norm(a, Ld["rm"].to(dtype), Ld["rv"].to(dtype), Ld["gamma"].to(dtype), Ld["beta"].to(dtype),
                          training=train, momentum=0.1, eps=1e-5)
         if Ld["relu"]:
-            nz = a.detach().abs()
-            nz = nz[:, Ld["gamma"].detach() != 0]          # gamma == 0 channels are constant: no switch possible
+            nz = a.detach()
+            if pool and li == len(layers) - 1:
+                nz = nz.max(dim=2, keepdim=True)[0]        # ReLU after the max-pool only sees the pooled value
+            nz = nz.abs()[:, Ld["gamma"].detach() != 0]    # gamma == 0 channels are constant: no switch possible
             if nz.numel():
                 margin = min(margin, nz.min().item())
             a = F.relu(a)
@@ -489,3 +491,119 @@ def test_pointnetcls_batch_of_one_raises():
     net = PointNetCls().to(DEV)
     with pytest.raises(ops.PcudaError):
         net(torch.rand(1, 3, 64, device=DEV))
+
+
+# ================================================= PointNet shared MLP on the tensor cores (bf16) ====
+TC_STACKS = [
+    # chans, relus, B, N
+    ([3, 64, 128, 1024], [True, True, True], 4, 64),        # STN3d trunk, partial tile
+    ([3, 64, 128, 1024], [True, True, False], 8, 300),      # main trunk at the reference's cloud size (cfg-1/2)
+    ([3, 64, 128, 1024], [True, True, False], 3, 1024),     # cfg-3 cloud size, full tiles
+    ([64, 64, 128, 1024], [True, True, True], 3, 70),       # STNkd trunk: first layer already wide
+    ([64, 128, 1024], [True, False], 4, 100),               # feature-transform post stack
+    ([3, 8, 64, 128, 256, 512, 1024], [True, True, True, True, False, True], 3, 40),   # ext trunk (K up to 512)
+]
+
+
+def _tc_stack(chans, relus, B, N, seed):
+    import torch.nn as nn
+    rs = np.random.RandomState(seed)
+    torch.manual_seed(seed)
+    convs, bns = [], []
+    for l in range(len(chans) - 1):
+        conv = nn.Conv1d(chans[l], chans[l + 1], 1).to(DEV)
+        bn = nn.BatchNorm1d(chans[l + 1]).to(DEV)
+        with torch.no_grad():
+            bn.weight.copy_(torch.from_numpy(1.0 + 0.5 * rs.standard_normal(chans[l + 1])).float())
+            bn.bias.copy_(torch.from_numpy(0.2 * rs.standard_normal(chans[l + 1])).float())
+        convs.append(conv); bns.append(bn)
+    pts = torch.from_numpy(rs.rand(B, N, chans[0])).float().to(DEV)
+    return convs, bns, pts
+
+
+def _tc_run(convs, bns, pts, relus, mask, precision="bf16"):
+    from pointcloududa_b200.networks.PointNetCls import shared_mlp
+    ops.tune(3, mask)
+    try:
+        for m in convs + bns:
+            for p in m.parameters():
+                p.grad = None
+        for bn in bns:
+            bn.reset_running_stats()
+        x = pts.transpose(2, 1).detach().requires_grad_(True)
+        out = shared_mlp(x, convs, bns, relus, pool=True, precision=precision)
+        w = torch.from_numpy(np.random.RandomState(7).standard_normal(tuple(out.shape))).float().to(DEV)
+        (out * w).sum().backward()
+        torch.cuda.synchronize()
+        g = {"out": out.detach().clone(), "gx": x.grad.clone()}
+        for l, (c, b) in enumerate(zip(convs, bns)):
+            g[f"gW{l}"] = c.weight.grad.clone()
+            g[f"ggamma{l}"] = b.weight.grad.clone()
+            g[f"gbeta{l}"] = b.bias.grad.clone()
+            g[f"rm{l}"] = b.running_mean.clone()
+            g[f"rv{l}"] = b.running_var.clone()
+        return g
+    finally:
+        ops.tune(3, 0)
+
+
+@pytest.mark.parametrize("chans,relus,B,N", TC_STACKS)
+def test_shared_mlp_tensor_core_forward(chans, relus, B, N):
+    """bf16 tcgen05 forward (values, BatchNorm running statistics) against an fp64 torch evaluation:
+    1e-2 relative, the bar BASELINE.json states for the bf16 MLP."""
+    convs, bns, pts = _tc_stack(chans, relus, B, N, seed=B * 100 + N)
+    ref_layers = [dict(weight=c.weight.detach().double(), bias=c.bias.detach().double(), gamma=b.weight.detach().double(),
+                       beta=b.bias.detach().double(), rm=torch.zeros_like(b.running_mean).double(),
+                       rv=torch.ones_like(b.running_var).double(), relu=r) for c, b, r in zip(convs, bns, relus)]
+    out_r, _ = _torch_stack(pts.transpose(2, 1).double(), ref_layers, True, True, torch.float64)
+    g = _tc_run(convs, bns, pts, relus, mask=0)
+    assert max_rel(g["out"].cpu().numpy(), out_r.cpu().numpy()) < 1e-2
+    for l, Ld in enumerate(ref_layers):
+        assert max_rel(g[f"rm{l}"].cpu().numpy(), Ld["rm"].cpu().numpy()) < 1e-2
+        assert max_rel(g[f"rv{l}"].cpu().numpy(), Ld["rv"].cpu().numpy()) < 1e-2
+
+
+@pytest.mark.parametrize("chans,relus,B,N", TC_STACKS)
+def test_shared_mlp_tensor_core_backward(chans, relus, B, N):
+    """tcgen05 backward (pooled low-rank dgrad, dense dgrad, wgrad, Gram) against the FP32 backward
+    kernels run through the SAME tensor-core forward (identical arg-max selection and saved statistics;
+    a bf16 forward may legitimately pick a different, nearly tied arg-max point than an fp32 one, so
+    point-wise gradient comparison across forwards is ill-posed).  1e-2 in L2, 3e-2 max-norm."""
+    convs, bns, pts = _tc_stack(chans, relus, B, N, seed=B * 100 + N + 1)
+    ref = _tc_run(convs, bns, pts, relus, mask=30)      # tensor-core forward, FP32 backward
+    got = _tc_run(convs, bns, pts, relus, mask=0)       # everything on tensor cores
+    assert torch.equal(ref["out"], got["out"])          # same forward, bit for bit
+    for k in ref:
+        if k == "out" or k.startswith(("rm", "rv")):
+            continue
+        a, b = got[k].double(), ref[k].double()
+        scale_n, scale_m = b.norm().item(), b.abs().max().item()
+        if k.startswith(("ggamma", "gbeta")):   # may be mathematically zero: use the weight gradient's scale
+            wk = ref["gW" + k.lstrip("gamebt")].double()
+            scale_m = max(scale_m, 1e-2 * wk.abs().max().item())
+            scale_n = max(scale_n, 1e-2 * wk.norm().item() / max(1.0, (wk.numel() / b.numel()) ** 0.5))
+        assert torch.isfinite(a).all(), k
+        assert (a - b).norm().item() <= 1e-2 * scale_n, (k, (a - b).norm().item() / scale_n)
+        assert (a - b).abs().max().item() <= 3e-2 * scale_m, (k, (a - b).abs().max().item() / scale_m)
+
+
+@pytest.mark.parametrize("case", ["default_b4_n64", "default_b6_n300", "ft_b5_n48", "nostn_b4_n32"])
+def test_pointnetcls_bf16_vs_reference_golden(golden_pointnet, case):
+    """Whole discriminator with the tensor-core MLP against the reference's own logits and loss."""
+    from pointcloududa_b200.networks.PointNetCls import PointNetCls
+    g = golden_pointnet[case]
+    kw, B, N, seed = POINTNET_CASES[case]
+    net = PointNetCls(drop=0.0, precision="bf16", **kw)
+    _load_params(net, oracle.make_params(oracle.PointNetSpec(**kw), seed))
+    net.to(DEV).train()
+    x = torch.from_numpy(g["pts"]).to(DEV).transpose(2, 1).requires_grad_(True)
+    logit, trans, _ = net(x)
+    assert max_rel(logit.detach().cpu().numpy(), g["logit"]) < 3e-2
+    if "trans" in g:
+        assert max_rel(trans.detach().cpu().numpy(), g["trans"]) < 3e-2
+    loss = F.binary_cross_entropy_with_logits(logit, torch.ones_like(logit))
+    assert abs(loss.item() - float(g["loss"])) < 1e-2 * max(abs(float(g["loss"])), 1.0)
+    loss.backward()
+    assert torch.isfinite(x.grad).all() and x.grad.abs().max() > 0
+    for k, p in net.named_parameters():
+        assert p.grad is None or torch.isfinite(p.grad).all(), k

@@ -50,8 +50,13 @@ def worker(case_name: str, mask: int) -> None:
     pts = torch.from_numpy(rs.rand(B, N, chans[0])).float().to(dev)
     res = {}
     outs = {}
-    for prec in ("fp32", "bf16"):
-        ops.tune(3, mask if prec == "bf16" else 0)
+    # three evaluations: FP32 kernels; tensor-core forward + FP32 backward (mask 30); the mask under test.
+    # Forward quantities are compared with FP32.  Backward quantities are compared with the mask-30 run:
+    # both back-propagate through the SAME tensor-core forward (same arg-max selection, same saved
+    # statistics), so they must agree to bf16 rounding, whereas a bf16 forward may legitimately select
+    # a different, nearly tied arg-max point than the FP32 forward.
+    for tag, prec, mk in (("fp32", "fp32", 0), ("tcfwd", "bf16", 30), ("test", "bf16", mask)):
+        ops.tune(3, mk)
         for m in convs + bns:
             for p in m.parameters():
                 p.grad = None
@@ -69,16 +74,18 @@ def worker(case_name: str, mask: int) -> None:
             g[f"gbeta{l}"] = b.bias.grad.clone()
             g[f"rm{l}"] = b.running_mean.clone()
             g[f"rv{l}"] = b.running_var.clone()
-        outs[prec] = g
+        outs[tag] = g
     ops.tune(3, 0)
     for k in outs["fp32"]:
-        a, b = outs["bf16"][k].double(), outs["fp32"][k].double()
+        fwd_q = k == "out" or k.startswith(("rm", "rv"))
+        ref = outs["fp32"] if fwd_q else outs["tcfwd"]
+        a, b = outs["test"][k].double(), ref[k].double()
         denom = b.abs().max().item() + 1e-30
         nrm = b.norm().item()
         if k.startswith(("ggamma", "gbeta")):
             # can be mathematically zero (BN without ReLU feeding a train-mode BN): use the scale of
             # the same layer's weight gradient
-            wk = outs["fp32"]["gW" + k.lstrip("gamebt")].double()
+            wk = ref["gW" + k.lstrip("gamebt")].double()
             denom = max(denom, 1e-2 * wk.abs().max().item())
             nrm = max(nrm, 1e-2 * wk.norm().item() / max(1.0, (wk.numel() / b.numel()) ** 0.5))
         res[k] = dict(max=float((a - b).abs().max().item() / denom),
