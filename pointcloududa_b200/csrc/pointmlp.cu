@@ -307,10 +307,27 @@ act_colsum_kernel(ActSrc src, int64_t M, int64_t chunk, double* __restrict__ par
   double s = 0.0;
   if (k < src.C) {
     float f = 0.f;
-    int cnt = 0;
-    for (int64_t m = m0 + warp; m < m1; m += 8) {
-      f += load_act1(src, m, k);
-      if (++cnt == 32) { s += static_cast<double>(f); f = 0.f; cnt = 0; }
+    if (src.y != nullptr) {
+      const float sc = src.invstd[k] * src.gamma[k];
+      const float sh = src.beta[k] - src.mean[k] * sc;
+      int64_t m = m0 + warp;
+      for (; m + 24 < m1; m += 32) {                       // 4 rows in flight per warp
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = src.y[(m + 8 * u) * src.C + k];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float t = fmaf(v[u], sc, sh);
+          f += src.relu ? fmaxf(t, 0.f) : t;
+        }
+        s += static_cast<double>(f); f = 0.f;
+      }
+      for (; m < m1; m += 8) {
+        const float t = fmaf(src.y[m * src.C + k], sc, sh);
+        f += src.relu ? fmaxf(t, 0.f) : t;
+      }
+    } else {
+      for (int64_t m = m0 + warp; m < m1; m += 8) f += load_act1(src, m, k);
     }
     s += static_cast<double>(f);
   }
@@ -377,16 +394,21 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int64_
   out[i] = static_cast<TOut>(s);
 }
 
-// abar[k] = (sum_s colsum_partial[s,k]) / M   (fixed order)
-__global__ void abar_kernel(const double* __restrict__ colsum_partial, int S, int K, double count,
-                            float* __restrict__ abar, double* __restrict__ abar_d) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+// abar[k] = (sum_s colsum_partial[s,k]) / M.  One warp per channel, lanes interleave the slices; the
+// butterfly reduction has a fixed order, so the result is deterministic.
+__global__ void __launch_bounds__(256)
+abar_kernel(const double* __restrict__ colsum_partial, int S, int K, double count, float* __restrict__ abar,
+            double* __restrict__ abar_d) {
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (k >= K) return;
   double a = 0.0;
-  for (int s = 0; s < S; ++s) a += colsum_partial[static_cast<int64_t>(s) * K + k];
-  a /= count;
-  abar[k] = static_cast<float>(a);
-  abar_d[k] = a;
+  for (int s = lane; s < S; s += 32) a += colsum_partial[static_cast<int64_t>(s) * K + k];
+  a = warp_sum(a);
+  if (lane == 0) {
+    a /= count;
+    abar[k] = static_cast<float>(a);
+    abar_d[k] = a;
+  }
 }
 
 // Ghat[k,k'] = G[k,k'] - M abar_k abar_k'
@@ -476,14 +498,14 @@ pool_u_kernel(const float* __restrict__ W, const float* __restrict__ alpha, cons
 //   head[b*N + n]  = h = the lowest such channel          (head must be pre-filled with -1)
 // grid (B, parts), 1024 threads; dynamic smem: C + N ints.  A warp owns a head channel, finds the other
 // channels selecting the same point with ballots over the shared-memory copy of arg, and sums their rows.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ coef, const float* __restrict__ W,
                    int C, int N, int K, int* __restrict__ head, float* __restrict__ srows) {
   extern __shared__ int sm_i[];
   int* sarg = sm_i;
   int* first = sm_i + C;
   const int b = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int c = threadIdx.x; c < C; c += blockDim.x)
     sarg[c] = coef[static_cast<int64_t>(b) * C + c] != 0.f ? arg[static_cast<int64_t>(b) * C + c] : -1;
   for (int n = threadIdx.x; n < N; n += blockDim.x) first[n] = 0x7fffffff;
@@ -491,8 +513,9 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
   for (int c = threadIdx.x; c < C; c += blockDim.x)
     if (sarg[c] >= 0) atomicMin(&first[sarg[c]], c);
   __syncthreads();
-  const int stride = 32 * gridDim.y;
-  for (int c = blockIdx.y * 32 + warp; c < C; c += stride) {
+  const int KPL = (K + 31) >> 5;               // output columns per lane (<= 16)
+  const int stride = nwarp * gridDim.y;
+  for (int c = blockIdx.y * nwarp + warp; c < C; c += stride) {
     const int a = sarg[c];
     if (a < 0 || first[a] != c) continue;      // warp-uniform
     if (lane == 0) head[static_cast<int64_t>(b) * N + a] = c;
@@ -503,12 +526,36 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
       const int cc = c0 + lane;
       unsigned mask = __ballot_sync(0xffffffffu, cc >= c && cc < C && sarg[cc] == a);
       while (mask) {
-        const int c2 = c0 + __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float cf = coef[static_cast<int64_t>(b) * C + c2];
+        // up to 4 matching channels in flight; they are accumulated in ascending order (deterministic)
+        int cs[4];
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj)
-          if (lane + 32 * jj < K) acc[jj] = fmaf(cf, W[static_cast<int64_t>(c2) * K + lane + 32 * jj], acc[jj]);
+        for (int u = 0; u < 4; ++u) {
+          cs[u] = mask ? c0 + __ffs(mask) - 1 : -1;
+          mask &= mask - 1;
+        }
+        if (KPL <= 4) {
+          float cf[4], wv[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            cf[u] = cs[u] >= 0 ? coef[static_cast<int64_t>(b) * C + cs[u]] : 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              wv[u][jj] = (cs[u] >= 0 && lane + 32 * jj < K) ? W[static_cast<int64_t>(cs[u]) * K + lane + 32 * jj] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[jj] = fmaf(cf[u], wv[u][jj], acc[jj]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (cs[u] < 0) continue;
+            const float cf = coef[static_cast<int64_t>(b) * C + cs[u]];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj)
+              if (lane + 32 * jj < K) acc[jj] = fmaf(cf, W[static_cast<int64_t>(cs[u]) * K + lane + 32 * jj], acc[jj]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -1049,7 +1096,7 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
       launches += 1;
     }
     reduce_partials_kernel<double><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(partial, kk, Sg, w.G);
-    abar_kernel<<<(K + 127) / 128, 128, 0, st>>>(w.colsum, S32, K, count, w.abar, w.abar_d);
+    abar_kernel<<<(K + 7) / 8, 256, 0, st>>>(w.colsum, S32, K, count, w.abar, w.abar_d);
     gram_center_kernel<<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(w.abar_d, w.G, K, count, w.Ghat);
     pool_q_kernel<<<dim3((K + 31) / 32, (K + 31) / 32, kPoolQSplits), 256, 0, st>>>(last.weight, ka, C, K, partial);
     reduce_partials_kernel<float><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(partial, kk, kPoolQSplits, w.Q);
@@ -1070,8 +1117,8 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
           attr_done = true;
         }
         cudaMemsetAsync(w.head, 0xFF, sizeof(int) * static_cast<size_t>(s.M), st);
-        const int parts = std::max(1, std::min(8, 2 * sm_count() / std::max(1, B)));
-        pool_sparse_kernel<<<dim3(B, parts), 1024, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, w.head, w.srows);
+        const int parts = std::max(1, std::min(16, 4 * sm_count() / std::max(1, B)));
+        pool_sparse_kernel<<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, w.head, w.srows);
         launches += 1;
         if (int rc = tc::pack_w(w.Q, K, K, false, w.qpack, st)) return rc;
         if (int rc = tc::pool_dgrad(tl, a_in, K, w.qpack, w.u, w.head, w.srows, C, o, st)) return rc;

@@ -35,6 +35,7 @@
 // full/empty mbarriers (MMA <-> epilogue); two 256-column accumulators so the epilogue of one
 // overlaps the MMAs of the other.
 #include <algorithm>
+#include <type_traits>
 
 #include "pointmlp_common.cuh"
 #include "pointmlp_tc.cuh"
@@ -370,6 +371,9 @@ __global__ void __launch_bounds__(kThreads, 1) ws_kernel(const WsParams p) {
         if (MODE == POOL_DGRAD && rok) act_slab = b_smem + ((it + (r >> 6)) % p.nstage) * kSlabB;
         if (MODE == DGRAD && p.side_slabs > 0 && rok) act_slab = side_smem + (r >> 6) * kSlabB;
         const float inv_g = e2 != 0.f ? 1.0f / e2 : 0.f;
+        // yhat = (a - beta) / gamma from the bf16 activation is only as good as 2^-9 (|yhat| + |beta/gamma|):
+        // channels with a small gamma take the fp32 pre-activation from HBM instead
+        const bool slab_ok = fabsf(e2) >= 0.25f && fabsf(e3) <= 4.0f * fabsf(e2);
         const bool to_x = p.out.grad_x != nullptr;
         float sa[4] = {0.f, 0.f, 0.f, 0.f}, qa[4] = {0.f, 0.f, 0.f, 0.f};   // 4-way split sums: ILP for one warp
         float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -380,68 +384,78 @@ __global__ void __launch_bounds__(kThreads, 1) ws_kernel(const WsParams p) {
           float v[32];
           tmem_ld32(tmem + lane_addr + slot * kNT + ch * 32, v);
           const int ncol = min(32, nvalid - ch * 32);
-          if (MODE == FWD_DENSE) {
-            if (rok) {
-              float* yp = p.y_out + (m0 + ch * 32) * p.R + r;
+          // FULL chunks (all but the last of a cloud) run without per-column predicates: straight-line
+          // code with 4 independent dependency chains per reduction
+          auto chunk_body = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            if (MODE == FWD_DENSE) {
+              if (rok) {
+                float* yp = p.y_out + (m0 + ch * 32) * p.R + r;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  if (FULL || i < ncol) {
+                    yp[static_cast<int64_t>(i) * p.R] = v[i] + e0;
+                    sa[i & 3] += v[i];
+                    qa[i & 3] = fmaf(v[i], v[i], qa[i & 3]);
+                  }
+                }
+              }
+            } else if (MODE == FWD_POOL) {
+              const int nb = n0 + ch * 32;
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                if (i < ncol) {
-                  yp[static_cast<int64_t>(i) * p.R] = v[i] + e0;
+                if (FULL || i < ncol) {
                   sa[i & 3] += v[i];
                   qa[i & 3] = fmaf(v[i], v[i], qa[i & 3]);
+                  const float vv = v[i] * e0;     // sign(gamma) * y: BN is monotone per channel
+                  const bool gt = vv > bv[i & 3];
+                  bv[i & 3] = gt ? vv : bv[i & 3];
+                  bi[i & 3] = gt ? nb + i : bi[i & 3];
                 }
               }
-            }
-          } else if (MODE == FWD_POOL) {
+            } else {
+              // dgrad epilogues
+              int hv = -1;
+              if (MODE == POOL_DGRAD) hv = (FULL || lane < ncol) ? __ldg(p.head + m0 + ch * 32 + lane) : -1;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (i < ncol) {
-                sa[i & 3] += v[i];
-                qa[i & 3] = fmaf(v[i], v[i], qa[i & 3]);
-                const float vv = v[i] * e0;     // sign(gamma) * y: BN is monotone per channel
-                if (vv > bv[i & 3]) { bv[i & 3] = vv; bi[i & 3] = n0 + ch * 32 + i; }
-              }
-            }
-          } else {
-            // dgrad epilogues
-            int hv = -1;
-            if (MODE == POOL_DGRAD) hv = (lane < ncol) ? __ldg(p.head + m0 + ch * 32 + lane) : -1;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (i < ncol) {
-                float val = v[i];
-                const int col = ch * 32 + i;
-                if (MODE == POOL_DGRAD) {
-                  const int h = __shfl_sync(0xffffffffu, hv, i);
-                  float sp = 0.f;
-                  if (h >= 0 && rok) sp = __ldg(p.srows + (static_cast<int64_t>(b) * p.Cpool + h) * p.K + r);
-                  val = sp - uk - val;
-                }
-                if (rok) {
-                  const int64_t m = m0 + col;
-                  if (to_x) {
-                    p.out.grad_x[(static_cast<int64_t>(b) * p.R + r) * p.tl.N + n0 + col] = val;
-                  } else {
-                    float yh;
-                    bool on = true;
-                    if (act_slab != nullptr && e2 != 0.f) {
-                      // a = relu?(gamma*yhat + beta) in bf16: mask = a > 0, yhat = (a - beta) / gamma
-                      const float a = bf16_at(act_slab, col, r & 63);
-                      if (p.out.relu) on = a > 0.f;
-                      yh = (a - e3) * inv_g;
+              for (int i = 0; i < 32; ++i) {
+                if (FULL || i < ncol) {
+                  float val = v[i];
+                  const int col = ch * 32 + i;
+                  if (MODE == POOL_DGRAD) {
+                    const int h = __shfl_sync(0xffffffffu, hv, i);
+                    float sp = 0.f;
+                    if (h >= 0 && rok) sp = __ldg(p.srows + (static_cast<int64_t>(b) * p.Cpool + h) * p.K + r);
+                    val = sp - uk - val;
+                  }
+                  if (rok) {
+                    const int64_t m = m0 + col;
+                    if (to_x) {
+                      p.out.grad_x[(static_cast<int64_t>(b) * p.R + r) * p.tl.N + n0 + col] = val;
                     } else {
-                      yh = (__ldg(p.out.y_prev + m * p.R + r) - e0) * e1;
-                      if (p.out.relu) on = fmaf(yh, e2, e3) > 0.f;
+                      float yh;
+                      bool on = true;
+                      if (act_slab != nullptr && slab_ok) {
+                        // a = relu?(gamma*yhat + beta) in bf16: mask = a > 0, yhat = (a - beta) / gamma
+                        const float a = bf16_at(act_slab, col, r & 63);
+                        if (p.out.relu) on = a > 0.f;
+                        yh = (a - e3) * inv_g;
+                      } else {
+                        yh = (__ldg(p.out.y_prev + m * p.R + r) - e0) * e1;
+                        if (p.out.relu) on = fmaf(yh, e2, e3) > 0.f;
+                      }
+                      val = on ? val : 0.f;
+                      p.out.dz_prev[m * p.R + r] = val;
+                      sa[i & 3] += val;
+                      qa[i & 3] = fmaf(val, yh, qa[i & 3]);
                     }
-                    if (!on) val = 0.f;
-                    p.out.dz_prev[m * p.R + r] = val;
-                    sa[i & 3] += val;
-                    qa[i & 3] = fmaf(val, yh, qa[i & 3]);
                   }
                 }
               }
             }
-          }
+          };
+          if (ncol == 32) chunk_body(std::true_type{});
+          else chunk_body(std::false_type{});
         }
         tc_fence_before();
         __syncwarp();
