@@ -11,6 +11,8 @@
  *   pcuda_chamfer_fwd / _bwd      utils/loss.py:40-76  (batch_NN_loss, batch_pairwise_dist)
  *   pcuda_pointmlp_fwd / _bwd     networks/PointNetCls.py:38-44 (STN3d trunk), :84-88 (STNkd
  *                                 trunk), :143-163 (PointNetfeat trunk + global max-pool)
+ *   pcuda_fcstack_fwd / _bwd      networks/PointNetCls.py:46-62 (STN3d head), :89-101 (STNkd head),
+ *                                 :208-213 (classifier head): Linear [+Dropout] [+BatchNorm1d] [+ReLU]
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless the parameter is documented "host";
@@ -173,6 +175,50 @@ int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, in
                        int L, const pcuda_mlp_layer_t* layers /*host*/, int pool, int train,
                        float eps, int precision, const float* out, const int32_t* pool_arg,
                        const float* grad_out, float* grad_x, void* ws, pcuda_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FC head: a stack of L layers on [B, C] features (the rows are the clouds of the batch)
+ *     y_l = (a_{l-1} W_l^T + b_l) * mask_l ;  z_l = bn ? BatchNorm1d(y_l) : y_l ;
+ *     a_l = relu ? max(z_l, 0) : z_l
+ * networks/PointNetCls.py:46-62 (STN3d: fc1-bn4-relu, fc2-bn5-relu, fc3, + identity), :89-101
+ * (STNkd), :208-213 (classifier: fc1-bn1-relu, fc2-dropout-bn2-relu, fc3).  mask_l is the Dropout
+ * mask (already scaled by 1/(1-p); drawn by the caller so the RNG stream stays the framework's),
+ * or NULL.  BatchNorm1d semantics as for pcuda_pointmlp_* (statistics over the B rows).
+ * One launch per layer and direction: a CTA owns 4 output channels and all B rows, so BatchNorm
+ * (forward and backward) needs no cross-CTA reduction; results are deterministic.
+ * Limits: cin % 4 == 0, cin <= 4096, B <= 2048.
+ */
+typedef struct pcuda_fc_layer {
+  int32_t cin, cout;
+  int32_t bn;            /* BatchNorm1d after the (masked) linear map */
+  int32_t relu;
+  const float* weight;   /* [cout, cin], 16-byte aligned */
+  const float* bias;     /* [cout] or NULL */
+  const float* mask;     /* [B, cout] or NULL */
+  const float* gamma;    /* [cout] BN weight (bn != 0) */
+  const float* beta;     /* [cout] BN bias */
+  float* running_mean;   /* [cout] or NULL */
+  float* running_var;    /* [cout] or NULL */
+  float* save_mean;      /* [cout]  fwd: out, bwd: in (bn != 0) */
+  float* save_invstd;    /* [cout]  fwd: out, bwd: in */
+  float* y;              /* [B, cout] BatchNorm input; fwd: out, bwd: in (bn != 0, else may be NULL) */
+  float* a;              /* [B, cout] layer output;    fwd: out, bwd: in */
+  float* grad_weight;    /* bwd out [cout, cin] (NULL: skip every parameter gradient of the layer) */
+  float* grad_bias;      /* bwd out [cout] or NULL */
+  float* grad_gamma;     /* bwd out [cout] or NULL */
+  float* grad_beta;      /* bwd out [cout] or NULL */
+} pcuda_fc_layer_t;
+
+/* x: [B, layers[0].cin] contiguous, 16-byte aligned.  The output is layers[L-1].a.
+ * add_identity_k > 0: adds the flattened k x k identity to the last layer's output (the STN heads;
+ * requires layers[L-1].cout == k*k). */
+int pcuda_fcstack_fwd(const float* x, int B, int L, const pcuda_fc_layer_t* layers /*host*/, int train,
+                      float momentum, float eps, int add_identity_k, pcuda_stream_t stream);
+/* grad_out: [B, layers[L-1].cout]; grad_x: [B, layers[0].cin] or NULL.
+ * ws: pcuda_fcstack_ws_bytes(B, L, layers, 1) bytes, any contents. */
+size_t pcuda_fcstack_ws_bytes(int B, int L, const pcuda_fc_layer_t* layers /*host*/, int backward);
+int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_layer_t* layers /*host*/, int train,
+                      const float* grad_out, float* grad_x, void* ws, pcuda_stream_t stream);
 
 #ifdef __cplusplus
 }

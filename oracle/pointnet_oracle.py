@@ -122,10 +122,28 @@ def _bn_bwd(dz, cache):
     return dy, dgamma, dbeta
 
 
-def _conv_bn(x2, W, b, gamma, beta, relu, dt):
+def bf16_round(a):
+    """Round-to-nearest-even to bfloat16 precision (returned in a's dtype).  Restates the operand
+    rounding of the product's tensor-core path (bf16 operands, fp32 accumulation) so that tests can
+    separate that rounding -- which train-mode BatchNorm over a handful of samples amplifies -- from
+    genuine kernel errors."""
+    a32 = np.ascontiguousarray(a, dtype=np.float32)
+    u = a32.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(a32.shape).astype(a.dtype)
+
+
+def bf16_layer(cin: int) -> bool:
+    """Layers the product runs on the tensor cores: contraction length a multiple of 64 in [64, 512]."""
+    return 64 <= cin <= 512 and cin % 64 == 0
+
+
+def _conv_bn(x2, W, b, gamma, beta, relu, dt, bf16_operands=False):
     """x2 [Cin, B*N] -> relu?(bn(W x + b)) [Cout, B*N]  (Conv1d k=1 + BatchNorm1d, :41-43,:143-161).
     The k=1 convolution over [B,C,N] is one GEMM over the B*N columns."""
     W2 = W.reshape(W.shape[0], -1).astype(dt)
+    if bf16_operands and bf16_layer(W2.shape[1]):
+        W2, x2 = bf16_round(W2), bf16_round(x2)
     y = W2 @ x2 + b.astype(dt)[:, None]
     mean = y.mean(axis=1, keepdims=True, dtype=dt)
     var = ((y - mean) ** 2).mean(axis=1, keepdims=True, dtype=dt)
@@ -180,7 +198,7 @@ def _fc_bn_relu_bwd(da, cache):
 
 
 # ---- shared-MLP stack + max-pool: the op the CUDA library implements ----------------------------
-def stack_forward(x, layers, pool: bool, dtype=np.float32):
+def stack_forward(x, layers, pool: bool, dtype=np.float32, bf16_operands=False):
     """layers: list of dict(weight [Cout,Cin(,1)], bias, gamma, beta, relu).  x [B,C0,N].
     Returns (out, cache); out is [B,C_L] when pool else [B,C_L,N].  cache['stats'] holds the
     per-layer batch mean / biased var (for running-stat checks)."""
@@ -189,7 +207,7 @@ def stack_forward(x, layers, pool: bool, dtype=np.float32):
     a = np.ascontiguousarray(x.astype(dt).transpose(1, 0, 2)).reshape(C0, B * N)
     caches, stats = [], []
     for L in layers:
-        a, c = _conv_bn(a, L["weight"], L["bias"], L["gamma"], L["beta"], bool(L["relu"]), dt)
+        a, c = _conv_bn(a, L["weight"], L["bias"], L["gamma"], L["beta"], bool(L["relu"]), dt, bf16_operands)
         caches.append(c)
         stats.append((c[2][4], c[2][5]))
     a3 = a.reshape(a.shape[0], B, N).transpose(1, 0, 2)  # [B, C, N]
@@ -240,8 +258,8 @@ def feat_stacks(params, spec: PointNetSpec):
     return pre, post
 
 
-def _stn_forward(params, prefix, x, k, dt):
-    g, sc = stack_forward(x, _stn_layers(params, prefix), True, dt)
+def _stn_forward(params, prefix, x, k, dt, bf16_operands=False):
+    g, sc = stack_forward(x, _stn_layers(params, prefix), True, dt, bf16_operands)
     h1, c1 = _fc_bn_relu(g, params[f"{prefix}fc1.weight"], params[f"{prefix}fc1.bias"],
                          params[f"{prefix}bn4.weight"], params[f"{prefix}bn4.bias"], dt)
     h2, c2 = _fc_bn_relu(h1, params[f"{prefix}fc2.weight"], params[f"{prefix}fc2.bias"],
@@ -271,27 +289,28 @@ def _stn_backward(dtrans, cache, grads):
 
 
 def pointnet_forward(params, x, spec: PointNetSpec = PointNetSpec(), drop_mask=None,
-                     dtype=np.float32):
+                     dtype=np.float32, bf16_operands=False):
     """x [B,3,N] -> (logit [B,1], trans [B,3,3]|None, trans_feat [B,64,64]|None, cache).
-    drop_mask: the (already 1/(1-p)-scaled) dropout mask applied to fc2's output, or None."""
+    drop_mask: the (already 1/(1-p)-scaled) dropout mask applied to fc2's output, or None.
+    bf16_operands: round the operands of the wide shared-MLP layers to bf16 (see bf16_round)."""
     dt = dtype
     x = x.astype(dt)
     cache = {"spec": spec}
     trans = None
     if spec.sample_transform:
-        trans, cache["stn"] = _stn_forward(params, "feat.stn.", x, 3, dt)
+        trans, cache["stn"] = _stn_forward(params, "feat.stn.", x, 3, dt, bf16_operands)
         cache["x_in"] = x
         x = np.matmul(x.transpose(0, 2, 1), trans).transpose(0, 2, 1)  # :140-142
         cache["trans"] = trans
     pre, post = feat_stacks(params, spec)
-    h, cache["pre"] = stack_forward(x, pre, False, dt)
+    h, cache["pre"] = stack_forward(x, pre, False, dt, bf16_operands)
     trans_feat = None
     if spec.feature_transform:
-        trans_feat, cache["fstn"] = _stn_forward(params, "feat.fstn.", h, 64, dt)
+        trans_feat, cache["fstn"] = _stn_forward(params, "feat.fstn.", h, 64, dt, bf16_operands)
         cache["h_in"] = h
         h = np.matmul(h.transpose(0, 2, 1), trans_feat).transpose(0, 2, 1)  # :147-151
         cache["trans_feat"] = trans_feat
-    g, cache["post"] = stack_forward(h, post, True, dt)
+    g, cache["post"] = stack_forward(h, post, True, dt, bf16_operands)
     a1, cache["h1"] = _fc_bn_relu(g, params["fc1.weight"], params["fc1.bias"], params["bn1.weight"],
                                   params["bn1.bias"], dt)
     a2, cache["h2"] = _fc_bn_relu(a1, params["fc2.weight"], params["fc2.bias"], params["bn2.weight"],

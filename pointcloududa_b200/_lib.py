@@ -29,6 +29,18 @@ class MlpLayer(ctypes.Structure):
     ]
 
 
+class FcLayer(ctypes.Structure):
+    """pcuda_fc_layer_t (include/pcuda.h)."""
+    _fields_ = [
+        ("cin", c_int32), ("cout", c_int32), ("bn", c_int32), ("relu", c_int32),
+        ("weight", c_void_p), ("bias", c_void_p), ("mask", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+        ("running_mean", c_void_p), ("running_var", c_void_p),
+        ("save_mean", c_void_p), ("save_invstd", c_void_p), ("y", c_void_p), ("a", c_void_p),
+        ("grad_weight", c_void_p), ("grad_bias", c_void_p), ("grad_gamma", c_void_p),
+        ("grad_beta", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/pcuda.h declares
 SIGNATURES = {
     "pcuda_version": (c_int, []),
@@ -55,6 +67,11 @@ SIGNATURES = {
     "pcuda_pointmlp_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                    POINTER(MlpLayer), c_int, c_int, c_float, c_int, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcuda_fcstack_fwd": (c_int, [c_void_p, c_int, c_int, POINTER(FcLayer), c_int, c_float, c_float, c_int,
+                                  c_void_p]),
+    "pcuda_fcstack_ws_bytes": (c_size_t, [c_int, c_int, POINTER(FcLayer), c_int]),
+    "pcuda_fcstack_bwd": (c_int, [c_void_p, c_int, c_int, POINTER(FcLayer), c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
 }
 
 

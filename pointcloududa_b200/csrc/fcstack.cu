@@ -1,0 +1,385 @@
+// FC heads of the point-cloud discriminator: Linear (+Dropout mask) (+BatchNorm1d over the batch) (+ReLU)
+// stacks on [B, C] features — STN3d / STNkd heads 1024->512->256->k*k (networks/PointNetCls.py:46-62,
+// :89-101) and the classifier head 1024->512->256->1 (:208-213).
+//
+// These layers are 0.2 % of D4's FLOPs but, run as individual framework ops, about half of its kernel
+// launches (GEMM + bias + three BatchNorm kernels + ReLU + counters, forward and backward).  Here one
+// layer is ONE launch in each direction.  The trick is the partitioning: a CTA owns a few OUTPUT
+// CHANNELS and all B rows, so everything BatchNorm needs (statistics over the batch, forward and
+// backward) is CTA-local — no grid-wide synchronisation and no atomics, results are deterministic.
+//
+//   forward  (layer l):  y = (x W^T + b) * mask ; (mean, var over b) ; a = relu?(bn(y))
+//   backward (layer l):  da = dy_{l+1} W_{l+1}   (pulled: this CTA's channels are columns of W_{l+1})
+//                        dz = da * [a > 0] ; BN backward over b -> dy ; dy *= mask
+//                        dW[c,:] = sum_b dy[b,c] x[b,:] ; db = sum_b dy ; dgamma, dbeta
+//   input gradient:      dx = dy_0 W_0           (one more pull launch)
+//
+// Latency-bound by construction (B <= a few hundred rows): the kernels are written for few, wide,
+// coalesced memory phases rather than for FLOPs.
+#include "pcuda_common.cuh"
+
+namespace pcuda {
+namespace {
+
+constexpr int kCPB = 4;        // output channels per CTA
+constexpr int kFcThreads = 256;
+constexpr int kMaxCin = 4096;  // staged weight rows: kCPB * cin floats of shared memory
+
+struct FcFwdParams {
+  const float* x;        // [B, cin]
+  const float* W;        // [cout, cin]
+  const float* bias;     // [cout] or nullptr
+  const float* mask;     // [B, cout] or nullptr
+  const float* gamma; const float* beta;       // BN (nullptr: no BN)
+  float* running_mean; float* running_var;
+  float* save_mean; float* save_invstd;
+  float* y;              // [B, cout] BN input (after mask); may be nullptr when there is no BN
+  float* a;              // [B, cout] layer output
+  int B, cin, cout, relu, train, iden_k;
+  float momentum, eps;
+};
+
+// dynamic shared memory: Wsm[kCPB][cin] | ys[B][kCPB]
+__global__ void __launch_bounds__(kFcThreads) fc_fwd_kernel(const FcFwdParams p) {
+  extern __shared__ float sm[];
+  float* Wsm = sm;
+  float* ys = sm + kCPB * p.cin;
+  __shared__ float s_mean[kCPB], s_scale[kCPB], s_shift[kCPB];
+  const int c0 = blockIdx.x * kCPB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cin4 = p.cin >> 2;
+  for (int i = threadIdx.x; i < kCPB * cin4; i += kFcThreads) {
+    const int cc = i / cin4, k4 = i - cc * cin4;
+    const int c = c0 + cc;
+    reinterpret_cast<float4*>(Wsm)[i] =
+        c < p.cout ? __ldg(reinterpret_cast<const float4*>(p.W + static_cast<int64_t>(c) * p.cin) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  // one warp per row b: the row of x is read once for the kCPB channels
+  for (int b = warp; b < p.B; b += kFcThreads / 32) {
+    const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(b) * p.cin);
+    float acc[kCPB] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k4 = lane; k4 < cin4; k4 += 32) {
+      const float4 xv = __ldg(xr + k4);
+#pragma unroll
+      for (int cc = 0; cc < kCPB; ++cc) {
+        const float4 wv = reinterpret_cast<const float4*>(Wsm)[cc * cin4 + k4];
+        acc[cc] = fmaf(xv.x, wv.x, acc[cc]); acc[cc] = fmaf(xv.y, wv.y, acc[cc]);
+        acc[cc] = fmaf(xv.z, wv.z, acc[cc]); acc[cc] = fmaf(xv.w, wv.w, acc[cc]);
+      }
+    }
+#pragma unroll
+    for (int cc = 0; cc < kCPB; ++cc) acc[cc] = warp_sum(acc[cc]);
+    if (lane < kCPB) {
+      const int c = c0 + lane;
+      float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+      if (c < p.cout) {
+        if (p.bias) v += p.bias[c];
+        if (p.mask) v *= p.mask[static_cast<int64_t>(b) * p.cout + c];
+      }
+      ys[b * kCPB + lane] = v;
+    }
+  }
+  __syncthreads();
+  // BatchNorm over the batch: warp cc owns channel c0 + cc (two-pass, fixed order: deterministic)
+  if (warp < kCPB) {
+    const int c = c0 + warp;
+    float scale = 1.f, shift = 0.f, mean = 0.f;
+    if (p.gamma != nullptr && c < p.cout) {
+      float invstd;
+      if (p.train) {
+        float s = 0.f;
+        for (int b = lane; b < p.B; b += 32) s += ys[b * kCPB + warp];
+        mean = warp_sum(s) / static_cast<float>(p.B);
+        float q = 0.f;
+        for (int b = lane; b < p.B; b += 32) { const float d = ys[b * kCPB + warp] - mean; q = fmaf(d, d, q); }
+        const float var = warp_sum(q) / static_cast<float>(p.B);
+        invstd = rsqrtf(var + p.eps);
+        if (lane == 0) {
+          p.save_mean[c] = mean;
+          p.save_invstd[c] = invstd;
+          if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
+          if (p.running_var) {
+            const float unb = p.B > 1 ? var * static_cast<float>(p.B) / static_cast<float>(p.B - 1) : var;
+            p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * unb;
+          }
+        }
+      } else {
+        mean = p.running_mean[c];
+        invstd = rsqrtf(p.running_var[c] + p.eps);
+        if (lane == 0) { p.save_mean[c] = mean; p.save_invstd[c] = invstd; }
+      }
+      scale = invstd * p.gamma[c];
+      shift = p.beta[c];
+    }
+    if (lane == 0) { s_mean[warp] = mean; s_scale[warp] = scale; s_shift[warp] = shift; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.B * kCPB; i += kFcThreads) {
+    const int b = i / kCPB, cc = i - b * kCPB, c = c0 + cc;
+    if (c >= p.cout) continue;
+    const float yv = ys[i];
+    float z = fmaf(yv - s_mean[cc], s_scale[cc], s_shift[cc]);
+    if (p.relu) z = fmaxf(z, 0.f);
+    if (p.iden_k > 0 && c % (p.iden_k + 1) == 0) z += 1.0f;       // + flattened identity (STN heads)
+    const int64_t o = static_cast<int64_t>(b) * p.cout + c;
+    if (p.y) p.y[o] = yv;
+    p.a[o] = z;
+  }
+}
+
+struct FcBwdParams {
+  // this layer
+  const float* x;        // [B, cin] layer input
+  const float* W;        // [cout, cin]   (unused here; the next launch pulls through it)
+  const float* mask;     // [B, cout] or nullptr
+  const float* gamma; const float* save_mean; const float* save_invstd;   // BN (gamma nullptr: none)
+  const float* y;        // [B, cout] BN input
+  const float* a;        // [B, cout] layer output (ReLU mask)
+  // upstream: either grad_out (last layer) or the next layer's dy and weights
+  const float* grad_out; // [B, cout] or nullptr
+  const float* dy_next;  // [B, cout_next]
+  const float* W_next;   // [cout_next, cout]
+  int cout_next;
+  // outputs
+  float* dy;             // [B, cout] gradient w.r.t. the linear output (consumed by the next launch)
+  float* grad_weight; float* grad_bias; float* grad_gamma; float* grad_beta;   // may be nullptr
+  int B, cin, cout, relu, train;
+};
+
+// dynamic shared memory: dys[B][kCPB]
+__global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p) {
+  extern __shared__ float sm[];
+  float* dys = sm;
+  const int c0 = blockIdx.x * kCPB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // (1) da for this CTA's channels
+  if (p.grad_out != nullptr) {
+    for (int i = threadIdx.x; i < p.B * kCPB; i += kFcThreads) {
+      const int b = i / kCPB, c = c0 + (i - b * kCPB);
+      dys[i] = c < p.cout ? p.grad_out[static_cast<int64_t>(b) * p.cout + c] : 0.f;
+    }
+  } else {
+    const bool vec = (p.cout & 3) == 0;
+    for (int b = warp; b < p.B; b += kFcThreads / 32) {
+      const float* dn = p.dy_next + static_cast<int64_t>(b) * p.cout_next;
+      float acc[kCPB] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int o = lane; o < p.cout_next; o += 32) {
+        const float d = __ldg(dn + o);
+        const float* wr = p.W_next + static_cast<int64_t>(o) * p.cout + c0;
+        if (vec) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wr));
+          acc[0] = fmaf(d, wv.x, acc[0]); acc[1] = fmaf(d, wv.y, acc[1]);
+          acc[2] = fmaf(d, wv.z, acc[2]); acc[3] = fmaf(d, wv.w, acc[3]);
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < kCPB; ++cc)
+            if (c0 + cc < p.cout) acc[cc] = fmaf(d, __ldg(wr + cc), acc[cc]);
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < kCPB; ++cc) acc[cc] = warp_sum(acc[cc]);
+      if (lane < kCPB) dys[b * kCPB + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+    }
+  }
+  __syncthreads();
+  // (2) ReLU mask, (3) BatchNorm backward over the batch, (4) dropout mask: warp cc owns channel c0 + cc
+  if (warp < kCPB) {
+    const int c = c0 + warp;
+    if (c < p.cout) {
+      const bool bn = p.gamma != nullptr;
+      const float mean = bn ? p.save_mean[c] : 0.f, invstd = bn ? p.save_invstd[c] : 1.f;
+      float sb = 0.f, sg = 0.f;
+      for (int b = lane; b < p.B; b += 32) {
+        const int64_t o = static_cast<int64_t>(b) * p.cout + c;
+        float dz = dys[b * kCPB + warp];
+        if (p.relu && !(p.a[o] > 0.f)) dz = 0.f;
+        dys[b * kCPB + warp] = dz;
+        if (bn) {
+          sb += dz;
+          sg = fmaf(dz, (p.y[o] - mean) * invstd, sg);
+        }
+      }
+      float dbias = 0.f;
+      if (bn) {
+        sb = warp_sum(sb);
+        sg = warp_sum(sg);
+        const float g = p.gamma[c];
+        const float kb = p.train ? sb / static_cast<float>(p.B) : 0.f;
+        const float kg = p.train ? sg / static_cast<float>(p.B) : 0.f;
+        for (int b = lane; b < p.B; b += 32) {
+          const int64_t o = static_cast<int64_t>(b) * p.cout + c;
+          const float yh = (p.y[o] - mean) * invstd;
+          float d = g * invstd * (dys[b * kCPB + warp] - kb - yh * kg);
+          if (p.mask) d *= p.mask[o];
+          dys[b * kCPB + warp] = d;
+          dbias += d;
+        }
+        if (lane == 0) {
+          if (p.grad_gamma) p.grad_gamma[c] = sg;
+          if (p.grad_beta) p.grad_beta[c] = sb;
+        }
+      } else {
+        for (int b = lane; b < p.B; b += 32) {
+          float d = dys[b * kCPB + warp];
+          if (p.mask) d *= p.mask[static_cast<int64_t>(b) * p.cout + c];
+          dys[b * kCPB + warp] = d;
+          dbias += d;
+        }
+      }
+      dbias = warp_sum(dbias);
+      if (lane == 0 && p.grad_bias) p.grad_bias[c] = dbias;
+    }
+  }
+  __syncthreads();
+  // (5) dy for the next launch
+  for (int i = threadIdx.x; i < p.B * kCPB; i += kFcThreads) {
+    const int b = i / kCPB, c = c0 + (i - b * kCPB);
+    if (c < p.cout) p.dy[static_cast<int64_t>(b) * p.cout + c] = dys[i];
+  }
+  // (6) weight gradient rows of this CTA's channels
+  if (p.grad_weight != nullptr) {
+    for (int k = threadIdx.x; k < p.cin; k += kFcThreads) {
+      float acc[kCPB] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int b = 0; b < p.B; ++b) {
+        const float xv = __ldg(p.x + static_cast<int64_t>(b) * p.cin + k);
+#pragma unroll
+        for (int cc = 0; cc < kCPB; ++cc) acc[cc] = fmaf(dys[b * kCPB + cc], xv, acc[cc]);
+      }
+#pragma unroll
+      for (int cc = 0; cc < kCPB; ++cc)
+        if (c0 + cc < p.cout) p.grad_weight[static_cast<int64_t>(c0 + cc) * p.cin + k] = acc[cc];
+    }
+  }
+}
+
+// dx[b, k] = sum_c dy[b, c] W[c, k]: thread = one input channel k (coalesced rows of W), rows of dy
+// broadcast from shared memory, kRB batch rows per pass.
+constexpr int kRB = 16;
+constexpr int kPullThreads = 64;
+__global__ void __launch_bounds__(kPullThreads) fc_pull_kernel(const float* __restrict__ dy, const float* __restrict__ W,
+                                                              int B, int cin, int cout, float* __restrict__ dx) {
+  extern __shared__ float sm[];   // dys[kRB][cout]
+  const int k = blockIdx.x * kPullThreads + threadIdx.x;
+  for (int b0 = 0; b0 < B; b0 += kRB) {
+    const int nb = min(kRB, B - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * cout; i += kPullThreads) sm[i] = dy[static_cast<int64_t>(b0) * cout + i];
+    __syncthreads();
+    if (k < cin) {
+      float acc[kRB];
+#pragma unroll
+      for (int r = 0; r < kRB; ++r) acc[r] = 0.f;
+#pragma unroll 4
+      for (int c = 0; c < cout; ++c) {
+        const float wv = __ldg(W + static_cast<int64_t>(c) * cin + k);
+#pragma unroll
+        for (int r = 0; r < kRB; ++r)
+          if (r < nb) acc[r] = fmaf(sm[r * cout + c], wv, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < kRB; ++r)
+        if (r < nb) dx[static_cast<int64_t>(b0 + r) * cin + k] = acc[r];
+    }
+  }
+}
+
+int validate_fc(const char* who, int B, int L, const pcuda_fc_layer_t* layers) {
+  PCUDA_REQUIRE(layers != nullptr, PCUDA_E_NULL, "%s: layers is NULL", who);
+  PCUDA_REQUIRE(B >= 1 && L >= 1 && L <= 8, PCUDA_E_SHAPE, "%s: bad shape B=%d L=%d", who, B, L);
+  PCUDA_REQUIRE(B <= 2048, PCUDA_E_UNSUPPORTED, "%s: B=%d > 2048 rows", who, B);
+  for (int l = 0; l < L; ++l) {
+    const pcuda_fc_layer_t& y = layers[l];
+    PCUDA_REQUIRE(y.cin >= 1 && y.cout >= 1, PCUDA_E_SHAPE, "%s: layer %d has cin=%d cout=%d", who, l, y.cin, y.cout);
+    PCUDA_REQUIRE(l == 0 || y.cin == layers[l - 1].cout, PCUDA_E_SHAPE, "%s: layer %d cin=%d != previous cout=%d", who, l, y.cin, layers[l - 1].cout);
+    PCUDA_REQUIRE((y.cin & 3) == 0 && y.cin <= kMaxCin, PCUDA_E_UNSUPPORTED, "%s: layer %d cin=%d must be a multiple of 4, <= %d", who, l, y.cin, kMaxCin);
+    PCUDA_REQUIRE(y.weight && y.a, PCUDA_E_NULL, "%s: layer %d needs weight and a", who, l);
+    PCUDA_REQUIRE(aligned16(y.weight), PCUDA_E_ALIGN, "%s: layer %d weight must be 16-byte aligned", who, l);
+    if (y.bn) PCUDA_REQUIRE(y.gamma && y.beta && y.save_mean && y.save_invstd && y.y, PCUDA_E_NULL, "%s: layer %d BatchNorm tensors missing", who, l);
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace pcuda
+
+using namespace pcuda;
+
+extern "C" size_t pcuda_fcstack_ws_bytes(int B, int L, const pcuda_fc_layer_t* layers, int backward) {
+  if (!backward || B < 1 || L < 1 || !layers) return 16;
+  size_t mx = 0;
+  for (int l = 0; l < L; ++l) mx = mx > static_cast<size_t>(layers[l].cout) ? mx : static_cast<size_t>(layers[l].cout);
+  return 2 * sizeof(float) * static_cast<size_t>(B) * mx + 16;   // dy ping-pong
+}
+
+extern "C" int pcuda_fcstack_fwd(const float* x, int B, int L, const pcuda_fc_layer_t* layers, int train, float momentum,
+                                 float eps, int add_identity_k, pcuda_stream_t stream) {
+  if (int rc = validate_fc("fcstack_fwd", B, L, layers)) return rc;
+  PCUDA_REQUIRE(x != nullptr && aligned16(x), PCUDA_E_NULL, "fcstack_fwd: x is NULL or not 16-byte aligned");
+  for (int l = 0; l < L; ++l) {
+    PCUDA_REQUIRE(!layers[l].bn || train || (layers[l].running_mean && layers[l].running_var), PCUDA_E_NULL,
+                  "fcstack_fwd: eval mode needs running stats (layer %d)", l);
+    PCUDA_REQUIRE(!(layers[l].bn && train) || B > 1, PCUDA_E_SHAPE, "fcstack_fwd: train-mode BatchNorm needs more than 1 row");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(fc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  const float* in = x;
+  for (int l = 0; l < L; ++l) {
+    const pcuda_fc_layer_t& y = layers[l];
+    FcFwdParams p{};
+    p.x = in; p.W = y.weight; p.bias = y.bias; p.mask = y.mask;
+    p.gamma = y.bn ? y.gamma : nullptr; p.beta = y.beta;
+    p.running_mean = y.running_mean; p.running_var = y.running_var; p.save_mean = y.save_mean; p.save_invstd = y.save_invstd;
+    p.y = y.y; p.a = y.a; p.B = B; p.cin = y.cin; p.cout = y.cout; p.relu = y.relu; p.train = train;
+    p.iden_k = l == L - 1 ? add_identity_k : 0;
+    p.momentum = momentum; p.eps = eps;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(kCPB) * y.cin + static_cast<size_t>(B) * kCPB);
+    PCUDA_REQUIRE(smem <= 160 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_fwd: layer %d does not fit shared memory", l);
+    fc_fwd_kernel<<<(y.cout + kCPB - 1) / kCPB, kFcThreads, smem, st>>>(p);
+    in = y.a;
+  }
+  count_launch(L);
+  return check_launch("fcstack_fwd");
+}
+
+extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_layer_t* layers, int train,
+                                 const float* grad_out, float* grad_x, void* ws, pcuda_stream_t stream) {
+  if (int rc = validate_fc("fcstack_bwd", B, L, layers)) return rc;
+  PCUDA_REQUIRE(x && grad_out && ws, PCUDA_E_NULL, "fcstack_bwd: NULL x/grad_out/ws");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t mx = 0;
+  for (int l = 0; l < L; ++l) mx = mx > static_cast<size_t>(layers[l].cout) ? mx : static_cast<size_t>(layers[l].cout);
+  float* dybuf[2] = {static_cast<float*>(ws), static_cast<float*>(ws) + static_cast<size_t>(B) * mx};
+  int cur = 0, launches = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    const pcuda_fc_layer_t& y = layers[l];
+    FcBwdParams p{};
+    p.x = l == 0 ? x : layers[l - 1].a; p.W = y.weight; p.mask = y.mask;
+    p.gamma = y.bn ? y.gamma : nullptr; p.save_mean = y.save_mean; p.save_invstd = y.save_invstd; p.y = y.y; p.a = y.a;
+    if (l == L - 1) p.grad_out = grad_out;
+    else { p.dy_next = dybuf[cur ^ 1]; p.W_next = layers[l + 1].weight; p.cout_next = layers[l + 1].cout; }
+    p.dy = dybuf[cur];
+    p.grad_weight = y.grad_weight; p.grad_bias = y.grad_weight ? y.grad_bias : nullptr;
+    p.grad_gamma = y.grad_weight ? y.grad_gamma : nullptr; p.grad_beta = y.grad_weight ? y.grad_beta : nullptr;
+    p.B = B; p.cin = y.cin; p.cout = y.cout; p.relu = y.relu; p.train = train;
+    fc_bwd_kernel<<<(y.cout + kCPB - 1) / kCPB, kFcThreads, sizeof(float) * static_cast<size_t>(B) * kCPB, st>>>(p);
+    ++launches;
+    cur ^= 1;
+  }
+  if (grad_x != nullptr) {
+    const pcuda_fc_layer_t& y = layers[0];
+    const size_t smem = sizeof(float) * static_cast<size_t>(kRB) * y.cout;
+    PCUDA_REQUIRE(smem <= 48 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_bwd: first layer too wide for the input-gradient kernel");
+    fc_pull_kernel<<<(y.cin + kPullThreads - 1) / kPullThreads, kPullThreads, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
+    ++launches;
+  }
+  count_launch(launches);
+  return check_launch("fcstack_bwd");
+}

@@ -80,14 +80,13 @@ mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
                const float* __restrict__ pivot, const float* __restrict__ gamma,
                unsigned long long* __restrict__ keys) {
   __shared__ Tiles t;
-  __shared__ float ssum[TN], ssq[TN];
   __shared__ unsigned long long skey[TN];
   const int b = blockIdx.x / tiles_per_sample;
   const int n0 = (blockIdx.x - b * tiles_per_sample) * TM;
   const int c0 = blockIdx.y * TN;
   const int K = src.C;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  if (threadIdx.x < TN) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; skey[threadIdx.x] = 0ull; }
+  if (threadIdx.x < TN) skey[threadIdx.x] = 0ull;
 
   float acc[4][4] = {};
   auto a4 = [&](int r, int k) -> float4 {
@@ -154,18 +153,24 @@ mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
       }
     }
   }
+  // column sums of the 16 row groups are combined in a FIXED order through the (now free) operand
+  // tiles: float atomics would make the statistics, and through them every bf16 rounding downstream,
+  // depend on the scheduling order
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    atomicAdd(&ssum[tx * 4 + j], cs[j]);
-    atomicAdd(&ssq[tx * 4 + j], cq[j]);
+    t.As[ty][tx * 4 + j] = cs[j];
+    t.Bs[ty][tx * 4 + j] = cq[j];
     if (POOL) atomicMax(&skey[tx * 4 + j], ck[j]);
   }
   __syncthreads();
   if (threadIdx.x < TN && c0 + threadIdx.x < Cout) {
     const int c = c0 + threadIdx.x;
-    atomicAdd(&stats[c], static_cast<double>(ssum[threadIdx.x]));
-    atomicAdd(&stats[Cout + c], static_cast<double>(ssq[threadIdx.x]));
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int g = 0; g < TK; ++g) { s += static_cast<double>(t.As[g][threadIdx.x]); q += static_cast<double>(t.Bs[g][threadIdx.x]); }
+    atomicAdd(&stats[c], s);
+    atomicAdd(&stats[Cout + c], q);
     if (POOL) atomicMax(&keys[static_cast<int64_t>(b) * Cout + c], skey[threadIdx.x]);
   }
 }
@@ -614,12 +619,17 @@ __device__ __forceinline__ void dgrad_epilogue(const DgradOut& o, float (&acc)[4
     }
   }
   if (o.grad_x != nullptr) return;
+  // fixed-order combination of the 16 row groups (see mlp_fwd_kernel): ssum / ssq are [16][TN]
+  __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { atomicAdd(&ssum[tx * 4 + j], cs[j]); atomicAdd(&ssq[tx * 4 + j], cq[j]); }
+  for (int j = 0; j < 4; ++j) { ssum[ty * TN + tx * 4 + j] = cs[j]; ssq[ty * TN + tx * 4 + j] = cq[j]; }
   __syncthreads();
   if (threadIdx.x < TN && c0 + threadIdx.x < o.Cp) {
-    atomicAdd(&o.sums[c0 + threadIdx.x], static_cast<double>(ssum[threadIdx.x]));
-    atomicAdd(&o.sums[o.Cp + c0 + threadIdx.x], static_cast<double>(ssq[threadIdx.x]));
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) { s += static_cast<double>(ssum[g * TN + threadIdx.x]); q += static_cast<double>(ssq[g * TN + threadIdx.x]); }
+    atomicAdd(&o.sums[c0 + threadIdx.x], s);
+    atomicAdd(&o.sums[o.Cp + c0 + threadIdx.x], q);
   }
 }
 
@@ -629,14 +639,13 @@ pool_dgrad_kernel(ActSrc src, const float* __restrict__ Q, const float* __restri
                   const float* __restrict__ coef, const int32_t* __restrict__ arg, int C, int N,
                   int tiles_per_sample, DgradOut o) {
   __shared__ Tiles t;
-  __shared__ float ssum[TN], ssq[TN];
+  __shared__ float ssum[16 * TN], ssq[16 * TN];
   __shared__ float sparse[TM][TN + 1];
   const int K = src.C;  // == o.Cp
   const int b = blockIdx.x / tiles_per_sample;
   const int n0 = (blockIdx.x - b * tiles_per_sample) * TM;
   const int c0 = blockIdx.y * TN;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  if (threadIdx.x < TN) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
   for (int i = threadIdx.x; i < TM * (TN + 1); i += kThreads) (&sparse[0][0])[i] = 0.f;
   __syncthreads();
   // sparse part, deterministic: thread kt owns column kt and walks the channels in order
@@ -683,13 +692,12 @@ pool_dgrad_kernel(ActSrc src, const float* __restrict__ Q, const float* __restri
 __global__ void __launch_bounds__(kThreads)
 dense_dgrad_kernel(DySrc dys, const float* __restrict__ W, int N, int tiles_per_sample, DgradOut o) {
   __shared__ Tiles t;
-  __shared__ float ssum[TN], ssq[TN];
+  __shared__ float ssum[16 * TN], ssq[16 * TN];
   const int C = dys.C, Kp = o.Cp;
   const int b = blockIdx.x / tiles_per_sample;
   const int n0 = (blockIdx.x - b * tiles_per_sample) * TM;
   const int c0 = blockIdx.y * TN;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  if (threadIdx.x < TN) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
   float acc[4][4] = {};
   auto a4 = [&](int r, int c) -> float4 {
     if (n0 + r >= N) return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -736,9 +744,8 @@ __global__ void dense_top_kernel(const float* __restrict__ grad_out, const float
                                  const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                                  int N, int C, float* __restrict__ dz, double* __restrict__ sums) {
   __shared__ float tile[32][33];
-  __shared__ float ssum[32], ssq[32];
+  __shared__ float ssum[8 * 32], ssq[8 * 32];   // launched with blockDim (32, 8)
   const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  if (threadIdx.y == 0) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int c = c0 + r, n = n0 + threadIdx.x;
     tile[r][threadIdx.x] = (c < C && n < N) ? grad_out[(static_cast<int64_t>(b) * C + c) * N + n] : 0.f;
@@ -758,12 +765,14 @@ __global__ void dense_top_kernel(const float* __restrict__ grad_out, const float
       q = fmaf(v, yh, q);
     }
   }
-  atomicAdd(&ssum[threadIdx.x], s);
-  atomicAdd(&ssq[threadIdx.x], q);
+  ssum[threadIdx.y * 32 + threadIdx.x] = s;
+  ssq[threadIdx.y * 32 + threadIdx.x] = q;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-    atomicAdd(&sums[c], static_cast<double>(ssum[threadIdx.x]));
-    atomicAdd(&sums[C + c], static_cast<double>(ssq[threadIdx.x]));
+    double sd = 0.0, qd = 0.0;
+    for (int g = 0; g < static_cast<int>(blockDim.y); ++g) { sd += static_cast<double>(ssum[g * 32 + threadIdx.x]); qd += static_cast<double>(ssq[g * 32 + threadIdx.x]); }
+    atomicAdd(&sums[c], sd);
+    atomicAdd(&sums[C + c], qd);
   }
 }
 

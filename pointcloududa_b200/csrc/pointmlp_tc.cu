@@ -414,38 +414,55 @@ __global__ void __launch_bounds__(kThreads, 1) ws_kernel(const WsParams p) {
                 }
               }
             } else {
-              // dgrad epilogues
-              int hv = -1;
-              if (MODE == POOL_DGRAD) hv = (FULL || lane < ncol) ? __ldg(p.head + m0 + ch * 32 + lane) : -1;
+              // dgrad epilogues.  Every global / shared load of the chunk is issued before its first
+              // store: the dz_prev stores may alias the loads as far as the compiler can tell, and a
+              // load placed behind a store (or behind a data-dependent branch) would serialise one
+              // L2 round trip per column.
+              const int col0 = ch * 32;
+              if (MODE == POOL_DGRAD) {
+                const int hv = (FULL || lane < ncol) ? __ldg(p.head + m0 + col0 + lane) : -1;
+                float sp[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (FULL || i < ncol) {
-                  float val = v[i];
-                  const int col = ch * 32 + i;
-                  if (MODE == POOL_DGRAD) {
-                    const int h = __shfl_sync(0xffffffffu, hv, i);
-                    float sp = 0.f;
-                    if (h >= 0 && rok) sp = __ldg(p.srows + (static_cast<int64_t>(b) * p.Cpool + h) * p.K + r);
-                    val = sp - uk - val;
+                for (int i = 0; i < 32; ++i) {
+                  const int h = __shfl_sync(0xffffffffu, hv, i);
+                  sp[i] = (h >= 0 && rok) ? __ldg(p.srows + (static_cast<int64_t>(b) * p.Cpool + h) * p.K + r) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = sp[i] - uk - v[i];
+              }
+              if (rok) {
+                if (to_x) {
+                  float* gx = p.out.grad_x + (static_cast<int64_t>(b) * p.R + r) * p.tl.N + n0 + col0;
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (FULL || i < ncol) gx[i] = v[i];
+                } else {
+                  const bool from_slab = act_slab != nullptr && slab_ok;
+                  float src[32];   // bf16 activation a (from_slab) or fp32 pre-activation y of the previous layer
+                  if (from_slab) {
+                    // a = relu?(gamma*yhat + beta) in bf16: mask = a > 0, yhat = (a - beta) / gamma
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) src[i] = bf16_at(act_slab, col0 + i, r & 63);
+                  } else {
+                    const float* yp = p.out.y_prev + (m0 + col0) * p.R + r;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) src[i] = (FULL || i < ncol) ? __ldg(yp + static_cast<int64_t>(i) * p.R) : 0.f;
                   }
-                  if (rok) {
-                    const int64_t m = m0 + col;
-                    if (to_x) {
-                      p.out.grad_x[(static_cast<int64_t>(b) * p.R + r) * p.tl.N + n0 + col] = val;
-                    } else {
+                  float* dzp = p.out.dz_prev + (m0 + col0) * p.R + r;
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    if (FULL || i < ncol) {
                       float yh;
                       bool on = true;
-                      if (act_slab != nullptr && slab_ok) {
-                        // a = relu?(gamma*yhat + beta) in bf16: mask = a > 0, yhat = (a - beta) / gamma
-                        const float a = bf16_at(act_slab, col, r & 63);
-                        if (p.out.relu) on = a > 0.f;
-                        yh = (a - e3) * inv_g;
+                      if (from_slab) {
+                        if (p.out.relu) on = src[i] > 0.f;
+                        yh = (src[i] - e3) * inv_g;
                       } else {
-                        yh = (__ldg(p.out.y_prev + m * p.R + r) - e0) * e1;
+                        yh = (src[i] - e0) * e1;
                         if (p.out.relu) on = fmaf(yh, e2, e3) > 0.f;
                       }
-                      val = on ? val : 0.f;
-                      p.out.dz_prev[m * p.R + r] = val;
+                      const float val = on ? v[i] : 0.f;
+                      dzp[static_cast<int64_t>(i) * p.R] = val;
                       sa[i & 3] += val;
                       qa[i & 3] = fmaf(val, yh, qa[i & 3]);
                     }

@@ -9,8 +9,10 @@ Same classes, constructor signatures, forward signatures and state_dict keys as 
 What changes is the execution: every "shared MLP" — a run of Conv1d(k=1)+BatchNorm1d(+ReLU)
 layers, optionally ending in the global max-pool — is one call into libpcuda
 (`pcuda_pointmlp_fwd/_bwd`, csrc/pointmlp*.cu).  The nn.Conv1d / nn.BatchNorm1d submodules remain
-as parameter and buffer containers only.  The tiny FC heads ([B,1024] -> ...) stay in PyTorch so
-Dropout draws from torch's Philox stream exactly like the reference.
+as parameter and buffer containers only.  The FC heads ([B,1024] -> 512 -> 256 -> k) are one call into
+`pcuda_fcstack_fwd/_bwd` each (csrc/fcstack.cu: one launch per layer and direction instead of ~8
+framework kernels); the Dropout mask is still drawn by torch (same Philox stream and offsets as the
+reference's nn.Dropout on a [B,256] tensor) and handed to the kernel.
 """
 from __future__ import annotations
 
@@ -23,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
-from .._lib import MlpLayer, PcudaError, check
+from .._lib import FcLayer, MlpLayer, PcudaError, check
 
 PRECISIONS = {"fp32": 0, "bf16": 1}
 DEFAULT_PRECISION = "bf16"
@@ -148,9 +150,122 @@ def shared_mlp(x: torch.Tensor, convs: Sequence[nn.Conv1d], bns: Sequence[nn.Bat
     out = _SharedMLP.apply(x, bool(pool), bool(train), PRECISIONS[precision], tuple(bool(r) for r in relus),
                            tuple(momenta), float(eps), tuple(buffers), *params)
     if train:
-        for bn in bns:
-            if bn.num_batches_tracked is not None:
-                bn.num_batches_tracked.add_(1)
+        counters = [bn.num_batches_tracked for bn in bns if bn.num_batches_tracked is not None]
+        if counters:
+            torch._foreach_add_(counters, 1)
+    return out
+
+
+class _FcStack(torch.autograd.Function):
+    """a_L = Linear [*mask] [BatchNorm1d] [ReLU] ... on [B, C] rows, one libpcuda launch per layer."""
+
+    @staticmethod
+    def forward(ctx, x, train: bool, relus: Tuple[bool, ...], bn_flags: Tuple[bool, ...], momentum: float, eps: float,
+                iden_k: int, buffers: Tuple[Optional[torch.Tensor], ...], masks: Tuple[Optional[torch.Tensor], ...], *params):
+        if not x.is_cuda:
+            raise PcudaError("PointNetCls runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if x.dtype != torch.float32 or x.dim() != 2:
+            raise PcudaError(f"expected a float32 [B, C] tensor, got {x.dtype} {tuple(x.shape)}")
+        L = len(relus)
+        xc = x.contiguous()
+        B = xc.shape[0]
+        dev = xc.device
+        lay = (FcLayer * L)()
+        keep, saved = [], []
+        for l in range(L):
+            w, b, g, be = params[4 * l: 4 * l + 4]
+            cout, cin = w.shape
+            w2 = w.detach().contiguous()
+            b2 = None if b is None else b.detach().contiguous()
+            g2 = None if g is None else g.detach().contiguous()
+            be2 = None if be is None else be.detach().contiguous()
+            m2 = None if masks[l] is None else masks[l].contiguous()
+            bn = bool(bn_flags[l])
+            mean = torch.empty(cout, dtype=torch.float32, device=dev) if bn else None
+            invstd = torch.empty(cout, dtype=torch.float32, device=dev) if bn else None
+            y = torch.empty((B, cout), dtype=torch.float32, device=dev) if bn else None
+            a = torch.empty((B, cout), dtype=torch.float32, device=dev)
+            keep += [w2, b2, g2, be2, m2]
+            saved.append((mean, invstd, y, a))
+            lay[l].cin, lay[l].cout, lay[l].bn, lay[l].relu = cin, cout, int(bn), int(relus[l])
+            lay[l].weight, lay[l].bias, lay[l].mask = _ptr(w2), _ptr(b2), _ptr(m2)
+            lay[l].gamma, lay[l].beta = _ptr(g2), _ptr(be2)
+            lay[l].running_mean, lay[l].running_var = _ptr(buffers[2 * l]), _ptr(buffers[2 * l + 1])
+            lay[l].save_mean, lay[l].save_invstd, lay[l].y, lay[l].a = _ptr(mean), _ptr(invstd), _ptr(y), _ptr(a)
+        with torch.cuda.device(dev):
+            check(_lib.lib().pcuda_fcstack_fwd(_ptr(xc), B, L, lay, int(train), float(momentum), float(eps), int(iden_k),
+                                               torch.cuda.current_stream().cuda_stream), "pcuda_fcstack_fwd")
+        ctx.cfg = (train, relus, bn_flags, B, L)
+        ctx.save_for_backward(xc)
+        ctx.keep, ctx.saved = keep, saved
+        return saved[-1][3]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        train, relus, bn_flags, B, L = ctx.cfg
+        (xc,) = ctx.saved_tensors
+        keep, saved = ctx.keep, ctx.saved
+        dev = xc.device
+        need_x = ctx.needs_input_grad[0]
+        needs_p = ctx.needs_input_grad[9:]
+        lay = (FcLayer * L)()
+        grads: List[Optional[torch.Tensor]] = []
+        for l in range(L):
+            w2, b2, g2, be2, m2 = keep[5 * l: 5 * l + 5]
+            mean, invstd, y, a = saved[l]
+            cout, cin = w2.shape
+            lay[l].cin, lay[l].cout, lay[l].bn, lay[l].relu = cin, cout, int(bn_flags[l]), int(relus[l])
+            lay[l].weight, lay[l].bias, lay[l].mask = _ptr(w2), _ptr(b2), _ptr(m2)
+            lay[l].gamma, lay[l].beta = _ptr(g2), _ptr(be2)
+            lay[l].save_mean, lay[l].save_invstd, lay[l].y, lay[l].a = _ptr(mean), _ptr(invstd), _ptr(y), _ptr(a)
+            if any(needs_p[4 * l: 4 * l + 4]):
+                gw = torch.empty((cout, cin), dtype=torch.float32, device=dev)
+                gb = torch.empty(cout, dtype=torch.float32, device=dev) if b2 is not None else None
+                gg = torch.empty(cout, dtype=torch.float32, device=dev) if g2 is not None else None
+                gbe = torch.empty(cout, dtype=torch.float32, device=dev) if be2 is not None else None
+                lay[l].grad_weight, lay[l].grad_bias = _ptr(gw), _ptr(gb)
+                lay[l].grad_gamma, lay[l].grad_beta = _ptr(gg), _ptr(gbe)
+                grads += [gw, gb, gg, gbe]
+            else:
+                grads += [None, None, None, None]
+        gx = torch.empty_like(xc) if need_x else None
+        go = grad_out.contiguous()
+        Lb = _lib.lib()
+        with torch.cuda.device(dev):
+            ws = torch.empty(max(Lb.pcuda_fcstack_ws_bytes(B, L, lay, 1), 16), dtype=torch.uint8, device=dev)
+            check(Lb.pcuda_fcstack_bwd(_ptr(xc), B, L, lay, int(train), _ptr(go), _ptr(gx), _ptr(ws),
+                                       torch.cuda.current_stream().cuda_stream), "pcuda_fcstack_bwd")
+        for i, need in enumerate(needs_p):
+            if not need:
+                grads[i] = None
+        return (gx, None, None, None, None, None, None, None, None, *grads)
+
+
+def fc_stack(x: torch.Tensor, linears: Sequence[nn.Linear], bns: Sequence[Optional[nn.BatchNorm1d]],
+             relus: Sequence[bool], masks: Optional[Sequence[Optional[torch.Tensor]]] = None,
+             add_identity_k: int = 0) -> torch.Tensor:
+    """Run Linear [* dropout mask] [+ BatchNorm1d] [+ ReLU] layers on [B, C] rows as one fused op per layer
+    (the FC heads of the reference, PointNetCls.py:46-62, :89-101, :208-213)."""
+    real = [bn for bn in bns if bn is not None]
+    eps = real[0].eps if real else 1e-5
+    momentum = real[0].momentum if real else 0.1
+    train = (real[0].training or not real[0].track_running_stats) if real else False
+    params, buffers = [], []
+    for lin, bn in zip(linears, bns):
+        if bn is not None:
+            if bn.momentum is None:
+                raise PcudaError("BatchNorm1d(momentum=None) (cumulative average) is not supported")
+            if bn.eps != eps or bn.momentum != momentum or (bn.training or not bn.track_running_stats) != train:
+                raise PcudaError("all BatchNorm layers of one FC head must share eps, momentum and mode")
+        params += [lin.weight, lin.bias, None if bn is None else bn.weight, None if bn is None else bn.bias]
+        buffers += [None if bn is None else bn.running_mean, None if bn is None else bn.running_var]
+    masks = tuple(masks) if masks is not None else (None,) * len(linears)
+    out = _FcStack.apply(x, bool(train), tuple(bool(r) for r in relus), tuple(bn is not None for bn in bns),
+                         float(momentum), float(eps), int(add_identity_k), tuple(buffers), masks, *params)
+    if train:
+        counters = [bn.num_batches_tracked for bn in real if bn.num_batches_tracked is not None]
+        if counters:
+            torch._foreach_add_(counters, 1)
     return out
 
 
@@ -193,11 +308,8 @@ class STN3d(nn.Module):
         _check_batch(batchsize)
         x = shared_mlp(x, [self.conv1, self.conv2, self.conv3], [self.bn1, self.bn2, self.bn3],
                        [True, True, True], pool=True, precision=self._precision)     # :41-45
-        x = F.relu(self.bn4(self.fc1(x)))
-        x = F.relu(self.bn5(self.fc2(x)))
-        x = self.fc3(x)
-        iden = torch.eye(3, dtype=x.dtype, device=x.device).reshape(1, 9)
-        x = x + iden
+        x = fc_stack(x, [self.fc1, self.fc2, self.fc3], [self.bn4, self.bn5, None], [True, True, False],
+                     add_identity_k=3)                                                # :46-62 (fc, bn, relu, + I)
         return x.view(-1, 3, 3)
 
 
@@ -226,11 +338,8 @@ class STNkd(nn.Module):
     def forward(self, x):
         x = shared_mlp(x, [self.conv1, self.conv2, self.conv3], [self.bn1, self.bn2, self.bn3],
                        [True, True, True], pool=True, precision=self._precision)     # :82-86
-        x = F.relu(self.bn4(self.fc1(x)))
-        x = F.relu(self.bn5(self.fc2(x)))
-        x = self.fc3(x)
-        iden = torch.eye(self.k, dtype=x.dtype, device=x.device).reshape(1, self.k * self.k)
-        x = x + iden
+        x = fc_stack(x, [self.fc1, self.fc2, self.fc3], [self.bn4, self.bn5, None], [True, True, False],
+                     add_identity_k=self.k)                                           # :89-101
         return x.view(-1, self.k, self.k)
 
 
@@ -341,6 +450,7 @@ class PointNetCls(nn.Module):
         self.in1 = nn.InstanceNorm1d(512, track_running_stats=True)
         self.in2 = nn.InstanceNorm1d(256, track_running_stats=True)
         self.relu = nn.ReLU()
+        self._ones = None
         if heinit or cvinit:
             self._initialize_weights(heinit=heinit)
 
@@ -358,9 +468,15 @@ class PointNetCls(nn.Module):
         x, trans, trans_feat = self.feat(x)
         batchsize = x.size()[0]
         _check_batch(batchsize)
-        x = F.relu(self.bn1(self.fc1(x)))                                          # :208
-        x = F.relu(self.bn2(self.dropout(self.fc2(x))))                            # :209
-        x = self.fc3(x)
+        # :208-213  relu(bn1(fc1)), relu(bn2(dropout(fc2))), fc3.  The Dropout mask comes from torch's own
+        # nn.Dropout applied to a tensor of ones of fc2's output shape: same Philox draw as the reference
+        mask = None
+        if self.dropout.training and self.dropout.p > 0:
+            if self._ones is None or self._ones.shape[0] != batchsize or self._ones.device != x.device:
+                self._ones = torch.ones(batchsize, self.fc2.out_features, dtype=x.dtype, device=x.device)
+            mask = self.dropout(self._ones)
+        x = fc_stack(x, [self.fc1, self.fc2, self.fc3], [self.bn1, self.bn2, None], [True, True, False],
+                     masks=[None, mask, None])
         return x, trans, trans_feat
 
 

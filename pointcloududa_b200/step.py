@@ -61,7 +61,9 @@ class AdversarialStep:
         self.d4 = PointNetCls(feature_transform=cfg.feature_transform, ext=cfg.ext,
                               precision=cfg.precision).to(device).train()
         # optim_dis4 of the reference: SGD, momentum .99, weight decay 5e-4 (train_mscmrseg.py:450-455)
-        self.opt = torch.optim.SGD(self.d4.parameters(), lr=cfg.lr_dis, momentum=0.99, weight_decay=0.0005)
+        # (fused=True: one multi-tensor kernel for the whole update; same arithmetic as the default foreach path)
+        self.opt = torch.optim.SGD(self.d4.parameters(), lr=cfg.lr_dis, momentum=0.99, weight_decay=0.0005,
+                                   fused=True)
         self._pnames = [n for n, _ in self.d4.named_parameters()]
         self.bucket = pdist.GradBucket(self.d4.parameters())
         B, C, H, W, N = cfg.B, cfg.C, cfg.H, cfg.W, cfg.N

@@ -50,6 +50,14 @@ def test_argument_validation_without_gpu():
     assert L.pcuda_chamfer_bwd_ws_bytes(8, 300, 300) == 8 * 3 * 8 * 600
     lay = (_lib.MlpLayer * 1)()
     assert L.pcuda_pointmlp_fwd(None, 0, 0, 0, 2, 8, 1, lay, 1, 1, 0.1, 1e-5, 0, None, None, None, None) == -2
+    fc = (_lib.FcLayer * 1)()
+    assert L.pcuda_fcstack_fwd(None, 4, 1, fc, 1, 0.1, 1e-5, 0, None) == -2           # cin = cout = 0
+    fc[0].cin, fc[0].cout = 6, 4
+    assert L.pcuda_fcstack_fwd(None, 4, 1, fc, 1, 0.1, 1e-5, 0, None) == -3           # cin % 4 != 0
+    assert L.pcuda_fcstack_fwd(None, 0, 1, fc, 1, 0.1, 1e-5, 0, None) == -2
+    fc[0].cin, fc[0].cout = 8, 4
+    assert L.pcuda_fcstack_fwd(None, 4, 1, fc, 1, 0.1, 1e-5, 0, None) == -1           # NULL weight
+    assert L.pcuda_fcstack_ws_bytes(4, 1, fc, 1) == 2 * 4 * 4 * 4 + 16
 
 
 def test_cpu_tensors_are_rejected_not_computed():

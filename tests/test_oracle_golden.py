@@ -174,3 +174,30 @@ def test_pointnet_running_stats(golden_pointnet):
     M = B * N
     assert max_rel(0.1 * mean, g["buf/feat.bn3.running_mean"]) < 1e-4
     assert max_rel(0.9 + 0.1 * var * M / (M - 1), g["buf/feat.bn3.running_var"]) < 1e-4
+
+
+def test_bf16_operand_rounding_matches_torch():
+    """oracle.bf16_round (used to restate the tensor-core path's operand rounding) == torch's
+    round-to-nearest-even float32 -> bfloat16 conversion, including ties and denormal-range values."""
+    import torch
+    rs = np.random.RandomState(0)
+    a = np.concatenate([rs.standard_normal(50000).astype(np.float32) * np.float32(3.0),
+                        np.array([0.0, -0.0, 1.0, 1.00390625, 1.01171875, -1.00390625, 3.4e38, 1e-39, 65280.0], np.float32)])
+    want = torch.from_numpy(a).bfloat16().float().numpy()
+    assert np.array_equal(oracle.bf16_round(a), want)
+    assert np.array_equal(oracle.bf16_round(a.astype(np.float64)), want.astype(np.float64))
+    assert oracle.bf16_layer(64) and oracle.bf16_layer(512) and not oracle.bf16_layer(3) and not oracle.bf16_layer(1024)
+
+
+def test_pointnet_oracle_bf16_operands_only_touch_wide_layers():
+    spec = oracle.PointNetSpec()
+    params = oracle.make_params(spec, 1)
+    x = np.random.RandomState(2).rand(4, 3, 40).astype(np.float32)
+    layers = [dict(weight=params["feat.conv1.weight"], bias=params["feat.conv1.bias"], gamma=params["feat.bn1.weight"],
+                   beta=params["feat.bn1.bias"], relu=True)]
+    a, _ = oracle.stack_forward(x, layers, False, np.float64)
+    b, _ = oracle.stack_forward(x, layers, False, np.float64, bf16_operands=True)
+    assert np.array_equal(a, b)                       # K = 3 layer stays full precision
+    l0 = oracle.pointnet_forward(params, x, spec, dtype=np.float64)[0]
+    l1 = oracle.pointnet_forward(params, x, spec, dtype=np.float64, bf16_operands=True)[0]
+    assert not np.array_equal(l0, l1) and np.abs(l0 - l1).max() < 0.5 * np.abs(l0).max()
