@@ -16,6 +16,8 @@
 //
 // Latency-bound by construction (B <= a few hundred rows): the kernels are written for few, wide,
 // coalesced memory phases rather than for FLOPs.
+#include <algorithm>
+
 #include "pcuda_common.cuh"
 
 namespace pcuda {
@@ -41,7 +43,7 @@ struct FcFwdParams {
 
 // dynamic shared memory: Wsm[kCPB][cin] | ys[B][kCPB]
 __global__ void __launch_bounds__(kFcThreads) fc_fwd_kernel(const FcFwdParams p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* Wsm = sm;
   float* ys = sm + kCPB * p.cin;
   __shared__ float s_mean[kCPB], s_scale[kCPB], s_shift[kCPB];
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(kFcThreads) fc_fwd_kernel(const FcFwdParams p)
   for (int b = warp; b < p.B; b += kFcThreads / 32) {
     const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(b) * p.cin);
     float acc[kCPB] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+#pragma unroll 8
     for (int k4 = lane; k4 < cin4; k4 += 32) {
       const float4 xv = __ldg(xr + k4);
 #pragma unroll
@@ -150,7 +152,7 @@ struct FcBwdParams {
 
 // dynamic shared memory: dys[B][kCPB]
 __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* dys = sm;
   const int c0 = blockIdx.x * kCPB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p)
     for (int b = warp; b < p.B; b += kFcThreads / 32) {
       const float* dn = p.dy_next + static_cast<int64_t>(b) * p.cout_next;
       float acc[kCPB] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+#pragma unroll 8
       for (int o = lane; o < p.cout_next; o += 32) {
         const float d = __ldg(dn + o);
         const float* wr = p.W_next + static_cast<int64_t>(o) * p.cout + c0;
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p)
   if (p.grad_weight != nullptr) {
     for (int k = threadIdx.x; k < p.cin; k += kFcThreads) {
       float acc[kCPB] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+#pragma unroll 8
       for (int b = 0; b < p.B; ++b) {
         const float xv = __ldg(p.x + static_cast<int64_t>(b) * p.cin + k);
 #pragma unroll
@@ -256,33 +258,49 @@ __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p)
   }
 }
 
-// dx[b, k] = sum_c dy[b, c] W[c, k]: thread = one input channel k (coalesced rows of W), rows of dy
-// broadcast from shared memory, kRB batch rows per pass.
+// dx[b, k] = sum_c dy[b, c] W[c, k].  A CTA owns 32 input channels k (one per lane: coalesced 128-byte
+// segments of the rows of W); its 8 warps split the contraction index c and are combined in a fixed
+// order through shared memory; kRB batch rows per pass, their dy values staged as [c][row] so a warp
+// reads them as broadcast float4.
 constexpr int kRB = 16;
-constexpr int kPullThreads = 64;
+constexpr int kPullThreads = 256;
 __global__ void __launch_bounds__(kPullThreads) fc_pull_kernel(const float* __restrict__ dy, const float* __restrict__ W,
                                                               int B, int cin, int cout, float* __restrict__ dx) {
-  extern __shared__ float sm[];   // dys[kRB][cout]
-  const int k = blockIdx.x * kPullThreads + threadIdx.x;
+  extern __shared__ __align__(16) float sm[];   // dys[cout][kRB], reused as red[8][kRB][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
   for (int b0 = 0; b0 < B; b0 += kRB) {
     const int nb = min(kRB, B - b0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nb * cout; i += kPullThreads) sm[i] = dy[static_cast<int64_t>(b0) * cout + i];
+    for (int i = threadIdx.x; i < cout * kRB; i += kPullThreads) {
+      const int c = i / kRB, r = i - c * kRB;
+      sm[i] = r < nb ? dy[static_cast<int64_t>(b0 + r) * cout + c] : 0.f;
+    }
     __syncthreads();
-    if (k < cin) {
-      float acc[kRB];
+    float acc[kRB];
 #pragma unroll
-      for (int r = 0; r < kRB; ++r) acc[r] = 0.f;
-#pragma unroll 4
-      for (int c = 0; c < cout; ++c) {
-        const float wv = __ldg(W + static_cast<int64_t>(c) * cin + k);
+    for (int r = 0; r < kRB; ++r) acc[r] = 0.f;
+#pragma unroll 8
+    for (int c = warp; c < cout; c += kPullThreads / 32) {
+      const float wv = k < cin ? __ldg(W + static_cast<int64_t>(c) * cin + k) : 0.f;
+      const float4* d4 = reinterpret_cast<const float4*>(sm + c * kRB);
 #pragma unroll
-        for (int r = 0; r < kRB; ++r)
-          if (r < nb) acc[r] = fmaf(sm[r * cout + c], wv, acc[r]);
+      for (int r4 = 0; r4 < kRB / 4; ++r4) {
+        const float4 d = d4[r4];
+        acc[4 * r4 + 0] = fmaf(d.x, wv, acc[4 * r4 + 0]); acc[4 * r4 + 1] = fmaf(d.y, wv, acc[4 * r4 + 1]);
+        acc[4 * r4 + 2] = fmaf(d.z, wv, acc[4 * r4 + 2]); acc[4 * r4 + 3] = fmaf(d.w, wv, acc[4 * r4 + 3]);
       }
+    }
+    __syncthreads();
 #pragma unroll
-      for (int r = 0; r < kRB; ++r)
-        if (r < nb) dx[static_cast<int64_t>(b0 + r) * cin + k] = acc[r];
+    for (int r = 0; r < kRB; ++r) sm[(warp * kRB + r) * 32 + lane] = acc[r];
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * 32; i += kPullThreads) {
+      const int r = i >> 5, l = i & 31;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kPullThreads / 32; ++w) t += sm[(w * kRB + r) * 32 + l];
+      if (blockIdx.x * 32 + l < cin) dx[static_cast<int64_t>(b0 + r) * cin + blockIdx.x * 32 + l] = t;
     }
   }
 }
@@ -375,9 +393,10 @@ extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_la
   }
   if (grad_x != nullptr) {
     const pcuda_fc_layer_t& y = layers[0];
-    const size_t smem = sizeof(float) * static_cast<size_t>(kRB) * y.cout;
+    const size_t need = static_cast<size_t>(kRB) * std::max(y.cout, (kPullThreads / 32) * 32);
+    const size_t smem = sizeof(float) * need;
     PCUDA_REQUIRE(smem <= 48 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_bwd: first layer too wide for the input-gradient kernel");
-    fc_pull_kernel<<<(y.cin + kPullThreads - 1) / kPullThreads, kPullThreads, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
+    fc_pull_kernel<<<(y.cin + 31) / 32, kPullThreads, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
     ++launches;
   }
   count_launch(launches);

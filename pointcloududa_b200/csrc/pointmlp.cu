@@ -230,7 +230,7 @@ __global__ void pool_finalize_kernel(const unsigned long long* __restrict__ keys
   const float g = gamma[c];
   const float y = g > 0.f ? vv : (g < 0.f ? -vv : mean[c]);
   out[i] = bn_act(y, mean[c], invstd[c], g, beta[c], relu);
-  arg[i] = n;
+  arg[i] = g == 0.f ? 0 : n;   // gamma == 0: every point ties at beta and the first one wins
 }
 
 // dense output (pool == 0): out[b, c, n] = act(y[(b,n), c]); 32x32 smem transpose
@@ -974,7 +974,8 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
   // bf16 copies of the tensor-core layers' weights
   for (int l = 0; l < L; ++l)
     if (layer_tc(l))
-      if (int rc = tc::pack_w(layers[l].weight, layers[l].cout, layers[l].cin, false, w.wpack[l], st)) return rc;
+      if (int rc = tc::pack_w(layers[l].weight, layers[l].cout, layers[l].cin, false, w.wpack[l], st,
+                              (pool && l == L - 1) ? layers[l].gamma : nullptr)) return rc;
   if (!layer_tc(0)) {
     // pivot of layer 0 (no BN to finalise yet)
     bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, 0, 1.0, eps, momentum, train, nullptr, nullptr, nullptr, nullptr,

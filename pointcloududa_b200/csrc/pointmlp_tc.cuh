@@ -25,7 +25,8 @@ size_t w_pack_bytes(int R, int K);                       // ceil(R/128) blocks o
 int pack_act(const ActSrc& src, const Tiling& tl, uint8_t* out, cudaStream_t st);
 int pack_dy(const DySrc& dys, const Tiling& tl, uint8_t* out, cudaStream_t st);
 // transposed == false: A[r,k] = W[r*K + k];  true: A[r,k] = W[k*R + r]
-int pack_w(const float* W, int R, int K, bool transposed, uint8_t* out, cudaStream_t st);
+// sign_src (non-transposed only): rows with sign_src[r] < 0 are negated (pooled forward layer)
+int pack_w(const float* W, int R, int K, bool transposed, uint8_t* out, cudaStream_t st, const float* sign_src = nullptr);
 
 // y_l = W a_{l-1} (+ bias): stores y (dense) or reduces to per-(cloud,channel) arg-max keys (pool);
 // accumulates bias-free per-channel sum / sum of squares into stats[0..C), stats[C..2C).
