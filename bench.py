@@ -162,6 +162,70 @@ def run_cpu_baseline(w: dict, budget_s: float, min_steps: int = 2, max_steps: in
 
 
 # ------------------------------------------------------------------------------------------------
+KERNEL_WORK = {
+    # kernel-name fragment -> (bound, algorithmic work per launch as a function of the per-rank workload)
+    # default D4 (3->64->128->1024 twice: STN3d trunk and main trunk), M = B*N points
+    "ws_kernel<1>": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 128 * 1024),     # pooled 128->1024 GEMM (tcgen05)
+    "ws_kernel<0>": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 64 * 128),       # dense 64->128 GEMM
+    "ws_kernel<2>": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 128 * 64),       # dgrad 128->64
+    "ws_kernel<3>": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 128 * 128),      # pooled-layer low-rank dgrad (a Q)
+    "pt_kernel": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 128 * 128),         # wgrad / Gram over points (upper bound of the two)
+    "entropy_fwd": ("hbm", lambda w: (8.0 + (4.0 if w["return_prob"] else 0.0)) * w["B"] * w["C"] * w["H"] * w["W"]),
+    "entropy_bwd": ("hbm", lambda w: 12.0 * w["B"] * w["C"] * w["H"] * w["W"]),
+    "chamfer_nn": ("hbm", lambda w: 48.0 * w["B"] * w["N"]),                      # 24 B/point in + out, both clouds
+    "pack_act_kernel": ("hbm", lambda w: (4.0 + 2.0) * w["B"] * w["N"] * 128),    # fp32 in, bf16 out (widest layer)
+}
+
+
+def kernel_profile(step, w: dict, pk: dict, reps: int = 5):
+    """Per-kernel device time of the (graph-replayed) step from CUPTI activity records, taken live in
+    this process right after the timed region: which kernel dominates, and its roofline."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(reps):
+            step.run()
+        torch.cuda.synchronize()
+    agg = {}
+    for e in prof.events():
+        if e.device_type != torch.autograd.DeviceType.CUDA:
+            continue
+        a = agg.setdefault(e.name, [0, 0.0])
+        a[0] += 1
+        a[1] += e.device_time
+    if not agg:
+        raise RuntimeError("no device activity records")
+    tot = sum(v[1] for v in agg.values())
+    ours = {k: v for k, v in agg.items() if "pcuda::" in k}
+    top = sorted(ours.items(), key=lambda kv: -kv[1][1])
+    short = lambda k: k.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0]
+    shares = [{"kernel": short(k), "launches_per_step": v[0] / reps, "us_per_launch": v[1] / v[0],
+               "share_of_step": v[1] / tot} for k, v in top[:8]]
+    dom_name, dom = top[0]
+    roof = {"kernel": short(dom_name), "launches_per_step": dom[0] / reps, "launch_us": dom[1] / dom[0],
+            "share_of_step": dom[1] / tot, "device_busy_us_per_step": tot / reps,
+            "libpcuda_share_of_step": sum(v[1] for v in ours.values()) / tot}
+    for frag, (bound, work) in KERNEL_WORK.items():
+        if frag in dom_name:
+            wk = work(w)
+            sec = dom[1] / dom[0] * 1e-6
+            if bound == "tensor":
+                roof.update({"bound": "tensor", "achieved": wk / sec / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s"})
+            else:
+                roof.update({"bound": "hbm", "achieved": wk / sec / 1e9, "peak": pk["hbm"], "unit": "GB/s"})
+            roof["frac"] = roof["achieved"] / roof["peak"]
+            roof["algorithmic_work_per_launch"] = wk
+            break
+    else:
+        roof.update({"bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None})
+    roof["traffic"] = None
+    roof["peak_source"] = pk["source"]
+    roof["note"] = ("dominant libpcuda kernel of the graph-replayed step at this workload (CUPTI device durations, warm L2); "
+                    "at cfg2 sizes (2400 points per call) every kernel is latency-bound - `large` holds the roofline-sized shapes")
+    return shares, roof
+
+
+# ------------------------------------------------------------------------------------------------
 def time_op(fn, iters: int, flush):
     import torch
     for _ in range(3):
@@ -257,7 +321,33 @@ def large_shape_rooflines(flush, pk: dict):
     with torch.no_grad():
         t = time_op(lambda: net.feat(pts), 5, flush)
     fl = 2 * 278912 * 32 * 4096
-    res["d4_feat_fwd_B32_N4096"] = dict(ms=t, tflops=fl / t / 1e9, frac_tensor=fl / t / 1e9 / pk["tensor"])
+    res["d4_feat_fwd_B32_N4096"] = dict(ms=t, tflops=fl / t / 1e9, frac_tensor=fl / t / 1e9 / pk["tensor"],
+                                        note="whole op, eager launches (CPU-launch-bound); kernel-level figures follow")
+    # kernel-level: the tcgen05 GEMMs of that forward and of one backward, from CUPTI device durations
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        ptsg = torch.rand(32, 4096, 3, device=dev, requires_grad=True)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                o = net(ptsg.transpose(2, 1))[0]
+                o.sum().backward()
+            torch.cuda.synchronize()
+        agg = {}
+        for e in prof.events():
+            if e.device_type == torch.autograd.DeviceType.CUDA and "pcuda::" in e.name:
+                a = agg.setdefault(e.name, [0, 0.0]); a[0] += 1; a[1] += e.device_time
+        M = 32 * 4096
+        for frag, name, flops in (("ws_kernel<1>", "mlp_pool_gemm_128x1024_fwd", 2.0 * M * 128 * 1024),
+                                  ("ws_kernel<0>", "mlp_dense_gemm_64x128_fwd", 2.0 * M * 64 * 128),
+                                  ("ws_kernel<3>", "mlp_pool_dgrad_lowrank", 2.0 * M * 128 * 128),
+                                  ("ws_kernel<2>", "mlp_dgrad_128x64", 2.0 * M * 128 * 64)):
+            for k, v in agg.items():
+                if frag in k:
+                    us = v[1] / v[0]
+                    res[name + "_B32_N4096"] = dict(us=us, tflops=flops / us / 1e6, frac_tensor=flops / us / 1e6 / pk["tensor"],
+                                                    frac_tensor_sustained=(flops / us / 1e6 / pk["tensor_sustained"]) if pk.get("tensor_sustained") else None)
+    except Exception as e:
+        res["kernel_level_error"] = repr(e)
     return res
 
 
@@ -317,17 +407,44 @@ def run_ours(args):
     t_dev = sum(e0.elapsed_time(e1) for e0, e1 in ev) / 1e3
 
     # ---- end-to-end: pinned host -> device inputs, step, device -> host result, per step --------
+    # The way a training loop feeds the step: a copy stream uploads step i+1's inputs from pinned host
+    # memory into one of two staging sets while step i computes; the compute stream then moves the
+    # staged set into the step's static input buffers (device-to-device), runs the step and reads the
+    # 32-byte result back.  Timed as ONE interval over all K steps (every step's upload, staging move,
+    # compute and read-back lie inside it), L2 flushed before every step.
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = [{k: torch.empty_like(v) for k, v in step.inputs.items()} for _ in range(2)]
+    staged = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream(dev)
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])          # the staging set is free again
+            for k, dst in staging[i % 2].items():
+                dst.copy_(host[k], non_blocking=True)
+            staged[i % 2].record(copy_stream)
+
     barrier()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for e0, e1 in ev2:
+    for ev_ in consumed:
+        ev_.record(main)
+    e2e0, e2e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush.fill_(1.0)
+    e2e0.record()
+    upload(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            upload(i + 1)
+        main.wait_event(staged[i % 2])
+        for k, dst in step.inputs.items():
+            dst.copy_(staging[i % 2][k], non_blocking=True)
+        consumed[i % 2].record(main)
         flush.fill_(1.0)
-        e0.record()
-        step.load_inputs(host, non_blocking=True)
         r = step.run()
         result_host.copy_(r, non_blocking=True)
-        e1.record()
+    e2e1.record()
     barrier()
-    t_e2e = sum(e0.elapsed_time(e1) for e0, e1 in ev2) / 1e3
+    t_e2e = e2e0.elapsed_time(e2e1) / 1e3
     clocks = sampler.stop() if rank == 0 else None
     last = {k: float(v) for k, v in zip(RESULT_FIELDS, result_host.tolist())}
 
@@ -338,7 +455,12 @@ def run_ours(args):
 
     line = None
     if rank == 0:
-        breakdown, roof = op_breakdown(step, w, flush, pk)
+        breakdown, roof_ops = op_breakdown(step, w, flush, pk)
+        try:
+            kernel_shares, roof = kernel_profile(step, w, pk)
+            roof["op_level"] = roof_ops
+        except Exception as e:   # CUPTI unavailable: keep the op-level roofline
+            kernel_shares, roof = {"error": repr(e)}, roof_ops
         large = None
         if not args.skip_large:
             try:
@@ -360,14 +482,16 @@ def run_ours(args):
                                    f"{w['C']}x{w['H']}x{w['W']} logits, {w['N']}-pt clouds"
                        if args.workload == "cfg2" else args.workload,
                        "per_rank": w, "global_batch": w["B"] * world, "parallelism": f"dp{world} (batch-sharded, D4 grad all-reduce)",
-                       "l2": "flushed between steps (256 MiB write) outside the per-step CUDA-event intervals",
+                       "l2": "flushed before every step (256 MiB write): outside the per-step CUDA-event intervals of `value`, "
+                             "inside the single interval of `e2e`",
+                       "e2e_pipeline": "copy stream uploads step i+1 from pinned memory into a staging set while step i runs",
                        "cuda_graph": bool(use_graph), "mlp_precision": args.precision},
             "e2e": {"value": world * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": result_host.numel() * 4, "ms_per_step": t_e2e / args.steps * 1e3},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "samples_per_s": world * w["B"] * args.steps / t_dev,
-            "roofline": roof, "ops": breakdown, "large": large, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roof, "kernels": kernel_shares, "ops": breakdown, "large": large, "cpu_baseline": cpu, "clocks": clocks,
             "last_step": last,
         }
         print(json.dumps(line))

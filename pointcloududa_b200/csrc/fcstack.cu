@@ -57,30 +57,46 @@ __global__ void __launch_bounds__(kFcThreads) fc_fwd_kernel(const FcFwdParams p)
         c < p.cout ? __ldg(reinterpret_cast<const float4*>(p.W + static_cast<int64_t>(c) * p.cin) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  // one warp per row b: the row of x is read once for the kCPB channels
-  for (int b = warp; b < p.B; b += kFcThreads / 32) {
-    const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(b) * p.cin);
-    float acc[kCPB] = {0.f, 0.f, 0.f, 0.f};
+  // a warp takes two rows at a time (b, b + 8): each row of x is read once for the kCPB channels and
+  // 16 independent 128-bit loads are in flight per lane
+  for (int b = warp; b < p.B; b += 2 * (kFcThreads / 32)) {
+    const int b1 = b + kFcThreads / 32;
+    const bool two = b1 < p.B;
+    const float4* xr0 = reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(b) * p.cin);
+    const float4* xr1 = reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(two ? b1 : b) * p.cin);
+    float acc[2][kCPB] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll 8
     for (int k4 = lane; k4 < cin4; k4 += 32) {
-      const float4 xv = __ldg(xr + k4);
+      const float4 x0 = __ldg(xr0 + k4), x1 = __ldg(xr1 + k4);
 #pragma unroll
       for (int cc = 0; cc < kCPB; ++cc) {
         const float4 wv = reinterpret_cast<const float4*>(Wsm)[cc * cin4 + k4];
-        acc[cc] = fmaf(xv.x, wv.x, acc[cc]); acc[cc] = fmaf(xv.y, wv.y, acc[cc]);
-        acc[cc] = fmaf(xv.z, wv.z, acc[cc]); acc[cc] = fmaf(xv.w, wv.w, acc[cc]);
+        acc[0][cc] = fmaf(x0.x, wv.x, acc[0][cc]); acc[0][cc] = fmaf(x0.y, wv.y, acc[0][cc]);
+        acc[0][cc] = fmaf(x0.z, wv.z, acc[0][cc]); acc[0][cc] = fmaf(x0.w, wv.w, acc[0][cc]);
+        acc[1][cc] = fmaf(x1.x, wv.x, acc[1][cc]); acc[1][cc] = fmaf(x1.y, wv.y, acc[1][cc]);
+        acc[1][cc] = fmaf(x1.z, wv.z, acc[1][cc]); acc[1][cc] = fmaf(x1.w, wv.w, acc[1][cc]);
       }
     }
 #pragma unroll
-    for (int cc = 0; cc < kCPB; ++cc) acc[cc] = warp_sum(acc[cc]);
-    if (lane < kCPB) {
-      const int c = c0 + lane;
-      float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
-      if (c < p.cout) {
-        if (p.bias) v += p.bias[c];
-        if (p.mask) v *= p.mask[static_cast<int64_t>(b) * p.cout + c];
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int cc = 0; cc < kCPB; ++cc) acc[h][cc] = warp_sum(acc[h][cc]);
+    if (lane < 2 * kCPB) {
+      const int h = lane / kCPB, cc = lane % kCPB, c = c0 + cc;
+      const int bb = h == 0 ? b : b1;
+      float v = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int j = 0; j < kCPB; ++j)
+          if (hh == h && j == cc) v = acc[hh][j];
+      if (h == 0 || two) {
+        if (c < p.cout) {
+          if (p.bias) v += p.bias[c];
+          if (p.mask) v *= p.mask[static_cast<int64_t>(bb) * p.cout + c];
+        }
+        ys[bb * kCPB + cc] = v;
       }
-      ys[b * kCPB + lane] = v;
     }
   }
   __syncthreads();
@@ -164,26 +180,42 @@ __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p)
     }
   } else {
     const bool vec = (p.cout & 3) == 0;
-    for (int b = warp; b < p.B; b += kFcThreads / 32) {
-      const float* dn = p.dy_next + static_cast<int64_t>(b) * p.cout_next;
-      float acc[kCPB] = {0.f, 0.f, 0.f, 0.f};
+    for (int b = warp; b < p.B; b += 2 * (kFcThreads / 32)) {
+      const int b1 = b + kFcThreads / 32;
+      const bool two = b1 < p.B;
+      const float* dn0 = p.dy_next + static_cast<int64_t>(b) * p.cout_next;
+      const float* dn1 = p.dy_next + static_cast<int64_t>(two ? b1 : b) * p.cout_next;
+      float acc[2][kCPB] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll 8
       for (int o = lane; o < p.cout_next; o += 32) {
-        const float d = __ldg(dn + o);
+        const float d0 = __ldg(dn0 + o), d1 = __ldg(dn1 + o);
         const float* wr = p.W_next + static_cast<int64_t>(o) * p.cout + c0;
+        float wv[kCPB];
         if (vec) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(wr));
-          acc[0] = fmaf(d, wv.x, acc[0]); acc[1] = fmaf(d, wv.y, acc[1]);
-          acc[2] = fmaf(d, wv.z, acc[2]); acc[3] = fmaf(d, wv.w, acc[3]);
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr));
+          wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
         } else {
 #pragma unroll
-          for (int cc = 0; cc < kCPB; ++cc)
-            if (c0 + cc < p.cout) acc[cc] = fmaf(d, __ldg(wr + cc), acc[cc]);
+          for (int cc = 0; cc < kCPB; ++cc) wv[cc] = c0 + cc < p.cout ? __ldg(wr + cc) : 0.f;
         }
+#pragma unroll
+        for (int cc = 0; cc < kCPB; ++cc) { acc[0][cc] = fmaf(d0, wv[cc], acc[0][cc]); acc[1][cc] = fmaf(d1, wv[cc], acc[1][cc]); }
       }
 #pragma unroll
-      for (int cc = 0; cc < kCPB; ++cc) acc[cc] = warp_sum(acc[cc]);
-      if (lane < kCPB) dys[b * kCPB + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int cc = 0; cc < kCPB; ++cc) acc[h][cc] = warp_sum(acc[h][cc]);
+      if (lane < 2 * kCPB) {
+        const int h = lane / kCPB, cc = lane % kCPB;
+        float v = 0.f;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int j = 0; j < kCPB; ++j)
+            if (hh == h && j == cc) v = acc[hh][j];
+        if (h == 0) dys[b * kCPB + cc] = v;
+        else if (two) dys[b1 * kCPB + cc] = v;
+      }
     }
   }
   __syncthreads();
@@ -262,30 +294,30 @@ __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p)
 // segments of the rows of W); its 8 warps split the contraction index c and are combined in a fixed
 // order through shared memory; kRB batch rows per pass, their dy values staged as [c][row] so a warp
 // reads them as broadcast float4.
-constexpr int kRB = 16;
 constexpr int kPullThreads = 256;
+template <int RB>
 __global__ void __launch_bounds__(kPullThreads) fc_pull_kernel(const float* __restrict__ dy, const float* __restrict__ W,
                                                               int B, int cin, int cout, float* __restrict__ dx) {
-  extern __shared__ __align__(16) float sm[];   // dys[cout][kRB], reused as red[8][kRB][32]
+  extern __shared__ __align__(16) float sm[];   // dys[cout][RB], reused as red[8][RB][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
-  for (int b0 = 0; b0 < B; b0 += kRB) {
-    const int nb = min(kRB, B - b0);
+  for (int b0 = 0; b0 < B; b0 += RB) {
+    const int nb = min(RB, B - b0);
     __syncthreads();
-    for (int i = threadIdx.x; i < cout * kRB; i += kPullThreads) {
-      const int c = i / kRB, r = i - c * kRB;
-      sm[i] = r < nb ? dy[static_cast<int64_t>(b0 + r) * cout + c] : 0.f;
+    for (int i = threadIdx.x; i < cout * RB; i += kPullThreads) {   // coalesced global reads (c fastest), transposed store
+      const int r = i / cout, c = i - r * cout;
+      sm[c * RB + r] = r < nb ? dy[static_cast<int64_t>(b0 + r) * cout + c] : 0.f;
     }
     __syncthreads();
-    float acc[kRB];
+    float acc[RB];
 #pragma unroll
-    for (int r = 0; r < kRB; ++r) acc[r] = 0.f;
+    for (int r = 0; r < RB; ++r) acc[r] = 0.f;
 #pragma unroll 8
     for (int c = warp; c < cout; c += kPullThreads / 32) {
       const float wv = k < cin ? __ldg(W + static_cast<int64_t>(c) * cin + k) : 0.f;
-      const float4* d4 = reinterpret_cast<const float4*>(sm + c * kRB);
+      const float4* d4 = reinterpret_cast<const float4*>(sm + c * RB);
 #pragma unroll
-      for (int r4 = 0; r4 < kRB / 4; ++r4) {
+      for (int r4 = 0; r4 < RB / 4; ++r4) {
         const float4 d = d4[r4];
         acc[4 * r4 + 0] = fmaf(d.x, wv, acc[4 * r4 + 0]); acc[4 * r4 + 1] = fmaf(d.y, wv, acc[4 * r4 + 1]);
         acc[4 * r4 + 2] = fmaf(d.z, wv, acc[4 * r4 + 2]); acc[4 * r4 + 3] = fmaf(d.w, wv, acc[4 * r4 + 3]);
@@ -293,13 +325,13 @@ __global__ void __launch_bounds__(kPullThreads) fc_pull_kernel(const float* __re
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < kRB; ++r) sm[(warp * kRB + r) * 32 + lane] = acc[r];
+    for (int r = 0; r < RB; ++r) sm[(warp * RB + r) * 32 + lane] = acc[r];
     __syncthreads();
     for (int i = threadIdx.x; i < nb * 32; i += kPullThreads) {
       const int r = i >> 5, l = i & 31;
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < kPullThreads / 32; ++w) t += sm[(w * kRB + r) * 32 + l];
+      for (int w = 0; w < kPullThreads / 32; ++w) t += sm[(w * RB + r) * 32 + l];
       if (blockIdx.x * 32 + l < cin) dx[static_cast<int64_t>(b0 + r) * cin + blockIdx.x * 32 + l] = t;
     }
   }
@@ -393,10 +425,18 @@ extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_la
   }
   if (grad_x != nullptr) {
     const pcuda_fc_layer_t& y = layers[0];
-    const size_t need = static_cast<size_t>(kRB) * std::max(y.cout, (kPullThreads / 32) * 32);
-    const size_t smem = sizeof(float) * need;
-    PCUDA_REQUIRE(smem <= 48 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_bwd: first layer too wide for the input-gradient kernel");
-    fc_pull_kernel<<<(y.cin + 31) / 32, kPullThreads, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
+    // rows per pass: 32 when the batch has more than 16 rows (one pass over W for B <= 32)
+    const int rb = B > 16 ? 32 : 16;
+    const size_t smem = sizeof(float) * static_cast<size_t>(rb) * std::max(y.cout, (kPullThreads / 32) * 32);
+    PCUDA_REQUIRE(smem <= 96 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_bwd: first layer too wide for the input-gradient kernel");
+    static bool pull_attr_done = false;
+    if (!pull_attr_done) {
+      cudaFuncSetAttribute(fc_pull_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(fc_pull_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      pull_attr_done = true;
+    }
+    if (rb == 32) fc_pull_kernel<32><<<(y.cin + 31) / 32, kPullThreads, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
+    else fc_pull_kernel<16><<<(y.cin + 31) / 32, kPullThreads, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
     ++launches;
   }
   count_launch(launches);

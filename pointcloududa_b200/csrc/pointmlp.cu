@@ -175,6 +175,183 @@ mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
   }
 }
 
+// ---- narrow layers (cin <= 8: the 3->64 / 3->8 / 8->64 first layers) ------------------------------------
+// With a contraction of 3 the layer is a pure HBM stream (write y forward, read dy backward), so the
+// 64x64x16 tile kernels above waste a factor 5 in staging.  Here a thread owns 4 consecutive channels of
+// one point: x[m, 0..K) and its 4 x K weights sit in registers, y / dy move as coalesced float4.
+constexpr int kNarrowK = 8;
+constexpr int kNarrowThreads = 256;
+
+// all K <= 8 input channels of point m (one 64-bit division instead of one per channel)
+__device__ __forceinline__ void load_point(const ActSrc& s, int64_t m, float (&xv)[kNarrowK]) {
+  if (s.y != nullptr) {
+#pragma unroll
+    for (int k = 0; k < kNarrowK; ++k)
+      xv[k] = k < s.C ? bn_act(s.y[m * s.C + k], s.mean[k], s.invstd[k], s.gamma[k], s.beta[k], s.relu) : 0.f;
+  } else {
+    const int64_t b = m / s.N, n = m - b * s.N;
+    const float* px = s.x + b * s.sxb + n * s.sxn;
+#pragma unroll
+    for (int k = 0; k < kNarrowK; ++k) xv[k] = k < s.C ? __ldg(px + k * s.sxc) : 0.f;
+  }
+}
+
+// forward: y = W a + b, centred BN statistics; CTA 0 also publishes the pivot (y of point 0)
+__global__ void __launch_bounds__(kNarrowThreads)
+mlp_fwd_narrow_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias, int Cout, int64_t M,
+                      float* __restrict__ y_out, double* __restrict__ stats, float* __restrict__ pivot) {
+  __shared__ float red[kNarrowThreads / 16][2][64];   // up to 16 channel groups... sized below by cgroups <= 16... see launch
+  const int K = src.C;
+  const int cgroups = Cout >> 2;                       // <= 64 (Cout <= 256): thread = (point slot, channel group)
+  const int tpp = cgroups;                             // threads per point
+  const int pslots = kNarrowThreads / tpp;             // points per CTA pass
+  const int cg = threadIdx.x % tpp, ps = threadIdx.x / tpp;
+  const int c0 = cg * 4;
+  float w[4][kNarrowK], bj[4], pv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bj[j] = bias ? bias[c0 + j] : 0.f;
+#pragma unroll
+    for (int k = 0; k < kNarrowK; ++k) w[j][k] = k < K ? W[static_cast<int64_t>(c0 + j) * K + k] : 0.f;
+  }
+  {  // pivot = pre-BN output at global point 0 (same definition as bn_finalize_pivot_kernel)
+    float x0[kNarrowK];
+    load_point(src, 0, x0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < kNarrowK; ++k) d = fmaf(w[j][k], x0[k], d);
+      pv[j] = d + bj[j];
+    }
+    if (blockIdx.x == 0 && ps == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pivot[c0 + j] = pv[j];
+    }
+  }
+  float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ps < pslots) {
+    for (int64_t m = static_cast<int64_t>(blockIdx.x) * pslots + ps; m < M; m += static_cast<int64_t>(gridDim.x) * pslots) {
+      float xv[kNarrowK];
+      load_point(src, m, xv);
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float d = 0.f;
+#pragma unroll
+        for (int k = 0; k < kNarrowK; ++k) d = fmaf(w[j][k], xv[k], d);
+        v[j] = d + bj[j];
+        const float vc = v[j] - pv[j];
+        cs[j] += vc;
+        cq[j] = fmaf(vc, vc, cq[j]);
+      }
+      *reinterpret_cast<float4*>(y_out + m * Cout + c0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+  // fixed-order reduction over the point slots of the CTA, then one fp64 atomic per channel and CTA
+  float* rs = &red[0][0][0];            // [pslots][2][Cout] floats, pslots * Cout = 256 -> 2 KB
+  if (ps < pslots) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { rs[(ps * 2 + 0) * Cout + c0 + j] = cs[j]; rs[(ps * 2 + 1) * Cout + c0 + j] = cq[j]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cout; c += kNarrowThreads) {
+    double sd = 0.0, qd = 0.0;
+    for (int g = 0; g < pslots; ++g) { sd += static_cast<double>(rs[(g * 2 + 0) * Cout + c]); qd += static_cast<double>(rs[(g * 2 + 1) * Cout + c]); }
+    atomicAdd(&stats[c], sd);
+    atomicAdd(&stats[Cout + c], qd);
+  }
+}
+
+// weight gradient: partial[blockIdx.x][c][k] = sum over this CTA's points of dy[m,c] * a_prev[m,k]
+__global__ void __launch_bounds__(kNarrowThreads)
+wgrad_narrow_kernel(DySrc dys, ActSrc aprev, int64_t M, float* __restrict__ partial) {
+  extern __shared__ float red_w[];     // [pslots][C][K]
+  const int C = dys.C, K = aprev.C;
+  const int tpp = C >> 2, pslots = kNarrowThreads / tpp;
+  const int cg = threadIdx.x % tpp, ps = threadIdx.x / tpp;
+  const int c0 = cg * 4;
+  float acc[4][kNarrowK];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < kNarrowK; ++k) acc[j][k] = 0.f;
+  if (ps < pslots) {
+    for (int64_t m = static_cast<int64_t>(blockIdx.x) * pslots + ps; m < M; m += static_cast<int64_t>(gridDim.x) * pslots) {
+      const float4 d = load_dy4(dys, m, c0);
+      const float dv[4] = {d.x, d.y, d.z, d.w};
+      float xv[kNarrowK];
+      load_point(aprev, m, xv);
+#pragma unroll
+      for (int k = 0; k < kNarrowK; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j][k] = fmaf(dv[j], xv[k], acc[j][k]);
+    }
+  }
+  if (ps < pslots) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < kNarrowK; ++k)
+        if (k < K) red_w[(static_cast<int64_t>(ps) * C + c0 + j) * K + k] = acc[j][k];
+  }
+  __syncthreads();
+  float* outp = partial + static_cast<int64_t>(blockIdx.x) * C * K;
+  for (int i = threadIdx.x; i < C * K; i += kNarrowThreads) {
+    double t = 0.0;
+    for (int g = 0; g < pslots; ++g) t += static_cast<double>(red_w[static_cast<int64_t>(g) * C * K + i]);
+    outp[i] = static_cast<float>(t);
+  }
+}
+
+// gradient w.r.t. the network input: grad_x[b, k, n] = sum_c dy[m, c] W[c, k]   (K <= 8, C <= 128: the
+// tpp = C/4 <= 32 threads of a point sit in one warp and combine with shuffles)
+__global__ void __launch_bounds__(kNarrowThreads)
+dgrad_input_narrow_kernel(DySrc dys, const float* __restrict__ W, int K, int N, int64_t M, float* __restrict__ grad_x) {
+  const int C = dys.C;
+  const int tpp = C >> 2, pslots = kNarrowThreads / tpp;
+  const int cg = threadIdx.x % tpp, ps = threadIdx.x / tpp;
+  const int c0 = cg * 4;
+  float w[4][kNarrowK];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < kNarrowK; ++k) w[j][k] = k < K ? W[static_cast<int64_t>(c0 + j) * K + k] : 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * pslots;
+  const int64_t iters = (M + stride - 1) / stride;       // uniform trip count: the shuffles below need full warps
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t m = it * stride + static_cast<int64_t>(blockIdx.x) * pslots + ps;
+    const bool ok = m < M && ps < pslots;
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) d = load_dy4(dys, m, c0);
+    float g[kNarrowK];
+#pragma unroll
+    for (int k = 0; k < kNarrowK; ++k) g[k] = d.x * w[0][k] + d.y * w[1][k] + d.z * w[2][k] + d.w * w[3][k];
+    for (int o = tpp >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < kNarrowK; ++k) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
+    }
+    if (ok && cg == 0) {
+      const int64_t b = m / N, n = m - b * N;
+#pragma unroll
+      for (int k = 0; k < kNarrowK; ++k)
+        if (k < K) grad_x[(b * K + k) * N + n] = g[k];
+    }
+  }
+}
+
+bool narrow_ok(int cin, int cout) {
+  // threads per point = cout/4 must divide the CTA (a power of two <= 64)
+  const int tpp = cout >> 2;
+  return cin <= kNarrowK && (cout & 3) == 0 && tpp >= 1 && tpp <= 64 && (tpp & (tpp - 1)) == 0;
+}
+int narrow_grid(int64_t M, int cout) {
+  const int pslots = kNarrowThreads / (cout >> 2);
+  const int64_t want = (M + pslots - 1) / pslots;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+  return static_cast<int>(std::max<int64_t>(1, std::min(want, cap)));
+}
+
 // One block.  Phase 1 (if stats != nullptr): finalise BatchNorm of layer l-1 from its centred sums.
 // Phase 2 (if W_next != nullptr): pivot of layer l = its pre-BN output at global point 0, which
 // needs layer l-1's finalised parameters — hence the same kernel, separated by a block barrier.
@@ -976,8 +1153,11 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
     if (layer_tc(l))
       if (int rc = tc::pack_w(layers[l].weight, layers[l].cout, layers[l].cin, false, w.wpack[l], st,
                               (pool && l == L - 1) ? layers[l].gamma : nullptr)) return rc;
-  if (!layer_tc(0)) {
-    // pivot of layer 0 (no BN to finalise yet)
+  auto layer_narrow = [&](int l) {
+    return !layer_tc(l) && !(pool && l == L - 1) && layers[l].y != nullptr && narrow_ok(layers[l].cin, layers[l].cout);
+  };
+  if (!layer_tc(0) && !layer_narrow(0)) {
+    // pivot of layer 0 (no BN to finalise yet; the narrow-layer kernel publishes its own pivot)
     bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, 0, 1.0, eps, momentum, train, nullptr, nullptr, nullptr, nullptr,
                                                  input_src(x, sxb, sxc, sxn, N, layers[0].cin), layers[0].weight, layers[0].bias,
                                                  layers[0].cout, piv_l);
@@ -994,6 +1174,9 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
       if (int rc = tc::pack_act(src, tl, w.apack[l], st)) return rc;
       if (int rc = tc::fwd_layer(tl, w.apack[l], w.wpack[l], y, is_pool, st_l, w.keys, st)) return rc;
       pivot_used = y.bias ? y.bias : w.zeros;
+    } else if (layer_narrow(l)) {
+      mlp_fwd_narrow_kernel<<<narrow_grid(s.M, y.cout), kNarrowThreads, 0, st>>>(src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
+      launches += 1;
     } else {
       const dim3 grid(B * tps, (y.cout + TN - 1) / TN);
       if (is_pool)
@@ -1003,7 +1186,7 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
       launches += 1;
     }
     // finalise this layer's BN; if an FP32 layer follows, compute its pivot in the same launch
-    const bool next_piv = l + 1 < L && !layer_tc(l + 1);
+    const bool next_piv = l + 1 < L && !layer_tc(l + 1) && !layer_narrow(l + 1);
     bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(st_l, pivot_used, y.cout, static_cast<double>(s.M), eps, momentum, train,
                                                  y.save_mean, y.save_invstd, y.running_mean, y.running_var,
                                                  next_piv ? layer_src(y, N) : ActSrc{}, next_piv ? layers[l + 1].weight : nullptr,
@@ -1170,6 +1353,11 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
       if (wgrad_tc) {
         Sw = tc::pt_splits(tl, (C + 127) / 128);
         if (int rc = tc::wgrad_layer(tl, w.dypack, C, apack[l], Kp, Sw, partial, st)) return rc;
+      } else if (narrow_ok(Kp, C)) {
+        Sw = std::min(narrow_grid(s.M, C), s.S);
+        const size_t smem = sizeof(float) * 1024 * static_cast<size_t>(Kp);   // [pslots][C][Kp], pslots * C = 1024
+        wgrad_narrow_kernel<<<Sw, kNarrowThreads, smem, st>>>(dys, src_of(l - 1), s.M, partial);
+        launches += 1;
       } else {
         point_contract_kernel<0><<<dim3(S32, (C + TM - 1) / TM, (Kp + TN - 1) / TN), kThreads, 0, st>>>(dys, ActSrc{}, src_of(l - 1), s.M, chunk32, C, Kp, partial);
         launches += 1;
@@ -1184,6 +1372,9 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
         if (int rc = tc::pack_w(y.weight, Kp, C, true, w.wtpack, st)) return rc;
         const uint8_t* side = dgrad_side ? apack[l] : nullptr;
         if (int rc = tc::dgrad_layer(tl, w.dypack, C, w.wtpack, side, o, st)) return rc;
+      } else if (o.grad_x != nullptr && narrow_ok(Kp, C) && C <= 128) {
+        dgrad_input_narrow_kernel<<<narrow_grid(s.M, C), kNarrowThreads, 0, st>>>(dys, y.weight, Kp, N, s.M, o.grad_x);
+        launches += 1;
       } else {
         dense_dgrad_kernel<<<dim3(B * tps, (Kp + TN - 1) / TN), kThreads, 0, st>>>(dys, y.weight, N, tps, o);
         launches += 1;

@@ -224,12 +224,14 @@ struct WsParams {
   const int* head;          // POOL_DGRAD: [B*N] lowest channel whose arg-max is this point, or -1
   const float* srows;       // POOL_DGRAD: [B, Cpool, K] row at (b, head) = sum over the channels selecting that point
   int Cpool;
+  int dbg;                  // timing experiments only (pcuda_tune key 4): 1 = TMEM loads without the epilogue math, 2 = no TMEM loads
 };
 
 struct __align__(8) WsBarriers {
   uint64_t full[8], empty[8], acc_full[2], acc_empty[2], a_full, side_full, side_empty;
   uint32_t tmem_base;
   uint32_t pad;
+  long long dbg[5];        // timing experiment (pcuda_tune key 4, bit 3)
 };
 
 __device__ __forceinline__ float bf16_at(const uint8_t* slab, int row, int ch) {
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsPa
   constexpr int kEpiWarps = WsCfg<MODE>::kEpiWarps, kSub = WsCfg<MODE>::kSub;
   constexpr int kMmaWarp = WsCfg<MODE>::kMmaWarp, kProdWarp = WsCfg<MODE>::kProdWarp;
   extern __shared__ uint8_t smem_raw[];
+  const long long dbg_kstart = clock64();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int KS = p.K >> 6;
   uint8_t* a_smem = smem;                                       // CB * KS slabs of 16 KB
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsPa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  const long long dbg_setup = clock64();
 
   if (warp == kProdWarp) {
     // ================================ producer (one lane) =========================================
@@ -283,11 +287,11 @@ __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsPa
       const uint8_t* a_src = p.A + static_cast<int64_t>(row_base / 128) * KS * kSlabA;
       for (uint32_t off = 0; off < a_bytes; off += kSlabA)
         bulk_g2s(smem_u32(a_smem + off), a_src + off, kSlabA, smem_u32(&bars->a_full));
-      uint32_t it = 0, tc = 0;
+      uint32_t tc = 0, stage = 0, ph = 0;
       for (int t = t_begin; t < t_end; ++t, ++tc) {
-        for (int s = 0; s < KS; ++s, ++it) {
-          const uint32_t stage = it % p.nstage, ph = (it / p.nstage) & 1u;
+        for (int s = 0; s < KS; ++s, stage = (stage + 1 == static_cast<uint32_t>(p.nstage)) ? 0u : stage + 1, ph ^= (stage == 0u)) {
           mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1u);
+          if ((p.dbg & 3) == 3) { mbar_arrive(smem_u32(&bars->full[stage])); continue; }   // timing experiment: no operand traffic
           mbar_arrive_expect_tx(smem_u32(&bars->full[stage]), kSlabB);
           bulk_g2s(smem_u32(b_smem + stage * kSlabB), p.Bop + (static_cast<int64_t>(t) * KS + s) * kSlabB, kSlabB,
                    smem_u32(&bars->full[stage]));
@@ -303,36 +307,54 @@ __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsPa
     }
   } else if (warp == kMmaWarp) {
     // ================================ MMA issuer ==================================================
+    // The loop below is the critical path of the kernel: one thread feeds the tensor core, and at
+    // K = 128 an accumulator is only 8 MMAs (~1000 cycles of tensor work), so every instruction between
+    // two issues counts.  Ring position and descriptors advance incrementally (no division, the 64-bit
+    // descriptors differ only in their 14-bit address field).
     const uint32_t idesc = make_idesc(128, kNT, MODE == DGRAD ? 1 : 0, 0);
     mbar_wait(smem_u32(&bars->a_full), 0);
     tc_fence_after();
-    uint32_t it = 0, ac = 0;
-    for (int t = t_begin; t < t_end; ++t, it += KS) {
+    const bool leader = elect_one();
+    const uint64_t bdesc0 = make_sdesc(smem_u32(b_smem), 16, 1024);
+    const uint64_t adesc0 = MODE == DGRAD ? make_sdesc(smem_u32(a_smem), p.K * 128, 1024) : make_sdesc(smem_u32(a_smem), 16, 1024);
+    const uint32_t a_kk = MODE == DGRAD ? (16u * 128u) >> 4 : 32u >> 4;        // descriptor step per 16-wide k block
+    const uint32_t a_s = MODE == DGRAD ? (64u * 128u) >> 4 : static_cast<uint32_t>(kSlabA) >> 4;   // ... per 64-wide slab
+    const uint32_t a_cbs = static_cast<uint32_t>(KS * kSlabA) >> 4;            // ... per row block
+    const uint32_t nst = static_cast<uint32_t>(p.nstage);
+    uint32_t ac = 0, stage0 = 0, ph0 = 0;    // ring position of the first slab of the current tile
+    long long dbg_acc = 0, dbg_full = 0;     // timing experiment (pcuda_tune key 4, bit 3)
+    const long long dbg_t0 = clock64();
+
+    for (int t = t_begin; t < t_end; ++t) {
       for (int cb = 0; cb < p.CB; ++cb, ++ac) {
         const uint32_t slot = ac & 1u, aph = (ac >> 1) & 1u;
+        const long long c0 = (p.dbg & 8) ? clock64() : 0;
         mbar_wait(smem_u32(&bars->acc_empty[slot]), aph ^ 1u);
         tc_fence_after();
-        const uint32_t a_cb = smem_u32(a_smem + cb * KS * kSlabA);
+        if (p.dbg & 8) dbg_acc += clock64() - c0;
+        uint32_t stage = stage0, ph = ph0;
         for (int s = 0; s < KS; ++s) {
-          const uint32_t seq = it + s, stage = seq % p.nstage, ph = (seq / p.nstage) & 1u;
+          const long long c1 = (p.dbg & 8) ? clock64() : 0;
           mbar_wait(smem_u32(&bars->full[stage]), ph);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t b_addr = smem_u32(b_smem + stage * kSlabB);
+          if (p.dbg & 8) dbg_full += clock64() - c1;
+          if (leader) {
+            const uint64_t bd = bdesc0 + stage * (static_cast<uint32_t>(kSlabB) >> 4);
+            const uint64_t ad = adesc0 + cb * a_cbs + s * a_s;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              uint64_t adesc;
-              const uint64_t bdesc = make_sdesc(b_addr + kk * 32, 16, 1024);
-              if (MODE == DGRAD) adesc = make_sdesc(a_cb + (s * 64 + kk * 16) * 128, p.K * 128, 1024);
-              else adesc = make_sdesc(a_cb + s * kSlabA + kk * 32, 16, 1024);
-              umma_bf16(tmem + slot * kNT, adesc, bdesc, idesc, (s | kk) != 0);
-            }
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(tmem + slot * kNT, ad + kk * a_kk, bd + kk * 2, idesc, (s | kk) != 0);
             if (cb == p.CB - 1) umma_commit(smem_u32(&bars->empty[stage]));   // slab consumed by every row block
             if (s == KS - 1) umma_commit(smem_u32(&bars->acc_full[slot]));
           }
           __syncwarp();
+          if (++stage == nst) { stage = 0; ph ^= 1u; }
         }
+        if (cb == p.CB - 1) { stage0 = stage; ph0 = ph; }
       }
+    }
+    if ((p.dbg & 8) && leader) {
+      bars->dbg[0] = dbg_t0 - dbg_kstart; bars->dbg[1] = clock64() - dbg_kstart; bars->dbg[2] = dbg_acc; bars->dbg[3] = dbg_full; bars->dbg[4] = ac;
     }
   } else {
     // ================================ epilogue (kEpiWarps warps) ==================================
@@ -402,7 +424,9 @@ __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsPa
         tc_fence_after();
         for (int ch = half; ch * 32 < nvalid; ch += kSub) {
           float v[32];
+          if ((p.dbg & 3) >= 2) continue;
           tmem_ld32(tmem + lane_addr + slot * kNT + ch * 32, v);
+          if ((p.dbg & 3) == 1) { sa[0] += v[0] + v[31]; continue; }
           const int ncol = min(32, nvalid - ch * 32);
           // FULL chunks (all but the last of a cloud) run without per-column predicates: straight-line
           // code with 4 independent dependency chains per reduction
@@ -557,6 +581,11 @@ __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsPa
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
+  if ((p.dbg & 8) && threadIdx.x == 0 && (blockIdx.x < 2 || blockIdx.x + 1 == gridDim.x)) {
+    const long long dbg_end = clock64() - dbg_kstart;
+    printf("ws_kernel<%d> cta %d: setup %lld | issue loop %lld .. %lld (%lld accumulators; waiting acc_empty %lld, full %lld) | end %lld clk\n",
+           MODE, static_cast<int>(blockIdx.x), dbg_setup - dbg_kstart, bars->dbg[0], bars->dbg[1], bars->dbg[4], bars->dbg[2], bars->dbg[3], dbg_end);
+  }
 }
 
 // ================================= point-contraction GEMM ==========================================
@@ -609,8 +638,8 @@ __global__ void __launch_bounds__(kPtThreads, 1) pt_kernel(const PtParams p) {
 
   if (warp == 5) {
     if (lane == 0) {
-      for (int i = 0; i < n_steps; ++i) {
-        const uint32_t stage = i % p.nstage, ph = (i / p.nstage) & 1u;
+      uint32_t stage = 0, ph = 0;
+      for (int i = 0; i < n_steps; ++i, stage = (stage + 1 == static_cast<uint32_t>(p.nstage)) ? 0u : stage + 1, ph ^= (stage == 0u)) {
         const int t = t_begin + i;
         mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1u);
         mbar_arrive_expect_tx(smem_u32(&bars->full[stage]), static_cast<uint32_t>((GP + GR) * kSlabB));
@@ -625,24 +654,24 @@ __global__ void __launch_bounds__(kPtThreads, 1) pt_kernel(const PtParams p) {
     }
   } else if (warp == 4) {
     const uint32_t idesc = make_idesc(128, p.Kr, 1, 1);
+    const bool leader = elect_one();
+    const uint64_t desc0 = make_sdesc(smem_u32(smem), kSlabB, 1024);
+    const uint32_t pa_off = static_cast<uint32_t>(p.gram ? (cblk * 2) * kSlabB : 0) >> 4;   // GRAM: the lanes are R's channel groups 2*cblk, 2*cblk+1
+    const uint32_t ra_off = static_cast<uint32_t>(p_off * kSlabB) >> 4;
+    uint32_t stage = 0, ph = 0;
     for (int i = 0; i < n_steps; ++i) {
-      const uint32_t stage = i % p.nstage, ph = (i / p.nstage) & 1u;
       mbar_wait(smem_u32(&bars->full[stage]), ph);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sb = smem_u32(smem + stage * stage_stride);
-        const uint32_t pa = p.gram ? sb + (cblk * 2) * kSlabB : sb;   // GRAM: the lanes are R's channel groups 2*cblk, 2*cblk+1
-        const uint32_t ra = sb + p_off * kSlabB;
+      if (leader) {
+        const uint64_t sd = desc0 + stage * (static_cast<uint32_t>(stage_stride) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < kNT / 16; ++kk) {
-          const uint64_t adesc = make_sdesc(pa + kk * 2048, kSlabB, 1024);
-          const uint64_t bdesc = make_sdesc(ra + kk * 2048, kSlabB, 1024);
-          umma_bf16(tmem, adesc, bdesc, idesc, (i | kk) != 0);
-        }
+        for (int kk = 0; kk < kNT / 16; ++kk)
+          umma_bf16(tmem, sd + pa_off + kk * (2048u >> 4), sd + ra_off + kk * (2048u >> 4), idesc, (i | kk) != 0);
         umma_commit(smem_u32(&bars->empty[stage]));
         if (i == n_steps - 1) umma_commit(smem_u32(&bars->done));
       }
       __syncwarp();
+      if (++stage == static_cast<uint32_t>(p.nstage)) { stage = 0; ph ^= 1u; }
     }
   } else {
     // final epilogue: lane quarter = warp % 4, write this split's partial
@@ -710,6 +739,7 @@ int launch_ws(WsParams& p, cudaStream_t st, const char* what) {
   const WsPlan pl = plan_ws(MODE, p.R, p.K, p.tl.n_tiles, p.side_slabs);
   if (!pl.ok) return fail(PCUDA_E_UNSUPPORTED, "%s: K=%d R=%d does not fit the tensor-core kernel", what, p.K, p.R);
   p.CB = pl.CB; p.G = pl.G; p.nstage = pl.nstage;
+  p.dbg = tuning(TUNE_MLP_EPI_DEBUG);
   static bool attr_done[4] = {false, false, false, false};
   if (!attr_done[MODE]) {
     cudaError_t e = cudaFuncSetAttribute(ws_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);

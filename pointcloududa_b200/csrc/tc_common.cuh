@@ -28,11 +28,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Spin on the phase with the given parity.  A wait that lasts longer than ~2 s of SM clocks traps
-// (the launch then fails with an error instead of hanging the device).
+// Spin on the phase with the given parity.  try_wait suspends the thread in hardware for a bounded time
+// per attempt, so the loop body is kept to a poll, a counter and a branch (the single MMA-issuing /
+// producer threads execute it on their critical path).  ~2^26 failed attempts (seconds) trap, so a
+// protocol bug fails the launch instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
+  uint32_t done = 0, spins = 0;
   for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -42,10 +43,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    const long long now = clock64();
-    if (t0 == 0) t0 = now;
-    else if (now - t0 > 4000000000ll) __trap();
+    if (++spins > (1u << 26)) __trap();
   }
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 // arm the barrier with one arrival of this thread plus `bytes` of expected bulk-copy traffic
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
