@@ -42,7 +42,7 @@ def peaks():
         with open(p) as f:
             d = json.load(f)
         return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained"),
-                    source="measured (MEASURED_PEAKS.json)")
+                    sm_max_mhz=d.get("sm_max_mhz", 1965.0), source="measured (MEASURED_PEAKS.json)")
     return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
@@ -300,21 +300,30 @@ def large_shape_rooflines(flush, pk: dict):
     from pointcloududa_b200.utils.loss import entropy_map
     dev = flush.device
     res = {}
-    z = torch.randn(32, 5, 256, 256, device=dev) * 3
+    # cfg-5 full batch (BASELINE configs[4]): 335 MB per tensor, well beyond the 126 MB L2
+    z = torch.randn(256, 5, 256, 256, device=dev) * 3
     g = torch.randn_like(z)
     nb = z.numel() * 4
     t = time_op(lambda: entropy_map(z, "softmax", True), 10, flush)
-    res["entropy_fwd_B32_C5_256x256"] = dict(ms=t, gbs=2 * nb / t / 1e6, frac_hbm=2 * nb / t / 1e6 / pk["hbm"])
-    zr = z.clone().requires_grad_(True)
+    res["entropy_fwd_B256_C5_256x256"] = dict(ms=t, gbs=2 * nb / t / 1e6, frac_hbm=2 * nb / t / 1e6 / pk["hbm"])
+    zr = z.detach().requires_grad_(True)
     mm = entropy_map(zr, "softmax", True)
     t = time_op(lambda: torch.autograd.grad(mm, zr, g, retain_graph=True), 10, flush)
-    res["entropy_bwd_B32_C5_256x256"] = dict(ms=t, gbs=3 * nb / t / 1e6, frac_hbm=3 * nb / t / 1e6 / pk["hbm"])
+    res["entropy_bwd_B256_C5_256x256"] = dict(ms=t, gbs=3 * nb / t / 1e6, frac_hbm=3 * nb / t / 1e6 / pk["hbm"])
     del z, g, zr, mm
+    torch.cuda.empty_cache()
     for B, N in ((64, 4096), (64, 16384)):
         x, y = synth_clouds(B, N, seed=5, mode="near")
         x, y = x.to(dev), y.to(dev)
         t = time_op(lambda: ops.chamfer_nn(x, y), 5, flush)
-        res[f"chamfer_fwd_B{B}_N{N}"] = dict(ms=t, tpairs_s=2.0 * B * N * N / t / 1e9)
+        # not HBM-bound by construction (24 B per point in + out): the binding resource is the FP32 pipe.
+        # 5 IEEE operations per ordered pair (mul, 2 fma, add, fma), issued two pairs per packed instruction;
+        # peak = SMs x 128 lanes x max SM clock
+        pairs = 2.0 * B * N * N
+        lane_peak = ops.sm_count() * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6
+        res[f"chamfer_fwd_B{B}_N{N}"] = dict(ms=t, tpairs_s=pairs / t / 1e9, hbm_gbs=48.0 * B * N / t / 1e6,
+                                             fp32_lane_ops_per_s=5.0 * pairs / (t * 1e-3),
+                                             frac_fp32_lanes=5.0 * pairs / (t * 1e-3) / lane_peak)
     from pointcloududa_b200.networks.PointNetCls import PointNetCls
     net = PointNetCls().to(dev).train()
     pts = torch.rand(32, 4096, 3, device=dev).transpose(2, 1)

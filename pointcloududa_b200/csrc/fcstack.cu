@@ -294,11 +294,10 @@ __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p)
 // segments of the rows of W); its 8 warps split the contraction index c and are combined in a fixed
 // order through shared memory; kRB batch rows per pass, their dy values staged as [c][row] so a warp
 // reads them as broadcast float4.
-constexpr int kPullThreads = 256;
-template <int RB>
+template <int RB, int kPullThreads>
 __global__ void __launch_bounds__(kPullThreads) fc_pull_kernel(const float* __restrict__ dy, const float* __restrict__ W,
                                                               int B, int cin, int cout, float* __restrict__ dx) {
-  extern __shared__ __align__(16) float sm[];   // dys[cout][RB], reused as red[8][RB][32]
+  extern __shared__ __align__(16) float sm[];   // dys[cout][RB], reused as red[warps][RB][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
   for (int b0 = 0; b0 < B; b0 += RB) {
@@ -425,18 +424,20 @@ extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_la
   }
   if (grad_x != nullptr) {
     const pcuda_fc_layer_t& y = layers[0];
-    // rows per pass: 32 when the batch has more than 16 rows (one pass over W for B <= 32)
+    // rows per pass: 32 when the batch has more than 16 rows (one pass over W for B <= 32); the contraction
+    // index is split over 32 (16) warps so that a warp walks only cout/32 (cout/16) rows of W
     const int rb = B > 16 ? 32 : 16;
-    const size_t smem = sizeof(float) * static_cast<size_t>(rb) * std::max(y.cout, (kPullThreads / 32) * 32);
-    PCUDA_REQUIRE(smem <= 96 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_bwd: first layer too wide for the input-gradient kernel");
+    const int threads = rb == 32 ? 512 : 1024;
+    const size_t smem = sizeof(float) * static_cast<size_t>(rb) * std::max(y.cout, threads);
+    PCUDA_REQUIRE(smem <= 160 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_bwd: first layer too wide for the input-gradient kernel");
     static bool pull_attr_done = false;
     if (!pull_attr_done) {
-      cudaFuncSetAttribute(fc_pull_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      cudaFuncSetAttribute(fc_pull_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(fc_pull_kernel<32, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      cudaFuncSetAttribute(fc_pull_kernel<16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
       pull_attr_done = true;
     }
-    if (rb == 32) fc_pull_kernel<32><<<(y.cin + 31) / 32, kPullThreads, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
-    else fc_pull_kernel<16><<<(y.cin + 31) / 32, kPullThreads, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
+    if (rb == 32) fc_pull_kernel<32, 512><<<(y.cin + 31) / 32, 512, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
+    else fc_pull_kernel<16, 1024><<<(y.cin + 31) / 32, 1024, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
     ++launches;
   }
   count_launch(launches);

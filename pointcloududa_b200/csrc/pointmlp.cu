@@ -675,14 +675,20 @@ pool_u_kernel(const float* __restrict__ W, const float* __restrict__ alpha, cons
   }
 }
 
-// Sparse part of the pooled layer's dgrad, aggregated per selected point:
-//   srows[b, h, :] = sum_{c : arg[b,c] == n, coef != 0} coef[b,c] * W[c, :]     (ascending c: deterministic)
-//   head[b*N + n]  = h = the lowest such channel          (head must be pre-filled with -1)
-// grid (B, parts), 1024 threads; dynamic smem: C + N ints.  A warp owns a head channel, finds the other
-// channels selecting the same point with ballots over the shared-memory copy of arg, and sums their rows.
+// Sparse part of the pooled layer's dgrad, applied AFTER the dense low-rank GEMM (tc::pool_dgrad wrote
+// dz_prev = mask * (-u - a Q) and its column sums):
+//   S[m, :] = sum_{c : arg[b,c] == n, coef != 0} coef[b,c] * W[c, :]            (ascending c: deterministic)
+//   dz_prev[m, :] += mask(m, :) * S[m, :]     and the dbeta / dgamma sums of the previous layer likewise
+// (or grad_x[b, :, n] += S[m, :] when the previous "layer" is the network input).
+// Only <= C points per cloud are touched, so this is a few MB of traffic next to the GEMM's epilogue,
+// which no longer gathers anything.  grid (B, parts), 512 threads; dynamic smem: max(C + N ints,
+// 2 * 16 * K floats).  A warp owns a head channel (the lowest channel selecting a point — one writer per
+// point, no atomics on dz_prev), finds the other channels selecting the same point with ballots over
+// the shared-memory copy of arg, and sums their rows.
+template <int KPL>   // output columns per lane: 4 (K <= 128) or 16 (K <= 512)
 __global__ void __launch_bounds__(512)
 pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ coef, const float* __restrict__ W,
-                   int C, int N, int K, int* __restrict__ head, float* __restrict__ srows) {
+                   int C, int N, int K, DgradOut o) {
   extern __shared__ int sm_i[];
   int* sarg = sm_i;
   int* first = sm_i + C;
@@ -695,15 +701,17 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
   for (int c = threadIdx.x; c < C; c += blockDim.x)
     if (sarg[c] >= 0) atomicMin(&first[sarg[c]], c);
   __syncthreads();
-  const int KPL = (K + 31) >> 5;               // output columns per lane (<= 16)
+  const bool to_x = o.grad_x != nullptr;
+  float ws[KPL], wq[KPL];                        // this warp's share of the previous layer's dbeta / dgamma sums
+#pragma unroll
+  for (int jj = 0; jj < KPL; ++jj) { ws[jj] = 0.f; wq[jj] = 0.f; }
   const int stride = nwarp * gridDim.y;
   for (int c = blockIdx.y * nwarp + warp; c < C; c += stride) {
     const int a = sarg[c];
     if (a < 0 || first[a] != c) continue;      // warp-uniform
-    if (lane == 0) head[static_cast<int64_t>(b) * N + a] = c;
-    float acc[16];
+    float acc[KPL];
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.f;
+    for (int jj = 0; jj < KPL; ++jj) acc[jj] = 0.f;
     for (int c0 = c & ~31; c0 < C; c0 += 32) {
       const int cc = c0 + lane;
       unsigned mask = __ballot_sync(0xffffffffu, cc >= c && cc < C && sarg[cc] == a);
@@ -716,33 +724,73 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
           mask &= mask - 1;
         }
         if (KPL <= 4) {
-          float cf[4], wv[4][4];
+          // all loads of the (up to) 4 channels are issued before the first use
+          float cf[4], wv[4][KPL];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             cf[u] = cs[u] >= 0 ? coef[static_cast<int64_t>(b) * C + cs[u]] : 0.f;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
+            for (int jj = 0; jj < KPL; ++jj)
               wv[u][jj] = (cs[u] >= 0 && lane + 32 * jj < K) ? W[static_cast<int64_t>(cs[u]) * K + lane + 32 * jj] : 0.f;
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[jj] = fmaf(cf[u], wv[u][jj], acc[jj]);
+            for (int jj = 0; jj < KPL; ++jj) acc[jj] = fmaf(cf[u], wv[u][jj], acc[jj]);
         } else {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (cs[u] < 0) continue;
+            if (cs[u] < 0) continue;               // warp-uniform
             const float cf = coef[static_cast<int64_t>(b) * C + cs[u]];
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj)
+            for (int jj = 0; jj < KPL; ++jj)
               if (lane + 32 * jj < K) acc[jj] = fmaf(cf, W[static_cast<int64_t>(cs[u]) * K + lane + 32 * jj], acc[jj]);
           }
         }
       }
     }
+    const int64_t m = static_cast<int64_t>(b) * N + a;
+    if (to_x) {
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj)
-      if (lane + 32 * jj < K) srows[(static_cast<int64_t>(b) * C + c) * K + lane + 32 * jj] = acc[jj];
+      for (int jj = 0; jj < KPL; ++jj) {
+        const int k = lane + 32 * jj;
+        if (k < K) o.grad_x[(static_cast<int64_t>(b) * K + k) * N + a] += acc[jj];
+      }
+    } else {
+      float yv[KPL], dv[KPL];
+#pragma unroll
+      for (int jj = 0; jj < KPL; ++jj) {
+        const int k = lane + 32 * jj;
+        yv[jj] = k < K ? o.y_prev[m * K + k] : 0.f;
+        dv[jj] = k < K ? o.dz_prev[m * K + k] : 0.f;
+      }
+#pragma unroll
+      for (int jj = 0; jj < KPL; ++jj) {
+        const int k = lane + 32 * jj;
+        if (k >= K) continue;
+        const float yh = (yv[jj] - o.mean[k]) * o.invstd[k];
+        const bool on = !o.relu || fmaf(yh, o.gamma[k], o.beta[k]) > 0.f;
+        const float v = on ? acc[jj] : 0.f;
+        o.dz_prev[m * K + k] = dv[jj] + v;
+        ws[jj] += v;
+        wq[jj] = fmaf(v, yh, wq[jj]);
+      }
+    }
+  }
+  if (to_x) return;
+  // fixed-order combination of the warps' sums, one fp64 atomic per channel and CTA
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(sm_i);            // [2][nwarp][K]
+#pragma unroll
+  for (int jj = 0; jj < KPL; ++jj) {
+    const int k = lane + 32 * jj;
+    if (k < K) { red[warp * K + k] = ws[jj]; red[(nwarp + warp) * K + k] = wq[jj]; }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double sd = 0.0, qd = 0.0;
+    for (int w = 0; w < nwarp; ++w) { sd += static_cast<double>(red[w * K + k]); qd += static_cast<double>(red[(nwarp + w) * K + k]); }
+    if (sd != 0.0 || qd != 0.0) { atomicAdd(&o.sums[k], sd); atomicAdd(&o.sums[K + k], qd); }
   }
 }
 
@@ -1026,9 +1074,8 @@ FwdWs carve_fwd(const Shape& s, const pcuda_mlp_layer_t* layers, void* base) {
 
 struct BwdWs {
   double* sums; float* alpha; float* kappa; float* partial;
-  float *coef, *gsel, *gyh, *Ghat, *Q, *abar, *u, *srows;
+  float *coef, *gsel, *gyh, *Ghat, *Q, *abar, *u;
   double *colsum, *G, *abar_d;
-  int* head;
   float* dzbuf[2];
   uint8_t* apack[17];   // apack[l + 1] = packed activation a_l; index 0 = the raw network input
   uint8_t* dypack; uint8_t* wtpack; uint8_t* qpack;
@@ -1055,8 +1102,6 @@ BwdWs carve_bwd(const Shape& s, const pcuda_mlp_layer_t* layers, void* base) {
     w.abar = cv.take<float>(K);
     w.u = cv.take<float>(K);
     w.abar_d = cv.take<double>(K);
-    w.head = cv.take<int>(static_cast<size_t>(s.M));
-    w.srows = cv.take<float>(static_cast<size_t>(s.B) * s.Clast * K);
     if (tc::supports(static_cast<int>(K))) w.qpack = cv.take<uint8_t>(tc::w_pack_bytes(static_cast<int>(K), static_cast<int>(K)));
   }
   w.dzbuf[0] = cv.take<float>(static_cast<size_t>(s.M) * s.maxC);
@@ -1302,19 +1347,23 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     }
     if (L >= 2 || grad_x) {
       const DgradOut o = dgrad_out(L - 2, dzbuf[cur]);
-      const size_t sparse_smem = sizeof(int) * (static_cast<size_t>(C) + N);
+      const size_t sparse_smem = std::max(sizeof(int) * (static_cast<size_t>(C) + N), sizeof(float) * 2 * 16 * static_cast<size_t>(K));
       if (tc_on(precision, TC_POOL_DGRAD) && a_in && w.qpack && tc::pool_dgrad_fits(K) && sparse_smem <= 200 * 1024 && K <= 512) {
         static bool attr_done = false;
         if (!attr_done) {
-          cudaFuncSetAttribute(pool_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cudaFuncSetAttribute(pool_sparse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cudaFuncSetAttribute(pool_sparse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
           attr_done = true;
         }
-        cudaMemsetAsync(w.head, 0xFF, sizeof(int) * static_cast<size_t>(s.M), st);
-        const int parts = std::max(1, std::min(16, 4 * sm_count() / std::max(1, B)));
-        pool_sparse_kernel<<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, w.head, w.srows);
-        launches += 1;
+        // dense part on the tensor cores: dz_prev = mask * (-u - a Q) (+ its column sums) ...
         if (int rc = tc::pack_w(w.Q, K, K, false, w.qpack, st)) return rc;
-        if (int rc = tc::pool_dgrad(tl, a_in, K, w.qpack, w.u, w.head, w.srows, C, o, st)) return rc;
+        if (int rc = tc::pool_dgrad(tl, a_in, K, w.qpack, w.u, o, st)) return rc;
+        // ... then the <= C selected points per cloud get their sparse rows added (one warp per point)
+        // about one wave of 512-thread CTAs (4 resident per SM); every CTA repeats the O(C + N) prologue
+        const int parts = std::max(1, std::min((C + 15) / 16, (4 * sm_count() + B - 1) / B));
+        if (K <= 128) pool_sparse_kernel<4><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
+        else pool_sparse_kernel<16><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
+        launches += 1;
       } else {
         pool_dgrad_kernel<<<dim3(B * tps, (K + TN - 1) / TN), kThreads, 0, st>>>(src, w.Q, w.u, last.weight, w.coef, pool_arg, C, N, tps, o);
         launches += 1;

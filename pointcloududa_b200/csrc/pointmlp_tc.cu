@@ -22,8 +22,9 @@
 //                                         the [B*N, 1024] activation is never written
 //          DGRAD       da = dy W          epilogue: ReLU mask of the producing layer (from its
 //                                         packed activation), store dz, dbeta / dgamma sums
-//          POOL_DGRAD  da = S - u - a Q   (low-rank backward of the pooled layer, see pointmlp.cu);
-//                                         the streamed operand doubles as the mask source
+//          POOL_DGRAD  da = -u - a Q      (dense part of the low-rank backward of the pooled layer, see
+//                                         pointmlp.cu; the sparse rows are added afterwards by
+//                                         pool_sparse_kernel); the streamed operand doubles as the mask source
 //
 //   pt_kernel  "point-contraction":  D[c, k] = sum_m P[m, c] * R[m, k]      (wgrad, Gram matrix)
 //        MN-major reads of the same slabs; the accumulator stays in TMEM over the CTA's tiles.
@@ -221,9 +222,6 @@ struct WsParams {
   // dgrad epilogues
   DgradOut out;
   const float* u;           // POOL_DGRAD: [R]
-  const int* head;          // POOL_DGRAD: [B*N] lowest channel whose arg-max is this point, or -1
-  const float* srows;       // POOL_DGRAD: [B, Cpool, K] row at (b, head) = sum over the channels selecting that point
-  int Cpool;
   int dbg;                  // timing experiments only (pcuda_tune key 4): 1 = TMEM loads without the epilogue math, 2 = no TMEM loads
 };
 
@@ -478,15 +476,8 @@ __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsPa
               // L2 round trip per column.
               const int col0 = ch * 32;
               if (MODE == POOL_DGRAD) {
-                const int hv = (FULL || lane < ncol) ? __ldg(p.head + m0 + col0 + lane) : -1;
-                float sp[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const int h = __shfl_sync(0xffffffffu, hv, i);
-                  sp[i] = (h >= 0 && rok) ? __ldg(p.srows + (static_cast<int64_t>(b) * p.Cpool + h) * p.K + r) : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = sp[i] - uk - v[i];
+                for (int i = 0; i < 32; ++i) v[i] = -uk - v[i];
               }
               if (rok) {
                 if (to_x) {
@@ -809,10 +800,10 @@ int dgrad_layer(const Tiling& tl, const uint8_t* dy_pack, int C, const uint8_t* 
   return launch_ws<DGRAD>(p, st, "tc::dgrad_layer");
 }
 
-int pool_dgrad(const Tiling& tl, const uint8_t* a_pack, int K, const uint8_t* q_pack, const float* u, const int* head,
-               const float* srows, int Cpool, const DgradOut& out, cudaStream_t st) {
+int pool_dgrad(const Tiling& tl, const uint8_t* a_pack, int K, const uint8_t* q_pack, const float* u, const DgradOut& out,
+               cudaStream_t st) {
   WsParams p{};
-  p.tl = tl; p.K = K; p.R = K; p.A = q_pack; p.Bop = a_pack; p.u = u; p.head = head; p.srows = srows; p.Cpool = Cpool;
+  p.tl = tl; p.K = K; p.R = K; p.A = q_pack; p.Bop = a_pack; p.u = u;
   p.out = out;
   return launch_ws<POOL_DGRAD>(p, st, "tc::pool_dgrad");
 }

@@ -38,9 +38,9 @@ int fwd_layer(const Tiling& tl, const uint8_t* a_pack, const uint8_t* w_pack, co
 int dgrad_layer(const Tiling& tl, const uint8_t* dy_pack, int C, const uint8_t* wt_pack, const uint8_t* aprev_pack,
                 const DgradOut& out, cudaStream_t st);
 
-// pooled layer: da = S - u - a Q; S[m,:] = srows[b, head[m], :] where head[m] >= 0
-int pool_dgrad(const Tiling& tl, const uint8_t* a_pack, int K, const uint8_t* q_pack, const float* u, const int* head,
-               const float* srows, int Cpool, const DgradOut& out, cudaStream_t st);
+// pooled layer, dense part: da = -u - a Q (the sparse rows S are added afterwards by pool_sparse_kernel)
+int pool_dgrad(const Tiling& tl, const uint8_t* a_pack, int K, const uint8_t* q_pack, const float* u, const DgradOut& out,
+               cudaStream_t st);
 
 // contraction over points.  partial: [S, C, Kr] fp32 (one slice per tile-range split)
 int pt_splits(const Tiling& tl, int rblocks);

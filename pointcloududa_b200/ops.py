@@ -168,5 +168,10 @@ def launch_count() -> int:
     return int(_lib.lib().pcuda_launch_count())
 
 
+def sm_count() -> int:
+    """SM count of the current device (148 on B200)."""
+    return int(_lib.lib().pcuda_sm_count())
+
+
 def tune(key: int, value: int) -> None:
     check(_lib.lib().pcuda_tune(int(key), int(value)), "pcuda_tune")
