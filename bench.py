@@ -177,10 +177,16 @@ KERNEL_WORK = {
 }
 
 
-def kernel_profile(step, w: dict, pk: dict, reps: int = 5):
+def kernel_profile(step, w: dict, pk: dict, reps: int = 5, record: bool = True):
     """Per-kernel device time of the (graph-replayed) step from CUPTI activity records, taken live in
-    this process right after the timed region: which kernel dominates, and its roofline."""
+    this process right after the timed region: which kernel dominates, and its roofline.
+    Every rank must call this (the step holds the gradient all-reduce); only `record` ranks profile."""
     import torch
+    if not record:
+        for _ in range(reps):
+            step.run()
+        torch.cuda.synchronize()
+        return None, None
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(reps):
@@ -462,14 +468,22 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = tt.tolist()
 
+    # kernel-level profile of the step: collective inside, so every rank runs the steps; rank 0 records
+    kernel_shares, roof = None, None
+    try:
+        kernel_shares, roof = kernel_profile(step, w, pk, record=(rank == 0))
+    except Exception as e:       # CUPTI unavailable: keep the op-level roofline
+        kernel_shares = {"error": repr(e)}
+        if rank == 0 and world > 1:
+            for _ in range(5):   # keep the collective count matched with the other ranks
+                step.run()
     line = None
     if rank == 0:
         breakdown, roof_ops = op_breakdown(step, w, flush, pk)
-        try:
-            kernel_shares, roof = kernel_profile(step, w, pk)
+        if roof is None:
+            roof = roof_ops
+        else:
             roof["op_level"] = roof_ops
-        except Exception as e:   # CUPTI unavailable: keep the op-level roofline
-            kernel_shares, roof = {"error": repr(e)}, roof_ops
         large = None
         if not args.skip_large:
             try:

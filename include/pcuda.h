@@ -220,6 +220,28 @@ size_t pcuda_fcstack_ws_bytes(int B, int L, const pcuda_fc_layer_t* layers /*hos
 int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_layer_t* layers /*host*/, int train,
                       const float* grad_out, float* grad_x, void* ws, pcuda_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Deferred BatchNorm running-statistics update.  pcuda_pointmlp_fwd / pcuda_fcstack_fwd skip the
+ * running_mean / running_var update when those pointers are NULL; a caller that runs several forward
+ * passes of the same network concurrently (independent streams) applies the updates afterwards, in
+ * the order the reference would have executed the passes:
+ *     running_mean <- (1-momentum) running_mean + momentum * save_mean
+ *     running_var  <- (1-momentum) running_var  + momentum * var * count/(count-1),
+ *     var = 1/save_invstd^2 - eps
+ * items[0..n) are applied in order by ONE launch (n <= 64); several items may name the same buffers.
+ */
+typedef struct pcuda_bn_update {
+  float* running_mean;      /* [C] */
+  float* running_var;       /* [C] */
+  const float* save_mean;   /* [C] from the forward call */
+  const float* save_invstd; /* [C] */
+  int32_t C;
+  int32_t reserved;
+  double count;             /* values per channel the statistics were taken over (B*N, or B) */
+  float momentum, eps;
+} pcuda_bn_update_t;
+int pcuda_bn_running_update(int n, const pcuda_bn_update_t* items /*host*/, pcuda_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,14 @@ class FcLayer(ctypes.Structure):
     ]
 
 
+class BnUpdate(ctypes.Structure):
+    """pcuda_bn_update_t (include/pcuda.h)."""
+    _fields_ = [
+        ("running_mean", c_void_p), ("running_var", c_void_p), ("save_mean", c_void_p), ("save_invstd", c_void_p),
+        ("C", c_int32), ("reserved", c_int32), ("count", c_double), ("momentum", c_float), ("eps", c_float),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/pcuda.h declares
 SIGNATURES = {
     "pcuda_version": (c_int, []),
@@ -72,6 +80,7 @@ SIGNATURES = {
     "pcuda_fcstack_ws_bytes": (c_size_t, [c_int, c_int, POINTER(FcLayer), c_int]),
     "pcuda_fcstack_bwd": (c_int, [c_void_p, c_int, c_int, POINTER(FcLayer), c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
+    "pcuda_bn_running_update": (c_int, [c_int, POINTER(BnUpdate), c_void_p]),
 }
 
 

@@ -336,6 +336,28 @@ __global__ void __launch_bounds__(kPullThreads) fc_pull_kernel(const float* __re
   }
 }
 
+constexpr int kMaxBnItems = 64;
+struct BnItems {
+  pcuda_bn_update_t it[kMaxBnItems];
+  int n;
+};
+// thread = channel; the items are applied in order inside the thread, so updates of the same buffer by
+// several passes compose exactly like sequential forward passes
+__global__ void bn_running_update_kernel(const BnItems items) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = 0; i < items.n; ++i) {
+    const pcuda_bn_update_t& u = items.it[i];
+    if (c >= u.C) continue;
+    const float m = u.momentum;
+    const double is = static_cast<double>(u.save_invstd[c]);
+    double var = 1.0 / (is * is) - static_cast<double>(u.eps);
+    var = var > 0.0 ? var : 0.0;
+    const double unb = u.count > 1.0 ? var * (u.count / (u.count - 1.0)) : var;
+    u.running_mean[c] = (1.f - m) * u.running_mean[c] + m * u.save_mean[c];
+    u.running_var[c] = (1.f - m) * u.running_var[c] + m * static_cast<float>(unb);
+  }
+}
+
 int validate_fc(const char* who, int B, int L, const pcuda_fc_layer_t* layers) {
   PCUDA_REQUIRE(layers != nullptr, PCUDA_E_NULL, "%s: layers is NULL", who);
   PCUDA_REQUIRE(B >= 1 && L >= 1 && L <= 8, PCUDA_E_SHAPE, "%s: bad shape B=%d L=%d", who, B, L);
@@ -442,4 +464,23 @@ extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_la
   }
   count_launch(launches);
   return check_launch("fcstack_bwd");
+}
+
+extern "C" int pcuda_bn_running_update(int n, const pcuda_bn_update_t* items, pcuda_stream_t stream) {
+  PCUDA_REQUIRE(n >= 0 && n <= kMaxBnItems, PCUDA_E_SHAPE, "bn_running_update: n=%d not in [0, %d]", n, kMaxBnItems);
+  if (n == 0) return 0;
+  PCUDA_REQUIRE(items != nullptr, PCUDA_E_NULL, "bn_running_update: items is NULL");
+  BnItems b{};
+  int maxc = 0;
+  for (int i = 0; i < n; ++i) {
+    PCUDA_REQUIRE(items[i].running_mean && items[i].running_var && items[i].save_mean && items[i].save_invstd, PCUDA_E_NULL,
+                  "bn_running_update: item %d has a NULL pointer", i);
+    PCUDA_REQUIRE(items[i].C >= 1, PCUDA_E_SHAPE, "bn_running_update: item %d has C=%d", i, items[i].C);
+    b.it[i] = items[i];
+    maxc = maxc > items[i].C ? maxc : items[i].C;
+  }
+  b.n = n;
+  bn_running_update_kernel<<<(maxc + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(b);
+  count_launch(1);
+  return check_launch("bn_running_update");
 }

@@ -16,7 +16,9 @@ reference's nn.Dropout on a [B,256] tensor) and handed to the kernel.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -25,7 +27,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
-from .._lib import FcLayer, MlpLayer, PcudaError, check
+from .._lib import BnUpdate, FcLayer, MlpLayer, PcudaError, check
 
 PRECISIONS = {"fp32": 0, "bf16": 1}
 DEFAULT_PRECISION = "bf16"
@@ -35,12 +37,59 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+# ---- deferred BatchNorm running statistics ------------------------------------------------------------
+# Train-mode forward passes of ONE network that run concurrently on different streams (the three D4 passes
+# of an adversarial step, pointcloududa_b200/step.py) must not race on running_mean / running_var /
+# num_batches_tracked.  Inside `with deferred_bn_updates(sink):` the kernels skip those updates and every
+# BatchNorm layer records (module, batch mean, batch invstd, count) in `sink`; `apply_bn_updates([sink_a,
+# sink_b, ...])` then applies them in the order the reference would have run the passes — one launch.
+_TLS = threading.local()
+
+
+@contextlib.contextmanager
+def deferred_bn_updates(sink: list):
+    prev = getattr(_TLS, "sink", None)
+    _TLS.sink = sink
+    try:
+        yield sink
+    finally:
+        _TLS.sink = prev
+
+
+def apply_bn_updates(sinks: Sequence[list]) -> None:
+    entries = [e for sink in sinks for e in sink]
+    if not entries:
+        return
+    dev = entries[0][1].device
+    Lb = _lib.lib()
+    with torch.cuda.device(dev):
+        for i0 in range(0, len(entries), 64):
+            chunk = entries[i0:i0 + 64]
+            items = (BnUpdate * len(chunk))()
+            for it, (bn, mean, invstd, count) in zip(items, chunk):
+                it.running_mean, it.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+                it.save_mean, it.save_invstd = mean.data_ptr(), invstd.data_ptr()
+                it.C, it.count, it.momentum, it.eps = mean.numel(), float(count), float(bn.momentum), float(bn.eps)
+            check(Lb.pcuda_bn_running_update(len(chunk), items, torch.cuda.current_stream().cuda_stream),
+                  "pcuda_bn_running_update")
+    counts = {}
+    for bn, _, _, _ in entries:
+        if bn.num_batches_tracked is not None:
+            counts[id(bn)] = (bn, counts.get(id(bn), (bn, 0))[1] + 1)
+    by_k = {}
+    for bn, k in counts.values():
+        by_k.setdefault(k, []).append(bn.num_batches_tracked)
+    for k, lst in by_k.items():
+        torch._foreach_add_(lst, k)
+
+
 class _SharedMLP(torch.autograd.Function):
     """y = [max_n] relu?(bn(conv1x1(...relu(bn(conv1x1(x)))))) on libpcuda."""
 
     @staticmethod
     def forward(ctx, x, pool: bool, train: bool, precision: int, relus: Tuple[bool, ...],
-                momenta: Tuple[float, ...], eps: float, buffers: Tuple[torch.Tensor, ...], *params):
+                momenta: Tuple[float, ...], eps: float, buffers: Tuple[Optional[torch.Tensor], ...],
+                stats_out: Optional[list], *params):
         # params: (weight, bias, gamma, beta) per layer; buffers: (running_mean, running_var) per layer
         if not x.is_cuda:
             raise PcudaError("PointNetCls runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -81,6 +130,8 @@ class _SharedMLP(torch.autograd.Function):
             check(Lb.pcuda_pointmlp_fwd(_ptr(x), x.stride(0), x.stride(1), x.stride(2), B, N, L, lay, int(pool),
                                         int(train), float(momenta[0]), float(eps), precision, _ptr(out), _ptr(arg),
                                         _ptr(ws), torch.cuda.current_stream().cuda_stream), "pcuda_pointmlp_fwd")
+        if stats_out is not None:
+            stats_out.extend(zip(means, invstds))
         ctx.cfg = (pool, train, precision, relus, eps, B, N, L)
         ctx.save_for_backward(x)
         ctx.keep = keep
@@ -96,7 +147,7 @@ class _SharedMLP(torch.autograd.Function):
         ys, means, invstds, out, arg = ctx.saved
         dev = x.device
         need_x = ctx.needs_input_grad[0]
-        needs_p = ctx.needs_input_grad[8:]
+        needs_p = ctx.needs_input_grad[9:]
         lay = (MlpLayer * L)()
         grads: List[Optional[torch.Tensor]] = []
         for l in range(L):
@@ -127,7 +178,7 @@ class _SharedMLP(torch.autograd.Function):
         for i, need in enumerate(needs_p):
             if not need:
                 grads[i] = None
-        return (gx, None, None, None, None, None, None, None, *grads)
+        return (gx, None, None, None, None, None, None, None, None, *grads)
 
 
 def shared_mlp(x: torch.Tensor, convs: Sequence[nn.Conv1d], bns: Sequence[nn.BatchNorm1d],
@@ -147,9 +198,16 @@ def shared_mlp(x: torch.Tensor, convs: Sequence[nn.Conv1d], bns: Sequence[nn.Bat
         params += [conv.weight, conv.bias, bn.weight, bn.bias]
         buffers += [bn.running_mean, bn.running_var]
         momenta.append(float(bn.momentum))
+    sink = getattr(_TLS, "sink", None) if train else None
+    stats_out = [] if sink is not None else None
+    if sink is not None:
+        buffers = [None] * len(buffers)          # the kernels skip the running-stat update
     out = _SharedMLP.apply(x, bool(pool), bool(train), PRECISIONS[precision], tuple(bool(r) for r in relus),
-                           tuple(momenta), float(eps), tuple(buffers), *params)
-    if train:
+                           tuple(momenta), float(eps), tuple(buffers), stats_out, *params)
+    if sink is not None:
+        count = x.shape[0] * x.shape[2]
+        sink.extend((bn, mean, invstd, count) for bn, (mean, invstd) in zip(bns, stats_out))
+    elif train:
         counters = [bn.num_batches_tracked for bn in bns if bn.num_batches_tracked is not None]
         if counters:
             torch._foreach_add_(counters, 1)
@@ -161,7 +219,8 @@ class _FcStack(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, train: bool, relus: Tuple[bool, ...], bn_flags: Tuple[bool, ...], momentum: float, eps: float,
-                iden_k: int, buffers: Tuple[Optional[torch.Tensor], ...], masks: Tuple[Optional[torch.Tensor], ...], *params):
+                iden_k: int, buffers: Tuple[Optional[torch.Tensor], ...], masks: Tuple[Optional[torch.Tensor], ...],
+                stats_out: Optional[list], *params):
         if not x.is_cuda:
             raise PcudaError("PointNetCls runs on CUDA (sm_100a) only; there is no CPU fallback")
         if x.dtype != torch.float32 or x.dim() != 2:
@@ -195,6 +254,8 @@ class _FcStack(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(_lib.lib().pcuda_fcstack_fwd(_ptr(xc), B, L, lay, int(train), float(momentum), float(eps), int(iden_k),
                                                torch.cuda.current_stream().cuda_stream), "pcuda_fcstack_fwd")
+        if stats_out is not None:
+            stats_out.extend((sv[0], sv[1]) for sv in saved)
         ctx.cfg = (train, relus, bn_flags, B, L)
         ctx.save_for_backward(xc)
         ctx.keep, ctx.saved = keep, saved
@@ -207,7 +268,7 @@ class _FcStack(torch.autograd.Function):
         keep, saved = ctx.keep, ctx.saved
         dev = xc.device
         need_x = ctx.needs_input_grad[0]
-        needs_p = ctx.needs_input_grad[9:]
+        needs_p = ctx.needs_input_grad[10:]
         lay = (FcLayer * L)()
         grads: List[Optional[torch.Tensor]] = []
         for l in range(L):
@@ -238,7 +299,7 @@ class _FcStack(torch.autograd.Function):
         for i, need in enumerate(needs_p):
             if not need:
                 grads[i] = None
-        return (gx, None, None, None, None, None, None, None, None, *grads)
+        return (gx, None, None, None, None, None, None, None, None, None, *grads)
 
 
 def fc_stack(x: torch.Tensor, linears: Sequence[nn.Linear], bns: Sequence[Optional[nn.BatchNorm1d]],
@@ -260,9 +321,15 @@ def fc_stack(x: torch.Tensor, linears: Sequence[nn.Linear], bns: Sequence[Option
         params += [lin.weight, lin.bias, None if bn is None else bn.weight, None if bn is None else bn.bias]
         buffers += [None if bn is None else bn.running_mean, None if bn is None else bn.running_var]
     masks = tuple(masks) if masks is not None else (None,) * len(linears)
+    sink = getattr(_TLS, "sink", None) if train else None
+    stats_out = [] if sink is not None else None
+    if sink is not None:
+        buffers = [None] * len(buffers)
     out = _FcStack.apply(x, bool(train), tuple(bool(r) for r in relus), tuple(bn is not None for bn in bns),
-                         float(momentum), float(eps), int(add_identity_k), tuple(buffers), masks, *params)
-    if train:
+                         float(momentum), float(eps), int(add_identity_k), tuple(buffers), masks, stats_out, *params)
+    if sink is not None:
+        sink.extend((bn, mean, invstd, x.shape[0]) for bn, (mean, invstd) in zip(bns, stats_out) if bn is not None)
+    elif train:
         counters = [bn.num_batches_tracked for bn in real if bn.num_batches_tracked is not None]
         if counters:
             torch._foreach_add_(counters, 1)

@@ -15,6 +15,13 @@ SURVEY.md §3.1 / §8d "one adversarial step"):
 
 The U-Net, D1/D2 and host-side bookkeeping are excluded.  All scalar results are kept on the
 device and returned as one small tensor so a caller pays a single device->host read per step.
+
+Phases P1+P2, P3 and P4 do not depend on each other (D4's parameters only change in P5), and at the
+reference's shapes (2400 points per D4 call) no single kernel fills 148 SMs, so the step issues them on
+three streams: inside a captured CUDA graph they become three concurrent branches.  The only shared
+mutable state, BatchNorm's running statistics / num_batches_tracked, is recorded per pass and applied
+after the join in the reference's pass order (networks.PointNetCls.deferred_bn_updates), so buffers and
+gradients are identical to sequential execution.
 The whole step is CUDA-graph capturable (`AdversarialStep.capture()`): no host synchronisation,
 no allocation outside torch's graph pool, every libpcuda launch on the capture stream.
 """
@@ -27,7 +34,7 @@ import torch
 import torch.nn.functional as F
 
 from . import dist as pdist
-from .networks.PointNetCls import PointNetCls
+from .networks.PointNetCls import PointNetCls, apply_bn_updates, deferred_bn_updates
 from .utils.loss import batch_NN_loss, entropy_map
 
 RESULT_FIELDS = ("chamfer_source", "chamfer_target", "entropy_mean_target", "adv_point_loss",
@@ -54,7 +61,7 @@ class StepConfig:
 class AdversarialStep:
     """Owns D4, its optimiser, static input buffers and (optionally) a captured CUDA graph."""
 
-    def __init__(self, cfg: StepConfig, device: torch.device, seed: int = 0):
+    def __init__(self, cfg: StepConfig, device: torch.device, seed: int = 0, concurrent: bool = True):
         self.cfg = cfg
         self.device = device
         torch.manual_seed(seed)
@@ -83,6 +90,8 @@ class AdversarialStep:
         self._res = []
         self._ones = torch.ones(B, 1, **f32)
         self._zeros = torch.zeros(B, 1, **f32)
+        self._side = None
+        self.concurrent = concurrent
 
     # -- inputs -----------------------------------------------------------------------------------
     def load_inputs(self, host: Dict[str, torch.Tensor], non_blocking: bool = True) -> int:
@@ -105,19 +114,28 @@ class AdversarialStep:
     # -- the step -----------------------------------------------------------------------------------
     def _pre(self) -> None:
         cfg, I = self.cfg, self.inputs
-        res = []
-        # P0: zero D4's gradients (they live in the flat bucket), freeze D4
-        self.bucket.zero()
-        self._set_requires_grad(False)
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if self._side is None:
+            self._side = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s1, s2 = self._side if self.concurrent else (main, main)
+        sink_p2, sink_p3, sink_p4 = [], [], []
 
-        # P1: source Chamfer, forward + backward into the predicted cloud
+        # P0: zero D4's gradients (they live in the flat bucket)
+        self.bucket.zero()
+        if self.concurrent:
+            s1.wait_stream(main)
+            s2.wait_stream(main)
+
+        # ---- branch A (this stream) — P1: source Chamfer, forward + backward into the predicted cloud.  Issued first
+        # so that Dropout consumes the generator in the reference's order (P2, P3, P4); the streams run concurrently
+        # regardless of the issue order.
+        self._set_requires_grad(False)
         vertS = I["vertS"].detach().requires_grad_(True)
         loss_seg3 = batch_NN_loss(x=vertS, y=I["vertexA"])
         (gS,) = torch.autograd.grad(loss_seg3, vertS)
         self.grad_vertS.copy_(gS)
-        res.append(loss_seg3.detach())
-
-        # P2: fool the discriminators
+        # P2: fool the discriminators (D4 frozen: gradient into the cloud only)
         oT = I["oT"].detach().requires_grad_(True)
         outs = entropy_map(oT, activation=cfg.activation, normalize=cfg.normalize,
                            return_prob=cfg.return_prob, return_mean=True)
@@ -127,33 +145,50 @@ class AdversarialStep:
         vertT = I["vertT"].detach().requires_grad_(True)
         with torch.no_grad():
             loss_vert_target = batch_NN_loss(x=vertT, y=I["vertexB"])
-        D_out4 = self.d4(vertT.transpose(2, 1))[0]
+        with deferred_bn_updates(sink_p2):
+            D_out4 = self.d4(vertT.transpose(2, 1))[0]
         loss_adv_point = cfg.dr * F.binary_cross_entropy_with_logits(D_out4, self._ones)
         (gT,) = torch.autograd.grad(loss_adv_point, vertT)
         self.grad_vertT.copy_(gT)
-        res += [loss_vert_target.detach(), ent_mean.detach(), loss_adv_point.detach()]
-
-        # P3: discriminators on the source domain (label 1).  D4 runs on fresh leaf views of its
-        # parameters (functional_call): their gradient-accumulator nodes are created on the stream
-        # the step runs on, so the step is legal under CUDA-graph capture on a side stream, and
-        # the gradients are summed straight into the flat bucket.
         self._set_requires_grad(True)
-        with torch.no_grad():
-            entropy_map(I["oS"], activation=cfg.activation, normalize=cfg.normalize,
-                        return_prob=cfg.return_prob)
-        D_out4, leaves = self._d4_fresh(I["vertS"].transpose(2, 1))
-        loss_D_same4 = F.binary_cross_entropy_with_logits(D_out4, self._ones)
-        self.bucket.accumulate(torch.autograd.grad(loss_D_same4, leaves, allow_unused=True))
-        acc_s = (torch.sigmoid(D_out4.detach()) >= 0.5).float().mean()
 
-        # P4: discriminators on the target domain (label 0)
-        D_out4, leaves = self._d4_fresh(I["vertT"].transpose(2, 1))
-        loss_D_diff_4 = F.binary_cross_entropy_with_logits(D_out4, self._zeros)
-        self.bucket.accumulate(torch.autograd.grad(loss_D_diff_4, leaves, allow_unused=True))
-        acc_t = 1.0 - (torch.sigmoid(D_out4.detach()) >= 0.5).float().mean()
-        res += [loss_D_same4.detach(), loss_D_diff_4.detach(), acc_s, acc_t]
+        # ---- branch B (stream s1) — P3: discriminators on the source domain (label 1).  D4 runs on fresh
+        # leaf views of its parameters (functional_call): their gradient-accumulator nodes are created on
+        # the stream the branch runs on, so the step is legal under CUDA-graph capture.
+        self._set_requires_grad(True)
+        with torch.cuda.stream(s1):
+            with torch.no_grad():
+                entropy_map(I["oS"], activation=cfg.activation, normalize=cfg.normalize, return_prob=cfg.return_prob)
+            with deferred_bn_updates(sink_p3):
+                D_out4, leaves = self._d4_fresh(I["vertS"].transpose(2, 1))
+            loss_D_same4 = F.binary_cross_entropy_with_logits(D_out4, self._ones)
+            grads_s = torch.autograd.grad(loss_D_same4, leaves, allow_unused=True)
+            acc_s = (torch.sigmoid(D_out4.detach()) >= 0.5).float().mean()
 
-        self._res = res
+        # ---- branch C (stream s2) — P4: discriminators on the target domain (label 0)
+        with torch.cuda.stream(s2):
+            with deferred_bn_updates(sink_p4):
+                D_out4, leaves = self._d4_fresh(I["vertT"].transpose(2, 1))
+            loss_D_diff_4 = F.binary_cross_entropy_with_logits(D_out4, self._zeros)
+            grads_t = torch.autograd.grad(loss_D_diff_4, leaves, allow_unused=True)
+            acc_t = 1.0 - (torch.sigmoid(D_out4.detach()) >= 0.5).float().mean()
+
+        # ---- join: parameter gradients into the flat bucket, BatchNorm buffers in the reference's pass order
+        if self.concurrent:
+            main.wait_stream(s1)
+            main.wait_stream(s2)
+            if not torch.cuda.is_current_stream_capturing():
+                # eager mode: tensors born on a side stream are consumed on this one after the join
+                crossing = list(grads_s) + list(grads_t) + [loss_D_same4, loss_D_diff_4, acc_s, acc_t]
+                crossing += [t for sink in (sink_p3, sink_p4) for e in sink for t in (e[1], e[2])]
+                for t in crossing:
+                    if t is not None:
+                        t.record_stream(main)
+        self.bucket.accumulate(grads_s)
+        self.bucket.accumulate(grads_t)
+        apply_bn_updates([sink_p2, sink_p3, sink_p4])
+        self._res = [loss_seg3.detach(), loss_vert_target.detach(), ent_mean.detach(), loss_adv_point.detach(),
+                     loss_D_same4.detach(), loss_D_diff_4.detach(), acc_s, acc_t]
 
     def _post(self) -> None:
         # P5 (after the gradient all-reduce): SGD step of D4, scalars of the step into one small tensor

@@ -793,3 +793,78 @@ def test_pointnetcls_dropout_mask_matches_torch_stream():
     got_mask = net.dropout(net._ones)
     assert torch.equal(got_mask, want_mask)
     assert 0.15 < (got_mask == 0).float().mean().item() < 0.45
+
+
+# ================================================= the adversarial step ================================
+def test_deferred_bn_updates_equal_sequential_forwards():
+    """Running statistics / num_batches_tracked recorded per pass and applied afterwards (what the
+    concurrent step does) == the plain sequential forwards of the reference's train loop."""
+    from pointcloududa_b200.networks.PointNetCls import PointNetCls, apply_bn_updates, deferred_bn_updates
+    torch.manual_seed(5)
+    a = PointNetCls(drop=0.0, precision="fp32", feature_transform=True).to(DEV).train()
+    b = PointNetCls(drop=0.0, precision="fp32", feature_transform=True).to(DEV).train()
+    b.load_state_dict(a.state_dict())
+    xs = [torch.rand(4, 3, 200, device=DEV), torch.rand(4, 3, 200, device=DEV) * 0.5, torch.rand(4, 3, 200, device=DEV) + 1.0]
+    outs_a = [a(x)[0] for x in xs]
+    sinks, outs_b = [], []
+    for x in xs:
+        sink = []
+        with deferred_bn_updates(sink):
+            outs_b.append(b(x)[0])
+        sinks.append(sink)
+    assert int(b.feat.bn3.num_batches_tracked.item()) == 0       # nothing applied yet
+    apply_bn_updates(sinks)
+    for oa, ob in zip(outs_a, outs_b):
+        assert torch.equal(oa, ob)                                # train-mode outputs do not depend on the buffers
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if "in" in k.split(".")[-2][:2] and "running" in k:       # unused InstanceNorm buffers
+            continue
+        if k.endswith("num_batches_tracked"):
+            assert int(sa[k].item()) == int(sb[k].item()), k
+        elif "running" in k:
+            assert max_rel(sb[k].cpu().numpy(), sa[k].cpu().numpy()) < 1e-5, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_adversarial_step_concurrent_branches_equal_sequential(precision):
+    """The three-stream step (eager and CUDA-graph replay) produces the same scalars, gradients, BatchNorm
+    buffers and updated parameters as the same step issued on one stream."""
+    from pointcloududa_b200.step import AdversarialStep, StepConfig
+    from bench import make_host_inputs
+    w = dict(B=4, C=4, H=32, W=32, N=300, activation="sigmoid", normalize=False, return_prob=False)
+    cfg = StepConfig(B=4, C=4, H=32, W=32, N=300, precision=precision)
+    host = make_host_inputs(w, 0, pinned=False)
+    dev = torch.device(DEV)
+
+    def run(concurrent, graph):
+        torch.manual_seed(1)
+        st = AdversarialStep(cfg, dev, seed=0, concurrent=concurrent)
+        for m in st.d4.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0                                         # graph replay re-draws masks per replay
+        st.load_inputs(host, non_blocking=False)
+        if graph:
+            st.capture(warmup=1)
+        res = [st.run().clone() for _ in range(2)]
+        torch.cuda.synchronize()
+        return st, res
+
+    ref, res_ref = run(False, False)
+    got, res = run(True, False)
+    for a, b in zip(res, res_ref):
+        assert max_rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-6
+    assert max_rel(got.bucket.flat.cpu().numpy(), ref.bucket.flat.cpu().numpy()) < 1e-6
+    sa, sb = got.d4.state_dict(), ref.d4.state_dict()
+    for k in sa:
+        if k.endswith("num_batches_tracked"):
+            assert int(sa[k].item()) == int(sb[k].item()), k
+        else:
+            assert max_rel(sa[k].cpu().numpy(), sb[k].cpu().numpy()) < 1e-6, k
+    # CUDA-graph replay of the three-branch step: finite, and the same scalars as the eager step's first run
+    # (the parameters have moved by the warm-up steps of capture(), so only the D4-independent entries are equal)
+    gst, gres = run(True, True)
+    assert torch.isfinite(gres[-1]).all()
+    for idx in (0, 1, 2):                                         # chamfer_source, chamfer_target, entropy_mean_target
+        assert abs(gres[-1][idx].item() - res_ref[0][idx].item()) <= 1e-6 * abs(res_ref[0][idx].item())
+    assert int(gst.d4.feat.bn3.num_batches_tracked.item()) > 0
