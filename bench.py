@@ -174,6 +174,12 @@ KERNEL_WORK = {
     "entropy_bwd": ("hbm", lambda w: 12.0 * w["B"] * w["C"] * w["H"] * w["W"]),
     "chamfer_nn": ("hbm", lambda w: 48.0 * w["B"] * w["N"]),                      # 24 B/point in + out, both clouds
     "pack_act_kernel": ("hbm", lambda w: (4.0 + 2.0) * w["B"] * w["N"] * 128),    # fp32 in, bf16 out (widest layer)
+    # sparse rows of the pooled-layer dgrad: arg/coef, one W row per (cloud, channel), read-modify-write of the
+    # <= min(C, N) selected points per cloud (y_prev, dz_prev in, dz_prev out), K = 128, C = 1024
+    "pool_sparse_kernel": ("hbm", lambda w: w["B"] * 1024 * (8.0 + 4.0 * 128) + w["B"] * min(1024, w["N"]) * 128 * 12.0),
+    "pool_dw_kernel": ("hbm", lambda w: 1024 * 128 * 8.0 + 128 * 128 * 4.0 + w["B"] * 1024 * (8.0 + 4.0 * 128)),
+    "fc_fwd_kernel": ("hbm", lambda w: 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) / 3 + 4.0 * w["B"] * (1024 + 512)),   # mean layer of a head
+    "fc_bwd_kernel": ("hbm", lambda w: 2 * 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) / 3 + 4.0 * w["B"] * (1024 + 512)),
 }
 
 

@@ -337,25 +337,47 @@ __global__ void __launch_bounds__(kPullThreads) fc_pull_kernel(const float* __re
 }
 
 constexpr int kMaxBnItems = 64;
-struct BnItems {
-  pcuda_bn_update_t it[kMaxBnItems];
-  int n;
+constexpr int kMaxBnGroups = 32;
+constexpr int kMaxPerGroup = 8;
+// items that update the same buffers form a group (applied in order, in registers); groups are independent
+struct BnGroups {
+  struct G {
+    float* running_mean; float* running_var;
+    const float* save_mean[kMaxPerGroup]; const float* save_invstd[kMaxPerGroup];
+    double count[kMaxPerGroup];
+    float momentum[kMaxPerGroup], eps[kMaxPerGroup];
+    int C, n;
+  } g[kMaxBnGroups];
 };
-// thread = channel; the items are applied in order inside the thread, so updates of the same buffer by
-// several passes compose exactly like sequential forward passes
-__global__ void bn_running_update_kernel(const BnItems items) {
+// blockIdx.y = group, thread = channel: every load of the group is issued up front, the updates compose
+// in registers exactly like sequential forward passes, one store per buffer
+constexpr int kBnGroupsPerLaunch = 12;        // 12 x 280 bytes of kernel parameters
+struct BnLaunch { BnGroups::G g[kBnGroupsPerLaunch]; };
+__global__ void bn_running_update_group_kernel(const BnLaunch a, int ngroups) {
+  const BnGroups::G& u = a.g[blockIdx.y];
+  if (static_cast<int>(blockIdx.y) >= ngroups) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int i = 0; i < items.n; ++i) {
-    const pcuda_bn_update_t& u = items.it[i];
-    if (c >= u.C) continue;
-    const float m = u.momentum;
-    const double is = static_cast<double>(u.save_invstd[c]);
-    double var = 1.0 / (is * is) - static_cast<double>(u.eps);
-    var = var > 0.0 ? var : 0.0;
-    const double unb = u.count > 1.0 ? var * (u.count / (u.count - 1.0)) : var;
-    u.running_mean[c] = (1.f - m) * u.running_mean[c] + m * u.save_mean[c];
-    u.running_var[c] = (1.f - m) * u.running_var[c] + m * static_cast<float>(unb);
+  if (c >= u.C) return;
+  float sm[kMaxPerGroup], is[kMaxPerGroup];
+#pragma unroll
+  for (int i = 0; i < kMaxPerGroup; ++i) {
+    sm[i] = i < u.n ? u.save_mean[i][c] : 0.f;
+    is[i] = i < u.n ? u.save_invstd[i][c] : 1.f;
   }
+  float rm = u.running_mean[c], rv = u.running_var[c];
+#pragma unroll
+  for (int i = 0; i < kMaxPerGroup; ++i) {
+    if (i >= u.n) break;
+    const float m = u.momentum[i];
+    const double isd = static_cast<double>(is[i]);
+    double var = 1.0 / (isd * isd) - static_cast<double>(u.eps[i]);
+    var = var > 0.0 ? var : 0.0;
+    const double unb = u.count[i] > 1.0 ? var * (u.count[i] / (u.count[i] - 1.0)) : var;
+    rm = (1.f - m) * rm + m * sm[i];
+    rv = (1.f - m) * rv + m * static_cast<float>(unb);
+  }
+  u.running_mean[c] = rm;
+  u.running_var[c] = rv;
 }
 
 int validate_fc(const char* who, int B, int L, const pcuda_fc_layer_t* layers) {
@@ -470,17 +492,38 @@ extern "C" int pcuda_bn_running_update(int n, const pcuda_bn_update_t* items, pc
   PCUDA_REQUIRE(n >= 0 && n <= kMaxBnItems, PCUDA_E_SHAPE, "bn_running_update: n=%d not in [0, %d]", n, kMaxBnItems);
   if (n == 0) return 0;
   PCUDA_REQUIRE(items != nullptr, PCUDA_E_NULL, "bn_running_update: items is NULL");
-  BnItems b{};
-  int maxc = 0;
+  // group the items by target buffer, keeping their order inside a group
+  static thread_local BnGroups gs;
+  int ng = 0;
   for (int i = 0; i < n; ++i) {
     PCUDA_REQUIRE(items[i].running_mean && items[i].running_var && items[i].save_mean && items[i].save_invstd, PCUDA_E_NULL,
                   "bn_running_update: item %d has a NULL pointer", i);
     PCUDA_REQUIRE(items[i].C >= 1, PCUDA_E_SHAPE, "bn_running_update: item %d has C=%d", i, items[i].C);
-    b.it[i] = items[i];
-    maxc = maxc > items[i].C ? maxc : items[i].C;
+    int g = 0;
+    while (g < ng && gs.g[g].running_mean != items[i].running_mean) ++g;
+    if (g == ng) {
+      PCUDA_REQUIRE(ng < kMaxBnGroups, PCUDA_E_UNSUPPORTED, "bn_running_update: more than %d distinct buffers", kMaxBnGroups);
+      gs.g[g].running_mean = items[i].running_mean; gs.g[g].running_var = items[i].running_var;
+      gs.g[g].C = items[i].C; gs.g[g].n = 0;
+      ++ng;
+    }
+    BnGroups::G& G = gs.g[g];
+    PCUDA_REQUIRE(G.n < kMaxPerGroup && G.C == items[i].C && G.running_var == items[i].running_var, PCUDA_E_UNSUPPORTED,
+                  "bn_running_update: item %d: more than %d updates of one buffer, or inconsistent buffers", i, kMaxPerGroup);
+    G.save_mean[G.n] = items[i].save_mean; G.save_invstd[G.n] = items[i].save_invstd;
+    G.count[G.n] = items[i].count; G.momentum[G.n] = items[i].momentum; G.eps[G.n] = items[i].eps;
+    ++G.n;
   }
-  b.n = n;
-  bn_running_update_kernel<<<(maxc + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(b);
-  count_launch(1);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int launches = 0;
+  for (int g0 = 0; g0 < ng; g0 += kBnGroupsPerLaunch) {
+    static thread_local BnLaunch a;
+    int maxc = 0;
+    const int cnt = ng - g0 < kBnGroupsPerLaunch ? ng - g0 : kBnGroupsPerLaunch;
+    for (int k = 0; k < cnt; ++k) { a.g[k] = gs.g[g0 + k]; maxc = maxc > a.g[k].C ? maxc : a.g[k].C; }
+    bn_running_update_group_kernel<<<dim3((maxc + 255) / 256, cnt), 256, 0, st>>>(a, cnt);
+    ++launches;
+  }
+  count_launch(launches);
   return check_launch("bn_running_update");
 }

@@ -799,16 +799,20 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
 // one coalesced read of a row of Ghat serves kDwCh accumulators (the previous one-thread-per-output
 // version walked K dependent loads per output: 17 us at C=1024, K=128).
 constexpr int kDwCh = 8;
-__global__ void __launch_bounds__(128)
+constexpr int kDwParts = 4;                    // the two contraction loops are split 4 ways inside the CTA
+__global__ void __launch_bounds__(128 * kDwParts)
 pool_dw_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ coef,
                const int32_t* __restrict__ arg, const float* __restrict__ kappa,
                const float* __restrict__ abar, const float* __restrict__ Ghat, int B, int N,
                int C, int train, float* __restrict__ dW) {
-  extern __shared__ float wrow[];              // [kDwCh][K] | sel_cf[B][kDwCh] | sel_m[B][kDwCh]
+  // dynamic smem: wrow[kDwCh][K] | sel_cf[B][kDwCh] | sel_m[B][kDwCh] | red[kDwParts][128][kDwCh] doubles
+  extern __shared__ __align__(16) float wrow[];
   const int K = src.C;
   float* sel_cf = wrow + kDwCh * K;
   int* sel_m = reinterpret_cast<int*>(sel_cf + B * kDwCh);
+  double* red = reinterpret_cast<double*>(wrow + ((kDwCh * (K + 2 * B) + 3) & ~3));
   const int c0 = blockIdx.x * kDwCh;
+  const int tk = threadIdx.x & 127, part = threadIdx.x >> 7;
   for (int i = threadIdx.x; i < kDwCh * K; i += blockDim.x) {
     const int j = i / K, k2 = i - j * K;
     wrow[i] = c0 + j < C ? W[static_cast<int64_t>(c0 + j) * K + k2] : 0.f;
@@ -822,46 +826,74 @@ pool_dw_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
     sel_m[i] = cf != 0.f ? b * N + arg[static_cast<int64_t>(b) * C + c] : 0;
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    double t[kDwCh];
+  for (int k0 = 0; k0 < K; k0 += 128) {
+    const int k = k0 + tk;
+    double acc[kDwCh];                         // this part's share of  sum_b coef (a - abar) - kappa * (W Ghat)
 #pragma unroll
-    for (int j = 0; j < kDwCh; ++j) t[j] = 0.0;
-#pragma unroll 8
-    for (int k2 = 0; k2 < K; ++k2) {
-      const double g = static_cast<double>(Ghat[static_cast<int64_t>(k2) * K + k]);
+    for (int j = 0; j < kDwCh; ++j) acc[j] = 0.0;
+    if (k < K) {
+      const int per = (K + kDwParts - 1) / kDwParts;
+      const int k2a = part * per, k2b = min(K, k2a + per);
+      // fp32 inside a part's K/4-long slice (two sub-chains), the parts are combined in double below
+      float t0[kDwCh], t1[kDwCh];
 #pragma unroll
-      for (int j = 0; j < kDwCh; ++j) t[j] = fma(static_cast<double>(wrow[j * K + k2]), g, t[j]);
-    }
-    // train: sum_b coef = M*alpha, which folds the rank-one BN term into a centring of a[sel];
-    // eval: there is no BN correction at all
-    const float ab = train ? abar[k] : 0.f;
-    float sc = 1.f, sh = 0.f;                   // a = relu?(y * sc + sh) for a BatchNorm'd source
-    if (src.y != nullptr) {
-      sc = src.invstd[k] * src.gamma[k];
-      sh = src.beta[k] - src.mean[k] * sc;
-    }
-    double sacc[kDwCh];
+      for (int j = 0; j < kDwCh; ++j) { t0[j] = 0.f; t1[j] = 0.f; }
+      int k2 = k2a;
+#pragma unroll 4
+      for (; k2 + 1 < k2b; k2 += 2) {
+        const float g0 = Ghat[static_cast<int64_t>(k2) * K + k], g1 = Ghat[static_cast<int64_t>(k2 + 1) * K + k];
 #pragma unroll
-    for (int j = 0; j < kDwCh; ++j) sacc[j] = 0.0;
-    for (int b = 0; b < B; ++b) {
-      float av[kDwCh];
+        for (int j = 0; j < kDwCh; ++j) { t0[j] = fmaf(wrow[j * K + k2], g0, t0[j]); t1[j] = fmaf(wrow[j * K + k2 + 1], g1, t1[j]); }
+      }
+      if (k2 < k2b) {
+        const float g0 = Ghat[static_cast<int64_t>(k2) * K + k];
 #pragma unroll
-      for (int j = 0; j < kDwCh; ++j) {         // independent loads: kDwCh in flight
-        const int m = sel_m[b * kDwCh + j];
-        if (src.y != nullptr) av[j] = src.y[static_cast<int64_t>(m) * K + k];
-        else av[j] = load_act1(src, m, k);
+        for (int j = 0; j < kDwCh; ++j) t0[j] = fmaf(wrow[j * K + k2], g0, t0[j]);
+      }
+      double t[kDwCh];
+#pragma unroll
+      for (int j = 0; j < kDwCh; ++j) t[j] = static_cast<double>(t0[j]) + static_cast<double>(t1[j]);
+      // train: sum_b coef = M*alpha, which folds the rank-one BN term into a centring of a[sel];
+      // eval: there is no BN correction at all
+      const float ab = train ? abar[k] : 0.f;
+      float sc = 1.f, sh = 0.f;                 // a = relu?(y * sc + sh) for a BatchNorm'd source
+      if (src.y != nullptr) {
+        sc = src.invstd[k] * src.gamma[k];
+        sh = src.beta[k] - src.mean[k] * sc;
+      }
+      for (int b = part; b < B; b += kDwParts) {
+        float av[kDwCh];
+#pragma unroll
+        for (int j = 0; j < kDwCh; ++j) {       // independent loads: kDwCh in flight
+          const int m = sel_m[b * kDwCh + j];
+          if (src.y != nullptr) av[j] = src.y[static_cast<int64_t>(m) * K + k];
+          else av[j] = load_act1(src, m, k);
+        }
+#pragma unroll
+        for (int j = 0; j < kDwCh; ++j) {
+          float a = av[j];
+          if (src.y != nullptr) { a = fmaf(a, sc, sh); a = src.relu ? fmaxf(a, 0.f) : a; }
+          acc[j] += static_cast<double>(sel_cf[b * kDwCh + j]) * static_cast<double>(a - ab);
+        }
       }
 #pragma unroll
       for (int j = 0; j < kDwCh; ++j) {
-        float a = av[j];
-        if (src.y != nullptr) { a = fmaf(a, sc, sh); a = src.relu ? fmaxf(a, 0.f) : a; }
-        sacc[j] += static_cast<double>(sel_cf[b * kDwCh + j]) * static_cast<double>(a - ab);
+        const int c = c0 + j;
+        acc[j] -= (c < C ? static_cast<double>(kappa[c]) : 0.0) * t[j];
       }
     }
+    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < kDwCh; ++j) {
-      const int c = c0 + j;
-      if (c < C) dW[static_cast<int64_t>(c) * K + k] = static_cast<float>(sacc[j] - static_cast<double>(kappa[c]) * t[j]);
+    for (int j = 0; j < kDwCh; ++j) red[(part * 128 + tk) * kDwCh + j] = acc[j];
+    __syncthreads();
+    if (part == 0 && k < K) {
+#pragma unroll
+      for (int j = 0; j < kDwCh; ++j) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < kDwParts; ++q) v += red[(q * 128 + tk) * kDwCh + j];   // fixed order
+        if (c0 + j < C) dW[static_cast<int64_t>(c0 + j) * K + k] = static_cast<float>(v);
+      }
     }
   }
 }
@@ -1389,14 +1421,15 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     launches += 6;
     if (last.grad_weight) {
       const int64_t ck = static_cast<int64_t>(C) * K;
-      const size_t dw_smem = sizeof(float) * kDwCh * (K + 2 * static_cast<size_t>(B));
+      const size_t dw_smem = sizeof(float) * ((kDwCh * (K + 2 * static_cast<size_t>(B)) + 3) & ~static_cast<size_t>(3)) +
+                             sizeof(double) * kDwParts * 128 * kDwCh;
       PCUDA_REQUIRE(dw_smem <= 200 * 1024, PCUDA_E_UNSUPPORTED, "pointmlp_bwd: batch %d too large for the pooled wgrad kernel", B);
       static bool dw_attr_done = false;
       if (!dw_attr_done) {
         cudaFuncSetAttribute(pool_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         dw_attr_done = true;
       }
-      pool_dw_kernel<<<(C + kDwCh - 1) / kDwCh, 128, dw_smem, st>>>(src, last.weight, w.coef, pool_arg, ka, w.abar, w.Ghat, B, N, C, train, last.grad_weight);
+      pool_dw_kernel<<<(C + kDwCh - 1) / kDwCh, 128 * kDwParts, dw_smem, st>>>(src, last.weight, w.coef, pool_arg, ka, w.abar, w.Ghat, B, N, C, train, last.grad_weight);
       launches += 1;
     }
     if (L >= 2 || grad_x) {

@@ -68,6 +68,17 @@ class GradBucket:
         if vs:
             torch._foreach_add_(vs, gs)
 
+    def assign_sum(self, grads_a: Sequence[Optional[torch.Tensor]], grads_b: Sequence[Optional[torch.Tensor]]) -> None:
+        """bucket = grads_a + grads_b in two multi-tensor launches (no zero fill) when both lists are
+        complete; otherwise zero + accumulate."""
+        if any(g is None for g in grads_a) or any(g is None for g in grads_b):
+            self.zero()
+            self.accumulate(grads_a)
+            self.accumulate(grads_b)
+            return
+        torch._foreach_copy_(self.views, [g.reshape(v.shape) for v, g in zip(self.views, grads_a)])
+        torch._foreach_add_(self.views, [g.reshape(v.shape) for v, g in zip(self.views, grads_b)])
+
     def gather_grads(self) -> None:
         """Copy .grad tensors that are not already views of the bucket into it."""
         for p, v in zip(self.params, self.views):

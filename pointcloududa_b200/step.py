@@ -121,8 +121,7 @@ class AdversarialStep:
         s1, s2 = self._side if self.concurrent else (main, main)
         sink_p2, sink_p3, sink_p4 = [], [], []
 
-        # P0: zero D4's gradients (they live in the flat bucket)
-        self.bucket.zero()
+        # (D4's gradients live in the flat bucket; it is overwritten at the join)
         if self.concurrent:
             s1.wait_stream(main)
             s2.wait_stream(main)
@@ -184,8 +183,7 @@ class AdversarialStep:
                 for t in crossing:
                     if t is not None:
                         t.record_stream(main)
-        self.bucket.accumulate(grads_s)
-        self.bucket.accumulate(grads_t)
+        self.bucket.assign_sum(grads_s, grads_t)
         apply_bn_updates([sink_p2, sink_p3, sink_p4])
         self._res = [loss_seg3.detach(), loss_vert_target.detach(), ent_mean.detach(), loss_adv_point.detach(),
                      loss_D_same4.detach(), loss_D_diff_4.detach(), acc_s, acc_t]

@@ -11,7 +11,7 @@ from pointcloududa_b200.synth import synth_clouds  # noqa: E402
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 dev = "cuda:0"
 if which in ("all", "entropy"):
-    for fast in (0, 1):
+    for fast in (0,):
         ops.tune(0, fast)
         z = torch.randn(256, 5, 256, 256, device=dev) * 3
         g = torch.randn_like(z)
@@ -30,7 +30,7 @@ if which in ("all", "chamfer"):
     for B, N in ((64, 4096), (64, 16384)):
         x, y = synth_clouds(B, N, seed=5, mode="near")
         x, y = x.to(dev), y.to(dev)
-        for var in (0, 104128):
+        for var in (0,):
             ops.tune(1, var)
             for _ in range(2):
                 ops.chamfer_nn(x, y)
