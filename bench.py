@@ -162,9 +162,16 @@ def run_cpu_baseline(w: dict, budget_s: float, min_steps: int = 2, max_steps: in
 
 
 # ------------------------------------------------------------------------------------------------
+def _splits(w):
+    m = w["B"] * w["N"]
+    return max(1, min(2 * 148, (m + 127) // 128))
+
+
 KERNEL_WORK = {
-    # kernel-name fragment -> (bound, algorithmic work per launch as a function of the per-rank workload)
-    # default D4 (3->64->128->1024 twice: STN3d trunk and main trunk), M = B*N points
+    # kernel-name fragment -> (bound, algorithmic work per launch as a function of the per-rank workload):
+    # FLOPs for the tcgen05 GEMMs, compulsory HBM bytes (every operand once, every result once) for the rest.
+    # default D4 (3->64->128->1024 twice: STN3d trunk and main trunk), M = B*N points, C = 1024, K = 128;
+    # where one kernel serves several layer shapes the widest is taken (an upper bound of the work).
     "ws_kernel<1>": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 128 * 1024),     # pooled 128->1024 GEMM (tcgen05)
     "ws_kernel<0>": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 64 * 128),       # dense 64->128 GEMM
     "ws_kernel<2>": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 128 * 64),       # dgrad 128->64
@@ -173,17 +180,56 @@ KERNEL_WORK = {
     "entropy_fwd": ("hbm", lambda w: (8.0 + (4.0 if w["return_prob"] else 0.0)) * w["B"] * w["C"] * w["H"] * w["W"]),
     "entropy_bwd": ("hbm", lambda w: 12.0 * w["B"] * w["C"] * w["H"] * w["W"]),
     "chamfer_nn": ("hbm", lambda w: 48.0 * w["B"] * w["N"]),                      # 24 B/point in + out, both clouds
+    "chamfer_bwd": ("hbm", lambda w: 36.0 * 2 * w["B"] * w["N"]),
     "pack_act_kernel": ("hbm", lambda w: (4.0 + 2.0) * w["B"] * w["N"] * 128),    # fp32 in, bf16 out (widest layer)
+    "pack_dy_kernel": ("hbm", lambda w: (8.0 + 2.0) * w["B"] * w["N"] * 128),     # dz and y in, bf16 out
+    "pack_w_kernel": ("hbm", lambda w: (4.0 + 2.0) * 1024 * 128),
     # sparse rows of the pooled-layer dgrad: arg/coef, one W row per (cloud, channel), read-modify-write of the
     # <= min(C, N) selected points per cloud (y_prev, dz_prev in, dz_prev out), K = 128, C = 1024
     "pool_sparse_kernel": ("hbm", lambda w: w["B"] * 1024 * (8.0 + 4.0 * 128) + w["B"] * min(1024, w["N"]) * 128 * 12.0),
     "pool_dw_kernel": ("hbm", lambda w: 1024 * 128 * 8.0 + 128 * 128 * 4.0 + w["B"] * 1024 * (8.0 + 4.0 * 128)),
+    "pool_sel_kernel": ("hbm", lambda w: w["B"] * 1024 * (4.0 * 128 + 24.0) + 1024 * 128 * 4.0),   # selected rows + W + out/arg/grad/coef
+    "pool_coef_kernel": ("hbm", lambda w: w["B"] * 1024 * 8.0 + 1024 * 28.0),
+    "pool_q_kernel": ("hbm", lambda w: 1024 * 128 * 4.0 + 1024 * 4.0 + 8 * 128 * 128 * 4.0),       # W, kappa in, split partials out
+    "pool_u_kernel": ("hbm", lambda w: 1024 * 128 * 4.0 + 128 * 128 * 4.0 + 1024 * 4.0 + 1024.0),
+    "pool_finalize_kernel": ("hbm", lambda w: w["B"] * 1024 * 16.0),
+    "act_colsum_kernel": ("hbm", lambda w: 4.0 * w["B"] * w["N"] * 128),
+    "abar_kernel": ("hbm", lambda w: _splits(w) * 128 * 8.0),
+    "gram_center_kernel": ("hbm", lambda w: 128 * 128 * 12.0),
+    "reduce_partials_kernel": ("hbm", lambda w: (_splits(w) + 1) * 1024 * 128 * 4.0),              # widest: dW of the pooled layer
+    "mlp_fwd_narrow_kernel": ("hbm", lambda w: (12.0 + 4.0 * 64) * w["B"] * w["N"]),               # 3 -> 64: cloud in, y out
+    "wgrad_narrow_kernel": ("hbm", lambda w: (12.0 + 8.0 * 64) * w["B"] * w["N"]),
+    "dgrad_input_narrow_kernel": ("hbm", lambda w: (8.0 * 64 + 12.0) * w["B"] * w["N"]),
+    "bn_finalize_pivot_kernel": ("hbm", lambda w: 1024 * 40.0),
+    "bn_bwd_coef_kernel": ("hbm", lambda w: 1024 * 44.0),
+    "bn_running_update": ("hbm", lambda w: 3968 * 3 * 16.0),
     "fc_fwd_kernel": ("hbm", lambda w: 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) / 3 + 4.0 * w["B"] * (1024 + 512)),   # mean layer of a head
     "fc_bwd_kernel": ("hbm", lambda w: 2 * 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) / 3 + 4.0 * w["B"] * (1024 + 512)),
+    "fc_pull_kernel": ("hbm", lambda w: 4.0 * 512 * 1024 + 4.0 * w["B"] * (1024 + 512)),
+    "sgd": ("hbm", lambda w: 1.6e6 * 16.0),
 }
 
 
-def kernel_profile(step, w: dict, pk: dict, reps: int = 5, record: bool = True):
+def ncu_traffic(workload: str, kernel_short: str):
+    """DRAM bytes per launch of `kernel_short` from the committed ncu pass over this workload's step
+    (profiles/traffic_<workload>.json, written by tools/ncu_traffic.py from `ncu --metrics
+    dram__bytes_read.sum,dram__bytes_write.sum`); None when the file or the kernel is absent."""
+    path = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
+    if not os.path.exists(path):
+        return None, None
+    try:
+        with open(path) as f:
+            d = json.load(f)
+    except Exception:
+        return None, None
+    base = kernel_short.replace("pcuda::", "").replace("tc::", "")
+    for k, v in d.get("kernels", {}).items():
+        if k == base or k.endswith(base) or base.endswith(k):
+            return v.get("dram_bytes_per_launch"), f"profiles/traffic_{workload}.json ({d.get('source', 'ncu')})"
+    return None, None
+
+
+def kernel_profile(step, w: dict, pk: dict, reps: int = 5, record: bool = True, workload: str = ""):
     """Per-kernel device time of the (graph-replayed) step from CUPTI activity records, taken live in
     this process right after the timed region: which kernel dominates, and its roofline.
     Every rank must call this (the step holds the gradient all-reduce); only `record` ranks profile."""
@@ -230,7 +276,7 @@ def kernel_profile(step, w: dict, pk: dict, reps: int = 5, record: bool = True):
             break
     else:
         roof.update({"bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None})
-    roof["traffic"] = None
+    roof["traffic"], roof["traffic_source"] = ncu_traffic(workload, short(dom_name))
     roof["peak_source"] = pk["source"]
     roof["note"] = ("dominant libpcuda kernel of the graph-replayed step at this workload (CUPTI device durations, warm L2); "
                     "at cfg2 sizes (2400 points per call) every kernel is latency-bound - `large` holds the roofline-sized shapes")
@@ -329,13 +375,24 @@ def large_shape_rooflines(flush, pk: dict):
         x, y = x.to(dev), y.to(dev)
         t = time_op(lambda: ops.chamfer_nn(x, y), 5, flush)
         # not HBM-bound by construction (24 B per point in + out): the binding resource is the FP32 pipe.
-        # 5 IEEE operations per ordered pair (mul, 2 fma, add, fma), issued two pairs per packed instruction;
-        # peak = SMs x 128 lanes x max SM clock
+        # The prefiltered kernel issues 3 packed FFMA2 per two ordered pairs (3 lane-operations per pair) and
+        # re-evaluates the reference's 5-operation formula only for pairs that can still lower a running
+        # minimum; peak = SMs x 128 FP32 lanes x max SM clock.  `exact_formula_ceiling_tpairs_s` is what a
+        # kernel that evaluates all 5 operations for every pair could reach at 100 % lane utilisation.
         pairs = 2.0 * B * N * N
         lane_peak = ops.sm_count() * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6
-        res[f"chamfer_fwd_B{B}_N{N}"] = dict(ms=t, tpairs_s=pairs / t / 1e9, hbm_gbs=48.0 * B * N / t / 1e6,
-                                             fp32_lane_ops_per_s=5.0 * pairs / (t * 1e-3),
-                                             frac_fp32_lanes=5.0 * pairs / (t * 1e-3) / lane_peak)
+        ent = dict(ms=t, tpairs_s=pairs / t / 1e9, hbm_gbs=48.0 * B * N / t / 1e6,
+                   fp32_lane_ops_per_s=3.0 * pairs / (t * 1e-3),
+                   frac_fp32_lanes=3.0 * pairs / (t * 1e-3) / lane_peak,
+                   exact_formula_ceiling_tpairs_s=lane_peak / 5.0 / 1e12)
+        # the exact packed kernel (every pair through the 5-operation formula) for comparison
+        ops.tune(1, 200000 + (4128 if N >= 4096 else 0))
+        try:
+            t2 = time_op(lambda: ops.chamfer_nn(x, y), 3, flush)
+        finally:
+            ops.tune(1, 0)
+        ent["exact_kernel"] = dict(ms=t2, tpairs_s=pairs / t2 / 1e9, frac_fp32_lanes=5.0 * pairs / (t2 * 1e-3) / lane_peak)
+        res[f"chamfer_fwd_B{B}_N{N}"] = ent
     from pointcloududa_b200.networks.PointNetCls import PointNetCls
     net = PointNetCls().to(dev).train()
     pts = torch.rand(32, 4096, 3, device=dev).transpose(2, 1)
@@ -477,7 +534,7 @@ def run_ours(args):
     # kernel-level profile of the step: collective inside, so every rank runs the steps; rank 0 records
     kernel_shares, roof = None, None
     try:
-        kernel_shares, roof = kernel_profile(step, w, pk, record=(rank == 0))
+        kernel_shares, roof = kernel_profile(step, w, pk, record=(rank == 0), workload=args.workload)
     except Exception as e:       # CUPTI unavailable: keep the op-level roofline
         kernel_shares = {"error": repr(e)}
         if rank == 0 and world > 1:

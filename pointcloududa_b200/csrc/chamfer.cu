@@ -300,6 +300,187 @@ chamfer_nn2_kernel(const float* __restrict__ x, const float* __restrict__ y, int
   }
 }
 
+// ---- v3: conservative 3-FMA prefilter in front of the exact evaluation ------------------------------
+// Only candidates that can still lower a row's running minimum need the reference's exact arithmetic.
+// With n = -2*a (exact) the chain
+//     Q = fma(n2,c2, fma(n1,c1, fma(n0,c0, r_c)))          ~  r_c - 2 a.c  =  P - r_a
+// costs 3 packed FFMA2 per two candidates instead of the 5 packed operations of the exact formula, and
+//     |P - (r_a + Q)| <= 13 u (r_a + r_c),  u = 2^-24
+// (3 roundings in Q: 3.1u(r_a + 2 r_c); 5 in P: 6.1u(r_a + r_c); Cauchy-Schwarz for sum|a_k c_k|).  A pair
+// is skipped iff  Q >= thr_a := (bestP_a - r_a) + 2^-19 (r_a + max_tile r_c) + 1e-36  (rounded up), which
+// implies P >= bestP_a, i.e. the exact scan would not have touched its state either.  Everything else —
+// including every NaN, the test is !(Q >= thr) — takes the slow path: the exact expression of v2 and
+// the same update rule, so distances and indices are bit-identical to the scalar kernel by construction.
+// The slow path is entered per thread and per row; a row sees ~ln N new minima over a whole scan.
+constexpr float kFilterMargin = 1.9073486328125e-06f;   // 2^-19  (> (13 + rounding of thr) * 2^-24)
+constexpr float kFilterAbs = 1e-36f;                    // covers underflow in the products
+
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M,
+                   float* __restrict__ d1, int64_t* __restrict__ i1, float* __restrict__ d2,
+                   int64_t* __restrict__ i2, FwdWs* __restrict__ ws, float* __restrict__ loss,
+                   int tiles_x, int tiles_y, int B) {
+  __shared__ float4 tileA[kTileJ / 2];
+  __shared__ float4 tileB[kTileJ / 2];
+  __shared__ float warp_rmax[THREADS / 32];
+  __shared__ double warp_part[THREADS / 32];
+
+  const int dir = blockIdx.z;
+  const int b = blockIdx.y;
+  const int nq = dir == 0 ? N : M;
+  const int nc = dir == 0 ? M : N;
+  const int tiles_q = dir == 0 ? tiles_x : tiles_y;
+  const bool active_block = static_cast<int>(blockIdx.x) < tiles_q;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  const float* __restrict__ qbase = (dir == 0 ? x : y) + static_cast<int64_t>(b) * nq * 3;
+  const float* __restrict__ cbase = (dir == 0 ? y : x) + static_cast<int64_t>(b) * nc * 3;
+  float* __restrict__ dout = (dir == 0 ? d1 : d2) + static_cast<int64_t>(b) * nq;
+  int64_t* __restrict__ iout = (dir == 0 ? i1 : i2) + static_cast<int64_t>(b) * nq;
+
+  double my_sum = 0.0;
+  if (active_block) {
+    float2 n0[R], n1[R], n2[R];          // (-2a_k, -2a_k)
+    float rq[R], thr[R], bestP[R], bestD[R];
+    int bestI[R];
+    const int row0 = blockIdx.x * (THREADS * R) + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r * THREADS;
+      const int rr = row < nq ? row : nq - 1;
+      const float a0 = __ldg(qbase + rr * 3 + 0);
+      const float a1 = __ldg(qbase + rr * 3 + 1);
+      const float a2 = __ldg(qbase + rr * 3 + 2);
+      rq[r] = norm3(a0, a1, a2);
+      n0[r] = make_float2(-2.0f * a0, -2.0f * a0);
+      n1[r] = make_float2(-2.0f * a1, -2.0f * a1);
+      n2[r] = make_float2(-2.0f * a2, -2.0f * a2);
+      bestP[r] = INFINITY;
+      bestD[r] = INFINITY;
+      bestI[r] = 0;
+      thr[r] = INFINITY;
+    }
+    const float2 neg2 = make_float2(-2.0f, -2.0f);
+
+    for (int j0 = 0; j0 < nc; j0 += kTileJ) {
+      const int tj = min(kTileJ, nc - j0);
+      const int npair = (tj + 1) >> 1;
+      __syncthreads();
+      float lmax = 0.0f;
+      // A tile whose candidates are all bitwise identical (the reference's all-zero GT cloud of an empty
+      // slice, npy2point.py:72,115) yields one P per row: only its first column can win under the
+      // first-index rule, so the scan below visits one column pair instead of tying tj times.
+      const uint32_t f0 = __float_as_uint(__ldg(cbase + j0 * 3 + 0)), f1 = __float_as_uint(__ldg(cbase + j0 * 3 + 1)),
+                     f2 = __float_as_uint(__ldg(cbase + j0 * 3 + 2));
+      bool same = true;
+      for (int t = threadIdx.x; t < npair; t += THREADS) {
+        const int ja = j0 + 2 * t;
+        const bool has_b = (2 * t + 1) < tj;
+        const float xa = __ldg(cbase + ja * 3 + 0), ya = __ldg(cbase + ja * 3 + 1), za = __ldg(cbase + ja * 3 + 2);
+        // odd tail: a sentinel column whose Q and P are +inf can never be selected
+        const float xb = has_b ? __ldg(cbase + ja * 3 + 3) : 0.0f;
+        const float yb = has_b ? __ldg(cbase + ja * 3 + 4) : 0.0f;
+        const float zb = has_b ? __ldg(cbase + ja * 3 + 5) : 0.0f;
+        const float ra = norm3(xa, ya, za);
+        const float rb = has_b ? norm3(xb, yb, zb) : INFINITY;
+        tileA[t] = make_float4(xa, xb, ya, yb);
+        tileB[t] = make_float4(za, zb, ra, rb);
+        // a NaN norm never enters the bound: that column's own Q is NaN and takes the slow path
+        lmax = fmaxf(lmax, ra);
+        if (has_b) lmax = fmaxf(lmax, rb);
+        same = same && __float_as_uint(xa) == f0 && __float_as_uint(ya) == f1 && __float_as_uint(za) == f2 &&
+               (!has_b || (__float_as_uint(xb) == f0 && __float_as_uint(yb) == f1 && __float_as_uint(zb) == f2));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+      if (lane == 0) warp_rmax[wid] = lmax;
+      const int scan_pairs = __syncthreads_and(same) ? 1 : npair;
+      float rmax = warp_rmax[0];
+#pragma unroll
+      for (int i = 1; i < THREADS / 32; ++i) rmax = fmaxf(rmax, warp_rmax[i]);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        thr[r] = __fadd_ru(__fsub_ru(bestP[r], rq[r]),
+                           __fadd_ru(__fmul_ru(kFilterMargin, __fadd_ru(rq[r], rmax)), kFilterAbs));
+#pragma unroll 2
+      for (int t = 0; t < scan_pairs; ++t) {
+        const float4 A = tileA[t];
+        const float4 Bv = tileB[t];
+        const float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w);
+        const float2 cz = make_float2(Bv.x, Bv.y), cr = make_float2(Bv.z, Bv.w);
+        float2 Q[R];
+        bool hit = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          Q[r] = __ffma2_rn(n2[r], cz, __ffma2_rn(n1[r], cy, __ffma2_rn(n0[r], cx, cr)));
+          hit = hit || !(Q[r].x >= thr[r]) || !(Q[r].y >= thr[r]);
+        }
+        if (hit) {
+          const int j = j0 + 2 * t;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (!(Q[r].x >= thr[r]) || !(Q[r].y >= thr[r])) {
+              // the reference's arithmetic, exactly as in v2 (a = -0.5 * (-2a) is exact).  The factor is
+              // laundered so the compiler cannot hoist the unscaled rows out of the scan (12 more
+              // registers per thread, i.e. spills or a lost CTA per SM).
+              float h = -0.5f;
+              asm volatile("" : "+f"(h));
+              const float2 negh = make_float2(h, h);
+              const float2 q0 = __fmul2_rn(n0[r], negh), q1 = __fmul2_rn(n1[r], negh), q2 = __fmul2_rn(n2[r], negh);
+              const float2 zz = __ffma2_rn(q2, cz, __ffma2_rn(q1, cy, __fmul2_rn(q0, cx)));
+              const float2 P = __ffma2_rn(neg2, zz, __fadd2_rn(make_float2(rq[r], rq[r]), cr));
+              nn_update(P.x, j, bestP[r], bestD[r], bestI[r]);
+              nn_update(P.y, j + 1, bestP[r], bestD[r], bestI[r]);
+              thr[r] = __fadd_ru(__fsub_ru(bestP[r], rq[r]),
+                                 __fadd_ru(__fmul_ru(kFilterMargin, __fadd_ru(rq[r], rmax)), kFilterAbs));
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r * THREADS;
+      if (row < nq) {
+        dout[row] = bestD[r];
+        iout[row] = bestI[r];
+        my_sum += static_cast<double>(bestD[r]);
+      }
+    }
+  }
+
+  if (loss == nullptr) return;
+  double w = warp_sum(my_sum);
+  if (lane == 0) warp_part[wid] = w;
+  __syncthreads();
+  __shared__ bool is_last;
+  const int tiles_max = gridDim.x;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) s += warp_part[i];
+    ws->partial[(static_cast<int64_t>(dir) * B + b) * tiles_max + blockIdx.x] = s;
+    __threadfence();
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    is_last = atomicAdd(&ws->ticket, 1u) == total - 1;
+  }
+  __syncthreads();
+  if (is_last && wid == 0) {
+    __threadfence();
+    double acc = 0.0;
+    const int64_t n_part = static_cast<int64_t>(2) * B * tiles_max;
+    const volatile double* part = ws->partial;
+    for (int64_t k = lane; k < n_part; k += 32) acc += part[k];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      *loss = static_cast<float>(acc / (static_cast<double>(N) * static_cast<double>(B)));
+      ws->ticket = 0u;
+      __threadfence();
+    }
+  }
+}
+
 // ---- backward ---------------------------------------------------------------------------------
 // Pass 1 (scatter): many-to-one terms, accumulated as 64-bit fixed point so the sum is exact
 // and order-independent.  Pass 2 (finalise): one-to-one term + conversion + scale.
@@ -362,7 +543,7 @@ Plan make_plan(int B, int N, int M) {
   Plan p{1, 64, 0, 0};
   for (int k = (forced > 0 ? 0 : 1); k < 5; ++k) {
     const int R = cand[k][0], T = cand[k][1];
-    if (forced >= 100000 && R == 8) continue;  // the scalar kernel has no 8-row instantiation
+    if (forced / 100000 == 1 && R == 8) continue;  // the scalar kernel has no 8-row instantiation
     const int tx = (N + R * T - 1) / (R * T), ty = (M + R * T - 1) / (R * T);
     p = Plan{R, T, tx, ty};
     if (forced > 0) {
@@ -410,25 +591,35 @@ extern "C" int pcuda_chamfer_fwd(const float* x, const float* y, int B, int N, i
 #define PCUDA_LAUNCH_NN(RR, TT)                                                              \
   chamfer_nn_kernel<RR, TT><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,        \
                                                  p.tiles_x, p.tiles_y, B)
+#define PCUDA_LAUNCH_NN3(RR, TT)                                                             \
+  chamfer_nn3_kernel<RR, TT><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,       \
+                                                  p.tiles_x, p.tiles_y, B)
 #define PCUDA_LAUNCH_NN2(RR, TT)                                                             \
   chamfer_nn2_kernel<RR, TT><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,       \
                                                   p.tiles_x, p.tiles_y, B)
-  // tuning value >= 100000 selects the scalar (v1) kernel for A/B runs
-  const bool scalar_variant = tuning(TUNE_CHAMFER_ROWS) >= 100000;
-  if (scalar_variant) {
+  // tuning value >= 200000 selects the packed exact kernel (v2), >= 100000 the scalar one (v1), for A/B runs
+  const int variant = tuning(TUNE_CHAMFER_ROWS) / 100000;
+  if (variant == 1) {
     if (p.R >= 4) PCUDA_LAUNCH_NN(4, 128);
     else if (p.R == 2) PCUDA_LAUNCH_NN(2, 128);
     else if (p.threads == 128) PCUDA_LAUNCH_NN(1, 128);
     else PCUDA_LAUNCH_NN(1, 64);
-  } else {
+  } else if (variant == 2) {
     if (p.R == 8) PCUDA_LAUNCH_NN2(8, 128);
     else if (p.R == 4) PCUDA_LAUNCH_NN2(4, 128);
     else if (p.R == 2) PCUDA_LAUNCH_NN2(2, 128);
     else if (p.threads == 128) PCUDA_LAUNCH_NN2(1, 128);
     else PCUDA_LAUNCH_NN2(1, 64);
+  } else {
+    if (p.R == 8) PCUDA_LAUNCH_NN3(8, 128);
+    else if (p.R == 4) PCUDA_LAUNCH_NN3(4, 128);
+    else if (p.R == 2) PCUDA_LAUNCH_NN3(2, 128);
+    else if (p.threads == 128) PCUDA_LAUNCH_NN3(1, 128);
+    else PCUDA_LAUNCH_NN3(1, 64);
   }
 #undef PCUDA_LAUNCH_NN
 #undef PCUDA_LAUNCH_NN2
+#undef PCUDA_LAUNCH_NN3
   count_launch(1);
   return check_launch("chamfer_nn_kernel");
 }

@@ -681,19 +681,24 @@ pool_u_kernel(const float* __restrict__ W, const float* __restrict__ alpha, cons
 //   dz_prev[m, :] += mask(m, :) * S[m, :]     and the dbeta / dgamma sums of the previous layer likewise
 // (or grad_x[b, :, n] += S[m, :] when the previous "layer" is the network input).
 // Only <= C points per cloud are touched, so this is a few MB of traffic next to the GEMM's epilogue,
-// which no longer gathers anything.  grid (B, parts), 512 threads; dynamic smem: max(C + N ints,
-// 2 * 16 * K floats).  A warp owns a head channel (the lowest channel selecting a point — one writer per
-// point, no atomics on dz_prev), finds the other channels selecting the same point with ballots over
-// the shared-memory copy of arg, and sums their rows.
-template <int KPL>   // output columns per lane: 4 (K <= 128) or 16 (K <= 512)
+// which no longer gathers anything.  grid (B, parts), 512 threads; dynamic smem: C + N ints, then one
+// uint16 match list of C entries per warp (re-used for the final reduction).  A warp owns a head channel
+// (the lowest channel selecting a point — one writer per point, no atomics on dz_prev).  It first compacts
+// the channels selecting the same point into its list with ballots over the shared-memory copy of arg
+// (no global access), then streams their rows of W with kSparseInFlight independent 128-bit loads in
+// flight: a popular point (at N = 300 some are selected by > 100 of the 1024 channels) costs
+// m / kSparseInFlight memory round trips instead of one per 32-channel group.
+template <int KPL>   // output columns per lane: 4 (K <= 128) or 16 (K <= 512); lane owns [KPL*lane, KPL*lane + KPL)
 __global__ void __launch_bounds__(512)
 pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ coef, const float* __restrict__ W,
                    int C, int N, int K, DgradOut o) {
+  constexpr int kSparseInFlight = 32 / KPL;      // 32 registers of W rows in flight per lane
   extern __shared__ int sm_i[];
   int* sarg = sm_i;
   int* first = sm_i + C;
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  uint16_t* lst = reinterpret_cast<uint16_t*>(sm_i + C + N) + static_cast<size_t>(warp) * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x)
     sarg[c] = coef[static_cast<int64_t>(b) * C + c] != 0.f ? arg[static_cast<int64_t>(b) * C + c] : -1;
   for (int n = threadIdx.x; n < N; n += blockDim.x) first[n] = 0x7fffffff;
@@ -702,6 +707,10 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
     if (sarg[c] >= 0) atomicMin(&first[sarg[c]], c);
   __syncthreads();
   const bool to_x = o.grad_x != nullptr;
+  const int k0 = KPL * lane;
+  // rows of W / dz_prev / y_prev are 16-byte aligned runs
+  const bool vec = (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(o.y_prev) |
+                                     reinterpret_cast<uintptr_t>(o.dz_prev)) & 15u) == 0;
   float ws[KPL], wq[KPL];                        // this warp's share of the previous layer's dbeta / dgamma sums
 #pragma unroll
   for (int jj = 0; jj < KPL; ++jj) { ws[jj] = 0.f; wq[jj] = 0.f; }
@@ -709,71 +718,97 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
   for (int c = blockIdx.y * nwarp + warp; c < C; c += stride) {
     const int a = sarg[c];
     if (a < 0 || first[a] != c) continue;      // warp-uniform
+    // pass 1: the channels selecting point a, ascending, into this warp's list
+    int m = 0;
+    for (int c0 = c & ~31; c0 < C; c0 += 32) {
+      const int cc = c0 + lane;
+      const bool hit = cc >= c && cc < C && sarg[cc] == a;
+      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      if (hit) lst[m + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint16_t>(cc);
+      m += __popc(mask);
+    }
+    __syncwarp();
+    // pass 2: S = sum coef * W[row, :], rows in ascending order, kSparseInFlight rows loaded before the first use
     float acc[KPL];
 #pragma unroll
     for (int jj = 0; jj < KPL; ++jj) acc[jj] = 0.f;
-    for (int c0 = c & ~31; c0 < C; c0 += 32) {
-      const int cc = c0 + lane;
-      unsigned mask = __ballot_sync(0xffffffffu, cc >= c && cc < C && sarg[cc] == a);
-      while (mask) {
-        // up to 4 matching channels in flight; they are accumulated in ascending order (deterministic)
-        int cs[4];
+    for (int i = 0; i < m; i += kSparseInFlight) {
+      float cf[kSparseInFlight];
+      float wv[kSparseInFlight][KPL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          cs[u] = mask ? c0 + __ffs(mask) - 1 : -1;
-          mask &= mask - 1;
-        }
-        if (KPL <= 4) {
-          // all loads of the (up to) 4 channels are issued before the first use
-          float cf[4], wv[4][KPL];
+      for (int u = 0; u < kSparseInFlight; ++u) {
+        const int cs = i + u < m ? static_cast<int>(lst[i + u]) : -1;
+        cf[u] = cs >= 0 ? coef[static_cast<int64_t>(b) * C + cs] : 0.f;
+        const float* wr = W + static_cast<int64_t>(cs >= 0 ? cs : 0) * K + k0;
+        if (vec) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            cf[u] = cs[u] >= 0 ? coef[static_cast<int64_t>(b) * C + cs[u]] : 0.f;
-#pragma unroll
-            for (int jj = 0; jj < KPL; ++jj)
-              wv[u][jj] = (cs[u] >= 0 && lane + 32 * jj < K) ? W[static_cast<int64_t>(cs[u]) * K + lane + 32 * jj] : 0.f;
+          for (int v = 0; v < KPL / 4; ++v) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cs >= 0 && k0 + 4 * v < K) t = __ldg(reinterpret_cast<const float4*>(wr) + v);
+            wv[u][4 * v + 0] = t.x; wv[u][4 * v + 1] = t.y; wv[u][4 * v + 2] = t.z; wv[u][4 * v + 3] = t.w;
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int jj = 0; jj < KPL; ++jj) acc[jj] = fmaf(cf[u], wv[u][jj], acc[jj]);
         } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (cs[u] < 0) continue;               // warp-uniform
-            const float cf = coef[static_cast<int64_t>(b) * C + cs[u]];
-#pragma unroll
-            for (int jj = 0; jj < KPL; ++jj)
-              if (lane + 32 * jj < K) acc[jj] = fmaf(cf, W[static_cast<int64_t>(cs[u]) * K + lane + 32 * jj], acc[jj]);
-          }
+          for (int jj = 0; jj < KPL; ++jj) wv[u][jj] = (cs >= 0 && k0 + jj < K) ? __ldg(wr + jj) : 0.f;
         }
       }
+#pragma unroll
+      for (int u = 0; u < kSparseInFlight; ++u)
+#pragma unroll
+        for (int jj = 0; jj < KPL; ++jj) acc[jj] = fmaf(cf[u], wv[u][jj], acc[jj]);
     }
-    const int64_t m = static_cast<int64_t>(b) * N + a;
+    __syncwarp();                                 // the list is rewritten for the next head
+    const int64_t mrow = static_cast<int64_t>(b) * N + a;
     if (to_x) {
 #pragma unroll
       for (int jj = 0; jj < KPL; ++jj) {
-        const int k = lane + 32 * jj;
+        const int k = k0 + jj;
         if (k < K) o.grad_x[(static_cast<int64_t>(b) * K + k) * N + a] += acc[jj];
       }
     } else {
       float yv[KPL], dv[KPL];
+      if (vec) {
 #pragma unroll
-      for (int jj = 0; jj < KPL; ++jj) {
-        const int k = lane + 32 * jj;
-        yv[jj] = k < K ? o.y_prev[m * K + k] : 0.f;
-        dv[jj] = k < K ? o.dz_prev[m * K + k] : 0.f;
+        for (int v = 0; v < KPL / 4; ++v) {
+          float4 ty = make_float4(0.f, 0.f, 0.f, 0.f), td = ty;
+          if (k0 + 4 * v < K) {
+            ty = *(reinterpret_cast<const float4*>(o.y_prev + mrow * K + k0) + v);
+            td = *(reinterpret_cast<const float4*>(o.dz_prev + mrow * K + k0) + v);
+          }
+          yv[4 * v + 0] = ty.x; yv[4 * v + 1] = ty.y; yv[4 * v + 2] = ty.z; yv[4 * v + 3] = ty.w;
+          dv[4 * v + 0] = td.x; dv[4 * v + 1] = td.y; dv[4 * v + 2] = td.z; dv[4 * v + 3] = td.w;
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < KPL; ++jj) {
+          const int k = k0 + jj;
+          yv[jj] = k < K ? o.y_prev[mrow * K + k] : 0.f;
+          dv[jj] = k < K ? o.dz_prev[mrow * K + k] : 0.f;
+        }
       }
 #pragma unroll
       for (int jj = 0; jj < KPL; ++jj) {
-        const int k = lane + 32 * jj;
-        if (k >= K) continue;
-        const float yh = (yv[jj] - o.mean[k]) * o.invstd[k];
-        const bool on = !o.relu || fmaf(yh, o.gamma[k], o.beta[k]) > 0.f;
-        const float v = on ? acc[jj] : 0.f;
-        o.dz_prev[m * K + k] = dv[jj] + v;
-        ws[jj] += v;
-        wq[jj] = fmaf(v, yh, wq[jj]);
+        const int k = k0 + jj;
+        float v = 0.f;
+        if (k < K) {
+          const float yh = (yv[jj] - o.mean[k]) * o.invstd[k];
+          const bool on = !o.relu || fmaf(yh, o.gamma[k], o.beta[k]) > 0.f;
+          v = on ? acc[jj] : 0.f;
+          ws[jj] += v;
+          wq[jj] = fmaf(v, yh, wq[jj]);
+        }
+        dv[jj] += v;
+      }
+      if (vec) {
+#pragma unroll
+        for (int v = 0; v < KPL / 4; ++v)
+          if (k0 + 4 * v < K)
+            *(reinterpret_cast<float4*>(o.dz_prev + mrow * K + k0) + v) =
+                make_float4(dv[4 * v + 0], dv[4 * v + 1], dv[4 * v + 2], dv[4 * v + 3]);
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < KPL; ++jj)
+          if (k0 + jj < K) o.dz_prev[mrow * K + k0 + jj] = dv[jj];
       }
     }
   }
@@ -783,7 +818,7 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
   float* red = reinterpret_cast<float*>(sm_i);            // [2][nwarp][K]
 #pragma unroll
   for (int jj = 0; jj < KPL; ++jj) {
-    const int k = lane + 32 * jj;
+    const int k = k0 + jj;
     if (k < K) { red[warp * K + k] = ws[jj]; red[(nwarp + warp) * K + k] = wq[jj]; }
   }
   __syncthreads();
@@ -1434,8 +1469,10 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     }
     if (L >= 2 || grad_x) {
       const DgradOut o = dgrad_out(L - 2, dzbuf[cur]);
-      const size_t sparse_smem = std::max(sizeof(int) * (static_cast<size_t>(C) + N), sizeof(float) * 2 * 16 * static_cast<size_t>(K));
-      if (tc_on(precision, TC_POOL_DGRAD) && a_in && w.qpack && tc::pool_dgrad_fits(K) && sparse_smem <= 200 * 1024 && K <= 512) {
+      // C + N ints, one uint16 match list of C entries per warp (16 warps); re-used as [2][16][K] floats
+      const size_t sparse_smem = std::max(sizeof(int) * (static_cast<size_t>(C) + N) + sizeof(uint16_t) * 16 * static_cast<size_t>(C),
+                                          sizeof(float) * 2 * 16 * static_cast<size_t>(K));
+      if (tc_on(precision, TC_POOL_DGRAD) && a_in && w.qpack && tc::pool_dgrad_fits(K) && sparse_smem <= 200 * 1024 && K <= 512 && C <= 65535) {
         static bool attr_done = false;
         if (!attr_done) {
           cudaFuncSetAttribute(pool_sparse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1446,8 +1483,9 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
         if (int rc = tc::pack_w(w.Q, K, K, false, w.qpack, st)) return rc;
         if (int rc = tc::pool_dgrad(tl, a_in, K, w.qpack, w.u, o, st)) return rc;
         // ... then the <= C selected points per cloud get their sparse rows added (one warp per point)
-        // about one wave of 512-thread CTAs (4 resident per SM); every CTA repeats the O(C + N) prologue
-        const int parts = std::max(1, std::min((C + 15) / 16, (4 * sm_count() + B - 1) / B));
+        // about two 512-thread CTAs per SM and >= 4 channels per warp: every CTA repeats the O(C + N)
+        // prologue and ends with 2K fp64 atomics on the same addresses, so fewer, longer CTAs win
+        const int parts = std::max(1, std::min((C + 63) / 64, (2 * sm_count() + B - 1) / B));
         if (K <= 128) pool_sparse_kernel<4><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
         else pool_sparse_kernel<16><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
         launches += 1;

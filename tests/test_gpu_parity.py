@@ -138,8 +138,9 @@ def test_entropy_empty_and_errors():
 # ================================================================ Chamfer ==========================
 CH_CASES = ["near_b3_n64", "near_b2_n300", "uniform_b2_n257", "identical_dups_b2_n128",
             "zero_gt_b2_n96", "shifted_b2_n80"]
-# (tuning value) kernel variants: packed-FP32 R=1/64thr, 1, 2, 4, 8 rows; scalar R=4, R=1
-VARIANTS = [0, 1064, 1128, 2128, 4128, 8128, 104128, 101064]
+# (tuning value) kernel variants: prefiltered packed-FP32 (default) R=1/64thr, 1, 2, 4, 8 rows;
+# exact packed-FP32 (2xxxxx) R=4, 8, 1; scalar (1xxxxx) R=4, R=1
+VARIANTS = [0, 1064, 1128, 2128, 4128, 8128, 204128, 208128, 201064, 104128, 101064]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -201,6 +202,66 @@ def test_chamfer_vs_oracle(B, N, mode):
     assert np.array_equal(d1.cpu().numpy().view(np.int32), o["d1"].view(np.int32))
     assert np.array_equal(d2.cpu().numpy().view(np.int32), o["d2"].view(np.int32))
     assert abs(loss.item() - float(o["loss"])) <= 2e-6 * abs(float(o["loss"]))
+
+
+def _adversarial_clouds(kind, B, N, seed):
+    """Inputs that stress the prefilter's error bound: heavy cancellation (far from the origin), near-ties
+    within a few ulp, mixed magnitudes, exact duplicates."""
+    rs = np.random.RandomState(seed)
+    if kind == "offset100":
+        y = (100.0 + 0.05 * rs.randn(B, N, 3)).astype(np.float32)
+        x = (y[:, rs.permutation(N)] + 1e-3 * rs.randn(B, N, 3)).astype(np.float32)
+    elif kind == "offset1e4":
+        y = (1e4 + rs.randn(B, N, 3)).astype(np.float32)
+        x = (1e4 + rs.randn(B, N, 3)).astype(np.float32)
+    elif kind == "ulp_ties":
+        base = rs.rand(B, N // 4, 3).astype(np.float32)
+        y = np.concatenate([base, np.nextafter(base, np.float32(2)), np.nextafter(base, np.float32(-1)), base], axis=1)
+        y = y[:, rs.permutation(y.shape[1])]
+        x = y[:, rs.permutation(y.shape[1])].copy()
+        x[:, ::3] += np.float32(1e-7)
+    elif kind == "mixed_scale":
+        y = (rs.randn(B, N, 3) * np.exp(rs.uniform(-8, 8, (B, N, 1)))).astype(np.float32)
+        x = (rs.randn(B, N, 3) * np.exp(rs.uniform(-8, 8, (B, N, 1)))).astype(np.float32)
+    elif kind == "grid":
+        y = (rs.randint(0, 32, (B, N, 3)) / 255.0).astype(np.float32)
+        x = (rs.randint(0, 32, (B, N, 3)) / 255.0).astype(np.float32)
+    else:
+        raise ValueError(kind)
+    return np.ascontiguousarray(x), np.ascontiguousarray(y)
+
+
+@pytest.mark.parametrize("variant", [0, 4128, 8128, 1064])
+@pytest.mark.parametrize("kind", ["offset100", "offset1e4", "ulp_ties", "mixed_scale", "grid"])
+def test_chamfer_prefilter_adversarial_bit_exact(kind, variant):
+    """The conservative prefilter must never drop a candidate the exact scan would have taken."""
+    x, y = _adversarial_clouds(kind, 3, 1100, seed=11)
+    o = oracle.chamfer_fwd(x, y)
+    ops.tune(1, variant)
+    try:
+        loss, d1, i1, d2, i2 = ops.chamfer_nn(torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV))
+    finally:
+        ops.tune(1, 0)
+    assert np.array_equal(i1.cpu().numpy(), o["i1"]) and np.array_equal(i2.cpu().numpy(), o["i2"])
+    assert np.array_equal(d1.cpu().numpy().view(np.int32), o["d1"].view(np.int32))
+    assert np.array_equal(d2.cpu().numpy().view(np.int32), o["d2"].view(np.int32))
+
+
+def test_chamfer_prefilter_equals_exact_kernels_at_size():
+    """B=16, N=8192 (2.1 G ordered pairs): the prefiltered kernel, the exact packed kernel and the scalar
+    kernel return identical bits."""
+    x, y = synth_clouds(16, 8192, seed=83, mode="near")
+    xg, yg = x.to(DEV), y.to(DEV)
+    outs = []
+    for variant in (0, 204128, 104128):
+        ops.tune(1, variant)
+        try:
+            outs.append(ops.chamfer_nn(xg, yg))
+        finally:
+            ops.tune(1, 0)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
 
 
 def test_chamfer_unequal_sizes_kernel_level():
