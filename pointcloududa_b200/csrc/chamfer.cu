@@ -307,22 +307,50 @@ chamfer_nn2_kernel(const float* __restrict__ x, const float* __restrict__ y, int
 // costs 3 packed FFMA2 per two candidates instead of the 5 packed operations of the exact formula, and
 //     |P - (r_a + Q)| <= 13 u (r_a + r_c),  u = 2^-24
 // (3 roundings in Q: 3.1u(r_a + 2 r_c); 5 in P: 6.1u(r_a + r_c); Cauchy-Schwarz for sum|a_k c_k|).  A pair
-// is skipped iff  Q >= thr_a := (bestP_a - r_a) + 2^-19 (r_a + max_tile r_c) + 1e-36  (rounded up), which
-// implies P >= bestP_a, i.e. the exact scan would not have touched its state either.  Everything else —
-// including every NaN, the test is !(Q >= thr) — takes the slow path: the exact expression of v2 and
-// the same update rule, so distances and indices are bit-identical to the scalar kernel by construction.
-// The slow path is entered per thread and per row; a row sees ~ln N new minima over a whole scan.
+// is skipped iff  Q >= thr_a := (lim_a - r_a) + 2^-19 (r_a + max_tile r_c) + 1e-36  (rounded up), which
+// implies P >= lim_a.  lim_a = min(bestP_a, cap_a):
+//   * P >= bestP_a: the exact scan would not have touched its state either;
+//   * P >  cap_a, where cap_a = U_a + 2^-19 (|U_a| + eps) and U_a >= min_j P_aj is an upper bound of the
+//     row's final minimum taken from a strided sample of the candidates (seed pass, filter arithmetic
+//     only): then sqrtf(P + eps) > sqrtf(U_a + eps) >= the final minimum distance, so the candidate is
+//     neither the arg-min nor tied with it, and dropping it from the in-order scan changes no output.
+//     The seed cuts the ~ln N running-minimum updates per row (each a divergent slow-path entry for the
+//     whole warp) to ~ln(sample stride).
+// Everything else takes the slow path: the exact expression of v2 and the same in-order update rule, so
+// distances and indices are bit-identical to the scalar kernel by construction.
 constexpr float kFilterMargin = 1.9073486328125e-06f;   // 2^-19  (> (13 + rounding of thr) * 2^-24)
 constexpr float kFilterAbs = 1e-36f;                    // covers underflow in the products
+constexpr int kSeedStride = 16;                         // seed pass: every 16th column pair
+constexpr int kSeedMinCols = 2048;                      // below this the seed pass does not pay
+
+// 128-bit shared-memory load from a 32-bit shared address: the scan walks the tile with one register and
+// immediate offsets (through generic pointers the compiler re-derived the shared window base — S2UR,
+// ULEA, LEA: 9 extra instructions per two column pairs — in every iteration).
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// in-order update of (bestP, bestI); the distance itself is recomputed from bestP at the end.
+// The index moves iff sqrtf(P + eps) < sqrtf(bestP + eps): decided without the square roots when the
+// arguments differ by more than 2^-20 relative (then the rounded roots differ too).
+__device__ __forceinline__ void nn_update_lazy(float P, int j, float& bestP, int& bestI) {
+  if (P < bestP) {
+    const float tn = __fadd_rn(P, kEps), to = __fadd_rn(bestP, kEps);
+    bestP = P;
+    if (tn <= __fmul_rd(to, 0.99999904632568359375f) || __fsqrt_rn(tn) < __fsqrt_rn(to)) bestI = j;
+  }
+}
 
 template <int R, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, R == 4 ? 7 : 1)
 chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M,
                    float* __restrict__ d1, int64_t* __restrict__ i1, float* __restrict__ d2,
                    int64_t* __restrict__ i2, FwdWs* __restrict__ ws, float* __restrict__ loss,
                    int tiles_x, int tiles_y, int B) {
-  __shared__ float4 tileA[kTileJ / 2];
-  __shared__ float4 tileB[kTileJ / 2];
+  __shared__ float4 tileA[kTileJ / 2 + 1];   // + 1: the scan prefetches one entry ahead
+  __shared__ float4 tileB[kTileJ / 2 + 1];
   __shared__ float warp_rmax[THREADS / 32];
   __shared__ double warp_part[THREADS / 32];
 
@@ -342,7 +370,7 @@ chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int
   double my_sum = 0.0;
   if (active_block) {
     float2 n0[R], n1[R], n2[R];          // (-2a_k, -2a_k)
-    float rq[R], thr[R], bestP[R], bestD[R];
+    float rq[R], thr[R], cap[R], bestP[R];
     int bestI[R];
     const int row0 = blockIdx.x * (THREADS * R) + threadIdx.x;
 #pragma unroll
@@ -357,20 +385,23 @@ chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int
       n1[r] = make_float2(-2.0f * a1, -2.0f * a1);
       n2[r] = make_float2(-2.0f * a2, -2.0f * a2);
       bestP[r] = INFINITY;
-      bestD[r] = INFINITY;
       bestI[r] = 0;
+      cap[r] = INFINITY;
       thr[r] = INFINITY;
     }
     const float2 neg2 = make_float2(-2.0f, -2.0f);
+    const uint32_t sA = static_cast<uint32_t>(__cvta_generic_to_shared(tileA));
+    const uint32_t sB = static_cast<uint32_t>(__cvta_generic_to_shared(tileB));
 
-    for (int j0 = 0; j0 < nc; j0 += kTileJ) {
-      const int tj = min(kTileJ, nc - j0);
+    // Fill the shared tile with columns [j0, j0 + tj); returns (max norm of the tile, all columns identical).
+    // Layout: A[t] = (x_2t, x_2t+1, y_2t, y_2t+1), B[t] = (z_2t, z_2t+1, r_2t, r_2t+1).
+    auto fill_tile = [&](int j0, int tj, float& rmax, bool& all_same) {
       const int npair = (tj + 1) >> 1;
       __syncthreads();
       float lmax = 0.0f;
       // A tile whose candidates are all bitwise identical (the reference's all-zero GT cloud of an empty
       // slice, npy2point.py:72,115) yields one P per row: only its first column can win under the
-      // first-index rule, so the scan below visits one column pair instead of tying tj times.
+      // first-index rule, so the scan visits one column pair instead of tying tj times.
       const uint32_t f0 = __float_as_uint(__ldg(cbase + j0 * 3 + 0)), f1 = __float_as_uint(__ldg(cbase + j0 * 3 + 1)),
                      f2 = __float_as_uint(__ldg(cbase + j0 * 3 + 2));
       bool same = true;
@@ -392,60 +423,115 @@ chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int
         same = same && __float_as_uint(xa) == f0 && __float_as_uint(ya) == f1 && __float_as_uint(za) == f2 &&
                (!has_b || (__float_as_uint(xb) == f0 && __float_as_uint(yb) == f1 && __float_as_uint(zb) == f2));
       }
+      if (threadIdx.x == 0) {                    // the prefetch slot past the last pair: a sentinel
+        tileA[npair] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tileB[npair] = make_float4(0.f, 0.f, INFINITY, INFINITY);
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
       if (lane == 0) warp_rmax[wid] = lmax;
-      const int scan_pairs = __syncthreads_and(same) ? 1 : npair;
-      float rmax = warp_rmax[0];
+      all_same = __syncthreads_and(same) != 0;
+      rmax = warp_rmax[0];
 #pragma unroll
       for (int i = 1; i < THREADS / 32; ++i) rmax = fmaxf(rmax, warp_rmax[i]);
+    };
+    auto margin = [&](float ra, float rmax) {
+      return __fadd_ru(__fmul_ru(kFilterMargin, __fadd_ru(ra, rmax)), kFilterAbs);
+    };
+
+    // ---- seed pass: an upper bound of every row's final minimum from every kSeedStride-th column pair
+    if (nc >= kSeedMinCols) {
+      float qmin[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) qmin[r] = INFINITY;
+      float rmax_all = 0.0f;
+      for (int j0 = 0; j0 < nc; j0 += kTileJ) {
+        const int tj = min(kTileJ, nc - j0);
+        const int npair = (tj + 1) >> 1;
+        float rmax;
+        bool all_same;
+        fill_tile(j0, tj, rmax, all_same);
+        rmax_all = fmaxf(rmax_all, rmax);
+#pragma unroll 2
+        for (int t = 0; t < npair; t += kSeedStride) {
+          const float4 A = lds128(sA + 16 * t);
+          const float4 Bv = lds128(sB + 16 * t);
+          const float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w);
+          const float2 cz = make_float2(Bv.x, Bv.y), cr = make_float2(Bv.z, Bv.w);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float2 Q = __ffma2_rn(n2[r], cz, __ffma2_rn(n1[r], cy, __ffma2_rn(n0[r], cx, cr)));
+            qmin[r] = fminf(qmin[r], fminf(Q.x, Q.y));      // NaN columns are ignored (they can never win)
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        // P_j <= r_a + Q_j + 13u(r_a + r_j) at the sampled arg-min column j, hence >= the row's minimum P
+        const float U = __fadd_ru(__fadd_ru(qmin[r], rq[r]), margin(rq[r], rmax_all));
+        cap[r] = __fadd_ru(U, __fmul_ru(kFilterMargin, __fadd_ru(fabsf(U), kEps)));
+      }
+    }
+
+    // ---- in-order scan
+    for (int j0 = 0; j0 < nc; j0 += kTileJ) {
+      const int tj = min(kTileJ, nc - j0);
+      float rmax;
+      bool all_same;
+      fill_tile(j0, tj, rmax, all_same);
+      const int scan_pairs = all_same ? 1 : (tj + 1) >> 1;
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        thr[r] = __fadd_ru(__fsub_ru(bestP[r], rq[r]),
-                           __fadd_ru(__fmul_ru(kFilterMargin, __fadd_ru(rq[r], rmax)), kFilterAbs));
-#pragma unroll 2
-      for (int t = 0; t < scan_pairs; ++t) {
-        const float4 A = tileA[t];
-        const float4 Bv = tileB[t];
+        thr[r] = __fadd_ru(__fsub_ru(fminf(bestP[r], cap[r]), rq[r]), margin(rq[r], rmax));
+      uint32_t pa = sA, pb = sB;
+      float4 A = lds128(pa), Bv = lds128(pb);
+#pragma unroll 4
+      for (int t = 0; t < scan_pairs; ++t, pa += 16, pb += 16) {
+        const float4 An = lds128(pa + 16), Bn = lds128(pb + 16);   // next pair's operands: in flight during this one
         const float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w);
         const float2 cz = make_float2(Bv.x, Bv.y), cr = make_float2(Bv.z, Bv.w);
         float2 Q[R];
+        bool h[R];
         bool hit = false;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           Q[r] = __ffma2_rn(n2[r], cz, __ffma2_rn(n1[r], cy, __ffma2_rn(n0[r], cx, cr)));
-          hit = hit || !(Q[r].x >= thr[r]) || !(Q[r].y >= thr[r]);
+          h[r] = !(Q[r].x >= thr[r]) | !(Q[r].y >= thr[r]);    // NaN -> slow path
+          hit = hit | h[r];
         }
         if (hit) {
           const int j = j0 + 2 * t;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            if (!(Q[r].x >= thr[r]) || !(Q[r].y >= thr[r])) {
+            if (h[r]) {
               // the reference's arithmetic, exactly as in v2 (a = -0.5 * (-2a) is exact).  The factor is
               // laundered so the compiler cannot hoist the unscaled rows out of the scan (12 more
               // registers per thread, i.e. spills or a lost CTA per SM).
-              float h = -0.5f;
-              asm volatile("" : "+f"(h));
-              const float2 negh = make_float2(h, h);
+              float hf = -0.5f;
+              asm volatile("" : "+f"(hf));
+              const float2 negh = make_float2(hf, hf);
               const float2 q0 = __fmul2_rn(n0[r], negh), q1 = __fmul2_rn(n1[r], negh), q2 = __fmul2_rn(n2[r], negh);
               const float2 zz = __ffma2_rn(q2, cz, __ffma2_rn(q1, cy, __fmul2_rn(q0, cx)));
               const float2 P = __ffma2_rn(neg2, zz, __fadd2_rn(make_float2(rq[r], rq[r]), cr));
-              nn_update(P.x, j, bestP[r], bestD[r], bestI[r]);
-              nn_update(P.y, j + 1, bestP[r], bestD[r], bestI[r]);
-              thr[r] = __fadd_ru(__fsub_ru(bestP[r], rq[r]),
-                                 __fadd_ru(__fmul_ru(kFilterMargin, __fadd_ru(rq[r], rmax)), kFilterAbs));
+              nn_update_lazy(P.x, j, bestP[r], bestI[r]);
+              nn_update_lazy(P.y, j + 1, bestP[r], bestI[r]);
+              thr[r] = __fadd_ru(__fsub_ru(fminf(bestP[r], cap[r]), rq[r]), margin(rq[r], rmax));
             }
           }
         }
+        A = An;
+        Bv = Bn;
       }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int row = row0 + r * THREADS;
       if (row < nq) {
-        dout[row] = bestD[r];
+        // bestP = +inf only if no column was ever comparable (NaN input): v1/v2 then report +inf, index 0
+        const float d = __fsqrt_rn(__fadd_rn(bestP[r], kEps));
+        dout[row] = d;
         iout[row] = bestI[r];
-        my_sum += static_cast<double>(bestD[r]);
+        my_sum += static_cast<double>(d);
       }
     }
   }

@@ -222,7 +222,8 @@ struct WsParams {
   // dgrad epilogues
   DgradOut out;
   const float* u;           // POOL_DGRAD: [R]
-  int dbg;                  // timing experiments only (pcuda_tune key 4): 1 = TMEM loads without the epilogue math, 2 = no TMEM loads
+  int dbg;                  // timing experiments only (pcuda_tune key 4): 1 = TMEM loads without the epilogue math, 2 = no TMEM loads,
+                            // 3 = no operand traffic either, +8 = per-CTA cycle report, +16 = FWD_POOL without max tracking, +32 = without BN sums
 };
 
 struct __align__(8) WsBarriers {
@@ -452,21 +453,25 @@ __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsPa
               // the packed weights carry sign(gamma), so the accumulator is sign(gamma) * y: BN is
               // monotone per channel and the pooled value is simply the largest accumulator
               const int nb = n0 + ch * 32;
-              float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+              if (!(p.dbg & 32)) {
+                float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const float2 pr = make_float2(v[i], v[i + 1]);
-                s2 = __fadd2_rn(s2, pr);
-                q2 = __ffma2_rn(pr, pr, q2);
+                for (int i = 0; i < 32; i += 2) {
+                  const float2 pr = make_float2(v[i], v[i + 1]);
+                  s2 = __fadd2_rn(s2, pr);
+                  q2 = __ffma2_rn(pr, pr, q2);
+                }
+                sa[0] += s2.x + s2.y;
+                qa[0] += q2.x + q2.y;
               }
-              sa[0] += s2.x + s2.y;
-              qa[0] += q2.x + q2.y;
+              if (!(p.dbg & 16)) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (FULL || i < ncol) {
-                  const bool gt = v[i] > bv[i & 3];
-                  bv[i & 3] = gt ? v[i] : bv[i & 3];
-                  bi[i & 3] = gt ? nb + i : bi[i & 3];
+                for (int i = 0; i < 32; ++i) {
+                  if (FULL || i < ncol) {
+                    const bool gt = v[i] > bv[i & 3];
+                    bv[i & 3] = gt ? v[i] : bv[i & 3];
+                    bi[i & 3] = gt ? nb + i : bi[i & 3];
+                  }
                 }
               }
             } else {

@@ -31,6 +31,8 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, device=DEV)
     out = {}
     sizes = [(64, 256), (64, 512), (64, 1024), (64, 2048), (64, 4096), (64, 8192), (64, 16384), (8, 300), (32, 1024), (32, 4096)]
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":
+        sizes = [(64, 2048), (64, 4096), (64, 16384), (32, 4096)]
     for mode in ("near", "uniform"):
         for B, N in sizes:
             if mode == "uniform" and (B, N) not in ((64, 4096), (64, 16384), (64, 1024)):
@@ -38,7 +40,10 @@ def main():
             x, y = synth_clouds(B, N, seed=5, mode=mode)
             x, y = x.to(DEV), y.to(DEV)
             pairs = 2.0 * B * N * N
-            for var in (0, 1064, 1128, 2128, 4128, 8128, 200000, 204128, 208128):
+            variants = (0, 1064, 1128, 2128, 4128, 8128, 200000, 204128, 208128)
+            if len(sys.argv) > 1 and sys.argv[1] == "quick":
+                variants = (0, 2128, 4128, 8128, 204128)
+            for var in variants:
                 if N >= 8192 and var in (1064, 1128):
                     continue
                 ops.tune(1, var)

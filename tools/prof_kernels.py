@@ -42,4 +42,12 @@ if which in ("all", "mlp"):
     for _ in range(2):
         o = net(pts.transpose(2, 1))[0]
         o.sum().backward()
+if which == "mlp_small":
+    # cfg2-sized D4 pass (B=8, N=300): the latency-bound helper kernels
+    from pointcloududa_b200.networks.PointNetCls import PointNetCls
+    net = PointNetCls().to(dev).train()
+    pts = torch.rand(8, 300, 3, device=dev, requires_grad=True)
+    for _ in range(3):
+        o = net(pts.transpose(2, 1))[0]
+        o.sum().backward()
 torch.cuda.synchronize()
