@@ -680,25 +680,35 @@ pool_u_kernel(const float* __restrict__ W, const float* __restrict__ alpha, cons
 //   S[m, :] = sum_{c : arg[b,c] == n, coef != 0} coef[b,c] * W[c, :]            (ascending c: deterministic)
 //   dz_prev[m, :] += mask(m, :) * S[m, :]     and the dbeta / dgamma sums of the previous layer likewise
 // (or grad_x[b, :, n] += S[m, :] when the previous "layer" is the network input).
-// Only <= C points per cloud are touched, so this is a few MB of traffic next to the GEMM's epilogue,
-// which no longer gathers anything.  grid (B, parts), 512 threads; dynamic smem: C + N ints, then one
-// uint16 match list of C entries per warp (re-used for the final reduction).  A warp owns a head channel
-// (the lowest channel selecting a point — one writer per point, no atomics on dz_prev).  It first compacts
-// the channels selecting the same point into its list with ballots over the shared-memory copy of arg
-// (no global access), then streams their rows of W with kSparseInFlight independent 128-bit loads in
-// flight: a popular point (at N = 300 some are selected by > 100 of the 1024 channels) costs
-// m / kSparseInFlight memory round trips instead of one per 32-channel group.
-template <int KPL>   // output columns per lane: 4 (K <= 128) or 16 (K <= 512); lane owns [KPL*lane, KPL*lane + KPL)
-__global__ void __launch_bounds__(512)
+// Only <= min(C, N) points per cloud are touched.  The kernel is a chain of dependent L2 round trips, not
+// bandwidth (measured at B=8, N=300: one selected point costs ~10k cycles when done naively, a point
+// selected by 140 channels 33k), so it is organised to keep the chains short and even:
+//   * prologue (per CTA): sarg[c] = selected point (or -1), first[n] = lowest channel selecting point n,
+//     then the HEAD channels (first[sarg[c]] == c: one per touched point, one writer per point, no
+//     atomics on dz_prev) are compacted into a list, so the warps of the grid take heads round-robin
+//     — at most ceil(heads / warps) each, instead of whatever a static channel split happens to give;
+//   * per head: the row of dz_prev / y_prev and the BN constants are requested FIRST, then the channels
+//     selecting the same point are compacted with ballots over sarg (4 groups of 32 per step), then their
+//     rows of W stream with kSparseInFlight independent 128-bit loads in flight, summed in ascending order.
+// grid (B, parts), 512 threads; dynamic smem: see pool_sparse_smem().
+// KPL: output columns per lane, 4 (K <= 128) or 16 (K <= 512); lane owns [KPL*lane, KPL*lane + KPL).
+// IF: rows of W in flight per lane; MINB = 2 caps the registers at 64 so two CTAs share an SM (many points
+// selected by one channel each, N >= C: more warps hide more latency than deeper batches do).
+template <int KPL, int IF, int MINB>
+__global__ void __launch_bounds__(512, MINB)
 pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ coef, const float* __restrict__ W,
                    int C, int N, int K, DgradOut o) {
-  constexpr int kSparseInFlight = 32 / KPL;      // 32 registers of W rows in flight per lane
+  constexpr int kSparseInFlight = IF;
   extern __shared__ int sm_i[];
-  int* sarg = sm_i;
-  int* first = sm_i + C;
+  const int nchunk = (C + 31) >> 5;
+  int* sarg = sm_i;                                        // [C]
+  int* first = sarg + C;                                   // [N]
+  int* cnt = first + N;                                    // [nchunk + 1] heads per 32-channel chunk -> exclusive offsets
+  unsigned* hmask = reinterpret_cast<unsigned*>(cnt + nchunk + 1);   // [nchunk]
+  uint16_t* heads = reinterpret_cast<uint16_t*>(hmask + nchunk);     // [C]
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  uint16_t* lst = reinterpret_cast<uint16_t*>(sm_i + C + N) + static_cast<size_t>(warp) * C;
+  uint16_t* lst = heads + ((C + 1) & ~1) + static_cast<size_t>(warp) * C;   // [nwarp][C]
   for (int c = threadIdx.x; c < C; c += blockDim.x)
     sarg[c] = coef[static_cast<int64_t>(b) * C + c] != 0.f ? arg[static_cast<int64_t>(b) * C + c] : -1;
   for (int n = threadIdx.x; n < N; n += blockDim.x) first[n] = 0x7fffffff;
@@ -706,26 +716,98 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
   for (int c = threadIdx.x; c < C; c += blockDim.x)
     if (sarg[c] >= 0) atomicMin(&first[sarg[c]], c);
   __syncthreads();
+  // head list, ascending: per-chunk ballots, a one-warp scan of the chunk counts, then the scatter
+  for (int ch = warp; ch < nchunk; ch += nwarp) {
+    const int c = ch * 32 + lane;
+    const bool is_head = c < C && sarg[c] >= 0 && first[sarg[c]] == c;
+    const unsigned m = __ballot_sync(0xffffffffu, is_head);
+    if (lane == 0) { hmask[ch] = m; cnt[ch] = __popc(m); }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int base = 0;
+    for (int c0 = 0; c0 < nchunk; c0 += 32) {
+      const int v = c0 + lane < nchunk ? cnt[c0 + lane] : 0;
+      int incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (c0 + lane < nchunk) cnt[c0 + lane] = base + incl - v;
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) cnt[nchunk] = base;
+  }
+  __syncthreads();
+  for (int ch = warp; ch < nchunk; ch += nwarp) {
+    const unsigned m = hmask[ch];
+    if ((m >> lane) & 1u) heads[cnt[ch] + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(ch * 32 + lane);
+  }
+  __syncthreads();
+  const int H = cnt[nchunk];
+
   const bool to_x = o.grad_x != nullptr;
   const int k0 = KPL * lane;
-  // rows of W / dz_prev / y_prev are 16-byte aligned runs
+  // rows of W / dz_prev / y_prev (and the per-channel BN vectors) are 16-byte aligned runs
   const bool vec = (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(o.y_prev) |
                                      reinterpret_cast<uintptr_t>(o.dz_prev)) & 15u) == 0;
   float ws[KPL], wq[KPL];                        // this warp's share of the previous layer's dbeta / dgamma sums
 #pragma unroll
   for (int jj = 0; jj < KPL; ++jj) { ws[jj] = 0.f; wq[jj] = 0.f; }
-  const int stride = nwarp * gridDim.y;
-  for (int c = blockIdx.y * nwarp + warp; c < C; c += stride) {
+  // per-channel BN constants of this lane's columns: loaded once when they fit in registers
+  constexpr bool kKeepBN = KPL == 4 && MINB == 1;
+  constexpr int KB = kKeepBN ? KPL : 1;
+  float mean_k[KB], istd_k[KB], gam_k[KB], bet_k[KB];
+#pragma unroll
+  for (int jj = 0; jj < KB; ++jj) {
+    const bool ok = kKeepBN && !to_x && k0 + jj < K;
+    mean_k[jj] = ok ? o.mean[k0 + jj] : 0.f;
+    istd_k[jj] = ok ? o.invstd[k0 + jj] : 0.f;
+    gam_k[jj] = ok ? o.gamma[k0 + jj] : 0.f;
+    bet_k[jj] = ok ? o.beta[k0 + jj] : 0.f;
+  }
+  for (int h = blockIdx.y * nwarp + warp; h < H; h += nwarp * gridDim.y) {
+    const int c = heads[h];
     const int a = sarg[c];
-    if (a < 0 || first[a] != c) continue;      // warp-uniform
-    // pass 1: the channels selecting point a, ascending, into this warp's list
+    const int64_t mrow = static_cast<int64_t>(b) * N + a;
+    // the read-modify-write operands first: their latency overlaps everything below
+    float yv[KPL], dv[KPL];
+#pragma unroll
+    for (int jj = 0; jj < KPL; ++jj) { yv[jj] = 0.f; dv[jj] = 0.f; }
+    if (!to_x) {
+      if (vec) {
+#pragma unroll
+        for (int v = 0; v < KPL / 4; ++v) {
+          if (k0 + 4 * v < K) {
+            const float4 ty = *(reinterpret_cast<const float4*>(o.y_prev + mrow * K + k0) + v);
+            const float4 td = *(reinterpret_cast<const float4*>(o.dz_prev + mrow * K + k0) + v);
+            yv[4 * v + 0] = ty.x; yv[4 * v + 1] = ty.y; yv[4 * v + 2] = ty.z; yv[4 * v + 3] = ty.w;
+            dv[4 * v + 0] = td.x; dv[4 * v + 1] = td.y; dv[4 * v + 2] = td.z; dv[4 * v + 3] = td.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < KPL; ++jj) {
+          const int k = k0 + jj;
+          if (k < K) { yv[jj] = o.y_prev[mrow * K + k]; dv[jj] = o.dz_prev[mrow * K + k]; }
+        }
+      }
+    }
+    // pass 1: the channels selecting point a, ascending, into this warp's list (4 groups of 32 per step)
     int m = 0;
-    for (int c0 = c & ~31; c0 < C; c0 += 32) {
-      const int cc = c0 + lane;
-      const bool hit = cc >= c && cc < C && sarg[cc] == a;
-      const unsigned mask = __ballot_sync(0xffffffffu, hit);
-      if (hit) lst[m + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint16_t>(cc);
-      m += __popc(mask);
+    for (int c0 = c & ~31; c0 < C; c0 += 128) {
+      unsigned mk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cc = c0 + 32 * u + lane;
+        mk[u] = __ballot_sync(0xffffffffu, cc >= c && cc < C && sarg[cc] == a);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if ((mk[u] >> lane) & 1u) lst[m + __popc(mk[u] & ((1u << lane) - 1u))] = static_cast<uint16_t>(c0 + 32 * u + lane);
+        m += __popc(mk[u]);
+      }
     }
     __syncwarp();
     // pass 2: S = sum coef * W[row, :], rows in ascending order, kSparseInFlight rows loaded before the first use
@@ -758,7 +840,6 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
         for (int jj = 0; jj < KPL; ++jj) acc[jj] = fmaf(cf[u], wv[u][jj], acc[jj]);
     }
     __syncwarp();                                 // the list is rewritten for the next head
-    const int64_t mrow = static_cast<int64_t>(b) * N + a;
     if (to_x) {
 #pragma unroll
       for (int jj = 0; jj < KPL; ++jj) {
@@ -766,33 +847,15 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
         if (k < K) o.grad_x[(static_cast<int64_t>(b) * K + k) * N + a] += acc[jj];
       }
     } else {
-      float yv[KPL], dv[KPL];
-      if (vec) {
-#pragma unroll
-        for (int v = 0; v < KPL / 4; ++v) {
-          float4 ty = make_float4(0.f, 0.f, 0.f, 0.f), td = ty;
-          if (k0 + 4 * v < K) {
-            ty = *(reinterpret_cast<const float4*>(o.y_prev + mrow * K + k0) + v);
-            td = *(reinterpret_cast<const float4*>(o.dz_prev + mrow * K + k0) + v);
-          }
-          yv[4 * v + 0] = ty.x; yv[4 * v + 1] = ty.y; yv[4 * v + 2] = ty.z; yv[4 * v + 3] = ty.w;
-          dv[4 * v + 0] = td.x; dv[4 * v + 1] = td.y; dv[4 * v + 2] = td.z; dv[4 * v + 3] = td.w;
-        }
-      } else {
-#pragma unroll
-        for (int jj = 0; jj < KPL; ++jj) {
-          const int k = k0 + jj;
-          yv[jj] = k < K ? o.y_prev[mrow * K + k] : 0.f;
-          dv[jj] = k < K ? o.dz_prev[mrow * K + k] : 0.f;
-        }
-      }
 #pragma unroll
       for (int jj = 0; jj < KPL; ++jj) {
         const int k = k0 + jj;
         float v = 0.f;
         if (k < K) {
-          const float yh = (yv[jj] - o.mean[k]) * o.invstd[k];
-          const bool on = !o.relu || fmaf(yh, o.gamma[k], o.beta[k]) > 0.f;
+          const float mu = kKeepBN ? mean_k[jj % KB] : o.mean[k], is = kKeepBN ? istd_k[jj % KB] : o.invstd[k];
+          const float ga = kKeepBN ? gam_k[jj % KB] : o.gamma[k], be = kKeepBN ? bet_k[jj % KB] : o.beta[k];
+          const float yh = (yv[jj] - mu) * is;
+          const bool on = !o.relu || fmaf(yh, ga, be) > 0.f;
           v = on ? acc[jj] : 0.f;
           ws[jj] += v;
           wq[jj] = fmaf(v, yh, wq[jj]);
@@ -827,6 +890,15 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
     for (int w = 0; w < nwarp; ++w) { sd += static_cast<double>(red[w * K + k]); qd += static_cast<double>(red[(nwarp + w) * K + k]); }
     if (sd != 0.0 || qd != 0.0) { atomicAdd(&o.sums[k], sd); atomicAdd(&o.sums[K + k], qd); }
   }
+}
+
+// dynamic shared memory of pool_sparse_kernel: sarg[C] first[N] cnt[nchunk+1] hmask[nchunk] ints, heads[C] +
+// 16 match lists of C uint16; re-used as [2][16][K] floats by the final reduction
+static size_t pool_sparse_smem(int C, int N, int K) {
+  const size_t nchunk = (static_cast<size_t>(C) + 31) / 32;
+  const size_t a = sizeof(int) * (static_cast<size_t>(C) + N + 2 * nchunk + 1) +
+                   sizeof(uint16_t) * (((static_cast<size_t>(C) + 1) & ~static_cast<size_t>(1)) + 16 * static_cast<size_t>(C));
+  return std::max(a, sizeof(float) * 2 * 16 * static_cast<size_t>(K));
 }
 
 // dW[c,k] = sum_b coef[b,c] (a[(b,sel),k] - abar_k) - kappa_c sum_k' W[c,k'] Ghat[k',k]
@@ -1469,25 +1541,27 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     }
     if (L >= 2 || grad_x) {
       const DgradOut o = dgrad_out(L - 2, dzbuf[cur]);
-      // C + N ints, one uint16 match list of C entries per warp (16 warps); re-used as [2][16][K] floats
-      const size_t sparse_smem = std::max(sizeof(int) * (static_cast<size_t>(C) + N) + sizeof(uint16_t) * 16 * static_cast<size_t>(C),
-                                          sizeof(float) * 2 * 16 * static_cast<size_t>(K));
+      const size_t sparse_smem = pool_sparse_smem(C, N, K);
       if (tc_on(precision, TC_POOL_DGRAD) && a_in && w.qpack && tc::pool_dgrad_fits(K) && sparse_smem <= 200 * 1024 && K <= 512 && C <= 65535) {
         static bool attr_done = false;
         if (!attr_done) {
-          cudaFuncSetAttribute(pool_sparse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-          cudaFuncSetAttribute(pool_sparse_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cudaFuncSetAttribute(pool_sparse_kernel<4, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cudaFuncSetAttribute(pool_sparse_kernel<4, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+          cudaFuncSetAttribute(pool_sparse_kernel<16, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
           attr_done = true;
         }
         // dense part on the tensor cores: dz_prev = mask * (-u - a Q) (+ its column sums) ...
         if (int rc = tc::pack_w(w.Q, K, K, false, w.qpack, st)) return rc;
         if (int rc = tc::pool_dgrad(tl, a_in, K, w.qpack, w.u, o, st)) return rc;
-        // ... then the <= C selected points per cloud get their sparse rows added (one warp per point)
-        // about two 512-thread CTAs per SM and >= 4 channels per warp: every CTA repeats the O(C + N)
-        // prologue and ends with 2K fp64 atomics on the same addresses, so fewer, longer CTAs win
-        const int parts = std::max(1, std::min((C + 63) / 64, (2 * sm_count() + B - 1) / B));
-        if (K <= 128) pool_sparse_kernel<4><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
-        else pool_sparse_kernel<16><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
+        // ... then the <= min(C, N) selected points per cloud get their sparse rows added (one warp per point).
+        // Every CTA repeats the O(C + N) prologue and ends with 2K fp64 atomics on the same 2K addresses
+        // (beyond ~300 CTAs those serialise: tools/micro/atomic_tail.cu), so about one wave of CTAs.
+        const bool many_points = K <= 128 && N >= C && sparse_smem <= 100 * 1024;   // ~1 channel per selected point
+        const int per_sm = many_points ? 2 : 1;
+        const int parts = std::max(1, std::min((std::min(C, N) + 31) / 32, (per_sm * sm_count() + B - 1) / B));
+        if (many_points) pool_sparse_kernel<4, 4, 2><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
+        else if (K <= 128) pool_sparse_kernel<4, 12, 1><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
+        else pool_sparse_kernel<16, 2, 1><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
         launches += 1;
       } else {
         pool_dgrad_kernel<<<dim3(B * tps, (K + TN - 1) / TN), kThreads, 0, st>>>(src, w.Q, w.u, last.weight, w.coef, pool_arg, C, N, tps, o);

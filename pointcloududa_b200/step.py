@@ -16,9 +16,10 @@ SURVEY.md §3.1 / §8d "one adversarial step"):
 The U-Net, D1/D2 and host-side bookkeeping are excluded.  All scalar results are kept on the
 device and returned as one small tensor so a caller pays a single device->host read per step.
 
-Phases P1+P2, P3 and P4 do not depend on each other (D4's parameters only change in P5), and at the
-reference's shapes (2400 points per D4 call) no single kernel fills 148 SMs, so the step issues them on
-three streams: inside a captured CUDA graph they become three concurrent branches.  The only shared
+The three D4 passes (P2, P3, P4) do not depend on each other (D4's parameters only change in P5), nor do
+the discriminator-free ops (Chamfer, entropy map), and at the reference's shapes (2400 points per D4 call)
+no single kernel fills 148 SMs, so the step issues them on four streams: inside a captured CUDA graph they
+become four concurrent branches (one per D4 pass + one for Chamfer / entropy).  The only shared
 mutable state, BatchNorm's running statistics / num_batches_tracked, is recorded per pass and applied
 after the join in the reference's pass order (networks.PointNetCls.deferred_bn_updates), so buffers and
 gradients are identical to sequential execution.
@@ -117,33 +118,37 @@ class AdversarialStep:
         dev = self.device
         main = torch.cuda.current_stream(dev)
         if self._side is None:
-            self._side = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
-        s1, s2 = self._side if self.concurrent else (main, main)
+            self._side = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        s1, s2, s3 = self._side if self.concurrent else (main, main, main)
         sink_p2, sink_p3, sink_p4 = [], [], []
 
         # (D4's gradients live in the flat bucket; it is overwritten at the join)
         if self.concurrent:
-            s1.wait_stream(main)
-            s2.wait_stream(main)
+            for s in (s1, s2, s3):
+                s.wait_stream(main)
 
-        # ---- branch A (this stream) — P1: source Chamfer, forward + backward into the predicted cloud.  Issued first
-        # so that Dropout consumes the generator in the reference's order (P2, P3, P4); the streams run concurrently
-        # regardless of the issue order.
+        # ---- branch D (stream s3) — the ops with no discriminator in them: P1 source Chamfer forward + backward
+        # into the predicted cloud, the target entropy map forward + backward (the part of P2 that feeds D2),
+        # the target Chamfer value.  None of them depends on D4, so they leave the critical branch.
         self._set_requires_grad(False)
-        vertS = I["vertS"].detach().requires_grad_(True)
-        loss_seg3 = batch_NN_loss(x=vertS, y=I["vertexA"])
-        (gS,) = torch.autograd.grad(loss_seg3, vertS)
-        self.grad_vertS.copy_(gS)
-        # P2: fool the discriminators (D4 frozen: gradient into the cloud only)
-        oT = I["oT"].detach().requires_grad_(True)
-        outs = entropy_map(oT, activation=cfg.activation, normalize=cfg.normalize,
-                           return_prob=cfg.return_prob, return_mean=True)
-        mapT, ent_mean = outs[0], outs[-1]
-        (gO,) = torch.autograd.grad(mapT, oT, I["grad_mapT"])
-        self.grad_oT.copy_(gO)
+        with torch.cuda.stream(s3):
+            vertS = I["vertS"].detach().requires_grad_(True)
+            loss_seg3 = batch_NN_loss(x=vertS, y=I["vertexA"])
+            (gS,) = torch.autograd.grad(loss_seg3, vertS)
+            self.grad_vertS.copy_(gS)
+            oT = I["oT"].detach().requires_grad_(True)
+            outs = entropy_map(oT, activation=cfg.activation, normalize=cfg.normalize,
+                               return_prob=cfg.return_prob, return_mean=True)
+            mapT, ent_mean = outs[0], outs[-1]
+            (gO,) = torch.autograd.grad(mapT, oT, I["grad_mapT"])
+            self.grad_oT.copy_(gO)
+            with torch.no_grad():
+                loss_vert_target = batch_NN_loss(x=I["vertT"], y=I["vertexB"])
+
+        # ---- branch A (this stream) — P2: fool the point-cloud discriminator (D4 frozen: gradient into the cloud
+        # only).  Issued before P3 / P4 so that Dropout consumes the generator in the reference's order (P2, P3, P4);
+        # the streams run concurrently regardless of the issue order.
         vertT = I["vertT"].detach().requires_grad_(True)
-        with torch.no_grad():
-            loss_vert_target = batch_NN_loss(x=vertT, y=I["vertexB"])
         with deferred_bn_updates(sink_p2):
             D_out4 = self.d4(vertT.transpose(2, 1))[0]
         loss_adv_point = cfg.dr * F.binary_cross_entropy_with_logits(D_out4, self._ones)
@@ -174,11 +179,12 @@ class AdversarialStep:
 
         # ---- join: parameter gradients into the flat bucket, BatchNorm buffers in the reference's pass order
         if self.concurrent:
-            main.wait_stream(s1)
-            main.wait_stream(s2)
+            for s in (s1, s2, s3):
+                main.wait_stream(s)
             if not torch.cuda.is_current_stream_capturing():
                 # eager mode: tensors born on a side stream are consumed on this one after the join
                 crossing = list(grads_s) + list(grads_t) + [loss_D_same4, loss_D_diff_4, acc_s, acc_t]
+                crossing += [loss_seg3, loss_vert_target, ent_mean]
                 crossing += [t for sink in (sink_p3, sink_p4) for e in sink for t in (e[1], e[2])]
                 for t in crossing:
                     if t is not None:
