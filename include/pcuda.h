@@ -242,6 +242,29 @@ typedef struct pcuda_bn_update {
 } pcuda_bn_update_t;
 int pcuda_bn_running_update(int n, const pcuda_bn_update_t* items /*host*/, pcuda_stream_t stream);
 
+/* ---- D4 parameter gradients and optimiser step ---------------------------------------------------
+ * Replaces the implicit .grad accumulation of the two discriminator backward passes
+ * (train_mscmrseg.py:288,319) and optim_dis4.step() = torch.optim.SGD(momentum, weight_decay)
+ * (train_mscmrseg.py:329-330,:450-455) by one launch each (per 48 tensors).  `slots` is a HOST array; the
+ * pointers it holds are device pointers and travel as kernel parameters (CUDA-graph capturable).
+ *   pcuda_grad_sum_pack:      flat[offset_i + j] = scale * (grad_a_i[j] + grad_b_i[j])   (grad_b may be NULL;
+ *                             scale = 1/world folds the mean of the gradient all-reduce)
+ *   pcuda_sgd_momentum_step:  g = flat_grad[offset_i + j] + weight_decay * param_i[j];
+ *                             buf = momentum * flat_momentum[offset_i + j] + g;  param_i[j] -= lr * buf
+ *                             (torch.optim.SGD, dampening 0, nesterov off; a zero-initialised buffer reproduces
+ *                             torch's first step).  lr is read from device memory (*lr_dev).
+ */
+typedef struct pcuda_param_slot {
+  const float* grad_a;   /* [numel] (pack only) */
+  const float* grad_b;   /* [numel] or NULL (pack only) */
+  float* param;          /* [numel] (sgd only) */
+  int64_t offset;        /* element offset of this tensor inside the flat buffers */
+  int64_t numel;
+} pcuda_param_slot_t;
+int pcuda_grad_sum_pack(const pcuda_param_slot_t* slots /*host*/, int n, float scale, float* flat, pcuda_stream_t stream);
+int pcuda_sgd_momentum_step(const pcuda_param_slot_t* slots /*host*/, int n, const float* flat_grad, float* flat_momentum,
+                            const float* lr_dev, float momentum, float weight_decay, pcuda_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,11 @@ class BnUpdate(ctypes.Structure):
     ]
 
 
+class ParamSlot(ctypes.Structure):
+    """pcuda_param_slot_t (include/pcuda.h)."""
+    _fields_ = [("grad_a", c_void_p), ("grad_b", c_void_p), ("param", c_void_p), ("offset", c_int64), ("numel", c_int64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/pcuda.h declares
 SIGNATURES = {
     "pcuda_version": (c_int, []),
@@ -81,6 +86,9 @@ SIGNATURES = {
     "pcuda_fcstack_bwd": (c_int, [c_void_p, c_int, c_int, POINTER(FcLayer), c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p]),
     "pcuda_bn_running_update": (c_int, [c_int, POINTER(BnUpdate), c_void_p]),
+    "pcuda_grad_sum_pack": (c_int, [POINTER(ParamSlot), c_int, c_float, c_void_p, c_void_p]),
+    "pcuda_sgd_momentum_step": (c_int, [POINTER(ParamSlot), c_int, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                        c_void_p]),
 }
 
 

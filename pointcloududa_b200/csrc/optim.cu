@@ -1,0 +1,128 @@
+// Parameter-gradient packing and the SGD step of the point-cloud discriminator (D4), one launch each.
+//
+// The reference sums D4's parameter gradients implicitly (two loss.backward() calls accumulate into
+// .grad, train_mscmrseg.py:288,319) and then runs torch.optim.SGD(momentum .99, weight_decay 5e-4)
+// (train_mscmrseg.py:329-330,:450-455).  The two D4 passes of this implementation run concurrently and
+// return separate gradient tensors, so the sum is explicit — as framework ops it was two multi-tensor
+// launches plus a two-launch fused SGD, ~65 us of serial tail behind the join of a 650 us step.  Here:
+//   pcuda_grad_sum_pack      flat[off_i + j] = scale * (ga_i[j] + gb_i[j])      (the all-reduce bucket)
+//   pcuda_sgd_momentum_step  g = flat[off_i + j] + wd * p;  buf = mu * buf + g;  p -= lr * buf
+// The per-tensor pointers travel as kernel parameters (<= 48 tensors per launch), so both calls are
+// legal under CUDA-graph capture; lr is read from device memory so a schedule needs no re-capture.
+// Arithmetic order is torch's (_single_tensor_sgd / the fused functor): weight decay added to the
+// gradient, buf = mu*buf + g in two roundings, p = p - lr*buf; buf starts at zero, which reproduces
+// torch's first step (buf = g) exactly.
+#include "pcuda_common.cuh"
+
+namespace pcuda {
+namespace {
+
+constexpr int kSlotsPerLaunch = 48;
+constexpr int kThreads = 256;
+constexpr int kPerThread = 8;
+constexpr int kChunk = kThreads * kPerThread;
+
+struct Slot {
+  const float* ga;
+  const float* gb;
+  float* param;
+  long long offset;
+  long long numel;
+};
+struct Table {
+  Slot s[kSlotsPerLaunch];
+  int cta_start[kSlotsPerLaunch + 1];
+  int n;
+};
+
+__device__ __forceinline__ int find_slot(const Table& t, int cta) {
+  int i = 0;
+  while (i + 1 < t.n && cta >= t.cta_start[i + 1]) ++i;
+  return i;
+}
+
+__global__ void __launch_bounds__(kThreads) grad_sum_pack_kernel(const __grid_constant__ Table t, float scale, float* __restrict__ flat) {
+  const int i = find_slot(t, blockIdx.x);
+  const Slot& s = t.s[i];
+  const long long base = static_cast<long long>(blockIdx.x - t.cta_start[i]) * kChunk;
+#pragma unroll
+  for (int u = 0; u < kPerThread; ++u) {
+    const long long j = base + u * kThreads + threadIdx.x;
+    if (j < s.numel) {
+      float g = s.ga[j];
+      if (s.gb != nullptr) g = __fadd_rn(g, s.gb[j]);
+      flat[s.offset + j] = scale == 1.0f ? g : g * scale;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sgd_momentum_kernel(const __grid_constant__ Table t, const float* __restrict__ flat_grad,
+                                                                float* __restrict__ flat_mom, const float* __restrict__ lr_dev,
+                                                                float momentum, float weight_decay) {
+  const int i = find_slot(t, blockIdx.x);
+  const Slot& s = t.s[i];
+  const float lr = __ldg(lr_dev);
+  const long long base = static_cast<long long>(blockIdx.x - t.cta_start[i]) * kChunk;
+#pragma unroll
+  for (int u = 0; u < kPerThread; ++u) {
+    const long long j = base + u * kThreads + threadIdx.x;
+    if (j < s.numel) {
+      const float p = s.param[j];
+      float g = flat_grad[s.offset + j];
+      if (weight_decay != 0.0f) g = __fmaf_rn(weight_decay, p, g);              // torch: grad.add(param, alpha=wd)
+      const float buf = __fadd_rn(__fmul_rn(momentum, flat_mom[s.offset + j]), g);   // buf.mul_(mu).add_(g)
+      flat_mom[s.offset + j] = buf;
+      s.param[j] = __fmaf_rn(-lr, buf, p);                                       // param.add_(buf, alpha=-lr)
+    }
+  }
+}
+
+template <typename F>
+int for_each_table(const pcuda_param_slot_t* slots, int n, const char* who, bool need_param, F&& launch) {
+  for (int s0 = 0; s0 < n; s0 += kSlotsPerLaunch) {
+    Table t{};
+    t.n = n - s0 < kSlotsPerLaunch ? n - s0 : kSlotsPerLaunch;
+    int ctas = 0;
+    for (int i = 0; i < t.n; ++i) {
+      const pcuda_param_slot_t& p = slots[s0 + i];
+      PCUDA_REQUIRE(p.numel >= 0 && p.offset >= 0, PCUDA_E_SHAPE, "%s: slot %d has numel %lld offset %lld", who, s0 + i,
+                    static_cast<long long>(p.numel), static_cast<long long>(p.offset));
+      PCUDA_REQUIRE(p.numel == 0 || (need_param ? p.param != nullptr : p.grad_a != nullptr), PCUDA_E_NULL, "%s: slot %d has a NULL tensor", who, s0 + i);
+      t.s[i] = Slot{p.grad_a, p.grad_b, p.param, static_cast<long long>(p.offset), static_cast<long long>(p.numel)};
+      t.cta_start[i] = ctas;
+      ctas += static_cast<int>((p.numel + kChunk - 1) / kChunk);
+    }
+    t.cta_start[t.n] = ctas;
+    if (ctas == 0) continue;
+    launch(t, ctas);
+    count_launch(1);
+    if (int rc = check_launch(who)) return rc;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace pcuda
+
+using namespace pcuda;
+
+extern "C" int pcuda_grad_sum_pack(const pcuda_param_slot_t* slots, int n, float scale, float* flat, pcuda_stream_t stream) {
+  PCUDA_REQUIRE(n >= 0, PCUDA_E_SHAPE, "grad_sum_pack: n=%d", n);
+  if (n == 0) return 0;
+  PCUDA_REQUIRE(slots && flat, PCUDA_E_NULL, "grad_sum_pack: NULL argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return for_each_table(slots, n, "grad_sum_pack", false, [&](const Table& t, int ctas) {
+    grad_sum_pack_kernel<<<ctas, kThreads, 0, st>>>(t, scale, flat);
+  });
+}
+
+extern "C" int pcuda_sgd_momentum_step(const pcuda_param_slot_t* slots, int n, const float* flat_grad, float* flat_momentum,
+                                       const float* lr_dev, float momentum, float weight_decay, pcuda_stream_t stream) {
+  PCUDA_REQUIRE(n >= 0, PCUDA_E_SHAPE, "sgd_momentum_step: n=%d", n);
+  if (n == 0) return 0;
+  PCUDA_REQUIRE(slots && flat_grad && flat_momentum && lr_dev, PCUDA_E_NULL, "sgd_momentum_step: NULL argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return for_each_table(slots, n, "sgd_momentum_step", true, [&](const Table& t, int ctas) {
+    sgd_momentum_kernel<<<ctas, kThreads, 0, st>>>(t, flat_grad, flat_momentum, lr_dev, momentum, weight_decay);
+  });
+}

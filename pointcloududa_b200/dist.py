@@ -88,6 +88,12 @@ class GradBucket:
                 v.copy_(p.grad)
                 p.grad = v
 
+    def allreduce_sum(self, group: Optional[dist.ProcessGroup] = None, async_op: bool = False):
+        """Sum over ranks (for a bucket that was filled pre-divided by the world size)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
     def allreduce_mean(self, group: Optional[dist.ProcessGroup] = None, async_op: bool = False):
         if not (dist.is_available() and dist.is_initialized()):
             return None

@@ -36,6 +36,7 @@ import torch.nn.functional as F
 
 from . import dist as pdist
 from .networks.PointNetCls import PointNetCls, apply_bn_updates, deferred_bn_updates
+from .optim import FusedSGD
 from .utils.loss import batch_NN_loss, entropy_map
 
 RESULT_FIELDS = ("chamfer_source", "chamfer_target", "entropy_mean_target", "adv_point_loss",
@@ -68,12 +69,12 @@ class AdversarialStep:
         torch.manual_seed(seed)
         self.d4 = PointNetCls(feature_transform=cfg.feature_transform, ext=cfg.ext,
                               precision=cfg.precision).to(device).train()
-        # optim_dis4 of the reference: SGD, momentum .99, weight decay 5e-4 (train_mscmrseg.py:450-455)
-        # (fused=True: one multi-tensor kernel for the whole update; same arithmetic as the default foreach path)
-        self.opt = torch.optim.SGD(self.d4.parameters(), lr=cfg.lr_dis, momentum=0.99, weight_decay=0.0005,
-                                   fused=True)
+        # optim_dis4 of the reference: SGD, momentum .99, weight decay 5e-4 (train_mscmrseg.py:450-455), as one
+        # libpcuda launch over all parameters (optim.FusedSGD: torch's arithmetic, momentum buffers in one flat tensor)
+        self.opt = FusedSGD(list(self.d4.parameters()), lr=cfg.lr_dis, momentum=0.99, weight_decay=0.0005)
         self._pnames = [n for n, _ in self.d4.named_parameters()]
         self.bucket = pdist.GradBucket(self.d4.parameters())
+        self._world = 1
         B, C, H, W, N = cfg.B, cfg.C, cfg.H, cfg.W, cfg.N
         f32 = dict(dtype=torch.float32, device=device)
         self.inputs: Dict[str, torch.Tensor] = {
@@ -189,20 +190,30 @@ class AdversarialStep:
                 for t in crossing:
                     if t is not None:
                         t.record_stream(main)
-        self.bucket.assign_sum(grads_s, grads_t)
+        # bucket = (grads_s + grads_t) / world: one launch; the division is the "mean" of the gradient all-reduce
+        if any(g is None for g in grads_s) or any(g is None for g in grads_t):
+            self.bucket.assign_sum(grads_s, grads_t)          # a parameter without gradient: zero-fill + accumulate
+            if self._world > 1:
+                self.bucket.flat.div_(self._world)
+        else:
+            self.opt.pack(grads_s, grads_t, self.bucket.flat, scale=1.0 / self._world)
         apply_bn_updates([sink_p2, sink_p3, sink_p4])
         self._res = [loss_seg3.detach(), loss_vert_target.detach(), ent_mean.detach(), loss_adv_point.detach(),
                      loss_D_same4.detach(), loss_D_diff_4.detach(), acc_s, acc_t]
 
     def _post(self) -> None:
         # P5 (after the gradient all-reduce): SGD step of D4, scalars of the step into one small tensor
-        self.bucket.attach()
-        self.opt.step()
+        self.opt.step(self.bucket.flat)
         self.result.copy_(torch.stack([r.reshape(()).float() for r in self._res]))
 
+    def _sync_world(self) -> None:
+        import torch.distributed as dist
+        self._world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
     def _body(self) -> None:
+        self._sync_world()
         self._pre()
-        self.bucket.allreduce_mean()
+        self.bucket.allreduce_sum()      # the bucket was filled pre-divided by the world size
         self._post()
 
     def run(self) -> torch.Tensor:
@@ -212,7 +223,7 @@ class AdversarialStep:
             self.graph.replay()
             if self.graph_post is not None:
                 # multi-GPU: the one NCCL call of the step sits between the two captured halves
-                self.bucket.allreduce_mean()
+                self.bucket.allreduce_sum()
                 self.graph_post.replay()
         else:
             self._body()
@@ -224,6 +235,7 @@ class AdversarialStep:
         on the same stream."""
         import torch.distributed as dist
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self._sync_world()
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):

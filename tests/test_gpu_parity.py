@@ -932,3 +932,37 @@ def test_adversarial_step_concurrent_branches_equal_sequential(precision):
     for idx in (0, 1, 2):                                         # chamfer_source, chamfer_target, entropy_mean_target
         assert abs(gres[-1][idx].item() - res_ref[0][idx].item()) <= 1e-6 * abs(res_ref[0][idx].item())
     assert int(gst.d4.feat.bn3.num_batches_tracked.item()) > 0
+
+
+# ================================================================ optimiser ========================
+def test_fused_sgd_matches_torch_sgd():
+    """pcuda_grad_sum_pack + pcuda_sgd_momentum_step against torch.optim.SGD(momentum .99, weight_decay 5e-4)
+    (train_mscmrseg.py:450-455) over several steps: the two D4 gradient lists are summed, scaled, applied."""
+    from pointcloududa_b200.optim import FusedSGD
+    g = torch.Generator().manual_seed(3)
+    shapes = [(64, 3), (64,), (128, 64), (1024, 128), (1024,), (512, 1024), (9,), (1, 256), (5, 7, 3)]
+    ref = [torch.nn.Parameter(torch.randn(s, generator=g).to(DEV)) for s in shapes]
+    ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    topt = torch.optim.SGD(ref, lr=2.5e-3, momentum=0.99, weight_decay=0.0005)
+    fopt = FusedSGD(ours, lr=2.5e-3, momentum=0.99, weight_decay=0.0005)
+    flat = torch.zeros(fopt.numel, device=DEV)
+    for it in range(6):
+        ga = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+        gb = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+        scale = 0.5 if it % 2 else 1.0
+        for p, a, b in zip(ref, ga, gb):
+            p.grad = (a + b) * scale
+        topt.step()
+        fopt.pack(ga, gb, flat, scale=scale)
+        want = torch.cat([((a + b) * scale).reshape(-1) for a, b in zip(ga, gb)])
+        assert torch.equal(flat, want)
+        fopt.step(flat)
+        if it == 2:
+            for o in topt.param_groups:
+                o["lr"] = 1e-3
+            fopt.set_lr(1e-3)
+    for p, q in zip(ref, ours):
+        assert max_rel(q.detach().cpu().numpy(), p.detach().cpu().numpy()) < 2e-6
+    # one-sided pack (second list absent)
+    fopt.pack(ga, None, flat)
+    assert torch.equal(flat, torch.cat([a.reshape(-1) for a in ga]))
