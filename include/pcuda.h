@@ -265,6 +265,16 @@ int pcuda_grad_sum_pack(const pcuda_param_slot_t* slots /*host*/, int n, float s
 int pcuda_sgd_momentum_step(const pcuda_param_slot_t* slots /*host*/, int n, const float* flat_grad, float* flat_momentum,
                             const float* lr_dev, float momentum, float weight_decay, pcuda_stream_t stream);
 
+/* ---- discriminator bookkeeping ---------------------------------------------------------------------
+ * Replaces F.binary_cross_entropy_with_logits(D_out4, full_like(D_out4, label)) (reduction 'mean',
+ * train_mscmrseg.py:233,286,316), its backward into the logits, and the accuracy bookkeeping
+ * (train_mscmrseg.py:290-296,:320-322) by one launch:
+ *   loss = weight * mean_i[(1 - target) x_i - log_sigmoid(x_i)],  grad_logit[i] = weight * (sigmoid(x_i) - target) / n
+ *   accuracy = mean_i[(sigmoid(x_i) >= 0.5) == (target >= 0.5)]      (grad_logit / accuracy may be NULL)
+ */
+int pcuda_bce_logits(const float* logit, int n, float target, float weight, float* loss, float* grad_logit,
+                     float* accuracy, pcuda_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,7 @@ SIGNATURES = {
                                   c_void_p, c_void_p]),
     "pcuda_bn_running_update": (c_int, [c_int, POINTER(BnUpdate), c_void_p]),
     "pcuda_grad_sum_pack": (c_int, [POINTER(ParamSlot), c_int, c_float, c_void_p, c_void_p]),
+    "pcuda_bce_logits": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcuda_sgd_momentum_step": (c_int, [POINTER(ParamSlot), c_int, c_void_p, c_void_p, c_void_p, c_float, c_float,
                                         c_void_p]),
 }

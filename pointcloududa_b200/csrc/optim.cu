@@ -77,6 +77,32 @@ __global__ void __launch_bounds__(kThreads) sgd_momentum_kernel(const __grid_con
   }
 }
 
+// ---- discriminator bookkeeping: BCE-with-logits (mean), its gradient and the accuracy, one warp ----------
+// loss = weight * mean_i [ (1 - t) x_i - log_sigmoid(x_i) ]   (F.binary_cross_entropy_with_logits, reduction 'mean',
+// train_mscmrseg.py:233,286,316), grad_i = weight * (sigmoid(x_i) - t) / n, acc = mean_i [ (sigmoid(x_i) >= 0.5) == (t >= 0.5) ]
+// (train_mscmrseg.py:290-296,:320-322).  n is the batch (<= a few hundred): one warp, fixed-order sums.
+__global__ void __launch_bounds__(32) bce_logits_kernel(const float* __restrict__ x, int n, float t, float weight,
+                                                        float* __restrict__ loss, float* __restrict__ grad, float* __restrict__ acc) {
+  double ls = 0.0;
+  int hits = 0;
+  for (int i = threadIdx.x; i < n; i += 32) {
+    const float v = x[i];
+    // log_sigmoid(v) = min(v, 0) - log1p(exp(-|v|))
+    const float lsg = fminf(v, 0.f) - log1pf(expf(-fabsf(v)));
+    ls += static_cast<double>((1.f - t) * v - lsg);
+    const float sg = 1.f / (1.f + expf(-v));
+    if (grad != nullptr) grad[i] = weight * (sg - t) / static_cast<float>(n);
+    hits += ((sg >= 0.5f) == (t >= 0.5f)) ? 1 : 0;
+  }
+  ls = warp_sum(ls);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
+  if (threadIdx.x == 0) {
+    *loss = weight * static_cast<float>(ls / static_cast<double>(n));
+    if (acc != nullptr) *acc = static_cast<float>(hits) / static_cast<float>(n);
+  }
+}
+
 template <typename F>
 int for_each_table(const pcuda_param_slot_t* slots, int n, const char* who, bool need_param, F&& launch) {
   for (int s0 = 0; s0 < n; s0 += kSlotsPerLaunch) {
@@ -125,4 +151,13 @@ extern "C" int pcuda_sgd_momentum_step(const pcuda_param_slot_t* slots, int n, c
   return for_each_table(slots, n, "sgd_momentum_step", true, [&](const Table& t, int ctas) {
     sgd_momentum_kernel<<<ctas, kThreads, 0, st>>>(t, flat_grad, flat_momentum, lr_dev, momentum, weight_decay);
   });
+}
+
+extern "C" int pcuda_bce_logits(const float* logit, int n, float target, float weight, float* loss, float* grad_logit,
+                                float* accuracy, pcuda_stream_t stream) {
+  PCUDA_REQUIRE(n >= 1, PCUDA_E_SHAPE, "bce_logits: n=%d", n);
+  PCUDA_REQUIRE(logit && loss, PCUDA_E_NULL, "bce_logits: NULL argument");
+  bce_logits_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(logit, n, target, weight, loss, grad_logit, accuracy);
+  count_launch(1);
+  return check_launch("bce_logits");
 }

@@ -163,6 +163,38 @@ def chamfer_nn(x: torch.Tensor, y: torch.Tensor):
     return _ChamferNN.apply(x, y)
 
 
+class _BceLogits(torch.autograd.Function):
+    """weight * F.binary_cross_entropy_with_logits(logit, full_like(logit, target)) (reduction 'mean'), its gradient
+    and the discriminator accuracy in one launch (pcuda_bce_logits)."""
+
+    @staticmethod
+    def forward(ctx, logit, target: float, weight: float):
+        _require_cuda_f32(logit, "logit")
+        x = logit.contiguous()
+        dev = x.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        acc = torch.empty((), dtype=torch.float32, device=dev)
+        grad = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            check(_lib.lib().pcuda_bce_logits(_ptr(x), x.numel(), float(target), float(weight), _ptr(loss), _ptr(grad),
+                                              _ptr(acc), _stream()), "pcuda_bce_logits")
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(acc)
+        return loss, acc
+
+    @staticmethod
+    def backward(ctx, gloss, _gacc):
+        (grad,) = ctx.saved_tensors
+        return grad * gloss, None, None
+
+
+def bce_with_logits(logit: torch.Tensor, target: float, weight: float = 1.0):
+    """Returns (loss, accuracy): loss = weight * mean BCE-with-logits against the constant label `target`
+    (train_mscmrseg.py:233,286,316), accuracy = fraction of samples whose sigmoid(logit) >= 0.5 agrees with the label
+    (train_mscmrseg.py:290-296,:320-322)."""
+    return _BceLogits.apply(logit, float(target), float(weight))
+
+
 def launch_count() -> int:
     """Kernels launched by libpcuda in this process so far."""
     return int(_lib.lib().pcuda_launch_count())

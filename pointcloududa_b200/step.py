@@ -32,10 +32,10 @@ from dataclasses import dataclass
 from typing import Dict, Optional
 
 import torch
-import torch.nn.functional as F
 
 from . import dist as pdist
 from .networks.PointNetCls import PointNetCls, apply_bn_updates, deferred_bn_updates
+from .ops import bce_with_logits
 from .optim import FusedSGD
 from .utils.loss import batch_NN_loss, entropy_map
 
@@ -90,8 +90,6 @@ class AdversarialStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_post: Optional[torch.cuda.CUDAGraph] = None
         self._res = []
-        self._ones = torch.ones(B, 1, **f32)
-        self._zeros = torch.zeros(B, 1, **f32)
         self._side = None
         self.concurrent = concurrent
 
@@ -152,7 +150,7 @@ class AdversarialStep:
         vertT = I["vertT"].detach().requires_grad_(True)
         with deferred_bn_updates(sink_p2):
             D_out4 = self.d4(vertT.transpose(2, 1))[0]
-        loss_adv_point = cfg.dr * F.binary_cross_entropy_with_logits(D_out4, self._ones)
+        loss_adv_point, _ = bce_with_logits(D_out4, 1.0, cfg.dr)
         (gT,) = torch.autograd.grad(loss_adv_point, vertT)
         self.grad_vertT.copy_(gT)
         self._set_requires_grad(True)
@@ -166,17 +164,15 @@ class AdversarialStep:
                 entropy_map(I["oS"], activation=cfg.activation, normalize=cfg.normalize, return_prob=cfg.return_prob)
             with deferred_bn_updates(sink_p3):
                 D_out4, leaves = self._d4_fresh(I["vertS"].transpose(2, 1))
-            loss_D_same4 = F.binary_cross_entropy_with_logits(D_out4, self._ones)
+            loss_D_same4, acc_s = bce_with_logits(D_out4, 1.0)
             grads_s = torch.autograd.grad(loss_D_same4, leaves, allow_unused=True)
-            acc_s = (torch.sigmoid(D_out4.detach()) >= 0.5).float().mean()
 
         # ---- branch C (stream s2) — P4: discriminators on the target domain (label 0)
         with torch.cuda.stream(s2):
             with deferred_bn_updates(sink_p4):
                 D_out4, leaves = self._d4_fresh(I["vertT"].transpose(2, 1))
-            loss_D_diff_4 = F.binary_cross_entropy_with_logits(D_out4, self._zeros)
+            loss_D_diff_4, acc_t = bce_with_logits(D_out4, 0.0)
             grads_t = torch.autograd.grad(loss_D_diff_4, leaves, allow_unused=True)
-            acc_t = 1.0 - (torch.sigmoid(D_out4.detach()) >= 0.5).float().mean()
 
         # ---- join: parameter gradients into the flat bucket, BatchNorm buffers in the reference's pass order
         if self.concurrent:

@@ -966,3 +966,23 @@ def test_fused_sgd_matches_torch_sgd():
     # one-sided pack (second list absent)
     fopt.pack(ga, None, flat)
     assert torch.equal(flat, torch.cat([a.reshape(-1) for a in ga]))
+
+
+@pytest.mark.parametrize("target,weight,n", [(1.0, 1.0, 8), (0.0, 1.0, 32), (1.0, 0.01, 5), (0.0, 0.3, 70)])
+def test_bce_with_logits_matches_torch(target, weight, n):
+    """pcuda_bce_logits against F.binary_cross_entropy_with_logits + autograd + the accuracy expression of
+    train_mscmrseg.py:290-296."""
+    g = torch.Generator().manual_seed(int(n + 10 * target))
+    x = (torch.randn(n, 1, generator=g) * 3).to(DEV)
+    x[0] = 40.0
+    x[1] = -40.0
+    xr = x.clone().requires_grad_(True)
+    want = weight * F.binary_cross_entropy_with_logits(xr, torch.full_like(xr, target))
+    (gw,) = torch.autograd.grad(want, xr)
+    xo = x.clone().requires_grad_(True)
+    loss, acc = ops.bce_with_logits(xo, target, weight)
+    (go,) = torch.autograd.grad(loss * 2.0, xo)
+    assert abs(loss.item() - want.item()) <= 2e-6 * abs(want.item()) + 1e-9
+    assert max_rel(go.cpu().numpy() / 2.0, gw.cpu().numpy()) < 2e-6
+    pred = (torch.sigmoid(x) >= 0.5).float().mean().item()
+    assert abs(acc.item() - (pred if target >= 0.5 else 1.0 - pred)) < 1e-6

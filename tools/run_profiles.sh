@@ -15,6 +15,10 @@ timeout 300 python tools/step_profile.py cfg5_rank > gpurun_out/step_profile_cfg
 timeout 300 python tools/tc_stress.py > gpurun_out/tc_stress.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1100 --csv --log-file gpurun_out/launches_cfg2.csv python bench.py --steps 2 --warmup 3 --no-graph --skip-cpu --skip-large > gpurun_out/ncu_launches.log 2>&1; tail -1 gpurun_out/ncu_launches.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1100 --csv --log-file gpurun_out/launches_cfg5rank.csv python bench.py --steps 2 --warmup 3 --workload cfg5_rank --no-graph --skip-cpu --skip-large > gpurun_out/ncu_launches5.log 2>&1; tail -1 gpurun_out/ncu_launches5.log
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1100 --csv --log-file gpurun_out/traffic_cfg2.csv python bench.py --steps 2 --warmup 3 --no-graph --skip-cpu --skip-large > gpurun_out/ncu_traffic.log 2>&1; tail -1 gpurun_out/ncu_traffic.log | cut -c1-120
+timeout 300 python tools/time_layer.py > gpurun_out/time_layer.log 2>&1; grep -c "dbg=" gpurun_out/time_layer.log
+timeout 300 python tools/chamfer_probe.py quick > gpurun_out/chamfer_probe.log 2>&1; tail -2 gpurun_out/chamfer_probe.log
+(timeout 60 ./tools/micro/atomic_tail; timeout 60 ./tools/micro/carveout_switch) > gpurun_out/micro.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ws_kernel|pt_kernel' -c 12 -o gpurun_out/prof_${R}_mlp python tools/prof_kernels.py mlp > gpurun_out/ncu_mlp.log 2>&1; tail -1 gpurun_out/ncu_mlp.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'chamfer_nn' -c 4 -o gpurun_out/prof_${R}_chamfer python tools/prof_kernels.py chamfer > gpurun_out/ncu_chamfer.log 2>&1; tail -1 gpurun_out/ncu_chamfer.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'entropy' -c 8 -o gpurun_out/prof_${R}_entropy python tools/prof_kernels.py entropy > gpurun_out/ncu_entropy.log 2>&1; tail -1 gpurun_out/ncu_entropy.log
