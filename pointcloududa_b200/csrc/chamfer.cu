@@ -321,7 +321,8 @@ chamfer_nn2_kernel(const float* __restrict__ x, const float* __restrict__ y, int
 constexpr float kFilterMargin = 1.9073486328125e-06f;   // 2^-19  (> (13 + rounding of thr) * 2^-24)
 constexpr float kFilterAbs = 1e-36f;                    // covers underflow in the products
 constexpr int kSeedStride = 16;                         // seed pass: every 16th column pair
-constexpr int kSeedMinCols = 2048;                      // below this the seed pass does not pay
+constexpr int kSeedMinCols = 2048;                      // below this the seed pass does not pay ...
+constexpr int kSeedMaxCols = 8192;                      // ... nor above (measured: +4 % at 4096, -1 % at 16384 columns)
 
 // 128-bit shared-memory load from a 32-bit shared address: the scan walks the tile with one register and
 // immediate offsets (through generic pointers the compiler re-derived the shared window base — S2UR,
@@ -343,12 +344,12 @@ __device__ __forceinline__ void nn_update_lazy(float P, int j, float& bestP, int
   }
 }
 
-template <int R, int THREADS>
-__global__ void __launch_bounds__(THREADS, R == 4 ? 7 : 1)
+template <int R, int THREADS, int MINB = (R == 4 ? 8 : 1)>
+__global__ void __launch_bounds__(THREADS, MINB)
 chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M,
                    float* __restrict__ d1, int64_t* __restrict__ i1, float* __restrict__ d2,
                    int64_t* __restrict__ i2, FwdWs* __restrict__ ws, float* __restrict__ loss,
-                   int tiles_x, int tiles_y, int B) {
+                   int tiles_x, int tiles_y, int B, int seed_stride, int seed_forced) {
   __shared__ float4 tileA[kTileJ / 2 + 1];   // + 1: the scan prefetches one entry ahead
   __shared__ float4 tileB[kTileJ / 2 + 1];
   __shared__ float warp_rmax[THREADS / 32];
@@ -440,7 +441,7 @@ chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int
     };
 
     // ---- seed pass: an upper bound of every row's final minimum from every kSeedStride-th column pair
-    if (nc >= kSeedMinCols) {
+    if (nc >= kSeedMinCols && (nc <= kSeedMaxCols || seed_forced) && seed_stride > 0) {
       float qmin[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) qmin[r] = INFINITY;
@@ -453,7 +454,7 @@ chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int
         fill_tile(j0, tj, rmax, all_same);
         rmax_all = fmaxf(rmax_all, rmax);
 #pragma unroll 2
-        for (int t = 0; t < npair; t += kSeedStride) {
+        for (int t = 0; t < npair; t += seed_stride) {
           const float4 A = lds128(sA + 16 * t);
           const float4 Bv = lds128(sB + 16 * t);
           const float2 cx = make_float2(A.x, A.y), cy = make_float2(A.z, A.w);
@@ -679,12 +680,18 @@ extern "C" int pcuda_chamfer_fwd(const float* x, const float* y, int B, int N, i
                                                  p.tiles_x, p.tiles_y, B)
 #define PCUDA_LAUNCH_NN3(RR, TT)                                                             \
   chamfer_nn3_kernel<RR, TT><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,       \
-                                                  p.tiles_x, p.tiles_y, B)
+                                                  p.tiles_x, p.tiles_y, B, seed_stride, seed_tune > 0)
+#define PCUDA_LAUNCH_NN3B(RR, TT, MB)                                                        \
+  chamfer_nn3_kernel<RR, TT, MB><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,   \
+                                                      p.tiles_x, p.tiles_y, B, seed_stride, seed_tune > 0)
 #define PCUDA_LAUNCH_NN2(RR, TT)                                                             \
   chamfer_nn2_kernel<RR, TT><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,       \
                                                   p.tiles_x, p.tiles_y, B)
   // tuning value >= 200000 selects the packed exact kernel (v2), >= 100000 the scalar one (v1), for A/B runs
   const int variant = tuning(TUNE_CHAMFER_ROWS) / 100000;
+  // seed pass: every seed_stride-th column pair (tuning key 5: 0 = default, < 0 = no seed pass)
+  const int seed_tune = tuning(TUNE_CHAMFER_SEED);
+  const int seed_stride = seed_tune == 0 ? kSeedStride : (seed_tune < 0 ? 0 : seed_tune);
   if (variant == 1) {
     if (p.R >= 4) PCUDA_LAUNCH_NN(4, 128);
     else if (p.R == 2) PCUDA_LAUNCH_NN(2, 128);
@@ -696,6 +703,8 @@ extern "C" int pcuda_chamfer_fwd(const float* x, const float* y, int B, int N, i
     else if (p.R == 2) PCUDA_LAUNCH_NN2(2, 128);
     else if (p.threads == 128) PCUDA_LAUNCH_NN2(1, 128);
     else PCUDA_LAUNCH_NN2(1, 64);
+  } else if (variant == 3) {
+    PCUDA_LAUNCH_NN3B(4, 128, 7);      // A/B: 72 registers (7 CTAs per SM) instead of 64 with a spilling slow path (+3 %)
   } else {
     if (p.R == 8) PCUDA_LAUNCH_NN3(8, 128);
     else if (p.R == 4) PCUDA_LAUNCH_NN3(4, 128);
@@ -706,6 +715,7 @@ extern "C" int pcuda_chamfer_fwd(const float* x, const float* y, int B, int N, i
 #undef PCUDA_LAUNCH_NN
 #undef PCUDA_LAUNCH_NN2
 #undef PCUDA_LAUNCH_NN3
+#undef PCUDA_LAUNCH_NN3B
   count_launch(1);
   return check_launch("chamfer_nn_kernel");
 }

@@ -20,7 +20,7 @@ void count_launch(int n = 1);        // bench accounting: kernels launched by th
 int sm_count();
 int tuning(int key);
 
-enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_FP32 = 2, TUNE_MLP_TC_MASK = 3, TUNE_MLP_EPI_DEBUG = 4, TUNE_NKEYS = 8 };
+enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_FP32 = 2, TUNE_MLP_TC_MASK = 3, TUNE_MLP_EPI_DEBUG = 4, TUNE_CHAMFER_SEED = 5, TUNE_MLP_NO_FORK = 6, TUNE_NKEYS = 8 };
 
 #define PCUDA_REQUIRE(cond, code, ...)                 \
   do {                                                 \

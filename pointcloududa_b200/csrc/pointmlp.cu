@@ -21,6 +21,9 @@
 //     with Q = W^T diag(kappa) W  [Cin x Cin]  and  Ghat the centred Gram matrix of the layer's
 //     input — an 8x cut in backward FLOPs for 128 -> 1024 (SURVEY.md §9 gives the dense formulas).
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "pointmlp_common.cuh"
@@ -1259,7 +1262,7 @@ FwdWs carve_fwd(const Shape& s, const pcuda_mlp_layer_t* layers, void* base) {
 }
 
 struct BwdWs {
-  double* sums; float* alpha; float* kappa; float* partial;
+  double* sums; float* alpha; float* kappa; float* partial; float* qpartial;
   float *coef, *gsel, *gyh, *Ghat, *Q, *abar, *u;
   double *colsum, *G, *abar_d;
   float* dzbuf[2];
@@ -1288,6 +1291,7 @@ BwdWs carve_bwd(const Shape& s, const pcuda_mlp_layer_t* layers, void* base) {
     w.abar = cv.take<float>(K);
     w.u = cv.take<float>(K);
     w.abar_d = cv.take<double>(K);
+    w.qpartial = cv.take<float>(static_cast<size_t>(kPoolQSplits) * K * K);   // pool_q runs beside the Gram chain
     if (tc::supports(static_cast<int>(K))) w.qpack = cv.take<uint8_t>(tc::w_pack_bytes(static_cast<int>(K), static_cast<int>(K)));
   }
   w.dzbuf[0] = cv.take<float>(static_cast<size_t>(s.M) * s.maxC);
@@ -1308,6 +1312,59 @@ BwdWs carve_bwd(const Shape& s, const pcuda_mlp_layer_t* layers, void* base) {
   if (wt_max) w.wtpack = cv.take<uint8_t>(wt_max);
   w.bytes = cv.off;
   return w;
+}
+
+
+// ---- fork / join inside one library call -----------------------------------------------------------
+// The pooled layer's backward is a chain of ~14 small launches of which several are independent (the
+// Gram-matrix side: column sums, Gram, centring; the selection side: coefficients, Q = W^T K W; the weight
+// gradient).  At the reference's sizes each launch is latency (~3-10 us), so the independent sides run on
+// an auxiliary stream tied to the caller's stream with events — ordinary stream semantics, and under
+// CUDA-graph capture the event edges become graph dependencies (the auxiliary stream joins the capture).
+// One auxiliary stream + 3 events per caller stream, created on first use (never freed: a handful per
+// process).  Creation is an ordinary runtime call, legal during capture.
+struct Aux {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, side = nullptr, done = nullptr;
+};
+static std::mutex g_aux_mu;
+static std::map<std::pair<int, cudaStream_t>, Aux> g_aux;
+
+static std::map<int, std::vector<Aux>> g_aux_pool;     // per device: spare (stream, events) sets, created outside of any capture
+
+static bool make_aux(Aux& a) {
+  if (cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&a.side, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
+
+// The auxiliary set of caller stream `st` (nullptr: none available -> the caller stays on one stream).
+// Streams are only ever CREATED while `st` is not capturing (a pool of spares is filled then); a caller
+// stream first seen during a capture takes a spare.
+static Aux* aux_for(cudaStream_t st) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  const bool capturing = cs != cudaStreamCaptureStatusNone;
+  std::lock_guard<std::mutex> lk(g_aux_mu);
+  std::vector<Aux>& pool = g_aux_pool[dev];
+  if (!capturing) {
+    while (pool.size() < 8) {
+      Aux a;
+      if (!make_aux(a)) break;
+      pool.push_back(a);
+    }
+  }
+  auto key = std::make_pair(dev, st);
+  auto it = g_aux.find(key);
+  if (it != g_aux.end()) return &it->second;
+  if (pool.empty()) return nullptr;
+  Aux a = pool.back();
+  pool.pop_back();
+  return &g_aux.emplace(key, a).first->second;
 }
 
 int validate(const char* who, int B, int N, int L, const pcuda_mlp_layer_t* layers, int pool) {
@@ -1489,6 +1546,7 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
         apack[l + 1] = w.apack[l + 1];
       }
 
+  Aux* dw_aux = nullptr;   // set when the pooled layer's weight gradient runs on the auxiliary stream
   int cur = 0;      // dzbuf[cur] holds dz of layer `top`
   int top = L - 1;  // highest layer whose dz is dense and stored
   const pcuda_mlp_layer_t& last = layers[L - 1];
@@ -1500,6 +1558,27 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     float* ka = kappa + off[L - 1];
     const int64_t bc = static_cast<int64_t>(B) * C;
     const int64_t kk = static_cast<int64_t>(K) * K;
+    // selection side on the caller's stream, Gram side on the auxiliary stream (see Aux above); tuning key 6
+    // keeps everything on one stream (A/B)
+    Aux* ax = tuning(TUNE_MLP_NO_FORK) ? nullptr : aux_for(st);
+    cudaStream_t sa = ax ? ax->s : st;
+    if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sa, ax->fork, 0); }
+    // -- Gram side: centred Gram matrix of the pooled layer's input (train-mode BN correction terms only)
+    int Sg = S32;
+    act_colsum_kernel<<<dim3(S32, (K + 31) / 32), 256, 0, sa>>>(src, s.M, chunk32, w.colsum);
+    launches += 1;
+    if (tc_on(precision, TC_GRAM) && a_in && tc::pt_supports(K, K, true)) {
+      Sg = tc::pt_splits(tl, (K + 127) / 128);
+      if (int rc = tc::gram(tl, a_in, K, Sg, partial, sa)) return rc;
+    } else {
+      point_contract_kernel<1><<<dim3(S32, (K + TM - 1) / TM, (K + TN - 1) / TN), kThreads, 0, sa>>>(DySrc{}, src, src, s.M, chunk32, K, K, partial);
+      launches += 1;
+    }
+    reduce_partials_kernel<double><<<static_cast<int>((kk + 255) / 256), 256, 0, sa>>>(partial, kk, Sg, w.G);
+    abar_kernel<<<(K + 7) / 8, 256, 0, sa>>>(w.colsum, S32, K, count, w.abar, w.abar_d);
+    gram_center_kernel<<<static_cast<int>((kk + 255) / 256), 256, 0, sa>>>(w.abar_d, w.G, K, count, w.Ghat);
+    if (ax) cudaEventRecord(ax->side, sa);
+    // -- selection side: per-(cloud, channel) coefficients, alpha / kappa, Q = W^T diag(kappa) W
     pool_sel_kernel<<<static_cast<int>((bc * 32 + 255) / 256), 256, 0, st>>>(src, last.weight, last.bias, last.save_mean,
                                                                             last.save_invstd, last.gamma, last.relu, out, pool_arg,
                                                                             grad_out, B, N, C, w.coef, w.gsel, w.gyh);
@@ -1507,27 +1586,13 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     pool_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(w.gsel, w.gyh, last.save_invstd, last.gamma, B, C, count, train, al, ka,
                                                       want_last ? last.grad_gamma : nullptr, want_last ? last.grad_beta : nullptr,
                                                       want_last ? last.grad_bias : nullptr);
-    launches += 2;
-    // centred Gram matrix of the pooled layer's input (train-mode BN correction terms only)
-    int Sg = S32;
-    act_colsum_kernel<<<dim3(S32, (K + 31) / 32), 256, 0, st>>>(src, s.M, chunk32, w.colsum);
-    launches += 1;
-    if (tc_on(precision, TC_GRAM) && a_in && tc::pt_supports(K, K, true)) {
-      Sg = tc::pt_splits(tl, (K + 127) / 128);
-      if (int rc = tc::gram(tl, a_in, K, Sg, partial, st)) return rc;
-    } else {
-      point_contract_kernel<1><<<dim3(S32, (K + TM - 1) / TM, (K + TN - 1) / TN), kThreads, 0, st>>>(DySrc{}, src, src, s.M, chunk32, K, K, partial);
-      launches += 1;
-    }
-    reduce_partials_kernel<double><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(partial, kk, Sg, w.G);
-    abar_kernel<<<(K + 7) / 8, 256, 0, st>>>(w.colsum, S32, K, count, w.abar, w.abar_d);
-    gram_center_kernel<<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(w.abar_d, w.G, K, count, w.Ghat);
-    pool_q_kernel<<<dim3((K + 31) / 32, (K + 31) / 32, kPoolQSplits), 256, 0, st>>>(last.weight, ka, C, K, partial);
-    reduce_partials_kernel<float><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(partial, kk, kPoolQSplits, w.Q);
+    pool_q_kernel<<<dim3((K + 31) / 32, (K + 31) / 32, kPoolQSplits), 256, 0, st>>>(last.weight, ka, C, K, w.qpartial);
+    reduce_partials_kernel<float><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(w.qpartial, kk, kPoolQSplits, w.Q);
+    // -- join: u needs Q (this stream) and abar (Gram side)
+    if (ax) cudaStreamWaitEvent(st, ax->side, 0);
     pool_u_kernel<<<(K + 31) / 32, 1024, 0, st>>>(last.weight, al, w.Q, w.abar, C, K, w.u);
-    launches += 6;
+    launches += 9;
     if (last.grad_weight) {
-      const int64_t ck = static_cast<int64_t>(C) * K;
       const size_t dw_smem = sizeof(float) * ((kDwCh * (K + 2 * static_cast<size_t>(B)) + 3) & ~static_cast<size_t>(3)) +
                              sizeof(double) * kDwParts * 128 * kDwCh;
       PCUDA_REQUIRE(dw_smem <= 200 * 1024, PCUDA_E_UNSUPPORTED, "pointmlp_bwd: batch %d too large for the pooled wgrad kernel", B);
@@ -1536,7 +1601,11 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
         cudaFuncSetAttribute(pool_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         dw_attr_done = true;
       }
-      pool_dw_kernel<<<(C + kDwCh - 1) / kDwCh, 128 * kDwParts, dw_smem, st>>>(src, last.weight, w.coef, pool_arg, ka, w.abar, w.Ghat, B, N, C, train, last.grad_weight);
+      // the pooled layer's weight gradient reads coef / kappa (this stream) and abar / Ghat (Gram side) and writes
+      // only grad_weight: it runs on the auxiliary stream beside the dgrad kernels below; joined before returning
+      if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sa, ax->fork, 0); dw_aux = ax; }
+      pool_dw_kernel<<<(C + kDwCh - 1) / kDwCh, 128 * kDwParts, dw_smem, sa>>>(src, last.weight, w.coef, pool_arg, ka, w.abar, w.Ghat, B, N, C, train, last.grad_weight);
+      if (ax) cudaEventRecord(ax->done, sa);
       launches += 1;
     }
     if (L >= 2 || grad_x) {
@@ -1630,6 +1699,7 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
       cur ^= 1;
     }
   }
+  if (dw_aux != nullptr) cudaStreamWaitEvent(st, dw_aux->done, 0);      // the pooled weight gradient (auxiliary stream)
   count_launch(launches);
   return check_launch("pointmlp_bwd");
 }

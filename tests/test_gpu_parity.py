@@ -139,8 +139,8 @@ def test_entropy_empty_and_errors():
 CH_CASES = ["near_b3_n64", "near_b2_n300", "uniform_b2_n257", "identical_dups_b2_n128",
             "zero_gt_b2_n96", "shifted_b2_n80"]
 # (tuning value) kernel variants: prefiltered packed-FP32 (default) R=1/64thr, 1, 2, 4, 8 rows;
-# exact packed-FP32 (2xxxxx) R=4, 8, 1; scalar (1xxxxx) R=4, R=1
-VARIANTS = [0, 1064, 1128, 2128, 4128, 8128, 204128, 208128, 201064, 104128, 101064]
+# 3xxxxx = prefiltered R=4 at 72 registers; exact packed-FP32 (2xxxxx) R=4, 8, 1; scalar (1xxxxx) R=4, R=1
+VARIANTS = [0, 1064, 1128, 2128, 4128, 8128, 304128, 204128, 208128, 201064, 104128, 101064]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)

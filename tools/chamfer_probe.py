@@ -42,15 +42,22 @@ def main():
             pairs = 2.0 * B * N * N
             variants = (0, 1064, 1128, 2128, 4128, 8128, 200000, 204128, 208128)
             if len(sys.argv) > 1 and sys.argv[1] == "quick":
-                variants = (0, 2128, 4128, 8128, 204128)
+                variants = (0, 4128, 304128, 204128, (4128, 8), (4128, 32), (4128, -1))
             for var in variants:
                 if N >= 8192 and var in (1064, 1128):
                     continue
+                seed = 0
+                if isinstance(var, tuple):
+                    var, seed = var
                 ops.tune(1, var)
+                ops.tune(5, seed)
                 try:
                     ms = timeit(lambda: ops.chamfer_nn(x, y), 5 if N > 4096 else 10, flush)
                 finally:
                     ops.tune(1, 0)
+                    ops.tune(5, 0)
+                if seed:
+                    var = f"{var}_seed{seed}"
                 out[f"{mode}/B{B}_N{N}/var{var}"] = dict(ms=ms, tpairs_s=pairs / ms / 1e9)
                 print(f"{mode} B{B} N{N} var{var}: {ms:.4f} ms  {pairs / ms / 1e9:.3f} Tpairs/s", flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
