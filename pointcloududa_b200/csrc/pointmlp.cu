@@ -1325,7 +1325,7 @@ BwdWs carve_bwd(const Shape& s, const pcuda_mlp_layer_t* layers, void* base) {
 // process).  Creation is an ordinary runtime call, legal during capture.
 struct Aux {
   cudaStream_t s = nullptr;
-  cudaEvent_t fork = nullptr, side = nullptr, done = nullptr;
+  cudaEvent_t fork = nullptr, side = nullptr, done = nullptr, wfork = nullptr, wdone = nullptr;
 };
 static std::mutex g_aux_mu;
 static std::map<std::pair<int, cudaStream_t>, Aux> g_aux;
@@ -1336,7 +1336,9 @@ static bool make_aux(Aux& a) {
   if (cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
   if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&a.side, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+      cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&a.wfork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&a.wdone, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
   return true;
 }
 
@@ -1546,7 +1548,11 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
         apack[l + 1] = w.apack[l + 1];
       }
 
-  Aux* dw_aux = nullptr;   // set when the pooled layer's weight gradient runs on the auxiliary stream
+  // auxiliary stream of this call (see Aux above); tuning key 6 keeps everything on the caller's stream (A/B)
+  Aux* ax = tuning(TUNE_MLP_NO_FORK) ? nullptr : aux_for(st);
+  cudaStream_t sa = ax ? ax->s : st;
+  bool aux_used = false;   // something was issued on the auxiliary stream: join before returning
+  bool wgrad_pending = false;   // a weight-gradient chain of the previous layer may still be running there
   int cur = 0;      // dzbuf[cur] holds dz of layer `top`
   int top = L - 1;  // highest layer whose dz is dense and stored
   const pcuda_mlp_layer_t& last = layers[L - 1];
@@ -1558,11 +1564,8 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     float* ka = kappa + off[L - 1];
     const int64_t bc = static_cast<int64_t>(B) * C;
     const int64_t kk = static_cast<int64_t>(K) * K;
-    // selection side on the caller's stream, Gram side on the auxiliary stream (see Aux above); tuning key 6
-    // keeps everything on one stream (A/B)
-    Aux* ax = tuning(TUNE_MLP_NO_FORK) ? nullptr : aux_for(st);
-    cudaStream_t sa = ax ? ax->s : st;
-    if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sa, ax->fork, 0); }
+    // selection side on the caller's stream, Gram side on the auxiliary stream
+    if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sa, ax->fork, 0); aux_used = true; }
     // -- Gram side: centred Gram matrix of the pooled layer's input (train-mode BN correction terms only)
     int Sg = S32;
     act_colsum_kernel<<<dim3(S32, (K + 31) / 32), 256, 0, sa>>>(src, s.M, chunk32, w.colsum);
@@ -1603,9 +1606,8 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
       }
       // the pooled layer's weight gradient reads coef / kappa (this stream) and abar / Ghat (Gram side) and writes
       // only grad_weight: it runs on the auxiliary stream beside the dgrad kernels below; joined before returning
-      if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sa, ax->fork, 0); dw_aux = ax; }
+      if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sa, ax->fork, 0); }
       pool_dw_kernel<<<(C + kDwCh - 1) / kDwCh, 128 * kDwParts, dw_smem, sa>>>(src, last.weight, w.coef, pool_arg, ka, w.abar, w.Ghat, B, N, C, train, last.grad_weight);
-      if (ax) cudaEventRecord(ax->done, sa);
       launches += 1;
     }
     if (L >= 2 || grad_x) {
@@ -1662,25 +1664,34 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
     const bool dgrad_side = l - 1 >= 0 && (Kp % 64) == 0 && apack[l] != nullptr;
     const bool dgrad_tc = need_dgrad && tc_on(precision, TC_DGRAD) && w.dypack && w.wtpack && (Kp % 8) == 0 &&
                           tc::dgrad_fits(Kp, C, dgrad_side);
+    // the previous layer's weight-gradient chain (auxiliary stream) read dypack / dzbuf[cur ^ 1]: both are
+    // rewritten below, so it has to be over first — it ran beside that layer's dgrad, which took longer
+    if (wgrad_pending) { cudaStreamWaitEvent(st, ax->wdone, 0); wgrad_pending = false; }
     if (wgrad_tc || dgrad_tc)
       if (int rc = tc::pack_dy(dys, tl, w.dypack, st)) return rc;      // dy_l as bf16 slabs, once for both GEMMs
     if (want_w) {
+      // dW_l and da_{l-1} both start from dy_l and are independent: the weight gradient (contraction + split
+      // reduction) runs on the auxiliary stream beside the dgrad GEMM
+      const bool fork_w = ax != nullptr && need_dgrad;
+      cudaStream_t sw = fork_w ? sa : st;
+      if (fork_w) { cudaEventRecord(ax->wfork, st); cudaStreamWaitEvent(sa, ax->wfork, 0); aux_used = true; }
       const int64_t ck = static_cast<int64_t>(C) * Kp;
       int Sw = S32;
       if (wgrad_tc) {
         Sw = tc::pt_splits(tl, (C + 127) / 128);
-        if (int rc = tc::wgrad_layer(tl, w.dypack, C, apack[l], Kp, Sw, partial, st)) return rc;
+        if (int rc = tc::wgrad_layer(tl, w.dypack, C, apack[l], Kp, Sw, partial, sw)) return rc;
       } else if (narrow_ok(Kp, C)) {
         Sw = std::min(narrow_grid(s.M, C), s.S);
         const size_t smem = sizeof(float) * 1024 * static_cast<size_t>(Kp);   // [pslots][C][Kp], pslots * C = 1024
-        wgrad_narrow_kernel<<<Sw, kNarrowThreads, smem, st>>>(dys, src_of(l - 1), s.M, partial);
+        wgrad_narrow_kernel<<<Sw, kNarrowThreads, smem, sw>>>(dys, src_of(l - 1), s.M, partial);
         launches += 1;
       } else {
-        point_contract_kernel<0><<<dim3(S32, (C + TM - 1) / TM, (Kp + TN - 1) / TN), kThreads, 0, st>>>(dys, ActSrc{}, src_of(l - 1), s.M, chunk32, C, Kp, partial);
+        point_contract_kernel<0><<<dim3(S32, (C + TM - 1) / TM, (Kp + TN - 1) / TN), kThreads, 0, sw>>>(dys, ActSrc{}, src_of(l - 1), s.M, chunk32, C, Kp, partial);
         launches += 1;
       }
-      reduce_partials_kernel<float><<<static_cast<int>((ck + 255) / 256), 256, 0, st>>>(partial, ck, Sw, y.grad_weight);
+      reduce_partials_kernel<float><<<static_cast<int>((ck + 255) / 256), 256, 0, sw>>>(partial, ck, Sw, y.grad_weight);
       launches += 1;
+      if (fork_w) { cudaEventRecord(ax->wdone, sa); wgrad_pending = true; }
     }
     if (need_dgrad) {
       const DgradOut o = dgrad_out(l - 1, dzbuf[cur ^ 1]);
@@ -1699,7 +1710,10 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
       cur ^= 1;
     }
   }
-  if (dw_aux != nullptr) cudaStreamWaitEvent(st, dw_aux->done, 0);      // the pooled weight gradient (auxiliary stream)
+  if (aux_used) {   // join: the pooled weight gradient / the last weight-gradient chain
+    cudaEventRecord(ax->done, sa);
+    cudaStreamWaitEvent(st, ax->done, 0);
+  }
   count_launch(launches);
   return check_launch("pointmlp_bwd");
 }
