@@ -1438,11 +1438,21 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
   double* st_l = w.stats;
   float* piv_l = w.pivots;
   int launches = 0;
-  // bf16 copies of the tensor-core layers' weights
-  for (int l = 0; l < L; ++l)
-    if (layer_tc(l))
-      if (int rc = tc::pack_w(layers[l].weight, layers[l].cout, layers[l].cin, false, w.wpack[l], st,
-                              (pool && l == L - 1) ? layers[l].gamma : nullptr)) return rc;
+  // bf16 copies of the tensor-core layers' weights: independent of the activations, so they are packed on the
+  // auxiliary stream (see Aux below) while the first layer runs; joined before the first tensor-core GEMM
+  bool any_pack = false;
+  for (int l = 0; l < L; ++l) any_pack = any_pack || layer_tc(l);
+  Aux* ax = (any_pack && !tuning(TUNE_MLP_NO_FORK)) ? aux_for(st) : nullptr;
+  bool packs_pending = false;
+  if (any_pack) {
+    cudaStream_t sp = ax ? ax->s : st;
+    if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sp, ax->fork, 0); }
+    for (int l = 0; l < L; ++l)
+      if (layer_tc(l))
+        if (int rc = tc::pack_w(layers[l].weight, layers[l].cout, layers[l].cin, false, w.wpack[l], sp,
+                                (pool && l == L - 1) ? layers[l].gamma : nullptr)) return rc;
+    if (ax) { cudaEventRecord(ax->done, sp); packs_pending = true; }
+  }
   auto layer_narrow = [&](int l) {
     return !layer_tc(l) && !(pool && l == L - 1) && layers[l].y != nullptr && narrow_ok(layers[l].cin, layers[l].cout);
   };
@@ -1462,6 +1472,7 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
       // tensor-core layer: one pass packs a_{l-1} = relu?(bn(y_{l-1})) as bf16 slabs, the GEMM streams them.
       // Statistics are accumulated bias-free, i.e. centred on pivot = bias.
       if (int rc = tc::pack_act(src, tl, w.apack[l], st)) return rc;
+      if (packs_pending) { cudaStreamWaitEvent(st, ax->done, 0); packs_pending = false; }
       if (int rc = tc::fwd_layer(tl, w.apack[l], w.wpack[l], y, is_pool, st_l, w.keys, st)) return rc;
       pivot_used = y.bias ? y.bias : w.zeros;
     } else if (layer_narrow(l)) {

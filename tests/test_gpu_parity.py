@@ -565,6 +565,7 @@ TC_STACKS = [
     ([3, 64, 128, 1024], [True, True, True], 4, 64),        # STN3d trunk, partial tile
     ([3, 64, 128, 1024], [True, True, False], 8, 300),      # main trunk at the reference's cloud size (cfg-1/2)
     ([3, 64, 128, 1024], [True, True, False], 3, 1024),     # cfg-3 cloud size, full tiles
+    ([3, 64, 128, 1024], [True, True, False], 2, 4096),     # cfg-5 cloud size: 16 tiles per cloud, N > C
     ([64, 64, 128, 1024], [True, True, True], 3, 70),       # STNkd trunk: first layer already wide
     ([64, 128, 1024], [True, False], 4, 100),               # feature-transform post stack
     ([3, 8, 64, 128, 256, 512, 1024], [True, True, True, True, False, True], 3, 40),   # ext trunk (K up to 512)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# r1q: 2-GPU bench lines (weak scaling): cfg2 and cfg5 per-rank shard
+# 2-GPU bench lines (weak scaling): cfg2 and cfg5 per-rank shard
 mkdir -p gpurun_out
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 50 --warmup 5 --skip-large > gpurun_out/bench_cfg2_n2.log 2>&1; echo "exit $?" >> gpurun_out/bench_cfg2_n2.log; tail -c 300 gpurun_out/bench_cfg2_n2.log
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 3 --workload cfg5_rank --skip-large > gpurun_out/bench_cfg5rank_n2.log 2>&1; echo "exit $?" >> gpurun_out/bench_cfg5rank_n2.log; tail -c 300 gpurun_out/bench_cfg5rank_n2.log
