@@ -77,12 +77,13 @@ class AdversarialStep:
         self._world = 1
         B, C, H, W, N = cfg.B, cfg.C, cfg.H, cfg.W, cfg.N
         f32 = dict(dtype=torch.float32, device=device)
-        self.inputs: Dict[str, torch.Tensor] = {
-            "oS": torch.zeros(B, C, H, W, **f32), "oT": torch.zeros(B, C, H, W, **f32),
-            "grad_mapT": torch.zeros(B, C, H, W, **f32),
-            "vertS": torch.zeros(B, N, 3, **f32), "vertT": torch.zeros(B, N, 3, **f32),
-            "vertexA": torch.zeros(B, N, 3, **f32), "vertexB": torch.zeros(B, N, 3, **f32),
-        }
+        # all inputs of a step are views of ONE flat buffer (every view 256-byte aligned), so a caller can move a
+        # whole step's inputs with a single copy (`inputs_flat`; `input_layout()` gives the same views of any
+        # other flat tensor, e.g. a pinned host staging buffer)
+        self._input_shapes = {"oS": (B, C, H, W), "oT": (B, C, H, W), "grad_mapT": (B, C, H, W),
+                              "vertS": (B, N, 3), "vertT": (B, N, 3), "vertexA": (B, N, 3), "vertexB": (B, N, 3)}
+        self.inputs_flat = torch.zeros(self.input_numel(), **f32)
+        self.inputs: Dict[str, torch.Tensor] = self.input_layout(self.inputs_flat)
         self.result = torch.zeros(len(RESULT_FIELDS), **f32)
         self.grad_oT = torch.zeros(B, C, H, W, **f32)
         self.grad_vertS = torch.zeros(B, N, 3, **f32)
@@ -94,6 +95,26 @@ class AdversarialStep:
         self.concurrent = concurrent
 
     # -- inputs -----------------------------------------------------------------------------------
+    def _input_offsets(self):
+        offs, off = {}, 0
+        for k, shp in self._input_shapes.items():
+            n = 1
+            for d in shp:
+                n *= d
+            offs[k] = (off, n, shp)
+            off += (n + 63) // 64 * 64          # 256-byte aligned views
+        return offs, off
+
+    def input_numel(self) -> int:
+        return self._input_offsets()[1]
+
+    def input_layout(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """The step's input tensors as views of `flat` (float32, input_numel() elements)."""
+        offs, total = self._input_offsets()
+        if flat.numel() != total or flat.dtype != torch.float32:
+            raise ValueError(f"expected a float32 tensor of {total} elements")
+        return {k: flat[o:o + n].view(shp) for k, (o, n, shp) in offs.items()}
+
     def load_inputs(self, host: Dict[str, torch.Tensor], non_blocking: bool = True) -> int:
         """Host (pinned) -> device copy of one step's inputs. Returns bytes copied."""
         n = 0
