@@ -400,7 +400,7 @@ bn_finalize_pivot_kernel(const double* __restrict__ stats, const float* __restri
 __global__ void pool_finalize_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ mean,
                                      const float* __restrict__ invstd, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, int relu, int B, int C,
-                                     float* __restrict__ out, int32_t* __restrict__ arg) {
+                                     float* __restrict__ out, int32_t* __restrict__ arg, BnRaw raw) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<int64_t>(B) * C) return;
   const int c = static_cast<int>(i % C);
@@ -408,8 +408,11 @@ __global__ void pool_finalize_kernel(const unsigned long long* __restrict__ keys
   const float vv = ordered_to_float(static_cast<uint32_t>(key >> 32));
   const int n = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull));
   const float g = gamma[c];
-  const float y = g > 0.f ? vv : (g < 0.f ? -vv : mean[c]);
-  out[i] = bn_act(y, mean[c], invstd[c], g, beta[c], relu);
+  float mu, is;
+  if (raw.stats != nullptr) bn_raw_channel(raw, c, C, i < C, mu, is);      // finalise-on-read; cloud 0's threads write
+  else { mu = mean[c]; is = invstd[c]; }
+  const float y = g > 0.f ? vv : (g < 0.f ? -vv : mu);
+  out[i] = bn_act(y, mu, is, g, beta[c], relu);
   arg[i] = g == 0.f ? 0 : n;   // gamma == 0: every point ties at beta and the first one wins
 }
 
@@ -1463,6 +1466,7 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
                                                  layers[0].cout, piv_l);
     launches += 1;
   }
+  BnRaw raw_prev{};     // raw sums of the previous layer when its BatchNorm is finalised by this layer's operand packer
   for (int l = 0; l < L; ++l) {
     const pcuda_mlp_layer_t& y = layers[l];
     const ActSrc src = l == 0 ? input_src(x, sxb, sxc, sxn, N, y.cin) : layer_src(layers[l - 1], N);
@@ -1471,7 +1475,8 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
     if (layer_tc(l)) {
       // tensor-core layer: one pass packs a_{l-1} = relu?(bn(y_{l-1})) as bf16 slabs, the GEMM streams them.
       // Statistics are accumulated bias-free, i.e. centred on pivot = bias.
-      if (int rc = tc::pack_act(src, tl, w.apack[l], st)) return rc;
+      if (int rc = tc::pack_act(src, tl, w.apack[l], st, raw_prev.stats ? &raw_prev : nullptr)) return rc;
+      raw_prev = BnRaw{};
       if (packs_pending) { cudaStreamWaitEvent(st, ax->done, 0); packs_pending = false; }
       if (int rc = tc::fwd_layer(tl, w.apack[l], w.wpack[l], y, is_pool, st_l, w.keys, st)) return rc;
       pivot_used = y.bias ? y.bias : w.zeros;
@@ -1486,14 +1491,23 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
         mlp_fwd_kernel<false><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, nullptr);
       launches += 1;
     }
-    // finalise this layer's BN; if an FP32 layer follows, compute its pivot in the same launch
+    // finalise this layer's BN.  When the only consumer of its output is the operand packer of a tensor-core
+    // layer, or the pooled-output kernel, that kernel finalises from the raw sums itself (BnRaw): no one-block
+    // launch between the GEMM and its consumer.  Otherwise: the finalise kernel; if an FP32 layer follows, it
+    // computes that layer's pivot in the same launch.
     const bool next_piv = l + 1 < L && !layer_tc(l + 1) && !layer_narrow(l + 1);
-    bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(st_l, pivot_used, y.cout, static_cast<double>(s.M), eps, momentum, train,
-                                                 y.save_mean, y.save_invstd, y.running_mean, y.running_var,
-                                                 next_piv ? layer_src(y, N) : ActSrc{}, next_piv ? layers[l + 1].weight : nullptr,
-                                                 next_piv ? layers[l + 1].bias : nullptr, next_piv ? layers[l + 1].cout : 0,
-                                                 piv_l + y.cout);
-    launches += 1;
+    const bool fold = !tuning(TUNE_MLP_NO_FORK) && ((l + 1 < L && layer_tc(l + 1)) || (l == L - 1 && pool));
+    if (fold) {
+      raw_prev = BnRaw{st_l, pivot_used, static_cast<double>(s.M), eps, momentum, train, y.save_mean, y.save_invstd,
+                       y.running_mean, y.running_var};
+    } else {
+      bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(st_l, pivot_used, y.cout, static_cast<double>(s.M), eps, momentum, train,
+                                                   y.save_mean, y.save_invstd, y.running_mean, y.running_var,
+                                                   next_piv ? layer_src(y, N) : ActSrc{}, next_piv ? layers[l + 1].weight : nullptr,
+                                                   next_piv ? layers[l + 1].bias : nullptr, next_piv ? layers[l + 1].cout : 0,
+                                                   piv_l + y.cout);
+      launches += 1;
+    }
     st_l += 2 * y.cout;
     piv_l += y.cout;
   }
@@ -1501,7 +1515,7 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
   if (pool) {
     const int64_t n = static_cast<int64_t>(B) * s.Clast;
     pool_finalize_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(w.keys, last.save_mean, last.save_invstd, last.gamma,
-                                                                            last.beta, last.relu, B, s.Clast, out, pool_arg);
+                                                                            last.beta, last.relu, B, s.Clast, out, pool_arg, raw_prev);
   } else {
     const dim3 grid((N + 31) / 32, (s.Clast + 31) / 32, B);
     dense_out_kernel<<<grid, dim3(32, 8), 0, st>>>(layer_src(last, N), B, out);

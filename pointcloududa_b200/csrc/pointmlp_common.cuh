@@ -19,6 +19,44 @@ struct ActSrc {
   int C;
 };
 
+// Finalise-on-read: the raw BatchNorm sums of the producing layer, handed to the kernel that consumes its
+// output (the operand packer of the next layer, the pooled-output kernel) so that no one-block
+// "finalise" launch sits between a GEMM and its consumer.  stats == nullptr: save_mean / save_invstd of the
+// ActSrc are already final.  Same arithmetic as bn_finalize_pivot_kernel.
+struct BnRaw {
+  const double* stats;       // [2C]: sum and sum of squares of (y - pivot)
+  const float* pivot;        // [C]
+  double count;
+  float eps, momentum;
+  int train;
+  float* save_mean;          // [C] written by the consumer's first CTA (the backward pass reads them)
+  float* save_invstd;
+  float* running_mean;       // [C] or nullptr (deferred / frozen): updated by the consumer's first CTA
+  float* running_var;
+};
+
+__device__ __forceinline__ void bn_raw_channel(const BnRaw& r, int c, int C, bool writer, float& mean_f, float& invstd_f) {
+  if (r.train) {
+    const double d = r.stats[c] / r.count;
+    const double mean = static_cast<double>(r.pivot[c]) + d;
+    double var = r.stats[C + c] / r.count - d * d;
+    var = var > 0.0 ? var : 0.0;
+    mean_f = static_cast<float>(mean);
+    invstd_f = static_cast<float>(1.0 / sqrt(var + static_cast<double>(r.eps)));
+    if (writer) {
+      if (r.running_mean) r.running_mean[c] = (1.0f - r.momentum) * r.running_mean[c] + r.momentum * static_cast<float>(mean);
+      if (r.running_var) {
+        const double unbiased = var * (r.count / (r.count - 1.0));
+        r.running_var[c] = (1.0f - r.momentum) * r.running_var[c] + r.momentum * static_cast<float>(unbiased);
+      }
+    }
+  } else {
+    mean_f = r.running_mean[c];
+    invstd_f = static_cast<float>(1.0 / sqrt(static_cast<double>(r.running_var[c]) + static_cast<double>(r.eps)));
+  }
+  if (writer) { r.save_mean[c] = mean_f; r.save_invstd[c] = invstd_f; }
+}
+
 __device__ __forceinline__ float bn_act(float y, float mean, float invstd, float gamma, float beta, int relu) {
   const float z = fmaf(y - mean, invstd * gamma, beta);
   return relu ? fmaxf(z, 0.0f) : z;

@@ -75,14 +75,17 @@ __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
 
 // a = relu?(y * p0 + p1)  (or the raw network input), p0 = invstd*gamma, p1 = beta - mean*p0
 // one thread = one 16-byte chunk (8 channels of one point)
-__global__ void __launch_bounds__(256) pack_act_kernel(ActSrc src, Tiling tl, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) pack_act_kernel(ActSrc src, Tiling tl, uint8_t* __restrict__ out, BnRaw raw) {
   __shared__ PackConsts pc;
   const int C = src.C;
   for (int k = threadIdx.x; k < C; k += blockDim.x) {
     if (src.y != nullptr) {
-      const float sc = src.invstd[k] * src.gamma[k];
+      float mean, invstd;
+      if (raw.stats != nullptr) bn_raw_channel(raw, k, C, blockIdx.x == 0, mean, invstd);   // finalise-on-read
+      else { mean = src.mean[k]; invstd = src.invstd[k]; }
+      const float sc = invstd * src.gamma[k];
       pc.p0[k] = sc;
-      pc.p1[k] = src.beta[k] - src.mean[k] * sc;
+      pc.p1[k] = src.beta[k] - mean * sc;
     } else { pc.p0[k] = 1.f; pc.p1[k] = 0.f; }
   }
   __syncthreads();
@@ -771,8 +774,8 @@ bool supports(int cin) { return cin >= 64 && cin <= kMaxK && (cin % 64) == 0; }
 size_t act_pack_bytes(const Tiling& tl, int C) { return static_cast<size_t>(tl.n_tiles) * (C / 64) * kSlabB; }
 size_t w_pack_bytes(int R, int K) { return static_cast<size_t>((R + 127) / 128) * K * 256; }
 
-int pack_act(const ActSrc& src, const Tiling& tl, uint8_t* out, cudaStream_t st) {
-  pack_act_kernel<<<pack_grid(static_cast<int64_t>(tl.n_tiles) * kNT * (src.C / 8)), 256, 0, st>>>(src, tl, out);
+int pack_act(const ActSrc& src, const Tiling& tl, uint8_t* out, cudaStream_t st, const BnRaw* raw) {
+  pack_act_kernel<<<pack_grid(static_cast<int64_t>(tl.n_tiles) * kNT * (src.C / 8)), 256, 0, st>>>(src, tl, out, raw ? *raw : BnRaw{});
   count_launch();
   return check_launch("tc::pack_act");
 }

@@ -22,7 +22,8 @@ bool pool_dgrad_fits(int K);
 // bf16 operand copies in the swizzled slab format (tc_common.cuh)
 size_t act_pack_bytes(const Tiling& tl, int C);          // [n_tiles][C/64] slabs of 256 rows
 size_t w_pack_bytes(int R, int K);                       // ceil(R/128) blocks of 128 rows x K
-int pack_act(const ActSrc& src, const Tiling& tl, uint8_t* out, cudaStream_t st);
+// raw != nullptr: the BatchNorm of src's layer is finalised here from its raw sums (see BnRaw)
+int pack_act(const ActSrc& src, const Tiling& tl, uint8_t* out, cudaStream_t st, const BnRaw* raw = nullptr);
 int pack_dy(const DySrc& dys, const Tiling& tl, uint8_t* out, cudaStream_t st);
 // transposed == false: A[r,k] = W[r*K + k];  true: A[r,k] = W[k*R + r]
 // sign_src (non-transposed only): rows with sign_src[r] < 0 are negated (pooled forward layer)
