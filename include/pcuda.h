@@ -175,6 +175,13 @@ int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, in
                        int L, const pcuda_mlp_layer_t* layers /*host*/, int pool, int train,
                        float eps, int precision, const float* out, const int32_t* pool_arg,
                        const float* grad_out, float* grad_x, void* ws, pcuda_stream_t stream);
+/* Same, with the workspace of the matching forward call still intact (fwd_ws, same B / N / layers / pool /
+ * precision): the bf16 operand slabs the forward packed are read in place instead of being packed again. */
+int pcuda_pointmlp_bwd_reuse(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N,
+                             int L, const pcuda_mlp_layer_t* layers /*host*/, int pool, int train,
+                             float eps, int precision, const float* out, const int32_t* pool_arg,
+                             const float* grad_out, float* grad_x, void* ws, const void* fwd_ws,
+                             pcuda_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * FC head: a stack of L layers on [B, C] features (the rows are the clouds of the batch)

@@ -1524,10 +1524,10 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
   return check_launch("pointmlp_fwd");
 }
 
-extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
-                                  const pcuda_mlp_layer_t* layers, int pool, int train, float eps,
-                                  int precision, const float* out, const int32_t* pool_arg,
-                                  const float* grad_out, float* grad_x, void* ws, pcuda_stream_t stream) {
+static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
+                             const pcuda_mlp_layer_t* layers, int pool, int train, float eps,
+                             int precision, const float* out, const int32_t* pool_arg,
+                             const float* grad_out, float* grad_x, void* ws, const void* fwd_ws, pcuda_stream_t stream) {
   (void)eps;
   if (int rc = validate("pointmlp_bwd", B, N, L, layers, pool)) return rc;
   PCUDA_REQUIRE(x && grad_out && ws, PCUDA_E_NULL, "pointmlp_bwd: NULL x/grad_out/ws");
@@ -1565,13 +1565,23 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
 
   // bf16 copies of the activations the tensor-core pieces stream: a_l for l = -1 (input) .. L-2
   const bool any_tc = precision == PCUDA_MLP_BF16 && !tuning(TUNE_MLP_FORCE_FP32) && (tuning(TUNE_MLP_TC_MASK) & 30) != 30;
+  // The forward call packed a_{j-1} for every layer j it ran on the tensor cores; with its workspace at hand
+  // (fwd_ws, contents intact) those slabs are read in place instead of being packed a second time.
   const uint8_t* apack[17] = {};
-  if (any_tc)
+  if (any_tc) {
+    const bool tcf = tc_on(precision, TC_FWD);
+    const FwdWs fw = fwd_ws != nullptr ? carve_fwd(s, layers, const_cast<void*>(fwd_ws)) : FwdWs{};
     for (int l = -1; l <= L - 2; ++l)
       if (w.apack[l + 1] != nullptr && (l >= 0 || layers[0].grad_weight != nullptr)) {
+        const int j = l + 1;     // a_l is the operand of layer j
+        if (fwd_ws != nullptr && tcf && fw.apack[j] != nullptr && tc::fwd_fits(layers[j].cout, layers[j].cin)) {
+          apack[l + 1] = fw.apack[j];
+          continue;
+        }
         if (int rc = tc::pack_act(src_of(l), tl, w.apack[l + 1], st)) return rc;
         apack[l + 1] = w.apack[l + 1];
       }
+  }
 
   // auxiliary stream of this call (see Aux above); tuning key 6 keeps everything on the caller's stream (A/B)
   Aux* ax = tuning(TUNE_MLP_NO_FORK) ? nullptr : aux_for(st);
@@ -1741,4 +1751,21 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
   }
   count_launch(launches);
   return check_launch("pointmlp_bwd");
+}
+
+extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
+                                  const pcuda_mlp_layer_t* layers, int pool, int train, float eps,
+                                  int precision, const float* out, const int32_t* pool_arg,
+                                  const float* grad_out, float* grad_x, void* ws, pcuda_stream_t stream) {
+  return pointmlp_bwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, eps, precision, out, pool_arg, grad_out, grad_x, ws,
+                           nullptr, stream);
+}
+
+extern "C" int pcuda_pointmlp_bwd_reuse(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
+                                        const pcuda_mlp_layer_t* layers, int pool, int train, float eps,
+                                        int precision, const float* out, const int32_t* pool_arg,
+                                        const float* grad_out, float* grad_x, void* ws, const void* fwd_ws,
+                                        pcuda_stream_t stream) {
+  return pointmlp_bwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, eps, precision, out, pool_arg, grad_out, grad_x, ws,
+                           fwd_ws, stream);
 }

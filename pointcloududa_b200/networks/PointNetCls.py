@@ -136,6 +136,7 @@ class _SharedMLP(torch.autograd.Function):
         ctx.save_for_backward(x)
         ctx.keep = keep
         ctx.saved = (ys, means, invstds, out if pool else None, arg)
+        ctx.fwd_ws = ws        # kept alive: the backward pass reads the packed bf16 operands in place
         ctx.param_shapes = [None if p is None else p.shape for p in params]
         return out
 
@@ -172,9 +173,10 @@ class _SharedMLP(torch.autograd.Function):
         Lb = _lib.lib()
         with torch.cuda.device(dev):
             ws = torch.empty(max(Lb.pcuda_pointmlp_ws_bytes(B, N, L, lay, int(pool), 1), 16), dtype=torch.uint8, device=dev)
-            check(Lb.pcuda_pointmlp_bwd(_ptr(x), x.stride(0), x.stride(1), x.stride(2), B, N, L, lay, int(pool),
-                                        int(train), float(eps), precision, _ptr(out), _ptr(arg), _ptr(go), _ptr(gx),
-                                        _ptr(ws), torch.cuda.current_stream().cuda_stream), "pcuda_pointmlp_bwd")
+            check(Lb.pcuda_pointmlp_bwd_reuse(_ptr(x), x.stride(0), x.stride(1), x.stride(2), B, N, L, lay, int(pool),
+                                              int(train), float(eps), precision, _ptr(out), _ptr(arg), _ptr(go), _ptr(gx),
+                                              _ptr(ws), _ptr(ctx.fwd_ws), torch.cuda.current_stream().cuda_stream),
+                  "pcuda_pointmlp_bwd")
         for i, need in enumerate(needs_p):
             if not need:
                 grads[i] = None
