@@ -182,24 +182,27 @@ mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
 // With a contraction of 3 the layer is a pure HBM stream (write y forward, read dy backward), so the
 // 64x64x16 tile kernels above waste a factor 5 in staging.  Here a thread owns 4 consecutive channels of
 // one point: x[m, 0..K) and its 4 x K weights sit in registers, y / dy move as coalesced float4.
-constexpr int kNarrowK = 8;
+constexpr int kNarrowK = 8;   // widest narrow layer; the kernels are instantiated for KN = 4 (cin <= 4: the 3 -> 64 / 3 -> 8
+                              // layers, i.e. all of them in the default network) and KN = 8
 constexpr int kNarrowThreads = 256;
 
 // all K <= 8 input channels of point m (one 64-bit division instead of one per channel)
-__device__ __forceinline__ void load_point(const ActSrc& s, int64_t m, float (&xv)[kNarrowK]) {
+template <int KN>
+__device__ __forceinline__ void load_point(const ActSrc& s, int64_t m, float (&xv)[KN]) {
   if (s.y != nullptr) {
 #pragma unroll
-    for (int k = 0; k < kNarrowK; ++k)
+    for (int k = 0; k < KN; ++k)
       xv[k] = k < s.C ? bn_act(s.y[m * s.C + k], s.mean[k], s.invstd[k], s.gamma[k], s.beta[k], s.relu) : 0.f;
   } else {
     const int64_t b = m / s.N, n = m - b * s.N;
     const float* px = s.x + b * s.sxb + n * s.sxn;
 #pragma unroll
-    for (int k = 0; k < kNarrowK; ++k) xv[k] = k < s.C ? __ldg(px + k * s.sxc) : 0.f;
+    for (int k = 0; k < KN; ++k) xv[k] = k < s.C ? __ldg(px + k * s.sxc) : 0.f;
   }
 }
 
 // forward: y = W a + b, centred BN statistics; CTA 0 also publishes the pivot (y of point 0)
+template <int KN>
 __global__ void __launch_bounds__(kNarrowThreads)
 mlp_fwd_narrow_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias, int Cout, int64_t M,
                       float* __restrict__ y_out, double* __restrict__ stats, float* __restrict__ pivot) {
@@ -210,21 +213,21 @@ mlp_fwd_narrow_kernel(ActSrc src, const float* __restrict__ W, const float* __re
   const int pslots = kNarrowThreads / tpp;             // points per CTA pass
   const int cg = threadIdx.x % tpp, ps = threadIdx.x / tpp;
   const int c0 = cg * 4;
-  float w[4][kNarrowK], bj[4], pv[4];
+  float w[4][KN], bj[4], pv[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     bj[j] = bias ? bias[c0 + j] : 0.f;
 #pragma unroll
-    for (int k = 0; k < kNarrowK; ++k) w[j][k] = k < K ? W[static_cast<int64_t>(c0 + j) * K + k] : 0.f;
+    for (int k = 0; k < KN; ++k) w[j][k] = k < K ? W[static_cast<int64_t>(c0 + j) * K + k] : 0.f;
   }
   {  // pivot = pre-BN output at global point 0 (same definition as bn_finalize_pivot_kernel)
-    float x0[kNarrowK];
-    load_point(src, 0, x0);
+    float x0[KN];
+    load_point<KN>(src, 0, x0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float d = 0.f;
 #pragma unroll
-      for (int k = 0; k < kNarrowK; ++k) d = fmaf(w[j][k], x0[k], d);
+      for (int k = 0; k < KN; ++k) d = fmaf(w[j][k], x0[k], d);
       pv[j] = d + bj[j];
     }
     if (blockIdx.x == 0 && ps == 0) {
@@ -235,14 +238,14 @@ mlp_fwd_narrow_kernel(ActSrc src, const float* __restrict__ W, const float* __re
   float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
   if (ps < pslots) {
     for (int64_t m = static_cast<int64_t>(blockIdx.x) * pslots + ps; m < M; m += static_cast<int64_t>(gridDim.x) * pslots) {
-      float xv[kNarrowK];
-      load_point(src, m, xv);
+      float xv[KN];
+      load_point<KN>(src, m, xv);
       float v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float d = 0.f;
 #pragma unroll
-        for (int k = 0; k < kNarrowK; ++k) d = fmaf(w[j][k], xv[k], d);
+        for (int k = 0; k < KN; ++k) d = fmaf(w[j][k], xv[k], d);
         v[j] = d + bj[j];
         const float vc = v[j] - pv[j];
         cs[j] += vc;
@@ -267,6 +270,7 @@ mlp_fwd_narrow_kernel(ActSrc src, const float* __restrict__ W, const float* __re
 }
 
 // weight gradient: partial[blockIdx.x][c][k] = sum over this CTA's points of dy[m,c] * a_prev[m,k]
+template <int KN>
 __global__ void __launch_bounds__(kNarrowThreads)
 wgrad_narrow_kernel(DySrc dys, ActSrc aprev, int64_t M, float* __restrict__ partial) {
   extern __shared__ float red_w[];     // [pslots][C][K]
@@ -274,19 +278,19 @@ wgrad_narrow_kernel(DySrc dys, ActSrc aprev, int64_t M, float* __restrict__ part
   const int tpp = C >> 2, pslots = kNarrowThreads / tpp;
   const int cg = threadIdx.x % tpp, ps = threadIdx.x / tpp;
   const int c0 = cg * 4;
-  float acc[4][kNarrowK];
+  float acc[4][KN];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int k = 0; k < kNarrowK; ++k) acc[j][k] = 0.f;
+    for (int k = 0; k < KN; ++k) acc[j][k] = 0.f;
   if (ps < pslots) {
     for (int64_t m = static_cast<int64_t>(blockIdx.x) * pslots + ps; m < M; m += static_cast<int64_t>(gridDim.x) * pslots) {
       const float4 d = load_dy4(dys, m, c0);
       const float dv[4] = {d.x, d.y, d.z, d.w};
-      float xv[kNarrowK];
-      load_point(aprev, m, xv);
+      float xv[KN];
+      load_point<KN>(aprev, m, xv);
 #pragma unroll
-      for (int k = 0; k < kNarrowK; ++k)
+      for (int k = 0; k < KN; ++k)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j][k] = fmaf(dv[j], xv[k], acc[j][k]);
     }
@@ -295,7 +299,7 @@ wgrad_narrow_kernel(DySrc dys, ActSrc aprev, int64_t M, float* __restrict__ part
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int k = 0; k < kNarrowK; ++k)
+      for (int k = 0; k < KN; ++k)
         if (k < K) red_w[(static_cast<int64_t>(ps) * C + c0 + j) * K + k] = acc[j][k];
   }
   __syncthreads();
@@ -309,17 +313,18 @@ wgrad_narrow_kernel(DySrc dys, ActSrc aprev, int64_t M, float* __restrict__ part
 
 // gradient w.r.t. the network input: grad_x[b, k, n] = sum_c dy[m, c] W[c, k]   (K <= 8, C <= 128: the
 // tpp = C/4 <= 32 threads of a point sit in one warp and combine with shuffles)
+template <int KN>
 __global__ void __launch_bounds__(kNarrowThreads)
 dgrad_input_narrow_kernel(DySrc dys, const float* __restrict__ W, int K, int N, int64_t M, float* __restrict__ grad_x) {
   const int C = dys.C;
   const int tpp = C >> 2, pslots = kNarrowThreads / tpp;
   const int cg = threadIdx.x % tpp, ps = threadIdx.x / tpp;
   const int c0 = cg * 4;
-  float w[4][kNarrowK];
+  float w[4][KN];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int k = 0; k < kNarrowK; ++k) w[j][k] = k < K ? W[static_cast<int64_t>(c0 + j) * K + k] : 0.f;
+    for (int k = 0; k < KN; ++k) w[j][k] = k < K ? W[static_cast<int64_t>(c0 + j) * K + k] : 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * pslots;
   const int64_t iters = (M + stride - 1) / stride;       // uniform trip count: the shuffles below need full warps
   for (int64_t it = 0; it < iters; ++it) {
@@ -327,17 +332,17 @@ dgrad_input_narrow_kernel(DySrc dys, const float* __restrict__ W, int K, int N, 
     const bool ok = m < M && ps < pslots;
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ok) d = load_dy4(dys, m, c0);
-    float g[kNarrowK];
+    float g[KN];
 #pragma unroll
-    for (int k = 0; k < kNarrowK; ++k) g[k] = d.x * w[0][k] + d.y * w[1][k] + d.z * w[2][k] + d.w * w[3][k];
+    for (int k = 0; k < KN; ++k) g[k] = d.x * w[0][k] + d.y * w[1][k] + d.z * w[2][k] + d.w * w[3][k];
     for (int o = tpp >> 1; o > 0; o >>= 1) {
 #pragma unroll
-      for (int k = 0; k < kNarrowK; ++k) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
+      for (int k = 0; k < KN; ++k) g[k] += __shfl_xor_sync(0xffffffffu, g[k], o);
     }
     if (ok && cg == 0) {
       const int64_t b = m / N, n = m - b * N;
 #pragma unroll
-      for (int k = 0; k < kNarrowK; ++k)
+      for (int k = 0; k < KN; ++k)
         if (k < K) grad_x[(b * K + k) * N + n] = g[k];
     }
   }
@@ -1481,7 +1486,8 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
       if (int rc = tc::fwd_layer(tl, w.apack[l], w.wpack[l], y, is_pool, st_l, w.keys, st)) return rc;
       pivot_used = y.bias ? y.bias : w.zeros;
     } else if (layer_narrow(l)) {
-      mlp_fwd_narrow_kernel<<<narrow_grid(s.M, y.cout), kNarrowThreads, 0, st>>>(src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
+      if (y.cin <= 4) mlp_fwd_narrow_kernel<4><<<narrow_grid(s.M, y.cout), kNarrowThreads, 0, st>>>(src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
+      else mlp_fwd_narrow_kernel<8><<<narrow_grid(s.M, y.cout), kNarrowThreads, 0, st>>>(src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
       launches += 1;
     } else {
       const dim3 grid(B * tps, (y.cout + TN - 1) / TN);
@@ -1718,7 +1724,8 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       } else if (narrow_ok(Kp, C)) {
         Sw = std::min(narrow_grid(s.M, C), s.S);
         const size_t smem = sizeof(float) * 1024 * static_cast<size_t>(Kp);   // [pslots][C][Kp], pslots * C = 1024
-        wgrad_narrow_kernel<<<Sw, kNarrowThreads, smem, sw>>>(dys, src_of(l - 1), s.M, partial);
+        if (Kp <= 4) wgrad_narrow_kernel<4><<<Sw, kNarrowThreads, smem, sw>>>(dys, src_of(l - 1), s.M, partial);
+        else wgrad_narrow_kernel<8><<<Sw, kNarrowThreads, smem, sw>>>(dys, src_of(l - 1), s.M, partial);
         launches += 1;
       } else {
         point_contract_kernel<0><<<dim3(S32, (C + TM - 1) / TM, (Kp + TN - 1) / TN), kThreads, 0, sw>>>(dys, ActSrc{}, src_of(l - 1), s.M, chunk32, C, Kp, partial);
@@ -1736,7 +1743,8 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
         const uint8_t* side = dgrad_side ? apack[l] : nullptr;
         if (int rc = tc::dgrad_layer(tl, w.dypack, C, w.wtpack, side, o, st)) return rc;
       } else if (o.grad_x != nullptr && narrow_ok(Kp, C) && C <= 128) {
-        dgrad_input_narrow_kernel<<<narrow_grid(s.M, C), kNarrowThreads, 0, st>>>(dys, y.weight, Kp, N, s.M, o.grad_x);
+        if (Kp <= 4) dgrad_input_narrow_kernel<4><<<narrow_grid(s.M, C), kNarrowThreads, 0, st>>>(dys, y.weight, Kp, N, s.M, o.grad_x);
+        else dgrad_input_narrow_kernel<8><<<narrow_grid(s.M, C), kNarrowThreads, 0, st>>>(dys, y.weight, Kp, N, s.M, o.grad_x);
         launches += 1;
       } else {
         dense_dgrad_kernel<<<dim3(B * tps, (Kp + TN - 1) / TN), kThreads, 0, st>>>(dys, y.weight, N, tps, o);
