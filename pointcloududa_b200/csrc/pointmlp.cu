@@ -284,8 +284,9 @@ wgrad_narrow_kernel(DySrc dys, ActSrc aprev, int64_t M, float* __restrict__ part
 #pragma unroll
     for (int k = 0; k < KN; ++k) acc[j][k] = 0.f;
   if (ps < pslots) {
+    const DyConst4 dk = dy_const4(dys, c0);
     for (int64_t m = static_cast<int64_t>(blockIdx.x) * pslots + ps; m < M; m += static_cast<int64_t>(gridDim.x) * pslots) {
-      const float4 d = load_dy4(dys, m, c0);
+      const float4 d = load_dy4c(dys, dk, m, c0);
       const float dv[4] = {d.x, d.y, d.z, d.w};
       float xv[KN];
       load_point<KN>(aprev, m, xv);
@@ -327,11 +328,12 @@ dgrad_input_narrow_kernel(DySrc dys, const float* __restrict__ W, int K, int N, 
     for (int k = 0; k < KN; ++k) w[j][k] = k < K ? W[static_cast<int64_t>(c0 + j) * K + k] : 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * pslots;
   const int64_t iters = (M + stride - 1) / stride;       // uniform trip count: the shuffles below need full warps
+  const DyConst4 dk = dy_const4(dys, c0);
   for (int64_t it = 0; it < iters; ++it) {
     const int64_t m = it * stride + static_cast<int64_t>(blockIdx.x) * pslots + ps;
     const bool ok = m < M && ps < pslots;
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok) d = load_dy4(dys, m, c0);
+    if (ok) d = load_dy4c(dys, dk, m, c0);
     float g[KN];
 #pragma unroll
     for (int k = 0; k < KN; ++k) g[k] = d.x * w[0][k] + d.y * w[1][k] + d.z * w[2][k] + d.w * w[3][k];

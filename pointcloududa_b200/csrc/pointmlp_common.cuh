@@ -125,6 +125,31 @@ __device__ __forceinline__ float4 load_dy4(const DySrc& s, int64_t m, int c) {
   return v;
 }
 
+// The same for a thread that keeps its 4 channels over many points (narrow-layer kernels): the per-channel
+// constants live in registers, dz and y move as 128-bit loads.  dy = dz*p0 + (y*p1 + p2), p0 = gamma*invstd,
+// p1 = -kappa, p2 = kappa*mean - alpha (the form pack_dy_kernel uses).  Needs C % 4 == 0 and c0 % 4 == 0.
+struct DyConst4 {
+  float p0[4], p1[4], p2[4];
+};
+__device__ __forceinline__ DyConst4 dy_const4(const DySrc& s, int c0) {
+  DyConst4 k;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cc = c0 + i;
+    const bool ok = cc < s.C;
+    k.p0[i] = ok ? s.gamma[cc] * s.invstd[cc] : 0.f;
+    k.p1[i] = ok ? -s.kappa[cc] : 0.f;
+    k.p2[i] = ok ? s.kappa[cc] * s.mean[cc] - s.alpha[cc] : 0.f;
+  }
+  return k;
+}
+__device__ __forceinline__ float4 load_dy4c(const DySrc& s, const DyConst4& k, int64_t m, int c0) {
+  const float4 dz = *reinterpret_cast<const float4*>(s.dz + m * s.C + c0);
+  const float4 y = *reinterpret_cast<const float4*>(s.y + m * s.C + c0);
+  return make_float4(fmaf(dz.x, k.p0[0], fmaf(y.x, k.p1[0], k.p2[0])), fmaf(dz.y, k.p0[1], fmaf(y.y, k.p1[1], k.p2[1])),
+                     fmaf(dz.z, k.p0[2], fmaf(y.z, k.p1[2], k.p2[2])), fmaf(dz.w, k.p0[3], fmaf(y.w, k.p1[3], k.p2[3])));
+}
+
 
 // Target of a dgrad epilogue: val -> (ReLU mask of the producing layer) -> store
 // dz_prev + accumulate that layer's dbeta / dgamma sums; or, for the network input, store grad_x.
