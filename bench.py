@@ -210,7 +210,9 @@ KERNEL_WORK = {
     "fc_fwd_kernel": ("hbm", lambda w: 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) / 3 + 4.0 * w["B"] * (1024 + 512)),   # mean layer of a head
     "fc_bwd_kernel": ("hbm", lambda w: 2 * 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) / 3 + 4.0 * w["B"] * (1024 + 512)),
     "fc_pull_kernel": ("hbm", lambda w: 4.0 * 512 * 1024 + 4.0 * w["B"] * (1024 + 512)),
-    "sgd": ("hbm", lambda w: 1.6e6 * 16.0),
+    "sgd": ("hbm", lambda w: 1.6e6 * 16.0),                                      # grad, momentum in / momentum, param in+out
+    "grad_sum_pack_kernel": ("hbm", lambda w: 1.6e6 * 12.0),                    # two gradient lists in, the bucket out
+    "bce_logits_kernel": ("hbm", lambda w: w["B"] * 8.0 + 8.0),
 }
 
 

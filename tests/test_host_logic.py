@@ -1,0 +1,56 @@
+"""CPU checks of the host-side logic around the C-ABI: no silent CPU fallback in the new entry points, the
+roofline bookkeeping of bench.py (every libpcuda kernel of the profiled step has an algorithmic-work model and a
+committed DRAM-traffic figure)."""
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from pointcloududa_b200 import ops  # noqa: E402
+from pointcloududa_b200._lib import PcudaError  # noqa: E402
+
+
+def test_fused_sgd_and_bce_refuse_cpu_tensors():
+    from pointcloududa_b200.optim import FusedSGD
+    p = torch.nn.Parameter(torch.zeros(4, 3))
+    with pytest.raises(PcudaError):
+        FusedSGD([p], lr=0.1, momentum=0.9)
+    with pytest.raises(PcudaError):
+        ops.bce_with_logits(torch.zeros(4, 1), 1.0)
+
+
+def test_kernel_work_table_covers_the_profiled_step():
+    import bench
+    path = os.path.join(ROOT, "profiles", "traffic_cfg2.json")
+    assert os.path.exists(path), "profiles/traffic_cfg2.json is committed evidence (tools/ncu_traffic.py)"
+    d = json.load(open(path))
+    framework = ("at::", "cutlass", "Memset", "Memcpy", "memset", "memcpy", "nccl")
+    ours = [k for k in d["kernels"] if not any(f in k for f in framework)]
+    assert len(ours) >= 30
+    w = dict(bench.WORKLOADS["cfg2"])
+    for k in ours:
+        hits = [frag for frag in bench.KERNEL_WORK if frag in k]
+        assert hits, f"no algorithmic-work model for kernel {k}"
+        bound, work = bench.KERNEL_WORK[hits[0]]
+        assert bound in ("hbm", "tensor") and work(w) > 0
+        traffic, src = bench.ncu_traffic("cfg2", "pcuda::" + k)
+        assert traffic is not None and traffic >= 0 and "traffic_cfg2.json" in src
+
+
+def test_step_input_layout_offsets_are_aligned():
+    # the flat layout arithmetic of AdversarialStep (no device needed for the offsets)
+    from pointcloududa_b200.step import AdversarialStep
+    obj = AdversarialStep.__new__(AdversarialStep)
+    obj._input_shapes = {"oS": (8, 4, 224, 224), "vertS": (8, 300, 3), "vertT": (8, 300, 3)}
+    offs, total = obj._input_offsets()
+    assert all(o % 64 == 0 for o, _, _ in offs.values()) and total % 64 == 0
+    flat = torch.zeros(total)
+    views = obj.input_layout(flat)
+    assert views["vertS"].shape == (8, 300, 3) and views["vertT"].data_ptr() - views["vertS"].data_ptr() == 7232 * 4
+    with pytest.raises(ValueError):
+        obj.input_layout(torch.zeros(total + 1))
