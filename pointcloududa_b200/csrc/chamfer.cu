@@ -36,6 +36,45 @@ __device__ __forceinline__ float norm3(float a0, float a1, float a2) {
   return __fmaf_rn(a2, a2, __fmaf_rn(a1, a1, __fmul_rn(a0, a0)));
 }
 
+// Deterministic loss reduction shared by the three forward kernels: every CTA (active or not) leaves the fp64 sum
+// of its rows' distances in ws->partial; the CTA that takes the last ticket adds all partials in a fixed order
+//     loss = sum_b (sum_i d1)/N /B + sum_b (sum_j d2)/N /B      (loss.py:73-75)
+// and re-arms the ticket, so the workspace is reusable without a host-side reset.
+template <int THREADS>
+__device__ __forceinline__ void finish_loss(double my_sum, FwdWs* __restrict__ ws, float* __restrict__ loss, int dir,
+                                            int b, int B, int N) {
+  __shared__ double warp_part[THREADS / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const double w = warp_sum(my_sum);
+  if (lane == 0) warp_part[wid] = w;
+  __syncthreads();
+  const int tiles_max = gridDim.x;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) s += warp_part[i];
+    ws->partial[(static_cast<int64_t>(dir) * B + b) * tiles_max + blockIdx.x] = s;
+    __threadfence();
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    is_last = atomicAdd(&ws->ticket, 1u) == total - 1;
+  }
+  __syncthreads();
+  if (is_last && wid == 0) {
+    __threadfence();
+    double acc = 0.0;
+    const int64_t n_part = static_cast<int64_t>(2) * B * tiles_max;
+    const volatile double* part = ws->partial;
+    for (int64_t k = lane; k < n_part; k += 32) acc += part[k];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      *loss = static_cast<float>(acc / (static_cast<double>(N) * static_cast<double>(B)));
+      ws->ticket = 0u;
+      __threadfence();
+    }
+  }
+}
+
 // One launch covers both directions: blockIdx.z == 0 searches y for every x_i (d1,i1),
 // blockIdx.z == 1 searches x for every y_j (d2,i2).
 template <int R, int THREADS>
@@ -45,8 +84,6 @@ chamfer_nn_kernel(const float* __restrict__ x, const float* __restrict__ y, int 
                   int64_t* __restrict__ i2, FwdWs* __restrict__ ws, float* __restrict__ loss,
                   int tiles_x, int tiles_y, int B) {
   __shared__ float4 tile[kTileJ];
-  __shared__ double warp_part[THREADS / 32];
-
   const int dir = blockIdx.z;
   const int b = blockIdx.y;
   const int nq = dir == 0 ? N : M;  // queries (rows)
@@ -117,38 +154,7 @@ chamfer_nn_kernel(const float* __restrict__ x, const float* __restrict__ y, int 
     }
   }
 
-  if (loss == nullptr) return;
-  // ---- deterministic loss reduction: per-block partial -> fixed-order final sum by last block
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double w = warp_sum(my_sum);
-  if (lane == 0) warp_part[wid] = w;
-  __syncthreads();
-  __shared__ bool is_last;
-  const int tiles_max = gridDim.x;
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-#pragma unroll
-    for (int i = 0; i < THREADS / 32; ++i) s += warp_part[i];
-    ws->partial[(static_cast<int64_t>(dir) * B + b) * tiles_max + blockIdx.x] = s;
-    __threadfence();
-    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-    is_last = atomicAdd(&ws->ticket, 1u) == total - 1;
-  }
-  __syncthreads();
-  if (is_last && wid == 0) {
-    __threadfence();
-    // loss = sum_b (sum_i d1)/N /B + sum_b (sum_j d2)/N /B      (loss.py:73-75)
-    double acc = 0.0;
-    const int64_t n_part = static_cast<int64_t>(2) * B * tiles_max;
-    const volatile double* part = ws->partial;
-    for (int64_t k = lane; k < n_part; k += 32) acc += part[k];
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      *loss = static_cast<float>(acc / (static_cast<double>(N) * static_cast<double>(B)));
-      ws->ticket = 0u;
-      __threadfence();
-    }
-  }
+  if (loss != nullptr) finish_loss<THREADS>(my_sum, ws, loss, dir, b, B, N);
 }
 
 
@@ -177,8 +183,6 @@ chamfer_nn2_kernel(const float* __restrict__ x, const float* __restrict__ y, int
                    int tiles_x, int tiles_y, int B) {
   __shared__ float4 tileA[kTileJ / 2];
   __shared__ float4 tileB[kTileJ / 2];
-  __shared__ double warp_part[THREADS / 32];
-
   const int dir = blockIdx.z;
   const int b = blockIdx.y;
   const int nq = dir == 0 ? N : M;
@@ -268,36 +272,7 @@ chamfer_nn2_kernel(const float* __restrict__ x, const float* __restrict__ y, int
     }
   }
 
-  if (loss == nullptr) return;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double w = warp_sum(my_sum);
-  if (lane == 0) warp_part[wid] = w;
-  __syncthreads();
-  __shared__ bool is_last;
-  const int tiles_max = gridDim.x;
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-#pragma unroll
-    for (int i = 0; i < THREADS / 32; ++i) s += warp_part[i];
-    ws->partial[(static_cast<int64_t>(dir) * B + b) * tiles_max + blockIdx.x] = s;
-    __threadfence();
-    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-    is_last = atomicAdd(&ws->ticket, 1u) == total - 1;
-  }
-  __syncthreads();
-  if (is_last && wid == 0) {
-    __threadfence();
-    double acc = 0.0;
-    const int64_t n_part = static_cast<int64_t>(2) * B * tiles_max;
-    const volatile double* part = ws->partial;
-    for (int64_t k = lane; k < n_part; k += 32) acc += part[k];
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      *loss = static_cast<float>(acc / (static_cast<double>(N) * static_cast<double>(B)));
-      ws->ticket = 0u;
-      __threadfence();
-    }
-  }
+  if (loss != nullptr) finish_loss<THREADS>(my_sum, ws, loss, dir, b, B, N);
 }
 
 // ---- v3: conservative 3-FMA prefilter in front of the exact evaluation ------------------------------
@@ -353,8 +328,6 @@ chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int
   __shared__ float4 tileA[kTileJ / 2 + 1];   // + 1: the scan prefetches one entry ahead
   __shared__ float4 tileB[kTileJ / 2 + 1];
   __shared__ float warp_rmax[THREADS / 32];
-  __shared__ double warp_part[THREADS / 32];
-
   const int dir = blockIdx.z;
   const int b = blockIdx.y;
   const int nq = dir == 0 ? N : M;
@@ -537,35 +510,7 @@ chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int
     }
   }
 
-  if (loss == nullptr) return;
-  double w = warp_sum(my_sum);
-  if (lane == 0) warp_part[wid] = w;
-  __syncthreads();
-  __shared__ bool is_last;
-  const int tiles_max = gridDim.x;
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-#pragma unroll
-    for (int i = 0; i < THREADS / 32; ++i) s += warp_part[i];
-    ws->partial[(static_cast<int64_t>(dir) * B + b) * tiles_max + blockIdx.x] = s;
-    __threadfence();
-    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-    is_last = atomicAdd(&ws->ticket, 1u) == total - 1;
-  }
-  __syncthreads();
-  if (is_last && wid == 0) {
-    __threadfence();
-    double acc = 0.0;
-    const int64_t n_part = static_cast<int64_t>(2) * B * tiles_max;
-    const volatile double* part = ws->partial;
-    for (int64_t k = lane; k < n_part; k += 32) acc += part[k];
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      *loss = static_cast<float>(acc / (static_cast<double>(N) * static_cast<double>(B)));
-      ws->ticket = 0u;
-      __threadfence();
-    }
-  }
+  if (loss != nullptr) finish_loss<THREADS>(my_sum, ws, loss, dir, b, B, N);
 }
 
 // ---- backward ---------------------------------------------------------------------------------
