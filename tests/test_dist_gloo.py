@@ -75,6 +75,12 @@ def _worker(rank: int, world: int, port: int, q):
         ref = torch.autograd.grad(net(xb).pow(2).mean(), list(net.parameters()))
         ref_flat = torch.cat([t.reshape(-1) for t in ref])
         err = float((bucket.flat - ref_flat).abs().max())
+        # the step's variant: the bucket is filled pre-divided by the world size, the collective is a plain sum
+        bucket.zero()
+        bucket.accumulate(torch.autograd.grad(net(xs).pow(2).mean(), bucket.params))
+        bucket.flat.div_(world)
+        bucket.allreduce_sum()
+        err = max(err, float((bucket.flat - ref_flat).abs().max()))
         sc = pdist.allreduce_scalars([torch.tensor(float(rank)), torch.tensor(2.0)])
         q.put((rank, err, sc.tolist()))
         dist.barrier()
