@@ -13,13 +13,19 @@
  *                                 trunk), :143-163 (PointNetfeat trunk + global max-pool)
  *   pcuda_fcstack_fwd / _bwd      networks/PointNetCls.py:46-62 (STN3d head), :89-101 (STNkd head),
  *                                 :208-213 (classifier head): Linear [+Dropout] [+BatchNorm1d] [+ReLU]
+ *   pcuda_bn_running_update       BatchNorm1d running statistics of several forward passes, in pass order
+ *   pcuda_bce_logits              F.binary_cross_entropy_with_logits + accuracy, train_mscmrseg.py:233,286-296,316-322
+ *   pcuda_grad_sum_pack /         .grad accumulation of the two D4 backward passes (train_mscmrseg.py:288,319) and
+ *   pcuda_sgd_momentum_step       optim_dis4.step() = torch.optim.SGD(momentum, weight_decay) (:329-330,:450-455)
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless the parameter is documented "host";
  *   - the caller allocates inputs, outputs and workspaces and keeps them alive until the
  *     stream has passed the launch; the library owns no device memory;
  *   - launches are asynchronous on `stream`; no entry point synchronises, allocates or frees,
- *     so all of them are legal under CUDA-graph stream capture;
+ *     so all of them are legal under CUDA-graph stream capture (pcuda_pointmlp_fwd / _bwd
+ *     fork onto an internal auxiliary stream and join back before returning; under capture the
+ *     fork / join events become graph dependencies);
  *   - return value: 0 on success; a negative PCUDA_E* code for a rejected argument;
  *     a positive value is a cudaError_t from the launch.  Nothing throws or exits.
  *     pcuda_last_error_string() gives a thread-local description of the last failure.
@@ -56,9 +62,11 @@ const char* pcuda_error_name(int code);
 int pcuda_sm_count(void);
 /* Benchmark / fault-isolation knob for A/B-ing kernel variants (key, value); not part of the
  * reference-facing contract.  Keys: 0 = entropy arithmetic (0 MUFU fast path, 1 libdevice precise),
- * 1 = chamfer rows*1000+threads (+100000: scalar variant), 2 = force the FP32 MLP kernels,
+ * 1 = chamfer rows*1000+threads (default: prefiltered packed kernel; +100000: scalar, +200000: exact packed,
+ * +300000: prefiltered at 72 registers), 2 = force the FP32 MLP kernels,
  * 3 = bit mask of MLP pieces switched from tcgen05 back to FP32 (1 forward, 2 pooled dgrad,
- * 4 dense dgrad, 8 wgrad, 16 Gram). */
+ * 4 dense dgrad, 8 wgrad, 16 Gram), 4 = timing experiments of the pooled tensor-core layer (results invalid),
+ * 5 = chamfer seed-pass stride (0 default, < 0 off), 6 = no auxiliary-stream fork / finalise-on-read in the MLP. */
 int pcuda_tune(int key, int value);
 /* Number of kernels this library has launched in this process (monotone; for bench accounting). */
 uint64_t pcuda_launch_count(void);
