@@ -1607,6 +1607,7 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
     float* ka = kappa + off[L - 1];
     const int64_t bc = static_cast<int64_t>(B) * C;
     const int64_t kk = static_cast<int64_t>(K) * K;
+    bool q_packed = false;   // Q already sits in w.qpack (tc::q_finish)
     // selection side on the caller's stream, Gram side on the auxiliary stream
     if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sa, ax->fork, 0); aux_used = true; }
     // -- Gram side: centred Gram matrix of the pooled layer's input (train-mode BN correction terms only)
@@ -1633,11 +1634,23 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
                                                       want_last ? last.grad_gamma : nullptr, want_last ? last.grad_beta : nullptr,
                                                       want_last ? last.grad_bias : nullptr);
     pool_q_kernel<<<dim3((K + 31) / 32, (K + 31) / 32, kPoolQSplits), 256, 0, st>>>(last.weight, ka, C, K, w.qpartial);
-    reduce_partials_kernel<float><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(w.qpartial, kk, kPoolQSplits, w.Q);
-    // -- join: u needs Q (this stream) and abar (Gram side)
-    if (ax) cudaStreamWaitEvent(st, ax->side, 0);
-    pool_u_kernel<<<(K + 31) / 32, 1024, 0, st>>>(last.weight, al, w.Q, w.abar, C, K, w.u);
-    launches += 9;
+    // the low-rank dgrad runs on the tensor cores (decided here: it changes how Q is finished)
+    const bool tc_pool = (L >= 2 || grad_x) && tc_on(precision, TC_POOL_DGRAD) && a_in && w.qpack && tc::pool_dgrad_fits(K) &&
+                         pool_sparse_smem(C, N, K) <= 200 * 1024 && K <= 512 && C <= 65535;
+    if (tc_pool && !tuning(TUNE_MLP_NO_FORK)) {
+      // -- join: u needs Q (this stream) and abar (Gram side); one launch sums the partials of Q, packs Q as the
+      // stationary bf16 operand of the dgrad GEMM and forms u
+      if (ax) cudaStreamWaitEvent(st, ax->side, 0);
+      if (int rc = tc::q_finish(w.qpartial, kPoolQSplits, last.weight, al, w.abar, C, K, w.Q, w.qpack, w.u, st)) return rc;
+      q_packed = true;
+      launches += 6;     // reduce<double>, abar, gram_center, pool_sel, pool_coef, pool_q (tc:: calls count themselves)
+    } else {
+      reduce_partials_kernel<float><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(w.qpartial, kk, kPoolQSplits, w.Q);
+      // -- join: u needs Q (this stream) and abar (Gram side)
+      if (ax) cudaStreamWaitEvent(st, ax->side, 0);
+      pool_u_kernel<<<(K + 31) / 32, 1024, 0, st>>>(last.weight, al, w.Q, w.abar, C, K, w.u);
+      launches += 8;
+    }
     if (last.grad_weight) {
       const size_t dw_smem = sizeof(float) * ((kDwCh * (K + 2 * static_cast<size_t>(B)) + 3) & ~static_cast<size_t>(3)) +
                              sizeof(double) * kDwParts * 128 * kDwCh;
@@ -1665,7 +1678,8 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
           attr_done = true;
         }
         // dense part on the tensor cores: dz_prev = mask * (-u - a Q) (+ its column sums) ...
-        if (int rc = tc::pack_w(w.Q, K, K, false, w.qpack, st)) return rc;
+        if (!q_packed)
+          if (int rc = tc::pack_w(w.Q, K, K, false, w.qpack, st)) return rc;
         if (int rc = tc::pool_dgrad(tl, a_in, K, w.qpack, w.u, o, st)) return rc;
         // ... then the <= min(C, N) selected points per cloud get their sparse rows added (one warp per point).
         // Every CTA repeats the O(C + N) prologue and ends with 2K fp64 atomics on the same 2K addresses
