@@ -195,6 +195,7 @@ KERNEL_WORK = {
     "pool_sel_kernel": ("hbm", lambda w: w["B"] * 1024 * (4.0 * 128 + 24.0) + 1024 * 128 * 4.0),   # selected rows + W + out/arg/grad/coef
     "pool_coef_kernel": ("hbm", lambda w: w["B"] * 1024 * 8.0 + 1024 * 28.0),
     "pool_q_kernel": ("hbm", lambda w: 1024 * 128 * 4.0 + 1024 * 4.0 + 8 * 128 * 128 * 4.0),       # W, kappa in, split partials out
+    "q_finish_kernel": ("hbm", lambda w: 8 * 128 * 128 * 4.0 + 1024 * 128 * 4.0 + 128 * 128 * 6.0),       # partials + W in, Q fp32 + bf16 out
     "pool_u_kernel": ("hbm", lambda w: 1024 * 128 * 4.0 + 128 * 128 * 4.0 + 1024 * 4.0 + 1024.0),
     "pool_finalize_kernel": ("hbm", lambda w: w["B"] * 1024 * 16.0),
     "act_colsum_kernel": ("hbm", lambda w: 4.0 * w["B"] * w["N"] * 128),
