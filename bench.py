@@ -143,26 +143,97 @@ def cpu_step(w: dict, host_np: dict, params, spec):
     return losses
 
 
-def run_cpu_baseline(w: dict, budget_s: float, min_steps: int = 2, max_steps: int = 50):
-    import numpy as np
-    import oracle
-    host = make_host_inputs(w, 0, pinned=False)
-    host_np = {k: v.numpy() for k, v in host.items()}
-    spec = oracle.PointNetSpec()
-    params = oracle.make_params(spec, 0)
+def workload_label(name: str, w: dict) -> str:
+    kind = {"cfg2": "MS-CMRSeg", "cfg3": "MM-WHS", "cfg3_rank": "MM-WHS (cfg-3 per-rank shard)",
+            "cfg5_rank": "large-batch (cfg-5 per-rank shard)"}.get(name, name)
+    return (f"{name}: {kind} adversarial step, per-rank batch {w['B']}, {w['C']}x{w['H']}x{w['W']} logits, "
+            f"{w['N']}-pt clouds")
+
+
+def bench_config(name: str, w: dict, world: int, precision: str = "bf16", use_graph: bool = True) -> dict:
+    """`config` of the JSON line — the SAME dict for the GPU arm and for `--impl reference` (the driver compares
+    them), so the statements about L2 / graphs name the arm they apply to."""
+    return {"workload": workload_label(name, w), "per_rank": w, "global_batch": w["B"] * world,
+            "parallelism": f"dp{world} (batch-sharded, D4 grad all-reduce)",
+            "l2": f"GPU arm: flushed before every step ({FLUSH_BYTES >> 20} MiB write, L2 = 126 MB): outside the per-step "
+                  "CUDA-event intervals of `value`, inside the single interval of `e2e`; reference arm: host cores, "
+                  "working set larger than the last-level cache slice of a core",
+            "e2e_pipeline": "GPU arm: copy stream uploads step i+1 (one flat pinned buffer) into a staging set while step i "
+                            "runs; one device-to-device move into the step's static inputs",
+            "cuda_graph": f"GPU arm: {bool(use_graph)}", "mlp_precision": f"GPU arm: {precision}; reference arm: fp32"}
+
+
+def reference_available() -> bool:
+    try:
+        from baseline import ref_step
+        return ref_step.available()
+    except Exception:
+        return False
+
+
+def run_cpu_baseline(w: dict, budget_s: float, min_steps: int = 2, max_steps: int = 50, warmup: int = 1):
+    """The reference path on the host cores.  kind="reference": the reference's own PyTorch code (baseline/_ref,
+    torch eager, every host core); kind="port" (only when baseline/_ref is not installed): the oracle port."""
     cores = os.cpu_count() or 1
-    oracle.set_num_threads(cores)
-    cpu_step(w, host_np, params, spec)  # warm-up
+    if reference_available():
+        import torch
+        from baseline import ref_step
+        torch.set_num_threads(cores)
+        host = make_host_inputs(w, 0, pinned=False)
+        ref = ref_step.ReferenceStep(w, "cpu", seed=0)
+        step_fn = lambda: ref.run(host)
+        kind = "reference"
+        what = ("the reference's own code (utils/loss.py batch_NN_loss with the one-token in-memory device patch, "
+                "networks/PointNetCls.py, inline entropy expressions) under torch eager")
+    else:
+        import oracle
+        host = make_host_inputs(w, 0, pinned=False)
+        host_np = {k: v.numpy() for k, v in host.items()}
+        spec = oracle.PointNetSpec()
+        params = oracle.make_params(spec, 0)
+        oracle.set_num_threads(cores)
+        step_fn = lambda: cpu_step(w, host_np, params, spec)
+        kind = "port"
+        what = "oracle port: C+OpenMP entropy/Chamfer, numpy/BLAS PointNet (baseline/_ref not installed)"
+    for _ in range(max(1, warmup)):
+        step_fn()
     ts = []
     t_start = time.perf_counter()
     while len(ts) < max_steps and (len(ts) < min_steps or time.perf_counter() - t_start < budget_s):
         t0 = time.perf_counter()
-        cpu_step(w, host_np, params, spec)
+        step_fn()
         ts.append(time.perf_counter() - t0)
     med = statistics.median(ts)
-    return {"value": 1.0 / med, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(ts)} full steps of the same workload (oracle port: C+OpenMP entropy/Chamfer, numpy/BLAS PointNet), median",
-            "ms_per_step": med * 1e3}
+    return {"value": 1.0 / med, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{len(ts)} full steps of the same workload ({what}), median",
+            "ms_per_step": med * 1e3, "ms_per_step_mean": statistics.mean(ts) * 1e3}
+
+
+def run_gpu_eager_baseline(w: dict, dev, host: dict, flush, steps: int = 20, warmup: int = 3):
+    """The UNPATCHED reference (baseline/_ref) executed under torch eager on this same B200 with its stock
+    cuBLAS / cuDNN / ATen kernels: the bar the sm_100a kernels have to beat.  Inputs resident,
+    L2 flushed between steps, per-step CUDA events like `value`."""
+    import torch
+    if not reference_available():
+        return {"unavailable": "baseline/_ref not installed (python baseline/make_ref.py needs /root/reference)"}
+    from baseline import ref_step
+    ref = ref_step.ReferenceStep(w, dev, seed=0)
+    I = {k: v.to(dev) for k, v in host.items()}
+    for _ in range(warmup):
+        ref.run(I)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in ev:
+        flush.fill_(1.0)
+        e0.record(); ref.run(I); e1.record()
+    torch.cuda.synchronize()
+    ts = [e0.elapsed_time(e1) for e0, e1 in ev]
+    ms = statistics.mean(ts)
+    del ref, I
+    torch.cuda.empty_cache()
+    return {"value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "ms_per_step_min": min(ts), "steps": steps,
+            "what": "unmodified reference code (baseline/_ref: batch_NN_loss, PointNetCls, inline entropy expressions, "
+                    "torch.optim.SGD) under torch eager on this GPU, fp32 (TF32 off), inputs resident, CUDA events"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -569,26 +640,27 @@ def run_ours(args):
                 cpu = run_cpu_baseline(w, budget_s=args.cpu_budget)
             except Exception as e:
                 cpu = {"error": repr(e)}
+        eager = None
+        if not args.skip_eager:
+            try:
+                eager = run_gpu_eager_baseline(w, dev, make_host_inputs(w, rank, pinned=False), flush,
+                                               steps=min(max(args.steps, 5), 30))
+                if "value" in eager:
+                    eager["ours_over_eager_value"] = (args.steps / t_dev) / eager["value"]     # per GPU, inputs resident
+            except Exception as e:
+                eager = {"error": repr(e)}
         line = {
             "metric": METRIC, "value": world * args.steps / t_dev, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f32+bf16",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: MS-CMRSeg adversarial step, per-rank batch {w['B']}, "
-                                   f"{w['C']}x{w['H']}x{w['W']} logits, {w['N']}-pt clouds"
-                       if args.workload == "cfg2" else args.workload,
-                       "per_rank": w, "global_batch": w["B"] * world, "parallelism": f"dp{world} (batch-sharded, D4 grad all-reduce)",
-                       "l2": f"flushed before every step ({FLUSH_BYTES >> 20} MiB write, L2 = 126 MB): outside the per-step CUDA-event intervals of `value`, "
-                             "inside the single interval of `e2e`",
-                       "e2e_pipeline": "copy stream uploads step i+1 (one flat pinned buffer) into a staging set while step i runs; "
-                                       "one device-to-device move into the step's static inputs",
-                       "cuda_graph": bool(use_graph), "mlp_precision": args.precision},
+            "config": bench_config(args.workload, w, world, args.precision, use_graph),
             "e2e": {"value": world * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": result_host.numel() * 4, "ms_per_step": t_e2e / args.steps * 1e3},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "samples_per_s": world * w["B"] * args.steps / t_dev,
-            "roofline": roof, "kernels": kernel_shares, "ops": breakdown, "large": large, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roof, "kernels": kernel_shares, "ops": breakdown, "large": large, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "clocks": clocks,
             "last_step": last,
         }
         print(json.dumps(line))
@@ -599,22 +671,25 @@ def run_ours(args):
 
 
 def run_reference(args):
-    """Reference arm for this tier: the reference's CPU path (oracle port; the Python reference
-    cannot travel to the GPU box) on the host cores, same workload / metric / unit."""
+    """Reference arm for this tier: the reference's own CPU path — its unmodified PyTorch code from baseline/_ref
+    under torch eager on every host core (oracle port only if baseline/_ref is not installed) — on the GPU arm's
+    workload / metric / unit, `--steps` timed steps after `--warmup` untimed ones.  Rank 0 alone runs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = dict(WORKLOADS[args.workload])
-    steps = max(1, min(args.steps, 10))
-    cpu = run_cpu_baseline(w, budget_s=60.0, min_steps=steps, max_steps=steps)
-    v = cpu["value"]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    warm = max(args.warmup, 1)
+    cpu = run_cpu_baseline(w, budget_s=0.0, min_steps=args.steps, max_steps=args.steps, warmup=warm)
+    v = 1e3 / cpu["ms_per_step_mean"]            # K steps / total time of the K steps
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": warm, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "per_rank": w},
+        "config": bench_config(args.workload, w, world, args.precision, not args.no_graph),
         "cpu_baseline": {**cpu, "value": v},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
     }
     print(json.dumps(line))
 
@@ -630,6 +705,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-large", action="store_true")
+    ap.add_argument("--skip-eager", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -3,7 +3,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "pcuda_common.cuh"
 
@@ -51,6 +53,24 @@ int sm_count() {
     g_sm_known[dev] = true;
   }
   return g_sm_count[dev];
+}
+
+// Opt-in to > 48 KB of dynamic shared memory.  The attribute is per (function, device): remembered per device so
+// that a process driving several GPUs sets it on each of them (a process-wide flag left every device but the
+// first without it), and guarded by the context mutex (launches may come from several host threads).
+static std::map<std::pair<const void*, int>, int> g_smem_optin;
+
+cudaError_t smem_optin_impl(const void* fn, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto key = std::make_pair(fn, dev);
+  auto it = g_smem_optin.find(key);
+  if (it != g_smem_optin.end() && it->second >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) g_smem_optin[key] = bytes;
+  return e;
 }
 
 static std::atomic<unsigned long long> g_launches{0};

@@ -418,11 +418,7 @@ extern "C" int pcuda_fcstack_fwd(const float* x, int B, int L, const pcuda_fc_la
     PCUDA_REQUIRE(!(layers[l].bn && train) || B > 1, PCUDA_E_SHAPE, "fcstack_fwd: train-mode BatchNorm needs more than 1 row");
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(fc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_done = true;
-  }
+  smem_optin(fc_fwd_kernel, 160 * 1024);
   const float* in = x;
   for (int l = 0; l < L; ++l) {
     const pcuda_fc_layer_t& y = layers[l];
@@ -474,12 +470,8 @@ extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_la
     const int threads = rb == 32 ? 512 : 1024;
     const size_t smem = sizeof(float) * static_cast<size_t>(rb) * std::max(y.cout, threads);
     PCUDA_REQUIRE(smem <= 160 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_bwd: first layer too wide for the input-gradient kernel");
-    static bool pull_attr_done = false;
-    if (!pull_attr_done) {
-      cudaFuncSetAttribute(fc_pull_kernel<32, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      cudaFuncSetAttribute(fc_pull_kernel<16, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      pull_attr_done = true;
-    }
+    smem_optin(fc_pull_kernel<32, 512>, 160 * 1024);
+    smem_optin(fc_pull_kernel<16, 1024>, 160 * 1024);
     if (rb == 32) fc_pull_kernel<32, 512><<<(y.cin + 31) / 32, 512, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
     else fc_pull_kernel<16, 1024><<<(y.cin + 31) / 32, 1024, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
     ++launches;

@@ -19,6 +19,11 @@ int check_launch(const char* what);  // returns cudaGetLastError() as a positive
 void count_launch(int n = 1);        // bench accounting: kernels launched by this library
 int sm_count();
 int tuning(int key);
+cudaError_t smem_optin_impl(const void* fn, int bytes);   // per (kernel, device) opt-in to large dynamic shared memory
+template <class F>
+static inline cudaError_t smem_optin(F* fn, int bytes) {
+  return smem_optin_impl(reinterpret_cast<const void*>(fn), bytes);
+}
 
 enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_FP32 = 2, TUNE_MLP_TC_MASK = 3, TUNE_MLP_EPI_DEBUG = 4, TUNE_CHAMFER_SEED = 5, TUNE_MLP_NO_FORK = 6, TUNE_NKEYS = 8 };
 

@@ -1655,11 +1655,7 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       const size_t dw_smem = sizeof(float) * ((kDwCh * (K + 2 * static_cast<size_t>(B)) + 3) & ~static_cast<size_t>(3)) +
                              sizeof(double) * kDwParts * 128 * kDwCh;
       PCUDA_REQUIRE(dw_smem <= 200 * 1024, PCUDA_E_UNSUPPORTED, "pointmlp_bwd: batch %d too large for the pooled wgrad kernel", B);
-      static bool dw_attr_done = false;
-      if (!dw_attr_done) {
-        cudaFuncSetAttribute(pool_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        dw_attr_done = true;
-      }
+      smem_optin(pool_dw_kernel, 200 * 1024);
       // the pooled layer's weight gradient reads coef / kappa (this stream) and abar / Ghat (Gram side) and writes
       // only grad_weight: it runs on the auxiliary stream beside the dgrad kernels below; joined before returning
       if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sa, ax->fork, 0); }
@@ -1670,13 +1666,9 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       const DgradOut o = dgrad_out(L - 2, dzbuf[cur]);
       const size_t sparse_smem = pool_sparse_smem(C, N, K);
       if (tc_on(precision, TC_POOL_DGRAD) && a_in && w.qpack && tc::pool_dgrad_fits(K) && sparse_smem <= 200 * 1024 && K <= 512 && C <= 65535) {
-        static bool attr_done = false;
-        if (!attr_done) {
-          cudaFuncSetAttribute(pool_sparse_kernel<4, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-          cudaFuncSetAttribute(pool_sparse_kernel<4, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-          cudaFuncSetAttribute(pool_sparse_kernel<16, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-          attr_done = true;
-        }
+        smem_optin(pool_sparse_kernel<4, 12, 1>, 200 * 1024);
+        smem_optin(pool_sparse_kernel<4, 4, 2>, 100 * 1024);
+        smem_optin(pool_sparse_kernel<16, 2, 1>, 200 * 1024);
         // dense part on the tensor cores: dz_prev = mask * (-u - a Q) (+ its column sums) ...
         if (!q_packed)
           if (int rc = tc::pack_w(w.Q, K, K, false, w.qpack, st)) return rc;

@@ -805,11 +805,9 @@ int launch_ws(WsParams& p, cudaStream_t st, const char* what) {
   if (!pl.ok) return fail(PCUDA_E_UNSUPPORTED, "%s: K=%d R=%d does not fit the tensor-core kernel", what, p.K, p.R);
   p.CB = pl.CB; p.G = pl.G; p.nstage = pl.nstage;
   p.dbg = tuning(TUNE_MLP_EPI_DEBUG);
-  static bool attr_done[4] = {false, false, false, false};
-  if (!attr_done[MODE]) {
-    cudaError_t e = cudaFuncSetAttribute(ws_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  {
+    cudaError_t e = smem_optin(ws_kernel<MODE>, static_cast<int>(kSmemBudget));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-    attr_done[MODE] = true;
   }
   ws_kernel<MODE><<<pl.grid, WsCfg<MODE>::kThreads, pl.smem, st>>>(p);
   count_launch();
@@ -907,11 +905,9 @@ static int launch_pt(PtParams& p, cudaStream_t st, const char* what) {
   const int ns = static_cast<int>((kSmemBudget - fixed) / stage);
   if (ns < 1) return fail(PCUDA_E_UNSUPPORTED, "%s: Kr=%d does not fit", what, p.Kr);
   p.nstage = std::min(4, ns);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(pt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  {
+    cudaError_t e = smem_optin(pt_kernel, static_cast<int>(kSmemBudget));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-    attr_done = true;
   }
   const dim3 grid(p.S, (p.C + 127) / 128);
   pt_kernel<<<grid, kPtThreads, fixed + p.nstage * stage, st>>>(p);

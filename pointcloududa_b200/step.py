@@ -246,19 +246,45 @@ class AdversarialStep:
             self._body()
         return self.result
 
+    def _snapshot_state(self):
+        """Everything a step mutates besides its outputs: D4's parameters and buffers (BatchNorm running statistics,
+        num_batches_tracked), the optimiser's momentum and the device RNG (Dropout)."""
+        return ([p.detach().clone() for p in self.bucket.params],
+                [b.detach().clone() for b in self.d4.buffers()],
+                self.opt.momentum_buffer.clone(), torch.cuda.get_rng_state(self.device))
+
+    def _restore_state(self, snap) -> None:
+        params, bufs, mom, rng = snap
+        with torch.no_grad():
+            for p, q in zip(self.bucket.params, params):
+                p.copy_(q)
+            for b, q in zip(self.d4.buffers(), bufs):
+                b.copy_(q)
+            self.opt.momentum_buffer.copy_(mom)
+        torch.cuda.set_rng_state(rng, self.device)
+
     def capture(self, warmup: int = 3) -> None:
         """Capture the step into CUDA graphs.  Single GPU: one graph.  With a process group the step
         is captured as two graphs around the gradient all-reduce, which stays an ordinary NCCL call
-        on the same stream."""
+        on the same stream.
+
+        The warm-up steps that precede the capture (allocator pools, lazy library state) run for real on whatever
+        the input buffers hold; the training state they touch -- D4's parameters, BatchNorm buffers and
+        num_batches_tracked, the SGD momentum, the Dropout RNG -- is saved before and restored after, so capturing
+        a model mid-training or right after load_state_dict() does not move it off the reference trajectory."""
         import torch.distributed as dist
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self._sync_world()
+        torch.cuda.synchronize(self.device)
+        snap = self._snapshot_state()
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(warmup):
                 self._body()
         torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self._restore_state(snap)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         if not multi:

@@ -201,3 +201,163 @@ def test_pointnet_oracle_bf16_operands_only_touch_wide_layers():
     l0 = oracle.pointnet_forward(params, x, spec, dtype=np.float64)[0]
     l1 = oracle.pointnet_forward(params, x, spec, dtype=np.float64, bf16_operands=True)[0]
     assert not np.array_equal(l0, l1) and np.abs(l0 - l1).max() < 0.5 * np.abs(l0).max()
+
+
+# ------------------------------------------------- torch restatement of the step (oracle/torch_step.py) ----
+def _torch_sd(spec, params, dtype):
+    """state_dict-shaped dict of torch tensors (parameters from `params`, fresh BatchNorm buffers)."""
+    import torch
+    from oracle import torch_step  # noqa: F401
+    sd = {}
+    for k, v in params.items():
+        sd[k] = torch.from_numpy(v.copy()).to(dtype)
+        mod = k.rsplit(".", 1)[0]
+        if mod.rsplit(".", 1)[-1].startswith("bn") and k.endswith(".weight"):
+            sd[mod + ".running_mean"] = torch.zeros(v.shape, dtype=dtype)
+            sd[mod + ".running_var"] = torch.ones(v.shape, dtype=dtype)
+            sd[mod + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    return sd
+
+
+@pytest.mark.parametrize("case", list(POINTNET_CASES))
+def test_torch_restatement_vs_reference_golden(golden_pointnet, case):
+    """oracle/torch_step.D4 (the oracle the GPU step-parity tests lean on) reproduces the reference's own logits,
+    transforms, input gradient, sampled parameter gradients and BatchNorm buffers."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import torch_step
+    g = golden_pointnet[case]
+    kw, B, N, seed = POINTNET_CASES[case]
+    spec = oracle.PointNetSpec(**kw)
+    tol, gtol = POINTNET_TOL[case]
+    sd = _torch_sd(spec, oracle.make_params(spec, seed), torch.float64)
+    keys = torch_step.trainable_keys(sd)
+    leaves = {k: (v.requires_grad_(True) if k in keys else v) for k, v in sd.items()}
+    x = torch.from_numpy(g["pts"]).double().transpose(2, 1).requires_grad_(True)
+    net = torch_step.D4(leaves, feature_transform=spec.feature_transform, ext=spec.ext, sample_transform=spec.sample_transform)
+    logit, trans, trans_feat = net(x)
+    assert max_rel(logit.detach().numpy(), g["logit"]) < tol
+    if trans is not None:
+        assert max_rel(trans.detach().numpy(), g["trans"]) < tol
+    if trans_feat is not None:
+        assert max_rel(trans_feat.detach().sum(dim=(1, 2)).numpy(), g["trans_feat_sum"]) < tol
+    for k, v in sd.items():
+        if f"buf/{k}" in g:
+            assert max_rel(v.detach().numpy(), g[f"buf/{k}"]) < 1e-4, k
+    if gtol is None:
+        return
+    loss = F.binary_cross_entropy_with_logits(logit, torch.ones_like(logit))
+    used = [k for k in keys if spec.sample_transform or not k.startswith("feat.stn.")]
+    grads = torch.autograd.grad(loss, [x] + [leaves[k] for k in used])
+    assert max_rel(grads[0].numpy(), g["grad_x"]) < gtol
+    for k, gr in zip(used, grads[1:]):
+        gs = g[f"gsample/{k}"]
+        mine = gr.numpy().reshape(-1)
+        idx = sample_index(mine.size, k)
+        scale = max(np.abs(gs).max(), float(g[f"gnorm/{k}"]) / np.sqrt(mine.size), 1e-12)
+        leaf = k.rsplit(".", 2)[-2]
+        if k.endswith(".bias") and (leaf.startswith("conv") or leaf in ("fc1", "fc2")):
+            assert np.abs(mine).max() < 1e-9, k
+        else:
+            assert np.abs(mine[idx] - gs).max() <= gtol * scale + gtol * 1e-3, k
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(feature_transform=True, ext=True)])
+def test_torch_restatement_bf16_equals_numpy_oracle(kw):
+    """The two same-rounding oracles (numpy pointnet_forward/backward with bf16_operands, torch D4 with
+    bf16_operands) agree in float64: logits, input gradient, every parameter gradient."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import torch_step
+    spec = oracle.PointNetSpec(**kw)
+    params = oracle.make_params(spec, 5)
+    rs = np.random.RandomState(6)
+    pts = (rs.rand(4, 48, 3) * rs.uniform(0.3, 1.0, (4, 1, 3))).astype(np.float32)
+    xo = np.ascontiguousarray(pts.transpose(0, 2, 1))
+    lo, _, _, cache = oracle.pointnet_forward(params, xo, spec, dtype=np.float64, bf16_operands=True)
+    dlogit = ((1.0 / (1.0 + np.exp(-lo))) - 1.0) / lo.shape[0]
+    dx, grads = oracle.pointnet_backward(dlogit, cache)
+    sd = _torch_sd(spec, params, torch.float64)
+    keys = torch_step.trainable_keys(sd)
+    leaves = {k: (v.requires_grad_(True) if k in keys else v) for k, v in sd.items()}
+    x = torch.from_numpy(pts).double().transpose(2, 1).requires_grad_(True)
+    logit = torch_step.D4(leaves, bf16_operands=True, **kw)(x)[0]
+    assert max_rel(logit.detach().numpy(), lo) < 1e-9
+    loss = F.binary_cross_entropy_with_logits(logit, torch.ones_like(logit))
+    gr = torch.autograd.grad(loss, [x] + [leaves[k] for k in keys])
+    assert max_rel(gr[0].numpy(), dx) < 1e-7
+    for k, t in zip(keys, gr[1:]):
+        ref = grads[k].reshape(t.shape)
+        scale = max(np.abs(ref).max(), 1e-12)
+        assert np.abs(t.numpy() - ref).max() <= 1e-6 * scale + 1e-12, k
+
+
+def test_torch_restatement_step_runs_and_moves_parameters():
+    """One restated step on the CPU: finite results, BatchNorm buffers advanced three times, SGD applied."""
+    import torch
+    from oracle import torch_step
+    from pointcloududa_b200.synth import synth_clouds, synth_logits
+    spec = oracle.PointNetSpec()
+    sd = _torch_sd(spec, oracle.make_params(spec, 2), torch.float64)
+    before = {k: v.clone() for k, v in sd.items()}
+    B, N = 4, 64
+    xS, yA = synth_clouds(B, N, seed=1, mode="near")
+    xT, yB = synth_clouds(B, N, seed=2, mode="uniform")
+    inputs = dict(oS=synth_logits(B, 4, 16, 16, seed=3), oT=synth_logits(B, 4, 16, 16, seed=4),
+                  grad_mapT=synth_logits(B, 4, 16, 16, seed=5, std=1.0), vertS=xS, vertT=xT, vertexA=yA, vertexB=yB)
+    inputs = {k: v.double() for k, v in inputs.items()}
+    mom = {}
+    out = torch_step.adversarial_step(sd, inputs, mom)
+    assert torch.isfinite(out["result"]).all() and len(out["result"]) == len(torch_step.RESULT_FIELDS)
+    assert int(sd["feat.bn3.num_batches_tracked"]) == 3
+    assert not torch.equal(sd["fc3.weight"], before["fc3.weight"])
+    w = "feat.conv3.weight"
+    want = before[w] - 2.5e-5 * (out["grads"][w] + 0.0005 * before[w])
+    assert torch.allclose(sd[w], want, rtol=0, atol=1e-15)
+    assert out["grad_vertS"].shape == (B, N, 3) and out["grad_oT"].shape == inputs["oT"].shape
+
+
+def test_reference_step_equals_torch_restatement():
+    """The reference's own code run as one step (baseline/ref_step.py over baseline/_ref, the arm bench.py times)
+    and the restated step agree: this pins oracle/torch_step.adversarial_step — every result field, the three input
+    gradients, the parameters and BatchNorm buffers after SGD — to the reference itself.  Needs baseline/_ref
+    (python baseline/make_ref.py in a container that has /root/reference)."""
+    import torch
+    from baseline import ref_step
+    from oracle import torch_step
+    from bench import WORKLOADS
+    if not ref_step.available():
+        pytest.skip("baseline/_ref not installed")
+    torch.set_num_threads(2)
+    w = dict(WORKLOADS["cfg2"]); w.update(B=6, H=32, W=32, N=64)
+    host = torch_step.conditioned_inputs(w, 11)
+    ref = ref_step.ReferenceStep(w, "cpu", seed=0)
+    for m in ref.model_dis4.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    sd = {k: (v.detach().clone().double() if v.is_floating_point() else v.clone()) for k, v in ref.model_dis4.state_dict().items()}
+    mom = {}
+    start = {k: v.clone() for k, v in sd.items()}
+    inputs = {k: v.double() for k, v in host.items()}
+    for it in range(2):
+        res = ref.run(host)
+        out = torch_step.adversarial_step(sd, inputs, mom, activation="sigmoid", normalize=False)
+        assert max_rel(res.numpy(), out["result"].numpy()) < 2e-5, it
+        assert max_rel(ref.grad_vertS.numpy(), out["grad_vertS"].numpy()) < 5e-3       # autograd's own cancellation noise
+        assert max_rel(ref.grad_oT.numpy(), out["grad_oT"].numpy()) < 1e-5
+        assert max_rel(ref.grad_vertT.numpy(), out["grad_vertT"].numpy()) < 1e-3
+        now = ref.model_dis4.state_dict()
+        for k, v in sd.items():
+            leaf = k.rsplit(".", 2)[-2] if k.count(".") else k
+            if leaf.startswith("in"):
+                continue
+            if k.endswith("num_batches_tracked"):
+                assert int(now[k]) == int(v) == 3 * (it + 1), k
+            elif "running" in k:
+                assert max_rel(now[k].numpy(), v.numpy()) < 1e-4, k
+            else:
+                # parameters move by lr * grad ~ 1e-5: compared on the scale of the accumulated update (gradient
+                # accuracy of the fp32 reference through batch-of-4 BatchNorms) plus fp32 resolution of the value
+                upd = (v - start[k]).abs().max().item()
+                err = np.abs(now[k].double().numpy() - v.numpy()).max()
+                assert err <= 5e-3 * upd + 2e-7 * v.abs().max().item() + 1e-10, (k, err, upd)   # 1e-10: mathematically zero gradients
