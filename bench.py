@@ -29,7 +29,7 @@ UNIT = "steps/s"
 WORKLOADS = {
     # BASELINE.json configs[1]: MS-CMRSeg step on 1xB200 (per-rank batch under weak scaling)
     "cfg2": dict(B=8, C=4, H=224, W=224, N=300, activation="sigmoid", normalize=False, return_prob=False),
-    # configs[2] per-rank shard is B=4; the full single-GPU batch:
+    # configs[2]: MM-WHS step, global batch 32 (strong scaling: 32 / n_gpus clouds per rank, 4 per rank on 8 GPUs)
     "cfg3": dict(B=32, C=5, H=256, W=256, N=1024, activation="softmax", normalize=True, return_prob=True),
     # configs[4] per-rank shard (32 of 256 samples)
     "cfg5_rank": dict(B=32, C=5, H=256, W=256, N=4096, activation="softmax", normalize=True, return_prob=True),
@@ -507,72 +507,29 @@ def large_shape_rooflines(flush, pk: dict):
     return res
 
 
-def run_ours(args):
+def measure_step(step, host_flat, result_host, flush, steps: int, world: int, dev):
+    """(seconds of `steps` device-resident steps, seconds of `steps` end-to-end steps) on this rank.
+    Device-resident: per-step CUDA events, L2 flushed before every step (outside the intervals).  End to end: the way
+    a training loop feeds the step -- a copy stream uploads step i+1's inputs from pinned host memory into one of two
+    staging sets while step i computes; the compute stream moves the staged set into the step's static input buffers
+    (device-to-device), runs the step and reads the 32-byte result back -- timed as ONE interval over all steps
+    (every upload, staging move, flush, compute and read-back inside it)."""
     import torch
     import torch.distributed as dist
-    from pointcloududa_b200 import dist as pdist
-    from pointcloududa_b200 import ops
-    from pointcloududa_b200.step import RESULT_FIELDS, AdversarialStep, StepConfig
-
-    rank, local, world = pdist.init_from_env("nccl")
-    if world != args.gpus:
-        if rank == 0:
-            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    w = dict(WORKLOADS[args.workload])
-    pk = peaks()
-    cfg = StepConfig(B=w["B"], C=w["C"], H=w["H"], W=w["W"], N=w["N"], activation=w["activation"],
-                     normalize=w["normalize"], return_prob=w["return_prob"], precision=args.precision)
-    step = AdversarialStep(cfg, dev, seed=0)
-    # one pinned host buffer holding a step's inputs in the step's flat layout: one H2D copy per step
-    host_flat = torch.zeros(step.input_numel(), dtype=torch.float32).pin_memory()
-    host = step.input_layout(host_flat)
-    for k, v in make_host_inputs(w, rank, pinned=False).items():
-        host[k].copy_(v)
-    step.inputs_flat.copy_(host_flat)
-    h2d_bytes = host_flat.numel() * 4
-    result_host = torch.empty(len(RESULT_FIELDS), dtype=torch.float32).pin_memory()
-    flush = torch.empty(FLUSH_BYTES // 4, device=dev)
-
-    # launches per step, counted on an eager step (a graph replays exactly these)
-    step.run(); torch.cuda.synchronize()
-    l0 = ops.launch_count(); step.run(); torch.cuda.synchronize()
-    launches_per_step = ops.launch_count() - l0
-
-    use_graph = not args.no_graph
-    if use_graph:
-        step.capture(warmup=2)
-    for _ in range(max(args.warmup, 3)):
-        step.run()
-    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-
-    # ---- device-resident timing: K steps, per-step CUDA events, L2 flushed between steps ---------
     barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for e0, e1 in ev:
         flush.fill_(1.0)
         e0.record(); step.run(); e1.record()
     barrier()
     t_dev = sum(e0.elapsed_time(e1) for e0, e1 in ev) / 1e3
 
-    # ---- end-to-end: pinned host -> device inputs, step, device -> host result, per step --------
-    # The way a training loop feeds the step: a copy stream uploads step i+1's inputs from pinned host
-    # memory into one of two staging sets while step i computes; the compute stream then moves the
-    # staged set into the step's static input buffers (device-to-device), runs the step and reads the
-    # 32-byte result back.  Timed as ONE interval over all K steps (every step's upload, staging move,
-    # compute and read-back lie inside it), L2 flushed before every step.
     copy_stream = torch.cuda.Stream(device=dev)
     staging = [torch.empty_like(step.inputs_flat) for _ in range(2)]
     staged = [torch.cuda.Event() for _ in range(2)]
@@ -592,8 +549,8 @@ def run_ours(args):
     flush.fill_(1.0)
     e2e0.record()
     upload(0)
-    for i in range(args.steps):
-        if i + 1 < args.steps:
+    for i in range(steps):
+        if i + 1 < steps:
             upload(i + 1)
         main.wait_event(staged[i % 2])
         step.inputs_flat.copy_(staging[i % 2], non_blocking=True)
@@ -604,13 +561,152 @@ def run_ours(args):
     e2e1.record()
     barrier()
     t_e2e = e2e0.elapsed_time(e2e1) / 1e3
-    clocks = sampler.stop() if rank == 0 else None
-    last = {k: float(v) for k, v in zip(RESULT_FIELDS, result_host.tolist())}
-
     tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = tt.tolist()
+    return t_dev, t_e2e
+
+
+def build_step(w: dict, rank: int, dev, precision: str, use_graph: bool, exchange: str = "auto"):
+    """AdversarialStep of workload `w` with its inputs loaded (per-rank synthetic shard), captured and warmed up."""
+    import torch
+    from pointcloududa_b200.step import RESULT_FIELDS, AdversarialStep, StepConfig
+    cfg = StepConfig(B=w["B"], C=w["C"], H=w["H"], W=w["W"], N=w["N"], activation=w["activation"],
+                     normalize=w["normalize"], return_prob=w["return_prob"], precision=precision)
+    step = AdversarialStep(cfg, dev, seed=0, exchange=exchange)
+    # one pinned host buffer holding a step's inputs in the step's flat layout: one H2D copy per step
+    host_flat = torch.zeros(step.input_numel(), dtype=torch.float32).pin_memory()
+    host = step.input_layout(host_flat)
+    for k, v in make_host_inputs(w, rank, pinned=False).items():
+        host[k].copy_(v)
+    step.inputs_flat.copy_(host_flat)
+    result_host = torch.empty(len(RESULT_FIELDS), dtype=torch.float32).pin_memory()
+    return step, host_flat, result_host
+
+
+def scale_lines(args, rank: int, world: int, dev, flush):
+    """The multi-GPU configurations BASELINE.json names, measured in the same run as `value` so that the driver's
+    1/2/4/8-GPU scaling runs carry them: cfg-5 (batch 256 over 8 GPUs = 32 clouds of 4096 points per rank; weak
+    scaling, per-rank work fixed) and cfg-3 (MM-WHS, global batch 32 split over the ranks; strong scaling, 4 per
+    rank on 8 GPUs), plus the cfg-4 Chamfer-only sweep (batch 64 split over the ranks)."""
+    import torch
+    out = {}
+    steps = max(5, min(args.steps, 20))
+    for name, scaling in (("cfg5_rank", "weak"), ("cfg3", "strong")):
+        w = dict(WORKLOADS[name])
+        if scaling == "strong":
+            if w["B"] % world != 0 or w["B"] // world < 2:
+                out[name] = {"skipped": f"global batch {w['B']} does not split into >= 2 clouds on each of {world} ranks"}
+                continue
+            w["B"] //= world
+        try:
+            step, host_flat, result_host = build_step(w, rank, dev, args.precision, not args.no_graph, args.exchange)
+            if not args.no_graph:
+                step.capture(warmup=2)
+            for _ in range(3):
+                step.run()
+            torch.cuda.synchronize()
+            t_dev, t_e2e = measure_step(step, host_flat, result_host, flush, steps, world, dev)
+            units = world if scaling == "weak" else 1           # per-rank-shard steps (weak) / global-batch steps (strong)
+            out[name] = {"scaling": scaling, "per_rank_batch": w["B"], "global_batch": w["B"] * world, "steps": steps,
+                         "workload": workload_label(name, w), "exchange": step.exchange,
+                         "value": units * steps / t_dev,
+                         "unit": "global-batch steps/s" if scaling == "strong" else "per-rank-shard steps/s summed over ranks",
+                         "ms_per_step": t_dev / steps * 1e3, "samples_per_s": world * w["B"] * steps / t_dev,
+                         "e2e": {"value": units * steps / t_e2e, "ms_per_step": t_e2e / steps * 1e3,
+                                 "h2d_bytes_per_step": host_flat.numel() * 4, "d2h_bytes_per_step": result_host.numel() * 4}}
+            if step.comm is not None:
+                step.comm.check_status()
+                step.comm.destroy()
+            del step, host_flat
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out[name] = {"error": repr(e)}
+    try:
+        out["cfg4_chamfer"] = chamfer_sweep(rank, world, dev, flush)
+    except Exception as e:
+        out["cfg4_chamfer"] = {"error": repr(e)}
+    return out
+
+
+CFG4_POINTS = (256, 512, 1024, 2048, 4096, 8192, 16384)
+
+
+def chamfer_sweep(rank: int, world: int, dev, flush, B: int = 64, points=CFG4_POINTS, iters: int = 5):
+    """BASELINE.json configs[3]: Chamfer-only sweep, 256-16k points per cloud, batch 64 sharded over the ranks
+    (no collective on the data path: each rank owns 64 / n_gpus clouds).  Forward (both directions, indices, loss)
+    per size; ordered pairs/s = 2 * B * N^2 / max-over-ranks device time, L2 flushed before every launch."""
+    import torch
+    import torch.distributed as dist
+    from pointcloududa_b200 import ops
+    from pointcloududa_b200.synth import synth_clouds
+    if B % world:
+        return {"skipped": f"batch {B} does not split over {world} ranks"}
+    Br = B // world
+    res = {"batch": B, "per_rank_batch": Br, "scaling": "strong", "unit": "T ordered pairs/s", "sizes": {}}
+    for N in points:
+        x, y = synth_clouds(B, N, seed=9, mode="near")
+        x, y = x[rank * Br:(rank + 1) * Br].to(dev), y[rank * Br:(rank + 1) * Br].to(dev)
+        for _ in range(2):
+            ops.chamfer_nn(x, y)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ops.chamfer_nn(x, y); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([statistics.mean(ts)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        res["sizes"][str(N)] = {"ms": ms, "tpairs_s": 2.0 * B * N * N / ms / 1e9}
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pointcloududa_b200 import dist as pdist
+    from pointcloududa_b200 import ops
+    from pointcloududa_b200.step import RESULT_FIELDS
+
+    rank, local, world = pdist.init_from_env("nccl")
+    if world != args.gpus:
+        if rank == 0:
+            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    w = dict(WORKLOADS[args.workload])
+    pk = peaks()
+    step, host_flat, result_host = build_step(w, rank, dev, args.precision, not args.no_graph, args.exchange)
+    h2d_bytes = host_flat.numel() * 4
+    flush = torch.empty(FLUSH_BYTES // 4, device=dev)
+
+    # launches per step, counted on an eager step (a graph replays exactly these)
+    step.run(); torch.cuda.synchronize()
+    l0 = ops.launch_count(); step.run(); torch.cuda.synchronize()
+    launches_per_step = ops.launch_count() - l0
+
+    use_graph = not args.no_graph
+    if use_graph:
+        step.capture(warmup=2)
+    for _ in range(max(args.warmup, 3)):
+        step.run()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_dev, t_e2e = measure_step(step, host_flat, result_host, flush, args.steps, world, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    last = {k: float(v) for k, v in zip(RESULT_FIELDS, result_host.tolist())}
 
     # kernel-level profile of the step: collective inside, so every rank runs the steps; rank 0 records
     kernel_shares, roof = None, None
@@ -621,6 +717,10 @@ def run_ours(args):
         if rank == 0 and world > 1:
             for _ in range(5):   # keep the collective count matched with the other ranks
                 step.run()
+    # the multi-GPU configurations BASELINE.json names + the Chamfer-only sweep (collective: every rank takes part)
+    scale = None
+    if not args.skip_scale:
+        scale = scale_lines(args, rank, world, dev, flush)
     line = None
     if rank == 0:
         breakdown, roof_ops = op_breakdown(step, w, flush, pk)
@@ -660,12 +760,16 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "samples_per_s": world * w["B"] * args.steps / t_dev,
+            "exchange": step.exchange, "scale": scale,
             "roofline": roof, "kernels": kernel_shares, "ops": breakdown, "large": large, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "clocks": clocks,
             "last_step": last,
         }
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        if step.comm is not None:
+            step.comm.check_status()
+            step.comm.destroy()
         dist.destroy_process_group()
     return line
 
@@ -706,6 +810,9 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-large", action="store_true")
     ap.add_argument("--skip-eager", action="store_true")
+    ap.add_argument("--skip-scale", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl", "torch"],
+                    help="how D4's gradient bucket is summed over the ranks (pointcloududa_b200/step.py)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -17,11 +17,14 @@
  *   pcuda_bce_logits              F.binary_cross_entropy_with_logits + accuracy, train_mscmrseg.py:233,286-296,316-322
  *   pcuda_grad_sum_pack /         .grad accumulation of the two D4 backward passes (train_mscmrseg.py:288,319) and
  *   pcuda_sgd_momentum_step       optim_dis4.step() = torch.optim.SGD(momentum, weight_decay) (:329-330,:450-455)
+ *   pcuda_comm_*                  no counterpart (the reference is single-process): sum of D4's parameter gradients over
+ *                                 the batch-sharded ranks in front of optim_dis4.step()
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless the parameter is documented "host";
  *   - the caller allocates inputs, outputs and workspaces and keeps them alive until the
- *     stream has passed the launch; the library owns no device memory;
+ *     stream has passed the launch; the library owns no device memory except what a communicator
+ *     (pcuda_comm_init ... pcuda_comm_destroy) holds: its NCCL communicator and its peer-memory region;
  *   - launches are asynchronous on `stream`; no entry point synchronises, allocates or frees,
  *     so all of them are legal under CUDA-graph stream capture (pcuda_pointmlp_fwd / _bwd
  *     fork onto an internal auxiliary stream and join back before returning; under capture the
@@ -66,7 +69,8 @@ int pcuda_sm_count(void);
  * +300000: prefiltered at 72 registers), 2 = force the FP32 MLP kernels,
  * 3 = bit mask of MLP pieces switched from tcgen05 back to FP32 (1 forward, 2 pooled dgrad,
  * 4 dense dgrad, 8 wgrad, 16 Gram), 4 = timing experiments of the pooled tensor-core layer (results invalid),
- * 5 = chamfer seed-pass stride (0 default, < 0 off), 6 = no auxiliary-stream fork / finalise-on-read in the MLP. */
+ * 5 = chamfer seed-pass stride (0 default, < 0 off), 6 = no auxiliary-stream fork / finalise-on-read in the MLP,
+ * 7 = CTAs of the peer-memory all-reduce (0 default). */
 int pcuda_tune(int key, int value);
 /* Number of kernels this library has launched in this process (monotone; for bench accounting). */
 uint64_t pcuda_launch_count(void);
@@ -289,6 +293,34 @@ int pcuda_sgd_momentum_step(const pcuda_param_slot_t* slots /*host*/, int n, con
  */
 int pcuda_bce_logits(const float* logit, int n, float target, float weight, float* loss, float* grad_logit,
                      float* accuracy, pcuda_stream_t stream);
+
+/* ---- multi-GPU exchange ----------------------------------------------------------
+ * One process per GPU; rank r holds samples [r*B/R, (r+1)*B/R).  The only data-path exchange of the step is the sum
+ * of D4's parameter gradients in front of the SGD step.  A communicator is created once per process on the CURRENT
+ * device (collective call: every rank calls pcuda_comm_init with the same 128-byte id, which rank 0 obtains from
+ * pcuda_comm_unique_id and distributes by any means, e.g. torch.distributed.broadcast_object_list).
+ *   pcuda_comm_allreduce      in-place sum of `count` floats over the ranks: ncclAllReduce on `stream` (libnccl is
+ *                             bound with dlopen on first use; error codes 1000 + ncclResult_t).
+ *   pcuda_comm_allreduce_p2p  the same sum over NVLink peer memory, for buffers that live inside the communicator's
+ *                             symmetric region (pcuda_comm_p2p_buffers): reads `count` floats of every rank's `in`
+ *                             buffer, leaves the sum in every rank's `out` buffer — one kernel, two-shot (each rank
+ *                             reduces its 1/R slice in rank order and stores it to all peers), bit-identical on all
+ *                             ranks.  Needs p2p_floats >= count at init, <= 8 ranks on one node with peer access
+ *                             (pcuda_comm_info tells whether it is available).  Every rank must issue the same
+ *                             sequence of calls.  The producer of `in` and the consumer of `out` are ordinary
+ *                             kernels before / after it on `stream`.
+ * Both are asynchronous launches on `stream` and legal under CUDA-graph capture.  pcuda_comm_status returns
+ * non-zero if a peer-memory wait ever gave up (a peer never arrived within ~2 s).
+ */
+typedef struct pcuda_comm pcuda_comm_t;
+int pcuda_comm_unique_id(void* id_out /*host, >= 128 bytes*/, int bytes);
+int pcuda_comm_init(const void* unique_id /*host, 128 bytes*/, int rank, int world, size_t p2p_floats, pcuda_comm_t** out);
+int pcuda_comm_allreduce(pcuda_comm_t* comm, float* buf, int64_t count, pcuda_stream_t stream);
+int pcuda_comm_p2p_buffers(pcuda_comm_t* comm, float** in, float** out, int64_t* capacity_floats);
+int pcuda_comm_allreduce_p2p(pcuda_comm_t* comm, int64_t count, pcuda_stream_t stream);
+int pcuda_comm_status(pcuda_comm_t* comm);
+int pcuda_comm_info(pcuda_comm_t* comm, int* rank, int* world, int* p2p_available, int* nccl_version);
+int pcuda_comm_destroy(pcuda_comm_t* comm);
 
 #ifdef __cplusplus
 }

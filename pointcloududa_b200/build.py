@@ -64,7 +64,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
         objs = list(ex.map(compile_one, sources))
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"]
+        cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -95,7 +95,7 @@ const char* pcuda_error_name(int code) {
     case PCUDA_E_UNSUPPORTED: return "PCUDA_E_UNSUPPORTED";
     case PCUDA_E_ALIGN: return "PCUDA_E_ALIGN";
     case PCUDA_E_WORKSPACE: return "PCUDA_E_WORKSPACE";
-    default: return code > 0 ? cudaGetErrorName(static_cast<cudaError_t>(code)) : "PCUDA_E_?";
+    default: return code >= 1000 ? "NCCL error (1000 + ncclResult_t)" : (code > 0 ? cudaGetErrorName(static_cast<cudaError_t>(code)) : "PCUDA_E_?");
   }
 }
 

@@ -36,16 +36,97 @@ def check_per_rank_batch(batch: int, world: int) -> None:
                          "PointNetCls needs >= 2 clouds per call")
 
 
+class _DeviceSpan:
+    """A span of device memory owned by libpcuda, exposed through __cuda_array_interface__ (zero-copy torch view)."""
+
+    def __init__(self, ptr: int, numel: int, owner):
+        self.owner = owner        # keeps the communicator (and with it the memory) alive as long as a view exists
+        self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PcudaComm:
+    """libpcuda's communicator (include/pcuda.h `pcuda_comm_*`): an NCCL communicator bound at run time plus, for up
+    to 8 ranks of one node with peer access, a symmetric peer-memory region for the NVLink all-reduce kernel.
+
+    Collective constructor: every rank of `group` calls it.  torch.distributed is used once, to hand rank 0's
+    128-byte NCCL id to the other ranks."""
+
+    def __init__(self, device: torch.device, p2p_floats: int = 0, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PcudaComm needs an initialised torch.distributed process group (plumbing for the id exchange)")
+        self.device = torch.device(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        L = _lib.lib()
+        buf = ctypes.create_string_buffer(128)
+        with torch.cuda.device(self.device):
+            if self.rank == 0:
+                _lib.check(L.pcuda_comm_unique_id(buf, 128), "pcuda_comm_unique_id")
+            box = [bytes(buf.raw)]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            idbuf = ctypes.create_string_buffer(box[0], 128)
+            handle = ctypes.c_void_p()
+            _lib.check(L.pcuda_comm_init(idbuf, self.rank, self.world, int(p2p_floats), ctypes.byref(handle)), "pcuda_comm_init")
+        self._h = handle
+        r, w, p2p, ver = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(L.pcuda_comm_info(self._h, ctypes.byref(r), ctypes.byref(w), ctypes.byref(p2p), ctypes.byref(ver)), "pcuda_comm_info")
+        self.p2p, self.nccl_version = bool(p2p.value), int(ver.value)
+        self.buf_in = self.buf_out = None
+        if self.p2p:
+            pin, pout, cap = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+            _lib.check(L.pcuda_comm_p2p_buffers(self._h, ctypes.byref(pin), ctypes.byref(pout), ctypes.byref(cap)), "pcuda_comm_p2p_buffers")
+            self.capacity = int(cap.value)
+            self.buf_in = torch.as_tensor(_DeviceSpan(pin.value, self.capacity, self), device=self.device)
+            self.buf_out = torch.as_tensor(_DeviceSpan(pout.value, self.capacity, self), device=self.device)
+
+    def allreduce_(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum over the ranks (ncclAllReduce on the current stream; CUDA-graph capturable)."""
+        from . import _lib
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+            raise _lib.PcudaError("PcudaComm.allreduce_ needs a contiguous float32 tensor on the communicator's device")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().pcuda_comm_allreduce(self._h, t.data_ptr(), t.numel(), torch.cuda.current_stream(self.device).cuda_stream),
+                       "pcuda_comm_allreduce")
+        return t
+
+    def allreduce_p2p(self, count: int) -> torch.Tensor:
+        """Sum of every rank's `buf_in[:count]` into every rank's `buf_out[:count]` (one NVLink peer-memory kernel)."""
+        from . import _lib
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().pcuda_comm_allreduce_p2p(self._h, int(count), torch.cuda.current_stream(self.device).cuda_stream),
+                       "pcuda_comm_allreduce_p2p")
+        return self.buf_out[:count]
+
+    def check_status(self) -> None:
+        from . import _lib
+        _lib.check(_lib.lib().pcuda_comm_status(self._h), "pcuda_comm_status")
+
+    def destroy(self) -> None:
+        from . import _lib
+        if self._h is not None and self._h.value:
+            self.buf_in = self.buf_out = None
+            _lib.lib().pcuda_comm_destroy(self._h)
+            self._h = None
+
+
 class GradBucket:
     """One flat fp32 buffer aliasing the gradients of a parameter list; all-reduced in one call."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], flat: Optional[torch.Tensor] = None):
         self.params: List[torch.nn.Parameter] = [p for p in params]
         if not self.params:
             raise ValueError("empty parameter list")
         dev, dt = self.params[0].device, self.params[0].dtype
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
+        if flat is not None:        # e.g. the head of a communicator's peer-memory input buffer
+            if flat.numel() != self.numel or flat.dtype != dt or flat.device != dev or not flat.is_contiguous():
+                raise ValueError("flat buffer does not match the parameter list")
+            self.flat = flat
+            self.flat.zero_()
+        else:
+            self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
         self.views: List[torch.Tensor] = []
         off = 0
         for p in self.params:

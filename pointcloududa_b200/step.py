@@ -63,7 +63,13 @@ class StepConfig:
 class AdversarialStep:
     """Owns D4, its optimiser, static input buffers and (optionally) a captured CUDA graph."""
 
-    def __init__(self, cfg: StepConfig, device: torch.device, seed: int = 0, concurrent: bool = True):
+    def __init__(self, cfg: StepConfig, device: torch.device, seed: int = 0, concurrent: bool = True,
+                 exchange: str = "auto"):
+        """exchange: how D4's gradient bucket is summed over the ranks of an initialised process group --
+        "p2p": libpcuda's NVLink peer-memory kernel (pcuda_comm_allreduce_p2p; the bucket is packed straight into the
+        communicator's symmetric buffer), "nccl": ncclAllReduce through libpcuda's own communicator, "torch":
+        torch.distributed.all_reduce between two captured half-graphs (round-1 behaviour), "auto": p2p when peer memory
+        is available, else nccl.  p2p / nccl are captured inside the ONE graph of the step."""
         self.cfg = cfg
         self.device = device
         torch.manual_seed(seed)
@@ -73,8 +79,27 @@ class AdversarialStep:
         # libpcuda launch over all parameters (optim.FusedSGD: torch's arithmetic, momentum buffers in one flat tensor)
         self.opt = FusedSGD(list(self.d4.parameters()), lr=cfg.lr_dis, momentum=0.99, weight_decay=0.0005)
         self._pnames = [n for n, _ in self.d4.named_parameters()]
-        self.bucket = pdist.GradBucket(self.d4.parameters())
         self._world = 1
+        self.comm: Optional[pdist.PcudaComm] = None
+        self.exchange = "none"
+        self._sync_world()
+        if self._world > 1 and device.type == "cuda":
+            if exchange not in ("auto", "p2p", "nccl", "torch"):
+                raise ValueError(f"unknown exchange {exchange!r}")
+            if exchange != "torch":
+                numel = sum(p.numel() for p in self.d4.parameters())
+                self.comm = pdist.PcudaComm(device, p2p_floats=numel if exchange in ("auto", "p2p") else 0)
+                if exchange == "p2p" and not self.comm.p2p:
+                    raise RuntimeError("exchange='p2p' requested but peer memory is not available between the ranks")
+                self.exchange = "p2p" if self.comm.p2p else "nccl"
+            else:
+                self.exchange = "torch"
+        if self.exchange == "p2p":
+            numel = sum(p.numel() for p in self.d4.parameters())
+            self.bucket = pdist.GradBucket(self.d4.parameters(), flat=self.comm.buf_in[:numel])
+        else:
+            self.bucket = pdist.GradBucket(self.d4.parameters())
+        self._grad_final = self.bucket.flat          # where the summed gradient is read by SGD
         B, C, H, W, N = cfg.B, cfg.C, cfg.H, cfg.W, cfg.N
         f32 = dict(dtype=torch.float32, device=device)
         # all inputs of a step are views of ONE flat buffer (every view 256-byte aligned), so a caller can move a
@@ -218,9 +243,20 @@ class AdversarialStep:
         self._res = [loss_seg3.detach(), loss_vert_target.detach(), ent_mean.detach(), loss_adv_point.detach(),
                      loss_D_same4.detach(), loss_D_diff_4.detach(), acc_s, acc_t]
 
+    def _exchange(self) -> None:
+        """Sum of the (pre-divided) gradient bucket over the ranks; sets where SGD reads the result."""
+        if self.exchange == "p2p":
+            self._grad_final = self.comm.allreduce_p2p(self.bucket.numel)
+        elif self.exchange == "nccl":
+            self.comm.allreduce_(self.bucket.flat)
+            self._grad_final = self.bucket.flat
+        else:
+            self.bucket.allreduce_sum()
+            self._grad_final = self.bucket.flat
+
     def _post(self) -> None:
         # P5 (after the gradient all-reduce): SGD step of D4, scalars of the step into one small tensor
-        self.opt.step(self.bucket.flat)
+        self.opt.step(self._grad_final)
         self.result.copy_(torch.stack([r.reshape(()).float() for r in self._res]))
 
     def _sync_world(self) -> None:
@@ -230,7 +266,7 @@ class AdversarialStep:
     def _body(self) -> None:
         self._sync_world()
         self._pre()
-        self.bucket.allreduce_sum()      # the bucket was filled pre-divided by the world size
+        self._exchange()                 # the bucket was filled pre-divided by the world size
         self._post()
 
     def run(self) -> torch.Tensor:
@@ -239,8 +275,8 @@ class AdversarialStep:
         if self.graph is not None:
             self.graph.replay()
             if self.graph_post is not None:
-                # multi-GPU: the one NCCL call of the step sits between the two captured halves
-                self.bucket.allreduce_sum()
+                # exchange="torch": the one torch.distributed call of the step sits between the two captured halves
+                self._exchange()
                 self.graph_post.replay()
         else:
             self._body()
@@ -264,16 +300,16 @@ class AdversarialStep:
         torch.cuda.set_rng_state(rng, self.device)
 
     def capture(self, warmup: int = 3) -> None:
-        """Capture the step into CUDA graphs.  Single GPU: one graph.  With a process group the step
-        is captured as two graphs around the gradient all-reduce, which stays an ordinary NCCL call
-        on the same stream.
+        """Capture the step into ONE CUDA graph (single GPU, or the gradient exchange done by libpcuda's own
+        communicator: exchange = "p2p" / "nccl").  Only exchange="torch" is captured as two graphs around an
+        ordinary torch.distributed call.
 
         The warm-up steps that precede the capture (allocator pools, lazy library state) run for real on whatever
         the input buffers hold; the training state they touch -- D4's parameters, BatchNorm buffers and
         num_batches_tracked, the SGD momentum, the Dropout RNG -- is saved before and restored after, so capturing
         a model mid-training or right after load_state_dict() does not move it off the reference trajectory."""
         import torch.distributed as dist
-        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and self.exchange == "torch"
         self._sync_world()
         torch.cuda.synchronize(self.device)
         snap = self._snapshot_state()
