@@ -11,6 +11,8 @@
  *   pcuda_chamfer_fwd / _bwd      utils/loss.py:40-76  (batch_NN_loss, batch_pairwise_dist)
  *   pcuda_pointmlp_fwd / _bwd     networks/PointNetCls.py:38-44 (STN3d trunk), :84-88 (STNkd
  *                                 trunk), :143-163 (PointNetfeat trunk + global max-pool)
+ *   pcuda_pointmlp_fwd_xf/_bwd_xf the same with the 3x3 input transform fused in: networks/PointNetCls.py:140-142
+ *   pcuda_point_transform_fwd/_bwd the 64x64 feature transform, networks/PointNetCls.py:147-151
  *   pcuda_fcstack_fwd / _bwd      networks/PointNetCls.py:46-62 (STN3d head), :89-101 (STNkd head),
  *                                 :208-213 (classifier head): Linear [+Dropout] [+BatchNorm1d] [+ReLU]
  *   pcuda_bn_running_update       BatchNorm1d running statistics of several forward passes, in pass order
@@ -194,6 +196,36 @@ int pcuda_pointmlp_bwd_reuse(const float* x, int64_t sxb, int64_t sxc, int64_t s
                              float eps, int precision, const float* out, const int32_t* pool_arg,
                              const float* grad_out, float* grad_x, void* ws, const void* fwd_ws,
                              pcuda_stream_t stream);
+
+/* The same two calls with the per-cloud INPUT TRANSFORM of PointNetfeat fused into the first layer's operand load:
+ *   a_0[b, k, n] = sum_j x[b, j, n] * in_trans[b][j][k]        (in_trans: [B, C0, C0] contiguous, C0 <= 4)
+ * i.e. torch.bmm(x.transpose(2, 1), trans).transpose(2, 1) (networks/PointNetCls.py:140-142) without materialising
+ * the transformed cloud.  in_trans == NULL: identical to pcuda_pointmlp_fwd / _bwd_reuse.  The first layer must be a
+ * narrow one (cin <= 4, cout <= 128, not the pooled layer).  Backward: grad_x is the gradient w.r.t. the
+ * UNtransformed cloud x, grad_trans [B, C0, C0] the gradient w.r.t. in_trans (either may be NULL); fwd_ws may be NULL. */
+int pcuda_pointmlp_fwd_xf(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, const float* in_trans, int B, int N,
+                          int L, const pcuda_mlp_layer_t* layers /*host*/, int pool, int train,
+                          float momentum, float eps, int precision, float* out, int32_t* pool_arg,
+                          void* ws, pcuda_stream_t stream);
+int pcuda_pointmlp_bwd_xf(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, const float* in_trans, int B, int N,
+                          int L, const pcuda_mlp_layer_t* layers /*host*/, int pool, int train,
+                          float eps, int precision, const float* out, const int32_t* pool_arg,
+                          const float* grad_out, float* grad_x, float* grad_trans, void* ws, const void* fwd_ws,
+                          pcuda_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-cloud feature transform of PointNetfeat (networks/PointNetCls.py:147-151, the 64 x 64 matrix of STNkd):
+ *   out[b, k, n] = sum_j trans[b][j][k] * x[b, j, n]           x: [B, K, N] by element strides, K <= 64
+ * = torch.bmm(x.transpose(2, 1), trans).transpose(2, 1); out, grad_out, grad_x: [B, K, N] contiguous;
+ * trans, grad_trans: [B, K, K] contiguous.  Backward: grad_x = trans . grad_out per point, grad_trans[b] =
+ * x[b] grad_out[b]^T (contraction over the N points, deterministic).  grad_x / grad_trans may be NULL.
+ * ws: pcuda_point_transform_ws_bytes(B, K, N) bytes (backward with grad_trans only). */
+size_t pcuda_point_transform_ws_bytes(int B, int K, int N);
+int pcuda_point_transform_fwd(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, const float* trans, int B, int K,
+                              int N, float* out, pcuda_stream_t stream);
+int pcuda_point_transform_bwd(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, const float* trans,
+                              const float* grad_out, int B, int K, int N, float* grad_x, float* grad_trans, void* ws,
+                              pcuda_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * FC head: a stack of L layers on [B, C] features (the rows are the clouds of the batch)

@@ -83,6 +83,17 @@ SIGNATURES = {
     "pcuda_pointmlp_bwd_reuse": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                          POINTER(MlpLayer), c_int, c_int, c_float, c_int, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcuda_pointmlp_fwd_xf": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
+                                      POINTER(MlpLayer), c_int, c_int, c_float, c_float, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcuda_pointmlp_bwd_xf": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
+                                      POINTER(MlpLayer), c_int, c_int, c_float, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pcuda_point_transform_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pcuda_point_transform_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_void_p,
+                                          c_void_p]),
+    "pcuda_point_transform_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcuda_fcstack_fwd": (c_int, [c_void_p, c_int, c_int, POINTER(FcLayer), c_int, c_float, c_float, c_int,
                                   c_void_p]),
     "pcuda_fcstack_ws_bytes": (c_size_t, [c_int, c_int, POINTER(FcLayer), c_int]),

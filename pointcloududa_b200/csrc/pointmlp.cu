@@ -195,6 +195,13 @@ __device__ __forceinline__ void load_point(const ActSrc& s, int64_t m, float (&x
       xv[k] = k < s.C ? bn_act(s.y[m * s.C + k], s.mean[k], s.invstd[k], s.gamma[k], s.beta[k], s.relu) : 0.f;
   } else {
     const int64_t b = m / s.N, n = m - b * s.N;
+    if (s.trans != nullptr) {          // C <= 4 (validated by the host): transformed on load
+      float t[4];
+      load_raw_point(s, b, n, t);
+#pragma unroll
+      for (int k = 0; k < KN; ++k) xv[k] = k < 4 ? t[k < 4 ? k : 0] : 0.f;
+      return;
+    }
     const float* px = s.x + b * s.sxb + n * s.sxn;
 #pragma unroll
     for (int k = 0; k < KN; ++k) xv[k] = k < s.C ? __ldg(px + k * s.sxc) : 0.f;
@@ -346,6 +353,62 @@ dgrad_input_narrow_kernel(DySrc dys, const float* __restrict__ W, int K, int N, 
 #pragma unroll
       for (int k = 0; k < KN; ++k)
         if (k < K) grad_x[(b * K + k) * N + n] = g[k];
+    }
+  }
+}
+
+// Backward of the input transform fused into the first layer's operand load (a = T^T x per point): with
+// g = dL/da [B, C, N] (written by the first layer's dgrad into the workspace),
+//   grad_x[b, j, n] = sum_k T[b][j][k] g[b, k, n]          (torch.bmm backward w.r.t. the cloud)
+//   grad_T[b][j][k] = sum_n x[b, j, n] g[b, k, n]          (w.r.t. the transform: into STN3d's head)
+// One CTA per cloud, fixed-order reduction: deterministic.  C <= 4.
+__global__ void __launch_bounds__(256)
+input_transform_bwd_kernel(const float* __restrict__ x, int64_t sxb, int64_t sxc, int64_t sxn, const float* __restrict__ T,
+                           const float* __restrict__ g, int C, int N, float* __restrict__ grad_x, float* __restrict__ grad_T) {
+  __shared__ double red[8][16];
+  const int b = blockIdx.x;
+  const float* Tb = T + static_cast<int64_t>(b) * C * C;
+  float t[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[j][k] = (j < C && k < C) ? Tb[j * C + k] : 0.f;
+  float acc[4][4] = {};
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float gv[4], xv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gv[k] = k < C ? g[(static_cast<int64_t>(b) * C + k) * N + n] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xv[j] = j < C ? __ldg(x + b * sxb + j * sxc + n * sxn) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (grad_x != nullptr && j < C) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v = fmaf(t[j][k], gv[k], v);
+        grad_x[(static_cast<int64_t>(b) * C + j) * N + n] = v;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[j][k] = fmaf(xv[j], gv[k], acc[j][k]);
+    }
+  }
+  if (grad_T == nullptr) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double v = warp_sum(static_cast<double>(acc[j][k]));
+      if (lane == 0) red[warp][j * 4 + k] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int j = threadIdx.x >> 2, k = threadIdx.x & 3;
+    if (j < C && k < C) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+      grad_T[static_cast<int64_t>(b) * C * C + j * C + k] = static_cast<float>(v);
     }
   }
 }
@@ -1276,6 +1339,7 @@ struct BwdWs {
   float *coef, *gsel, *gyh, *Ghat, *Q, *abar, *u;
   double *colsum, *G, *abar_d;
   float* dzbuf[2];
+  float* dxp;           // [B, C0, N] gradient w.r.t. the transformed input cloud (fused input transform, C0 <= 4)
   uint8_t* apack[17];   // apack[l + 1] = packed activation a_l; index 0 = the raw network input
   uint8_t* dypack; uint8_t* wtpack; uint8_t* qpack;
   size_t bytes;
@@ -1306,6 +1370,7 @@ BwdWs carve_bwd(const Shape& s, const pcuda_mlp_layer_t* layers, void* base) {
   }
   w.dzbuf[0] = cv.take<float>(static_cast<size_t>(s.M) * s.maxC);
   w.dzbuf[1] = cv.take<float>(static_cast<size_t>(s.M) * s.maxC);
+  w.dxp = layers[0].cin <= 4 ? cv.take<float>(static_cast<size_t>(s.M) * layers[0].cin) : nullptr;
   size_t dy_max = 0, wt_max = 0;
   for (int l = -1; l <= s.L - 2; ++l) {
     const int C = l < 0 ? layers[0].cin : layers[l].cout;
@@ -1379,6 +1444,24 @@ static Aux* aux_for(cudaStream_t st) {
   return &g_aux.emplace(key, a).first->second;
 }
 
+// Joins the auxiliary stream back into the caller's stream on EVERY exit path once a fork has been issued: an early
+// error return would otherwise leave aux-stream kernels running on a workspace the caller is about to free (eager
+// mode), or an unjoined forked stream inside a capture (which invalidates the capture with an unrelated error).
+struct AuxJoin {
+  Aux* ax;
+  cudaStream_t st;
+  bool pending = false;
+  AuxJoin(Aux* a, cudaStream_t s) : ax(a), st(s) {}
+  void join() {
+    if (ax != nullptr && pending) {
+      cudaEventRecord(ax->done, ax->s);
+      cudaStreamWaitEvent(st, ax->done, 0);
+    }
+    pending = false;
+  }
+  ~AuxJoin() { join(); }
+};
+
 int validate(const char* who, int B, int N, int L, const pcuda_mlp_layer_t* layers, int pool) {
   PCUDA_REQUIRE(layers != nullptr, PCUDA_E_NULL, "%s: layers is NULL", who);
   PCUDA_REQUIRE(B >= 1 && N >= 1 && L >= 1 && L <= 16, PCUDA_E_SHAPE, "%s: bad shape B=%d N=%d L=%d", who, B, N, L);
@@ -1397,11 +1480,19 @@ int validate(const char* who, int B, int N, int L, const pcuda_mlp_layer_t* laye
   return 0;
 }
 
-ActSrc input_src(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int N, int C0) {
-  return ActSrc{nullptr, nullptr, nullptr, nullptr, nullptr, 0, x, sxb, sxc, sxn, N, C0};
+ActSrc input_src(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int N, int C0, const float* trans = nullptr) {
+  return ActSrc{nullptr, nullptr, nullptr, nullptr, nullptr, 0, x, sxb, sxc, sxn, N, C0, trans};
+}
+// the input transform is applied inside the first layer's kernels: only where those are the narrow ones
+int validate_trans(const char* who, const float* trans, int L, const pcuda_mlp_layer_t* layers, int pool) {
+  if (trans == nullptr) return 0;
+  PCUDA_REQUIRE(layers[0].cin <= 4, PCUDA_E_UNSUPPORTED, "%s: the fused input transform needs cin <= 4 (got %d); use pcuda_point_transform_fwd", who, layers[0].cin);
+  PCUDA_REQUIRE(narrow_ok(layers[0].cin, layers[0].cout) && layers[0].cout <= 128 && !(pool && L == 1) && layers[0].y != nullptr, PCUDA_E_UNSUPPORTED,
+                "%s: the fused input transform needs a first layer of <= 128 channels (power of two x 4) that is not the pooled one", who);
+  return 0;
 }
 ActSrc layer_src(const pcuda_mlp_layer_t& y, int N) {
-  return ActSrc{y.y, y.save_mean, y.save_invstd, y.gamma, y.beta, y.relu, nullptr, 0, 0, 0, N, y.cout};
+  return ActSrc{y.y, y.save_mean, y.save_invstd, y.gamma, y.beta, y.relu, nullptr, 0, 0, 0, N, y.cout, nullptr};
 }
 
 // Which pieces run on the tensor cores.  TUNE_MLP_TC_MASK bits switch single pieces back to the
@@ -1424,11 +1515,12 @@ extern "C" size_t pcuda_pointmlp_ws_bytes(int B, int N, int L, const pcuda_mlp_l
   return backward ? carve_bwd(s, layers, nullptr).bytes : carve_fwd(s, layers, nullptr).bytes;
 }
 
-extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
-                                  const pcuda_mlp_layer_t* layers, int pool, int train, float momentum,
-                                  float eps, int precision, float* out, int32_t* pool_arg, void* ws,
-                                  pcuda_stream_t stream) {
+static int pointmlp_fwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
+                             const pcuda_mlp_layer_t* layers, int pool, int train, float momentum,
+                             float eps, int precision, float* out, int32_t* pool_arg, void* ws,
+                             const float* in_trans, pcuda_stream_t stream) {
   if (int rc = validate("pointmlp_fwd", B, N, L, layers, pool)) return rc;
+  if (int rc = validate_trans("pointmlp_fwd", in_trans, L, layers, pool)) return rc;
   PCUDA_REQUIRE(x && out && ws, PCUDA_E_NULL, "pointmlp_fwd: NULL x/out/ws");
   PCUDA_REQUIRE(!pool || pool_arg, PCUDA_E_NULL, "pointmlp_fwd: pool needs pool_arg");
   PCUDA_REQUIRE(precision == PCUDA_MLP_FP32 || precision == PCUDA_MLP_BF16, PCUDA_E_UNSUPPORTED, "pointmlp_fwd: precision %d", precision);
@@ -1453,10 +1545,11 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
   bool any_pack = false;
   for (int l = 0; l < L; ++l) any_pack = any_pack || layer_tc(l);
   Aux* ax = (any_pack && !tuning(TUNE_MLP_NO_FORK)) ? aux_for(st) : nullptr;
+  AuxJoin joiner(ax, st);
   bool packs_pending = false;
   if (any_pack) {
     cudaStream_t sp = ax ? ax->s : st;
-    if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sp, ax->fork, 0); }
+    if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sp, ax->fork, 0); joiner.pending = true; }
     for (int l = 0; l < L; ++l)
       if (layer_tc(l))
         if (int rc = tc::pack_w(layers[l].weight, layers[l].cout, layers[l].cin, false, w.wpack[l], sp,
@@ -1469,14 +1562,14 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
   if (!layer_tc(0) && !layer_narrow(0)) {
     // pivot of layer 0 (no BN to finalise yet; the narrow-layer kernel publishes its own pivot)
     bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, 0, 1.0, eps, momentum, train, nullptr, nullptr, nullptr, nullptr,
-                                                 input_src(x, sxb, sxc, sxn, N, layers[0].cin), layers[0].weight, layers[0].bias,
+                                                 input_src(x, sxb, sxc, sxn, N, layers[0].cin, in_trans), layers[0].weight, layers[0].bias,
                                                  layers[0].cout, piv_l);
     launches += 1;
   }
   BnRaw raw_prev{};     // raw sums of the previous layer when its BatchNorm is finalised by this layer's operand packer
   for (int l = 0; l < L; ++l) {
     const pcuda_mlp_layer_t& y = layers[l];
-    const ActSrc src = l == 0 ? input_src(x, sxb, sxc, sxn, N, y.cin) : layer_src(layers[l - 1], N);
+    const ActSrc src = l == 0 ? input_src(x, sxb, sxc, sxn, N, y.cin, in_trans) : layer_src(layers[l - 1], N);
     const bool is_pool = pool && l == L - 1;
     const float* pivot_used = piv_l;
     if (layer_tc(l)) {
@@ -1484,7 +1577,7 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
       // Statistics are accumulated bias-free, i.e. centred on pivot = bias.
       if (int rc = tc::pack_act(src, tl, w.apack[l], st, raw_prev.stats ? &raw_prev : nullptr)) return rc;
       raw_prev = BnRaw{};
-      if (packs_pending) { cudaStreamWaitEvent(st, ax->done, 0); packs_pending = false; }
+      if (packs_pending) { cudaStreamWaitEvent(st, ax->done, 0); packs_pending = false; joiner.pending = false; }
       if (int rc = tc::fwd_layer(tl, w.apack[l], w.wpack[l], y, is_pool, st_l, w.keys, st)) return rc;
       pivot_used = y.bias ? y.bias : w.zeros;
     } else if (layer_narrow(l)) {
@@ -1532,12 +1625,29 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
   return check_launch("pointmlp_fwd");
 }
 
+extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
+                                  const pcuda_mlp_layer_t* layers, int pool, int train, float momentum,
+                                  float eps, int precision, float* out, int32_t* pool_arg, void* ws,
+                                  pcuda_stream_t stream) {
+  return pointmlp_fwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, momentum, eps, precision, out, pool_arg, ws, nullptr, stream);
+}
+
+extern "C" int pcuda_pointmlp_fwd_xf(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, const float* in_trans, int B, int N, int L,
+                                     const pcuda_mlp_layer_t* layers, int pool, int train, float momentum,
+                                     float eps, int precision, float* out, int32_t* pool_arg, void* ws,
+                                     pcuda_stream_t stream) {
+  return pointmlp_fwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, momentum, eps, precision, out, pool_arg, ws, in_trans, stream);
+}
+
 static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
                              const pcuda_mlp_layer_t* layers, int pool, int train, float eps,
                              int precision, const float* out, const int32_t* pool_arg,
-                             const float* grad_out, float* grad_x, void* ws, const void* fwd_ws, pcuda_stream_t stream) {
+                             const float* grad_out, float* grad_x, void* ws, const void* fwd_ws,
+                             const float* in_trans, float* grad_trans, pcuda_stream_t stream) {
   (void)eps;
   if (int rc = validate("pointmlp_bwd", B, N, L, layers, pool)) return rc;
+  if (int rc = validate_trans("pointmlp_bwd", in_trans, L, layers, pool)) return rc;
+  PCUDA_REQUIRE(grad_trans == nullptr || in_trans != nullptr, PCUDA_E_NULL, "pointmlp_bwd: grad_trans without in_trans");
   PCUDA_REQUIRE(x && grad_out && ws, PCUDA_E_NULL, "pointmlp_bwd: NULL x/grad_out/ws");
   PCUDA_REQUIRE(!pool || (pool_arg && out), PCUDA_E_NULL, "pointmlp_bwd: pool needs out and pool_arg");
   PCUDA_REQUIRE(precision == PCUDA_MLP_FP32 || precision == PCUDA_MLP_BF16, PCUDA_E_UNSUPPORTED, "pointmlp_bwd: precision %d", precision);
@@ -1558,11 +1668,15 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
   for (int l = 0; l < L; ++l) off[l + 1] = off[l] + layers[l].cout;
   const int S32 = splits_for(s.M);                       // FP32 contraction kernels
   const int64_t chunk32 = (s.M + S32 - 1) / S32;
-  auto src_of = [&](int l) { return l < 0 ? input_src(x, sxb, sxc, sxn, N, layers[0].cin) : layer_src(layers[l], N); };
+  auto src_of = [&](int l) { return l < 0 ? input_src(x, sxb, sxc, sxn, N, layers[0].cin, in_trans) : layer_src(layers[l], N); };
+  // with an input transform the first layer's dgrad lands in the workspace (gradient w.r.t. the TRANSFORMED cloud);
+  // input_transform_bwd_kernel turns it into grad_x and grad_trans
+  float* const gx_target = in_trans != nullptr ? w.dxp : grad_x;
+  const bool want_gx = grad_x != nullptr || (in_trans != nullptr && grad_trans != nullptr);
   auto dgrad_out = [&](int lp, float* dzp) {  // epilogue target: previous layer lp (or input if lp < 0)
     DgradOut o{};
     if (lp < 0) {
-      o.grad_x = grad_x;
+      o.grad_x = gx_target;
       o.Cp = layers[0].cin;
     } else {
       const pcuda_mlp_layer_t& p = layers[lp];
@@ -1594,7 +1708,8 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
   // auxiliary stream of this call (see Aux above); tuning key 6 keeps everything on the caller's stream (A/B)
   Aux* ax = tuning(TUNE_MLP_NO_FORK) ? nullptr : aux_for(st);
   cudaStream_t sa = ax ? ax->s : st;
-  bool aux_used = false;   // something was issued on the auxiliary stream: join before returning
+  AuxJoin joiner(ax, st);  // joins on every exit path once joiner.pending is set
+  bool& aux_used = joiner.pending;   // something was issued on the auxiliary stream: join before returning
   bool wgrad_pending = false;   // a weight-gradient chain of the previous layer may still be running there
   int cur = 0;      // dzbuf[cur] holds dz of layer `top`
   int top = L - 1;  // highest layer whose dz is dense and stored
@@ -1708,7 +1823,7 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
                                                         want_w ? y.grad_bias : nullptr);
     launches += 1;
     const DySrc dys{dzbuf[cur], y.y, y.save_mean, y.save_invstd, y.gamma, al, ka, C};
-    const bool need_dgrad = l > 0 || grad_x != nullptr;
+    const bool need_dgrad = l > 0 || want_gx;
     const bool wgrad_tc = want_w && tc_on(precision, TC_WGRAD) && w.dypack && apack[l] && tc::pt_supports(C, Kp, false);
     const bool dgrad_side = l - 1 >= 0 && (Kp % 64) == 0 && apack[l] != nullptr;
     const bool dgrad_tc = need_dgrad && tc_on(precision, TC_DGRAD) && w.dypack && w.wtpack && (Kp % 8) == 0 &&
@@ -1761,10 +1876,11 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       cur ^= 1;
     }
   }
-  if (aux_used) {   // join: the pooled weight gradient / the last weight-gradient chain
-    cudaEventRecord(ax->done, sa);
-    cudaStreamWaitEvent(st, ax->done, 0);
+  if (in_trans != nullptr && want_gx) {
+    input_transform_bwd_kernel<<<B, 256, 0, st>>>(x, sxb, sxc, sxn, in_trans, w.dxp, layers[0].cin, N, grad_x, grad_trans);
+    launches += 1;
   }
+  joiner.join();    // the pooled weight gradient / the last weight-gradient chain
   count_launch(launches);
   return check_launch("pointmlp_bwd");
 }
@@ -1774,7 +1890,7 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
                                   int precision, const float* out, const int32_t* pool_arg,
                                   const float* grad_out, float* grad_x, void* ws, pcuda_stream_t stream) {
   return pointmlp_bwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, eps, precision, out, pool_arg, grad_out, grad_x, ws,
-                           nullptr, stream);
+                           nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int pcuda_pointmlp_bwd_reuse(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
@@ -1783,5 +1899,14 @@ extern "C" int pcuda_pointmlp_bwd_reuse(const float* x, int64_t sxb, int64_t sxc
                                         const float* grad_out, float* grad_x, void* ws, const void* fwd_ws,
                                         pcuda_stream_t stream) {
   return pointmlp_bwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, eps, precision, out, pool_arg, grad_out, grad_x, ws,
-                           fwd_ws, stream);
+                           fwd_ws, nullptr, nullptr, stream);
+}
+
+extern "C" int pcuda_pointmlp_bwd_xf(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, const float* in_trans, int B, int N, int L,
+                                     const pcuda_mlp_layer_t* layers, int pool, int train, float eps,
+                                     int precision, const float* out, const int32_t* pool_arg,
+                                     const float* grad_out, float* grad_x, float* grad_trans, void* ws, const void* fwd_ws,
+                                     pcuda_stream_t stream) {
+  return pointmlp_bwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, eps, precision, out, pool_arg, grad_out, grad_x, ws,
+                           fwd_ws, in_trans, grad_trans, stream);
 }

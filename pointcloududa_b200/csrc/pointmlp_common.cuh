@@ -17,7 +17,35 @@ struct ActSrc {
   int64_t sxb, sxc, sxn;
   int N;
   int C;
+  // raw input only: per-cloud input transform T[b] (row-major [C, C], C <= 4) applied on load,
+  // a[m, k] = sum_j x[b, j, n] T[b][j][k]  — torch.bmm(x.transpose(2, 1), trans) of PointNetfeat.forward
+  // (networks/PointNetCls.py:140-142) without materialising the transformed cloud.  nullptr: identity.
+  const float* trans;
 };
+
+// the C <= 4 raw channels of point (b, n), transformed when the source carries an input transform
+__device__ __forceinline__ void load_raw_point(const ActSrc& s, int64_t b, int64_t n, float (&v)[4]) {
+  const float* px = s.x + b * s.sxb + n * s.sxn;
+  float r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r[j] = j < s.C ? __ldg(px + j * s.sxc) : 0.f;
+  if (s.trans == nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = r[j];
+    return;
+  }
+  const float* T = s.trans + b * s.C * s.C;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float acc = 0.f;
+    if (k < s.C) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < s.C) acc = fmaf(r[j], __ldg(T + j * s.C + k), acc);     // j ascending: the order of a K = 3 dot product
+    }
+    v[k] = acc;
+  }
+}
 
 // Finalise-on-read: the raw BatchNorm sums of the producing layer, handed to the kernel that consumes its
 // output (the operand packer of the next layer, the pooled-output kernel) so that no one-block
@@ -83,6 +111,11 @@ __device__ __forceinline__ float4 load_act4(const ActSrc& s, int64_t m, int k) {
     }
   } else {
     const int64_t b = m / s.N, n = m - b * s.N;
+    if (s.trans != nullptr) {        // C <= 4, so k == 0
+      float t[4];
+      load_raw_point(s, b, n, t);
+      return make_float4(t[0], t[1], t[2], t[3]);
+    }
     const float* px = s.x + b * s.sxb + n * s.sxn;
     float* pv = &v.x;
 #pragma unroll
@@ -95,6 +128,11 @@ __device__ __forceinline__ float4 load_act4(const ActSrc& s, int64_t m, int k) {
 __device__ __forceinline__ float load_act1(const ActSrc& s, int64_t m, int k) {
   if (s.y != nullptr) return bn_act(s.y[m * s.C + k], s.mean[k], s.invstd[k], s.gamma[k], s.beta[k], s.relu);
   const int64_t b = m / s.N, n = m - b * s.N;
+  if (s.trans != nullptr) {
+    float t[4];
+    load_raw_point(s, b, n, t);
+    return k == 0 ? t[0] : (k == 1 ? t[1] : (k == 2 ? t[2] : t[3]));
+  }
   return __ldg(s.x + b * s.sxb + n * s.sxn + k * s.sxc);
 }
 

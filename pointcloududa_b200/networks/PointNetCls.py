@@ -87,10 +87,11 @@ class _SharedMLP(torch.autograd.Function):
     """y = [max_n] relu?(bn(conv1x1(...relu(bn(conv1x1(x)))))) on libpcuda."""
 
     @staticmethod
-    def forward(ctx, x, pool: bool, train: bool, precision: int, relus: Tuple[bool, ...],
+    def forward(ctx, x, in_trans, pool: bool, train: bool, precision: int, relus: Tuple[bool, ...],
                 momenta: Tuple[float, ...], eps: float, buffers: Tuple[Optional[torch.Tensor], ...],
                 stats_out: Optional[list], *params):
         # params: (weight, bias, gamma, beta) per layer; buffers: (running_mean, running_var) per layer
+        # in_trans: [B, C0, C0] per-cloud input transform applied inside the first layer's operand load, or None
         if not x.is_cuda:
             raise PcudaError("PointNetCls runs on CUDA (sm_100a) only; there is no CPU fallback")
         if x.dtype != torch.float32 or x.dim() != 3:
@@ -99,6 +100,11 @@ class _SharedMLP(torch.autograd.Function):
         B, C0, N = x.shape
         dev = x.device
         M = B * N
+        tr = None
+        if in_trans is not None:
+            if in_trans.shape != (B, C0, C0) or in_trans.dtype != torch.float32 or in_trans.device != dev:
+                raise PcudaError(f"input transform must be a float32 [B, {C0}, {C0}] tensor on the input's device")
+            tr = in_trans.detach().contiguous()
         lay = (MlpLayer * L)()
         keep = []  # tensors referenced by raw pointers
         ys, means, invstds = [], [], []
@@ -127,15 +133,21 @@ class _SharedMLP(torch.autograd.Function):
         Lb = _lib.lib()
         with torch.cuda.device(dev):
             ws = torch.empty(max(Lb.pcuda_pointmlp_ws_bytes(B, N, L, lay, int(pool), 0), 16), dtype=torch.uint8, device=dev)
-            check(Lb.pcuda_pointmlp_fwd(_ptr(x), x.stride(0), x.stride(1), x.stride(2), B, N, L, lay, int(pool),
-                                        int(train), float(momenta[0]), float(eps), precision, _ptr(out), _ptr(arg),
-                                        _ptr(ws), torch.cuda.current_stream().cuda_stream), "pcuda_pointmlp_fwd")
+            check(Lb.pcuda_pointmlp_fwd_xf(_ptr(x), x.stride(0), x.stride(1), x.stride(2), _ptr(tr), B, N, L, lay, int(pool),
+                                           int(train), float(momenta[0]), float(eps), precision, _ptr(out), _ptr(arg),
+                                           _ptr(ws), torch.cuda.current_stream().cuda_stream), "pcuda_pointmlp_fwd")
         if stats_out is not None:
             stats_out.extend(zip(means, invstds))
         ctx.cfg = (pool, train, precision, relus, eps, B, N, L)
-        ctx.save_for_backward(x)
+        # the pooled output is an OUTPUT of this node: it goes through save_for_backward (a plain attribute would form
+        # the output -> grad_fn -> ctx -> output cycle and keep every activation below alive until the cyclic GC runs)
+        if pool:
+            ctx.save_for_backward(x, out)
+        else:
+            ctx.save_for_backward(x)
         ctx.keep = keep
-        ctx.saved = (ys, means, invstds, out if pool else None, arg)
+        ctx.trans = tr
+        ctx.saved = (ys, means, invstds, arg)
         ctx.fwd_ws = ws        # kept alive: the backward pass reads the packed bf16 operands in place
         ctx.param_shapes = [None if p is None else p.shape for p in params]
         return out
@@ -143,12 +155,19 @@ class _SharedMLP(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         pool, train, precision, relus, eps, B, N, L = ctx.cfg
-        (x,) = ctx.saved_tensors
+        if pool:
+            x, out = ctx.saved_tensors
+        else:
+            (x,), out = ctx.saved_tensors, None
         keep = ctx.keep
-        ys, means, invstds, out, arg = ctx.saved
+        if keep is None:
+            raise PcudaError("the shared-MLP node was already back-propagated (its buffers are released after backward)")
+        ys, means, invstds, arg = ctx.saved
+        tr = ctx.trans
         dev = x.device
         need_x = ctx.needs_input_grad[0]
-        needs_p = ctx.needs_input_grad[9:]
+        need_t = tr is not None and ctx.needs_input_grad[1]
+        needs_p = ctx.needs_input_grad[10:]
         lay = (MlpLayer * L)()
         grads: List[Optional[torch.Tensor]] = []
         for l in range(L):
@@ -169,23 +188,39 @@ class _SharedMLP(torch.autograd.Function):
             else:
                 grads += [None, None, None, None]
         gx = torch.empty((B, x.shape[1], N), dtype=torch.float32, device=dev) if need_x else None
+        gt = torch.empty_like(tr) if need_t else None
         go = grad_out.contiguous()
         Lb = _lib.lib()
         with torch.cuda.device(dev):
             ws = torch.empty(max(Lb.pcuda_pointmlp_ws_bytes(B, N, L, lay, int(pool), 1), 16), dtype=torch.uint8, device=dev)
-            check(Lb.pcuda_pointmlp_bwd_reuse(_ptr(x), x.stride(0), x.stride(1), x.stride(2), B, N, L, lay, int(pool),
-                                              int(train), float(eps), precision, _ptr(out), _ptr(arg), _ptr(go), _ptr(gx),
-                                              _ptr(ws), _ptr(ctx.fwd_ws), torch.cuda.current_stream().cuda_stream),
+            check(Lb.pcuda_pointmlp_bwd_xf(_ptr(x), x.stride(0), x.stride(1), x.stride(2), _ptr(tr), B, N, L, lay, int(pool),
+                                           int(train), float(eps), precision, _ptr(out), _ptr(arg), _ptr(go), _ptr(gx), _ptr(gt),
+                                           _ptr(ws), _ptr(ctx.fwd_ws), torch.cuda.current_stream().cuda_stream),
                   "pcuda_pointmlp_bwd")
         for i, need in enumerate(needs_p):
             if not need:
                 grads[i] = None
-        return (gx, None, None, None, None, None, None, None, None, *grads)
+        # release everything this node held (per-layer activations, the forward workspace with the bf16 slabs, weight
+        # aliases): at cfg-5 sizes that is hundreds of MB per D4 pass
+        ctx.keep = ctx.saved = ctx.fwd_ws = ctx.trans = None
+        return (gx, gt, None, None, None, None, None, None, None, None, *grads)
+
+
+def can_fuse_input_transform(convs: Sequence[nn.Conv1d], pool: bool) -> bool:
+    """Whether shared_mlp(..., in_trans=T) can apply the per-cloud input transform inside its first layer (include/pcuda.h,
+    pcuda_pointmlp_fwd_xf): <= 4 input channels into a narrow first layer that is not the pooled one."""
+    c0 = convs[0]
+    tpp = c0.out_channels // 4
+    return (c0.in_channels <= 4 and c0.out_channels % 4 == 0 and c0.out_channels <= 128 and tpp >= 1
+            and (tpp & (tpp - 1)) == 0 and not (pool and len(convs) == 1))
 
 
 def shared_mlp(x: torch.Tensor, convs: Sequence[nn.Conv1d], bns: Sequence[nn.BatchNorm1d],
-               relus: Sequence[bool], pool: bool, precision: str = DEFAULT_PRECISION) -> torch.Tensor:
-    """Run Conv1d(k=1)+BatchNorm1d(+ReLU) layers [+ max over points] as one fused op."""
+               relus: Sequence[bool], pool: bool, precision: str = DEFAULT_PRECISION,
+               in_trans: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Run Conv1d(k=1)+BatchNorm1d(+ReLU) layers [+ max over points] as one fused op.  in_trans [B, C0, C0]: the
+    per-cloud transform torch.bmm(x.transpose(2, 1), in_trans).transpose(2, 1) applied to the input first
+    (reference :140-142), inside the first layer's operand load."""
     params, buffers, momenta = [], [], []
     eps = bns[0].eps
     train = bns[0].training or not bns[0].track_running_stats
@@ -204,7 +239,7 @@ def shared_mlp(x: torch.Tensor, convs: Sequence[nn.Conv1d], bns: Sequence[nn.Bat
     stats_out = [] if sink is not None else None
     if sink is not None:
         buffers = [None] * len(buffers)          # the kernels skip the running-stat update
-    out = _SharedMLP.apply(x, bool(pool), bool(train), PRECISIONS[precision], tuple(bool(r) for r in relus),
+    out = _SharedMLP.apply(x, in_trans, bool(pool), bool(train), PRECISIONS[precision], tuple(bool(r) for r in relus),
                            tuple(momenta), float(eps), tuple(buffers), stats_out, *params)
     if sink is not None:
         count = x.shape[0] * x.shape[2]
@@ -259,15 +294,21 @@ class _FcStack(torch.autograd.Function):
         if stats_out is not None:
             stats_out.extend((sv[0], sv[1]) for sv in saved)
         ctx.cfg = (train, relus, bn_flags, B, L)
-        ctx.save_for_backward(xc)
+        out = saved[-1][3]
+        saved[-1] = saved[-1][:3] + (None,)         # the output travels through save_for_backward (no ctx <-> output cycle)
+        ctx.save_for_backward(xc, out)
         ctx.keep, ctx.saved = keep, saved
-        return saved[-1][3]
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
         train, relus, bn_flags, B, L = ctx.cfg
-        (xc,) = ctx.saved_tensors
+        xc, out = ctx.saved_tensors
         keep, saved = ctx.keep, ctx.saved
+        if keep is None:
+            raise PcudaError("the FC-head node was already back-propagated (its buffers are released after backward)")
+        saved = list(saved)
+        saved[-1] = saved[-1][:3] + (out,)
         dev = xc.device
         need_x = ctx.needs_input_grad[0]
         needs_p = ctx.needs_input_grad[10:]
@@ -301,6 +342,7 @@ class _FcStack(torch.autograd.Function):
         for i, need in enumerate(needs_p):
             if not need:
                 grads[i] = None
+        ctx.keep = ctx.saved = None
         return (gx, None, None, None, None, None, None, None, None, None, *grads)
 
 
@@ -336,6 +378,46 @@ def fc_stack(x: torch.Tensor, linears: Sequence[nn.Linear], bns: Sequence[Option
         if counters:
             torch._foreach_add_(counters, 1)
     return out
+
+
+class _PointTransform(torch.autograd.Function):
+    """out[b, k, n] = sum_j trans[b][j][k] x[b, j, n] = bmm(x^T, trans)^T on libpcuda (csrc/transform.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, trans):
+        if not x.is_cuda:
+            raise PcudaError("PointNetCls runs on CUDA (sm_100a) only; there is no CPU fallback")
+        B, K, N = x.shape
+        if x.dtype != torch.float32 or trans.dtype != torch.float32 or trans.shape != (B, K, K):
+            raise PcudaError(f"point_transform expects float32 x [B, K, N] and trans [B, K, K], got {tuple(x.shape)} / {tuple(trans.shape)}")
+        tr = trans.contiguous()
+        out = torch.empty((B, K, N), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(_lib.lib().pcuda_point_transform_fwd(_ptr(x), x.stride(0), x.stride(1), x.stride(2), _ptr(tr), B, K, N, _ptr(out),
+                                                       torch.cuda.current_stream().cuda_stream), "pcuda_point_transform_fwd")
+        ctx.save_for_backward(x, tr)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, tr = ctx.saved_tensors
+        B, K, N = x.shape
+        go = grad_out.contiguous()
+        gx = torch.empty((B, K, N), dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        gt = torch.empty_like(tr) if ctx.needs_input_grad[1] else None
+        Lb = _lib.lib()
+        with torch.cuda.device(x.device):
+            ws = torch.empty(max(Lb.pcuda_point_transform_ws_bytes(B, K, N), 16), dtype=torch.uint8, device=x.device)
+            check(Lb.pcuda_point_transform_bwd(_ptr(x), x.stride(0), x.stride(1), x.stride(2), _ptr(tr), _ptr(go), B, K, N,
+                                               _ptr(gx), _ptr(gt), _ptr(ws), torch.cuda.current_stream().cuda_stream),
+                  "pcuda_point_transform_bwd")
+        return gx, gt
+
+
+def point_transform(x: torch.Tensor, trans: torch.Tensor) -> torch.Tensor:
+    """torch.bmm(x.transpose(2, 1), trans).transpose(2, 1) for x [B, K, N], trans [B, K, K] (K <= 64), as one libpcuda
+    launch (reference :140-142 / :147-151); the result is a contiguous [B, K, N] tensor."""
+    return _PointTransform.apply(x, trans)
 
 
 def _check_batch(batchsize: int) -> None:
@@ -462,28 +544,31 @@ class PointNetfeat(nn.Module):
         n_pts = x.size()[2]
         _check_batch(x.size()[0])
         trans = None
+        (pc, pb, pr), (qc, qb, qr) = self._stacks()
+        two_stacks = self.feature_transform or not self.global_feat
+        in_trans = None
         if self._sample_transform:
             trans = self.stn(x)
-            x = x.transpose(2, 1)
-            x = torch.bmm(x, trans)                                                # :140-142
-            x = x.transpose(2, 1)
-        (pc, pb, pr), (qc, qb, qr) = self._stacks()
+            # x' = bmm(x^T, trans)^T (:140-142): applied inside the first layer's operand load when that layer is a
+            # narrow one (always, for the 3-channel clouds of the reference), else as its own libpcuda launch
+            if can_fuse_input_transform(pc, pool=not two_stacks and len(pc + qc) == 1):
+                in_trans = trans
+            else:
+                x = point_transform(x, trans)
         pointfeat = None
-        if self.feature_transform or not self.global_feat:
+        if two_stacks:
             # the 64-wide point features are needed as a tensor: run the trunk as two stacks
-            x = shared_mlp(x, pc, pb, pr, pool=False, precision=self._precision)
+            x = shared_mlp(x, pc, pb, pr, pool=False, precision=self._precision, in_trans=in_trans)
             if self.feature_transform:
                 trans_feat = self.fstn(x)
-                x = x.transpose(2, 1)
-                x = torch.bmm(x, trans_feat)                                       # :147-151
-                x = x.transpose(2, 1)
+                x = point_transform(x, trans_feat)                                 # :147-151
             else:
                 trans_feat = None
             pointfeat = x
             x = shared_mlp(x, qc, qb, qr, pool=True, precision=self._precision)
         else:
             trans_feat = None
-            x = shared_mlp(x, pc + qc, pb + qb, pr + qr, pool=True, precision=self._precision)  # :143-162
+            x = shared_mlp(x, pc + qc, pb + qb, pr + qr, pool=True, precision=self._precision, in_trans=in_trans)  # :143-162
         x = x.view(-1, 1024)
         if self.global_feat:
             return x, trans, trans_feat

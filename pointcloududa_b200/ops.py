@@ -38,15 +38,29 @@ def _require_cuda_f32(t: torch.Tensor, name: str) -> None:
 # Small zero-initialised workspaces the kernels leave zeroed (tickets / partial sums), cached per
 # (device, stream) so concurrent streams never share one.
 _ws_cache: dict = {}
+_ws_retired: list = []      # superseded workspaces are never freed: a captured CUDA graph or in-flight work may hold the pointer
 
 
 def _zero_ws(nbytes: int, device: torch.device, tag: str) -> torch.Tensor:
     key = (tag, device.index, _stream())
     t = _ws_cache.get(key)
     if t is None or t.numel() < nbytes:
-        t = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=device)
+        if t is not None:
+            _ws_retired.append(t)
+        t = torch.zeros(max(nbytes, 4096), dtype=torch.uint8, device=device)
         _ws_cache[key] = t
     return t
+
+
+def _check_ws(rc: int, what: str, ws: Optional[torch.Tensor]) -> None:
+    """check(), and on failure re-zero the ticket workspace: a rejected or failed launch may leave partial sums / a
+    ticket behind, after which no later call on this stream would elect its last CTA."""
+    try:
+        check(rc, what)
+    except PcudaError:
+        if ws is not None:
+            ws.zero_()
+        raise
 
 
 # ------------------------------------------------------------------------------------------------
@@ -67,9 +81,9 @@ class _EntropyMap(torch.autograd.Function):
         mean = torch.empty((), dtype=torch.float32, device=zc.device) if want_mean else None
         with torch.cuda.device(zc.device):
             ws = _zero_ws(16, zc.device, "entropy") if want_mean else None
-            check(_lib.lib().pcuda_entropy_fwd(_ptr(zc), _ptr(m), _ptr(p), _ptr(mean), _ptr(ws), B, C, HW,
-                                              ACT[activation], inv_norm, smooth, _stream()),
-                  "pcuda_entropy_fwd")
+            _check_ws(_lib.lib().pcuda_entropy_fwd(_ptr(zc), _ptr(m), _ptr(p), _ptr(mean), _ptr(ws), B, C, HW,
+                                                  ACT[activation], inv_norm, smooth, _stream()),
+                      "pcuda_entropy_fwd", ws)
         ctx.save_for_backward(zc)
         ctx.cfg = (activation, inv_norm, smooth, B, C, HW)
         return m, p, mean
@@ -133,8 +147,8 @@ class _ChamferNN(torch.autograd.Function):
         L = _lib.lib()
         with torch.cuda.device(dev):
             ws = _zero_ws(L.pcuda_chamfer_ws_bytes(B, N, M), dev, "chamfer")
-            check(L.pcuda_chamfer_fwd(_ptr(xc), _ptr(yc), B, N, M, _ptr(d1), _ptr(i1), _ptr(d2), _ptr(i2),
-                                      _ptr(loss), _ptr(ws), _stream()), "pcuda_chamfer_fwd")
+            _check_ws(L.pcuda_chamfer_fwd(_ptr(xc), _ptr(yc), B, N, M, _ptr(d1), _ptr(i1), _ptr(d2), _ptr(i2),
+                                          _ptr(loss), _ptr(ws), _stream()), "pcuda_chamfer_fwd", ws)
         ctx.save_for_backward(xc, yc, d1, i1, d2, i2)
         ctx.mark_non_differentiable(d1, i1, d2, i2)
         return loss, d1, i1, d2, i2

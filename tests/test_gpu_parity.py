@@ -987,3 +987,104 @@ def test_bce_with_logits_matches_torch(target, weight, n):
     assert max_rel(go.cpu().numpy() / 2.0, gw.cpu().numpy()) < 2e-6
     pred = (torch.sigmoid(x) >= 0.5).float().mean().item()
     assert abs(acc.item() - (pred if target >= 0.5 else 1.0 - pred)) < 1e-6
+
+
+# ================================================================ per-cloud transforms ==============
+@pytest.mark.parametrize("B,K,N", [(4, 64, 300), (2, 64, 1), (3, 17, 130), (2, 3, 4096), (8, 64, 1024)])
+def test_point_transform_vs_torch_bmm(B, K, N):
+    """pcuda_point_transform_fwd/_bwd against torch.bmm(x^T, T)^T and its autograd (reference :147-151), on a strided view."""
+    from pointcloududa_b200.networks.PointNetCls import point_transform
+    g = torch.Generator().manual_seed(B * 1000 + K + N)
+    base = torch.randn(B, N, K, generator=g).to(DEV)
+    T = (torch.randn(B, K, K, generator=g) / math.sqrt(K)).to(DEV)
+    w = torch.randn(B, K, N, generator=g).to(DEV)
+    x = base.transpose(2, 1).detach().requires_grad_(True)            # [B, K, N] view of [B, N, K]
+    Tr = T.detach().requires_grad_(True)
+    out = point_transform(x, Tr)
+    assert out.shape == (B, K, N) and out.is_contiguous()
+    (out * w).sum().backward()
+    xd = base.double().transpose(2, 1).detach().requires_grad_(True)
+    Td = T.double().detach().requires_grad_(True)
+    ref = torch.bmm(xd.transpose(2, 1), Td).transpose(2, 1)
+    (ref * w.double()).sum().backward()
+    assert max_rel(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 2e-6
+    assert max_rel(x.grad.cpu().numpy(), xd.grad.cpu().numpy()) < 2e-6
+    assert max_rel(Tr.grad.cpu().numpy(), Td.grad.cpu().numpy()) < 5e-6
+    # deterministic
+    x2 = base.transpose(2, 1).detach().requires_grad_(True)
+    T2 = T.detach().requires_grad_(True)
+    (point_transform(x2, T2) * w).sum().backward()
+    assert torch.equal(x2.grad, x.grad) and torch.equal(T2.grad, Tr.grad)
+    # frozen transform / frozen input
+    with torch.no_grad():
+        assert torch.equal(point_transform(x.detach(), T), out.detach())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("chans,relus,pool,B,N", [([3, 64, 128, 1024], [True, True, False], True, 4, 300),
+                                                   ([3, 64], [True], False, 3, 130),
+                                                   ([3, 8, 64], [True, True], False, 2, 70)])
+def test_shared_mlp_fused_input_transform(chans, relus, pool, B, N, precision):
+    """The 3x3 input transform applied inside the first layer's operand load (pcuda_pointmlp_fwd_xf / _bwd_xf) equals
+    the transform as its own op followed by the same stack -- values, gradient into the cloud, gradient into the
+    transform, every parameter gradient -- and matches a float64 torch evaluation of bmm + stack (reference :140-162)."""
+    from pointcloududa_b200.networks.PointNetCls import point_transform, shared_mlp
+    convs, bns, pts = _tc_stack(chans, relus, B, N, seed=77 + N)
+    g = torch.Generator().manual_seed(5)
+    T0 = (torch.eye(3) + 0.3 * torch.randn(B, 3, 3, generator=g)).to(DEV)
+    w = torch.randn((B, chans[-1]) if pool else (B, chans[-1], N), generator=g).to(DEV)
+
+    def run(fused):
+        for m in convs + bns:
+            for p in m.parameters():
+                p.grad = None
+        for bn in bns:
+            bn.reset_running_stats()
+        x = pts.transpose(2, 1).detach().requires_grad_(True)
+        T = T0.detach().requires_grad_(True)
+        if fused:
+            out = shared_mlp(x, convs, bns, relus, pool=pool, precision=precision, in_trans=T)
+        else:
+            out = shared_mlp(point_transform(x, T), convs, bns, relus, pool=pool, precision=precision)
+        (out * w).sum().backward()
+        return out.detach(), x.grad.clone(), T.grad.clone(), [c.weight.grad.clone() for c in convs], [b.running_var.clone() for b in bns]
+
+    a, b = run(True), run(False)
+    tol = 1e-5 if precision == "fp32" else 2e-3      # bf16: an activation may straddle a rounding boundary between the two orders of evaluation
+    assert max_rel(a[0].cpu().numpy(), b[0].cpu().numpy()) < tol
+    assert max_rel(a[1].cpu().numpy(), b[1].cpu().numpy()) < 20 * tol
+    assert max_rel(a[2].cpu().numpy(), b[2].cpu().numpy()) < 20 * tol
+    for ga, gb in zip(a[3], b[3]):
+        assert max_rel(ga.cpu().numpy(), gb.cpu().numpy()) < 20 * tol
+    for ra, rb in zip(a[4], b[4]):
+        assert max_rel(ra.cpu().numpy(), rb.cpu().numpy()) < 10 * tol
+    if precision == "fp32":
+        xd = pts.double().transpose(2, 1).detach().requires_grad_(True)
+        Td = T0.double().detach().requires_grad_(True)
+        layers = [dict(weight=c.weight.detach().double(), bias=c.bias.detach().double(), gamma=bn.weight.detach().double(),
+                       beta=bn.bias.detach().double(), rm=torch.zeros_like(bn.running_mean).double(),
+                       rv=torch.ones_like(bn.running_var).double(), relu=r) for c, bn, r in zip(convs, bns, relus)]
+        ref, _ = _torch_stack(torch.bmm(xd.transpose(2, 1), Td).transpose(2, 1), layers, pool, True, torch.float64)
+        (ref * w.double()).sum().backward()
+        assert max_rel(a[0].cpu().numpy(), ref.detach().cpu().numpy()) < 2e-5
+        if _torch_stack.margin > 1e-5:
+            assert max_rel(a[1].cpu().numpy(), xd.grad.cpu().numpy()) < 5e-4
+            assert max_rel(a[2].cpu().numpy(), Td.grad.cpu().numpy()) < 5e-4
+
+
+def test_pointnetcls_launches_no_framework_gemm():
+    """No cuBLAS / ATen matmul on the D4 path: the input and feature transforms run inside libpcuda."""
+    from torch.profiler import ProfilerActivity, profile
+    from pointcloududa_b200.networks.PointNetCls import PointNetCls
+    for kw in (dict(), dict(feature_transform=True, ext=True)):
+        net = PointNetCls(drop=0.0, **kw).to(DEV).train()
+        pts = torch.rand(4, 300, 3, device=DEV, requires_grad=True)
+        net(pts.transpose(2, 1))[0].sum().backward()          # warm-up
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            net(pts.transpose(2, 1))[0].sum().backward()
+            torch.cuda.synchronize()
+        names = [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        assert any("pcuda::" in n for n in names)
+        bad = [n for n in names if any(t in n.lower() for t in ("gemm", "cutlass", "cublas", "bmm"))]
+        assert not bad, bad
