@@ -342,7 +342,7 @@ int pcuda_bce_logits(const float* logit, int n, float target, float weight, floa
  *                             sequence of calls.  The producer of `in` and the consumer of `out` are ordinary
  *                             kernels before / after it on `stream`.
  * Both are asynchronous launches on `stream` and legal under CUDA-graph capture.  pcuda_comm_status returns
- * non-zero if a peer-memory wait ever gave up (a peer never arrived within ~2 s).
+ * non-zero if a peer-memory wait ever gave up (a peer never arrived within 30 s).
  */
 typedef struct pcuda_comm pcuda_comm_t;
 int pcuda_comm_unique_id(void* id_out /*host, >= 128 bytes*/, int bytes);

@@ -20,7 +20,7 @@
 //
 // Both are plain launches on the caller's stream: legal under CUDA-graph capture, so the whole step — three D4
 // passes, the exchange, SGD — replays as ONE graph per rank.  A peer that never arrives makes the spin loops give
-// up after ~2 s (pcuda_comm_status reports it) instead of hanging the GPU.
+// up after 30 s (pcuda_comm_status reports it) instead of hanging the GPU.
 #include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
@@ -78,7 +78,9 @@ static const Nccl* nccl() {
 constexpr int kMaxRanks = 8;
 constexpr int kMaxBlocks = 128;
 constexpr int kP2PThreads = 512;
-constexpr unsigned long long kSpinLimit = 4000000000ull;     // cycles (~2 s): a peer that never arrives
+constexpr unsigned long long kSpinLimitNs = 30000000000ull;  // 30 s: a peer that never arrives.  Generous on purpose: on the
+                                                             // first step one rank may still be loading its CUDA modules
+                                                             // (lazy loading, ~200 kernels) seconds after the other
 
 // [ epoch[kMaxBlocks] | start[kMaxRanks][kMaxBlocks] | end[kMaxRanks][kMaxBlocks] | status[4] | pad ] [ in ] [ out ]
 constexpr size_t kEpochOff = 0;
@@ -103,6 +105,12 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // thread r < world: tell peer r that (this rank, block b) reached `epoch`, then wait for peer r's same message
 __device__ __forceinline__ void pair_barrier(const P2PArgs& a, size_t flag_off, int b, unsigned epoch) {
   if (static_cast<int>(threadIdx.x) < a.world) {
@@ -111,9 +119,9 @@ __device__ __forceinline__ void pair_barrier(const P2PArgs& a, size_t flag_off, 
     const unsigned* mine = reinterpret_cast<const unsigned*>(a.peer[a.rank] + flag_off) + r * kMaxBlocks + b;
     __threadfence_system();
     st_release_sys(theirs, epoch);
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_ns();
     while (static_cast<int>(ld_acquire_sys(mine) - epoch) < 0) {
-      if (static_cast<unsigned long long>(clock64() - t0) > kSpinLimit) {
+      if (global_ns() - t0 > kSpinLimitNs) {
         reinterpret_cast<unsigned*>(a.peer[a.rank] + kStatusOff)[0] = 1u;      // reported by pcuda_comm_status
         break;
       }

@@ -23,42 +23,55 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, fn_name, q):
+def _worker_main(fn_name, rank, world, port):
+    """Entry of one rank (a fresh interpreter: `python tests/test_gpu_multi.py <fn> <rank> <world> <port>`)."""
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)        # a deadlocked rank prints where it is stuck and dies
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        sys.path.insert(0, ROOT)
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                          LOCAL_RANK=str(rank))
-        import torch.distributed as dist
-        torch.cuda.set_device(rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-        try:
-            globals()[fn_name](rank, world)
-        finally:
-            dist.barrier()
-            dist.destroy_process_group()
-        q.put((rank, None))
-    except Exception:
-        q.put((rank, traceback.format_exc()))
+        globals()[fn_name](rank, world)
+    except BaseException:
+        traceback.print_exc()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(1)                                           # no collective on the way out: the peer must not wait for us
+    dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank}: ok", flush=True)
 
 
-def _run(fn_name, world=2):
+def _run(fn_name, world=2, timeout=240):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
+    import subprocess
+    import tempfile
+    import time
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, fn_name, q)) for r in range(world)]
+    logs = [tempfile.NamedTemporaryFile("w+", suffix=f".rank{r}.log", delete=False) for r in range(world)]
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), fn_name, str(r), str(world), str(port)],
+                              stdout=logs[r], stderr=subprocess.STDOUT, cwd=ROOT) for r in range(world)]
+    t0 = time.time()
+    failed = False
+    while any(p.poll() is None for p in procs):
+        if any(p.poll() not in (None, 0) for p in procs) or time.time() - t0 > timeout:
+            failed = True
+            time.sleep(2.0)
+            break
+        time.sleep(0.2)
     for p in procs:
-        p.start()
-    results = []
-    for _ in procs:
-        results.append(q.get(timeout=600))
-    for p in procs:
-        p.join(timeout=60)
-    errs = [f"rank {r}:\n{e}" for r, e in results if e is not None]
-    assert not errs, "\n".join(errs)
+        if p.poll() is None:
+            p.kill()
+    out = []
+    for r, f in enumerate(logs):
+        f.flush(); f.seek(0)
+        out.append(f"---- rank {r} (exit {procs[r].poll()}) ----\n" + f.read()[-6000:])
+        f.close(); os.unlink(f.name)
+    assert not failed and all(p.returncode == 0 for p in procs), "\n".join(out)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -175,3 +188,7 @@ def _step_body(rank, world):
 
 def test_adversarial_step_two_ranks_every_exchange_mode():
     _run("_step_body")
+
+
+if __name__ == "__main__":
+    _worker_main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
