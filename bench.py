@@ -616,9 +616,7 @@ def scale_lines(args, rank: int, world: int, dev, flush):
                          "ms_per_step": t_dev / steps * 1e3, "samples_per_s": world * w["B"] * steps / t_dev,
                          "e2e": {"value": units * steps / t_e2e, "ms_per_step": t_e2e / steps * 1e3,
                                  "h2d_bytes_per_step": host_flat.numel() * 4, "d2h_bytes_per_step": result_host.numel() * 4}}
-            if step.comm is not None:
-                step.comm.check_status()
-                step.comm.destroy()
+            step.close()
             del step, host_flat
             torch.cuda.empty_cache()
         except Exception as e:
@@ -767,9 +765,7 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
-        if step.comm is not None:
-            step.comm.check_status()
-            step.comm.destroy()
+        step.close()
         dist.destroy_process_group()
     return line
 

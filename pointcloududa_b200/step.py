@@ -282,6 +282,19 @@ class AdversarialStep:
             self._body()
         return self.result
 
+    def close(self) -> None:
+        """Release the captured graphs, then the communicator (collective: every rank calls it).  The order matters:
+        NCCL keeps a communicator alive while a CUDA graph that captured one of its collectives exists, so
+        ncclCommDestroy waits for the graph's destruction."""
+        import gc
+        self.graph = self.graph_post = None
+        gc.collect()
+        torch.cuda.synchronize(self.device)
+        if self.comm is not None:
+            self.comm.check_status()
+            self.comm.destroy()
+            self.comm = None
+
     def _snapshot_state(self):
         """Everything a step mutates besides its outputs: D4's parameters and buffers (BatchNorm running statistics,
         num_batches_tracked), the optimiser's momentum and the device RNG (Dropout)."""
