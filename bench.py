@@ -242,50 +242,94 @@ def _splits(w):
     return max(1, min(2 * 148, (m + 127) // 128))
 
 
+def _M(w):
+    return float(w["B"]) * w["N"]
+
+
 KERNEL_WORK = {
-    # kernel-name fragment -> (bound, algorithmic work per launch as a function of the per-rank workload):
-    # FLOPs for the tcgen05 GEMMs, compulsory HBM bytes (every operand once, every result once) for the rest.
-    # default D4 (3->64->128->1024 twice: STN3d trunk and main trunk), M = B*N points, C = 1024, K = 128;
-    # where one kernel serves several layer shapes the widest is taken (an upper bound of the work).
-    "ws_kernel<1>": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 128 * 1024),     # pooled 128->1024 GEMM (tcgen05)
-    "ws_kernel<0>": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 64 * 128),       # dense 64->128 GEMM
-    "ws_kernel<2>": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 128 * 64),       # dgrad 128->64
-    "ws_kernel<3>": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 128 * 128),      # pooled-layer low-rank dgrad (a Q)
-    "pt_kernel": ("tensor", lambda w: 2.0 * w["B"] * w["N"] * 128 * 128),         # wgrad / Gram over points (upper bound of the two)
-    "entropy_fwd": ("hbm", lambda w: (8.0 + (4.0 if w["return_prob"] else 0.0)) * w["B"] * w["C"] * w["H"] * w["W"]),
-    "entropy_bwd": ("hbm", lambda w: 12.0 * w["B"] * w["C"] * w["H"] * w["W"]),
-    "chamfer_nn": ("hbm", lambda w: 48.0 * w["B"] * w["N"]),                      # 24 B/point in + out, both clouds
-    "chamfer_bwd": ("hbm", lambda w: 36.0 * 2 * w["B"] * w["N"]),
-    "pack_act_kernel": ("hbm", lambda w: (4.0 + 2.0) * w["B"] * w["N"] * 128),    # fp32 in, bf16 out (widest layer)
-    "pack_dy_kernel": ("hbm", lambda w: (8.0 + 2.0) * w["B"] * w["N"] * 128),     # dz and y in, bf16 out
-    "pack_w_kernel": ("hbm", lambda w: (4.0 + 2.0) * 1024 * 128),
+    # kernel-name fragment -> (algorithmic FLOPs per launch or None, compulsory HBM bytes per launch: every operand once,
+    # every result once) as functions of the per-rank workload.  Default D4 (3->64->128->1024 twice: STN3d trunk and
+    # main trunk), M = B*N points, C = 1024, K = 128; where one kernel serves several layer shapes the widest is taken
+    # (an upper bound of the work).  The roofline of a kernel is the LARGER of flops / tensor peak and bytes / HBM peak:
+    # only the pooled 128->1024 GEMM (1024 FLOP per byte of operand) is tensor-bound, the narrow GEMMs move a bf16
+    # operand and an fp32 result per ~20 FLOP/B and sit on the HBM roof.
+    "ws_kernel<1>": (lambda w: 2.0 * _M(w) * 128 * 1024, lambda w: _M(w) * 128 * 2.0 + 1024 * 128 * 2.0 + w["B"] * 1024 * 8.0),
+    "ws_kernel<0>": (lambda w: 2.0 * _M(w) * 64 * 128, lambda w: _M(w) * (64 * 2.0 + 128 * 4.0)),            # a bf16 in, y fp32 out
+    "ws_kernel<2>": (lambda w: 2.0 * _M(w) * 128 * 64, lambda w: _M(w) * (128 * 2.0 + 64 * 4.0 + 64 * 4.0)),   # dy bf16, y_prev in, dz out
+    "ws_kernel<3>": (lambda w: 2.0 * _M(w) * 128 * 128, lambda w: _M(w) * (128 * 2.0 + 128 * 4.0 + 128 * 4.0)),  # a bf16, y_prev in, dz out
+    "pt_kernel": (lambda w: 2.0 * _M(w) * 128 * 128, lambda w: _M(w) * (128 + 128) * 2.0),                   # both operands bf16 slabs
+    "entropy_fwd": (None, lambda w: (8.0 + (4.0 if w["return_prob"] else 0.0)) * w["B"] * w["C"] * w["H"] * w["W"]),
+    "entropy_bwd": (None, lambda w: 12.0 * w["B"] * w["C"] * w["H"] * w["W"]),
+    "chamfer_nn": (lambda w: 3.0 * 2.0 * w["B"] * w["N"] * w["N"], lambda w: 48.0 * w["B"] * w["N"]),          # 3 FP32 lane-ops per ordered pair (prefilter)
+    "chamfer_bwd": (None, lambda w: 36.0 * 2 * w["B"] * w["N"]),
+    "pack_act_kernel": (None, lambda w: (4.0 + 2.0) * _M(w) * 128),    # fp32 in, bf16 out (widest layer)
+    "pack_dy_kernel": (None, lambda w: (8.0 + 2.0) * _M(w) * 128),     # dz and y in, bf16 out
+    "pack_w_kernel": (None, lambda w: (4.0 + 2.0) * 1024 * 128),
     # sparse rows of the pooled-layer dgrad: arg/coef, one W row per (cloud, channel), read-modify-write of the
     # <= min(C, N) selected points per cloud (y_prev, dz_prev in, dz_prev out), K = 128, C = 1024
-    "pool_sparse_kernel": ("hbm", lambda w: w["B"] * 1024 * (8.0 + 4.0 * 128) + w["B"] * min(1024, w["N"]) * 128 * 12.0),
-    "pool_dw_kernel": ("hbm", lambda w: 1024 * 128 * 8.0 + 128 * 128 * 4.0 + w["B"] * 1024 * (8.0 + 4.0 * 128)),
-    "pool_sel_kernel": ("hbm", lambda w: w["B"] * 1024 * (4.0 * 128 + 24.0) + 1024 * 128 * 4.0),   # selected rows + W + out/arg/grad/coef
-    "pool_coef_kernel": ("hbm", lambda w: w["B"] * 1024 * 8.0 + 1024 * 28.0),
-    "pool_q_kernel": ("hbm", lambda w: 1024 * 128 * 4.0 + 1024 * 4.0 + 8 * 128 * 128 * 4.0),       # W, kappa in, split partials out
-    "q_finish_kernel": ("hbm", lambda w: 8 * 128 * 128 * 4.0 + 1024 * 128 * 4.0 + 128 * 128 * 6.0),       # partials + W in, Q fp32 + bf16 out
-    "pool_u_kernel": ("hbm", lambda w: 1024 * 128 * 4.0 + 128 * 128 * 4.0 + 1024 * 4.0 + 1024.0),
-    "pool_finalize_kernel": ("hbm", lambda w: w["B"] * 1024 * 16.0),
-    "act_colsum_kernel": ("hbm", lambda w: 4.0 * w["B"] * w["N"] * 128),
-    "abar_kernel": ("hbm", lambda w: _splits(w) * 128 * 8.0),
-    "gram_center_kernel": ("hbm", lambda w: 128 * 128 * 12.0),
-    "reduce_partials_kernel": ("hbm", lambda w: (_splits(w) + 1) * 1024 * 128 * 4.0),              # widest: dW of the pooled layer
-    "mlp_fwd_narrow_kernel": ("hbm", lambda w: (12.0 + 4.0 * 64) * w["B"] * w["N"]),               # 3 -> 64: cloud in, y out
-    "wgrad_narrow_kernel": ("hbm", lambda w: (12.0 + 8.0 * 64) * w["B"] * w["N"]),
-    "dgrad_input_narrow_kernel": ("hbm", lambda w: (8.0 * 64 + 12.0) * w["B"] * w["N"]),
-    "bn_finalize_pivot_kernel": ("hbm", lambda w: 1024 * 40.0),
-    "bn_bwd_coef_kernel": ("hbm", lambda w: 1024 * 44.0),
-    "bn_running_update": ("hbm", lambda w: 3968 * 3 * 16.0),
-    "fc_fwd_kernel": ("hbm", lambda w: 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) / 3 + 4.0 * w["B"] * (1024 + 512)),   # mean layer of a head
-    "fc_bwd_kernel": ("hbm", lambda w: 2 * 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) / 3 + 4.0 * w["B"] * (1024 + 512)),
-    "fc_pull_kernel": ("hbm", lambda w: 4.0 * 512 * 1024 + 4.0 * w["B"] * (1024 + 512)),
-    "sgd": ("hbm", lambda w: 1.6e6 * 16.0),                                      # grad, momentum in / momentum, param in+out
-    "grad_sum_pack_kernel": ("hbm", lambda w: 1.6e6 * 12.0),                    # two gradient lists in, the bucket out
-    "bce_logits_kernel": ("hbm", lambda w: w["B"] * 8.0 + 8.0),
+    "pool_sparse_kernel": (None, lambda w: w["B"] * 1024 * (8.0 + 4.0 * 128) + w["B"] * min(1024, w["N"]) * 128 * 12.0),
+    "pool_dw_kernel": (None, lambda w: 1024 * 128 * 8.0 + 128 * 128 * 4.0 + w["B"] * 1024 * (8.0 + 4.0 * 128)),
+    "pool_sel_kernel": (None, lambda w: w["B"] * 1024 * (4.0 * 128 + 24.0) + 1024 * 128 * 4.0),   # selected rows + W + out/arg/grad/coef
+    "pool_coef_kernel": (None, lambda w: w["B"] * 1024 * 8.0 + 1024 * 28.0),
+    "pool_q_kernel": (None, lambda w: 1024 * 128 * 4.0 + 1024 * 4.0 + 8 * 128 * 128 * 4.0),       # W, kappa in, split partials out
+    "q_finish_kernel": (None, lambda w: 8 * 128 * 128 * 4.0 + 1024 * 128 * 4.0 + 128 * 128 * 6.0),       # partials + W in, Q fp32 + bf16 out
+    "pool_u_kernel": (None, lambda w: 1024 * 128 * 4.0 + 128 * 128 * 4.0 + 1024 * 4.0 + 1024.0),
+    "pool_finalize_kernel": (None, lambda w: w["B"] * 1024 * 16.0),
+    "act_colsum_kernel": (None, lambda w: 4.0 * _M(w) * 128),
+    "abar_kernel": (None, lambda w: _splits(w) * 128 * 8.0),
+    "gram_center_kernel": (None, lambda w: 128 * 128 * 12.0),
+    "reduce_partials_kernel": (None, lambda w: (_splits(w) + 1) * 1024 * 128 * 4.0),              # widest: dW of the pooled layer
+    "mlp_fwd_narrow_kernel": (None, lambda w: (12.0 + 4.0 * 64) * _M(w)),               # 3 -> 64: cloud in, y out
+    "wgrad_narrow_kernel": (None, lambda w: (12.0 + 8.0 * 64) * _M(w)),
+    "dgrad_input_narrow_kernel": (None, lambda w: (8.0 * 64 + 12.0) * _M(w)),
+    "input_transform_bwd_kernel": (None, lambda w: 36.0 * _M(w)),
+    "point_transform_kernel": (None, lambda w: 2 * 4.0 * 64 * _M(w)),
+    "bn_finalize_pivot_kernel": (None, lambda w: 1024 * 40.0),
+    "bn_bwd_coef_kernel": (None, lambda w: 1024 * 44.0),
+    "bn_running_update": (None, lambda w: 3968 * 3 * 16.0),
+    "fc_fwd_kernel": (None, lambda w: 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) / 3 + 4.0 * w["B"] * (1024 + 512)),   # mean layer of a head
+    "fc_bwd_kernel": (None, lambda w: 2 * 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) / 3 + 4.0 * w["B"] * (1024 + 512)),
+    "fc_pull_kernel": (None, lambda w: 4.0 * 512 * 1024 + 4.0 * w["B"] * (1024 + 512)),
+    "fc_head": (None, lambda w: 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) + 4.0 * w["B"] * (1024 + 512 + 256)),
+    "sgd": (None, lambda w: 1.6e6 * 16.0),                                      # grad, momentum in / momentum, param in+out
+    "grad_sum_pack_kernel": (None, lambda w: 1.6e6 * 12.0),                    # two gradient lists in, the bucket out
+    "p2p_allreduce_kernel": (None, lambda w: 1.6e6 * 8.0),                     # per GPU: (R-1)/R of the bucket read + written over NVLink
+    "bce_logits_kernel": (None, lambda w: w["B"] * 8.0 + 8.0),
 }
+
+
+def kernel_roofline(name: str, w: dict, seconds: float, pk: dict, traffic=None) -> dict:
+    """Roofline record of one launch of kernel `name` that took `seconds`: achieved rate against the roof that bounds
+    it — tensor peak if flops / peak_tensor > bytes / peak_hbm, else HBM — with both fractions kept for reference.
+    When the ncu DRAM traffic of the launch is below half of its algorithmic bytes the working set is L2-resident and
+    the launch is a chain of dependent L2 round trips: labelled "l2-latency" (the HBM fraction is then not a statement
+    about the kernel)."""
+    for frag, (flops_f, bytes_f) in KERNEL_WORK.items():
+        if frag not in name:
+            continue
+        nbytes = bytes_f(w)
+        flops = flops_f(w) if flops_f is not None else None
+        rec = {"algorithmic_bytes_per_launch": nbytes, "hbm_gbs": nbytes / seconds / 1e9,
+               "frac_hbm": nbytes / seconds / 1e9 / pk["hbm"]}
+        is_chamfer = "chamfer_nn" in name
+        if flops is not None and not is_chamfer:
+            rec.update({"algorithmic_flops_per_launch": flops, "tflops": flops / seconds / 1e12,
+                        "frac_tensor": flops / seconds / 1e12 / pk["tensor"]})
+        if is_chamfer:
+            lane_peak = 148 * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6
+            rec.update({"bound": "fp32-issue", "achieved": flops / seconds / 1e12, "peak": lane_peak / 1e12,
+                        "unit": "T FP32 lane-ops/s", "frac": flops / seconds / lane_peak})
+        elif flops is not None and flops / (pk["tensor"] * 1e12) > nbytes / (pk["hbm"] * 1e9):
+            rec.update({"bound": "tensor", "achieved": rec["tflops"], "peak": pk["tensor"], "unit": "TFLOP/s", "frac": rec["frac_tensor"]})
+        else:
+            rec.update({"bound": "hbm", "achieved": rec["hbm_gbs"], "peak": pk["hbm"], "unit": "GB/s", "frac": rec["frac_hbm"]})
+        if traffic is not None:
+            rec["traffic"] = traffic
+            rec["traffic_over_algorithmic"] = traffic / nbytes if nbytes else None
+            if rec["bound"] == "hbm" and traffic < 0.5 * nbytes:
+                rec["bound"] = "l2-latency"
+        return rec
+    return {"bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None}
 
 
 def ncu_traffic(workload: str, kernel_short: str):
@@ -341,20 +385,12 @@ def kernel_profile(step, w: dict, pk: dict, reps: int = 5, record: bool = True, 
     roof = {"kernel": short(dom_name), "launches_per_step": dom[0] / reps, "launch_us": dom[1] / dom[0],
             "share_of_step": dom[1] / tot, "device_busy_us_per_step": tot / reps,
             "libpcuda_share_of_step": sum(v[1] for v in ours.values()) / tot}
-    for frag, (bound, work) in KERNEL_WORK.items():
-        if frag in dom_name:
-            wk = work(w)
-            sec = dom[1] / dom[0] * 1e-6
-            if bound == "tensor":
-                roof.update({"bound": "tensor", "achieved": wk / sec / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s"})
-            else:
-                roof.update({"bound": "hbm", "achieved": wk / sec / 1e9, "peak": pk["hbm"], "unit": "GB/s"})
-            roof["frac"] = roof["achieved"] / roof["peak"]
-            roof["algorithmic_work_per_launch"] = wk
-            break
-    else:
-        roof.update({"bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None})
-    roof["traffic"], roof["traffic_source"] = ncu_traffic(workload, short(dom_name))
+    traffic, tsrc = ncu_traffic(workload, short(dom_name))
+    roof.update(kernel_roofline(dom_name, w, dom[1] / dom[0] * 1e-6, pk, traffic))
+    roof["traffic"], roof["traffic_source"] = traffic, tsrc
+    for sh, (k, v) in zip(shares, top[:8]):
+        r = kernel_roofline(k, w, v[1] / v[0] * 1e-6, pk, ncu_traffic(workload, short(k))[0])
+        sh.update({"bound": r.get("bound"), "frac": r.get("frac"), "frac_hbm": r.get("frac_hbm"), "frac_tensor": r.get("frac_tensor")})
     roof["peak_source"] = pk["source"]
     roof["note"] = ("dominant libpcuda kernel of the graph-replayed step at this workload (CUPTI device durations, warm L2); "
                     "at cfg2 sizes (2400 points per call) every kernel is latency-bound - `large` holds the roofline-sized shapes")
@@ -500,8 +536,11 @@ def large_shape_rooflines(flush, pk: dict):
             for k, v in agg.items():
                 if frag in k:
                     us = v[1] / v[0]
+                    rr = kernel_roofline(k, dict(B=32, N=4096, C=5, H=256, W=256, return_prob=True), us * 1e-6, pk)
                     res[name + "_B32_N4096"] = dict(us=us, tflops=flops / us / 1e6, frac_tensor=flops / us / 1e6 / pk["tensor"],
-                                                    frac_tensor_sustained=(flops / us / 1e6 / pk["tensor_sustained"]) if pk.get("tensor_sustained") else None)
+                                                    frac_tensor_sustained=(flops / us / 1e6 / pk["tensor_sustained"]) if pk.get("tensor_sustained") else None,
+                                                    bound=rr.get("bound"), hbm_gbs=rr.get("hbm_gbs"), frac_hbm=rr.get("frac_hbm"),
+                                                    frac=rr.get("frac"), algorithmic_bytes=rr.get("algorithmic_bytes_per_launch"))
     except Exception as e:
         res["kernel_level_error"] = repr(e)
     return res
