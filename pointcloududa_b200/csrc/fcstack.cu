@@ -21,6 +21,17 @@
 #include "pcuda_common.cuh"
 
 namespace pcuda {
+// fchead.cu: a whole head as one thread-block-cluster launch per direction (small batches)
+bool fc_head_supported(int B, int L, const pcuda_fc_layer_t* layers, int cluster);
+int fc_head_fwd(const float* x, int B, int L, const pcuda_fc_layer_t* layers, int train, float momentum, float eps, int iden_k,
+                int cluster, cudaStream_t st);
+int fc_head_bwd(const float* x, int B, int L, const pcuda_fc_layer_t* layers, int train, const float* grad_out, float* grad_x,
+                int cluster, cudaStream_t st);
+static int head_cluster_size() {
+  const int t = tuning(TUNE_FC_CLUSTER_SIZE);
+  return (t == 1 || t == 2 || t == 4 || t == 8 || t == 16) ? t : 8;
+}
+
 namespace {
 
 constexpr int kCPB = 4;        // output channels per CTA
@@ -418,6 +429,10 @@ extern "C" int pcuda_fcstack_fwd(const float* x, int B, int L, const pcuda_fc_la
     PCUDA_REQUIRE(!(layers[l].bn && train) || B > 1, PCUDA_E_SHAPE, "fcstack_fwd: train-mode BatchNorm needs more than 1 row");
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (fc_head_supported(B, L, layers, head_cluster_size())) {
+    const int rc = fc_head_fwd(x, B, L, layers, train, momentum, eps, add_identity_k, head_cluster_size(), st);
+    if (rc != PCUDA_E_UNSUPPORTED) return rc;
+  }
   smem_optin(fc_fwd_kernel, 160 * 1024);
   const float* in = x;
   for (int l = 0; l < L; ++l) {
@@ -443,6 +458,10 @@ extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_la
   if (int rc = validate_fc("fcstack_bwd", B, L, layers)) return rc;
   PCUDA_REQUIRE(x && grad_out && ws, PCUDA_E_NULL, "fcstack_bwd: NULL x/grad_out/ws");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (aligned16(x) && fc_head_supported(B, L, layers, head_cluster_size())) {
+    const int rc = fc_head_bwd(x, B, L, layers, train, grad_out, grad_x, head_cluster_size(), st);
+    if (rc != PCUDA_E_UNSUPPORTED) return rc;
+  }
   size_t mx = 0;
   for (int l = 0; l < L; ++l) mx = mx > static_cast<size_t>(layers[l].cout) ? mx : static_cast<size_t>(layers[l].cout);
   float* dybuf[2] = {static_cast<float*>(ws), static_cast<float*>(ws) + static_cast<size_t>(B) * mx};
