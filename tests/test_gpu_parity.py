@@ -816,16 +816,18 @@ def _fc_stack_vs_torch(dims, B, iden_k, drop):
         p.grad = None
     ref = _fc_torch(x64, lins, bns, relus, masks, iden_k, torch.float64)
     (ref * w.double()).sum().backward()
-    assert max_rel(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 2e-5
-    assert max_rel(got["x"].cpu().numpy(), x64.grad.cpu().numpy()) < 2e-4
+    # BatchNorm over a batch of two rows maps every channel to +-1: conditioning-limited (cf. default_b2_n50 golden case)
+    gt = 2e-4 if B > 2 else 2e-3
+    assert max_rel(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < (2e-5 if B > 2 else 2e-4)
+    assert max_rel(got["x"].cpu().numpy(), x64.grad.cpu().numpy()) < gt
     for l, (lin, bn) in enumerate(zip(lins, bns)):
-        assert max_rel(got[f"W{l}"].cpu().numpy(), lin.weight.grad.cpu().numpy()) < 2e-4, l
+        assert max_rel(got[f"W{l}"].cpu().numpy(), lin.weight.grad.cpu().numpy()) < gt, l
         # (behind a train-mode BN the bias gradient is a rounding-level zero unless a Dropout mask sits between)
         berr = (got[f"b{l}"].double() - lin.bias.grad).abs().max().item()
-        assert berr < 2e-4 * max(lin.bias.grad.abs().max().item(), 1e-2 * lin.weight.grad.abs().max().item()), l
+        assert berr < gt * max(lin.bias.grad.abs().max().item(), 1e-2 * lin.weight.grad.abs().max().item()), l
         if bn is not None:
-            assert max_rel(got[f"g{l}"].cpu().numpy(), bn.weight.grad.cpu().numpy()) < 2e-4, l
-            assert max_rel(got[f"be{l}"].cpu().numpy(), bn.bias.grad.cpu().numpy()) < 2e-4, l
+            assert max_rel(got[f"g{l}"].cpu().numpy(), bn.weight.grad.cpu().numpy()) < gt, l
+            assert max_rel(got[f"be{l}"].cpu().numpy(), bn.bias.grad.cpu().numpy()) < gt, l
     # running statistics against torch's own BatchNorm1d on the fp32 activations
     a = x.detach()
     for lin, bn, relu, m in zip(lins, bns, relus, masks):
