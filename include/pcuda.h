@@ -72,8 +72,7 @@ int pcuda_sm_count(void);
  * 3 = bit mask of MLP pieces switched from tcgen05 back to FP32 (1 forward, 2 pooled dgrad,
  * 4 dense dgrad, 8 wgrad, 16 Gram), 4 = timing experiments of the pooled tensor-core layer (results invalid),
  * 5 = chamfer seed-pass stride (0 default, < 0 off), 6 = no auxiliary-stream fork / finalise-on-read in the MLP,
- * 7 = CTAs of the peer-memory all-reduce (0 default), 8 = FC heads on the per-layer kernels instead of the
- * cluster kernel, 9 = cluster size of the FC-head kernel (1, 2, 4, 8 default, 16). */
+ * 7 = CTAs of the peer-memory all-reduce (0 default), 8 = launch without programmatic dependent launch (A/B). */
 int pcuda_tune(int key, int value);
 /* Number of kernels this library has launched in this process (monotone; for bench accounting). */
 uint64_t pcuda_launch_count(void);

@@ -83,6 +83,7 @@ chamfer_nn_kernel(const float* __restrict__ x, const float* __restrict__ y, int 
                   float* __restrict__ d1, int64_t* __restrict__ i1, float* __restrict__ d2,
                   int64_t* __restrict__ i2, FwdWs* __restrict__ ws, float* __restrict__ loss,
                   int tiles_x, int tiles_y, int B) {
+  pdl_entry();
   __shared__ float4 tile[kTileJ];
   const int dir = blockIdx.z;
   const int b = blockIdx.y;
@@ -181,6 +182,7 @@ chamfer_nn2_kernel(const float* __restrict__ x, const float* __restrict__ y, int
                    float* __restrict__ d1, int64_t* __restrict__ i1, float* __restrict__ d2,
                    int64_t* __restrict__ i2, FwdWs* __restrict__ ws, float* __restrict__ loss,
                    int tiles_x, int tiles_y, int B) {
+  pdl_entry();
   __shared__ float4 tileA[kTileJ / 2];
   __shared__ float4 tileB[kTileJ / 2];
   const int dir = blockIdx.z;
@@ -325,6 +327,7 @@ chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int
                    float* __restrict__ d1, int64_t* __restrict__ i1, float* __restrict__ d2,
                    int64_t* __restrict__ i2, FwdWs* __restrict__ ws, float* __restrict__ loss,
                    int tiles_x, int tiles_y, int B, int seed_stride, int seed_forced) {
+  pdl_entry();
   __shared__ float4 tileA[kTileJ / 2 + 1];   // + 1: the scan prefetches one entry ahead
   __shared__ float4 tileB[kTileJ / 2 + 1];
   __shared__ float warp_rmax[THREADS / 32];
@@ -519,6 +522,7 @@ chamfer_nn3_kernel(const float* __restrict__ x, const float* __restrict__ y, int
 __global__ void chamfer_bwd_scatter(const float* __restrict__ q, const float* __restrict__ c,
                                     const float* __restrict__ dq, const int64_t* __restrict__ iq,
                                     int nq, int nc, int B, long long* __restrict__ acc_c) {
+  pdl_entry();
   // for every query point (b,i) with nearest candidate j: acc_c[b,j] += (c_j - q_i)/d_i
   const int64_t total = static_cast<int64_t>(B) * nq;
   for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
@@ -543,6 +547,7 @@ __global__ void chamfer_bwd_finalize(const float* __restrict__ q, const float* _
                                      const long long* __restrict__ acc_q,
                                      const float* __restrict__ grad_loss, int nq, int nc, int B,
                                      double inv_nb, float* __restrict__ grad_q) {
+  pdl_entry();
   const int64_t total = static_cast<int64_t>(B) * nq;
   const double scale = static_cast<double>(__ldg(grad_loss)) * inv_nb;
   for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
@@ -621,16 +626,16 @@ extern "C" int pcuda_chamfer_fwd(const float* x, const float* y, int B, int N, i
   const dim3 grid(p.tiles_x > p.tiles_y ? p.tiles_x : p.tiles_y, B, 2);
   FwdWs* w = static_cast<FwdWs*>(ws);
 #define PCUDA_LAUNCH_NN(RR, TT)                                                              \
-  chamfer_nn_kernel<RR, TT><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,        \
+  PCUDA_LAUNCH((chamfer_nn_kernel<RR, TT>), grid, TT, 0, st, x, y, N, M, d1, i1, d2, i2, w, loss,        \
                                                  p.tiles_x, p.tiles_y, B)
 #define PCUDA_LAUNCH_NN3(RR, TT)                                                             \
-  chamfer_nn3_kernel<RR, TT><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,       \
+  PCUDA_LAUNCH((chamfer_nn3_kernel<RR, TT>), grid, TT, 0, st, x, y, N, M, d1, i1, d2, i2, w, loss,       \
                                                   p.tiles_x, p.tiles_y, B, seed_stride, seed_tune > 0)
 #define PCUDA_LAUNCH_NN3B(RR, TT, MB)                                                        \
-  chamfer_nn3_kernel<RR, TT, MB><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,   \
+  PCUDA_LAUNCH((chamfer_nn3_kernel<RR, TT, MB>), grid, TT, 0, st, x, y, N, M, d1, i1, d2, i2, w, loss,   \
                                                       p.tiles_x, p.tiles_y, B, seed_stride, seed_tune > 0)
 #define PCUDA_LAUNCH_NN2(RR, TT)                                                             \
-  chamfer_nn2_kernel<RR, TT><<<grid, TT, 0, st>>>(x, y, N, M, d1, i1, d2, i2, w, loss,       \
+  PCUDA_LAUNCH((chamfer_nn2_kernel<RR, TT>), grid, TT, 0, st, x, y, N, M, d1, i1, d2, i2, w, loss,       \
                                                   p.tiles_x, p.tiles_y, B)
   // tuning value >= 200000 selects the packed exact kernel (v2), >= 100000 the scalar one (v1), for A/B runs
   const int variant = tuning(TUNE_CHAMFER_ROWS) / 100000;
@@ -691,13 +696,13 @@ extern "C" int pcuda_chamfer_bwd(const float* x, const float* y, const float* d1
   if (grad_x) {
     cudaMemsetAsync(acc_x, 0, sizeof(long long) * 3 * static_cast<size_t>(B) * N, st);
     // y_j -> nearest x_i contributes to grad_x[i2(j)]
-    chamfer_bwd_scatter<<<blocks(static_cast<int64_t>(B) * M), threads, 0, st>>>(y, x, d2, i2, M, N, B, acc_x);
-    chamfer_bwd_finalize<<<blocks(static_cast<int64_t>(B) * N), threads, 0, st>>>(x, y, d1, i1, acc_x, grad_loss, N, M, B, inv_nb, grad_x);
+    PCUDA_LAUNCH(chamfer_bwd_scatter, blocks(static_cast<int64_t>(B) * M), threads, 0, st, y, x, d2, i2, M, N, B, acc_x);
+    PCUDA_LAUNCH(chamfer_bwd_finalize, blocks(static_cast<int64_t>(B) * N), threads, 0, st, x, y, d1, i1, acc_x, grad_loss, N, M, B, inv_nb, grad_x);
   }
   if (grad_y) {
     cudaMemsetAsync(acc_y, 0, sizeof(long long) * 3 * static_cast<size_t>(B) * M, st);
-    chamfer_bwd_scatter<<<blocks(static_cast<int64_t>(B) * N), threads, 0, st>>>(x, y, d1, i1, N, M, B, acc_y);
-    chamfer_bwd_finalize<<<blocks(static_cast<int64_t>(B) * M), threads, 0, st>>>(y, x, d2, i2, acc_y, grad_loss, M, N, B, inv_nb, grad_y);
+    PCUDA_LAUNCH(chamfer_bwd_scatter, blocks(static_cast<int64_t>(B) * N), threads, 0, st, x, y, d1, i1, N, M, B, acc_y);
+    PCUDA_LAUNCH(chamfer_bwd_finalize, blocks(static_cast<int64_t>(B) * M), threads, 0, st, y, x, d2, i2, acc_y, grad_loss, M, N, B, inv_nb, grad_y);
   }
   count_launch((grad_x ? 2 : 0) + (grad_y ? 2 : 0));
   return check_launch("chamfer_bwd");

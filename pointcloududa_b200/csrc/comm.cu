@@ -131,6 +131,7 @@ __device__ __forceinline__ void pair_barrier(const P2PArgs& a, size_t flag_off, 
 }
 
 __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(const __grid_constant__ P2PArgs a) {
+  pdl_entry();
   const int b = blockIdx.x, nb = gridDim.x;
   __shared__ unsigned s_epoch;
   unsigned* epochs = reinterpret_cast<unsigned*>(a.peer[a.rank] + kEpochOff);
@@ -297,7 +298,7 @@ extern "C" int pcuda_comm_allreduce_p2p(pcuda_comm_t* c, int64_t count, pcuda_st
   const int tuned = tuning(TUNE_COMM_BLOCKS);
   const int cap = tuned > 0 ? tuned : c->blocks;
   const int blocks = std::max(1, std::min(std::min(want, cap), kMaxBlocks));
-  p2p_allreduce_kernel<<<blocks, kP2PThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  PCUDA_LAUNCH(p2p_allreduce_kernel, blocks, kP2PThreads, 0, static_cast<cudaStream_t>(stream), a);
   count_launch(1);
   return check_launch("comm_allreduce_p2p");
 }

@@ -112,6 +112,7 @@ entropy_fwd_vec4(const float* __restrict__ z, float* __restrict__ m, float* __re
                  float* __restrict__ mean_out, MeanWs* __restrict__ ws, int64_t n_quads,
                  int64_t quads_per_img, int64_t HW, float inv_norm, float smooth,
                  double inv_count) {
+  pdl_entry();
   float local = 0.0f;
   // (image, quad-in-image) advance incrementally: no 64-bit division inside the streaming loop
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(kThreads)
 entropy_fwd_generic(const float* __restrict__ z, float* __restrict__ m, float* __restrict__ p_out,
                     float* __restrict__ mean_out, MeanWs* __restrict__ ws, int64_t n_pix, int C,
                     int64_t HW, float inv_norm, float smooth, double inv_count) {
+  pdl_entry();
   float local = 0.0f;
   for (int64_t q = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; q < n_pix;
        q += static_cast<int64_t>(gridDim.x) * kThreads) {
@@ -213,6 +215,7 @@ entropy_bwd_vec4(const float* __restrict__ z, const float* __restrict__ grad_m,
                  const float* __restrict__ grad_p, const float* __restrict__ grad_mean,
                  float* __restrict__ grad_z, int64_t n_quads, int64_t quads_per_img, int64_t HW,
                  float inv_norm, float smooth, float inv_count) {
+  pdl_entry();
   const float gs = grad_mean ? __ldg(grad_mean) * inv_count : 0.0f;
   // (image, quad-in-image) advance incrementally: no 64-bit division inside the streaming loop
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
@@ -296,6 +299,7 @@ entropy_bwd_generic(const float* __restrict__ z, const float* __restrict__ grad_
                     const float* __restrict__ grad_p, const float* __restrict__ grad_mean,
                     float* __restrict__ grad_z, int64_t n_pix, int C, int64_t HW, float inv_norm,
                     float smooth, float inv_count) {
+  pdl_entry();
   const float gs = grad_mean ? __ldg(grad_mean) * inv_count : 0.0f;
   for (int64_t q = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; q < n_pix;
        q += static_cast<int64_t>(gridDim.x) * kThreads) {
@@ -348,7 +352,7 @@ template <int ACT, int C, bool WP, bool WM, bool FAST>
 int launch_fwd_vec4(const FwdArgs& a, int64_t n_quads, int64_t qpi) {
   auto k = entropy_fwd_vec4<ACT, C, WP, WM, FAST>;
   const int grid = grid_for(k, n_quads);
-  k<<<grid, kThreads, 0, a.st>>>(a.z, a.m, a.p, a.mean_out, a.ws, n_quads, qpi, a.HW, a.inv_norm,
+  PCUDA_LAUNCH(k, grid, kThreads, 0, a.st, a.z, a.m, a.p, a.mean_out, a.ws, n_quads, qpi, a.HW, a.inv_norm,
                                  a.smooth, 1.0 / (static_cast<double>(a.B) * a.HW));
   count_launch(); return check_launch("entropy_fwd_vec4");
 }
@@ -386,7 +390,7 @@ template <int ACT, int C, bool GM, bool GP, bool FAST>
 int launch_bwd_vec4(const BwdArgs& a, int64_t n_quads, int64_t qpi) {
   auto k = entropy_bwd_vec4<ACT, C, GM, GP, FAST>;
   const int grid = grid_for(k, n_quads);
-  k<<<grid, kThreads, 0, a.st>>>(a.z, a.gm, a.gp, a.gmean, a.gz, n_quads, qpi, a.HW, a.inv_norm,
+  PCUDA_LAUNCH(k, grid, kThreads, 0, a.st, a.z, a.gm, a.gp, a.gmean, a.gz, n_quads, qpi, a.HW, a.inv_norm,
                                  a.smooth, static_cast<float>(1.0 / (static_cast<double>(a.B) * a.HW)));
   count_launch(); return check_launch("entropy_bwd_vec4");
 }
@@ -453,7 +457,7 @@ extern "C" int pcuda_entropy_fwd(const float* z, float* m, float* p, float* mean
         const double invc = 1.0 / static_cast<double>(n_pix);
         auto go = [&](auto k) {
           const int grid = grid_for(k, n / 4);
-          k<<<grid, kThreads, 0, f.st>>>(z, m, p, mean_out, f.ws, n / 4, n / 4, n, inv_norm, smooth, invc);
+          PCUDA_LAUNCH(k, grid, kThreads, 0, f.st, z, m, p, mean_out, f.ws, n / 4, n / 4, n, inv_norm, smooth, invc);
           count_launch(); return check_launch("entropy_fwd_vec4(sigmoid)");
         };
         if (wp && wm) return go(entropy_fwd_vec4<PCUDA_ACT_SIGMOID, 1, true, true, F>);
@@ -472,7 +476,7 @@ extern "C" int pcuda_entropy_fwd(const float* z, float* m, float* p, float* mean
   const double invc = 1.0 / static_cast<double>(n_pix);
   auto go = [&](auto k) {
     const int grid = grid_for(k, n_pix);
-    k<<<grid, kThreads, 0, a.st>>>(z, m, p, mean_out, a.ws, n_pix, C, HW, inv_norm, smooth, invc);
+    PCUDA_LAUNCH(k, grid, kThreads, 0, a.st, z, m, p, mean_out, a.ws, n_pix, C, HW, inv_norm, smooth, invc);
     count_launch(); return check_launch("entropy_fwd_generic");
   };
   if (activation == PCUDA_ACT_SOFTMAX)
@@ -501,7 +505,7 @@ extern "C" int pcuda_entropy_bwd(const float* z, const float* grad_m, const floa
         constexpr bool F = decltype(fastc)::value;
         auto go = [&](auto k) {
           const int grid = grid_for(k, n / 4);
-          k<<<grid, kThreads, 0, a.st>>>(z, grad_m, grad_p, grad_mean, grad_z, n / 4, n / 4, n, inv_norm, smooth, invc);
+          PCUDA_LAUNCH(k, grid, kThreads, 0, a.st, z, grad_m, grad_p, grad_mean, grad_z, n / 4, n / 4, n, inv_norm, smooth, invc);
           count_launch(); return check_launch("entropy_bwd_vec4(sigmoid)");
         };
         const bool gm = grad_m != nullptr, gp = grad_p != nullptr;
@@ -519,7 +523,7 @@ extern "C" int pcuda_entropy_bwd(const float* z, const float* grad_m, const floa
   }
   auto go = [&](auto k) {
     const int grid = grid_for(k, n_pix);
-    k<<<grid, kThreads, 0, a.st>>>(z, grad_m, grad_p, grad_mean, grad_z, n_pix, C, HW, inv_norm, smooth, invc);
+    PCUDA_LAUNCH(k, grid, kThreads, 0, a.st, z, grad_m, grad_p, grad_mean, grad_z, n_pix, C, HW, inv_norm, smooth, invc);
     count_launch(); return check_launch("entropy_bwd_generic");
   };
   if (activation == PCUDA_ACT_SOFTMAX)

@@ -21,17 +21,6 @@
 #include "pcuda_common.cuh"
 
 namespace pcuda {
-// fchead.cu: a whole head as one thread-block-cluster launch per direction (small batches)
-bool fc_head_supported(int B, int L, const pcuda_fc_layer_t* layers, int cluster);
-int fc_head_fwd(const float* x, int B, int L, const pcuda_fc_layer_t* layers, int train, float momentum, float eps, int iden_k,
-                int cluster, cudaStream_t st);
-int fc_head_bwd(const float* x, int B, int L, const pcuda_fc_layer_t* layers, int train, const float* grad_out, float* grad_x,
-                int cluster, cudaStream_t st);
-static int head_cluster_size() {
-  const int t = tuning(TUNE_FC_CLUSTER_SIZE);
-  return (t == 1 || t == 2 || t == 4 || t == 8 || t == 16) ? t : 8;
-}
-
 namespace {
 
 constexpr int kCPB = 4;        // output channels per CTA
@@ -54,6 +43,7 @@ struct FcFwdParams {
 
 // dynamic shared memory: Wsm[kCPB][cin] | ys[B][kCPB]
 __global__ void __launch_bounds__(kFcThreads) fc_fwd_kernel(const FcFwdParams p) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   float* Wsm = sm;
   float* ys = sm + kCPB * p.cin;
@@ -179,6 +169,7 @@ struct FcBwdParams {
 
 // dynamic shared memory: dys[B][kCPB]
 __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   float* dys = sm;
   const int c0 = blockIdx.x * kCPB;
@@ -308,6 +299,7 @@ __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p)
 template <int RB, int kPullThreads>
 __global__ void __launch_bounds__(kPullThreads) fc_pull_kernel(const float* __restrict__ dy, const float* __restrict__ W,
                                                               int B, int cin, int cout, float* __restrict__ dx) {
+  pdl_entry();
   extern __shared__ __align__(16) float sm[];   // dys[cout][RB], reused as red[warps][RB][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
@@ -365,6 +357,7 @@ struct BnGroups {
 constexpr int kBnGroupsPerLaunch = 12;        // 12 x 280 bytes of kernel parameters
 struct BnLaunch { BnGroups::G g[kBnGroupsPerLaunch]; };
 __global__ void bn_running_update_group_kernel(const BnLaunch a, int ngroups) {
+  pdl_entry();
   const BnGroups::G& u = a.g[blockIdx.y];
   if (static_cast<int>(blockIdx.y) >= ngroups) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -429,10 +422,6 @@ extern "C" int pcuda_fcstack_fwd(const float* x, int B, int L, const pcuda_fc_la
     PCUDA_REQUIRE(!(layers[l].bn && train) || B > 1, PCUDA_E_SHAPE, "fcstack_fwd: train-mode BatchNorm needs more than 1 row");
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (fc_head_supported(B, L, layers, head_cluster_size())) {
-    const int rc = fc_head_fwd(x, B, L, layers, train, momentum, eps, add_identity_k, head_cluster_size(), st);
-    if (rc != PCUDA_E_UNSUPPORTED) return rc;
-  }
   smem_optin(fc_fwd_kernel, 160 * 1024);
   const float* in = x;
   for (int l = 0; l < L; ++l) {
@@ -446,7 +435,7 @@ extern "C" int pcuda_fcstack_fwd(const float* x, int B, int L, const pcuda_fc_la
     p.momentum = momentum; p.eps = eps;
     const size_t smem = sizeof(float) * (static_cast<size_t>(kCPB) * y.cin + static_cast<size_t>(B) * kCPB);
     PCUDA_REQUIRE(smem <= 160 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_fwd: layer %d does not fit shared memory", l);
-    fc_fwd_kernel<<<(y.cout + kCPB - 1) / kCPB, kFcThreads, smem, st>>>(p);
+    PCUDA_LAUNCH(fc_fwd_kernel, (y.cout + kCPB - 1) / kCPB, kFcThreads, smem, st, p);
     in = y.a;
   }
   count_launch(L);
@@ -458,10 +447,7 @@ extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_la
   if (int rc = validate_fc("fcstack_bwd", B, L, layers)) return rc;
   PCUDA_REQUIRE(x && grad_out && ws, PCUDA_E_NULL, "fcstack_bwd: NULL x/grad_out/ws");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (aligned16(x) && fc_head_supported(B, L, layers, head_cluster_size())) {
-    const int rc = fc_head_bwd(x, B, L, layers, train, grad_out, grad_x, head_cluster_size(), st);
-    if (rc != PCUDA_E_UNSUPPORTED) return rc;
-  }
+
   size_t mx = 0;
   for (int l = 0; l < L; ++l) mx = mx > static_cast<size_t>(layers[l].cout) ? mx : static_cast<size_t>(layers[l].cout);
   float* dybuf[2] = {static_cast<float*>(ws), static_cast<float*>(ws) + static_cast<size_t>(B) * mx};
@@ -477,7 +463,7 @@ extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_la
     p.grad_weight = y.grad_weight; p.grad_bias = y.grad_weight ? y.grad_bias : nullptr;
     p.grad_gamma = y.grad_weight ? y.grad_gamma : nullptr; p.grad_beta = y.grad_weight ? y.grad_beta : nullptr;
     p.B = B; p.cin = y.cin; p.cout = y.cout; p.relu = y.relu; p.train = train;
-    fc_bwd_kernel<<<(y.cout + kCPB - 1) / kCPB, kFcThreads, sizeof(float) * static_cast<size_t>(B) * kCPB, st>>>(p);
+    PCUDA_LAUNCH(fc_bwd_kernel, (y.cout + kCPB - 1) / kCPB, kFcThreads, sizeof(float) * static_cast<size_t>(B) * kCPB, st, p);
     ++launches;
     cur ^= 1;
   }
@@ -491,8 +477,8 @@ extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_la
     PCUDA_REQUIRE(smem <= 160 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_bwd: first layer too wide for the input-gradient kernel");
     smem_optin(fc_pull_kernel<32, 512>, 160 * 1024);
     smem_optin(fc_pull_kernel<16, 1024>, 160 * 1024);
-    if (rb == 32) fc_pull_kernel<32, 512><<<(y.cin + 31) / 32, 512, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
-    else fc_pull_kernel<16, 1024><<<(y.cin + 31) / 32, 1024, smem, st>>>(dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
+    if (rb == 32) PCUDA_LAUNCH((fc_pull_kernel<32, 512>), (y.cin + 31) / 32, 512, smem, st, dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
+    else PCUDA_LAUNCH((fc_pull_kernel<16, 1024>), (y.cin + 31) / 32, 1024, smem, st, dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
     ++launches;
   }
   count_launch(launches);
@@ -532,7 +518,7 @@ extern "C" int pcuda_bn_running_update(int n, const pcuda_bn_update_t* items, pc
     int maxc = 0;
     const int cnt = ng - g0 < kBnGroupsPerLaunch ? ng - g0 : kBnGroupsPerLaunch;
     for (int k = 0; k < cnt; ++k) { a.g[k] = gs.g[g0 + k]; maxc = maxc > a.g[k].C ? maxc : a.g[k].C; }
-    bn_running_update_group_kernel<<<dim3((maxc + 255) / 256, cnt), 256, 0, st>>>(a, cnt);
+    PCUDA_LAUNCH(bn_running_update_group_kernel, dim3((maxc + 255) / 256, cnt), 256, 0, st, a, cnt);
     ++launches;
   }
   count_launch(launches);

@@ -42,6 +42,7 @@ __device__ __forceinline__ int find_slot(const Table& t, int cta) {
 }
 
 __global__ void __launch_bounds__(kThreads) grad_sum_pack_kernel(const __grid_constant__ Table t, float scale, float* __restrict__ flat) {
+  pdl_entry();
   const int i = find_slot(t, blockIdx.x);
   const Slot& s = t.s[i];
   const long long base = static_cast<long long>(blockIdx.x - t.cta_start[i]) * kChunk;
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(kThreads) grad_sum_pack_kernel(const __grid_co
 __global__ void __launch_bounds__(kThreads) sgd_momentum_kernel(const __grid_constant__ Table t, const float* __restrict__ flat_grad,
                                                                 float* __restrict__ flat_mom, const float* __restrict__ lr_dev,
                                                                 float momentum, float weight_decay) {
+  pdl_entry();
   const int i = find_slot(t, blockIdx.x);
   const Slot& s = t.s[i];
   const float lr = __ldg(lr_dev);
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(kThreads) sgd_momentum_kernel(const __grid_con
 // (train_mscmrseg.py:290-296,:320-322).  n is the batch (<= a few hundred): one warp, fixed-order sums.
 __global__ void __launch_bounds__(32) bce_logits_kernel(const float* __restrict__ x, int n, float t, float weight,
                                                         float* __restrict__ loss, float* __restrict__ grad, float* __restrict__ acc) {
+  pdl_entry();
   double ls = 0.0;
   int hits = 0;
   for (int i = threadIdx.x; i < n; i += 32) {
@@ -138,7 +141,7 @@ extern "C" int pcuda_grad_sum_pack(const pcuda_param_slot_t* slots, int n, float
   PCUDA_REQUIRE(slots && flat, PCUDA_E_NULL, "grad_sum_pack: NULL argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return for_each_table(slots, n, "grad_sum_pack", false, [&](const Table& t, int ctas) {
-    grad_sum_pack_kernel<<<ctas, kThreads, 0, st>>>(t, scale, flat);
+    PCUDA_LAUNCH(grad_sum_pack_kernel, ctas, kThreads, 0, st, t, scale, flat);
   });
 }
 
@@ -149,7 +152,7 @@ extern "C" int pcuda_sgd_momentum_step(const pcuda_param_slot_t* slots, int n, c
   PCUDA_REQUIRE(slots && flat_grad && flat_momentum && lr_dev, PCUDA_E_NULL, "sgd_momentum_step: NULL argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return for_each_table(slots, n, "sgd_momentum_step", true, [&](const Table& t, int ctas) {
-    sgd_momentum_kernel<<<ctas, kThreads, 0, st>>>(t, flat_grad, flat_momentum, lr_dev, momentum, weight_decay);
+    PCUDA_LAUNCH(sgd_momentum_kernel, ctas, kThreads, 0, st, t, flat_grad, flat_momentum, lr_dev, momentum, weight_decay);
   });
 }
 
@@ -157,7 +160,7 @@ extern "C" int pcuda_bce_logits(const float* logit, int n, float target, float w
                                 float* accuracy, pcuda_stream_t stream) {
   PCUDA_REQUIRE(n >= 1, PCUDA_E_SHAPE, "bce_logits: n=%d", n);
   PCUDA_REQUIRE(logit && loss, PCUDA_E_NULL, "bce_logits: NULL argument");
-  bce_logits_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(logit, n, target, weight, loss, grad_logit, accuracy);
+  PCUDA_LAUNCH(bce_logits_kernel, 1, 32, 0, static_cast<cudaStream_t>(stream), logit, n, target, weight, loss, grad_logit, accuracy);
   count_launch(1);
   return check_launch("bce_logits");
 }

@@ -25,7 +25,50 @@ static inline cudaError_t smem_optin(F* fn, int bytes) {
   return smem_optin_impl(reinterpret_cast<const void*>(fn), bytes);
 }
 
-enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_FP32 = 2, TUNE_MLP_TC_MASK = 3, TUNE_MLP_EPI_DEBUG = 4, TUNE_CHAMFER_SEED = 5, TUNE_MLP_NO_FORK = 6, TUNE_COMM_BLOCKS = 7, TUNE_FC_NO_CLUSTER = 8, TUNE_FC_CLUSTER_SIZE = 9, TUNE_NKEYS = 12 };
+enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_FP32 = 2, TUNE_MLP_TC_MASK = 3, TUNE_MLP_EPI_DEBUG = 4, TUNE_CHAMFER_SEED = 5, TUNE_MLP_NO_FORK = 6, TUNE_COMM_BLOCKS = 7, TUNE_NO_PDL = 8, TUNE_NKEYS = 12 };
+
+// ---- programmatic dependent launch -----------------------------------------------------------------
+// The hot path at the reference's shapes is a chain of ~70 dependent launches of 3-20 us per D4 pass: what a step
+// costs is launch-to-launch latency, not work.  Every libpcuda kernel therefore starts with pdl_entry() —
+// `griddepcontrol.launch_dependents` (the next kernel of the stream may be scheduled as soon as all CTAs of this one
+// are resident) followed by `griddepcontrol.wait` (block until the preceding kernel has completed and its writes
+// are visible) — and is launched through launch_k() with the programmatic-stream-serialisation attribute: ordering
+// and visibility are exactly those of ordinary stream order, but the dependent's launch latency (block scheduling,
+// parameter fetch, prologue that does not touch the predecessor's output) overlaps the predecessor's tail.  A kernel
+// that is launched without the attribute executes both instructions as no-ops.  Under stream capture the edges become
+// programmatic dependency edges of the CUDA graph.  pcuda_tune(8, 1) launches without the attribute (A/B).
+__device__ __forceinline__ void pdl_trigger() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_entry() {
+  pdl_trigger();
+  pdl_wait();
+}
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tuning(TUNE_NO_PDL) ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// PCUDA_LAUNCH((kernel<T...>), grid, block, smem, stream, args...): parenthesise kernel names that contain commas
+#define PCUDA_LAUNCH(kernel, grid, block, smem, st, ...) \
+  (void)::pcuda::launch_k(kernel, dim3(grid), dim3(block), static_cast<size_t>(smem), st, __VA_ARGS__)
 
 #define PCUDA_REQUIRE(cond, code, ...)                 \
   do {                                                 \

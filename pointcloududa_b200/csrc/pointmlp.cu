@@ -82,6 +82,7 @@ mlp_fwd_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
                int N, int tiles_per_sample, float* __restrict__ y_out, double* __restrict__ stats,
                const float* __restrict__ pivot, const float* __restrict__ gamma,
                unsigned long long* __restrict__ keys) {
+  pdl_entry();
   __shared__ Tiles t;
   __shared__ unsigned long long skey[TN];
   const int b = blockIdx.x / tiles_per_sample;
@@ -213,6 +214,7 @@ template <int KN>
 __global__ void __launch_bounds__(kNarrowThreads)
 mlp_fwd_narrow_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias, int Cout, int64_t M,
                       float* __restrict__ y_out, double* __restrict__ stats, float* __restrict__ pivot) {
+  pdl_entry();
   __shared__ float red[kNarrowThreads / 16][2][64];   // up to 16 channel groups... sized below by cgroups <= 16... see launch
   const int K = src.C;
   const int cgroups = Cout >> 2;                       // <= 64 (Cout <= 256): thread = (point slot, channel group)
@@ -280,6 +282,7 @@ mlp_fwd_narrow_kernel(ActSrc src, const float* __restrict__ W, const float* __re
 template <int KN>
 __global__ void __launch_bounds__(kNarrowThreads)
 wgrad_narrow_kernel(DySrc dys, ActSrc aprev, int64_t M, float* __restrict__ partial) {
+  pdl_entry();
   extern __shared__ float red_w[];     // [pslots][C][K]
   const int C = dys.C, K = aprev.C;
   const int tpp = C >> 2, pslots = kNarrowThreads / tpp;
@@ -324,6 +327,7 @@ wgrad_narrow_kernel(DySrc dys, ActSrc aprev, int64_t M, float* __restrict__ part
 template <int KN>
 __global__ void __launch_bounds__(kNarrowThreads)
 dgrad_input_narrow_kernel(DySrc dys, const float* __restrict__ W, int K, int N, int64_t M, float* __restrict__ grad_x) {
+  pdl_entry();
   const int C = dys.C;
   const int tpp = C >> 2, pslots = kNarrowThreads / tpp;
   const int cg = threadIdx.x % tpp, ps = threadIdx.x / tpp;
@@ -365,6 +369,7 @@ dgrad_input_narrow_kernel(DySrc dys, const float* __restrict__ W, int K, int N, 
 __global__ void __launch_bounds__(256)
 input_transform_bwd_kernel(const float* __restrict__ x, int64_t sxb, int64_t sxc, int64_t sxn, const float* __restrict__ T,
                            const float* __restrict__ g, int C, int N, float* __restrict__ grad_x, float* __restrict__ grad_T) {
+  pdl_entry();
   __shared__ double red[8][16];
   const int b = blockIdx.x;
   const float* Tb = T + static_cast<int64_t>(b) * C * C;
@@ -434,6 +439,7 @@ bn_finalize_pivot_kernel(const double* __restrict__ stats, const float* __restri
                          float* __restrict__ save_invstd, float* __restrict__ running_mean,
                          float* __restrict__ running_var, ActSrc src_next, const float* __restrict__ W_next,
                          const float* __restrict__ bias_next, int C_next, float* __restrict__ pivot_next) {
+  pdl_entry();
   if (stats != nullptr) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       if (train) {
@@ -471,6 +477,7 @@ __global__ void pool_finalize_kernel(const unsigned long long* __restrict__ keys
                                      const float* __restrict__ invstd, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, int relu, int B, int C,
                                      float* __restrict__ out, int32_t* __restrict__ arg, BnRaw raw) {
+  pdl_entry();
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<int64_t>(B) * C) return;
   const int c = static_cast<int>(i % C);
@@ -488,6 +495,7 @@ __global__ void pool_finalize_kernel(const unsigned long long* __restrict__ keys
 
 // dense output (pool == 0): out[b, c, n] = act(y[(b,n), c]); 32x32 smem transpose
 __global__ void dense_out_kernel(ActSrc src, int B, float* __restrict__ out) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int N = src.N, C = src.C;
   const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -509,6 +517,7 @@ __global__ void pool_sel_kernel(ActSrc src, const float* __restrict__ W, const f
                                 const float* __restrict__ gamma, int relu, const float* __restrict__ out,
                                 const int32_t* __restrict__ arg, const float* __restrict__ grad_out, int B, int N,
                                 int C, float* __restrict__ coef, float* __restrict__ gsel, float* __restrict__ gyh) {
+  pdl_entry();
   const int64_t w = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= static_cast<int64_t>(B) * C) return;
@@ -538,6 +547,7 @@ __global__ void pool_coef_kernel(const float* __restrict__ gsel, const float* __
                                  double count, int train, float* __restrict__ alpha, float* __restrict__ kappa,
                                  float* __restrict__ grad_gamma, float* __restrict__ grad_beta,
                                  float* __restrict__ grad_bias) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double dbeta = 0.0, dgamma = 0.0;
@@ -557,6 +567,7 @@ __global__ void pool_coef_kernel(const float* __restrict__ gsel, const float* __
 // grid (S, ceil(K/32)), 256 threads: lane = channel, the 8 warps interleave the rows of the slice
 __global__ void __launch_bounds__(256)
 act_colsum_kernel(ActSrc src, int64_t M, int64_t chunk, double* __restrict__ partial) {
+  pdl_entry();
   __shared__ double part[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.y * 32 + lane;
@@ -605,6 +616,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 point_contract_kernel(DySrc dys, ActSrc pact, ActSrc ract, int64_t M, int64_t chunk, int CR, int CC,
                       float* __restrict__ partial) {
+  pdl_entry();
   __shared__ Tiles t;
   const int r0 = blockIdx.y * TM, c0 = blockIdx.z * TN;
   const int64_t m0 = blockIdx.x * chunk;
@@ -645,6 +657,7 @@ point_contract_kernel(DySrc dys, ActSrc pact, ActSrc ract, int64_t M, int64_t ch
 // out[i] = scale * sum_s partial[s, i]  (fixed order, double accumulation)
 template <typename TOut>
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int64_t n, int S, TOut* __restrict__ out) {
+  pdl_entry();
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
@@ -657,6 +670,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int64_
 __global__ void __launch_bounds__(256)
 abar_kernel(const double* __restrict__ colsum_partial, int S, int K, double count, float* __restrict__ abar,
             double* __restrict__ abar_d) {
+  pdl_entry();
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (k >= K) return;
   double a = 0.0;
@@ -672,6 +686,7 @@ abar_kernel(const double* __restrict__ colsum_partial, int S, int K, double coun
 // Ghat[k,k'] = G[k,k'] - M abar_k abar_k'
 __global__ void gram_center_kernel(const double* __restrict__ abar_d, const double* __restrict__ G, int K,
                                    double count, float* __restrict__ Ghat) {
+  pdl_entry();
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<int64_t>(K) * K) return;
   const int k = static_cast<int>(i / K), k2 = static_cast<int>(i % K);
@@ -684,6 +699,7 @@ __global__ void gram_center_kernel(const double* __restrict__ abar_d, const doub
 constexpr int kPoolQSplits = 8;
 __global__ void __launch_bounds__(256)
 pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, int C, int K, float* __restrict__ partial) {
+  pdl_entry();
   __shared__ float Wa[32][33], Wb[32][33];
   const int k0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
   const int per = (C + gridDim.z - 1) / gridDim.z;
@@ -727,6 +743,7 @@ pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, int 
 __global__ void __launch_bounds__(1024)
 pool_u_kernel(const float* __restrict__ W, const float* __restrict__ alpha, const float* __restrict__ Q,
               const float* __restrict__ abar, int C, int K, float* __restrict__ u) {
+  pdl_entry();
   __shared__ double part[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
@@ -774,6 +791,7 @@ template <int KPL, int IF, int MINB>
 __global__ void __launch_bounds__(512, MINB)
 pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ coef, const float* __restrict__ W,
                    int C, int N, int K, DgradOut o) {
+  pdl_entry();
   constexpr int kSparseInFlight = IF;
   extern __shared__ int sm_i[];
   const int nchunk = (C + 31) >> 5;
@@ -988,6 +1006,7 @@ pool_dw_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
                const int32_t* __restrict__ arg, const float* __restrict__ kappa,
                const float* __restrict__ abar, const float* __restrict__ Ghat, int B, int N,
                int C, int train, float* __restrict__ dW) {
+  pdl_entry();
   // dynamic smem: wrow[kDwCh][K] | sel_cf[B][kDwCh] | sel_m[B][kDwCh] | red[kDwParts][128][kDwCh] doubles
   extern __shared__ __align__(16) float wrow[];
   const int K = src.C;
@@ -1125,6 +1144,7 @@ __global__ void __launch_bounds__(kThreads)
 pool_dgrad_kernel(ActSrc src, const float* __restrict__ Q, const float* __restrict__ u, const float* __restrict__ W,
                   const float* __restrict__ coef, const int32_t* __restrict__ arg, int C, int N,
                   int tiles_per_sample, DgradOut o) {
+  pdl_entry();
   __shared__ Tiles t;
   __shared__ float ssum[16 * TN], ssq[16 * TN];
   __shared__ float sparse[TM][TN + 1];
@@ -1178,6 +1198,7 @@ pool_dgrad_kernel(ActSrc src, const float* __restrict__ Q, const float* __restri
 // dense layer dgrad: da_prev[m,k] = sum_c dy[m,c] W[c,k]
 __global__ void __launch_bounds__(kThreads)
 dense_dgrad_kernel(DySrc dys, const float* __restrict__ W, int N, int tiles_per_sample, DgradOut o) {
+  pdl_entry();
   __shared__ Tiles t;
   __shared__ float ssum[16 * TN], ssq[16 * TN];
   const int C = dys.C, Kp = o.Cp;
@@ -1213,6 +1234,7 @@ __global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, const float*
                                    float* __restrict__ alpha, float* __restrict__ kappa,
                                    float* __restrict__ grad_gamma, float* __restrict__ grad_beta,
                                    float* __restrict__ grad_bias) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double dbeta = sums[c], dgamma = sums[C + c];
@@ -1230,6 +1252,7 @@ __global__ void dense_top_kernel(const float* __restrict__ grad_out, const float
                                  const float* __restrict__ mean, const float* __restrict__ invstd,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                                  int N, int C, float* __restrict__ dz, double* __restrict__ sums) {
+  pdl_entry();
   __shared__ float tile[32][33];
   __shared__ float ssum[8 * 32], ssq[8 * 32];   // launched with blockDim (32, 8)
   const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -1561,7 +1584,7 @@ static int pointmlp_fwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
   };
   if (!layer_tc(0) && !layer_narrow(0)) {
     // pivot of layer 0 (no BN to finalise yet; the narrow-layer kernel publishes its own pivot)
-    bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, 0, 1.0, eps, momentum, train, nullptr, nullptr, nullptr, nullptr,
+    PCUDA_LAUNCH(bn_finalize_pivot_kernel, 1, 1024, 0, st, nullptr, nullptr, 0, 1.0, eps, momentum, train, nullptr, nullptr, nullptr, nullptr,
                                                  input_src(x, sxb, sxc, sxn, N, layers[0].cin, in_trans), layers[0].weight, layers[0].bias,
                                                  layers[0].cout, piv_l);
     launches += 1;
@@ -1581,15 +1604,15 @@ static int pointmlp_fwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       if (int rc = tc::fwd_layer(tl, w.apack[l], w.wpack[l], y, is_pool, st_l, w.keys, st)) return rc;
       pivot_used = y.bias ? y.bias : w.zeros;
     } else if (layer_narrow(l)) {
-      if (y.cin <= 4) mlp_fwd_narrow_kernel<4><<<narrow_grid(s.M, y.cout), kNarrowThreads, 0, st>>>(src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
-      else mlp_fwd_narrow_kernel<8><<<narrow_grid(s.M, y.cout), kNarrowThreads, 0, st>>>(src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
+      if (y.cin <= 4) PCUDA_LAUNCH(mlp_fwd_narrow_kernel<4>, narrow_grid(s.M, y.cout), kNarrowThreads, 0, st, src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
+      else PCUDA_LAUNCH(mlp_fwd_narrow_kernel<8>, narrow_grid(s.M, y.cout), kNarrowThreads, 0, st, src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
       launches += 1;
     } else {
       const dim3 grid(B * tps, (y.cout + TN - 1) / TN);
       if (is_pool)
-        mlp_fwd_kernel<true><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, w.keys);
+        PCUDA_LAUNCH(mlp_fwd_kernel<true>, grid, kThreads, 0, st, src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, w.keys);
       else
-        mlp_fwd_kernel<false><<<grid, kThreads, 0, st>>>(src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, nullptr);
+        PCUDA_LAUNCH(mlp_fwd_kernel<false>, grid, kThreads, 0, st, src, y.weight, y.bias, y.cout, N, tps, y.y, st_l, piv_l, y.gamma, nullptr);
       launches += 1;
     }
     // finalise this layer's BN.  When the only consumer of its output is the operand packer of a tensor-core
@@ -1602,7 +1625,7 @@ static int pointmlp_fwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       raw_prev = BnRaw{st_l, pivot_used, static_cast<double>(s.M), eps, momentum, train, y.save_mean, y.save_invstd,
                        y.running_mean, y.running_var};
     } else {
-      bn_finalize_pivot_kernel<<<1, 1024, 0, st>>>(st_l, pivot_used, y.cout, static_cast<double>(s.M), eps, momentum, train,
+      PCUDA_LAUNCH(bn_finalize_pivot_kernel, 1, 1024, 0, st, st_l, pivot_used, y.cout, static_cast<double>(s.M), eps, momentum, train,
                                                    y.save_mean, y.save_invstd, y.running_mean, y.running_var,
                                                    next_piv ? layer_src(y, N) : ActSrc{}, next_piv ? layers[l + 1].weight : nullptr,
                                                    next_piv ? layers[l + 1].bias : nullptr, next_piv ? layers[l + 1].cout : 0,
@@ -1615,11 +1638,11 @@ static int pointmlp_fwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
   const pcuda_mlp_layer_t& last = layers[L - 1];
   if (pool) {
     const int64_t n = static_cast<int64_t>(B) * s.Clast;
-    pool_finalize_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(w.keys, last.save_mean, last.save_invstd, last.gamma,
+    PCUDA_LAUNCH(pool_finalize_kernel, static_cast<int>((n + 255) / 256), 256, 0, st, w.keys, last.save_mean, last.save_invstd, last.gamma,
                                                                             last.beta, last.relu, B, s.Clast, out, pool_arg, raw_prev);
   } else {
     const dim3 grid((N + 31) / 32, (s.Clast + 31) / 32, B);
-    dense_out_kernel<<<grid, dim3(32, 8), 0, st>>>(layer_src(last, N), B, out);
+    PCUDA_LAUNCH(dense_out_kernel, grid, dim3(32, 8), 0, st, layer_src(last, N), B, out);
   }
   count_launch(launches + 1);
   return check_launch("pointmlp_fwd");
@@ -1727,28 +1750,28 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
     if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sa, ax->fork, 0); aux_used = true; }
     // -- Gram side: centred Gram matrix of the pooled layer's input (train-mode BN correction terms only)
     int Sg = S32;
-    act_colsum_kernel<<<dim3(S32, (K + 31) / 32), 256, 0, sa>>>(src, s.M, chunk32, w.colsum);
+    PCUDA_LAUNCH(act_colsum_kernel, dim3(S32, (K + 31) / 32), 256, 0, sa, src, s.M, chunk32, w.colsum);
     launches += 1;
     if (tc_on(precision, TC_GRAM) && a_in && tc::pt_supports(K, K, true)) {
       Sg = tc::pt_splits(tl, (K + 127) / 128);
       if (int rc = tc::gram(tl, a_in, K, Sg, partial, sa)) return rc;
     } else {
-      point_contract_kernel<1><<<dim3(S32, (K + TM - 1) / TM, (K + TN - 1) / TN), kThreads, 0, sa>>>(DySrc{}, src, src, s.M, chunk32, K, K, partial);
+      PCUDA_LAUNCH(point_contract_kernel<1>, dim3(S32, (K + TM - 1) / TM, (K + TN - 1) / TN), kThreads, 0, sa, DySrc{}, src, src, s.M, chunk32, K, K, partial);
       launches += 1;
     }
-    reduce_partials_kernel<double><<<static_cast<int>((kk + 255) / 256), 256, 0, sa>>>(partial, kk, Sg, w.G);
-    abar_kernel<<<(K + 7) / 8, 256, 0, sa>>>(w.colsum, S32, K, count, w.abar, w.abar_d);
-    gram_center_kernel<<<static_cast<int>((kk + 255) / 256), 256, 0, sa>>>(w.abar_d, w.G, K, count, w.Ghat);
+    PCUDA_LAUNCH(reduce_partials_kernel<double>, static_cast<int>((kk + 255) / 256), 256, 0, sa, partial, kk, Sg, w.G);
+    PCUDA_LAUNCH(abar_kernel, (K + 7) / 8, 256, 0, sa, w.colsum, S32, K, count, w.abar, w.abar_d);
+    PCUDA_LAUNCH(gram_center_kernel, static_cast<int>((kk + 255) / 256), 256, 0, sa, w.abar_d, w.G, K, count, w.Ghat);
     if (ax) cudaEventRecord(ax->side, sa);
     // -- selection side: per-(cloud, channel) coefficients, alpha / kappa, Q = W^T diag(kappa) W
-    pool_sel_kernel<<<static_cast<int>((bc * 32 + 255) / 256), 256, 0, st>>>(src, last.weight, last.bias, last.save_mean,
+    PCUDA_LAUNCH(pool_sel_kernel, static_cast<int>((bc * 32 + 255) / 256), 256, 0, st, src, last.weight, last.bias, last.save_mean,
                                                                             last.save_invstd, last.gamma, last.relu, out, pool_arg,
                                                                             grad_out, B, N, C, w.coef, w.gsel, w.gyh);
     const bool want_last = last.grad_weight != nullptr;
-    pool_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(w.gsel, w.gyh, last.save_invstd, last.gamma, B, C, count, train, al, ka,
+    PCUDA_LAUNCH(pool_coef_kernel, (C + 127) / 128, 128, 0, st, w.gsel, w.gyh, last.save_invstd, last.gamma, B, C, count, train, al, ka,
                                                       want_last ? last.grad_gamma : nullptr, want_last ? last.grad_beta : nullptr,
                                                       want_last ? last.grad_bias : nullptr);
-    pool_q_kernel<<<dim3((K + 31) / 32, (K + 31) / 32, kPoolQSplits), 256, 0, st>>>(last.weight, ka, C, K, w.qpartial);
+    PCUDA_LAUNCH(pool_q_kernel, dim3((K + 31) / 32, (K + 31) / 32, kPoolQSplits), 256, 0, st, last.weight, ka, C, K, w.qpartial);
     // the low-rank dgrad runs on the tensor cores (decided here: it changes how Q is finished)
     const bool tc_pool = (L >= 2 || grad_x) && tc_on(precision, TC_POOL_DGRAD) && a_in && w.qpack && tc::pool_dgrad_fits(K) &&
                          pool_sparse_smem(C, N, K) <= 200 * 1024 && K <= 512 && C <= 65535;
@@ -1760,10 +1783,10 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       q_packed = true;
       launches += 6;     // reduce<double>, abar, gram_center, pool_sel, pool_coef, pool_q (tc:: calls count themselves)
     } else {
-      reduce_partials_kernel<float><<<static_cast<int>((kk + 255) / 256), 256, 0, st>>>(w.qpartial, kk, kPoolQSplits, w.Q);
+      PCUDA_LAUNCH(reduce_partials_kernel<float>, static_cast<int>((kk + 255) / 256), 256, 0, st, w.qpartial, kk, kPoolQSplits, w.Q);
       // -- join: u needs Q (this stream) and abar (Gram side)
       if (ax) cudaStreamWaitEvent(st, ax->side, 0);
-      pool_u_kernel<<<(K + 31) / 32, 1024, 0, st>>>(last.weight, al, w.Q, w.abar, C, K, w.u);
+      PCUDA_LAUNCH(pool_u_kernel, (K + 31) / 32, 1024, 0, st, last.weight, al, w.Q, w.abar, C, K, w.u);
       launches += 8;
     }
     if (last.grad_weight) {
@@ -1774,7 +1797,7 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       // the pooled layer's weight gradient reads coef / kappa (this stream) and abar / Ghat (Gram side) and writes
       // only grad_weight: it runs on the auxiliary stream beside the dgrad kernels below; joined before returning
       if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sa, ax->fork, 0); }
-      pool_dw_kernel<<<(C + kDwCh - 1) / kDwCh, 128 * kDwParts, dw_smem, sa>>>(src, last.weight, w.coef, pool_arg, ka, w.abar, w.Ghat, B, N, C, train, last.grad_weight);
+      PCUDA_LAUNCH(pool_dw_kernel, (C + kDwCh - 1) / kDwCh, 128 * kDwParts, dw_smem, sa, src, last.weight, w.coef, pool_arg, ka, w.abar, w.Ghat, B, N, C, train, last.grad_weight);
       launches += 1;
     }
     if (L >= 2 || grad_x) {
@@ -1794,19 +1817,19 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
         const bool many_points = K <= 128 && N >= C && sparse_smem <= 100 * 1024;   // ~1 channel per selected point
         const int per_sm = many_points ? 2 : 1;
         const int parts = std::max(1, std::min((std::min(C, N) + 31) / 32, (per_sm * sm_count() + B - 1) / B));
-        if (many_points) pool_sparse_kernel<4, 4, 2><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
-        else if (K <= 128) pool_sparse_kernel<4, 12, 1><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
-        else pool_sparse_kernel<16, 2, 1><<<dim3(B, parts), 512, sparse_smem, st>>>(pool_arg, w.coef, last.weight, C, N, K, o);
+        if (many_points) PCUDA_LAUNCH((pool_sparse_kernel<4, 4, 2>), dim3(B, parts), 512, sparse_smem, st, pool_arg, w.coef, last.weight, C, N, K, o);
+        else if (K <= 128) PCUDA_LAUNCH((pool_sparse_kernel<4, 12, 1>), dim3(B, parts), 512, sparse_smem, st, pool_arg, w.coef, last.weight, C, N, K, o);
+        else PCUDA_LAUNCH((pool_sparse_kernel<16, 2, 1>), dim3(B, parts), 512, sparse_smem, st, pool_arg, w.coef, last.weight, C, N, K, o);
         launches += 1;
       } else {
-        pool_dgrad_kernel<<<dim3(B * tps, (K + TN - 1) / TN), kThreads, 0, st>>>(src, w.Q, w.u, last.weight, w.coef, pool_arg, C, N, tps, o);
+        PCUDA_LAUNCH(pool_dgrad_kernel, dim3(B * tps, (K + TN - 1) / TN), kThreads, 0, st, src, w.Q, w.u, last.weight, w.coef, pool_arg, C, N, tps, o);
         launches += 1;
       }
     }
     top = L - 2;
   } else {
     const int C = last.cout;
-    dense_top_kernel<<<dim3((N + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, st>>>(grad_out, last.y, last.save_mean, last.save_invstd,
+    PCUDA_LAUNCH(dense_top_kernel, dim3((N + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, st, grad_out, last.y, last.save_mean, last.save_invstd,
                                                                                    last.gamma, last.beta, last.relu, N, C,
                                                                                    dzbuf[cur], sums + 2 * off[L - 1]);
     launches += 1;
@@ -1818,7 +1841,7 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
     float* al = alpha + off[l];
     float* ka = kappa + off[l];
     const bool want_w = y.grad_weight != nullptr;
-    bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums + 2 * off[l], y.save_invstd, y.gamma, C, count, train, al, ka,
+    PCUDA_LAUNCH(bn_bwd_coef_kernel, (C + 127) / 128, 128, 0, st, sums + 2 * off[l], y.save_invstd, y.gamma, C, count, train, al, ka,
                                                         want_w ? y.grad_gamma : nullptr, want_w ? y.grad_beta : nullptr,
                                                         want_w ? y.grad_bias : nullptr);
     launches += 1;
@@ -1847,14 +1870,14 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       } else if (narrow_ok(Kp, C)) {
         Sw = std::min(narrow_grid(s.M, C), s.S);
         const size_t smem = sizeof(float) * 1024 * static_cast<size_t>(Kp);   // [pslots][C][Kp], pslots * C = 1024
-        if (Kp <= 4) wgrad_narrow_kernel<4><<<Sw, kNarrowThreads, smem, sw>>>(dys, src_of(l - 1), s.M, partial);
-        else wgrad_narrow_kernel<8><<<Sw, kNarrowThreads, smem, sw>>>(dys, src_of(l - 1), s.M, partial);
+        if (Kp <= 4) PCUDA_LAUNCH(wgrad_narrow_kernel<4>, Sw, kNarrowThreads, smem, sw, dys, src_of(l - 1), s.M, partial);
+        else PCUDA_LAUNCH(wgrad_narrow_kernel<8>, Sw, kNarrowThreads, smem, sw, dys, src_of(l - 1), s.M, partial);
         launches += 1;
       } else {
-        point_contract_kernel<0><<<dim3(S32, (C + TM - 1) / TM, (Kp + TN - 1) / TN), kThreads, 0, sw>>>(dys, ActSrc{}, src_of(l - 1), s.M, chunk32, C, Kp, partial);
+        PCUDA_LAUNCH(point_contract_kernel<0>, dim3(S32, (C + TM - 1) / TM, (Kp + TN - 1) / TN), kThreads, 0, sw, dys, ActSrc{}, src_of(l - 1), s.M, chunk32, C, Kp, partial);
         launches += 1;
       }
-      reduce_partials_kernel<float><<<static_cast<int>((ck + 255) / 256), 256, 0, sw>>>(partial, ck, Sw, y.grad_weight);
+      PCUDA_LAUNCH(reduce_partials_kernel<float>, static_cast<int>((ck + 255) / 256), 256, 0, sw, partial, ck, Sw, y.grad_weight);
       launches += 1;
       if (fork_w) { cudaEventRecord(ax->wdone, sa); wgrad_pending = true; }
     }
@@ -1866,18 +1889,18 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
         const uint8_t* side = dgrad_side ? apack[l] : nullptr;
         if (int rc = tc::dgrad_layer(tl, w.dypack, C, w.wtpack, side, o, st)) return rc;
       } else if (o.grad_x != nullptr && narrow_ok(Kp, C) && C <= 128) {
-        if (Kp <= 4) dgrad_input_narrow_kernel<4><<<narrow_grid(s.M, C), kNarrowThreads, 0, st>>>(dys, y.weight, Kp, N, s.M, o.grad_x);
-        else dgrad_input_narrow_kernel<8><<<narrow_grid(s.M, C), kNarrowThreads, 0, st>>>(dys, y.weight, Kp, N, s.M, o.grad_x);
+        if (Kp <= 4) PCUDA_LAUNCH(dgrad_input_narrow_kernel<4>, narrow_grid(s.M, C), kNarrowThreads, 0, st, dys, y.weight, Kp, N, s.M, o.grad_x);
+        else PCUDA_LAUNCH(dgrad_input_narrow_kernel<8>, narrow_grid(s.M, C), kNarrowThreads, 0, st, dys, y.weight, Kp, N, s.M, o.grad_x);
         launches += 1;
       } else {
-        dense_dgrad_kernel<<<dim3(B * tps, (Kp + TN - 1) / TN), kThreads, 0, st>>>(dys, y.weight, N, tps, o);
+        PCUDA_LAUNCH(dense_dgrad_kernel, dim3(B * tps, (Kp + TN - 1) / TN), kThreads, 0, st, dys, y.weight, N, tps, o);
         launches += 1;
       }
       cur ^= 1;
     }
   }
   if (in_trans != nullptr && want_gx) {
-    input_transform_bwd_kernel<<<B, 256, 0, st>>>(x, sxb, sxc, sxn, in_trans, w.dxp, layers[0].cin, N, grad_x, grad_trans);
+    PCUDA_LAUNCH(input_transform_bwd_kernel, B, 256, 0, st, x, sxb, sxc, sxn, in_trans, w.dxp, layers[0].cin, N, grad_x, grad_trans);
     launches += 1;
   }
   joiner.join();    // the pooled weight gradient / the last weight-gradient chain

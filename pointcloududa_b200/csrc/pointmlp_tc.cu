@@ -76,6 +76,7 @@ __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
 // a = relu?(y * p0 + p1)  (or the raw network input), p0 = invstd*gamma, p1 = beta - mean*p0
 // one thread = one 16-byte chunk (8 channels of one point)
 __global__ void __launch_bounds__(256) pack_act_kernel(ActSrc src, Tiling tl, uint8_t* __restrict__ out, BnRaw raw) {
+  pdl_entry();
   __shared__ PackConsts pc;
   const int C = src.C;
   for (int k = threadIdx.x; k < C; k += blockDim.x) {
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(256) pack_act_kernel(ActSrc src, Tiling tl, ui
 
 // dy = dz * p0 + (y * p1 + p2),  p0 = gamma*invstd, p1 = -kappa, p2 = kappa*mean - alpha
 __global__ void __launch_bounds__(256) pack_dy_kernel(DySrc dys, Tiling tl, uint8_t* __restrict__ out) {
+  pdl_entry();
   __shared__ PackConsts pc;
   const int C = dys.C;
   for (int k = threadIdx.x; k < C; k += blockDim.x) {
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(256) pack_dy_kernel(DySrc dys, Tiling tl, uint
 // layer tracks max_n sign(gamma) * y).
 __global__ void __launch_bounds__(256) pack_w_kernel(const float* __restrict__ W, int R, int K, int transposed,
                                                      const float* __restrict__ sign_src, uint8_t* __restrict__ out) {
+  pdl_entry();
   const int rblocks = (R + 127) / 128;
   const int64_t total = static_cast<int64_t>(rblocks) * 128 * (K >> 3);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -213,6 +216,7 @@ __global__ void __launch_bounds__(1024) q_finish_kernel(const float* __restrict_
                                                         const float* __restrict__ alpha, const float* __restrict__ abar,
                                                         int C, int K, float* __restrict__ Q, uint8_t* __restrict__ qpack,
                                                         float* __restrict__ u) {
+  pdl_entry();
   __shared__ double part[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r0 = blockIdx.x * 32;
@@ -310,6 +314,7 @@ __device__ __forceinline__ float bf16_at(const uint8_t* slab, int row, int ch) {
 
 template <int MODE>
 __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsParams p) {
+  pdl_entry();
   constexpr int kEpiWarps = WsCfg<MODE>::kEpiWarps, kSub = WsCfg<MODE>::kSub;
   constexpr int kMmaWarp = WsCfg<MODE>::kMmaWarp, kProdWarp = WsCfg<MODE>::kProdWarp;
   extern __shared__ uint8_t smem_raw[];
@@ -673,6 +678,7 @@ struct __align__(8) PtBarriers {
 };
 
 __global__ void __launch_bounds__(kPtThreads, 1) pt_kernel(const PtParams p) {
+  pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int GR = p.Kr >> 6;                       // slabs per tile of R
@@ -809,7 +815,7 @@ int launch_ws(WsParams& p, cudaStream_t st, const char* what) {
     cudaError_t e = smem_optin(ws_kernel<MODE>, static_cast<int>(kSmemBudget));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
   }
-  ws_kernel<MODE><<<pl.grid, WsCfg<MODE>::kThreads, pl.smem, st>>>(p);
+  PCUDA_LAUNCH(ws_kernel<MODE>, pl.grid, WsCfg<MODE>::kThreads, pl.smem, st, p);
   count_launch();
   return check_launch(what);
 }
@@ -839,17 +845,17 @@ size_t act_pack_bytes(const Tiling& tl, int C) { return static_cast<size_t>(tl.n
 size_t w_pack_bytes(int R, int K) { return static_cast<size_t>((R + 127) / 128) * K * 256; }
 
 int pack_act(const ActSrc& src, const Tiling& tl, uint8_t* out, cudaStream_t st, const BnRaw* raw) {
-  pack_act_kernel<<<pack_grid(static_cast<int64_t>(tl.n_tiles) * kNT * (src.C / 8)), 256, 0, st>>>(src, tl, out, raw ? *raw : BnRaw{});
+  PCUDA_LAUNCH(pack_act_kernel, pack_grid(static_cast<int64_t>(tl.n_tiles) * kNT * (src.C / 8)), 256, 0, st, src, tl, out, raw ? *raw : BnRaw{});
   count_launch();
   return check_launch("tc::pack_act");
 }
 int pack_dy(const DySrc& dys, const Tiling& tl, uint8_t* out, cudaStream_t st) {
-  pack_dy_kernel<<<pack_grid(static_cast<int64_t>(tl.n_tiles) * kNT * (dys.C / 8)), 256, 0, st>>>(dys, tl, out);
+  PCUDA_LAUNCH(pack_dy_kernel, pack_grid(static_cast<int64_t>(tl.n_tiles) * kNT * (dys.C / 8)), 256, 0, st, dys, tl, out);
   count_launch();
   return check_launch("tc::pack_dy");
 }
 int pack_w(const float* W, int R, int K, bool transposed, uint8_t* out, cudaStream_t st, const float* sign_src) {
-  pack_w_kernel<<<pack_grid(static_cast<int64_t>((R + 127) / 128) * 128 * (K / 8)), 256, 0, st>>>(W, R, K, transposed ? 1 : 0,
+  PCUDA_LAUNCH(pack_w_kernel, pack_grid(static_cast<int64_t>((R + 127) / 128) * 128 * (K / 8)), 256, 0, st, W, R, K, transposed ? 1 : 0,
                                                                                                    transposed ? nullptr : sign_src, out);
   count_launch();
   return check_launch("tc::pack_w");
@@ -858,7 +864,7 @@ int pack_w(const float* W, int R, int K, bool transposed, uint8_t* out, cudaStre
 int q_finish(const float* partial, int S, const float* W, const float* alpha, const float* abar, int C, int K, float* Q,
              uint8_t* qpack, float* u, cudaStream_t st) {
   if ((K & 7) != 0) return fail(PCUDA_E_UNSUPPORTED, "tc::q_finish: K=%d is not a multiple of 8", K);
-  q_finish_kernel<<<((K + 127) / 128) * 4, 1024, 0, st>>>(partial, S, W, alpha, abar, C, K, Q, qpack, u);
+  PCUDA_LAUNCH(q_finish_kernel, ((K + 127) / 128) * 4, 1024, 0, st, partial, S, W, alpha, abar, C, K, Q, qpack, u);
   count_launch();
   return check_launch("tc::q_finish");
 }
@@ -910,7 +916,7 @@ static int launch_pt(PtParams& p, cudaStream_t st, const char* what) {
     if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
   }
   const dim3 grid(p.S, (p.C + 127) / 128);
-  pt_kernel<<<grid, kPtThreads, fixed + p.nstage * stage, st>>>(p);
+  PCUDA_LAUNCH(pt_kernel, grid, kPtThreads, fixed + p.nstage * stage, st, p);
   count_launch();
   return check_launch(what);
 }

@@ -20,6 +20,7 @@ template <bool TRANSPOSED>
 __global__ void __launch_bounds__(kPtThreads)
 point_transform_kernel(const float* __restrict__ x, int64_t sxb, int64_t sxc, int64_t sxn, const float* __restrict__ T,
                        int K, int N, float* __restrict__ out) {
+  pdl_entry();
   __shared__ __align__(16) float sT[kMaxK * kMaxK];          // sT[i * kMaxK + o]: input channel i -> output channel o
   const int b = blockIdx.y;
   const float* Tb = T + static_cast<int64_t>(b) * K * K;
@@ -58,6 +59,7 @@ point_transform_kernel(const float* __restrict__ x, int64_t sxb, int64_t sxc, in
 __global__ void __launch_bounds__(256)
 transform_wgrad_kernel(const float* __restrict__ x, int64_t sxb, int64_t sxc, int64_t sxn, const float* __restrict__ g,
                        int K, int N, int chunk, float* __restrict__ partial) {
+  pdl_entry();
   __shared__ float xs[32][kMaxK + 4], gs[32][kMaxK + 4];
   const int b = blockIdx.y, s = blockIdx.x;
   const int n0 = s * chunk, n1 = min(N, n0 + chunk);
@@ -95,6 +97,7 @@ transform_wgrad_kernel(const float* __restrict__ x, int64_t sxb, int64_t sxc, in
 }
 
 __global__ void transform_wgrad_reduce_kernel(const float* __restrict__ partial, int64_t n, int S, float* __restrict__ out) {
+  pdl_entry();
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   double t = 0.0;
@@ -120,7 +123,7 @@ extern "C" int pcuda_point_transform_fwd(const float* x, int64_t sxb, int64_t sx
   PCUDA_REQUIRE(K <= kMaxK, PCUDA_E_UNSUPPORTED, "point_transform_fwd: K=%d > %d", K, kMaxK);
   if (B == 0 || N == 0) return 0;
   PCUDA_REQUIRE(x && trans && out, PCUDA_E_NULL, "point_transform_fwd: NULL argument");
-  point_transform_kernel<false><<<dim3((N + kPtThreads - 1) / kPtThreads, B), kPtThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  PCUDA_LAUNCH(point_transform_kernel<false>, dim3((N + kPtThreads - 1) / kPtThreads, B), kPtThreads, 0, static_cast<cudaStream_t>(stream), 
       x, sxb, sxc, sxn, trans, K, N, out);
   count_launch(1);
   return check_launch("point_transform_fwd");
@@ -137,7 +140,7 @@ extern "C" int pcuda_point_transform_bwd(const float* x, int64_t sxb, int64_t sx
   int launches = 0;
   if (grad_x != nullptr) {
     // grad_out is contiguous [B, K, N]
-    point_transform_kernel<true><<<dim3((N + kPtThreads - 1) / kPtThreads, B), kPtThreads, 0, st>>>(
+    PCUDA_LAUNCH(point_transform_kernel<true>, dim3((N + kPtThreads - 1) / kPtThreads, B), kPtThreads, 0, st, 
         grad_out, static_cast<int64_t>(K) * N, N, 1, trans, K, N, grad_x);
     launches += 1;
   }
@@ -146,11 +149,11 @@ extern "C" int pcuda_point_transform_bwd(const float* x, int64_t sxb, int64_t sx
     const int S = wgrad_splits(N);
     const int chunk = ((N + S - 1) / S + 31) / 32 * 32;
     float* partial = S == 1 ? grad_trans : static_cast<float*>(ws);
-    transform_wgrad_kernel<<<dim3(S, B), 256, 0, st>>>(x, sxb, sxc, sxn, grad_out, K, N, chunk, partial);
+    PCUDA_LAUNCH(transform_wgrad_kernel, dim3(S, B), 256, 0, st, x, sxb, sxc, sxn, grad_out, K, N, chunk, partial);
     launches += 1;
     if (S > 1) {
       const int64_t n = static_cast<int64_t>(B) * K * K;
-      transform_wgrad_reduce_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(partial, n, S, grad_trans);
+      PCUDA_LAUNCH(transform_wgrad_reduce_kernel, static_cast<int>((n + 255) / 256), 256, 0, st, partial, n, S, grad_trans);
       launches += 1;
     }
   }

@@ -770,25 +770,12 @@ def _fc_torch(x, lins, bns, relus, masks, iden_k, dtype):
     ([1024, 512, 256, 1], 32, 0, True),        # cfg-5 per-rank batch
     ([1024, 512, 256, 4096], 5, 64, False),    # STNkd head (k = 64)
     ([64, 20, 6], 2, 0, False),                # odd widths, minimum batch
-    ([1024, 512, 256, 9], 16, 3, True),        # largest batch of the cluster kernel
+    ([1024, 512, 256, 9], 16, 3, True),        # 16 rows with Dropout and the identity add
     ([1024, 512, 256, 1], 2, 0, False),        # minimum batch
     ([256, 64, 8], 3, 0, False),               # a two-hidden-layer head of other widths
 ])
-@pytest.mark.parametrize("path", ["cluster8", "cluster16", "cluster4", "per_layer"])
-def test_fc_stack_vs_torch(dims, B, iden_k, drop, path):
-    """FC heads: the thread-block-cluster kernel (one launch per head and direction, csrc/fchead.cu; shapes it does not
-    take fall through to the per-layer kernels) and the per-layer kernels (csrc/fcstack.cu) against float64 torch."""
-    ops.tune(8, 1 if path == "per_layer" else 0)
-    ops.tune(9, {"cluster8": 8, "cluster16": 16, "cluster4": 4}.get(path, 0))
-    try:
-        n0 = ops.launch_count()
-        _fc_stack_vs_torch(dims, B, iden_k, drop)
-        torch.cuda.synchronize()
-        if path == "cluster8" and B <= 16 and dims[1] % 8 == 0 and dims[0] <= 1024:
-            assert ops.launch_count() - n0 == 2, "expected one cluster launch per direction"
-    finally:
-        ops.tune(8, 0)
-        ops.tune(9, 0)
+def test_fc_stack_vs_torch(dims, B, iden_k, drop):
+    _fc_stack_vs_torch(dims, B, iden_k, drop)
 
 
 def _fc_stack_vs_torch(dims, B, iden_k, drop):
