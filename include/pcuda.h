@@ -72,7 +72,8 @@ int pcuda_sm_count(void);
  * 3 = bit mask of MLP pieces switched from tcgen05 back to FP32 (1 forward, 2 pooled dgrad,
  * 4 dense dgrad, 8 wgrad, 16 Gram), 4 = timing experiments of the pooled tensor-core layer (results invalid),
  * 5 = chamfer seed-pass stride (0 default, < 0 off), 6 = no auxiliary-stream fork / finalise-on-read in the MLP,
- * 7 = CTAs of the peer-memory all-reduce (0 default), 8 = launch without programmatic dependent launch (A/B). */
+ * 7 = CTAs of the peer-memory all-reduce (0 default), 8 = programmatic dependent launch (0 default: off; 2: every launch;
+ * 3: launches of >= 2 waves of CTAs). */
 int pcuda_tune(int key, int value);
 /* Number of kernels this library has launched in this process (monotone; for bench accounting). */
 uint64_t pcuda_launch_count(void);

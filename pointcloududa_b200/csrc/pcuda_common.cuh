@@ -25,7 +25,7 @@ static inline cudaError_t smem_optin(F* fn, int bytes) {
   return smem_optin_impl(reinterpret_cast<const void*>(fn), bytes);
 }
 
-enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_FP32 = 2, TUNE_MLP_TC_MASK = 3, TUNE_MLP_EPI_DEBUG = 4, TUNE_CHAMFER_SEED = 5, TUNE_MLP_NO_FORK = 6, TUNE_COMM_BLOCKS = 7, TUNE_NO_PDL = 8, TUNE_NKEYS = 12 };
+enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_FP32 = 2, TUNE_MLP_TC_MASK = 3, TUNE_MLP_EPI_DEBUG = 4, TUNE_CHAMFER_SEED = 5, TUNE_MLP_NO_FORK = 6, TUNE_COMM_BLOCKS = 7, TUNE_PDL = 8, TUNE_NKEYS = 12 };
 
 // ---- programmatic dependent launch -----------------------------------------------------------------
 // The hot path at the reference's shapes is a chain of ~70 dependent launches of 3-20 us per D4 pass: what a step
@@ -36,7 +36,7 @@ enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_F
 // and visibility are exactly those of ordinary stream order, but the dependent's launch latency (block scheduling,
 // parameter fetch, prologue that does not touch the predecessor's output) overlaps the predecessor's tail.  A kernel
 // that is launched without the attribute executes both instructions as no-ops.  Under stream capture the edges become
-// programmatic dependency edges of the CUDA graph.  pcuda_tune(8, 1) launches without the attribute (A/B).
+// programmatic dependency edges of the CUDA graph.  Which launches carry the attribute: see launch_k().
 __device__ __forceinline__ void pdl_trigger() {
 #if defined(__CUDA_ARCH__)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -63,7 +63,17 @@ static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 blo
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = tuning(TUNE_NO_PDL) ? 0 : 1;
+  // Measured (tools/ab_pdl.py, profiles/r2_ab_pdl.txt; CUDA-graph replay, L2 flushed, 40 steps each, two rounds):
+  //   cfg2 (grids <= 148 CTAs, 4 + 3 concurrent branches)   off 0.475 / 0.478 ms   always 0.495 / 0.496   >= 2 waves 0.477 / 0.476
+  //   cfg-5 shard (grids of several waves)                   off 2.730 / 2.734      always 2.670 / 2.680   >= 2 waves 2.846 / 2.769
+  //   cfg-3 (B = 32, N = 1024)                               off 1.192 / 1.198      always 1.166 / 1.293   >= 2 waves 1.211 / 1.232
+  // Early-resident dependents take SM slots from the concurrent branches of the step: +4 % at the reference's shapes,
+  // -2 % at cfg-5, noise in between.  Inside a CUDA graph the kernel-to-kernel hand-over is already cheap on this
+  // part; the chain is bound by each small kernel's own dependent memory round trips.  So the attribute is OFF by
+  // default; pcuda_tune(8, 2) sets it on every launch, pcuda_tune(8, 3) on launches of at least two waves of CTAs.
+  const int mode = tuning(TUNE_PDL);
+  const long long ctas = static_cast<long long>(grid.x) * grid.y * grid.z;
+  cfg.numAttrs = (mode == 2 || (mode == 3 && ctas >= 2ll * sm_count())) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 // PCUDA_LAUNCH((kernel<T...>), grid, block, smem, stream, args...): parenthesise kernel names that contain commas
