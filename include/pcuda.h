@@ -203,16 +203,25 @@ int pcuda_pointmlp_bwd_reuse(const float* x, int64_t sxb, int64_t sxc, int64_t s
  * i.e. torch.bmm(x.transpose(2, 1), trans).transpose(2, 1) (networks/PointNetCls.py:140-142) without materialising
  * the transformed cloud.  in_trans == NULL: identical to pcuda_pointmlp_fwd / _bwd_reuse.  The first layer must be a
  * narrow one (cin <= 4, cout <= 128, not the pooled layer).  Backward: grad_x is the gradient w.r.t. the
- * UNtransformed cloud x, grad_trans [B, C0, C0] the gradient w.r.t. in_trans (either may be NULL); fwd_ws may be NULL. */
+ * UNtransformed cloud x, grad_trans [B, C0, C0] the gradient w.r.t. in_trans (either may be NULL); fwd_ws may be NULL.
+ *
+ * sync_bn != NULL (train mode): CROSS-RANK BatchNorm statistics.  Every per-channel sum BatchNorm takes
+ * over the points — forward (sum y, sum y^2), backward (sum dz, sum dz*yhat; for the pooled layer also the column means
+ * of its input) — is summed over the ranks of the communicator (ncclAllReduce of the raw fp64 sums on `stream`, between
+ * the producing and the consuming kernel) and the point count becomes world * B * N, so that R ranks holding B/R clouds
+ * each normalise and back-propagate exactly like one process holding all B.  The parameter gradients a rank returns are
+ * its LOCAL share: summed over the ranks (the gradient all-reduce) they are the single-process gradient.  Every rank
+ * must call with the same shapes. */
+struct pcuda_comm;
 int pcuda_pointmlp_fwd_xf(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, const float* in_trans, int B, int N,
                           int L, const pcuda_mlp_layer_t* layers /*host*/, int pool, int train,
                           float momentum, float eps, int precision, float* out, int32_t* pool_arg,
-                          void* ws, pcuda_stream_t stream);
+                          void* ws, struct pcuda_comm* sync_bn, pcuda_stream_t stream);
 int pcuda_pointmlp_bwd_xf(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, const float* in_trans, int B, int N,
                           int L, const pcuda_mlp_layer_t* layers /*host*/, int pool, int train,
                           float eps, int precision, const float* out, const int32_t* pool_arg,
                           const float* grad_out, float* grad_x, float* grad_trans, void* ws, const void* fwd_ws,
-                          pcuda_stream_t stream);
+                          struct pcuda_comm* sync_bn, pcuda_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Per-cloud feature transform of PointNetfeat (networks/PointNetCls.py:147-151, the 64 x 64 matrix of STNkd):
@@ -349,6 +358,10 @@ typedef struct pcuda_comm pcuda_comm_t;
 int pcuda_comm_unique_id(void* id_out /*host, >= 128 bytes*/, int bytes);
 int pcuda_comm_init(const void* unique_id /*host, 128 bytes*/, int rank, int world, size_t p2p_floats, pcuda_comm_t** out);
 int pcuda_comm_allreduce(pcuda_comm_t* comm, float* buf, int64_t count, pcuda_stream_t stream);
+/* in-place sum of `count` doubles (BatchNorm statistics in the cross-rank mode); ncclAllGather of count_per_rank floats. */
+int pcuda_comm_allreduce_f64(pcuda_comm_t* comm, double* buf, int64_t count, pcuda_stream_t stream);
+int pcuda_comm_allgather(pcuda_comm_t* comm, const float* send, float* recv /*[world * count_per_rank]*/, int64_t count_per_rank,
+                         pcuda_stream_t stream);
 int pcuda_comm_p2p_buffers(pcuda_comm_t* comm, float** in, float** out, int64_t* capacity_floats);
 int pcuda_comm_allreduce_p2p(pcuda_comm_t* comm, int64_t count, pcuda_stream_t stream);
 int pcuda_comm_status(pcuda_comm_t* comm);

@@ -85,10 +85,10 @@ SIGNATURES = {
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcuda_pointmlp_fwd_xf": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
                                       POINTER(MlpLayer), c_int, c_int, c_float, c_float, c_int,
-                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcuda_pointmlp_bwd_xf": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
                                       POINTER(MlpLayer), c_int, c_int, c_float, c_int, c_void_p,
-                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcuda_point_transform_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcuda_point_transform_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_void_p,
                                           c_void_p]),
@@ -107,6 +107,8 @@ SIGNATURES = {
     "pcuda_comm_unique_id": (c_int, [c_void_p, c_int]),
     "pcuda_comm_init": (c_int, [c_void_p, c_int, c_int, c_size_t, POINTER(c_void_p)]),
     "pcuda_comm_allreduce": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pcuda_comm_allreduce_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pcuda_comm_allgather": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pcuda_comm_p2p_buffers": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64)]),
     "pcuda_comm_allreduce_p2p": (c_int, [c_void_p, c_int64, c_void_p]),
     "pcuda_comm_status": (c_int, [c_void_p]),

@@ -268,6 +268,36 @@ extern "C" int pcuda_comm_allreduce(pcuda_comm_t* c, float* buf, int64_t count, 
   return 0;
 }
 
+extern "C" int pcuda_comm_allreduce_f64(pcuda_comm_t* c, double* buf, int64_t count, pcuda_stream_t stream) {
+  PCUDA_REQUIRE(c && buf, PCUDA_E_NULL, "comm_allreduce_f64: NULL argument");
+  PCUDA_REQUIRE(count >= 0, PCUDA_E_SHAPE, "comm_allreduce_f64: count %lld", static_cast<long long>(count));
+  if (count == 0 || c->world == 1) return 0;
+  const Nccl* n = nccl();
+  if (!n) return PCUDA_E_UNSUPPORTED;
+  const ncclResult_t r = n->AllReduce(buf, buf, static_cast<size_t>(count), ncclDouble, ncclSum, c->nccl, static_cast<cudaStream_t>(stream));
+  if (r != ncclSuccess) return fail(1000 + static_cast<int>(r), "ncclAllReduce(f64): %s", n->GetErrorString(r));
+  return 0;
+}
+
+extern "C" int pcuda_comm_allgather(pcuda_comm_t* c, const float* send, float* recv, int64_t count_per_rank, pcuda_stream_t stream) {
+  PCUDA_REQUIRE(c && send && recv, PCUDA_E_NULL, "comm_allgather: NULL argument");
+  PCUDA_REQUIRE(count_per_rank >= 0, PCUDA_E_SHAPE, "comm_allgather: count %lld", static_cast<long long>(count_per_rank));
+  if (count_per_rank == 0) return 0;
+  const Nccl* n = nccl();
+  if (!n) return PCUDA_E_UNSUPPORTED;
+  const ncclResult_t r = n->AllGather(send, recv, static_cast<size_t>(count_per_rank), ncclFloat, c->nccl, static_cast<cudaStream_t>(stream));
+  if (r != ncclSuccess) return fail(1000 + static_cast<int>(r), "ncclAllGather: %s", n->GetErrorString(r));
+  return 0;
+}
+
+namespace pcuda {
+// for the BatchNorm statistics exchange inside pcuda_pointmlp_*_xf (pointmlp.cu)
+int comm_world(pcuda_comm_t* c) { return c ? c->world : 1; }
+int comm_sum_f64(pcuda_comm_t* c, double* buf, int64_t count, cudaStream_t st) {
+  return pcuda_comm_allreduce_f64(c, buf, count, st);
+}
+}  // namespace pcuda
+
 extern "C" int pcuda_comm_p2p_buffers(pcuda_comm_t* c, float** in, float** out, int64_t* capacity) {
   PCUDA_REQUIRE(c, PCUDA_E_NULL, "comm_p2p_buffers: NULL communicator");
   if (!c->p2p) {

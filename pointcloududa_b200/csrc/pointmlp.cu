@@ -30,6 +30,10 @@
 #include "pointmlp_tc.cuh"
 
 namespace pcuda {
+// comm.cu: sum of raw fp64 BatchNorm statistics over the ranks of a communicator (cross-rank BatchNorm mode)
+int comm_world(pcuda_comm_t* c);
+int comm_sum_f64(pcuda_comm_t* c, double* buf, int64_t count, cudaStream_t st);
+
 namespace {
 
 constexpr int TM = 64;   // tile rows
@@ -546,19 +550,33 @@ __global__ void pool_coef_kernel(const float* __restrict__ gsel, const float* __
                                  const float* __restrict__ invstd, const float* __restrict__ gamma, int B, int C,
                                  double count, int train, float* __restrict__ alpha, float* __restrict__ kappa,
                                  float* __restrict__ grad_gamma, float* __restrict__ grad_beta,
-                                 float* __restrict__ grad_bias) {
+                                 float* __restrict__ grad_bias, double* __restrict__ xsums, int phase) {
+  // phase 0: everything.  Cross-rank BatchNorm: phase 1 = this rank's sums (-> its parameter gradients, and xsums[2C]
+  // for the all-reduce), phase 2 = alpha / kappa from the reduced xsums and the global count.
   pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double dbeta = 0.0, dgamma = 0.0;
-  for (int b = 0; b < B; ++b) {
-    dbeta += static_cast<double>(gsel[static_cast<int64_t>(b) * C + c]);
-    dgamma += static_cast<double>(gyh[static_cast<int64_t>(b) * C + c]);
+  if (phase == 2) {
+    dbeta = xsums[c];
+    dgamma = xsums[C + c];
+  } else {
+    for (int b = 0; b < B; ++b) {
+      dbeta += static_cast<double>(gsel[static_cast<int64_t>(b) * C + c]);
+      dgamma += static_cast<double>(gyh[static_cast<int64_t>(b) * C + c]);
+    }
   }
   const double sc = static_cast<double>(gamma[c]) * static_cast<double>(invstd[c]);
-  if (grad_gamma) grad_gamma[c] = static_cast<float>(dgamma);
-  if (grad_beta) grad_beta[c] = static_cast<float>(dbeta);
-  if (grad_bias) grad_bias[c] = train ? 0.f : static_cast<float>(sc * dbeta);
+  if (phase != 2) {
+    if (grad_gamma) grad_gamma[c] = static_cast<float>(dgamma);
+    if (grad_beta) grad_beta[c] = static_cast<float>(dbeta);
+    if (grad_bias) grad_bias[c] = train ? 0.f : static_cast<float>(sc * dbeta);
+  }
+  if (phase == 1) {
+    xsums[c] = dbeta;
+    xsums[C + c] = dgamma;
+    return;
+  }
   alpha[c] = train ? static_cast<float>(sc * dbeta / count) : 0.f;
   kappa[c] = train ? static_cast<float>(sc * static_cast<double>(invstd[c]) * dgamma / count) : 0.f;
 }
@@ -677,10 +695,24 @@ abar_kernel(const double* __restrict__ colsum_partial, int S, int K, double coun
   for (int s = lane; s < S; s += 32) a += colsum_partial[static_cast<int64_t>(s) * K + k];
   a = warp_sum(a);
   if (lane == 0) {
-    a /= count;
+    a /= count;          // count == 1: the raw column sum (cross-rank BatchNorm: divided after the all-reduce)
     abar[k] = static_cast<float>(a);
     abar_d[k] = a;
   }
+}
+
+// Cross-rank BatchNorm: the sums of (y - pivot), (y - pivot)^2 of this rank are re-expressed around a pivot every rank
+// shares (the layer's bias, or 0) before they are summed over the ranks:  with d = pivot - pivot',
+//   sum (y - pivot') = S + n d,     sum (y - pivot')^2 = Q + 2 d S + n d^2.
+__global__ void stats_rebase_kernel(double* __restrict__ stats, const float* __restrict__ pivot_from,
+                                    const float* __restrict__ pivot_to, int C, double count) {
+  pdl_entry();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double d = static_cast<double>(pivot_from[c]) - (pivot_to ? static_cast<double>(pivot_to[c]) : 0.0);
+  const double S = stats[c], Q = stats[C + c];
+  stats[c] = S + count * d;
+  stats[C + c] = Q + 2.0 * d * S + count * d * d;
 }
 
 // Ghat[k,k'] = G[k,k'] - M abar_k abar_k'
@@ -1541,7 +1573,7 @@ extern "C" size_t pcuda_pointmlp_ws_bytes(int B, int N, int L, const pcuda_mlp_l
 static int pointmlp_fwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
                              const pcuda_mlp_layer_t* layers, int pool, int train, float momentum,
                              float eps, int precision, float* out, int32_t* pool_arg, void* ws,
-                             const float* in_trans, pcuda_stream_t stream) {
+                             const float* in_trans, pcuda_comm_t* sync_bn, pcuda_stream_t stream) {
   if (int rc = validate("pointmlp_fwd", B, N, L, layers, pool)) return rc;
   if (int rc = validate_trans("pointmlp_fwd", in_trans, L, layers, pool)) return rc;
   PCUDA_REQUIRE(x && out && ws, PCUDA_E_NULL, "pointmlp_fwd: NULL x/out/ws");
@@ -1555,6 +1587,9 @@ static int pointmlp_fwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const FwdWs w = carve_fwd(s, layers, ws);
   cudaMemsetAsync(w.stats, 0, w.zero_span, st);
+  // cross-rank BatchNorm statistics (train mode, more than one rank): see include/pcuda.h
+  pcuda_comm_t* const sync = (train && sync_bn != nullptr && comm_world(sync_bn) > 1) ? sync_bn : nullptr;
+  const double count_bn = static_cast<double>(s.M) * (sync ? comm_world(sync) : 1);
 
   const bool tcf = tc_on(precision, TC_FWD);
   auto layer_tc = [&](int l) { return tcf && tc::fwd_fits(layers[l].cout, layers[l].cin); };
@@ -1570,6 +1605,7 @@ static int pointmlp_fwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
   Aux* ax = (any_pack && !tuning(TUNE_MLP_NO_FORK)) ? aux_for(st) : nullptr;
   AuxJoin joiner(ax, st);
   bool packs_pending = false;
+  int sync_launches = 0;
   if (any_pack) {
     cudaStream_t sp = ax ? ax->s : st;
     if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sp, ax->fork, 0); joiner.pending = true; }
@@ -1619,13 +1655,23 @@ static int pointmlp_fwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
     // layer, or the pooled-output kernel, that kernel finalises from the raw sums itself (BnRaw): no one-block
     // launch between the GEMM and its consumer.  Otherwise: the finalise kernel; if an FP32 layer follows, it
     // computes that layer's pivot in the same launch.
+    if (sync) {
+      // this rank's sums, re-expressed around a pivot all ranks share (tensor-core layers already use it), summed over the ranks
+      const float* common = y.bias ? y.bias : w.zeros;
+      if (pivot_used != common) {
+        PCUDA_LAUNCH(stats_rebase_kernel, (y.cout + 127) / 128, 128, 0, st, st_l, pivot_used, y.bias, y.cout, static_cast<double>(s.M));
+        sync_launches += 1;
+        pivot_used = common;
+      }
+      if (int rc = comm_sum_f64(sync, st_l, 2 * static_cast<int64_t>(y.cout), st)) return rc;
+    }
     const bool next_piv = l + 1 < L && !layer_tc(l + 1) && !layer_narrow(l + 1);
     const bool fold = !tuning(TUNE_MLP_NO_FORK) && ((l + 1 < L && layer_tc(l + 1)) || (l == L - 1 && pool));
     if (fold) {
-      raw_prev = BnRaw{st_l, pivot_used, static_cast<double>(s.M), eps, momentum, train, y.save_mean, y.save_invstd,
+      raw_prev = BnRaw{st_l, pivot_used, count_bn, eps, momentum, train, y.save_mean, y.save_invstd,
                        y.running_mean, y.running_var};
     } else {
-      PCUDA_LAUNCH(bn_finalize_pivot_kernel, 1, 1024, 0, st, st_l, pivot_used, y.cout, static_cast<double>(s.M), eps, momentum, train,
+      PCUDA_LAUNCH(bn_finalize_pivot_kernel, 1, 1024, 0, st, st_l, pivot_used, y.cout, count_bn, eps, momentum, train,
                                                    y.save_mean, y.save_invstd, y.running_mean, y.running_var,
                                                    next_piv ? layer_src(y, N) : ActSrc{}, next_piv ? layers[l + 1].weight : nullptr,
                                                    next_piv ? layers[l + 1].bias : nullptr, next_piv ? layers[l + 1].cout : 0,
@@ -1644,7 +1690,7 @@ static int pointmlp_fwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
     const dim3 grid((N + 31) / 32, (s.Clast + 31) / 32, B);
     PCUDA_LAUNCH(dense_out_kernel, grid, dim3(32, 8), 0, st, layer_src(last, N), B, out);
   }
-  count_launch(launches + 1);
+  count_launch(launches + 1 + sync_launches);
   return check_launch("pointmlp_fwd");
 }
 
@@ -1652,21 +1698,22 @@ extern "C" int pcuda_pointmlp_fwd(const float* x, int64_t sxb, int64_t sxc, int6
                                   const pcuda_mlp_layer_t* layers, int pool, int train, float momentum,
                                   float eps, int precision, float* out, int32_t* pool_arg, void* ws,
                                   pcuda_stream_t stream) {
-  return pointmlp_fwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, momentum, eps, precision, out, pool_arg, ws, nullptr, stream);
+  return pointmlp_fwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, momentum, eps, precision, out, pool_arg, ws, nullptr, nullptr, stream);
 }
 
 extern "C" int pcuda_pointmlp_fwd_xf(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, const float* in_trans, int B, int N, int L,
                                      const pcuda_mlp_layer_t* layers, int pool, int train, float momentum,
                                      float eps, int precision, float* out, int32_t* pool_arg, void* ws,
-                                     pcuda_stream_t stream) {
-  return pointmlp_fwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, momentum, eps, precision, out, pool_arg, ws, in_trans, stream);
+                                     pcuda_comm_t* sync_bn, pcuda_stream_t stream) {
+  return pointmlp_fwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, momentum, eps, precision, out, pool_arg, ws, in_trans, sync_bn,
+                           stream);
 }
 
 static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
                              const pcuda_mlp_layer_t* layers, int pool, int train, float eps,
                              int precision, const float* out, const int32_t* pool_arg,
                              const float* grad_out, float* grad_x, void* ws, const void* fwd_ws,
-                             const float* in_trans, float* grad_trans, pcuda_stream_t stream) {
+                             const float* in_trans, float* grad_trans, pcuda_comm_t* sync_bn, pcuda_stream_t stream) {
   (void)eps;
   if (int rc = validate("pointmlp_bwd", B, N, L, layers, pool)) return rc;
   if (int rc = validate_trans("pointmlp_bwd", in_trans, L, layers, pool)) return rc;
@@ -1676,7 +1723,11 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
   PCUDA_REQUIRE(precision == PCUDA_MLP_FP32 || precision == PCUDA_MLP_BF16, PCUDA_E_UNSUPPORTED, "pointmlp_bwd: precision %d", precision);
   const Shape s = make_shape(B, N, L, layers, pool);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const double count = static_cast<double>(s.M);
+  // cross-rank BatchNorm (include/pcuda.h): `count` is the number of values a statistic was taken over (all ranks),
+  // count_local this rank's share
+  pcuda_comm_t* const sync = (train && sync_bn != nullptr && comm_world(sync_bn) > 1) ? sync_bn : nullptr;
+  const double count_local = static_cast<double>(s.M);
+  const double count = count_local * (sync ? comm_world(sync) : 1);
   const int tps = (N + TM - 1) / TM;
   const tc::Tiling tl = tc::make_tiling(B, N);
   int launches = 0;
@@ -1729,7 +1780,8 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
   }
 
   // auxiliary stream of this call (see Aux above); tuning key 6 keeps everything on the caller's stream (A/B)
-  Aux* ax = tuning(TUNE_MLP_NO_FORK) ? nullptr : aux_for(st);
+  // (cross-rank mode: one stream, so that the collectives of one communicator are issued in one order)
+  Aux* ax = (tuning(TUNE_MLP_NO_FORK) || sync) ? nullptr : aux_for(st);
   cudaStream_t sa = ax ? ax->s : st;
   AuxJoin joiner(ax, st);  // joins on every exit path once joiner.pending is set
   bool& aux_used = joiner.pending;   // something was issued on the auxiliary stream: join before returning
@@ -1760,17 +1812,36 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       launches += 1;
     }
     PCUDA_LAUNCH(reduce_partials_kernel<double>, static_cast<int>((kk + 255) / 256), 256, 0, sa, partial, kk, Sg, w.G);
-    PCUDA_LAUNCH(abar_kernel, (K + 7) / 8, 256, 0, sa, w.colsum, S32, K, count, w.abar, w.abar_d);
-    PCUDA_LAUNCH(gram_center_kernel, static_cast<int>((kk + 255) / 256), 256, 0, sa, w.abar_d, w.G, K, count, w.Ghat);
+    if (sync) {
+      // column means over ALL ranks' points; the Gram matrix stays local and is centred with the global mean
+      // (sum_r [G_r - M_r abar abar^T] is the centred Gram matrix of the global batch)
+      PCUDA_LAUNCH(abar_kernel, (K + 7) / 8, 256, 0, sa, w.colsum, S32, K, 1.0, w.abar, w.abar_d);
+      if (int rc = comm_sum_f64(sync, w.abar_d, K, sa)) return rc;
+      PCUDA_LAUNCH(abar_kernel, (K + 7) / 8, 256, 0, sa, w.abar_d, 1, K, count, w.abar, w.abar_d);
+      launches += 1;
+    } else {
+      PCUDA_LAUNCH(abar_kernel, (K + 7) / 8, 256, 0, sa, w.colsum, S32, K, count, w.abar, w.abar_d);
+    }
+    PCUDA_LAUNCH(gram_center_kernel, static_cast<int>((kk + 255) / 256), 256, 0, sa, w.abar_d, w.G, K, count_local, w.Ghat);
     if (ax) cudaEventRecord(ax->side, sa);
     // -- selection side: per-(cloud, channel) coefficients, alpha / kappa, Q = W^T diag(kappa) W
     PCUDA_LAUNCH(pool_sel_kernel, static_cast<int>((bc * 32 + 255) / 256), 256, 0, st, src, last.weight, last.bias, last.save_mean,
                                                                             last.save_invstd, last.gamma, last.relu, out, pool_arg,
                                                                             grad_out, B, N, C, w.coef, w.gsel, w.gyh);
     const bool want_last = last.grad_weight != nullptr;
-    PCUDA_LAUNCH(pool_coef_kernel, (C + 127) / 128, 128, 0, st, w.gsel, w.gyh, last.save_invstd, last.gamma, B, C, count, train, al, ka,
-                                                      want_last ? last.grad_gamma : nullptr, want_last ? last.grad_beta : nullptr,
-                                                      want_last ? last.grad_bias : nullptr);
+    if (sync) {
+      double* xs = sums + 2 * off[L - 1];      // the pooled layer's own slot of `sums` is otherwise unused
+      PCUDA_LAUNCH(pool_coef_kernel, (C + 127) / 128, 128, 0, st, w.gsel, w.gyh, last.save_invstd, last.gamma, B, C, count, train, al, ka,
+                   want_last ? last.grad_gamma : nullptr, want_last ? last.grad_beta : nullptr, want_last ? last.grad_bias : nullptr, xs, 1);
+      if (int rc = comm_sum_f64(sync, xs, 2 * static_cast<int64_t>(C), st)) return rc;
+      PCUDA_LAUNCH(pool_coef_kernel, (C + 127) / 128, 128, 0, st, w.gsel, w.gyh, last.save_invstd, last.gamma, B, C, count, train, al, ka,
+                   static_cast<float*>(nullptr), static_cast<float*>(nullptr), static_cast<float*>(nullptr), xs, 2);
+      launches += 1;
+    } else {
+      PCUDA_LAUNCH(pool_coef_kernel, (C + 127) / 128, 128, 0, st, w.gsel, w.gyh, last.save_invstd, last.gamma, B, C, count, train, al, ka,
+                   want_last ? last.grad_gamma : nullptr, want_last ? last.grad_beta : nullptr, want_last ? last.grad_bias : nullptr,
+                   static_cast<double*>(nullptr), 0);
+    }
     PCUDA_LAUNCH(pool_q_kernel, dim3((K + 31) / 32, (K + 31) / 32, kPoolQSplits), 256, 0, st, last.weight, ka, C, K, w.qpartial);
     // the low-rank dgrad runs on the tensor cores (decided here: it changes how Q is finished)
     const bool tc_pool = (L >= 2 || grad_x) && tc_on(precision, TC_POOL_DGRAD) && a_in && w.qpack && tc::pool_dgrad_fits(K) &&
@@ -1841,9 +1912,21 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
     float* al = alpha + off[l];
     float* ka = kappa + off[l];
     const bool want_w = y.grad_weight != nullptr;
-    PCUDA_LAUNCH(bn_bwd_coef_kernel, (C + 127) / 128, 128, 0, st, sums + 2 * off[l], y.save_invstd, y.gamma, C, count, train, al, ka,
-                                                        want_w ? y.grad_gamma : nullptr, want_w ? y.grad_beta : nullptr,
-                                                        want_w ? y.grad_bias : nullptr);
+    if (sync) {
+      // parameter gradients from this rank's sums (they are summed over the ranks by the gradient all-reduce) ...
+      if (want_w) {
+        PCUDA_LAUNCH(bn_bwd_coef_kernel, (C + 127) / 128, 128, 0, st, sums + 2 * off[l], y.save_invstd, y.gamma, C, count, train, al, ka,
+                     y.grad_gamma, y.grad_beta, y.grad_bias);
+        launches += 1;
+      }
+      // ... the BatchNorm backward coefficients from the sums over all ranks
+      if (int rc = comm_sum_f64(sync, sums + 2 * off[l], 2 * static_cast<int64_t>(C), st)) return rc;
+      PCUDA_LAUNCH(bn_bwd_coef_kernel, (C + 127) / 128, 128, 0, st, sums + 2 * off[l], y.save_invstd, y.gamma, C, count, train, al, ka,
+                   static_cast<float*>(nullptr), static_cast<float*>(nullptr), static_cast<float*>(nullptr));
+    } else {
+      PCUDA_LAUNCH(bn_bwd_coef_kernel, (C + 127) / 128, 128, 0, st, sums + 2 * off[l], y.save_invstd, y.gamma, C, count, train, al, ka,
+                   want_w ? y.grad_gamma : nullptr, want_w ? y.grad_beta : nullptr, want_w ? y.grad_bias : nullptr);
+    }
     launches += 1;
     const DySrc dys{dzbuf[cur], y.y, y.save_mean, y.save_invstd, y.gamma, al, ka, C};
     const bool need_dgrad = l > 0 || want_gx;
@@ -1913,7 +1996,7 @@ extern "C" int pcuda_pointmlp_bwd(const float* x, int64_t sxb, int64_t sxc, int6
                                   int precision, const float* out, const int32_t* pool_arg,
                                   const float* grad_out, float* grad_x, void* ws, pcuda_stream_t stream) {
   return pointmlp_bwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, eps, precision, out, pool_arg, grad_out, grad_x, ws,
-                           nullptr, nullptr, nullptr, stream);
+                           nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int pcuda_pointmlp_bwd_reuse(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, int B, int N, int L,
@@ -1922,14 +2005,14 @@ extern "C" int pcuda_pointmlp_bwd_reuse(const float* x, int64_t sxb, int64_t sxc
                                         const float* grad_out, float* grad_x, void* ws, const void* fwd_ws,
                                         pcuda_stream_t stream) {
   return pointmlp_bwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, eps, precision, out, pool_arg, grad_out, grad_x, ws,
-                           fwd_ws, nullptr, nullptr, stream);
+                           fwd_ws, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int pcuda_pointmlp_bwd_xf(const float* x, int64_t sxb, int64_t sxc, int64_t sxn, const float* in_trans, int B, int N, int L,
                                      const pcuda_mlp_layer_t* layers, int pool, int train, float eps,
                                      int precision, const float* out, const int32_t* pool_arg,
                                      const float* grad_out, float* grad_x, float* grad_trans, void* ws, const void* fwd_ws,
-                                     pcuda_stream_t stream) {
+                                     pcuda_comm_t* sync_bn, pcuda_stream_t stream) {
   return pointmlp_bwd_impl(x, sxb, sxc, sxn, B, N, L, layers, pool, train, eps, precision, out, pool_arg, grad_out, grad_x, ws,
-                           fwd_ws, in_trans, grad_trans, stream);
+                           fwd_ws, in_trans, grad_trans, sync_bn, stream);
 }

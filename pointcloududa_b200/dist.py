@@ -91,6 +91,17 @@ class PcudaComm:
                        "pcuda_comm_allreduce")
         return t
 
+    def allgather(self, send: torch.Tensor, recv: torch.Tensor) -> torch.Tensor:
+        """recv[r * n:(r + 1) * n] = rank r's send (n = send.numel(); ncclAllGather on the current stream)."""
+        from . import _lib
+        if send.dtype != torch.float32 or recv.dtype != torch.float32 or not send.is_contiguous() or not recv.is_contiguous() \
+                or recv.numel() != self.world * send.numel():
+            raise _lib.PcudaError("PcudaComm.allgather needs contiguous float32 tensors, recv = world x send")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().pcuda_comm_allgather(self._h, send.data_ptr(), recv.data_ptr(), send.numel(),
+                                                       torch.cuda.current_stream(self.device).cuda_stream), "pcuda_comm_allgather")
+        return recv
+
     def allreduce_p2p(self, count: int) -> torch.Tensor:
         """Sum of every rank's `buf_in[:count]` into every rank's `buf_out[:count]` (one NVLink peer-memory kernel)."""
         from . import _lib

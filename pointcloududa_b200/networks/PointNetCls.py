@@ -87,11 +87,12 @@ class _SharedMLP(torch.autograd.Function):
     """y = [max_n] relu?(bn(conv1x1(...relu(bn(conv1x1(x)))))) on libpcuda."""
 
     @staticmethod
-    def forward(ctx, x, in_trans, pool: bool, train: bool, precision: int, relus: Tuple[bool, ...],
+    def forward(ctx, x, in_trans, sync, pool: bool, train: bool, precision: int, relus: Tuple[bool, ...],
                 momenta: Tuple[float, ...], eps: float, buffers: Tuple[Optional[torch.Tensor], ...],
                 stats_out: Optional[list], *params):
         # params: (weight, bias, gamma, beta) per layer; buffers: (running_mean, running_var) per layer
         # in_trans: [B, C0, C0] per-cloud input transform applied inside the first layer's operand load, or None
+        # sync: a dist.PcudaComm for cross-rank BatchNorm statistics (include/pcuda.h), or None
         if not x.is_cuda:
             raise PcudaError("PointNetCls runs on CUDA (sm_100a) only; there is no CPU fallback")
         if x.dtype != torch.float32 or x.dim() != 3:
@@ -135,7 +136,8 @@ class _SharedMLP(torch.autograd.Function):
             ws = torch.empty(max(Lb.pcuda_pointmlp_ws_bytes(B, N, L, lay, int(pool), 0), 16), dtype=torch.uint8, device=dev)
             check(Lb.pcuda_pointmlp_fwd_xf(_ptr(x), x.stride(0), x.stride(1), x.stride(2), _ptr(tr), B, N, L, lay, int(pool),
                                            int(train), float(momenta[0]), float(eps), precision, _ptr(out), _ptr(arg),
-                                           _ptr(ws), torch.cuda.current_stream().cuda_stream), "pcuda_pointmlp_fwd")
+                                           _ptr(ws), None if sync is None else sync._h, torch.cuda.current_stream().cuda_stream),
+                  "pcuda_pointmlp_fwd")
         if stats_out is not None:
             stats_out.extend(zip(means, invstds))
         ctx.cfg = (pool, train, precision, relus, eps, B, N, L)
@@ -147,6 +149,7 @@ class _SharedMLP(torch.autograd.Function):
             ctx.save_for_backward(x)
         ctx.keep = keep
         ctx.trans = tr
+        ctx.sync = sync
         ctx.saved = (ys, means, invstds, arg)
         ctx.fwd_ws = ws        # kept alive: the backward pass reads the packed bf16 operands in place
         ctx.param_shapes = [None if p is None else p.shape for p in params]
@@ -167,7 +170,8 @@ class _SharedMLP(torch.autograd.Function):
         dev = x.device
         need_x = ctx.needs_input_grad[0]
         need_t = tr is not None and ctx.needs_input_grad[1]
-        needs_p = ctx.needs_input_grad[10:]
+        needs_p = ctx.needs_input_grad[11:]
+        sync = ctx.sync
         lay = (MlpLayer * L)()
         grads: List[Optional[torch.Tensor]] = []
         for l in range(L):
@@ -195,15 +199,16 @@ class _SharedMLP(torch.autograd.Function):
             ws = torch.empty(max(Lb.pcuda_pointmlp_ws_bytes(B, N, L, lay, int(pool), 1), 16), dtype=torch.uint8, device=dev)
             check(Lb.pcuda_pointmlp_bwd_xf(_ptr(x), x.stride(0), x.stride(1), x.stride(2), _ptr(tr), B, N, L, lay, int(pool),
                                            int(train), float(eps), precision, _ptr(out), _ptr(arg), _ptr(go), _ptr(gx), _ptr(gt),
-                                           _ptr(ws), _ptr(ctx.fwd_ws), torch.cuda.current_stream().cuda_stream),
+                                           _ptr(ws), _ptr(ctx.fwd_ws), None if sync is None else sync._h,
+                                           torch.cuda.current_stream().cuda_stream),
                   "pcuda_pointmlp_bwd")
         for i, need in enumerate(needs_p):
             if not need:
                 grads[i] = None
         # release everything this node held (per-layer activations, the forward workspace with the bf16 slabs, weight
         # aliases): at cfg-5 sizes that is hundreds of MB per D4 pass
-        ctx.keep = ctx.saved = ctx.fwd_ws = ctx.trans = None
-        return (gx, gt, None, None, None, None, None, None, None, None, *grads)
+        ctx.keep = ctx.saved = ctx.fwd_ws = ctx.trans = ctx.sync = None
+        return (gx, gt, None, None, None, None, None, None, None, None, None, *grads)
 
 
 def can_fuse_input_transform(convs: Sequence[nn.Conv1d], pool: bool) -> bool:
@@ -217,10 +222,11 @@ def can_fuse_input_transform(convs: Sequence[nn.Conv1d], pool: bool) -> bool:
 
 def shared_mlp(x: torch.Tensor, convs: Sequence[nn.Conv1d], bns: Sequence[nn.BatchNorm1d],
                relus: Sequence[bool], pool: bool, precision: str = DEFAULT_PRECISION,
-               in_trans: Optional[torch.Tensor] = None) -> torch.Tensor:
+               in_trans: Optional[torch.Tensor] = None, sync=None) -> torch.Tensor:
     """Run Conv1d(k=1)+BatchNorm1d(+ReLU) layers [+ max over points] as one fused op.  in_trans [B, C0, C0]: the
     per-cloud transform torch.bmm(x.transpose(2, 1), in_trans).transpose(2, 1) applied to the input first
-    (reference :140-142), inside the first layer's operand load."""
+    (reference :140-142), inside the first layer's operand load.  sync: a dist.PcudaComm — BatchNorm statistics (forward
+    and backward) are taken over the clouds of ALL its ranks (cross-rank mode); None: this rank's clouds."""
     params, buffers, momenta = [], [], []
     eps = bns[0].eps
     train = bns[0].training or not bns[0].track_running_stats
@@ -239,10 +245,12 @@ def shared_mlp(x: torch.Tensor, convs: Sequence[nn.Conv1d], bns: Sequence[nn.Bat
     stats_out = [] if sink is not None else None
     if sink is not None:
         buffers = [None] * len(buffers)          # the kernels skip the running-stat update
-    out = _SharedMLP.apply(x, in_trans, bool(pool), bool(train), PRECISIONS[precision], tuple(bool(r) for r in relus),
+    if sync is not None and (not train or sync.world == 1):
+        sync = None
+    out = _SharedMLP.apply(x, in_trans, sync, bool(pool), bool(train), PRECISIONS[precision], tuple(bool(r) for r in relus),
                            tuple(momenta), float(eps), tuple(buffers), stats_out, *params)
     if sink is not None:
-        count = x.shape[0] * x.shape[2]
+        count = x.shape[0] * x.shape[2] * (sync.world if sync is not None else 1)
         sink.extend((bn, mean, invstd, count) for bn, (mean, invstd) in zip(bns, stats_out))
     elif train:
         counters = [bn.num_batches_tracked for bn in bns if bn.num_batches_tracked is not None]
@@ -346,11 +354,81 @@ class _FcStack(torch.autograd.Function):
         return (gx, None, None, None, None, None, None, None, None, None, *grads)
 
 
+class _GatherRows(torch.autograd.Function):
+    """[B_r, C] rows of this rank -> [R * B_r, C] rows of all ranks (rank-major), through libpcuda's communicator.
+    Backward: this rank's slice of the gradient (every rank computes the identical full gradient downstream)."""
+
+    @staticmethod
+    def forward(ctx, x, comm):
+        xc = x.contiguous()
+        out = torch.empty((comm.world * xc.shape[0],) + tuple(xc.shape[1:]), dtype=xc.dtype, device=xc.device)
+        comm.allgather(xc, out)
+        ctx.rows, ctx.rank = xc.shape[0], comm.rank
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[ctx.rank * ctx.rows:(ctx.rank + 1) * ctx.rows].contiguous(), None
+
+
+class _LocalRows(torch.autograd.Function):
+    """[R * B_r, C] -> this rank's [B_r, C] rows.  Backward: gathers every rank's gradient rows, so that each rank
+    back-propagates the FULL output gradient through its (replicated) copy of the head."""
+
+    @staticmethod
+    def forward(ctx, y, comm):
+        rows = y.shape[0] // comm.world
+        ctx.comm = comm
+        return y[comm.rank * rows:(comm.rank + 1) * rows].contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        comm = ctx.comm
+        gc = g.contiguous()
+        out = torch.empty((comm.world * gc.shape[0],) + tuple(gc.shape[1:]), dtype=gc.dtype, device=gc.device)
+        comm.allgather(gc, out)
+        return out, None
+
+
+class _ScaleGrad(torch.autograd.Function):
+    """Identity whose gradient is scaled: parameters of a head that every rank evaluates on the gathered batch receive
+    the identical full gradient on every rank; 1/R of it per rank sums to the gradient once in the all-reduce."""
+
+    @staticmethod
+    def forward(ctx, p, scale: float):
+        ctx.scale = scale
+        return p.view_as(p)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.scale, None
+
+
 def fc_stack(x: torch.Tensor, linears: Sequence[nn.Linear], bns: Sequence[Optional[nn.BatchNorm1d]],
              relus: Sequence[bool], masks: Optional[Sequence[Optional[torch.Tensor]]] = None,
-             add_identity_k: int = 0) -> torch.Tensor:
+             add_identity_k: int = 0, sync=None) -> torch.Tensor:
     """Run Linear [* dropout mask] [+ BatchNorm1d] [+ ReLU] layers on [B, C] rows as one fused op per layer
-    (the FC heads of the reference, PointNetCls.py:46-62, :89-101, :208-213)."""
+    (the FC heads of the reference, PointNetCls.py:46-62, :89-101, :208-213).
+
+    sync (a dist.PcudaComm, train mode): cross-rank BatchNorm.  The heads are 0.2 % of D4's FLOPs, so instead of
+    exchanging statistics per layer the [B_r, 1024] pooled features of all ranks are gathered, every rank runs the head on
+    the global batch, keeps its own rows of the result, and in backward gathers the output gradients: BatchNorm then sees
+    exactly the rows a single process would.  Parameter gradients come out identical on every rank and are scaled by 1/R
+    so that the gradient all-reduce counts them once.  Dropout masks (drawn per rank for its own rows) are gathered too."""
+    real0 = [bn for bn in bns if bn is not None]
+    if sync is not None and sync.world > 1 and real0 and (real0[0].training or not real0[0].track_running_stats):
+        xg = _GatherRows.apply(x, sync)
+        mg = None
+        if masks is not None:
+            mg = [None if m is None else _GatherRows.apply(m, sync) for m in masks]
+        out = _fc_stack_local(xg, linears, bns, relus, mg, add_identity_k, grad_scale=1.0 / sync.world)
+        return _LocalRows.apply(out, sync)
+    return _fc_stack_local(x, linears, bns, relus, masks, add_identity_k)
+
+
+def _fc_stack_local(x: torch.Tensor, linears: Sequence[nn.Linear], bns: Sequence[Optional[nn.BatchNorm1d]],
+                    relus: Sequence[bool], masks: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                    add_identity_k: int = 0, grad_scale: float = 1.0) -> torch.Tensor:
     real = [bn for bn in bns if bn is not None]
     eps = real[0].eps if real else 1e-5
     momentum = real[0].momentum if real else 0.1
@@ -364,6 +442,8 @@ def fc_stack(x: torch.Tensor, linears: Sequence[nn.Linear], bns: Sequence[Option
                 raise PcudaError("all BatchNorm layers of one FC head must share eps, momentum and mode")
         params += [lin.weight, lin.bias, None if bn is None else bn.weight, None if bn is None else bn.bias]
         buffers += [None if bn is None else bn.running_mean, None if bn is None else bn.running_var]
+    if grad_scale != 1.0:
+        params = [None if p is None else (_ScaleGrad.apply(p, grad_scale) if p.requires_grad else p) for p in params]
     masks = tuple(masks) if masks is not None else (None,) * len(linears)
     sink = getattr(_TLS, "sink", None) if train else None
     stats_out = [] if sink is not None else None
@@ -453,14 +533,15 @@ class STN3d(nn.Module):
         self.in4 = nn.InstanceNorm1d(512, track_running_stats=True)
         self.in5 = nn.InstanceNorm1d(256, track_running_stats=True)
         self._precision = precision
+        self._sync = None          # dist.PcudaComm: cross-rank BatchNorm statistics (PointNetCls.set_sync_bn)
 
     def forward(self, x):
         batchsize = x.size()[0]
         _check_batch(batchsize)
         x = shared_mlp(x, [self.conv1, self.conv2, self.conv3], [self.bn1, self.bn2, self.bn3],
-                       [True, True, True], pool=True, precision=self._precision)     # :41-45
+                       [True, True, True], pool=True, precision=self._precision, sync=self._sync)     # :41-45
         x = fc_stack(x, [self.fc1, self.fc2, self.fc3], [self.bn4, self.bn5, None], [True, True, False],
-                     add_identity_k=3)                                                # :46-62 (fc, bn, relu, + I)
+                     add_identity_k=3, sync=self._sync)                               # :46-62 (fc, bn, relu, + I)
         return x.view(-1, 3, 3)
 
 
@@ -485,12 +566,13 @@ class STNkd(nn.Module):
 
         self.k = k
         self._precision = precision
+        self._sync = None
 
     def forward(self, x):
         x = shared_mlp(x, [self.conv1, self.conv2, self.conv3], [self.bn1, self.bn2, self.bn3],
-                       [True, True, True], pool=True, precision=self._precision)     # :82-86
+                       [True, True, True], pool=True, precision=self._precision, sync=self._sync)     # :82-86
         x = fc_stack(x, [self.fc1, self.fc2, self.fc3], [self.bn4, self.bn5, None], [True, True, False],
-                     add_identity_k=self.k)                                           # :89-101
+                     add_identity_k=self.k, sync=self._sync)                          # :89-101
         return x.view(-1, self.k, self.k)
 
 
@@ -529,6 +611,7 @@ class PointNetfeat(nn.Module):
         if self.feature_transform:
             self.fstn = STNkd(k=64, precision=precision)
         self._precision = precision
+        self._sync = None
 
     def _stacks(self):
         if self._ext:
@@ -558,17 +641,18 @@ class PointNetfeat(nn.Module):
         pointfeat = None
         if two_stacks:
             # the 64-wide point features are needed as a tensor: run the trunk as two stacks
-            x = shared_mlp(x, pc, pb, pr, pool=False, precision=self._precision, in_trans=in_trans)
+            x = shared_mlp(x, pc, pb, pr, pool=False, precision=self._precision, in_trans=in_trans, sync=self._sync)
             if self.feature_transform:
                 trans_feat = self.fstn(x)
                 x = point_transform(x, trans_feat)                                 # :147-151
             else:
                 trans_feat = None
             pointfeat = x
-            x = shared_mlp(x, qc, qb, qr, pool=True, precision=self._precision)
+            x = shared_mlp(x, qc, qb, qr, pool=True, precision=self._precision, sync=self._sync)
         else:
             trans_feat = None
-            x = shared_mlp(x, pc + qc, pb + qb, pr + qr, pool=True, precision=self._precision, in_trans=in_trans)  # :143-162
+            x = shared_mlp(x, pc + qc, pb + qb, pr + qr, pool=True, precision=self._precision, in_trans=in_trans,
+                           sync=self._sync)                                        # :143-162
         x = x.view(-1, 1024)
         if self.global_feat:
             return x, trans, trans_feat
@@ -605,8 +689,18 @@ class PointNetCls(nn.Module):
         self.in2 = nn.InstanceNorm1d(256, track_running_stats=True)
         self.relu = nn.ReLU()
         self._ones = None
+        self._sync = None
         if heinit or cvinit:
             self._initialize_weights(heinit=heinit)
+
+    def set_sync_bn(self, comm) -> None:
+        """Cross-rank BatchNorm: with a dist.PcudaComm, every train-mode BatchNorm of the network takes
+        its statistics — forward and backward — over the clouds of ALL ranks, so that R ranks holding B/R clouds each
+        compute what one process holding all B would (the reference is single-process: its BatchNorm always sees the
+        whole batch).  None restores per-rank statistics (what stock DistributedDataParallel does)."""
+        for m in self.modules():
+            if hasattr(m, "_sync"):
+                m._sync = comm
 
     def _initialize_weights(self, heinit=False):
         # The reference only re-initialises nn.Conv2d modules (:188-202) and this network has none,
@@ -630,7 +724,7 @@ class PointNetCls(nn.Module):
                 self._ones = torch.ones(batchsize, self.fc2.out_features, dtype=x.dtype, device=x.device)
             mask = self.dropout(self._ones)
         x = fc_stack(x, [self.fc1, self.fc2, self.fc3], [self.bn1, self.bn2, None], [True, True, False],
-                     masks=[None, mask, None])
+                     masks=[None, mask, None], sync=self._sync)
         return x, trans, trans_feat
 
 

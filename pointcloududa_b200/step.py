@@ -58,6 +58,7 @@ class StepConfig:
     precision: str = "bf16"
     feature_transform: bool = False
     ext: bool = False
+    sync_bn: bool = False         # multi-GPU: BatchNorm statistics over the clouds of all ranks instead of per rank
 
 
 class AdversarialStep:
@@ -69,7 +70,8 @@ class AdversarialStep:
         "p2p": libpcuda's NVLink peer-memory kernel (pcuda_comm_allreduce_p2p; the bucket is packed straight into the
         communicator's symmetric buffer), "nccl": ncclAllReduce through libpcuda's own communicator, "torch":
         torch.distributed.all_reduce between two captured half-graphs (round-1 behaviour), "auto": p2p when peer memory
-        is available, else nccl.  p2p / nccl are captured inside the ONE graph of the step."""
+        is available, else nccl.  p2p / nccl are captured inside the ONE graph of the step.  "local": ignore the process
+        group (a single-process step inside a multi-rank job, e.g. as the reference of a parity test)."""
         self.cfg = cfg
         self.device = device
         torch.manual_seed(seed)
@@ -82,9 +84,10 @@ class AdversarialStep:
         self._world = 1
         self.comm: Optional[pdist.PcudaComm] = None
         self.exchange = "none"
+        self._force_local = exchange == "local"
         self._sync_world()
         if self._world > 1 and device.type == "cuda":
-            if exchange not in ("auto", "p2p", "nccl", "torch"):
+            if exchange not in ("auto", "p2p", "nccl", "torch", "local"):
                 raise ValueError(f"unknown exchange {exchange!r}")
             if exchange != "torch":
                 numel = sum(p.numel() for p in self.d4.parameters())
@@ -94,6 +97,10 @@ class AdversarialStep:
                 self.exchange = "p2p" if self.comm.p2p else "nccl"
             else:
                 self.exchange = "torch"
+        if cfg.sync_bn and self._world > 1:
+            if self.comm is None:
+                raise ValueError("sync_bn needs libpcuda's communicator (exchange 'auto', 'p2p' or 'nccl')")
+            self.d4.set_sync_bn(self.comm)
         if self.exchange == "p2p":
             numel = sum(p.numel() for p in self.d4.parameters())
             self.bucket = pdist.GradBucket(self.d4.parameters(), flat=self.comm.buf_in[:numel])
@@ -261,7 +268,7 @@ class AdversarialStep:
 
     def _sync_world(self) -> None:
         import torch.distributed as dist
-        self._world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._world = dist.get_world_size() if dist.is_available() and dist.is_initialized() and not self._force_local else 1
 
     def _body(self) -> None:
         self._sync_world()

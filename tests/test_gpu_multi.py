@@ -189,5 +189,155 @@ def test_adversarial_step_two_ranks_every_exchange_mode():
     _run("_step_body")
 
 
+# ---------------------------------------------------------------------------------------------------------
+def _syncbn_body(rank, world):
+    """Cross-rank BatchNorm: R ranks x B/R clouds == one process x B clouds — for a shared-MLP stack, the
+    whole discriminator (default and -ft -extd4) and the whole adversarial step."""
+    import numpy as np
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from oracle import torch_step
+    from pointcloududa_b200 import dist as pdist
+    from pointcloududa_b200.networks.PointNetCls import PointNetCls, shared_mlp
+    from pointcloududa_b200.step import AdversarialStep, StepConfig
+    dev = torch.device("cuda", rank)
+    comm = pdist.PcudaComm(dev)
+
+    def rel(a, b):
+        return (a.double() - b.double()).abs().max().item() / max(b.double().abs().max().item(), 1e-30)
+
+    def allsum(t):
+        t = t.clone()
+        dist.all_reduce(t)
+        return t
+
+    # ---- (1) one shared-MLP stack (fp32 kernels and the tensor-core path) -------------------------------------
+    import torch.nn as nn
+    for precision, tol in (("fp32", 2e-5), ("bf16", 2e-3)):
+        torch.manual_seed(7)
+        chans, relus = [3, 64, 128, 1024], [True, True, False]
+        convs = [nn.Conv1d(chans[i], chans[i + 1], 1).to(dev) for i in range(3)]
+        bns = [nn.BatchNorm1d(chans[i + 1]).to(dev) for i in range(3)]
+        g = torch.Generator().manual_seed(3)
+        for bn in bns:
+            with torch.no_grad():
+                bn.weight.copy_(1.0 + 0.3 * torch.randn(bn.weight.shape, generator=g))
+                bn.bias.copy_(0.2 * torch.randn(bn.bias.shape, generator=g))
+        Bg, N = 6, 260
+        pts = (torch.rand(Bg, N, 3, generator=g) * (torch.rand(Bg, 1, 3, generator=g) * 0.7 + 0.3)).to(dev)
+        wgt = torch.randn(Bg, 1024, generator=g).to(dev)
+        Br = Bg // world
+
+        def run(x_rows, w_rows, sync):
+            for m in convs + bns:
+                for p_ in m.parameters():
+                    p_.grad = None
+            for bn in bns:
+                bn.reset_running_stats()
+            x = x_rows.transpose(2, 1).detach().requires_grad_(True)
+            out = shared_mlp(x, convs, bns, relus, pool=True, precision=precision, sync=sync)
+            (out * w_rows).sum().backward()
+            return (out.detach(), x.grad.clone(), [c.weight.grad.clone() for c in convs] + [b.weight.grad.clone() for b in bns] +
+                    [b.bias.grad.clone() for b in bns], [b.running_mean.clone() for b in bns] + [b.running_var.clone() for b in bns])
+
+        full = run(pts, wgt, None)
+        mine = run(pts[rank * Br:(rank + 1) * Br], wgt[rank * Br:(rank + 1) * Br], comm)
+        sl = slice(rank * Br, (rank + 1) * Br)
+        assert rel(mine[0], full[0][sl]) < tol, (precision, "out", rel(mine[0], full[0][sl]))
+        assert rel(mine[1], full[1][sl]) < 20 * tol, (precision, "grad_x", rel(mine[1], full[1][sl]))
+        for i, (a, b) in enumerate(zip(mine[2], full[2])):
+            assert rel(allsum(a), b) < 20 * tol, (precision, "param grad", i, rel(allsum(a), b))
+        for i, (a, b) in enumerate(zip(mine[3], full[3])):
+            assert rel(a, b) < max(tol, 1e-4), (precision, "running stat", i, rel(a, b))
+        # and per-rank statistics really are different (the test would be vacuous otherwise)
+        local = run(pts[sl], wgt[sl], None)
+        assert rel(local[0], full[0][sl]) > 10 * tol
+    print(f"rank {rank}: shared-MLP stack ok", flush=True)
+
+    # ---- (2) the whole discriminator ------------------------------------------------------------------------
+    for kw in (dict(), dict(feature_transform=True, ext=True)):
+        torch.manual_seed(11)
+        net = PointNetCls(drop=0.0, precision="fp32", **kw).to(dev).train()
+        g = torch.Generator().manual_seed(5)
+        Bg, N = 8, 200
+        pts = (torch.rand(Bg, N, 3, generator=g) * (torch.rand(Bg, 1, 3, generator=g) * 0.7 + 0.3)).to(dev)
+        Br = Bg // world
+        sl = slice(rank * Br, (rank + 1) * Br)
+        state0 = {k: v.clone() for k, v in net.state_dict().items()}
+
+        def run_net(rows, sync):
+            net.load_state_dict(state0)
+            net.set_sync_bn(sync)
+            for p_ in net.parameters():
+                p_.grad = None
+            x = rows.transpose(2, 1).detach().requires_grad_(True)
+            logit = net(x)[0]
+            F.binary_cross_entropy_with_logits(logit, torch.ones_like(logit)).backward()
+            return (logit.detach(), x.grad.clone(), {k: (p_.grad.clone() if p_.grad is not None else None) for k, p_ in net.named_parameters()},
+                    {k: v.clone() for k, v in net.state_dict().items() if "running" in k and ".in" not in k and not k.startswith("in")})
+
+        full = run_net(pts, None)
+        mine = run_net(pts[sl], comm)
+        net.set_sync_bn(None)
+        assert rel(mine[0], full[0][sl]) < 1e-4, (kw, rel(mine[0], full[0][sl]))
+        # the rank back-propagates the mean over ITS rows: world x the single-process gradient of these rows
+        assert rel(mine[1] / world, full[1][sl]) < 5e-3, (kw, rel(mine[1] / world, full[1][sl]))
+        worst = 0.0
+        for k, gfull in full[2].items():
+            if gfull is None or gfull.abs().max().item() < 1e-9:
+                continue
+            leaf = k.rsplit(".", 2)[-2]
+            if k.endswith(".bias") and (leaf.startswith("conv") or leaf in ("fc1", "fc2")):
+                continue
+            e = rel(allsum(mine[2][k]) / world, gfull)
+            worst = max(worst, e)
+            assert e < 5e-3, (kw, k, e)
+        for k, v in full[3].items():
+            assert rel(mine[3][k], v) < 1e-4, (kw, k)
+        print(f"rank {rank}: PointNetCls{kw} ok (worst parameter-gradient error {worst:.1e})", flush=True)
+
+    # ---- (3) the whole step: 2 ranks x B/2 with sync_bn == one process x B --------------------------------------
+    w = dict(B=8, C=4, H=32, W=32, N=300, activation="sigmoid", normalize=False, return_prob=False)
+    host = torch_step.conditioned_inputs(w, seed=900)
+    Br = w["B"] // world
+    sl = slice(rank * Br, (rank + 1) * Br)
+    lr = 2.5e-3
+    ref = AdversarialStep(StepConfig(B=w["B"], C=4, H=32, W=32, N=300, precision="fp32", lr_dis=lr), dev, seed=0, exchange="local")
+    st = AdversarialStep(StepConfig(B=Br, C=4, H=32, W=32, N=300, precision="fp32", lr_dis=lr, sync_bn=True), dev, seed=0, exchange="auto")
+    for s_ in (ref, st):
+        for m in s_.d4.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+    ref.load_inputs(host, non_blocking=False)
+    st.load_inputs({k: v[sl] for k, v in host.items()}, non_blocking=False)
+    p0 = torch.cat([p_.detach().reshape(-1) for p_ in ref.d4.parameters()]).clone()
+    for graph in (False, True):
+        if graph:
+            st.capture(warmup=1)
+        r_ref = ref.run().clone()
+        r_mine = st.run().clone()
+        torch.cuda.synchronize()
+        r_all = allsum(r_mine) / world            # every field is a mean over the rank's rows
+        for i in (3, 4, 5, 6, 7):                 # adv_point_loss, d4 losses, accuracies
+            assert abs(r_all[i].item() - r_ref[i].item()) <= 2e-4 * max(abs(r_ref[i].item()), 1e-3), (graph, i, r_all[i].item(), r_ref[i].item())
+        assert rel(st.grad_vertT / world, ref.grad_vertT[sl]) < 5e-3, (graph, rel(st.grad_vertT / world, ref.grad_vertT[sl]))
+        assert rel(st._grad_final, ref.bucket.flat) < 5e-3, (graph, rel(st._grad_final, ref.bucket.flat))
+        pa = torch.cat([p_.detach().reshape(-1) for p_ in st.d4.parameters()])
+        pb = torch.cat([p_.detach().reshape(-1) for p_ in ref.d4.parameters()])
+        upd = (pb - p0).abs().max().item()
+        assert (pa - pb).abs().max().item() <= 5e-3 * upd + 1e-7, (graph, (pa - pb).abs().max().item(), upd)
+        for (k, a), (_, b) in zip(st.d4.state_dict().items(), ref.d4.state_dict().items()):
+            if "running" in k and ".in" not in k and not k.startswith("in"):
+                assert rel(a, b) < 2e-4, (graph, k, rel(a, b))
+        print(f"rank {rank}: step graph={graph} ok", flush=True)
+    dist.barrier()
+    st.close()
+    comm.destroy()
+
+
+def test_cross_rank_batchnorm_equals_single_process():
+    _run("_syncbn_body", timeout=300)
+
+
 if __name__ == "__main__":
     _worker_main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))

@@ -36,10 +36,24 @@ def test_kernel_work_table_covers_the_profiled_step():
     for k in ours:
         hits = [frag for frag in bench.KERNEL_WORK if frag in k]
         assert hits, f"no algorithmic-work model for kernel {k}"
-        bound, work = bench.KERNEL_WORK[hits[0]]
-        assert bound in ("hbm", "tensor") and work(w) > 0
+        flops_f, bytes_f = bench.KERNEL_WORK[hits[0]]
+        assert bytes_f(w) > 0 and (flops_f is None or flops_f(w) > 0)
         traffic, src = bench.ncu_traffic("cfg2", "pcuda::" + k)
         assert traffic is not None and traffic >= 0 and "traffic_cfg2.json" in src
+        rec = bench.kernel_roofline("pcuda::" + k, w, 10e-6, bench.peaks(), traffic)
+        assert rec["bound"] in ("hbm", "tensor", "l2-latency", "fp32-issue") and rec["frac"] > 0
+
+
+def test_kernel_roofline_picks_the_limiting_roof():
+    import bench
+    pk = bench.peaks()
+    w = dict(B=32, N=4096, C=5, H=256, W=256, return_prob=True)
+    pooled = bench.kernel_roofline("pcuda::tc::ws_kernel<1>", w, 46e-6, pk)
+    assert pooled["bound"] == "tensor" and 0.3 < pooled["frac"] < 0.7
+    dgrad = bench.kernel_roofline("pcuda::tc::ws_kernel<2>", w, 39e-6, pk)
+    assert dgrad["bound"] == "hbm" and dgrad["frac_hbm"] > 5 * dgrad["frac_tensor"]
+    small = bench.kernel_roofline("pcuda::pool_sparse_kernel<4, 12, 1>", dict(bench.WORKLOADS["cfg2"]), 20e-6, pk, traffic=1.8e6)
+    assert small["bound"] == "l2-latency" and small["traffic_over_algorithmic"] < 0.5
 
 
 def test_step_input_layout_offsets_are_aligned():
