@@ -283,15 +283,19 @@ def _syncbn_body(rank, world):
         # the rank back-propagates the mean over ITS rows: world x the single-process gradient of these rows
         assert rel(mine[1] / world, full[1][sl]) < 5e-3, (kw, rel(mine[1] / world, full[1][sl]))
         worst = 0.0
+        gmax = max(g_.abs().max().item() for g_ in full[2].values() if g_ is not None)
         for k, gfull in full[2].items():
-            if gfull is None or gfull.abs().max().item() < 1e-9:
+            if gfull is None:
                 continue
             leaf = k.rsplit(".", 2)[-2]
             if k.endswith(".bias") and (leaf.startswith("conv") or leaf in ("fc1", "fc2")):
                 continue
-            e = rel(allsum(mine[2][k]) / world, gfull)
+            # gradients that are mathematically (near) zero — a BatchNorm shift that the next train-mode BatchNorm
+            # removes — hold cancellation noise on both sides: compared on the scale of the largest gradient
+            scale = max(gfull.abs().max().item(), 1e-4 * gmax)
+            e = (allsum(mine[2][k]) / world - gfull).abs().max().item() / scale
             worst = max(worst, e)
-            assert e < 5e-3, (kw, k, e)
+            assert e < 5e-3, (kw, k, e, gfull.abs().max().item(), gmax)
         for k, v in full[3].items():
             assert rel(mine[3][k], v) < 1e-4, (kw, k)
         print(f"rank {rank}: PointNetCls{kw} ok (worst parameter-gradient error {worst:.1e})", flush=True)
