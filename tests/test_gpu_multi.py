@@ -325,6 +325,13 @@ def _syncbn_body(rank, world):
         for i in (3, 4, 5, 6, 7):                 # adv_point_loss, d4 losses, accuracies
             assert abs(r_all[i].item() - r_ref[i].item()) <= 2e-4 * max(abs(r_ref[i].item()), 1e-3), (graph, i, r_all[i].item(), r_ref[i].item())
         assert rel(st.grad_vertT / world, ref.grad_vertT[sl]) < 5e-3, (graph, rel(st.grad_vertT / world, ref.grad_vertT[sl]))
+        if rel(st._grad_final, ref.bucket.flat) >= 5e-3:
+            off = 0
+            for k, p_ in zip(st._pnames, st.bucket.params):
+                a, b = st._grad_final[off:off + p_.numel()].double(), ref.bucket.flat[off:off + p_.numel()].double()
+                off += p_.numel()
+                if b.abs().max().item() > 1e-9:
+                    print(f"rank {rank}: {k}: ratio {(a * b).sum().item() / (b * b).sum().item():.4f} err {rel(a, b):.2e}", flush=True)
         assert rel(st._grad_final, ref.bucket.flat) < 5e-3, (graph, rel(st._grad_final, ref.bucket.flat))
         pa = torch.cat([p_.detach().reshape(-1) for p_ in st.d4.parameters()])
         pb = torch.cat([p_.detach().reshape(-1) for p_ in ref.d4.parameters()])
