@@ -326,6 +326,10 @@ def _syncbn_body(rank, world):
             assert abs(r_all[i].item() - r_ref[i].item()) <= 2e-4 * max(abs(r_ref[i].item()), 1e-3), (graph, i, r_all[i].item(), r_ref[i].item())
         assert rel(st.grad_vertT / world, ref.grad_vertT[sl]) < 5e-3, (graph, rel(st.grad_vertT / world, ref.grad_vertT[sl]))
         if rel(st._grad_final, ref.bucket.flat) >= 5e-3:
+            loc, fin, rf = st.bucket.flat.double(), st._grad_final.double(), ref.bucket.flat.double()
+            print(f"rank {rank}: exchange={st.exchange} world={st._world} local/ref={(loc * rf).sum().item() / (rf * rf).sum().item():.4f} "
+                  f"final/ref={(fin * rf).sum().item() / (rf * rf).sum().item():.4f} |local-final|={(loc - fin).abs().max().item():.3e} "
+                  f"same_storage={st._grad_final.data_ptr() == st.bucket.flat.data_ptr()}", flush=True)
             off = 0
             for k, p_ in zip(st._pnames, st.bucket.params):
                 a, b = st._grad_final[off:off + p_.numel()].double(), ref.bucket.flat[off:off + p_.numel()].double()
