@@ -330,6 +330,18 @@ def _syncbn_body(rank, world):
             print(f"rank {rank}: exchange={st.exchange} world={st._world} local/ref={(loc * rf).sum().item() / (rf * rf).sum().item():.4f} "
                   f"final/ref={(fin * rf).sum().item() / (rf * rf).sum().item():.4f} |local-final|={(loc - fin).abs().max().item():.3e} "
                   f"same_storage={st._grad_final.data_ptr() == st.bucket.flat.data_ptr()}", flush=True)
+            st2 = AdversarialStep(StepConfig(B=Br, C=4, H=32, W=32, N=300, precision="fp32", lr_dis=lr, sync_bn=True), dev, seed=0,
+                                  exchange="nccl", concurrent=False)
+            for m in st2.d4.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+            st2.load_inputs({k: v[sl] for k, v in host.items()}, non_blocking=False)
+            st2.run(); torch.cuda.synchronize()
+            f2 = st2._grad_final.double()
+            print(f"rank {rank}: sequential/nccl step: final/ref={(f2 * rf).sum().item() / (rf * rf).sum().item():.4f}", flush=True)
+            x_ = st2.inputs["vertS"].transpose(2, 1)
+            o_ = st2.d4(x_)[0]
+            print(f"rank {rank}: D_out4 shape {tuple(o_.shape)} sync={st2.d4._sync is not None} feat_sync={st2.d4.feat._sync is not None}", flush=True)
             off = 0
             for k, p_ in zip(st._pnames, st.bucket.params):
                 a, b = st._grad_final[off:off + p_.numel()].double(), ref.bucket.flat[off:off + p_.numel()].double()
