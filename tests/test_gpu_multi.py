@@ -366,5 +366,50 @@ def test_cross_rank_batchnorm_equals_single_process():
     _run("_syncbn_body", timeout=300)
 
 
+def _dbg_body(rank, world):
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from pointcloududa_b200 import dist as pdist, ops
+    from pointcloududa_b200.networks.PointNetCls import PointNetCls
+    dev = torch.device("cuda", rank)
+    comm = pdist.PcudaComm(dev)
+    torch.manual_seed(11)
+    net = PointNetCls(drop=0.0, precision="fp32").to(dev).train()
+    g = torch.Generator().manual_seed(5)
+    pts = (torch.rand(8, 200, 3, generator=g) * (torch.rand(8, 1, 3, generator=g) * 0.7 + 0.3)).to(dev)
+    sl = slice(rank * 4, rank * 4 + 4)
+    state0 = {k: v.clone() for k, v in net.state_dict().items()}
+    res = {}
+    for name, rows, sync, lossfn in (("full_F", pts, None, "F"), ("full_ops", pts, None, "ops"), ("sync_F", pts[sl], comm, "F"),
+                                     ("sync_ops", pts[sl], comm, "ops"), ("sync_ops_fc", pts[sl], comm, "ops_fc")):
+        net.load_state_dict(state0)
+        net.set_sync_bn(sync)
+        names = [n for n, _ in net.named_parameters()]
+        if lossfn == "ops_fc":
+            leaves = [p.detach().requires_grad_(True) for p in net.parameters()]
+            logit = torch.func.functional_call(net, dict(zip(names, leaves)), (rows.transpose(2, 1),))[0]
+        else:
+            leaves = list(net.parameters())
+            logit = net(rows.transpose(2, 1))[0]
+        if lossfn == "F":
+            loss = F.binary_cross_entropy_with_logits(logit, torch.ones_like(logit))
+        else:
+            loss, _ = ops.bce_with_logits(logit, 1.0)
+        gr = torch.autograd.grad(loss, leaves, allow_unused=True)
+        d = dict(zip(names, gr))
+        res[name] = (d["fc3.bias"].clone(), d["feat.conv2.weight"].clone(), tuple(logit.shape))
+    net.set_sync_bn(None)
+    for k, (a, b, shp) in res.items():
+        a2, b2 = a.clone(), b.clone()
+        if k.startswith("sync"):
+            dist.all_reduce(a2); dist.all_reduce(b2)
+        print(f"rank {rank}: {k}: logit {shp} fc3.bias {a.item():.6f} allsum {a2.item():.6f}  conv2 |g| {b.norm().item():.6f} allsum {b2.norm().item():.6f}", flush=True)
+    comm.destroy()
+
+
+def test_dbg():
+    _run("_dbg_body")
+
+
 if __name__ == "__main__":
     _worker_main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
