@@ -71,6 +71,7 @@ def _run(fn_name, world=2, timeout=240):
         f.flush(); f.seek(0)
         out.append(f"---- rank {r} (exit {procs[r].poll()}) ----\n" + f.read()[-6000:])
         f.close(); os.unlink(f.name)
+    print("\n".join(out))          # visible with pytest -s / in the failure report
     assert not failed and all(p.returncode == 0 for p in procs), "\n".join(out)
 
 
