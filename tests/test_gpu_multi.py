@@ -399,7 +399,42 @@ def _dbg_body(rank, world):
         gr = torch.autograd.grad(loss, leaves, allow_unused=True)
         d = dict(zip(names, gr))
         res[name] = (d["fc3.bias"].clone(), d["feat.conv2.weight"].clone(), tuple(logit.shape))
+    # the step's own P3, piece by piece
+    from oracle import torch_step
+    from pointcloududa_b200.networks.PointNetCls import deferred_bn_updates
+    from pointcloududa_b200.step import AdversarialStep, StepConfig
+    w = dict(B=8, C=4, H=32, W=32, N=300, activation="sigmoid", normalize=False, return_prob=False)
+    host = torch_step.conditioned_inputs(w, seed=900)
+    vs = host["vertS"].to(dev)
+    for name, rows, sync, deferred in (("stepin_full", vs, None, False), ("stepin_sync", vs[sl], comm, False), ("stepin_sync_deferred", vs[sl], comm, True)):
+        net.load_state_dict(state0)
+        net.set_sync_bn(sync)
+        names = [n for n, _ in net.named_parameters()]
+        leaves = [p.detach().requires_grad_(True) for p in net.parameters()]
+        sink = []
+        if deferred:
+            with deferred_bn_updates(sink):
+                logit = torch.func.functional_call(net, dict(zip(names, leaves)), (rows.transpose(2, 1),))[0]
+        else:
+            logit = torch.func.functional_call(net, dict(zip(names, leaves)), (rows.transpose(2, 1),))[0]
+        loss, _ = ops.bce_with_logits(logit, 1.0)
+        gr = torch.autograd.grad(loss, leaves, allow_unused=True)
+        d = dict(zip(names, gr))
+        res[name] = (d["fc3.bias"].clone(), d["feat.conv2.weight"].clone(), tuple(logit.shape))
     net.set_sync_bn(None)
+    ref = AdversarialStep(StepConfig(B=8, C=4, H=32, W=32, N=300, precision="fp32"), dev, seed=0, exchange="local")
+    st = AdversarialStep(StepConfig(B=4, C=4, H=32, W=32, N=300, precision="fp32", sync_bn=True), dev, seed=0, exchange="nccl", concurrent=False)
+    for s_ in (ref, st):
+        for m in s_.d4.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+    ref.load_inputs(host, non_blocking=False)
+    st.load_inputs({k: v[sl] for k, v in host.items()}, non_blocking=False)
+    ref.run(); st.run(); torch.cuda.synchronize()
+    i = st._pnames.index("fc3.bias")
+    print(f"rank {rank}: step ref fc3.bias(gs+gt) {ref.bucket.views[i].item():.6f} st local {st.bucket.views[i].item():.6f} world {st._world} "
+          f"ref world {ref._world} results ref {ref.result.tolist()} st {st.result.tolist()}", flush=True)
+    st.close()
     for k, (a, b, shp) in res.items():
         a2, b2 = a.clone(), b.clone()
         if k.startswith("sync"):
