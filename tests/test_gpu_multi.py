@@ -430,8 +430,21 @@ def _dbg_body(rank, world):
                 m.p = 0.0
     ref.load_inputs(host, non_blocking=False)
     st.load_inputs({k: v[sl] for k, v in host.items()}, non_blocking=False)
-    ref.run(); st.run(); torch.cuda.synchronize()
+    def direct(step_obj, rows_s, rows_t):
+        names = step_obj._pnames
+        tot = None
+        for rows, tgt in ((rows_s, 1.0), (rows_t, 0.0)):
+            leaves = [p.detach().requires_grad_(True) for p in step_obj.d4.parameters()]
+            logit = torch.func.functional_call(step_obj.d4, dict(zip(names, leaves)), (rows.transpose(2, 1),))[0]
+            loss, _ = ops.bce_with_logits(logit, tgt)
+            gr = torch.autograd.grad(loss, leaves, allow_unused=True)
+            tot = [g.clone() for g in gr] if tot is None else [a + b for a, b in zip(tot, gr)]
+        return tot
     i = st._pnames.index("fc3.bias")
+    d_ref = direct(ref, ref.inputs["vertS"], ref.inputs["vertT"])
+    d_st = direct(st, st.inputs["vertS"], st.inputs["vertT"])
+    print(f"rank {rank}: direct ref fc3.bias {d_ref[i].item():.6f}  direct st (sync) {d_st[i].item():.6f}", flush=True)
+    ref.run(); st.run(); torch.cuda.synchronize()
     print(f"rank {rank}: step ref fc3.bias(gs+gt) {ref.bucket.views[i].item():.6f} st local {st.bucket.views[i].item():.6f} world {st._world} "
           f"ref world {ref._world} results ref {ref.result.tolist()} st {st.result.tolist()}", flush=True)
     st.close()
