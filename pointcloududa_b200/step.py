@@ -252,6 +252,9 @@ class AdversarialStep:
 
     def _exchange(self) -> None:
         """Sum of the (pre-divided) gradient bucket over the ranks; sets where SGD reads the result."""
+        if self._world == 1:                 # single process, or exchange="local" inside a multi-rank job
+            self._grad_final = self.bucket.flat
+            return
         if self.exchange == "p2p":
             self._grad_final = self.comm.allreduce_p2p(self.bucket.numel)
         elif self.exchange == "nccl":

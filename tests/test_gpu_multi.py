@@ -326,29 +326,6 @@ def _syncbn_body(rank, world):
         for i in (3, 4, 5, 6, 7):                 # adv_point_loss, d4 losses, accuracies
             assert abs(r_all[i].item() - r_ref[i].item()) <= 2e-4 * max(abs(r_ref[i].item()), 1e-3), (graph, i, r_all[i].item(), r_ref[i].item())
         assert rel(st.grad_vertT / world, ref.grad_vertT[sl]) < 5e-3, (graph, rel(st.grad_vertT / world, ref.grad_vertT[sl]))
-        if rel(st._grad_final, ref.bucket.flat) >= 5e-3:
-            loc, fin, rf = st.bucket.flat.double(), st._grad_final.double(), ref.bucket.flat.double()
-            print(f"rank {rank}: exchange={st.exchange} world={st._world} local/ref={(loc * rf).sum().item() / (rf * rf).sum().item():.4f} "
-                  f"final/ref={(fin * rf).sum().item() / (rf * rf).sum().item():.4f} |local-final|={(loc - fin).abs().max().item():.3e} "
-                  f"same_storage={st._grad_final.data_ptr() == st.bucket.flat.data_ptr()}", flush=True)
-            st2 = AdversarialStep(StepConfig(B=Br, C=4, H=32, W=32, N=300, precision="fp32", lr_dis=lr, sync_bn=True), dev, seed=0,
-                                  exchange="nccl", concurrent=False)
-            for m in st2.d4.modules():
-                if isinstance(m, torch.nn.Dropout):
-                    m.p = 0.0
-            st2.load_inputs({k: v[sl] for k, v in host.items()}, non_blocking=False)
-            st2.run(); torch.cuda.synchronize()
-            f2 = st2._grad_final.double()
-            print(f"rank {rank}: sequential/nccl step: final/ref={(f2 * rf).sum().item() / (rf * rf).sum().item():.4f}", flush=True)
-            x_ = st2.inputs["vertS"].transpose(2, 1)
-            o_ = st2.d4(x_)[0]
-            print(f"rank {rank}: D_out4 shape {tuple(o_.shape)} sync={st2.d4._sync is not None} feat_sync={st2.d4.feat._sync is not None}", flush=True)
-            off = 0
-            for k, p_ in zip(st._pnames, st.bucket.params):
-                a, b = st._grad_final[off:off + p_.numel()].double(), ref.bucket.flat[off:off + p_.numel()].double()
-                off += p_.numel()
-                if b.abs().max().item() > 1e-9:
-                    print(f"rank {rank}: {k}: ratio {(a * b).sum().item() / (b * b).sum().item():.4f} err {rel(a, b):.2e}", flush=True)
         assert rel(st._grad_final, ref.bucket.flat) < 5e-3, (graph, rel(st._grad_final, ref.bucket.flat))
         pa = torch.cat([p_.detach().reshape(-1) for p_ in st.d4.parameters()])
         pb = torch.cat([p_.detach().reshape(-1) for p_ in ref.d4.parameters()])
@@ -365,99 +342,6 @@ def _syncbn_body(rank, world):
 
 def test_cross_rank_batchnorm_equals_single_process():
     _run("_syncbn_body", timeout=300)
-
-
-def _dbg_body(rank, world):
-    import torch.distributed as dist
-    import torch.nn.functional as F
-    from pointcloududa_b200 import dist as pdist, ops
-    from pointcloududa_b200.networks.PointNetCls import PointNetCls
-    dev = torch.device("cuda", rank)
-    comm = pdist.PcudaComm(dev)
-    torch.manual_seed(11)
-    net = PointNetCls(drop=0.0, precision="fp32").to(dev).train()
-    g = torch.Generator().manual_seed(5)
-    pts = (torch.rand(8, 200, 3, generator=g) * (torch.rand(8, 1, 3, generator=g) * 0.7 + 0.3)).to(dev)
-    sl = slice(rank * 4, rank * 4 + 4)
-    state0 = {k: v.clone() for k, v in net.state_dict().items()}
-    res = {}
-    for name, rows, sync, lossfn in (("full_F", pts, None, "F"), ("full_ops", pts, None, "ops"), ("sync_F", pts[sl], comm, "F"),
-                                     ("sync_ops", pts[sl], comm, "ops"), ("sync_ops_fc", pts[sl], comm, "ops_fc")):
-        net.load_state_dict(state0)
-        net.set_sync_bn(sync)
-        names = [n for n, _ in net.named_parameters()]
-        if lossfn == "ops_fc":
-            leaves = [p.detach().requires_grad_(True) for p in net.parameters()]
-            logit = torch.func.functional_call(net, dict(zip(names, leaves)), (rows.transpose(2, 1),))[0]
-        else:
-            leaves = list(net.parameters())
-            logit = net(rows.transpose(2, 1))[0]
-        if lossfn == "F":
-            loss = F.binary_cross_entropy_with_logits(logit, torch.ones_like(logit))
-        else:
-            loss, _ = ops.bce_with_logits(logit, 1.0)
-        gr = torch.autograd.grad(loss, leaves, allow_unused=True)
-        d = dict(zip(names, gr))
-        res[name] = (d["fc3.bias"].clone(), d["feat.conv2.weight"].clone(), tuple(logit.shape))
-    # the step's own P3, piece by piece
-    from oracle import torch_step
-    from pointcloududa_b200.networks.PointNetCls import deferred_bn_updates
-    from pointcloududa_b200.step import AdversarialStep, StepConfig
-    w = dict(B=8, C=4, H=32, W=32, N=300, activation="sigmoid", normalize=False, return_prob=False)
-    host = torch_step.conditioned_inputs(w, seed=900)
-    vs = host["vertS"].to(dev)
-    for name, rows, sync, deferred in (("stepin_full", vs, None, False), ("stepin_sync", vs[sl], comm, False), ("stepin_sync_deferred", vs[sl], comm, True)):
-        net.load_state_dict(state0)
-        net.set_sync_bn(sync)
-        names = [n for n, _ in net.named_parameters()]
-        leaves = [p.detach().requires_grad_(True) for p in net.parameters()]
-        sink = []
-        if deferred:
-            with deferred_bn_updates(sink):
-                logit = torch.func.functional_call(net, dict(zip(names, leaves)), (rows.transpose(2, 1),))[0]
-        else:
-            logit = torch.func.functional_call(net, dict(zip(names, leaves)), (rows.transpose(2, 1),))[0]
-        loss, _ = ops.bce_with_logits(logit, 1.0)
-        gr = torch.autograd.grad(loss, leaves, allow_unused=True)
-        d = dict(zip(names, gr))
-        res[name] = (d["fc3.bias"].clone(), d["feat.conv2.weight"].clone(), tuple(logit.shape))
-    net.set_sync_bn(None)
-    ref = AdversarialStep(StepConfig(B=8, C=4, H=32, W=32, N=300, precision="fp32"), dev, seed=0, exchange="local")
-    st = AdversarialStep(StepConfig(B=4, C=4, H=32, W=32, N=300, precision="fp32", sync_bn=True), dev, seed=0, exchange="nccl", concurrent=False)
-    for s_ in (ref, st):
-        for m in s_.d4.modules():
-            if isinstance(m, torch.nn.Dropout):
-                m.p = 0.0
-    ref.load_inputs(host, non_blocking=False)
-    st.load_inputs({k: v[sl] for k, v in host.items()}, non_blocking=False)
-    def direct(step_obj, rows_s, rows_t):
-        names = step_obj._pnames
-        tot = None
-        for rows, tgt in ((rows_s, 1.0), (rows_t, 0.0)):
-            leaves = [p.detach().requires_grad_(True) for p in step_obj.d4.parameters()]
-            logit = torch.func.functional_call(step_obj.d4, dict(zip(names, leaves)), (rows.transpose(2, 1),))[0]
-            loss, _ = ops.bce_with_logits(logit, tgt)
-            gr = torch.autograd.grad(loss, leaves, allow_unused=True)
-            tot = [g.clone() for g in gr] if tot is None else [a + b for a, b in zip(tot, gr)]
-        return tot
-    i = st._pnames.index("fc3.bias")
-    d_ref = direct(ref, ref.inputs["vertS"], ref.inputs["vertT"])
-    d_st = direct(st, st.inputs["vertS"], st.inputs["vertT"])
-    print(f"rank {rank}: direct ref fc3.bias {d_ref[i].item():.6f}  direct st (sync) {d_st[i].item():.6f}", flush=True)
-    ref.run(); st.run(); torch.cuda.synchronize()
-    print(f"rank {rank}: step ref fc3.bias(gs+gt) {ref.bucket.views[i].item():.6f} st local {st.bucket.views[i].item():.6f} world {st._world} "
-          f"ref world {ref._world} results ref {ref.result.tolist()} st {st.result.tolist()}", flush=True)
-    st.close()
-    for k, (a, b, shp) in res.items():
-        a2, b2 = a.clone(), b.clone()
-        if k.startswith("sync"):
-            dist.all_reduce(a2); dist.all_reduce(b2)
-        print(f"rank {rank}: {k}: logit {shp} fc3.bias {a.item():.6f} allsum {a2.item():.6f}  conv2 |g| {b.norm().item():.6f} allsum {b2.norm().item():.6f}", flush=True)
-    comm.destroy()
-
-
-def test_dbg():
-    _run("_dbg_body")
 
 
 if __name__ == "__main__":
