@@ -319,6 +319,11 @@ def _syncbn_body(rank, world):
     for graph in (False, True):
         if graph:
             st.capture(warmup=1)
+        # every step is compared from IDENTICAL state (two trajectories that differ by rounding drift apart through the
+        # small-batch BatchNorms; see tests/test_gpu_step_parity.py): in-place copies, the captured graph stays valid
+        st.d4.load_state_dict(ref.d4.state_dict())
+        st.opt.momentum_buffer.copy_(ref.opt.momentum_buffer)
+        p0 = torch.cat([p_.detach().reshape(-1) for p_ in ref.d4.parameters()]).clone()
         r_ref = ref.run().clone()
         r_mine = st.run().clone()
         torch.cuda.synchronize()
