@@ -607,12 +607,12 @@ def measure_step(step, host_flat, result_host, flush, steps: int, world: int, de
     return t_dev, t_e2e
 
 
-def build_step(w: dict, rank: int, dev, precision: str, use_graph: bool, exchange: str = "auto"):
+def build_step(w: dict, rank: int, dev, precision: str, use_graph: bool, exchange: str = "auto", sync_bn: bool = False):
     """AdversarialStep of workload `w` with its inputs loaded (per-rank synthetic shard), captured and warmed up."""
     import torch
     from pointcloududa_b200.step import RESULT_FIELDS, AdversarialStep, StepConfig
     cfg = StepConfig(B=w["B"], C=w["C"], H=w["H"], W=w["W"], N=w["N"], activation=w["activation"],
-                     normalize=w["normalize"], return_prob=w["return_prob"], precision=precision)
+                     normalize=w["normalize"], return_prob=w["return_prob"], precision=precision, sync_bn=sync_bn)
     step = AdversarialStep(cfg, dev, seed=0, exchange=exchange)
     # one pinned host buffer holding a step's inputs in the step's flat layout: one H2D copy per step
     host_flat = torch.zeros(step.input_numel(), dtype=torch.float32).pin_memory()
@@ -632,15 +632,18 @@ def scale_lines(args, rank: int, world: int, dev, flush):
     import torch
     out = {}
     steps = max(5, min(args.steps, 20))
-    for name, scaling in (("cfg5_rank", "weak"), ("cfg3", "strong")):
-        w = dict(WORKLOADS[name])
+    for name, scaling in (("cfg5_rank", "weak"), ("cfg3", "strong"), ("cfg3_syncbn", "strong")):
+        sync_bn = name.endswith("_syncbn")          # cfg-3 with BatchNorm statistics over the clouds of all ranks
+        if sync_bn and (world == 1 or args.exchange == "torch"):
+            continue
+        w = dict(WORKLOADS[name.replace("_syncbn", "")])
         if scaling == "strong":
             if w["B"] % world != 0 or w["B"] // world < 2:
                 out[name] = {"skipped": f"global batch {w['B']} does not split into >= 2 clouds on each of {world} ranks"}
                 continue
             w["B"] //= world
         try:
-            step, host_flat, result_host = build_step(w, rank, dev, args.precision, not args.no_graph, args.exchange)
+            step, host_flat, result_host = build_step(w, rank, dev, args.precision, not args.no_graph, args.exchange, sync_bn)
             if not args.no_graph:
                 step.capture(warmup=2)
             for _ in range(3):
@@ -648,8 +651,8 @@ def scale_lines(args, rank: int, world: int, dev, flush):
             torch.cuda.synchronize()
             t_dev, t_e2e = measure_step(step, host_flat, result_host, flush, steps, world, dev)
             units = world if scaling == "weak" else 1           # per-rank-shard steps (weak) / global-batch steps (strong)
-            out[name] = {"scaling": scaling, "per_rank_batch": w["B"], "global_batch": w["B"] * world, "steps": steps,
-                         "workload": workload_label(name, w), "exchange": step.exchange,
+            out[name] = {"scaling": scaling, "batchnorm": "cross-rank statistics" if sync_bn else "per-rank statistics", "per_rank_batch": w["B"], "global_batch": w["B"] * world, "steps": steps,
+                         "workload": workload_label(name.replace("_syncbn", ""), w), "exchange": step.exchange,
                          "value": units * steps / t_dev,
                          "unit": "global-batch steps/s" if scaling == "strong" else "per-rank-shard steps/s summed over ranks",
                          "ms_per_step": t_dev / steps * 1e3, "samples_per_s": world * w["B"] * steps / t_dev,
@@ -720,6 +723,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pdist.bind_to_gpu_numa(local) if world > 1 else None      # before any pinned host allocation
     w = dict(WORKLOADS[args.workload])
     pk = peaks()
     step, host_flat, result_host = build_step(w, rank, dev, args.precision, not args.no_graph, args.exchange)
@@ -797,7 +801,7 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "samples_per_s": world * w["B"] * args.steps / t_dev,
-            "exchange": step.exchange, "scale": scale,
+            "exchange": step.exchange, "host_affinity": numa, "scale": scale,
             "roofline": roof, "kernels": kernel_shares, "ops": breakdown, "large": large, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "clocks": clocks,
             "last_step": last,
         }

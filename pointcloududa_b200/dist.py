@@ -205,6 +205,26 @@ def allreduce_scalars(values: Sequence[torch.Tensor], group=None) -> torch.Tenso
     return t
 
 
+def bind_to_gpu_numa(local_rank: int) -> Optional[str]:
+    """Pin this process (and with it the pages of the pinned host buffers it allocates afterwards) to the CPU cores
+    NVML reports as local to GPU `local_rank`.  With one process per GPU feeding inputs from pinned host memory, all
+    ranks otherwise share whatever NUMA node the scheduler happened to start them on.  Returns a description, or None
+    when NVML / affinity control is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} cores local to GPU {local_rank}"
+    except Exception:
+        return None
+
+
 def init_from_env(backend: Optional[str] = None) -> tuple:
     """(rank, local_rank, world) from torchrun's environment; initialises the process group if
     WORLD_SIZE > 1."""
