@@ -349,5 +349,33 @@ def test_cross_rank_batchnorm_equals_single_process():
     _run("_syncbn_body", timeout=300)
 
 
+def test_one_process_two_devices():
+    """The opt-in to large dynamic shared memory is per (kernel, device): a process that has run D4 on cuda:0 runs it on
+    cuda:1 as well (round-1 advisory: process-wide flags left every device but the first without the attribute)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    import torch.nn.functional as F
+    from pointcloududa_b200.networks.PointNetCls import PointNetCls
+    from pointcloududa_b200.utils.loss import batch_NN_loss, entropy_map
+    outs = []
+    for d in (0, 1, 0):
+        dev = torch.device("cuda", d)
+        torch.manual_seed(0)
+        net = PointNetCls(drop=0.0).to(dev).train()
+        g = torch.Generator().manual_seed(1)
+        pts = torch.rand(4, 300, 3, generator=g).to(dev).requires_grad_(True)
+        logit = net(pts.transpose(2, 1))[0]
+        F.binary_cross_entropy_with_logits(logit, torch.ones_like(logit)).backward()
+        z = torch.randn(2, 4, 32, 32, generator=g).to(dev)
+        m = entropy_map(z)
+        loss = batch_NN_loss(x=pts.detach(), y=torch.rand(4, 300, 3, generator=g).to(dev))
+        torch.cuda.synchronize(dev)
+        assert torch.isfinite(pts.grad).all() and torch.isfinite(m).all()
+        outs.append((logit.detach().cpu(), loss.item()))
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-3, atol=1e-4) and torch.allclose(outs[0][0], outs[2][0], rtol=1e-3, atol=1e-4)
+    assert abs(outs[0][1] - outs[1][1]) < 1e-6
+
+
 if __name__ == "__main__":
     _worker_main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
