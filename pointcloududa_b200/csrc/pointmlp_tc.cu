@@ -539,32 +539,12 @@ __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsPa
                 qa[0] += q2.x + q2.y;
               }
               if (!(p.dbg & 16)) {
-                if (FULL) {
-                  // The maximum of the 32 columns by a tree of 3-input maxima (15 FMNMX3 + 1 FMNMX instead of 96
-                  // compare / select / select), and the index only when some lane of the warp has a new running
-                  // maximum — a record: over the T chunks of a cloud a channel sets ~ln T of them, so with 32
-                  // channels per warp about 60 % of the chunks at N = 4096 pay the 62-instruction search, the rest
-                  // nothing.  Same result as the element-wise scan: strict `>` keeps the earlier chunk on ties, the
-                  // search returns the FIRST column that holds the maximum.
-                  float m = v[0];
 #pragma unroll
-                  for (int i = 1; i < 31; i += 2) m = fmax3(m, v[i], v[i + 1]);
-                  m = fmaxf(m, v[31]);
-                  const bool rec = m > bv[0];
-                  if (__any_sync(0xffffffffu, rec)) {
-                    int idx = 31;
-#pragma unroll
-                    for (int i = 30; i >= 0; --i) idx = (v[i] == m) ? i : idx;
-                    if (rec) { bv[0] = m; bi[0] = nb + idx; }
-                  }
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) {
-                    if (i < ncol) {
-                      const bool gt = v[i] > bv[0];
-                      bv[0] = gt ? v[i] : bv[0];
-                      bi[0] = gt ? nb + i : bi[0];
-                    }
+                for (int i = 0; i < 32; ++i) {
+                  if (FULL || i < ncol) {
+                    const bool gt = v[i] > bv[i & 3];
+                    bv[i & 3] = gt ? v[i] : bv[i & 3];
+                    bi[i & 3] = gt ? nb + i : bi[i & 3];
                   }
                 }
               }
