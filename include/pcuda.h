@@ -19,6 +19,7 @@
  *   pcuda_bce_logits              F.binary_cross_entropy_with_logits + accuracy, train_mscmrseg.py:233,286-296,316-322
  *   pcuda_grad_sum_pack /         .grad accumulation of the two D4 backward passes (train_mscmrseg.py:288,319) and
  *   pcuda_sgd_momentum_step       optim_dis4.step() = torch.optim.SGD(momentum, weight_decay) (:329-330,:450-455)
+ *   pcuda_fps                     utils/npy2point.py:11-18 (graipher: farthest-point sampling of the GT boundary clouds)
  *   pcuda_comm_*                  no counterpart (the reference is single-process): sum of D4's parameter gradients over
  *                                 the batch-sharded ranks in front of optim_dis4.step()
  *
@@ -335,6 +336,15 @@ int pcuda_sgd_momentum_step(const pcuda_param_slot_t* slots /*host*/, int n, con
  */
 int pcuda_bce_logits(const float* logit, int n, float target, float weight, float* loss, float* grad_logit,
                      float* accuracy, pcuda_stream_t stream);
+
+/* ---- farthest-point sampling ------------------------------------------------------
+ * utils/npy2point.py:11-18 `graipher(pts, K, dim)`: the K points of a cloud chosen greedily by largest squared distance
+ * to the set chosen so far, starting from point starts[b] (the reference draws it with np.random.randint), float64
+ * arithmetic and np.argmax tie-breaking (first index), so the selection is bit-identical to numpy's.
+ * pts: [B, Vmax, dim] float64, counts[b] (<= Vmax, NULL: all Vmax) valid points of cloud b, dim <= 3, Vmax <= 25600.
+ * out_pts: [B, K, dim] float64, out_idx: [B, K] int32 (the chosen rows; an empty cloud gives zero rows / -1). */
+int pcuda_fps(const double* pts, const int32_t* counts, const int32_t* starts, int B, int Vmax, int K, int dim,
+              double* out_pts, int32_t* out_idx, pcuda_stream_t stream);
 
 /* ---- multi-GPU exchange ----------------------------------------------------------
  * One process per GPU; rank r holds samples [r*B/R, (r+1)*B/R).  The only data-path exchange of the step is the sum

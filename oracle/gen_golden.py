@@ -221,12 +221,57 @@ def gen_pointnet():
     print("pointnet:", list(POINTNET_CASES))
 
 
+FPS_CASES = {
+    # name: (V, dim, K, kind)
+    "grid_v2000_k300": (2000, 3, 300, "halfgrid"),      # marching-cubes-like vertices: multiples of 0.5, many exact ties
+    "uniform_v5000_k300": (5000, 3, 300, "uniform"),
+    "dim2_v700_k64": (700, 2, 64, "uniform"),
+    "dups_v512_k40": (512, 3, 40, "dups"),              # duplicated points: distance-0 ties, first index wins
+    "k_exceeds_v": (20, 3, 32, "uniform"),              # K > V: the reference keeps re-selecting index 0 once all distances are 0
+}
+
+
+def fps_points(name):
+    V, dim, K, kind = FPS_CASES[name]
+    rs = np.random.RandomState(sum(map(ord, name)))
+    if kind == "halfgrid":
+        p = rs.randint(0, 60, size=(V, dim)) * 0.5
+    elif kind == "dups":
+        base = rs.rand(V // 4, dim)
+        p = np.concatenate([base, base, base, base], axis=0)
+    else:
+        p = rs.rand(V, dim) * 100.0
+    return p.astype(np.float64), K, dim
+
+
+def gen_fps():
+    """Golden vectors of the reference's own graipher (utils/npy2point.py:11-18), the start index pinned by seeding
+    numpy's global generator exactly as a seeded data pipeline would."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_npy2point", str(REF_SRC / "utils" / "npy2point.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {}
+    for name in FPS_CASES:
+        pts, K, dim = fps_points(name)
+        np.random.seed(1234)
+        start = int(np.random.randint(len(pts)))
+        np.random.seed(1234)
+        far = mod.graipher(pts, K, dim=dim)
+        out[f"{name}/pts"] = pts
+        out[f"{name}/start"] = np.int64(start)
+        out[f"{name}/far"] = far
+    np.savez_compressed(OUT / "fps_ref.npz", **out)
+    print("fps:", list(FPS_CASES))
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(1)
     gen_chamfer()
     gen_entropy()
     gen_pointnet()
+    gen_fps()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")
 

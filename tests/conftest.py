@@ -55,6 +55,11 @@ def golden_entropy():
 
 
 @pytest.fixture(scope="session")
+def golden_fps():
+    return Golden("fps_ref.npz").cases
+
+
+@pytest.fixture(scope="session")
 def golden_pointnet():
     return Golden("pointnet_ref.npz").cases
 

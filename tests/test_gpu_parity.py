@@ -1097,3 +1097,46 @@ def test_pointnetcls_launches_no_framework_gemm():
         assert any("pcuda::" in n for n in names)
         bad = [n for n in names if any(t in n.lower() for t in ("gemm", "cutlass", "cublas", "bmm"))]
         assert not bad, bad
+
+
+# ================================================================ farthest-point sampling ===========
+@pytest.mark.parametrize("case", ["grid_v2000_k300", "uniform_v5000_k300", "dim2_v700_k64", "dups_v512_k40", "k_exceeds_v"])
+def test_fps_vs_reference_golden(golden_fps, case):
+    """pcuda_fps against the reference's own graipher output (utils/npy2point.py:11-18): bit-identical points, including
+    exact distance ties on the half-integer grid of marching-cubes vertices and duplicated points."""
+    from pointcloududa_b200.utils.npy2point import graipher, graipher_batch
+    g = golden_fps[case]
+    K, dim = g["far"].shape
+    far = graipher(g["pts"], K, dim=dim, start=int(g["start"]))
+    assert isinstance(far, np.ndarray) and far.dtype == np.float64
+    assert np.array_equal(far, g["far"])
+    # the reference's own start draw: same numpy global generator, same draw
+    np.random.seed(1234)
+    assert np.array_equal(graipher(g["pts"], K, dim=dim), g["far"])
+    # indices against the oracle, CUDA tensor in -> CUDA tensor out
+    _, idx_o = oracle.fps(g["pts"], K, int(g["start"]))
+    pts = torch.from_numpy(g["pts"]).to(DEV)
+    out, idx = graipher_batch(pts[None], K, starts=torch.tensor([int(g["start"])], dtype=torch.int32))
+    assert out.is_cuda and np.array_equal(idx[0].cpu().numpy(), idx_o)
+
+
+def test_fps_batch_ragged_and_errors():
+    from pointcloududa_b200.utils.npy2point import graipher, graipher_batch
+    rs = np.random.RandomState(3)
+    clouds = [rs.rand(n, 3) * 50 for n in (900, 17, 4000, 1)]
+    V = max(len(c) for c in clouds)
+    pts = np.zeros((len(clouds), V, 3))
+    for i, c in enumerate(clouds):
+        pts[i, :len(c)] = c
+    counts = torch.tensor([len(c) for c in clouds] + [0], dtype=torch.int32)
+    starts = torch.tensor([5, 16, 3999, 0, 0], dtype=torch.int32)
+    batch = torch.from_numpy(np.concatenate([pts, np.zeros((1, V, 3))])).to(DEV)
+    out, idx = graipher_batch(batch, 64, counts=counts, starts=starts)
+    for i, c in enumerate(clouds):
+        far, ix = oracle.fps(c, 64, int(starts[i]))
+        assert np.array_equal(out[i].cpu().numpy(), far) and np.array_equal(idx[i].cpu().numpy(), ix)
+    assert (out[4] == 0).all() and (idx[4] == -1).all()          # empty cloud: zero rows like the reference's np.zeros
+    with pytest.raises(ValueError):
+        graipher(np.zeros((0, 3)), 4, dim=3)
+    with pytest.raises(ops.PcudaError):
+        graipher_batch(torch.zeros(1, 10, 3), 4)                 # CPU tensor: no fallback

@@ -361,3 +361,15 @@ def test_reference_step_equals_torch_restatement():
                 upd = (v - start[k]).abs().max().item()
                 err = np.abs(now[k].double().numpy() - v.numpy()).max()
                 assert err <= 5e-3 * upd + 2e-7 * v.abs().max().item() + 1e-10, (k, err, upd)   # 1e-10: mathematically zero gradients
+
+
+# ---------------------------------------------------------------- farthest-point sampling ------------
+@pytest.mark.parametrize("case", ["grid_v2000_k300", "uniform_v5000_k300", "dim2_v700_k64", "dups_v512_k40", "k_exceeds_v"])
+def test_fps_oracle_vs_reference_golden(golden_fps, case):
+    """oracle.fps (graipher with the start index explicit) reproduces the reference's own selection bit for bit."""
+    g = golden_fps[case]
+    far, idx = oracle.fps(g["pts"], g["far"].shape[0], int(g["start"]))
+    assert np.array_equal(far, g["far"])
+    assert idx[0] == int(g["start"])
+    if case == "k_exceeds_v":           # once every distance is 0 np.argmax returns index 0 for good
+        assert (idx[g["pts"].shape[0]:] == 0).all()
