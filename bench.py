@@ -863,13 +863,51 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_chamfer_only(args):
+    """`--workload cfg4` (BASELINE.json configs[3]): the Chamfer-only sweep as its own line — metric = ordered pairs/s
+    at the largest size, every size under `sweep`; batch 64 sharded over the ranks, no data-path collective."""
+    import torch
+    import torch.distributed as dist
+    from pointcloududa_b200 import dist as pdist
+    from pointcloududa_b200 import ops
+    rank, local, world = pdist.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    flush = torch.empty(FLUSH_BYTES // 4, device=dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_count()
+    sweep = chamfer_sweep(rank, world, dev, flush, iters=max(3, min(args.steps, 20)))
+    launches = ops.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and "sizes" in sweep:
+        top = sweep["sizes"][str(CFG4_POINTS[-1])]
+        pk = peaks()
+        lane_peak = 148 * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6
+        line = {"metric": "chamfer_ordered_pairs_per_s", "value": top["tpairs_s"] * 1e12, "unit": "ordered pairs/s", "n_gpus": world,
+                "steps": max(3, min(args.steps, 20)), "warmup": 2, "ms_per_step": top["ms"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"cfg4: Chamfer-only forward (both directions, indices, loss), batch 64 over {world} rank(s), "
+                                       f"{CFG4_POINTS[-1]} points per cloud (sweep 256-16384 under `sweep`)",
+                           "l2": "flushed before every launch"},
+                "sweep": sweep, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "fp32-issue", "achieved": 3.0 * top["tpairs_s"], "peak": lane_peak * world / 1e12,
+                             "unit": "T FP32 lane-ops/s (3 per ordered pair: the prefilter)", "frac": 3.0 * top["tpairs_s"] * 1e12 / (lane_peak * world),
+                             "traffic": None}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg4"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -881,7 +919,11 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload == "cfg4":
+            args.workload = "cfg2"
         run_reference(args)
+    elif args.workload == "cfg4":
+        run_chamfer_only(args)
     else:
         run_ours(args)
 
