@@ -22,3 +22,4 @@ for f in gpurun_out/prof_${R}_mlp.ncu-rep gpurun_out/prof_${R}_chamfer.ncu-rep g
 done
 rm -f gpurun_out/prof_${R}_*.ncu-rep
 du -sm gpurun_out
+timeout 500 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_parity.py -q -x -p no:cacheprovider -k "point_transform or fused_input_transform or fps or fc_stack_vs_torch" > gpurun_out/r2_memcheck_new_kernels.txt 2>&1; tail -4 gpurun_out/r2_memcheck_new_kernels.txt
