@@ -74,7 +74,7 @@ int pcuda_sm_count(void);
  * 4 dense dgrad, 8 wgrad, 16 Gram), 4 = timing experiments of the pooled tensor-core layer (results invalid),
  * 5 = chamfer seed-pass stride (0 default, < 0 off), 6 = no auxiliary-stream fork / finalise-on-read in the MLP,
  * 7 = CTAs of the peer-memory all-reduce (0 default), 8 = programmatic dependent launch (0 default: off; 2: every launch;
- * 3: launches of >= 2 waves of CTAs). */
+ * 3: launches of >= 2 waves of CTAs), 9 = small fp64 sums through NCCL instead of the peer-memory mailbox. */
 int pcuda_tune(int key, int value);
 /* Number of kernels this library has launched in this process (monotone; for bench accounting). */
 uint64_t pcuda_launch_count(void);
@@ -368,7 +368,10 @@ typedef struct pcuda_comm pcuda_comm_t;
 int pcuda_comm_unique_id(void* id_out /*host, >= 128 bytes*/, int bytes);
 int pcuda_comm_init(const void* unique_id /*host, 128 bytes*/, int rank, int world, size_t p2p_floats, pcuda_comm_t** out);
 int pcuda_comm_allreduce(pcuda_comm_t* comm, float* buf, int64_t count, pcuda_stream_t stream);
-/* in-place sum of `count` doubles (BatchNorm statistics in the cross-rank mode); ncclAllGather of count_per_rank floats. */
+/* in-place sum of `count` doubles (BatchNorm statistics in the cross-rank mode): up to 2048 doubles with peer memory
+ * available go through a one-shot NVLink mailbox kernel (every rank stores its values into every peer's mailbox, one flag
+ * round trip, sum in rank order: bit-identical on all ranks; one channel per caller stream), anything else through
+ * ncclAllReduce.  pcuda_comm_allgather: ncclAllGather of count_per_rank floats. */
 int pcuda_comm_allreduce_f64(pcuda_comm_t* comm, double* buf, int64_t count, pcuda_stream_t stream);
 int pcuda_comm_allgather(pcuda_comm_t* comm, const float* send, float* recv /*[world * count_per_rank]*/, int64_t count_per_rank,
                          pcuda_stream_t stream);

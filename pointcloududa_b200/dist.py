@@ -91,6 +91,17 @@ class PcudaComm:
                        "pcuda_comm_allreduce")
         return t
 
+    def allreduce_f64_(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum of a float64 tensor over the ranks (the exchange of BatchNorm sums in the cross-rank mode): up to
+        2048 values go through the one-shot peer-memory mailbox kernel, more through ncclAllReduce."""
+        from . import _lib
+        if t.dtype != torch.float64 or not t.is_contiguous() or t.device != self.device:
+            raise _lib.PcudaError("PcudaComm.allreduce_f64_ needs a contiguous float64 tensor on the communicator's device")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().pcuda_comm_allreduce_f64(self._h, t.data_ptr(), t.numel(), torch.cuda.current_stream(self.device).cuda_stream),
+                       "pcuda_comm_allreduce_f64")
+        return t
+
     def allgather(self, send: torch.Tensor, recv: torch.Tensor) -> torch.Tensor:
         """recv[r * n:(r + 1) * n] = rank r's send (n = send.numel(); ncclAllGather on the current stream)."""
         from . import _lib

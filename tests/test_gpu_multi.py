@@ -127,6 +127,29 @@ def _comm_body(rank, world):
         gph.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, exact)
+    # small fp64 sums (cross-rank BatchNorm statistics): the one-shot mailbox kernel (<= 2048 doubles) and NCCL beyond,
+    # repeated calls (parity of the mailbox), two streams (two channels), exact rank-order sums, identical on all ranks
+    side = torch.cuda.Stream()
+    for it, cnt in enumerate([2048, 2048, 128, 1, 2048, 777, 5000]):
+        gd = torch.Generator().manual_seed(1000 * rank + it)
+        v = torch.randn(cnt, generator=gd, dtype=torch.float64).to(dev)
+        parts = [torch.empty_like(v) for _ in range(world)]
+        dist.all_gather(parts, v)
+        want64 = parts[0].clone()
+        for t in parts[1:]:
+            want64 = want64 + t
+        a = v.clone()
+        comm.allreduce_f64_(a)
+        b = v.clone() * 2.0
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            comm.allreduce_f64_(b)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if cnt <= 2048:
+            assert torch.equal(a, want64) and torch.equal(b, want64 * 2.0), (it, cnt)
+        else:
+            assert (a - want64).abs().max().item() <= 1e-12 * want64.abs().max().item(), (it, cnt)
     comm.check_status()
     dist.barrier()
     comm.destroy()
