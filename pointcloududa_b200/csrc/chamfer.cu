@@ -17,6 +17,8 @@
 //
 // Roofline: FP32 issue rate, not HBM — algorithmic HBM bytes are 12*B*(N+M) in and
 // 12*B*(N+M) out, the work is 2*B*N*M ordered pair evaluations at 5 FP32 ops + compare each.
+#include <algorithm>
+
 #include "pcuda_common.cuh"
 
 namespace pcuda {
@@ -571,25 +573,29 @@ struct Plan {
 };
 
 Plan make_plan(int B, int N, int M) {
-  // Fill the machine: prefer 4 rows/thread (amortises each shared-memory broadcast over 4 pair
-  // evaluations) but fall back to fewer rows / smaller blocks while the grid would be < 4 CTAs per SM
-  // (measured on B200: R=4 wins from B*N >= 64*4096, R=1 below 32*1024).
-  const int64_t target = static_cast<int64_t>(sm_count()) * 4;
+  // Rows per thread / CTA size, from the measured table profiles/r2_chamfer_plan_probe.txt (22 shapes x 5 variants):
+  //   * 4 rows per thread (each shared-memory broadcast amortised over 4 pair evaluations) pays once its grid —
+  //     2 directions x B x ceil(rows / 512) CTAs — reaches ~512 CTAs AND the scan is long (>= 4096 columns):
+  //     B32 x 4096, B16 x 8192, B8 x 16384 and up (5-10 % over the old rule at the boundary);
+  //   * everything smaller runs 1 row per thread in 128-thread CTAs (most warps per SM: 11-18 % faster than the old
+  //     2-row choice at B64 x 2048, B32 x 2048, B8 x 4096, B64 x 256), 64-thread CTAs while even that grid is < 1 wave;
+  //   * 2 rows per thread never won a shape; 8 rows always lost.
+  // pcuda_tune(1, rows * 1000 + threads) forces a variant (A/B runs, tests).
   const int forced = tuning(TUNE_CHAMFER_ROWS);
-  const int cand[5][2] = {{8, 128}, {4, 128}, {2, 128}, {1, 128}, {1, 64}};
-  Plan p{1, 64, 0, 0};
-  for (int k = (forced > 0 ? 0 : 1); k < 5; ++k) {
-    const int R = cand[k][0], T = cand[k][1];
-    if (forced / 100000 == 1 && R == 8) continue;  // the scalar kernel has no 8-row instantiation
-    const int tx = (N + R * T - 1) / (R * T), ty = (M + R * T - 1) / (R * T);
-    p = Plan{R, T, tx, ty};
-    if (forced > 0) {
-      if (forced % 100000 == R * 1000 + T) break;
-      continue;
+  auto plan = [&](int R, int T) { return Plan{R, T, (N + R * T - 1) / (R * T), (M + R * T - 1) / (R * T)}; };
+  if (forced > 0) {
+    const int cand[5][2] = {{8, 128}, {4, 128}, {2, 128}, {1, 128}, {1, 64}};
+    for (int k = 0; k < 5; ++k) {
+      if (forced / 100000 == 1 && cand[k][0] == 8) continue;  // the scalar kernel has no 8-row instantiation
+      if (forced % 100000 == cand[k][0] * 1000 + cand[k][1]) return plan(cand[k][0], cand[k][1]);
     }
-    if (static_cast<int64_t>(B) * (tx + ty) >= target) break;
+    return plan(1, 64);
   }
-  return p;
+  const Plan p4 = plan(4, 128);
+  if (static_cast<int64_t>(B) * (p4.tiles_x + p4.tiles_y) >= 512 && std::min(N, M) >= 4096) return p4;
+  const Plan p1 = plan(1, 128);
+  if (static_cast<int64_t>(B) * (p1.tiles_x + p1.tiles_y) >= sm_count()) return p1;
+  return plan(1, 64);
 }
 
 }  // namespace
