@@ -391,6 +391,11 @@ def kernel_profile(step, w: dict, pk: dict, reps: int = 5, record: bool = True, 
     for sh, (k, v) in zip(shares, top[:8]):
         r = kernel_roofline(k, w, v[1] / v[0] * 1e-6, pk, ncu_traffic(workload, short(k))[0])
         sh.update({"bound": r.get("bound"), "frac": r.get("frac"), "frac_hbm": r.get("frac_hbm"), "frac_tensor": r.get("frac_tensor")})
+    # the serial tail of the step (bucket fill, exchange, SGD): listed whatever their rank among the kernels
+    roof["tail_kernels"] = [{"kernel": short(k), "launches_per_step": v[0] / reps, "us_per_launch": v[1] / v[0]}
+                            for k, v in ours.items() if any(f in k for f in ("p2p_allreduce", "p2p_sum_f64", "sgd_momentum", "grad_sum_pack", "ncclDevKernel"))]
+    roof["tail_kernels"] += [{"kernel": short(k), "launches_per_step": v[0] / reps, "us_per_launch": v[1] / v[0]}
+                             for k, v in agg.items() if "nccl" in k.lower() and k not in ours]
     roof["peak_source"] = pk["source"]
     roof["note"] = ("dominant libpcuda kernel of the graph-replayed step at this workload (CUPTI device durations, warm L2); "
                     "at cfg2 sizes (2400 points per call) every kernel is latency-bound - `large` holds the roofline-sized shapes")
