@@ -326,10 +326,6 @@ typedef struct pcuda_param_slot {
 int pcuda_grad_sum_pack(const pcuda_param_slot_t* slots /*host*/, int n, float scale, float* flat, pcuda_stream_t stream);
 int pcuda_sgd_momentum_step(const pcuda_param_slot_t* slots /*host*/, int n, const float* flat_grad, float* flat_momentum,
                             const float* lr_dev, float momentum, float weight_decay, pcuda_stream_t stream);
-/* L2 prefetch (a hint: no data dependency, no ordering requirement) of every slot's `param` tensor: one launch at the start
- * of a step pulls D4's parameters into the L2 beside the first kernels, instead of one HBM round trip at the head of each of
- * the ~100 small kernels that read them. */
-int pcuda_prefetch_params_l2(const pcuda_param_slot_t* slots /*host*/, int n, pcuda_stream_t stream);
 
 /* ---- discriminator bookkeeping ---------------------------------------------------------------------
  * Replaces F.binary_cross_entropy_with_logits(D_out4, full_like(D_out4, label)) (reduction 'mean',

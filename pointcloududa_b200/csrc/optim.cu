@@ -106,21 +106,6 @@ __global__ void __launch_bounds__(32) bce_logits_kernel(const float* __restrict_
   }
 }
 
-// L2 prefetch of every parameter tensor (prefetch.global.L2: a hint, no data dependency — a later write to the line
-// simply updates it in the L2, the point of coherence).  The step touches each of D4's 6.4 MB of parameters in ~100
-// latency-bound kernels of a few CTAs; when the L2 does not hold them (the U-Net ran in between; bench.py flushes it)
-// every one of those kernels starts with an HBM round trip.  One launch at the start of the step, beside the first
-// kernels, pulls them in at full bandwidth.
-__global__ void __launch_bounds__(kThreads) prefetch_l2_kernel(const __grid_constant__ Table t) {
-  pdl_entry();
-  const int i = find_slot(t, blockIdx.x);
-  const Slot& s = t.s[i];
-  const long long base = static_cast<long long>(blockIdx.x - t.cta_start[i]) * kChunk;
-  // one 128-byte line per thread: 32 floats
-  const long long j = base + static_cast<long long>(threadIdx.x) * 32;
-  if (j < s.numel && threadIdx.x * 32 < kChunk) asm volatile("prefetch.global.L2 [%0];" ::"l"(s.param + j));
-}
-
 template <typename F>
 int for_each_table(const pcuda_param_slot_t* slots, int n, const char* who, bool need_param, F&& launch) {
   for (int s0 = 0; s0 < n; s0 += kSlotsPerLaunch) {
@@ -168,16 +153,6 @@ extern "C" int pcuda_sgd_momentum_step(const pcuda_param_slot_t* slots, int n, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return for_each_table(slots, n, "sgd_momentum_step", true, [&](const Table& t, int ctas) {
     PCUDA_LAUNCH(sgd_momentum_kernel, ctas, kThreads, 0, st, t, flat_grad, flat_momentum, lr_dev, momentum, weight_decay);
-  });
-}
-
-extern "C" int pcuda_prefetch_params_l2(const pcuda_param_slot_t* slots, int n, pcuda_stream_t stream) {
-  PCUDA_REQUIRE(n >= 0, PCUDA_E_SHAPE, "prefetch_params_l2: n=%d", n);
-  if (n == 0) return 0;
-  PCUDA_REQUIRE(slots != nullptr, PCUDA_E_NULL, "prefetch_params_l2: NULL argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return for_each_table(slots, n, "prefetch_params_l2", true, [&](const Table& t, int ctas) {
-    PCUDA_LAUNCH(prefetch_l2_kernel, ctas, kThreads, 0, st, t);
   });
 }
 

@@ -68,15 +68,6 @@ class FusedSGD:
             st = torch.cuda.current_stream(self.device).cuda_stream
             check(L.pcuda_grad_sum_pack(self._slots, len(self._slots), float(scale), flat.data_ptr(), st), "pcuda_grad_sum_pack")
 
-    def prefetch_params(self) -> None:
-        """L2 prefetch of every parameter (a hint; one launch on the current stream)."""
-        for s, p in zip(self._slots, self.params):
-            s.param = p.data_ptr()
-        L = _lib.lib()
-        with torch.cuda.device(self.device):
-            st = torch.cuda.current_stream(self.device).cuda_stream
-            check(L.pcuda_prefetch_params_l2(self._slots, len(self._slots), st), "pcuda_prefetch_params_l2")
-
     def step(self, flat_grad: torch.Tensor) -> None:
         """One SGD step of every parameter from the flat gradient bucket, one launch."""
         if flat_grad.numel() != self.numel or flat_grad.dtype != torch.float32 or not flat_grad.is_contiguous():

@@ -125,7 +125,6 @@ class AdversarialStep:
         self._res = []
         self._side = None
         self.concurrent = concurrent
-        self.prefetch = True
 
     # -- inputs -----------------------------------------------------------------------------------
     def _input_offsets(self):
@@ -179,10 +178,6 @@ class AdversarialStep:
         if self.concurrent:
             for s in (s1, s2, s3):
                 s.wait_stream(main)
-        if self.prefetch:
-            # D4's parameters into the L2 beside the first kernels of the step (a hint; issued on the branch that has no D4 in it)
-            with torch.cuda.stream(s3):
-                self.opt.prefetch_params()
 
         # ---- branch D (stream s3) — the ops with no discriminator in them: P1 source Chamfer forward + backward
         # into the predicted cloud, the target entropy map forward + backward (the part of P2 that feeds D2),
