@@ -73,8 +73,9 @@ int pcuda_sm_count(void);
  * 3 = bit mask of MLP pieces switched from tcgen05 back to FP32 (1 forward, 2 pooled dgrad,
  * 4 dense dgrad, 8 wgrad, 16 Gram), 4 = timing experiments of the pooled tensor-core layer (results invalid),
  * 5 = chamfer seed-pass stride (0 default, < 0 off), 6 = no auxiliary-stream fork / finalise-on-read in the MLP,
- * 7 = CTAs of the peer-memory all-reduce (0 default), 8 = programmatic dependent launch (0 default: off; 2: every launch;
- * 3: launches of >= 2 waves of CTAs), 9 = small fp64 sums through NCCL instead of the peer-memory mailbox. */
+ * 7 = CTAs of the peer-memory all-reduce (0 default), 8 = programmatic dependent launch (0 default: every launch; 1: off;
+ * 3: launches of >= 2 waves of CTAs; 4: only kernels with a prologue before their wait), 9 = small fp64 sums through NCCL instead of the peer-memory mailbox,
+ * 10 = pooled dgrad, sparse rows: < 0 switches the sorted / evenly cut kernel off (one warp per selected point instead). */
 int pcuda_tune(int key, int value);
 /* Number of kernels this library has launched in this process (monotone; for bench accounting). */
 uint64_t pcuda_launch_count(void);

@@ -43,7 +43,6 @@ struct FcFwdParams {
 
 // dynamic shared memory: Wsm[kCPB][cin] | ys[B][kCPB]
 __global__ void __launch_bounds__(kFcThreads) fc_fwd_kernel(const FcFwdParams p) {
-  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   float* Wsm = sm;
   float* ys = sm + kCPB * p.cin;
@@ -51,12 +50,14 @@ __global__ void __launch_bounds__(kFcThreads) fc_fwd_kernel(const FcFwdParams p)
   const int c0 = blockIdx.x * kCPB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cin4 = p.cin >> 2;
+  // the weight rows are parameters (nothing in flight writes them): staged while the previous kernel is still running
   for (int i = threadIdx.x; i < kCPB * cin4; i += kFcThreads) {
     const int cc = i / cin4, k4 = i - cc * cin4;
     const int c = c0 + cc;
     reinterpret_cast<float4*>(Wsm)[i] =
         c < p.cout ? __ldg(reinterpret_cast<const float4*>(p.W + static_cast<int64_t>(c) * p.cin) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  pdl_entry();
   __syncthreads();
   // a warp takes two rows at a time (b, b + 8): each row of x is read once for the kCPB channels and
   // 16 independent 128-bit loads are in flight per lane
@@ -168,12 +169,24 @@ struct FcBwdParams {
 };
 
 // dynamic shared memory: dys[B][kCPB]
+constexpr int kBwdPre = 16;   // rows of W_next per lane requested before the grid-dependency wait (cout_next <= 512)
 __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p) {
-  pdl_entry();
   extern __shared__ __align__(16) float sm[];
   float* dys = sm;
   const int c0 = blockIdx.x * kCPB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the next layer's weights (this CTA's kCPB columns of rows lane, lane + 32, ...) are parameters: in flight while the
+  // kernel that produces dy_next is still running
+  const bool vec = (p.cout & 3) == 0;
+  const bool pre = p.grad_out == nullptr && vec;
+  float4 wpre[kBwdPre];
+#pragma unroll
+  for (int j = 0; j < kBwdPre; ++j) {
+    const int o = lane + 32 * j;
+    wpre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pre && o < p.cout_next) wpre[j] = __ldg(reinterpret_cast<const float4*>(p.W_next + static_cast<int64_t>(o) * p.cout + c0));
+  }
+  pdl_entry();
   // (1) da for this CTA's channels
   if (p.grad_out != nullptr) {
     for (int i = threadIdx.x; i < p.B * kCPB; i += kFcThreads) {
@@ -181,15 +194,27 @@ __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p)
       dys[i] = c < p.cout ? p.grad_out[static_cast<int64_t>(b) * p.cout + c] : 0.f;
     }
   } else {
-    const bool vec = (p.cout & 3) == 0;
     for (int b = warp; b < p.B; b += 2 * (kFcThreads / 32)) {
       const int b1 = b + kFcThreads / 32;
       const bool two = b1 < p.B;
       const float* dn0 = p.dy_next + static_cast<int64_t>(b) * p.cout_next;
       const float* dn1 = p.dy_next + static_cast<int64_t>(two ? b1 : b) * p.cout_next;
       float acc[2][kCPB] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      if (pre) {
+#pragma unroll
+        for (int j = 0; j < kBwdPre; ++j) {
+          const int o = lane + 32 * j;
+          if (o < p.cout_next) {
+            const float d0 = __ldg(dn0 + o), d1 = __ldg(dn1 + o);
+            acc[0][0] = fmaf(d0, wpre[j].x, acc[0][0]); acc[0][1] = fmaf(d0, wpre[j].y, acc[0][1]);
+            acc[0][2] = fmaf(d0, wpre[j].z, acc[0][2]); acc[0][3] = fmaf(d0, wpre[j].w, acc[0][3]);
+            acc[1][0] = fmaf(d1, wpre[j].x, acc[1][0]); acc[1][1] = fmaf(d1, wpre[j].y, acc[1][1]);
+            acc[1][2] = fmaf(d1, wpre[j].z, acc[1][2]); acc[1][3] = fmaf(d1, wpre[j].w, acc[1][3]);
+          }
+        }
+      }
 #pragma unroll 8
-      for (int o = lane; o < p.cout_next; o += 32) {
+      for (int o = lane + (pre ? 32 * kBwdPre : 0); o < p.cout_next; o += 32) {
         const float d0 = __ldg(dn0 + o), d1 = __ldg(dn1 + o);
         const float* wr = p.W_next + static_cast<int64_t>(o) * p.cout + c0;
         float wv[kCPB];
@@ -299,10 +324,18 @@ __global__ void __launch_bounds__(kFcThreads) fc_bwd_kernel(const FcBwdParams p)
 template <int RB, int kPullThreads>
 __global__ void __launch_bounds__(kPullThreads) fc_pull_kernel(const float* __restrict__ dy, const float* __restrict__ W,
                                                               int B, int cin, int cout, float* __restrict__ dx) {
-  pdl_entry();
   extern __shared__ __align__(16) float sm[];   // dys[cout][RB], reused as red[warps][RB][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
+  // this thread's first kPullPre weights (rows warp, warp + nwarps, ...: parameters) are requested before the wait
+  constexpr int kPullPre = 16, kWarps = kPullThreads / 32;
+  float wpre[kPullPre];
+#pragma unroll
+  for (int j = 0; j < kPullPre; ++j) {
+    const int c = warp + kWarps * j;
+    wpre[j] = (c < cout && k < cin) ? __ldg(W + static_cast<int64_t>(c) * cin + k) : 0.f;
+  }
+  pdl_entry();
   for (int b0 = 0; b0 < B; b0 += RB) {
     const int nb = min(RB, B - b0);
     __syncthreads();
@@ -314,9 +347,7 @@ __global__ void __launch_bounds__(kPullThreads) fc_pull_kernel(const float* __re
     float acc[RB];
 #pragma unroll
     for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-#pragma unroll 8
-    for (int c = warp; c < cout; c += kPullThreads / 32) {
-      const float wv = k < cin ? __ldg(W + static_cast<int64_t>(c) * cin + k) : 0.f;
+    auto row = [&](int c, float wv) {
       const float4* d4 = reinterpret_cast<const float4*>(sm + c * RB);
 #pragma unroll
       for (int r4 = 0; r4 < RB / 4; ++r4) {
@@ -324,7 +355,13 @@ __global__ void __launch_bounds__(kPullThreads) fc_pull_kernel(const float* __re
         acc[4 * r4 + 0] = fmaf(d.x, wv, acc[4 * r4 + 0]); acc[4 * r4 + 1] = fmaf(d.y, wv, acc[4 * r4 + 1]);
         acc[4 * r4 + 2] = fmaf(d.z, wv, acc[4 * r4 + 2]); acc[4 * r4 + 3] = fmaf(d.w, wv, acc[4 * r4 + 3]);
       }
-    }
+    };
+#pragma unroll
+    for (int j = 0; j < kPullPre; ++j)
+      if (warp + kWarps * j < cout) row(warp + kWarps * j, wpre[j]);
+#pragma unroll 8
+    for (int c = warp + kWarps * kPullPre; c < cout; c += kWarps)
+      row(c, k < cin ? __ldg(W + static_cast<int64_t>(c) * cin + k) : 0.f);
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RB; ++r) sm[(warp * RB + r) * 32 + lane] = acc[r];
@@ -435,7 +472,7 @@ extern "C" int pcuda_fcstack_fwd(const float* x, int B, int L, const pcuda_fc_la
     p.momentum = momentum; p.eps = eps;
     const size_t smem = sizeof(float) * (static_cast<size_t>(kCPB) * y.cin + static_cast<size_t>(B) * kCPB);
     PCUDA_REQUIRE(smem <= 160 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_fwd: layer %d does not fit shared memory", l);
-    PCUDA_LAUNCH(fc_fwd_kernel, (y.cout + kCPB - 1) / kCPB, kFcThreads, smem, st, p);
+    PCUDA_LAUNCH_PDL(fc_fwd_kernel, (y.cout + kCPB - 1) / kCPB, kFcThreads, smem, st, p);
     in = y.a;
   }
   count_launch(L);
@@ -463,7 +500,7 @@ extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_la
     p.grad_weight = y.grad_weight; p.grad_bias = y.grad_weight ? y.grad_bias : nullptr;
     p.grad_gamma = y.grad_weight ? y.grad_gamma : nullptr; p.grad_beta = y.grad_weight ? y.grad_beta : nullptr;
     p.B = B; p.cin = y.cin; p.cout = y.cout; p.relu = y.relu; p.train = train;
-    PCUDA_LAUNCH(fc_bwd_kernel, (y.cout + kCPB - 1) / kCPB, kFcThreads, sizeof(float) * static_cast<size_t>(B) * kCPB, st, p);
+    PCUDA_LAUNCH_PDL(fc_bwd_kernel, (y.cout + kCPB - 1) / kCPB, kFcThreads, sizeof(float) * static_cast<size_t>(B) * kCPB, st, p);
     ++launches;
     cur ^= 1;
   }
@@ -477,8 +514,8 @@ extern "C" int pcuda_fcstack_bwd(const float* x, int B, int L, const pcuda_fc_la
     PCUDA_REQUIRE(smem <= 160 * 1024, PCUDA_E_UNSUPPORTED, "fcstack_bwd: first layer too wide for the input-gradient kernel");
     smem_optin(fc_pull_kernel<32, 512>, 160 * 1024);
     smem_optin(fc_pull_kernel<16, 1024>, 160 * 1024);
-    if (rb == 32) PCUDA_LAUNCH((fc_pull_kernel<32, 512>), (y.cin + 31) / 32, 512, smem, st, dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
-    else PCUDA_LAUNCH((fc_pull_kernel<16, 1024>), (y.cin + 31) / 32, 1024, smem, st, dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
+    if (rb == 32) PCUDA_LAUNCH_PDL((fc_pull_kernel<32, 512>), (y.cin + 31) / 32, 512, smem, st, dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
+    else PCUDA_LAUNCH_PDL((fc_pull_kernel<16, 1024>), (y.cin + 31) / 32, 1024, smem, st, dybuf[cur ^ 1], y.weight, B, y.cin, y.cout, grad_x);
     ++launches;
   }
   count_launch(launches);

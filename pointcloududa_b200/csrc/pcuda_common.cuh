@@ -25,18 +25,18 @@ static inline cudaError_t smem_optin(F* fn, int bytes) {
   return smem_optin_impl(reinterpret_cast<const void*>(fn), bytes);
 }
 
-enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_FP32 = 2, TUNE_MLP_TC_MASK = 3, TUNE_MLP_EPI_DEBUG = 4, TUNE_CHAMFER_SEED = 5, TUNE_MLP_NO_FORK = 6, TUNE_COMM_BLOCKS = 7, TUNE_PDL = 8, TUNE_COMM_NO_SMALL_P2P = 9, TUNE_NKEYS = 12 };
+enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_FP32 = 2, TUNE_MLP_TC_MASK = 3, TUNE_MLP_EPI_DEBUG = 4, TUNE_CHAMFER_SEED = 5, TUNE_MLP_NO_FORK = 6, TUNE_COMM_BLOCKS = 7, TUNE_PDL = 8, TUNE_COMM_NO_SMALL_P2P = 9, TUNE_SPARSE_SORTED = 10, TUNE_NKEYS = 12 };
 
 // ---- programmatic dependent launch -----------------------------------------------------------------
 // The hot path at the reference's shapes is a chain of ~70 dependent launches of 3-20 us per D4 pass: what a step
-// costs is launch-to-launch latency, not work.  Every libpcuda kernel therefore starts with pdl_entry() —
-// `griddepcontrol.launch_dependents` (the next kernel of the stream may be scheduled as soon as all CTAs of this one
-// are resident) followed by `griddepcontrol.wait` (block until the preceding kernel has completed and its writes
-// are visible) — and is launched through launch_k() with the programmatic-stream-serialisation attribute: ordering
-// and visibility are exactly those of ordinary stream order, but the dependent's launch latency (block scheduling,
-// parameter fetch, prologue that does not touch the predecessor's output) overlaps the predecessor's tail.  A kernel
-// that is launched without the attribute executes both instructions as no-ops.  Under stream capture the edges become
-// programmatic dependency edges of the CUDA graph.  Which launches carry the attribute: see launch_k().
+// costs is launch-to-launch latency, not work.  Every libpcuda kernel calls pdl_entry() — `griddepcontrol.wait` (block
+// until the preceding kernel of the stream has completed and its writes are visible) followed by
+// `griddepcontrol.launch_dependents` (the next kernel may be scheduled once all CTAs of this one got here) — and kernels
+// with work that does not depend on their predecessor (staging weights, barrier / TMEM set-up) do that work BEFORE
+// pdl_entry() and are launched with the programmatic-stream-serialisation attribute (PCUDA_LAUNCH_PDL): ordering and
+// visibility of everything after pdl_entry() are exactly those of ordinary stream order, while launch latency and the
+// prologue overlap the predecessor.  Without the attribute both instructions are no-ops.  Under stream capture the edges
+// become programmatic dependency edges of the CUDA graph.
 __device__ __forceinline__ void pdl_trigger() {
 #if defined(__CUDA_ARCH__)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -47,12 +47,26 @@ __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
 }
+// Every kernel starts with pdl_entry(): wait for the grid before it in the stream (a no-op unless this launch carries
+// the programmatic-serialization attribute), THEN let the grid after it start early.  In this order at most two kernels
+// of a stream overlap, and when a dependent starts, everything before its predecessor has completed: code a kernel runs
+// BEFORE pdl_entry() may read anything except what its immediate predecessor writes (parameters, its own shared memory,
+// barrier / TMEM set-up), and must not write global memory.
 __device__ __forceinline__ void pdl_entry() {
-  pdl_trigger();
   pdl_wait();
+  pdl_trigger();
 }
 
-template <class... KArgs, class... Args>
+// kPrologue marks launches of kernels that do useful work before pdl_entry() (weight staging, barrier / TMEM set-up).
+// pcuda_tune(8, v): 0 default = every launch carries the programmatic-serialization attribute, 1 = none, 4 = only the
+// kPrologue ones, 3 = only launches of at least two waves of CTAs.
+// Measured (tools/ab_pdl.py, graph replay, L2 flushed, 40 steps, two rounds), cfg2:
+//   trigger-before-wait in every kernel, every launch (profiles/r2_ab_pdl.txt):      off 0.475 / 0.478 ms   on 0.495 / 0.496
+//   wait-then-trigger (this code), fc_fwd staging its weights early (r2_ab_pdl2.txt): off 0.457 / 0.459   fc_fwd only 0.447 /
+//   0.453   every launch 0.426 / 0.424
+// With the trigger first, dependents of dependents pile up on the SMs the concurrent branches of the step need; with the
+// wait first at most one successor per stream is resident early, and launch latency plus prologue are hidden.
+template <bool kPrologue, class... KArgs, class... Args>
 static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
@@ -63,22 +77,16 @@ static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 blo
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  // Measured (tools/ab_pdl.py, profiles/r2_ab_pdl.txt; CUDA-graph replay, L2 flushed, 40 steps each, two rounds):
-  //   cfg2 (grids <= 148 CTAs, 4 + 3 concurrent branches)   off 0.475 / 0.478 ms   always 0.495 / 0.496   >= 2 waves 0.477 / 0.476
-  //   cfg-5 shard (grids of several waves)                   off 2.730 / 2.734      always 2.670 / 2.680   >= 2 waves 2.846 / 2.769
-  //   cfg-3 (B = 32, N = 1024)                               off 1.192 / 1.198      always 1.166 / 1.293   >= 2 waves 1.211 / 1.232
-  // Early-resident dependents take SM slots from the concurrent branches of the step: +4 % at the reference's shapes,
-  // -2 % at cfg-5, noise in between.  Inside a CUDA graph the kernel-to-kernel hand-over is already cheap on this
-  // part; the chain is bound by each small kernel's own dependent memory round trips.  So the attribute is OFF by
-  // default; pcuda_tune(8, 2) sets it on every launch, pcuda_tune(8, 3) on launches of at least two waves of CTAs.
   const int mode = tuning(TUNE_PDL);
   const long long ctas = static_cast<long long>(grid.x) * grid.y * grid.z;
-  cfg.numAttrs = (mode == 2 || (mode == 3 && ctas >= 2ll * sm_count())) ? 1 : 0;
+  cfg.numAttrs = (mode == 0 || mode == 2 || (mode == 4 && kPrologue) || (mode == 3 && ctas >= 2ll * sm_count())) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 // PCUDA_LAUNCH((kernel<T...>), grid, block, smem, stream, args...): parenthesise kernel names that contain commas
 #define PCUDA_LAUNCH(kernel, grid, block, smem, st, ...) \
-  (void)::pcuda::launch_k(kernel, dim3(grid), dim3(block), static_cast<size_t>(smem), st, __VA_ARGS__)
+  (void)::pcuda::launch_k<false>(kernel, dim3(grid), dim3(block), static_cast<size_t>(smem), st, __VA_ARGS__)
+#define PCUDA_LAUNCH_PDL(kernel, grid, block, smem, st, ...) \
+  (void)::pcuda::launch_k<true>(kernel, dim3(grid), dim3(block), static_cast<size_t>(smem), st, __VA_ARGS__)
 
 #define PCUDA_REQUIRE(cond, code, ...)                 \
   do {                                                 \

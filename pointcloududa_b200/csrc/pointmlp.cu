@@ -218,7 +218,6 @@ template <int KN>
 __global__ void __launch_bounds__(kNarrowThreads)
 mlp_fwd_narrow_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias, int Cout, int64_t M,
                       float* __restrict__ y_out, double* __restrict__ stats, float* __restrict__ pivot) {
-  pdl_entry();
   __shared__ float red[kNarrowThreads / 16][2][64];   // up to 16 channel groups... sized below by cgroups <= 16... see launch
   const int K = src.C;
   const int cgroups = Cout >> 2;                       // <= 64 (Cout <= 256): thread = (point slot, channel group)
@@ -233,6 +232,7 @@ mlp_fwd_narrow_kernel(ActSrc src, const float* __restrict__ W, const float* __re
 #pragma unroll
     for (int k = 0; k < KN; ++k) w[j][k] = k < K ? W[static_cast<int64_t>(c0 + j) * K + k] : 0.f;
   }
+  pdl_entry();                                         // weights and bias (parameters) were requested before the wait
   {  // pivot = pre-BN output at global point 0 (same definition as bn_finalize_pivot_kernel)
     float x0[KN];
     load_point<KN>(src, 0, x0);
@@ -331,7 +331,6 @@ wgrad_narrow_kernel(DySrc dys, ActSrc aprev, int64_t M, float* __restrict__ part
 template <int KN>
 __global__ void __launch_bounds__(kNarrowThreads)
 dgrad_input_narrow_kernel(DySrc dys, const float* __restrict__ W, int K, int N, int64_t M, float* __restrict__ grad_x) {
-  pdl_entry();
   const int C = dys.C;
   const int tpp = C >> 2, pslots = kNarrowThreads / tpp;
   const int cg = threadIdx.x % tpp, ps = threadIdx.x / tpp;
@@ -341,6 +340,7 @@ dgrad_input_narrow_kernel(DySrc dys, const float* __restrict__ W, int K, int N, 
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int k = 0; k < KN; ++k) w[j][k] = k < K ? W[static_cast<int64_t>(c0 + j) * K + k] : 0.f;
+  pdl_entry();                                           // the weights (parameters) were requested before the wait
   const int64_t stride = static_cast<int64_t>(gridDim.x) * pslots;
   const int64_t iters = (M + stride - 1) / stride;       // uniform trip count: the shuffles below need full warps
   const DyConst4 dk = dy_const4(dys, c0);
@@ -893,7 +893,10 @@ pool_sparse_kernel(const int32_t* __restrict__ arg, const float* __restrict__ co
     gam_k[jj] = ok ? o.gamma[k0 + jj] : 0.f;
     bet_k[jj] = ok ? o.beta[k0 + jj] : 0.f;
   }
-  for (int h = blockIdx.y * nwarp + warp; h < H; h += nwarp * gridDim.y) {
+  // heads are in ascending channel order, which is roughly descending popularity (a point many channels select is
+  // very likely selected by an early one): consecutive heads go to different CTAs, so every warp of the grid gets one
+  // early (long) and one late (short) head instead of one CTA getting the 16 longest
+  for (int h = warp * gridDim.y + blockIdx.y; h < H; h += nwarp * gridDim.y) {
     const int c = heads[h];
     const int a = sarg[c];
     const int64_t mrow = static_cast<int64_t>(b) * N + a;
@@ -1027,6 +1030,257 @@ static size_t pool_sparse_smem(int C, int N, int K) {
   return std::max(a, sizeof(float) * 2 * 16 * static_cast<size_t>(K));
 }
 
+// ---- pool_sparse_sorted_kernel: the same update for K <= 128 and fewer points than channels (the 300-point clouds) ----
+// There a handful of points are selected by 100+ channels each and most by one to three, so "one warp per point" leaves
+// the kernel waiting for the few warps that walk ceil(m / IF) dependent round trips (measured, B=8 N=300: median CTA
+// done after 6 us, the last after 14-27 us).  Here the channels of a cloud are first sorted by selected point (stable
+// counting sort in shared memory: ascending channel inside a point), the sorted rows are cut into gridDim.y CTA ranges at
+// point boundaries and every CTA range into 16 equal warp segments regardless of point boundaries, so every warp loads
+// <= ceil(range / 16) rows of W, normally in ONE round trip:
+//   phase A  a warp sums its segment point by point; a point that lies inside the segment goes to sbuf[point], the (at
+//            most two) points cut by a segment end go to part[2 * warp + {0: cut on the left, 1: cut on the right only}];
+//   phase B  warp w owns points w, w + 16, ... of the CTA range: S = sbuf[point], or the partials of the warps the point
+//            spans in warp order (= ascending channel: deterministic), then the masked read-modify-write of dz_prev and
+//            the BN sums.  The rows of y_prev / dz_prev of a warp's first two points are requested before phase A.
+// grid (B, parts), 512 threads.  Needs N <= 1024, C <= 65535, K % 4 == 0, 16-byte aligned rows.
+constexpr int kSsWarps = 16;
+constexpr int kSsIF = 12;      // rows of W in flight per lane
+constexpr int kSsPre = 2;      // points per warp whose read-modify-write operands are requested up front
+
+struct SsLayout { size_t sarg, start, wtot, gpoint, order, cm, bn, part, sbuf, bytes; };
+__host__ __device__ inline SsLayout ss_layout(int C, int N, int K, int sb_rows) {
+  const size_t nchunk = (static_cast<size_t>(C) + 31) / 32;
+  auto even = [](size_t v) { return (v + 1) & ~static_cast<size_t>(1); };
+  SsLayout l{};
+  size_t off = 0;
+  l.sarg = off;   off += sizeof(int) * static_cast<size_t>(C);
+  l.start = off;  off += sizeof(uint32_t) * (static_cast<size_t>(N) + 1);
+  l.wtot = off;   off += sizeof(uint32_t) * 32;
+  l.gpoint = off; off += sizeof(uint16_t) * even(N);
+  l.order = off;  off += sizeof(uint16_t) * even(C);
+  l.cm = off;     off += sizeof(uint16_t) * even(nchunk * N);
+  off = (off + 15) & ~static_cast<size_t>(15);
+  l.bn = off;     off += sizeof(float) * 4 * static_cast<size_t>(K);                 // mean | invstd | gamma | beta of the previous layer
+  l.part = off;   off += sizeof(float) * 2 * kSsWarps * static_cast<size_t>(K);      // also the final [2][16][K] reduction
+  l.sbuf = off;   off += sizeof(float) * static_cast<size_t>(sb_rows) * K;
+  l.bytes = off;
+  return l;
+}
+
+__global__ void __launch_bounds__(32 * kSsWarps, 1)
+pool_sparse_sorted_kernel(const int32_t* __restrict__ arg, const float* __restrict__ coef, const float* __restrict__ W,
+                          int C, int N, int K, int sb_rows, DgradOut o) {
+  pdl_entry();
+  extern __shared__ __align__(16) unsigned char ss_raw[];
+  const SsLayout L = ss_layout(C, N, K, sb_rows);
+  int* sarg = reinterpret_cast<int*>(ss_raw + L.sarg);                 // [C] selected point, -1 when coef == 0
+  uint32_t* start = reinterpret_cast<uint32_t*>(ss_raw + L.start);     // [N + 1] low 16: sorted rows before point n; high 16: non-empty points before n
+  uint32_t* wtot = reinterpret_cast<uint32_t*>(ss_raw + L.wtot);
+  uint16_t* gpoint = reinterpret_cast<uint16_t*>(ss_raw + L.gpoint);   // [#non-empty] their point ids, ascending
+  uint16_t* order = reinterpret_cast<uint16_t*>(ss_raw + L.order);     // [T] channels sorted by (point, channel)
+  uint16_t* cm = reinterpret_cast<uint16_t*>(ss_raw + L.cm);           // [nchunk][N] channels of chunk ch selecting point n -> prefix over ch
+  float* part = reinterpret_cast<float*>(ss_raw + L.part);
+  float* sbuf = reinterpret_cast<float*>(ss_raw + L.sbuf);
+  const int nchunk = (C + 31) >> 5;
+  const int b = blockIdx.x, P = gridDim.y, p = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int k0 = 4 * lane;
+  const bool kin = k0 < K;
+  // per-channel BN constants of the previous layer: requested first, used last
+  float* bn = reinterpret_cast<float*>(ss_raw + L.bn);
+  for (int i = tid; i < 4 * K; i += blockDim.x) {
+    const int which = i / K, k = i - which * K;
+    bn[i] = which == 0 ? o.mean[k] : which == 1 ? o.invstd[k] : which == 2 ? o.gamma[k] : o.beta[k];
+  }
+  for (int c = tid; c < C; c += blockDim.x)
+    sarg[c] = coef[static_cast<int64_t>(b) * C + c] != 0.f ? arg[static_cast<int64_t>(b) * C + c] : -1;
+  {
+    uint32_t* cz = reinterpret_cast<uint32_t*>(cm);
+    const int nw = (nchunk * N + 1) >> 1;
+    for (int i = tid; i < nw; i += blockDim.x) cz[i] = 0u;
+  }
+  __syncthreads();
+  // channels of each 32-channel chunk per point (the lowest lane of a group of equal points writes the group size)
+  for (int ch = warp; ch < nchunk; ch += kSsWarps) {
+    const int c = ch * 32 + lane;
+    const int a = c < C ? sarg[c] : -1;
+    const unsigned mk = __match_any_sync(0xffffffffu, a);
+    if (a >= 0 && lane == __ffs(mk) - 1) cm[ch * N + a] = static_cast<uint16_t>(__popc(mk));
+  }
+  __syncthreads();
+  // per point: exclusive prefix over the chunks (in place) and the total
+  for (int n = tid; n < N; n += blockDim.x) {
+    uint32_t run = 0;
+    for (int ch = 0; ch < nchunk; ++ch) {
+      const uint32_t t = cm[ch * N + n];
+      cm[ch * N + n] = static_cast<uint16_t>(run);
+      run += t;
+    }
+    start[n] = run | (run ? 0x10000u : 0u);
+  }
+  __syncthreads();
+  // exclusive scan over the points of (rows, non-empty flag) packed in one word: two points per thread
+  {
+    const int i0 = 2 * tid;
+    const uint32_t v0 = i0 < N ? start[i0] : 0u, v1 = i0 + 1 < N ? start[i0 + 1] : 0u;
+    const uint32_t s = v0 + v1;
+    uint32_t incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += wtot[w];
+    const uint32_t excl = base + incl - s;
+    if (i0 < N) start[i0] = excl;
+    if (i0 + 1 < N) start[i0 + 1] = excl + v0;
+    if (tid == 32 * kSsWarps - 1) start[N] = base + incl;
+  }
+  __syncthreads();
+  for (int ch = warp; ch < nchunk; ch += kSsWarps) {
+    const int c = ch * 32 + lane;
+    const int a = c < C ? sarg[c] : -1;
+    const unsigned mk = __match_any_sync(0xffffffffu, a);
+    if (a >= 0) order[(start[a] & 0xffffu) + cm[ch * N + a] + __popc(mk & lt)] = static_cast<uint16_t>(c);
+  }
+  for (int n = tid; n < N; n += blockDim.x)
+    if ((start[n + 1] >> 16) != (start[n] >> 16)) gpoint[start[n] >> 16] = static_cast<uint16_t>(n);
+  __syncthreads();
+  const int T = static_cast<int>(start[N] & 0xffffu), Gtot = static_cast<int>(start[N] >> 16);
+  // this CTA's rows [R0, R1): cuts at q * T / P moved down to the start of the point they fall in
+  auto cut = [&](int q) -> int {
+    if (q >= P) return T;
+    const int r = static_cast<int>(static_cast<int64_t>(q) * T / P);
+    return r >= T ? T : static_cast<int>(start[sarg[order[r]]] & 0xffffu);
+  };
+  const int R0 = cut(p), R1 = cut(p + 1);
+  const int len = R1 - R0;
+  float ws[4] = {0.f, 0.f, 0.f, 0.f}, wq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (len > 0) {
+    const int g0 = static_cast<int>(start[sarg[order[R0]]] >> 16);
+    const int G = (R1 < T ? static_cast<int>(start[sarg[order[R1]]] >> 16) : Gtot) - g0;
+    if (G > sb_rows) __trap();                      // cannot happen: a range holds <= ceil(T / P) + 1 points
+    const int per = (len + kSsWarps - 1) / kSsWarps;
+    const int s0 = R0 + min(len, warp * per), s1 = R0 + min(len, warp * per + per);
+    // the rows this warp will read-modify-write in phase B: in flight during phase A
+    float4 yp[kSsPre], dp[kSsPre];
+#pragma unroll
+    for (int t = 0; t < kSsPre; ++t) {
+      yp[t] = make_float4(0.f, 0.f, 0.f, 0.f); dp[t] = yp[t];
+      const int gi = warp + t * kSsWarps;
+      if (gi < G && kin) {
+        const int64_t mrow = static_cast<int64_t>(b) * N + gpoint[g0 + gi];
+        yp[t] = *reinterpret_cast<const float4*>(o.y_prev + mrow * K + k0);
+        dp[t] = *reinterpret_cast<const float4*>(o.dz_prev + mrow * K + k0);
+      }
+    }
+    // phase A
+    {
+      int cur = -1;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto emit = [&]() {
+        const int st = static_cast<int>(start[cur] & 0xffffu), en = static_cast<int>(start[cur + 1] & 0xffffu);
+        float* dst = st < s0 ? part + static_cast<size_t>(2 * warp) * K
+                   : en > s1 ? part + static_cast<size_t>(2 * warp + 1) * K
+                             : sbuf + static_cast<size_t>(static_cast<int>(start[cur] >> 16) - g0) * K;
+        if (kin) *reinterpret_cast<float4*>(dst + k0) = acc;
+      };
+      for (int i = s0; i < s1; i += kSsIF) {
+        float cf[kSsIF];
+        float4 wv[kSsIF];
+#pragma unroll
+        for (int u = 0; u < kSsIF; ++u) {
+          const int cs = i + u < s1 ? static_cast<int>(order[i + u]) : -1;
+          cf[u] = cs >= 0 ? coef[static_cast<int64_t>(b) * C + cs] : 0.f;
+          wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cs >= 0 && kin) wv[u] = __ldg(reinterpret_cast<const float4*>(W + static_cast<int64_t>(cs) * K + k0));
+        }
+#pragma unroll
+        for (int u = 0; u < kSsIF; ++u) {
+          if (i + u >= s1) break;
+          const int a = sarg[order[i + u]];
+          if (a != cur) {
+            if (cur >= 0) emit();
+            cur = a;
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          acc.x = fmaf(cf[u], wv[u].x, acc.x); acc.y = fmaf(cf[u], wv[u].y, acc.y);
+          acc.z = fmaf(cf[u], wv[u].z, acc.z); acc.w = fmaf(cf[u], wv[u].w, acc.w);
+        }
+      }
+      if (cur >= 0) emit();
+    }
+    __syncthreads();
+    // phase B
+    auto do_point = [&](int gi, float4 y4, float4 d4) {
+      const int a = gpoint[g0 + gi];
+      const int st = static_cast<int>(start[a] & 0xffffu), en = static_cast<int>(start[a + 1] & 0xffffu);
+      const int wf = (st - R0) / per, wl = (en - 1 - R0) / per;
+      float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kin) {
+        if (wf == wl) {
+          S = *reinterpret_cast<const float4*>(sbuf + static_cast<size_t>(gi) * K + k0);
+        } else {
+          S = *reinterpret_cast<const float4*>(part + static_cast<size_t>(2 * wf + 1) * K + k0);
+          for (int w = wf + 1; w <= wl; ++w) {
+            const float4 t = *reinterpret_cast<const float4*>(part + static_cast<size_t>(2 * w) * K + k0);
+            S.x += t.x; S.y += t.y; S.z += t.z; S.w += t.w;
+          }
+        }
+      }
+      const float yv[4] = {y4.x, y4.y, y4.z, y4.w}, sv[4] = {S.x, S.y, S.z, S.w};
+      float4 mean4 = make_float4(0.f, 0.f, 0.f, 0.f), istd4 = mean4, gam4 = mean4, bet4 = mean4;
+      if (kin) {
+        mean4 = *reinterpret_cast<const float4*>(bn + k0);         istd4 = *reinterpret_cast<const float4*>(bn + K + k0);
+        gam4 = *reinterpret_cast<const float4*>(bn + 2 * K + k0);  bet4 = *reinterpret_cast<const float4*>(bn + 3 * K + k0);
+      }
+      const float mu[4] = {mean4.x, mean4.y, mean4.z, mean4.w}, is[4] = {istd4.x, istd4.y, istd4.z, istd4.w};
+      const float ga[4] = {gam4.x, gam4.y, gam4.z, gam4.w}, be[4] = {bet4.x, bet4.y, bet4.z, bet4.w};
+      float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float yh = (yv[jj] - mu[jj]) * is[jj];
+        const bool on = !o.relu || fmaf(yh, ga[jj], be[jj]) > 0.f;
+        const float v = (kin && on) ? sv[jj] : 0.f;
+        ws[jj] += v;
+        wq[jj] = fmaf(v, yh, wq[jj]);
+        dv[jj] += v;
+      }
+      if (kin)
+        *reinterpret_cast<float4*>(o.dz_prev + (static_cast<int64_t>(b) * N + a) * K + k0) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    };
+#pragma unroll
+    for (int t = 0; t < kSsPre; ++t)
+      if (warp + t * kSsWarps < G) do_point(warp + t * kSsWarps, yp[t], dp[t]);
+    for (int gi = warp + kSsPre * kSsWarps; gi < G; gi += kSsWarps) {
+      float4 y4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = y4;
+      if (kin) {
+        const int64_t mrow = static_cast<int64_t>(b) * N + gpoint[g0 + gi];
+        y4 = *reinterpret_cast<const float4*>(o.y_prev + mrow * K + k0);
+        d4 = *reinterpret_cast<const float4*>(o.dz_prev + mrow * K + k0);
+      }
+      do_point(gi, y4, d4);
+    }
+  }
+  // fixed-order combination of the warps' sums, one fp64 atomic per channel and CTA
+  __syncthreads();
+  float* red = part;                                       // [2][16][K]
+  if (kin) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) { red[warp * K + k0 + jj] = ws[jj]; red[(kSsWarps + warp) * K + k0 + jj] = wq[jj]; }
+  }
+  __syncthreads();
+  for (int k = tid; k < K; k += blockDim.x) {
+    double sd = 0.0, qd = 0.0;
+    for (int w = 0; w < kSsWarps; ++w) { sd += static_cast<double>(red[w * K + k]); qd += static_cast<double>(red[(kSsWarps + w) * K + k]); }
+    if (sd != 0.0 || qd != 0.0) { atomicAdd(&o.sums[k], sd); atomicAdd(&o.sums[K + k], qd); }
+  }
+}
+
 // dW[c,k] = sum_b coef[b,c] (a[(b,sel),k] - abar_k) - kappa_c sum_k' W[c,k'] Ghat[k',k]
 // A CTA owns kDwCh channels (their rows of W staged in shared memory), a thread owns output columns k:
 // one coalesced read of a row of Ghat serves kDwCh accumulators (the previous one-thread-per-output
@@ -1038,7 +1292,6 @@ pool_dw_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
                const int32_t* __restrict__ arg, const float* __restrict__ kappa,
                const float* __restrict__ abar, const float* __restrict__ Ghat, int B, int N,
                int C, int train, float* __restrict__ dW) {
-  pdl_entry();
   // dynamic smem: wrow[kDwCh][K] | sel_cf[B][kDwCh] | sel_m[B][kDwCh] | red[kDwParts][128][kDwCh] doubles
   extern __shared__ __align__(16) float wrow[];
   const int K = src.C;
@@ -1051,6 +1304,7 @@ pool_dw_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict_
     const int j = i / K, k2 = i - j * K;
     wrow[i] = c0 + j < C ? W[static_cast<int64_t>(c0 + j) * K + k2] : 0.f;
   }
+  pdl_entry();                                   // the rows of W (parameters) were staged before the wait
   // the selected point and its coefficient of every (cloud, channel) of this CTA: one round trip here
   // instead of a dependent coef -> arg -> activation chain per term below
   for (int i = threadIdx.x; i < B * kDwCh; i += blockDim.x) {
@@ -1640,8 +1894,8 @@ static int pointmlp_fwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       if (int rc = tc::fwd_layer(tl, w.apack[l], w.wpack[l], y, is_pool, st_l, w.keys, st)) return rc;
       pivot_used = y.bias ? y.bias : w.zeros;
     } else if (layer_narrow(l)) {
-      if (y.cin <= 4) PCUDA_LAUNCH(mlp_fwd_narrow_kernel<4>, narrow_grid(s.M, y.cout), kNarrowThreads, 0, st, src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
-      else PCUDA_LAUNCH(mlp_fwd_narrow_kernel<8>, narrow_grid(s.M, y.cout), kNarrowThreads, 0, st, src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
+      if (y.cin <= 4) PCUDA_LAUNCH_PDL(mlp_fwd_narrow_kernel<4>, narrow_grid(s.M, y.cout), kNarrowThreads, 0, st, src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
+      else PCUDA_LAUNCH_PDL(mlp_fwd_narrow_kernel<8>, narrow_grid(s.M, y.cout), kNarrowThreads, 0, st, src, y.weight, y.bias, y.cout, s.M, y.y, st_l, piv_l);
       launches += 1;
     } else {
       const dim3 grid(B * tps, (y.cout + TN - 1) / TN);
@@ -1868,7 +2122,7 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       // the pooled layer's weight gradient reads coef / kappa (this stream) and abar / Ghat (Gram side) and writes
       // only grad_weight: it runs on the auxiliary stream beside the dgrad kernels below; joined before returning
       if (ax) { cudaEventRecord(ax->fork, st); cudaStreamWaitEvent(sa, ax->fork, 0); }
-      PCUDA_LAUNCH(pool_dw_kernel, (C + kDwCh - 1) / kDwCh, 128 * kDwParts, dw_smem, sa, src, last.weight, w.coef, pool_arg, ka, w.abar, w.Ghat, B, N, C, train, last.grad_weight);
+      PCUDA_LAUNCH_PDL(pool_dw_kernel, (C + kDwCh - 1) / kDwCh, 128 * kDwParts, dw_smem, sa, src, last.weight, w.coef, pool_arg, ka, w.abar, w.Ghat, B, N, C, train, last.grad_weight);
       launches += 1;
     }
     if (L >= 2 || grad_x) {
@@ -1888,7 +2142,19 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
         const bool many_points = K <= 128 && N >= C && sparse_smem <= 100 * 1024;   // ~1 channel per selected point
         const int per_sm = many_points ? 2 : 1;
         const int parts = std::max(1, std::min((std::min(C, N) + 31) / 32, (per_sm * sm_count() + B - 1) / B));
-        if (many_points) PCUDA_LAUNCH((pool_sparse_kernel<4, 4, 2>), dim3(B, parts), 512, sparse_smem, st, pool_arg, w.coef, last.weight, C, N, K, o);
+        // few points, many channels each (N < C, K <= 128): the sorted, evenly cut variant (tuning key 10 < 0: off)
+        const int sb_rows = (C + parts - 1) / parts + 2;
+        const size_t sorted_smem = ss_layout(C, N, K, sb_rows).bytes;
+        const bool rows16 = (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(last.weight) | reinterpret_cast<uintptr_t>(o.y_prev) |
+                                              reinterpret_cast<uintptr_t>(o.dz_prev) | reinterpret_cast<uintptr_t>(o.mean) |
+                                              reinterpret_cast<uintptr_t>(o.invstd) | reinterpret_cast<uintptr_t>(o.gamma) |
+                                              reinterpret_cast<uintptr_t>(o.beta)) & 15u) == 0;
+        const bool sorted = !many_points && K <= 128 && N <= 1024 && o.grad_x == nullptr && rows16 &&
+                            sorted_smem <= 200 * 1024 && tuning(TUNE_SPARSE_SORTED) >= 0;
+        if (sorted) {
+          smem_optin(pool_sparse_sorted_kernel, 200 * 1024);
+          PCUDA_LAUNCH(pool_sparse_sorted_kernel, dim3(B, parts), 32 * kSsWarps, sorted_smem, st, pool_arg, w.coef, last.weight, C, N, K, sb_rows, o);
+        } else if (many_points) PCUDA_LAUNCH((pool_sparse_kernel<4, 4, 2>), dim3(B, parts), 512, sparse_smem, st, pool_arg, w.coef, last.weight, C, N, K, o);
         else if (K <= 128) PCUDA_LAUNCH((pool_sparse_kernel<4, 12, 1>), dim3(B, parts), 512, sparse_smem, st, pool_arg, w.coef, last.weight, C, N, K, o);
         else PCUDA_LAUNCH((pool_sparse_kernel<16, 2, 1>), dim3(B, parts), 512, sparse_smem, st, pool_arg, w.coef, last.weight, C, N, K, o);
         launches += 1;
@@ -1972,8 +2238,8 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
         const uint8_t* side = dgrad_side ? apack[l] : nullptr;
         if (int rc = tc::dgrad_layer(tl, w.dypack, C, w.wtpack, side, o, st)) return rc;
       } else if (o.grad_x != nullptr && narrow_ok(Kp, C) && C <= 128) {
-        if (Kp <= 4) PCUDA_LAUNCH(dgrad_input_narrow_kernel<4>, narrow_grid(s.M, C), kNarrowThreads, 0, st, dys, y.weight, Kp, N, s.M, o.grad_x);
-        else PCUDA_LAUNCH(dgrad_input_narrow_kernel<8>, narrow_grid(s.M, C), kNarrowThreads, 0, st, dys, y.weight, Kp, N, s.M, o.grad_x);
+        if (Kp <= 4) PCUDA_LAUNCH_PDL(dgrad_input_narrow_kernel<4>, narrow_grid(s.M, C), kNarrowThreads, 0, st, dys, y.weight, Kp, N, s.M, o.grad_x);
+        else PCUDA_LAUNCH_PDL(dgrad_input_narrow_kernel<8>, narrow_grid(s.M, C), kNarrowThreads, 0, st, dys, y.weight, Kp, N, s.M, o.grad_x);
         launches += 1;
       } else {
         PCUDA_LAUNCH(dense_dgrad_kernel, dim3(B * tps, (Kp + TN - 1) / TN), kThreads, 0, st, dys, y.weight, N, tps, o);

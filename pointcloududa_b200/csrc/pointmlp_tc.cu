@@ -314,7 +314,6 @@ __device__ __forceinline__ float bf16_at(const uint8_t* slab, int row, int ch) {
 
 template <int MODE>
 __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsParams p) {
-  pdl_entry();
   constexpr int kEpiWarps = WsCfg<MODE>::kEpiWarps, kSub = WsCfg<MODE>::kSub;
   constexpr int kMmaWarp = WsCfg<MODE>::kMmaWarp, kProdWarp = WsCfg<MODE>::kProdWarp;
   extern __shared__ uint8_t smem_raw[];
@@ -350,16 +349,26 @@ __global__ void __launch_bounds__(WsCfg<MODE>::kThreads, 1) ws_kernel(const WsPa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  // Everything above (barriers, TMEM) is independent of the preceding kernel and runs while it finishes.  So does the
+  // fetch of the stationary operand in the forward modes: the packed weights were written on the auxiliary stream (a full
+  // dependency of this launch) or at least two kernels back.  In the dgrad modes the kernel right before this one packs
+  // the operand, so it is fetched after the wait.
+  constexpr bool kEarlyA = MODE == FWD_DENSE || MODE == FWD_POOL;
+  auto load_a = [&]() {
+    const uint32_t a_bytes = static_cast<uint32_t>(p.CB * KS * kSlabA);
+    mbar_arrive_expect_tx(smem_u32(&bars->a_full), a_bytes);
+    const uint8_t* a_src = p.A + static_cast<int64_t>(row_base / 128) * KS * kSlabA;
+    for (uint32_t off = 0; off < a_bytes; off += kSlabA)
+      bulk_g2s(smem_u32(a_smem + off), a_src + off, kSlabA, smem_u32(&bars->a_full));
+  };
+  if (kEarlyA && warp == kProdWarp && lane == 0) load_a();
+  pdl_entry();
   const long long dbg_setup = clock64();
 
   if (warp == kProdWarp) {
     // ================================ producer (one lane) =========================================
     if (lane == 0) {
-      const uint32_t a_bytes = static_cast<uint32_t>(p.CB * KS * kSlabA);
-      mbar_arrive_expect_tx(smem_u32(&bars->a_full), a_bytes);
-      const uint8_t* a_src = p.A + static_cast<int64_t>(row_base / 128) * KS * kSlabA;
-      for (uint32_t off = 0; off < a_bytes; off += kSlabA)
-        bulk_g2s(smem_u32(a_smem + off), a_src + off, kSlabA, smem_u32(&bars->a_full));
+      if (!kEarlyA) load_a();
       uint32_t tc = 0, stage = 0, ph = 0;
       for (int t = t_begin; t < t_end; ++t, ++tc) {
         for (int s = 0; s < KS; ++s, stage = (stage + 1 == static_cast<uint32_t>(p.nstage)) ? 0u : stage + 1, ph ^= (stage == 0u)) {
@@ -678,7 +687,6 @@ struct __align__(8) PtBarriers {
 };
 
 __global__ void __launch_bounds__(kPtThreads, 1) pt_kernel(const PtParams p) {
-  pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int GR = p.Kr >> 6;                       // slabs per tile of R
@@ -706,6 +714,7 @@ __global__ void __launch_bounds__(kPtThreads, 1) pt_kernel(const PtParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  pdl_entry();                                    // the set-up above overlaps the preceding kernel
 
   if (warp == 5) {
     if (lane == 0) {
@@ -815,7 +824,7 @@ int launch_ws(WsParams& p, cudaStream_t st, const char* what) {
     cudaError_t e = smem_optin(ws_kernel<MODE>, static_cast<int>(kSmemBudget));
     if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
   }
-  PCUDA_LAUNCH(ws_kernel<MODE>, pl.grid, WsCfg<MODE>::kThreads, pl.smem, st, p);
+  PCUDA_LAUNCH_PDL(ws_kernel<MODE>, pl.grid, WsCfg<MODE>::kThreads, pl.smem, st, p);
   count_launch();
   return check_launch(what);
 }
@@ -916,7 +925,7 @@ static int launch_pt(PtParams& p, cudaStream_t st, const char* what) {
     if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
   }
   const dim3 grid(p.S, (p.C + 127) / 128);
-  PCUDA_LAUNCH(pt_kernel, grid, kPtThreads, fixed + p.nstage * stage, st, p);
+  PCUDA_LAUNCH_PDL(pt_kernel, grid, kPtThreads, fixed + p.nstage * stage, st, p);
   count_launch();
   return check_launch(what);
 }
