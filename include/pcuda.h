@@ -18,7 +18,8 @@
  *   pcuda_bn_running_update       BatchNorm1d running statistics of several forward passes, in pass order
  *   pcuda_bce_logits              F.binary_cross_entropy_with_logits + accuracy, train_mscmrseg.py:233,286-296,316-322
  *   pcuda_grad_sum_pack /         .grad accumulation of the two D4 backward passes (train_mscmrseg.py:288,319) and
- *   pcuda_sgd_momentum_step       optim_dis4.step() = torch.optim.SGD(momentum, weight_decay) (:329-330,:450-455)
+ *   pcuda_sgd_momentum_step /     optim_dis4.step() = torch.optim.SGD(momentum, weight_decay) (:329-330,:450-455)
+ *   pcuda_sgd_momentum_sum_step
  *   pcuda_fps                     utils/npy2point.py:11-18 (graipher: farthest-point sampling of the GT boundary clouds)
  *   pcuda_comm_*                  no counterpart (the reference is single-process): sum of D4's parameter gradients over
  *                                 the batch-sharded ranks in front of optim_dis4.step()
@@ -316,6 +317,8 @@ int pcuda_bn_running_update(int n, const pcuda_bn_update_t* items /*host*/, pcud
  *                             buf = momentum * flat_momentum[offset_i + j] + g;  param_i[j] -= lr * buf
  *                             (torch.optim.SGD, dampening 0, nesterov off; a zero-initialised buffer reproduces
  *                             torch's first step).  lr is read from device memory (*lr_dev).
+ *   pcuda_sgd_momentum_sum_step: both in one launch for a single process (nothing to exchange in between): flat_grad
+ *                             receives scale * (grad_a + grad_b) as above and the update uses it; same roundings.
  */
 typedef struct pcuda_param_slot {
   const float* grad_a;   /* [numel] (pack only) */
@@ -327,6 +330,8 @@ typedef struct pcuda_param_slot {
 int pcuda_grad_sum_pack(const pcuda_param_slot_t* slots /*host*/, int n, float scale, float* flat, pcuda_stream_t stream);
 int pcuda_sgd_momentum_step(const pcuda_param_slot_t* slots /*host*/, int n, const float* flat_grad, float* flat_momentum,
                             const float* lr_dev, float momentum, float weight_decay, pcuda_stream_t stream);
+int pcuda_sgd_momentum_sum_step(const pcuda_param_slot_t* slots /*host*/, int n, float scale, float* flat_grad, float* flat_momentum,
+                                const float* lr_dev, float momentum, float weight_decay, pcuda_stream_t stream);
 
 /* ---- discriminator bookkeeping ---------------------------------------------------------------------
  * Replaces F.binary_cross_entropy_with_logits(D_out4, full_like(D_out4, label)) (reduction 'mean',

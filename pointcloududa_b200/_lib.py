@@ -104,6 +104,8 @@ SIGNATURES = {
     "pcuda_bce_logits": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pcuda_sgd_momentum_step": (c_int, [POINTER(ParamSlot), c_int, c_void_p, c_void_p, c_void_p, c_float, c_float,
                                         c_void_p]),
+    "pcuda_sgd_momentum_sum_step": (c_int, [POINTER(ParamSlot), c_int, c_float, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                            c_void_p]),
     "pcuda_fps": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pcuda_comm_unique_id": (c_int, [c_void_p, c_int]),
     "pcuda_comm_init": (c_int, [c_void_p, c_int, c_int, c_size_t, POINTER(c_void_p)]),

@@ -79,6 +79,33 @@ __global__ void __launch_bounds__(kThreads) sgd_momentum_kernel(const __grid_con
   }
 }
 
+// single-process step (no exchange between the sum and the update): both of the above in one pass, the summed gradient
+// still written to the bucket (flat_grad) for whoever inspects it.  Same roundings as the two-launch path.
+__global__ void __launch_bounds__(kThreads) sgd_momentum_sum_kernel(const __grid_constant__ Table t, float scale, float* __restrict__ flat_grad,
+                                                                    float* __restrict__ flat_mom, const float* __restrict__ lr_dev,
+                                                                    float momentum, float weight_decay) {
+  pdl_entry();
+  const int i = find_slot(t, blockIdx.x);
+  const Slot& s = t.s[i];
+  const float lr = __ldg(lr_dev);
+  const long long base = static_cast<long long>(blockIdx.x - t.cta_start[i]) * kChunk;
+#pragma unroll
+  for (int u = 0; u < kPerThread; ++u) {
+    const long long j = base + u * kThreads + threadIdx.x;
+    if (j < s.numel) {
+      float g = s.ga[j];
+      if (s.gb != nullptr) g = __fadd_rn(g, s.gb[j]);
+      if (scale != 1.0f) g = __fmul_rn(g, scale);
+      flat_grad[s.offset + j] = g;
+      const float p = s.param[j];
+      if (weight_decay != 0.0f) g = __fmaf_rn(weight_decay, p, g);
+      const float buf = __fadd_rn(__fmul_rn(momentum, flat_mom[s.offset + j]), g);
+      flat_mom[s.offset + j] = buf;
+      s.param[j] = __fmaf_rn(-lr, buf, p);
+    }
+  }
+}
+
 // ---- discriminator bookkeeping: BCE-with-logits (mean), its gradient and the accuracy, one warp ----------
 // loss = weight * mean_i [ (1 - t) x_i - log_sigmoid(x_i) ]   (F.binary_cross_entropy_with_logits, reduction 'mean',
 // train_mscmrseg.py:233,286,316), grad_i = weight * (sigmoid(x_i) - t) / n, acc = mean_i [ (sigmoid(x_i) >= 0.5) == (t >= 0.5) ]
@@ -153,6 +180,19 @@ extern "C" int pcuda_sgd_momentum_step(const pcuda_param_slot_t* slots, int n, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return for_each_table(slots, n, "sgd_momentum_step", true, [&](const Table& t, int ctas) {
     PCUDA_LAUNCH(sgd_momentum_kernel, ctas, kThreads, 0, st, t, flat_grad, flat_momentum, lr_dev, momentum, weight_decay);
+  });
+}
+
+extern "C" int pcuda_sgd_momentum_sum_step(const pcuda_param_slot_t* slots, int n, float scale, float* flat_grad, float* flat_momentum,
+                                           const float* lr_dev, float momentum, float weight_decay, pcuda_stream_t stream) {
+  PCUDA_REQUIRE(n >= 0, PCUDA_E_SHAPE, "sgd_momentum_sum_step: n=%d", n);
+  if (n == 0) return 0;
+  PCUDA_REQUIRE(slots && flat_grad && flat_momentum && lr_dev, PCUDA_E_NULL, "sgd_momentum_sum_step: NULL argument");
+  for (int i = 0; i < n; ++i)
+    PCUDA_REQUIRE(slots[i].numel == 0 || (slots[i].grad_a && slots[i].param), PCUDA_E_NULL, "sgd_momentum_sum_step: slot %d has a NULL tensor", i);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return for_each_table(slots, n, "sgd_momentum_sum_step", true, [&](const Table& t, int ctas) {
+    PCUDA_LAUNCH(sgd_momentum_sum_kernel, ctas, kThreads, 0, st, t, scale, flat_grad, flat_momentum, lr_dev, momentum, weight_decay);
   });
 }
 

@@ -209,6 +209,22 @@ def bce_with_logits(logit: torch.Tensor, target: float, weight: float = 1.0):
     return _BceLogits.apply(logit, float(target), float(weight))
 
 
+def bce_with_logits_grad(logit: torch.Tensor, target: float, weight: float = 1.0):
+    """(loss, accuracy, d loss / d logit) of bce_with_logits in the same one launch, outside autograd: the caller
+    continues with torch.autograd.grad(logit, inputs, grad_outputs=grad) — no unit root gradient to fill, no
+    gradient-times-one launch on the way back (the adversarial step's three D4 passes end this way)."""
+    _require_cuda_f32(logit, "logit")
+    x = logit.detach().contiguous()
+    dev = x.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    acc = torch.empty((), dtype=torch.float32, device=dev)
+    grad = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        check(_lib.lib().pcuda_bce_logits(_ptr(x), x.numel(), float(target), float(weight), _ptr(loss), _ptr(grad),
+                                          _ptr(acc), _stream()), "pcuda_bce_logits")
+    return loss, acc, grad
+
+
 def launch_count() -> int:
     """Kernels launched by libpcuda in this process so far."""
     return int(_lib.lib().pcuda_launch_count())

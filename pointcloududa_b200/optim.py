@@ -51,6 +51,13 @@ class FusedSGD:
         """flat[slice_i] = scale * (grads_a[i] + grads_b[i]) for every parameter, one launch."""
         if flat.numel() != self.numel or flat.dtype != torch.float32 or not flat.is_contiguous():
             raise PcudaError("pack: flat bucket does not match the parameter list")
+        keep = self._bind_grads(grads_a, grads_b)
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            check(L.pcuda_grad_sum_pack(self._slots, len(self._slots), float(scale), flat.data_ptr(), st), "pcuda_grad_sum_pack")
+
+    def _bind_grads(self, grads_a, grads_b) -> list:
         keep = []
         for i, s in enumerate(self._slots):
             ga = grads_a[i]
@@ -63,10 +70,24 @@ class FusedSGD:
                 raise PcudaError("pack: gradient shape mismatch")
             keep += [ga, gb]
             s.grad_a, s.grad_b = ga.data_ptr(), _ptr(gb)
+        return keep
+
+    def sum_step(self, grads_a: Sequence[torch.Tensor], grads_b: Optional[Sequence[torch.Tensor]], flat: torch.Tensor,
+                 scale: float = 1.0) -> None:
+        """pack() followed by step(flat) in ONE launch: for a single process, where nothing is exchanged in between.
+        `flat` still receives the summed gradient."""
+        if flat.numel() != self.numel or flat.dtype != torch.float32 or not flat.is_contiguous():
+            raise PcudaError("sum_step: flat bucket does not match the parameter list")
+        keep = self._bind_grads(grads_a, grads_b)
+        for s, p in zip(self._slots, self.params):
+            s.param = p.data_ptr()
         L = _lib.lib()
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
-            check(L.pcuda_grad_sum_pack(self._slots, len(self._slots), float(scale), flat.data_ptr(), st), "pcuda_grad_sum_pack")
+            check(L.pcuda_sgd_momentum_sum_step(self._slots, len(self._slots), float(scale), flat.data_ptr(),
+                                                self.momentum_buffer.data_ptr(), self.lr.data_ptr(), self.momentum,
+                                                self.weight_decay, st), "pcuda_sgd_momentum_sum_step")
+        del keep
 
     def step(self, flat_grad: torch.Tensor) -> None:
         """One SGD step of every parameter from the flat gradient bucket, one launch."""

@@ -35,7 +35,7 @@ import torch
 
 from . import dist as pdist
 from .networks.PointNetCls import PointNetCls, apply_bn_updates, deferred_bn_updates
-from .ops import bce_with_logits
+from .ops import bce_with_logits_grad
 from .optim import FusedSGD
 from .utils.loss import batch_NN_loss, entropy_map
 
@@ -123,6 +123,7 @@ class AdversarialStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_post: Optional[torch.cuda.CUDAGraph] = None
         self._res = []
+        self._pending = None
         self._side = None
         self.concurrent = concurrent
 
@@ -203,8 +204,8 @@ class AdversarialStep:
         vertT = I["vertT"].detach().requires_grad_(True)
         with deferred_bn_updates(sink_p2):
             D_out4 = self.d4(vertT.transpose(2, 1))[0]
-        loss_adv_point, _ = bce_with_logits(D_out4, 1.0, cfg.dr)
-        (gT,) = torch.autograd.grad(loss_adv_point, vertT)
+        loss_adv_point, _, g_logit = bce_with_logits_grad(D_out4, 1.0, cfg.dr)
+        (gT,) = torch.autograd.grad(D_out4, vertT, g_logit)
         self.grad_vertT.copy_(gT)
         self._set_requires_grad(True)
 
@@ -217,15 +218,15 @@ class AdversarialStep:
                 entropy_map(I["oS"], activation=cfg.activation, normalize=cfg.normalize, return_prob=cfg.return_prob)
             with deferred_bn_updates(sink_p3):
                 D_out4, leaves = self._d4_fresh(I["vertS"].transpose(2, 1))
-            loss_D_same4, acc_s = bce_with_logits(D_out4, 1.0)
-            grads_s = torch.autograd.grad(loss_D_same4, leaves, allow_unused=True)
+            loss_D_same4, acc_s, g_logit = bce_with_logits_grad(D_out4, 1.0)
+            grads_s = torch.autograd.grad(D_out4, leaves, g_logit, allow_unused=True)
 
         # ---- branch C (stream s2) — P4: discriminators on the target domain (label 0)
         with torch.cuda.stream(s2):
             with deferred_bn_updates(sink_p4):
                 D_out4, leaves = self._d4_fresh(I["vertT"].transpose(2, 1))
-            loss_D_diff_4, acc_t = bce_with_logits(D_out4, 0.0)
-            grads_t = torch.autograd.grad(loss_D_diff_4, leaves, allow_unused=True)
+            loss_D_diff_4, acc_t, g_logit = bce_with_logits_grad(D_out4, 0.0)
+            grads_t = torch.autograd.grad(D_out4, leaves, g_logit, allow_unused=True)
 
         # ---- join: parameter gradients into the flat bucket, BatchNorm buffers in the reference's pass order
         if self.concurrent:
@@ -240,10 +241,13 @@ class AdversarialStep:
                     if t is not None:
                         t.record_stream(main)
         # bucket = (grads_s + grads_t) / world: one launch; the division is the "mean" of the gradient all-reduce
+        self._pending = None
         if any(g is None for g in grads_s) or any(g is None for g in grads_t):
             self.bucket.assign_sum(grads_s, grads_t)          # a parameter without gradient: zero-fill + accumulate
             if self._world > 1:
                 self.bucket.flat.div_(self._world)
+        elif self._world == 1:
+            self._pending = (grads_s, grads_t)                # nothing to exchange: summed inside the SGD launch (_post)
         else:
             self.opt.pack(grads_s, grads_t, self.bucket.flat, scale=1.0 / self._world)
         apply_bn_updates([sink_p2, sink_p3, sink_p4])
@@ -266,8 +270,23 @@ class AdversarialStep:
 
     def _post(self) -> None:
         # P5 (after the gradient all-reduce): SGD step of D4, scalars of the step into one small tensor
-        self.opt.step(self._grad_final)
-        self.result.copy_(torch.stack([r.reshape(()).float() for r in self._res]))
+        main = torch.cuda.current_stream(self.device)
+        side = self._side[2] if self.concurrent else main
+        if self.concurrent:
+            # the scalars of the step are gathered beside the optimiser launch, not after it
+            side.wait_stream(main)
+            if not torch.cuda.is_current_stream_capturing():
+                for r in self._res:
+                    r.record_stream(side)
+        with torch.cuda.stream(side):
+            self.result.copy_(torch.stack([r.reshape(()).float() for r in self._res]))
+        if self._pending is not None:
+            self.opt.sum_step(self._pending[0], self._pending[1], self.bucket.flat)
+            self._pending = None
+        else:
+            self.opt.step(self._grad_final)
+        if self.concurrent:
+            main.wait_stream(side)
 
     def _sync_world(self) -> None:
         import torch.distributed as dist

@@ -978,6 +978,31 @@ def test_fused_sgd_matches_torch_sgd():
     assert torch.equal(flat, torch.cat([a.reshape(-1) for a in ga]))
 
 
+def test_fused_sgd_sum_step_equals_pack_then_step():
+    """pcuda_sgd_momentum_sum_step (single process: nothing is exchanged between the gradient sum and the update)
+    is bit-identical to pcuda_grad_sum_pack followed by pcuda_sgd_momentum_step, bucket included."""
+    from pointcloududa_b200.optim import FusedSGD
+    g = torch.Generator().manual_seed(5)
+    shapes = [(64, 3), (64,), (1024, 128), (512, 1024), (9,), (5, 7, 3)]
+    init = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+    two = [torch.nn.Parameter(p.clone()) for p in init]
+    one = [torch.nn.Parameter(p.clone()) for p in init]
+    o2 = FusedSGD(two, lr=2.5e-3, momentum=0.99, weight_decay=0.0005)
+    o1 = FusedSGD(one, lr=2.5e-3, momentum=0.99, weight_decay=0.0005)
+    f2, f1 = torch.zeros(o2.numel, device=DEV), torch.zeros(o1.numel, device=DEV)
+    for it in range(4):
+        ga = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+        gb = [torch.randn(s, generator=g).to(DEV) for s in shapes] if it != 2 else None
+        scale = 0.25 if it == 3 else 1.0
+        o2.pack(ga, gb, f2, scale=scale)
+        o2.step(f2)
+        o1.sum_step(ga, gb, f1, scale=scale)
+        assert torch.equal(f1, f2)
+        assert torch.equal(o1.momentum_buffer, o2.momentum_buffer)
+        for p, q in zip(one, two):
+            assert torch.equal(p, q)
+
+
 @pytest.mark.parametrize("target,weight,n", [(1.0, 1.0, 8), (0.0, 1.0, 32), (1.0, 0.01, 5), (0.0, 0.3, 70)])
 def test_bce_with_logits_matches_torch(target, weight, n):
     """pcuda_bce_logits against F.binary_cross_entropy_with_logits + autograd + the accuracy expression of
@@ -996,6 +1021,10 @@ def test_bce_with_logits_matches_torch(target, weight, n):
     assert max_rel(go.cpu().numpy() / 2.0, gw.cpu().numpy()) < 2e-6
     pred = (torch.sigmoid(x) >= 0.5).float().mean().item()
     assert abs(acc.item() - (pred if target >= 0.5 else 1.0 - pred)) < 1e-6
+    # the autograd-free form the adversarial step uses: same launch, the gradient handed back directly
+    loss2, acc2, g2 = ops.bce_with_logits_grad(xo, target, weight)
+    assert torch.equal(loss2, loss.detach()) and torch.equal(acc2, acc) and torch.equal(g2 * 2.0, go)
+    assert not g2.requires_grad and not loss2.requires_grad
 
 
 # ================================================================ per-cloud transforms ==============
