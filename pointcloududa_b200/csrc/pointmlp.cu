@@ -515,33 +515,39 @@ __global__ void dense_out_kernel(ActSrc src, int B, float* __restrict__ out) {
 }
 
 // ---- backward: pooled last layer ---------------------------------------------------------------
-// One warp per (cloud, channel): masked upstream gradient and yhat at the selected point.
+// One warp per (cloud, channel): masked upstream gradient and yhat at the selected point.  Only grad_out comes from the
+// kernel before this one: the pre-BN value at the selected point (a K-long dot product behind a dependent arg -> row
+// fetch) is recomputed from forward-pass state before the grid-dependency wait.
 __global__ void pool_sel_kernel(ActSrc src, const float* __restrict__ W, const float* __restrict__ bias,
                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                 const float* __restrict__ gamma, int relu, const float* __restrict__ out,
                                 const int32_t* __restrict__ arg, const float* __restrict__ grad_out, int B, int N,
                                 int C, float* __restrict__ coef, float* __restrict__ gsel, float* __restrict__ gyh) {
-  pdl_entry();
   const int64_t w = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (w >= static_cast<int64_t>(B) * C) return;
-  const int c = static_cast<int>(w % C);
-  const int64_t b = w / C;
+  const bool valid = w < static_cast<int64_t>(B) * C;
+  const int c = valid ? static_cast<int>(w % C) : 0;
+  const int64_t b = valid ? w / C : 0;
   const int K = src.C;
-  float g = grad_out[w];
-  if (relu && !(out[w] > 0.f)) g = 0.f;
-  float yhat = 0.f;
-  if (g != 0.f) {
+  float yhat = 0.f, ov = 0.f, sc = 0.f;
+  if (valid) {
     const int64_t m = b * N + arg[w];
+    ov = out[w];
+    const float mu = mean[c], is = invstd[c], bs = bias ? bias[c] : 0.f;
+    sc = gamma[c] * is;
     float dot = 0.f;
     for (int k = lane; k < K; k += 32) dot = fmaf(W[static_cast<int64_t>(c) * K + k], load_act1(src, m, k), dot);
     dot = warp_sum(dot);
-    yhat = (dot + (bias ? bias[c] : 0.f) - mean[c]) * invstd[c];
+    yhat = (dot + bs - mu) * is;
   }
+  pdl_entry();
+  if (!valid) return;
+  float g = grad_out[w];
+  if (relu && !(ov > 0.f)) g = 0.f;
   if (lane == 0) {
-    coef[w] = gamma[c] * invstd[c] * g;
+    coef[w] = sc * g;
     gsel[w] = g;
-    gyh[w] = g * yhat;
+    gyh[w] = g != 0.f ? g * yhat : 0.f;
   }
 }
 
@@ -726,29 +732,47 @@ __global__ void gram_center_kernel(const double* __restrict__ abar_d, const doub
 }
 
 // Q[k,k'] = sum_c kappa_c W[c,k] W[c,k'].  grid (K/32, K/32, CS), 256 threads, each 2x2 outputs; slice z
-// of the channels goes to partial[z] (reduced in a fixed order by reduce_partials_kernel).  The 32 x 32
-// output tile walks over its channels in chunks of 32 staged in shared memory.
+// of the channels goes to partial[z] (reduced in a fixed order by q_finish_kernel / reduce_partials_kernel).  The 32 x 32
+// output tile walks over its channels in chunks of 32 staged in shared memory.  The tiles of W (parameters) of the
+// first kQPre chunks are requested before the grid-dependency wait and all at once; kappa / alpha after it.
+// upartial != nullptr: the CTAs of the first tile column also emit  upartial[z][k] = sum_{c in slice z} alpha_c W[c,k],
+// the first term of u' (they hold those tiles of W anyway).
 constexpr int kPoolQSplits = 8;
+constexpr int kQPre = 4;
 __global__ void __launch_bounds__(256)
-pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, int C, int K, float* __restrict__ partial) {
-  pdl_entry();
+pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, const float* __restrict__ alpha, int C, int K,
+              float* __restrict__ partial, float* __restrict__ upartial) {
   __shared__ float Wa[32][33], Wb[32][33];
+  __shared__ float ured[8][32];
   const int k0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
   const int per = (C + gridDim.z - 1) / gridDim.z;
   const int cbeg = blockIdx.z * per, cend = min(C, cbeg + per);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int lr = threadIdx.x >> 5, lc = threadIdx.x & 31;   // loader: 8 rows x 32 columns per pass
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int c0 = cbeg; c0 < cend; c0 += 32) {
-    float ra[4], rb[4];
+  const bool with_u = upartial != nullptr && blockIdx.y == 0;
+  float wa[kQPre][4], wb[kQPre][4];
+#pragma unroll
+  for (int it = 0; it < kQPre; ++it)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int c = c0 + lr + 8 * i;
+      const int c = cbeg + 32 * it + lr + 8 * i;
       const bool ok = c < cend;
-      const float kp = ok ? kappa[c] : 0.f;
-      ra[i] = (ok && k0 + lc < K) ? kp * W[static_cast<int64_t>(c) * K + k0 + lc] : 0.f;
-      rb[i] = (ok && j0 + lc < K) ? W[static_cast<int64_t>(c) * K + j0 + lc] : 0.f;
+      wa[it][i] = (ok && k0 + lc < K) ? W[static_cast<int64_t>(c) * K + k0 + lc] : 0.f;
+      wb[it][i] = (ok && j0 + lc < K) ? W[static_cast<int64_t>(c) * K + j0 + lc] : 0.f;
     }
+  pdl_entry();
+  float kp[kQPre][4], al[kQPre][4];
+#pragma unroll
+  for (int it = 0; it < kQPre; ++it)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = cbeg + 32 * it + lr + 8 * i;
+      kp[it][i] = c < cend ? kappa[c] : 0.f;
+      al[it][i] = (with_u && c < cend) ? alpha[c] : 0.f;
+    }
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float uacc = 0.f;
+  auto chunk = [&](const float (&ra)[4], const float (&rb)[4]) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) { Wa[lr + 8 * i][lc] = ra[i]; Wb[lr + 8 * i][lc] = rb[i]; }
@@ -759,6 +783,27 @@ pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, int 
       acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
       acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
     }
+  };
+#pragma unroll
+  for (int it = 0; it < kQPre; ++it) {
+    if (cbeg + 32 * it >= cend) break;
+    float ra[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ra[i] = kp[it][i] * wa[it][i]; uacc = fmaf(al[it][i], wa[it][i], uacc); }
+    chunk(ra, wb[it]);
+  }
+  for (int c0 = cbeg + 32 * kQPre; c0 < cend; c0 += 32) {      // slices longer than kQPre chunks
+    float ra[4], rb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + lr + 8 * i;
+      const bool ok = c < cend;
+      const float wk = (ok && k0 + lc < K) ? W[static_cast<int64_t>(c) * K + k0 + lc] : 0.f;
+      ra[i] = ok ? kappa[c] * wk : 0.f;
+      if (with_u && ok) uacc = fmaf(alpha[c], wk, uacc);
+      rb[i] = (ok && j0 + lc < K) ? W[static_cast<int64_t>(c) * K + j0 + lc] : 0.f;
+    }
+    chunk(ra, rb);
   }
   float* Q = partial + static_cast<int64_t>(blockIdx.z) * K * K;
 #pragma unroll
@@ -768,6 +813,16 @@ pool_q_kernel(const float* __restrict__ W, const float* __restrict__ kappa, int 
       const int k = k0 + ty * 2 + i, k2 = j0 + tx * 2 + j;
       if (k < K && k2 < K) Q[static_cast<int64_t>(k) * K + k2] = acc[i][j];
     }
+  if (with_u) {
+    ured[lr][lc] = uacc;
+    __syncthreads();
+    if (lr == 0 && k0 + lc < K) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += ured[r][lc];
+      upartial[static_cast<int64_t>(blockIdx.z) * K + k0 + lc] = t;
+    }
+  }
 }
 
 // u'[k] = sum_c alpha_c W[c,k] - sum_k' Q[k',k] abar_k'.  grid K/32, 1024 threads: lane = k, the 32 warps
@@ -1644,7 +1699,7 @@ FwdWs carve_fwd(const Shape& s, const pcuda_mlp_layer_t* layers, void* base) {
 }
 
 struct BwdWs {
-  double* sums; float* alpha; float* kappa; float* partial; float* qpartial;
+  double* sums; float* alpha; float* kappa; float* partial; float* qpartial; float* upartial;
   float *coef, *gsel, *gyh, *Ghat, *Q, *abar, *u;
   double *colsum, *G, *abar_d;
   float* dzbuf[2];
@@ -1675,6 +1730,7 @@ BwdWs carve_bwd(const Shape& s, const pcuda_mlp_layer_t* layers, void* base) {
     w.u = cv.take<float>(K);
     w.abar_d = cv.take<double>(K);
     w.qpartial = cv.take<float>(static_cast<size_t>(kPoolQSplits) * K * K);   // pool_q runs beside the Gram chain
+    w.upartial = cv.take<float>(static_cast<size_t>(kPoolQSplits) * K);
     if (tc::supports(static_cast<int>(K))) w.qpack = cv.take<uint8_t>(tc::w_pack_bytes(static_cast<int>(K), static_cast<int>(K)));
   }
   w.dzbuf[0] = cv.take<float>(static_cast<size_t>(s.M) * s.maxC);
@@ -2079,7 +2135,7 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
     PCUDA_LAUNCH(gram_center_kernel, static_cast<int>((kk + 255) / 256), 256, 0, sa, w.abar_d, w.G, K, count_local, w.Ghat);
     if (ax) cudaEventRecord(ax->side, sa);
     // -- selection side: per-(cloud, channel) coefficients, alpha / kappa, Q = W^T diag(kappa) W
-    PCUDA_LAUNCH(pool_sel_kernel, static_cast<int>((bc * 32 + 255) / 256), 256, 0, st, src, last.weight, last.bias, last.save_mean,
+    PCUDA_LAUNCH_PDL(pool_sel_kernel, static_cast<int>((bc * 32 + 255) / 256), 256, 0, st, src, last.weight, last.bias, last.save_mean,
                                                                             last.save_invstd, last.gamma, last.relu, out, pool_arg,
                                                                             grad_out, B, N, C, w.coef, w.gsel, w.gyh);
     const bool want_last = last.grad_weight != nullptr;
@@ -2096,15 +2152,17 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
                    want_last ? last.grad_gamma : nullptr, want_last ? last.grad_beta : nullptr, want_last ? last.grad_bias : nullptr,
                    static_cast<double*>(nullptr), 0);
     }
-    PCUDA_LAUNCH(pool_q_kernel, dim3((K + 31) / 32, (K + 31) / 32, kPoolQSplits), 256, 0, st, last.weight, ka, C, K, w.qpartial);
     // the low-rank dgrad runs on the tensor cores (decided here: it changes how Q is finished)
     const bool tc_pool = (L >= 2 || grad_x) && tc_on(precision, TC_POOL_DGRAD) && a_in && w.qpack && tc::pool_dgrad_fits(K) &&
                          pool_sparse_smem(C, N, K) <= 200 * 1024 && K <= 512 && C <= 65535;
-    if (tc_pool && !tuning(TUNE_MLP_NO_FORK)) {
-      // -- join: u needs Q (this stream) and abar (Gram side); one launch sums the partials of Q, packs Q as the
-      // stationary bf16 operand of the dgrad GEMM and forms u
+    const bool fused_tail = tc_pool && !tuning(TUNE_MLP_NO_FORK);
+    PCUDA_LAUNCH_PDL(pool_q_kernel, dim3((K + 31) / 32, (K + 31) / 32, kPoolQSplits), 256, 0, st, last.weight, ka, al, C, K, w.qpartial,
+                     fused_tail ? w.upartial : static_cast<float*>(nullptr));
+    if (fused_tail) {
+      // -- join: u needs Q (this stream) and abar (Gram side); one launch sums the partials of Q (and of the alpha term
+      // of u), packs Q as the stationary bf16 operand of the dgrad GEMM and forms u
       if (ax) cudaStreamWaitEvent(st, ax->side, 0);
-      if (int rc = tc::q_finish(w.qpartial, kPoolQSplits, last.weight, al, w.abar, C, K, w.Q, w.qpack, w.u, st)) return rc;
+      if (int rc = tc::q_finish(w.qpartial, w.upartial, kPoolQSplits, w.abar, K, w.Q, w.qpack, w.u, st)) return rc;
       q_packed = true;
       launches += 6;     // reduce<double>, abar, gram_center, pool_sel, pool_coef, pool_q (tc:: calls count themselves)
     } else {

@@ -209,28 +209,15 @@ __global__ void __launch_bounds__(256) pack_w_kernel(const float* __restrict__ W
 // in the same launch, emits everything that follows from it — Q in fp32, Q as the packed bf16 stationary operand of
 // the low-rank dgrad GEMM (exactly what pack_w_kernel would write for the K-major [K, K] matrix) and
 //     u'[k] = sum_c alpha_c W[c,k] - sum_k2 Q[k,k2] abar[k2]            (Q is symmetric)
-// (three launches of 2-5 us each, back to back on the critical chain of every backward pass, before).
-// grid = ceil(K/128)*4 CTAs of 1024 threads; a CTA owns 32 rows of Q: phase 1 lane = row (coalesced rows of W, the
-// 32 warps interleave c), phase 2 warp = row (lanes over the 16-byte chunks of the row).
-__global__ void __launch_bounds__(1024) q_finish_kernel(const float* __restrict__ partial, int S, const float* __restrict__ W,
-                                                        const float* __restrict__ alpha, const float* __restrict__ abar,
-                                                        int C, int K, float* __restrict__ Q, uint8_t* __restrict__ qpack,
-                                                        float* __restrict__ u) {
+// whose first term arrives as S partial sums from pool_q_kernel (upartial[z][k]).
+// One warp per row of Q (lanes over its 16-byte chunks, all S x 2 loads of a chunk in flight at once), 8 rows per CTA.
+constexpr int kQfRows = 8;
+__global__ void __launch_bounds__(32 * kQfRows) q_finish_kernel(const float* __restrict__ partial, const float* __restrict__ upartial, int S,
+                                                                const float* __restrict__ abar, int K, float* __restrict__ Q,
+                                                                uint8_t* __restrict__ qpack, float* __restrict__ u) {
   pdl_entry();
-  __shared__ double part[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r0 = blockIdx.x * 32;
-  {
-    const int k = r0 + lane;
-    float f = 0.f;
-    if (k < K) {
-#pragma unroll 8
-      for (int c = warp; c < C; c += 32) f = fmaf(alpha[c], W[static_cast<int64_t>(c) * K + k], f);
-    }
-    part[warp][lane] = static_cast<double>(f);
-  }
-  __syncthreads();
-  const int r = r0 + warp;
+  const int r = blockIdx.x * kQfRows + warp;
   const int nchunk = K >> 3;
   uint8_t* prow = qpack ? qpack + static_cast<int64_t>(r >> 7) * K * 256 : nullptr;
   if (r >= K) {                                   // padding rows of the last 128-row block: zeros, like pack_w_kernel
@@ -239,6 +226,9 @@ __global__ void __launch_bounds__(1024) q_finish_kernel(const float* __restrict_
         *reinterpret_cast<uint4*>(prow + (ch >> 3) * kSlabA + slab_off(r & 127, ch & 7)) = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
+  double u1 = 0.0;
+  if (lane < S) u1 = static_cast<double>(upartial[static_cast<int64_t>(lane) * K + r]);
+  for (int z = 32 + lane; z < S; z += 32) u1 += static_cast<double>(upartial[static_cast<int64_t>(z) * K + r]);
   double dot = 0.0;
   const int64_t kk = static_cast<int64_t>(K) * K;
   for (int ch = lane; ch < nchunk; ch += 32) {
@@ -246,6 +236,7 @@ __global__ void __launch_bounds__(1024) q_finish_kernel(const float* __restrict_
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.0;
     const float* p0 = partial + static_cast<int64_t>(r) * K + ch * 8;
+#pragma unroll 8
     for (int z = 0; z < S; ++z) {
       const float4 a = *reinterpret_cast<const float4*>(p0 + z * kk);
       const float4 b = *reinterpret_cast<const float4*>(p0 + z * kk + 4);
@@ -262,14 +253,10 @@ __global__ void __launch_bounds__(1024) q_finish_kernel(const float* __restrict_
 #pragma unroll
     for (int e = 0; e < 8; ++e) dot += static_cast<double>(q[e]) * static_cast<double>(abar[ch * 8 + e]);
   }
+  // butterfly sums: every lane ends with the same value, in a fixed order
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  if (lane == 0) {
-    double t = 0.0;
-#pragma unroll
-    for (int w2 = 0; w2 < 32; ++w2) t += part[w2][warp];
-    u[r] = static_cast<float>(t - dot);
-  }
+  for (int o = 16; o > 0; o >>= 1) { dot += __shfl_xor_sync(0xffffffffu, dot, o); u1 += __shfl_xor_sync(0xffffffffu, u1, o); }
+  if (lane == 0) u[r] = static_cast<float>(u1 - dot);
 }
 
 // ================================= weight-stationary GEMM ==========================================
@@ -870,10 +857,11 @@ int pack_w(const float* W, int R, int K, bool transposed, uint8_t* out, cudaStre
   return check_launch("tc::pack_w");
 }
 
-int q_finish(const float* partial, int S, const float* W, const float* alpha, const float* abar, int C, int K, float* Q,
-             uint8_t* qpack, float* u, cudaStream_t st) {
+int q_finish(const float* partial, const float* upartial, int S, const float* abar, int K, float* Q, uint8_t* qpack, float* u,
+             cudaStream_t st) {
   if ((K & 7) != 0) return fail(PCUDA_E_UNSUPPORTED, "tc::q_finish: K=%d is not a multiple of 8", K);
-  PCUDA_LAUNCH(q_finish_kernel, ((K + 127) / 128) * 4, 1024, 0, st, partial, S, W, alpha, abar, C, K, Q, qpack, u);
+  const int rows = ((K + 127) / 128) * 128;       // the padding rows of the last 128-row block are written too
+  PCUDA_LAUNCH(q_finish_kernel, (rows + kQfRows - 1) / kQfRows, 32 * kQfRows, 0, st, partial, upartial, S, abar, K, Q, qpack, u);
   count_launch();
   return check_launch("tc::q_finish");
 }

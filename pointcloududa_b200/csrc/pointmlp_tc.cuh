@@ -29,9 +29,9 @@ int pack_dy(const DySrc& dys, const Tiling& tl, uint8_t* out, cudaStream_t st);
 // sign_src (non-transposed only): rows with sign_src[r] < 0 are negated (pooled forward layer)
 int pack_w(const float* W, int R, int K, bool transposed, uint8_t* out, cudaStream_t st, const float* sign_src = nullptr);
 // Q = sum_z partial[z] ([S][K*K] split partials, symmetric) -> Q (fp32), qpack (= pack_w(Q, K, K, false)), and
-// u[k] = sum_c alpha_c W[c,k] - sum_k2 Q[k,k2] abar[k2], in one launch
-int q_finish(const float* partial, int S, const float* W, const float* alpha, const float* abar, int C, int K, float* Q,
-             uint8_t* qpack, float* u, cudaStream_t st);
+// u[k] = sum_z upartial[z][k] - sum_k2 Q[k,k2] abar[k2]   (upartial[z][k] = sum_{c in slice z} alpha_c W[c,k]), in one launch
+int q_finish(const float* partial, const float* upartial, int S, const float* abar, int K, float* Q, uint8_t* qpack, float* u,
+             cudaStream_t st);
 
 // y_l = W a_{l-1} (+ bias): stores y (dense) or reduces to per-(cloud,channel) arg-max keys (pool);
 // accumulates bias-free per-channel sum / sum of squares into stats[0..C), stats[C..2C).
