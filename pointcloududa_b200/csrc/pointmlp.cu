@@ -689,6 +689,31 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int64_
   out[i] = static_cast<TOut>(s);
 }
 
+// The same for MANY partials of FEW outputs (the narrow layers' weight gradient: one partial per SM of 64 x 3 values): a
+// thread walking 148 slices alone is 37 dependent round trips.  The 8 warps of a CTA split the slices (contiguous
+// ranges, summed in warp order: deterministic), 32 outputs per CTA.
+template <typename TOut>
+__global__ void __launch_bounds__(256) reduce_partials_split_kernel(const float* __restrict__ partial, int64_t n, int S, TOut* __restrict__ out) {
+  pdl_entry();
+  __shared__ double part[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = blockIdx.x * 32ll + lane;
+  const int per = (S + 7) / 8, s0 = warp * per, s1 = min(S, s0 + per);
+  double t = 0.0;
+  if (i < n) {
+#pragma unroll 8
+    for (int k = s0; k < s1; ++k) t += static_cast<double>(partial[static_cast<int64_t>(k) * n + i]);
+  }
+  part[warp][lane] = t;
+  __syncthreads();
+  if (warp == 0 && i < n) {
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += part[w][lane];
+    out[i] = static_cast<TOut>(r);
+  }
+}
+
 // abar[k] = (sum_s colsum_partial[s,k]) / M.  One warp per channel, lanes interleave the slices; the
 // butterfly reduction has a fixed order, so the result is deterministic.
 __global__ void __launch_bounds__(256)
@@ -729,6 +754,31 @@ __global__ void gram_center_kernel(const double* __restrict__ abar_d, const doub
   if (i >= static_cast<int64_t>(K) * K) return;
   const int k = static_cast<int>(i / K), k2 = static_cast<int>(i % K);
   Ghat[i] = static_cast<float>(G[i] - count * abar_d[k] * abar_d[k2]);
+}
+
+// The three kernels above in one launch (single rank: abar needs no exchange): every CTA sums the column-sum partials
+// into abar (CTA 0 publishes it), then its 256 elements of G = sum_s partial[s] and centres them.
+__global__ void __launch_bounds__(256)
+gram_finish_kernel(const float* __restrict__ gpartial, int Sg, const double* __restrict__ colsum_partial, int Sc, int K,
+                   double count, float* __restrict__ abar, double* __restrict__ abar_d, float* __restrict__ Ghat) {
+  pdl_entry();
+  extern __shared__ double ab[];                   // [K]
+  const int64_t kk = static_cast<int64_t>(K) * K;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  double g = 0.0;
+  if (i < kk)
+    for (int s = 0; s < Sg; ++s) g += static_cast<double>(gpartial[static_cast<int64_t>(s) * kk + i]);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double a = 0.0;
+    for (int s = 0; s < Sc; ++s) a += colsum_partial[static_cast<int64_t>(s) * K + k];
+    a /= count;
+    ab[k] = a;
+    if (blockIdx.x == 0) { abar[k] = static_cast<float>(a); abar_d[k] = a; }
+  }
+  __syncthreads();
+  if (i >= kk) return;
+  const int k = static_cast<int>(i / K), k2 = static_cast<int>(i % K);
+  Ghat[i] = static_cast<float>(g - count * ab[k] * ab[k2]);
 }
 
 // Q[k,k'] = sum_c kappa_c W[c,k] W[c,k'].  grid (K/32, K/32, CS), 256 threads, each 2x2 outputs; slice z
@@ -2121,18 +2171,19 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       PCUDA_LAUNCH(point_contract_kernel<1>, dim3(S32, (K + TM - 1) / TM, (K + TN - 1) / TN), kThreads, 0, sa, DySrc{}, src, src, s.M, chunk32, K, K, partial);
       launches += 1;
     }
-    PCUDA_LAUNCH(reduce_partials_kernel<double>, static_cast<int>((kk + 255) / 256), 256, 0, sa, partial, kk, Sg, w.G);
-    if (sync) {
+    if (!sync) {
+      PCUDA_LAUNCH(gram_finish_kernel, static_cast<int>((kk + 255) / 256), 256, sizeof(double) * K, sa, partial, Sg, w.colsum, S32, K, count,
+                   w.abar, w.abar_d, w.Ghat);
+    } else {
+      PCUDA_LAUNCH(reduce_partials_kernel<double>, static_cast<int>((kk + 255) / 256), 256, 0, sa, partial, kk, Sg, w.G);
       // column means over ALL ranks' points; the Gram matrix stays local and is centred with the global mean
       // (sum_r [G_r - M_r abar abar^T] is the centred Gram matrix of the global batch)
       PCUDA_LAUNCH(abar_kernel, (K + 7) / 8, 256, 0, sa, w.colsum, S32, K, 1.0, w.abar, w.abar_d);
       if (int rc = comm_sum_f64(sync, w.abar_d, K, sa)) return rc;
       PCUDA_LAUNCH(abar_kernel, (K + 7) / 8, 256, 0, sa, w.abar_d, 1, K, count, w.abar, w.abar_d);
-      launches += 1;
-    } else {
-      PCUDA_LAUNCH(abar_kernel, (K + 7) / 8, 256, 0, sa, w.colsum, S32, K, count, w.abar, w.abar_d);
+      PCUDA_LAUNCH(gram_center_kernel, static_cast<int>((kk + 255) / 256), 256, 0, sa, w.abar_d, w.G, K, count_local, w.Ghat);
+      launches += 3;
     }
-    PCUDA_LAUNCH(gram_center_kernel, static_cast<int>((kk + 255) / 256), 256, 0, sa, w.abar_d, w.G, K, count_local, w.Ghat);
     if (ax) cudaEventRecord(ax->side, sa);
     // -- selection side: per-(cloud, channel) coefficients, alpha / kappa, Q = W^T diag(kappa) W
     PCUDA_LAUNCH_PDL(pool_sel_kernel, static_cast<int>((bc * 32 + 255) / 256), 256, 0, st, src, last.weight, last.bias, last.save_mean,
@@ -2164,13 +2215,13 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
       if (ax) cudaStreamWaitEvent(st, ax->side, 0);
       if (int rc = tc::q_finish(w.qpartial, w.upartial, kPoolQSplits, w.abar, K, w.Q, w.qpack, w.u, st)) return rc;
       q_packed = true;
-      launches += 6;     // reduce<double>, abar, gram_center, pool_sel, pool_coef, pool_q (tc:: calls count themselves)
+      launches += 4;     // gram_finish, pool_sel, pool_coef, pool_q (tc:: calls count themselves; cross-rank: + 3 above)
     } else {
       PCUDA_LAUNCH(reduce_partials_kernel<float>, static_cast<int>((kk + 255) / 256), 256, 0, st, w.qpartial, kk, kPoolQSplits, w.Q);
       // -- join: u needs Q (this stream) and abar (Gram side)
       if (ax) cudaStreamWaitEvent(st, ax->side, 0);
       PCUDA_LAUNCH(pool_u_kernel, (K + 31) / 32, 1024, 0, st, last.weight, al, w.Q, w.abar, C, K, w.u);
-      launches += 8;
+      launches += 6;
     }
     if (last.grad_weight) {
       const size_t dw_smem = sizeof(float) * ((kDwCh * (K + 2 * static_cast<size_t>(B)) + 3) & ~static_cast<size_t>(3)) +
@@ -2284,7 +2335,8 @@ static int pointmlp_bwd_impl(const float* x, int64_t sxb, int64_t sxc, int64_t s
         PCUDA_LAUNCH(point_contract_kernel<0>, dim3(S32, (C + TM - 1) / TM, (Kp + TN - 1) / TN), kThreads, 0, sw, dys, ActSrc{}, src_of(l - 1), s.M, chunk32, C, Kp, partial);
         launches += 1;
       }
-      PCUDA_LAUNCH(reduce_partials_kernel<float>, static_cast<int>((ck + 255) / 256), 256, 0, sw, partial, ck, Sw, y.grad_weight);
+      if (Sw >= 32 && ck <= 16384) PCUDA_LAUNCH(reduce_partials_split_kernel<float>, static_cast<int>((ck + 31) / 32), 256, 0, sw, partial, ck, Sw, y.grad_weight);
+      else PCUDA_LAUNCH(reduce_partials_kernel<float>, static_cast<int>((ck + 255) / 256), 256, 0, sw, partial, ck, Sw, y.grad_weight);
       launches += 1;
       if (fork_w) { cudaEventRecord(ax->wdone, sa); wgrad_pending = true; }
     }
