@@ -160,7 +160,10 @@ def bench_config(name: str, w: dict, world: int, precision: str = "bf16", use_gr
                   "working set larger than the last-level cache slice of a core",
             "e2e_pipeline": "GPU arm: copy stream uploads step i+1 (one flat pinned buffer) into a staging set while step i "
                             "runs; one device-to-device move into the step's static inputs",
-            "cuda_graph": f"GPU arm: {bool(use_graph)}", "mlp_precision": f"GPU arm: {precision}; reference arm: fp32"}
+            "cuda_graph": f"GPU arm: {bool(use_graph)}", "mlp_precision": f"GPU arm: {precision}; reference arm: fp32",
+            "d4_passes": "three full D4 forward + backward passes per step in both arms (P2, P3, P4 each compute their own "
+                         "forward); the GPU arm's `shared_trunk` object is the same step with P4 reusing the part of P2's "
+                         "forward that is identical (same cloud, same weights), bit-identical results"}
 
 
 def reference_available() -> bool:
@@ -638,13 +641,16 @@ def measure_step(step, host_flat, result_host, flush, steps: int, world: int, de
     return t_dev, t_e2e
 
 
-def build_step(w: dict, rank: int, dev, precision: str, use_graph: bool, exchange: str = "auto", sync_bn: bool = False):
-    """AdversarialStep of workload `w` with its inputs loaded (per-rank synthetic shard), captured and warmed up."""
+def build_step(w: dict, rank: int, dev, precision: str, use_graph: bool, exchange: str = "auto", sync_bn: bool = False,
+               share_trunk: bool = False):
+    """AdversarialStep of workload `w` with its inputs loaded (per-rank synthetic shard).  share_trunk False: the three D4
+    passes of the step each run their own forward, as the reference does (the configuration every headline number is
+    measured in); True: the product's default, P4 reuses what P2 already computed on the same cloud."""
     import torch
     from pointcloududa_b200.step import RESULT_FIELDS, AdversarialStep, StepConfig
     cfg = StepConfig(B=w["B"], C=w["C"], H=w["H"], W=w["W"], N=w["N"], activation=w["activation"],
                      normalize=w["normalize"], return_prob=w["return_prob"], precision=precision, sync_bn=sync_bn)
-    step = AdversarialStep(cfg, dev, seed=0, exchange=exchange)
+    step = AdversarialStep(cfg, dev, seed=0, exchange=exchange, share_trunk=share_trunk)
     # one pinned host buffer holding a step's inputs in the step's flat layout: one H2D copy per step
     host_flat = torch.zeros(step.input_numel(), dtype=torch.float32).pin_memory()
     host = step.input_layout(host_flat)
@@ -793,6 +799,30 @@ def run_ours(args):
     scale = None
     if not args.skip_scale:
         scale = scale_lines(args, rank, world, dev, flush)
+    # the same step with the product's default forward sharing (collective inside: every rank runs it)
+    shared = None
+    try:
+        step2, hf2, rh2 = build_step(w, rank, dev, args.precision, use_graph, args.exchange, share_trunk=True)
+        step2.run(); torch.cuda.synchronize()
+        l0 = ops.launch_count(); step2.run(); torch.cuda.synchronize()
+        launches2 = ops.launch_count() - l0
+        if use_graph:
+            step2.capture(warmup=2)
+        for _ in range(3):
+            step2.run()
+        torch.cuda.synchronize()
+        k2 = max(5, min(args.steps, 30))
+        t2_dev, t2_e2e = measure_step(step2, hf2, rh2, flush, k2, world, dev)
+        shared = {"value": world * k2 / t2_dev, "unit": UNIT, "ms_per_step": t2_dev / k2 * 1e3, "steps": k2,
+                  "e2e": {"value": world * k2 / t2_e2e, "ms_per_step": t2_e2e / k2 * 1e3},
+                  "gpu_launches_per_step": int(launches2),
+                  "what": "P4 takes both trunks and the STN head of D4's forward pass from P2 (same cloud, same weights: "
+                          "networks/PointNetCls.py share_forward); tests/test_gpu_step_parity.py checks bit-identity"}
+        if world > 1:
+            step2.close()
+        del step2
+    except Exception as e:
+        shared = {"error": repr(e)}
     line = None
     if rank == 0:
         breakdown, roof_ops = op_breakdown(step, w, flush, pk)
@@ -832,7 +862,7 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "samples_per_s": world * w["B"] * args.steps / t_dev,
-            "exchange": step.exchange, "host_affinity": numa, "scale": scale,
+            "exchange": step.exchange, "host_affinity": numa, "scale": scale, "shared_trunk": shared,
             "parity": {"chamfer_indices": "bit-exact (int64 equality vs golden / oracle / torch on this GPU)",
                        "fp32": "entropy 1e-5 rel (+5e-7 abs), Chamfer loss 2e-6, D4 fp32 path 2e-5 values / 2e-4 gradients vs float64",
                        "bf16_mlp": "op level (tensor-core shared-MLP stack, every gradient, L2 and max-norm) <= 1e-2 vs the float64 "

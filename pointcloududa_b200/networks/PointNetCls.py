@@ -56,6 +56,56 @@ def deferred_bn_updates(sink: list):
         _TLS.sink = prev
 
 
+# ---- shared forward passes ------------------------------------------------------------------------------
+# Two of the three D4 passes of an adversarial step see the SAME cloud with the SAME weights (train_mscmrseg.py:232 and
+# :314: the target cloud, once to fool the frozen discriminator, once detached to train it), so everything up to the
+# Dropout of the classifier head — both trunks and the STN head — computes identical values twice.  Inside
+# `with share_forward(memo):` every fused op looks its inputs up in `memo` (storage pointers, shapes, strides of the
+# tensors and parameters it reads, its mode flags): a hit returns aliases of the outputs and saved activations the
+# first call produced — no launch — in a fresh autograd node with its own `needs_input_grad`, ordered behind the
+# producer's kernels by a CUDA event; a miss runs the op and records it.  The caller guarantees that nothing the ops
+# read is modified while the memo is alive (parameters are updated after both passes).  BatchNorm running statistics
+# are unaffected: each pass still reports its (identical) batch statistics to its own `deferred_bn_updates` sink.
+class ForwardMemo:
+    def __init__(self):
+        self.entries = {}
+        self.hits = 0
+
+    def clear(self) -> None:
+        self.entries.clear()
+
+
+@contextlib.contextmanager
+def share_forward(memo: Optional[ForwardMemo]):
+    prev = getattr(_TLS, "memo", None)
+    _TLS.memo = memo
+    try:
+        yield memo
+    finally:
+        _TLS.memo = prev
+
+
+def _tkey(t: Optional[torch.Tensor]):
+    return None if t is None else (t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+
+
+def _memo_wait(entry, tensors) -> None:
+    """Order the current stream behind the kernels that produced a memo entry; in eager mode also tell the caching
+    allocator that the shared tensors are now used on this stream."""
+    cur = torch.cuda.current_stream()
+    cur.wait_event(entry["event"])
+    if not torch.cuda.is_current_stream_capturing():
+        for t in tensors:
+            if t is not None:
+                t.record_stream(cur)
+
+
+def _memo_event():
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    return ev
+
+
 def apply_bn_updates(sinks: Sequence[list]) -> None:
     entries = [e for sink in sinks for e in sink]
     if not entries:
@@ -101,6 +151,27 @@ class _SharedMLP(torch.autograd.Function):
         B, C0, N = x.shape
         dev = x.device
         M = B * N
+        memo = getattr(_TLS, "memo", None)
+        mkey = None
+        if memo is not None and sync is None and all(b is None for b in buffers):
+            mkey = ("mlp", _tkey(x), _tkey(in_trans), pool, train, precision, relus, float(eps), tuple(_tkey(p) for p in params))
+            hit = memo.entries.get(mkey)
+            if hit is not None:
+                memo.hits += 1
+                _memo_wait(hit, [hit["out"], hit["arg"], hit["ws"], hit["tr"], *hit["keep"], *hit["ys"], *hit["means"], *hit["invstds"]])
+                if stats_out is not None:
+                    stats_out.extend(zip(hit["means"], hit["invstds"]))
+                out = hit["out"].detach()
+                ctx.cfg = (pool, train, precision, relus, eps, B, N, L)
+                if pool:
+                    ctx.save_for_backward(x, out)
+                else:
+                    ctx.save_for_backward(x)
+                ctx.keep, ctx.trans, ctx.sync = hit["keep"], hit["tr"], None
+                ctx.saved = (hit["ys"], hit["means"], hit["invstds"], hit["arg"])
+                ctx.fwd_ws = hit["ws"]
+                ctx.param_shapes = [None if p is None else p.shape for p in params]
+                return out
         tr = None
         if in_trans is not None:
             if in_trans.shape != (B, C0, C0) or in_trans.dtype != torch.float32 or in_trans.device != dev:
@@ -153,6 +224,9 @@ class _SharedMLP(torch.autograd.Function):
         ctx.saved = (ys, means, invstds, arg)
         ctx.fwd_ws = ws        # kept alive: the backward pass reads the packed bf16 operands in place
         ctx.param_shapes = [None if p is None else p.shape for p in params]
+        if mkey is not None:
+            memo.entries[mkey] = {"out": out, "arg": arg, "ws": ws, "tr": tr, "keep": keep, "ys": ys, "means": means,
+                                  "invstds": invstds, "event": _memo_event()}
         return out
 
     @staticmethod
@@ -274,6 +348,23 @@ class _FcStack(torch.autograd.Function):
         xc = x.contiguous()
         B = xc.shape[0]
         dev = xc.device
+        memo = getattr(_TLS, "memo", None)
+        mkey = None
+        if memo is not None and all(b is None for b in buffers):
+            mkey = ("fc", _tkey(xc), train, relus, bn_flags, float(eps), int(iden_k), tuple(_tkey(m) for m in masks),
+                    tuple(_tkey(p) for p in params))
+            hit = memo.entries.get(mkey)
+            if hit is not None:
+                memo.hits += 1
+                flat = [t for sv in hit["saved"] for t in sv] + list(hit["keep"]) + [hit["out"]]
+                _memo_wait(hit, flat)
+                if stats_out is not None:
+                    stats_out.extend((sv[0], sv[1]) for sv in hit["saved"])
+                out = hit["out"].detach()
+                ctx.cfg = (train, relus, bn_flags, B, L)
+                ctx.save_for_backward(xc, out)
+                ctx.keep, ctx.saved = hit["keep"], hit["saved"]
+                return out
         lay = (FcLayer * L)()
         keep, saved = [], []
         for l in range(L):
@@ -306,6 +397,8 @@ class _FcStack(torch.autograd.Function):
         saved[-1] = saved[-1][:3] + (None,)         # the output travels through save_for_backward (no ctx <-> output cycle)
         ctx.save_for_backward(xc, out)
         ctx.keep, ctx.saved = keep, saved
+        if mkey is not None:
+            memo.entries[mkey] = {"out": out, "keep": keep, "saved": saved, "event": _memo_event()}
         return out
 
     @staticmethod

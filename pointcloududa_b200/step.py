@@ -34,7 +34,7 @@ from typing import Dict, Optional
 import torch
 
 from . import dist as pdist
-from .networks.PointNetCls import PointNetCls, apply_bn_updates, deferred_bn_updates
+from .networks.PointNetCls import ForwardMemo, PointNetCls, apply_bn_updates, deferred_bn_updates, share_forward
 from .ops import bce_with_logits_grad
 from .optim import FusedSGD
 from .utils.loss import batch_NN_loss, entropy_map
@@ -65,13 +65,15 @@ class AdversarialStep:
     """Owns D4, its optimiser, static input buffers and (optionally) a captured CUDA graph."""
 
     def __init__(self, cfg: StepConfig, device: torch.device, seed: int = 0, concurrent: bool = True,
-                 exchange: str = "auto"):
+                 exchange: str = "auto", share_trunk: bool = True):
         """exchange: how D4's gradient bucket is summed over the ranks of an initialised process group --
         "p2p": libpcuda's NVLink peer-memory kernel (pcuda_comm_allreduce_p2p; the bucket is packed straight into the
         communicator's symmetric buffer), "nccl": ncclAllReduce through libpcuda's own communicator, "torch":
         torch.distributed.all_reduce between two captured half-graphs (round-1 behaviour), "auto": p2p when peer memory
         is available, else nccl.  p2p / nccl are captured inside the ONE graph of the step.  "local": ignore the process
-        group (a single-process step inside a multi-rank job, e.g. as the reference of a parity test)."""
+        group (a single-process step inside a multi-rank job, e.g. as the reference of a parity test).
+        share_trunk: P2 and P4 see the same cloud with the same weights, so P4 takes the part of D4's forward pass below
+        the classifier head's Dropout from P2 instead of recomputing it (bit-identical results either way)."""
         self.cfg = cfg
         self.device = device
         torch.manual_seed(seed)
@@ -124,6 +126,7 @@ class AdversarialStep:
         self.graph_post: Optional[torch.cuda.CUDAGraph] = None
         self._res = []
         self._pending = None
+        self.share_trunk = share_trunk
         self._side = None
         self.concurrent = concurrent
 
@@ -201,8 +204,11 @@ class AdversarialStep:
         # ---- branch A (this stream) — P2: fool the point-cloud discriminator (D4 frozen: gradient into the cloud
         # only).  Issued before P3 / P4 so that Dropout consumes the generator in the reference's order (P2, P3, P4);
         # the streams run concurrently regardless of the issue order.
+        # P2 and P4 run D4 on the same cloud with the same weights: everything below the classifier head's Dropout is
+        # computed once (P2 records, P4 takes aliases: networks/PointNetCls.py, share_forward)
+        memo = ForwardMemo() if self.share_trunk else None
         vertT = I["vertT"].detach().requires_grad_(True)
-        with deferred_bn_updates(sink_p2):
+        with deferred_bn_updates(sink_p2), share_forward(memo):
             D_out4 = self.d4(vertT.transpose(2, 1))[0]
         loss_adv_point, _, g_logit = bce_with_logits_grad(D_out4, 1.0, cfg.dr)
         (gT,) = torch.autograd.grad(D_out4, vertT, g_logit)
@@ -223,7 +229,7 @@ class AdversarialStep:
 
         # ---- branch C (stream s2) — P4: discriminators on the target domain (label 0)
         with torch.cuda.stream(s2):
-            with deferred_bn_updates(sink_p4):
+            with deferred_bn_updates(sink_p4), share_forward(memo):
                 D_out4, leaves = self._d4_fresh(I["vertT"].transpose(2, 1))
             loss_D_diff_4, acc_t, g_logit = bce_with_logits_grad(D_out4, 0.0)
             grads_t = torch.autograd.grad(D_out4, leaves, g_logit, allow_unused=True)

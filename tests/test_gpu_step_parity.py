@@ -355,3 +355,36 @@ def test_adversarial_step_vs_torch_restatement(shape, precision, graph):
             f_m = _l2(mom[torch.float32][k].double().cpu().numpy(), ref_m)
             if np.abs(ref_m).max() > 1e-12:
                 assert _l2(mine, ref_m) <= max(base, 4 * f_m, 2 * worst) + 1e-6, (it, "momentum:" + k)
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+@pytest.mark.parametrize("shape", ["cfg2_small_maps", "mmwhs_shard"])
+def test_shared_trunk_forward_is_bit_identical(shape, graph):
+    """P4 taking the part of D4's forward pass that P2 already computed on the same cloud (share_forward: both trunks and
+    the STN head, everything below the classifier head's Dropout) against every pass computing its own: same seeds, same
+    Dropout draws, two steps — results, gradients, parameters, BatchNorm buffers and momentum must match bit for bit."""
+    from pointcloududa_b200.step import AdversarialStep, StepConfig
+    w = STEP_SHAPES[shape]
+    cfg = StepConfig(B=w["B"], C=w["C"], H=w["H"], W=w["W"], N=w["N"], activation=w["activation"],
+                     normalize=w["normalize"], return_prob=w["return_prob"], precision="bf16", lr_dis=2.5e-3)
+    dev = torch.device(DEV)
+    host = _step_inputs(w, seed=78)
+    outs = []
+    for share in (False, True):
+        torch.cuda.manual_seed(1234)
+        st = AdversarialStep(cfg, dev, seed=3, share_trunk=share)
+        st.load_inputs(host, non_blocking=False)
+        if graph:
+            st.capture(warmup=2)
+        torch.cuda.manual_seed(99)
+        res = [st.run().clone() for _ in range(2)]
+        torch.cuda.synchronize()
+        outs.append((res, st.grad_vertT.clone(), st.bucket.flat.clone(), st.opt.momentum_buffer.clone(),
+                     {k: v.clone() for k, v in st.d4.state_dict().items()}))
+        st.close()
+    (ra, ga, fa, ma, sa), (rb, gb, fb, mb, sb) = outs
+    for x, y in zip(ra, rb):
+        assert torch.equal(x, y)
+    assert torch.equal(ga, gb) and torch.equal(fa, fb) and torch.equal(ma, mb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
