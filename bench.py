@@ -150,6 +150,14 @@ def workload_label(name: str, w: dict) -> str:
             f"{w['N']}-pt clouds")
 
 
+_T0 = time.time()
+
+
+def progress(msg: str) -> None:
+    """Phase marker on stderr (rank-tagged): where a multi-rank run spends its time, and where it stops if it ever hangs."""
+    print(f"[bench rank {os.environ.get('RANK', '0')} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def bench_config(name: str, w: dict, world: int, precision: str = "bf16", use_graph: bool = True) -> dict:
     """`config` of the JSON line — the SAME dict for the GPU arm and for `--impl reference` (the driver compares
     them), so the statements about L2 / graphs name the arm they apply to."""
@@ -270,12 +278,13 @@ KERNEL_WORK = {
     "pack_w_kernel": (None, lambda w: (4.0 + 2.0) * 1024 * 128),
     # sparse rows of the pooled-layer dgrad: arg/coef, one W row per (cloud, channel), read-modify-write of the
     # <= min(C, N) selected points per cloud (y_prev, dz_prev in, dz_prev out), K = 128, C = 1024
-    "pool_sparse_kernel": (None, lambda w: w["B"] * 1024 * (8.0 + 4.0 * 128) + w["B"] * min(1024, w["N"]) * 128 * 12.0),
+    "pool_sparse": (None, lambda w: w["B"] * 1024 * (8.0 + 4.0 * 128) + w["B"] * min(1024, w["N"]) * 128 * 12.0),
     "pool_dw_kernel": (None, lambda w: 1024 * 128 * 8.0 + 128 * 128 * 4.0 + w["B"] * 1024 * (8.0 + 4.0 * 128)),
     "pool_sel_kernel": (None, lambda w: w["B"] * 1024 * (4.0 * 128 + 24.0) + 1024 * 128 * 4.0),   # selected rows + W + out/arg/grad/coef
     "pool_coef_kernel": (None, lambda w: w["B"] * 1024 * 8.0 + 1024 * 28.0),
-    "pool_q_kernel": (None, lambda w: 1024 * 128 * 4.0 + 1024 * 4.0 + 8 * 128 * 128 * 4.0),       # W, kappa in, split partials out
-    "q_finish_kernel": (None, lambda w: 8 * 128 * 128 * 4.0 + 1024 * 128 * 4.0 + 128 * 128 * 6.0),       # partials + W in, Q fp32 + bf16 out
+    "pool_q_kernel": (None, lambda w: 1024 * 128 * 4.0 + 1024 * 8.0 + 8 * 128 * (128 + 1) * 4.0),   # W, kappa, alpha in, split partials out
+    "q_finish_kernel": (None, lambda w: 8 * 128 * (128 + 1) * 4.0 + 128 * 128 * 6.0),                # partials in, Q fp32 + bf16 out
+    "gram_finish_kernel": (None, lambda w: (_splits(w) + 1) * 128 * 128 * 4.0 + _splits(w) * 128 * 8.0),
     "pool_u_kernel": (None, lambda w: 1024 * 128 * 4.0 + 128 * 128 * 4.0 + 1024 * 4.0 + 1024.0),
     "pool_finalize_kernel": (None, lambda w: w["B"] * 1024 * 16.0),
     "act_colsum_kernel": (None, lambda w: 4.0 * _M(w) * 128),
@@ -294,6 +303,7 @@ KERNEL_WORK = {
     "fc_bwd_kernel": (None, lambda w: 2 * 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) / 3 + 4.0 * w["B"] * (1024 + 512)),
     "fc_pull_kernel": (None, lambda w: 4.0 * 512 * 1024 + 4.0 * w["B"] * (1024 + 512)),
     "fc_head": (None, lambda w: 4.0 * (1024 * 512 + 512 * 256 + 256 * 9) + 4.0 * w["B"] * (1024 + 512 + 256)),
+    "sgd_momentum_sum": (None, lambda w: 1.6e6 * 28.0),                        # two gradient lists, momentum, param in / bucket, momentum, param out
     "sgd": (None, lambda w: 1.6e6 * 16.0),                                      # grad, momentum in / momentum, param in+out
     "grad_sum_pack_kernel": (None, lambda w: 1.6e6 * 12.0),                    # two gradient lists in, the bucket out
     "p2p_allreduce_kernel": (None, lambda w: 1.6e6 * 8.0),                     # per GPU: (R-1)/R of the bucket read + written over NVLink
@@ -400,7 +410,8 @@ def kernel_profile(step, w: dict, pk: dict, reps: int = 5, record: bool = True, 
     roof["tail_kernels"] += [{"kernel": short(k), "launches_per_step": v[0] / reps, "us_per_launch": v[1] / v[0]}
                              for k, v in agg.items() if "nccl" in k.lower() and k not in ours]
     roof["peak_source"] = pk["source"]
-    roof["note"] = ("dominant libpcuda kernel of the graph-replayed step at this workload (CUPTI device durations, warm L2); "
+    roof["note"] = ("dominant libpcuda kernel of the graph-replayed step at this workload (CUPTI device durations, warm L2, captured "
+                    "without programmatic dependent launch so that a duration is the kernel's own work, not its wait); "
                     "at cfg2 sizes (2400 points per call) every kernel is latency-bound - `large` holds the roofline-sized shapes")
     return shares, roof
 
@@ -673,6 +684,7 @@ def scale_lines(args, rank: int, world: int, dev, flush):
         sync_bn = name.endswith("_syncbn")          # cfg-3 with BatchNorm statistics over the clouds of all ranks
         if sync_bn and (world == 1 or args.exchange == "torch"):
             continue
+        progress(f"scale line {name}")
         w = dict(WORKLOADS[name.replace("_syncbn", "")])
         if scaling == "strong":
             if w["B"] % world != 0 or w["B"] // world < 2:
@@ -782,23 +794,34 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    progress("timed region")
     t_dev, t_e2e = measure_step(step, host_flat, result_host, flush, args.steps, world, dev)
     clocks = sampler.stop() if rank == 0 else None
+    progress("kernel profile")
     last = {k: float(v) for k, v in zip(RESULT_FIELDS, result_host.tolist())}
 
     # kernel-level profile of the step: collective inside, so every rank runs the steps; rank 0 records
     kernel_shares, roof = None, None
     try:
+        if use_graph:
+            # With programmatic dependent launch a kernel is resident (and its CUPTI record runs) while it still waits
+            # for its predecessor: the per-kernel durations of the profile are taken from a capture without it.
+            ops.tune(8, 1)
+            step.capture(warmup=1)
         kernel_shares, roof = kernel_profile(step, w, pk, record=(rank == 0), workload=args.workload)
     except Exception as e:       # CUPTI unavailable: keep the op-level roofline
         kernel_shares = {"error": repr(e)}
         if rank == 0 and world > 1:
             for _ in range(5):   # keep the collective count matched with the other ranks
                 step.run()
+    finally:
+        ops.tune(8, 0)
     # the multi-GPU configurations BASELINE.json names + the Chamfer-only sweep (collective: every rank takes part)
     scale = None
     if not args.skip_scale:
+        progress("scale lines")
         scale = scale_lines(args, rank, world, dev, flush)
+    progress("shared-trunk variant")
     # the same step with the product's default forward sharing (collective inside: every rank runs it)
     shared = None
     try:
@@ -824,6 +847,7 @@ def run_ours(args):
     except Exception as e:
         shared = {"error": repr(e)}
     line = None
+    progress("rank-0 extras (op breakdown, large shapes, baselines)")
     if rank == 0:
         breakdown, roof_ops = op_breakdown(step, w, flush, pk)
         if roof is None:
@@ -873,6 +897,7 @@ def run_ours(args):
             "last_step": last,
         }
         print(json.dumps(line))
+    progress("done")
     if world > 1:
         dist.barrier()
         step.close()
@@ -943,6 +968,11 @@ def run_chamfer_only(args):
 
 
 def main():
+    # PCUDA_BENCH_WATCHDOG=<seconds>: dump every thread's Python stack and exit if the run is still going by then
+    wd = float(os.environ.get("PCUDA_BENCH_WATCHDOG", "0") or 0)
+    if wd > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

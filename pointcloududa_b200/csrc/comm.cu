@@ -148,8 +148,13 @@ __device__ __forceinline__ void pair_barrier(const P2PArgs& a, size_t flag_off, 
   __syncthreads();
 }
 
+// Neither kernel below lets its successor start early (no griddepcontrol.launch_dependents: pdl_wait() only).  A
+// successor that is resident while this kernel spins on a PEER holds shared memory / thread slots on its SMs; with three
+// concurrent branches per rank those waiting CTAs can cover every SM, the large-shared-memory GEMM another branch needs
+// before ITS exchange cannot be placed, and the two ranks wait for each other until the spin limit (seen with cross-rank
+// BatchNorm at cfg-3 on 2 GPUs).  Kernels waiting on LOCAL predecessors cannot form such a cycle.
 __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(const __grid_constant__ P2PArgs a) {
-  pdl_entry();
+  pdl_wait();
   const int b = blockIdx.x, nb = gridDim.x;
   __shared__ unsigned s_epoch;
   unsigned* epochs = reinterpret_cast<unsigned*>(a.peer[a.rank] + kEpochOff);
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_allreduce_kernel(const __grid
 }
 
 __global__ void __launch_bounds__(1024) p2p_sum_f64_kernel(const __grid_constant__ SmallArgs a) {
-  pdl_entry();
+  pdl_wait();
   char* mine = a.peer[a.rank] + a.chan_off;
   unsigned* ep = reinterpret_cast<unsigned*>(mine);
   const unsigned* flags_mine = ep + 8;

@@ -365,6 +365,28 @@ def _syncbn_body(rank, world):
         print(f"rank {rank}: step graph={graph} ok", flush=True)
     dist.barrier()
     st.close()
+    # ---- (4) cross-rank BatchNorm at the cfg-3 shard shape, bf16, three concurrent branches, graph replay: kernels
+    # waiting for a PEER must not let their successors become resident early (programmatic dependent launch) — with 128-CTA
+    # successors of three branches resident on every SM, the tensor-core GEMM another branch needs before its own
+    # exchange cannot be placed and both ranks spin until the limit (seen in bench.py's cfg3_syncbn line).
+    import time
+    wb = dict(B=16, C=5, H=64, W=64, N=1024, activation="softmax", normalize=True, return_prob=True)
+    big = AdversarialStep(StepConfig(B=wb["B"], C=5, H=64, W=64, N=1024, activation="softmax", normalize=True, return_prob=True,
+                                     precision="bf16", sync_bn=True), dev, seed=0, exchange="auto")
+    big.load_inputs(torch_step.conditioned_inputs(wb, seed=901 + rank), non_blocking=False)
+    big.capture(warmup=1)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(10):
+        res = big.run()
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    big.comm.check_status()                     # raises if any exchange hit the spin limit
+    assert torch.isfinite(res).all()
+    assert dt < 5.0, f"10 cross-rank BatchNorm steps took {dt:.1f} s: an exchange is waiting for the spin limit"
+    print(f"rank {rank}: cfg-3 shard cross-rank BatchNorm, 10 graph replays in {dt * 1e3:.1f} ms", flush=True)
+    dist.barrier()
+    big.close()
     comm.destroy()
 
 
