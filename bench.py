@@ -313,7 +313,8 @@ KERNEL_WORK = {
 
 def kernel_roofline(name: str, w: dict, seconds: float, pk: dict, traffic=None) -> dict:
     """Roofline record of one launch of kernel `name` that took `seconds`: achieved rate against the roof that bounds
-    it — tensor peak if flops / peak_tensor > bytes / peak_hbm, else HBM — with both fractions kept for reference.
+    it — tensor peak if flops / peak_tensor > bytes / peak_hbm, else HBM — with both fractions kept for reference
+    ("latency": the launch's whole roofline time is below 1 us, so neither roof can be approached at this size).
     When the ncu DRAM traffic of the launch is below half of its algorithmic bytes the working set is L2-resident and
     the launch is a chain of dependent L2 round trips: labelled "l2-latency" (the HBM fraction is then not a statement
     about the kernel)."""
@@ -341,6 +342,12 @@ def kernel_roofline(name: str, w: dict, seconds: float, pk: dict, traffic=None) 
             rec["traffic_over_algorithmic"] = traffic / nbytes if nbytes else None
             if rec["bound"] == "hbm" and traffic < 0.5 * nbytes:
                 rec["bound"] = "l2-latency"
+        # a launch whose whole roofline time is below a microsecond cannot reach either roof: it is a chain of a few
+        # dependent memory round trips plus launch latency (the cfg2-sized kernels); `large` holds roofline-sized shapes
+        roof_us = max(nbytes / (pk["hbm"] * 1e9), (flops or 0.0) / (pk["tensor"] * 1e12) if not is_chamfer else 0.0) * 1e6
+        rec["roofline_time_us"] = roof_us
+        if roof_us < 1.0 and not is_chamfer:
+            rec["bound"] = "latency"
         return rec
     return {"bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None}
 

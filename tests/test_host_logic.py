@@ -41,7 +41,7 @@ def test_kernel_work_table_covers_the_profiled_step():
         traffic, src = bench.ncu_traffic("cfg2", "pcuda::" + k)
         assert traffic is not None and traffic >= 0 and "traffic_cfg2.json" in src
         rec = bench.kernel_roofline("pcuda::" + k, w, 10e-6, bench.peaks(), traffic)
-        assert rec["bound"] in ("hbm", "tensor", "l2-latency", "fp32-issue") and rec["frac"] > 0
+        assert rec["bound"] in ("hbm", "tensor", "l2-latency", "latency", "fp32-issue") and rec["frac"] > 0
 
 
 def test_kernel_roofline_picks_the_limiting_roof():

@@ -4,7 +4,9 @@ f = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 rows = [r for r in csv.reader(open(f)) if len(r) > 5]
 hdr = rows[0]; ik = hdr.index("Kernel Name"); iv = hdr.index("Metric Value"); iid = hdr.index("ID")
-data = [(int(r[iid]), r[ik], float(r[iv].replace(",", ""))) for r in rows[1:] if r[iid].isdigit()]
+im = hdr.index("Metric Name")
+# (a list taken together with other metrics, e.g. the DRAM-traffic pass, holds several rows per launch)
+data = [(int(r[iid]), r[ik], float(r[iv].replace(",", ""))) for r in rows[1:] if r[iid].isdigit() and r[im] == "gpu__time_duration.sum"]
 def short(k):
     k = re.sub(r"\(.*", "", k)
     return k.replace("void ", "").replace("pcuda::", "").replace("<unnamed>::", "").replace("unnamed>::", "")[:100]
