@@ -291,6 +291,7 @@ KERNEL_WORK = {
     "abar_kernel": (None, lambda w: _splits(w) * 128 * 8.0),
     "gram_center_kernel": (None, lambda w: 128 * 128 * 12.0),
     "reduce_partials_kernel": (None, lambda w: (_splits(w) + 1) * 1024 * 128 * 4.0),              # widest: dW of the pooled layer
+    "reduce_partials_split_kernel": (None, lambda w: (148 + 1) * 64 * 4 * 4.0),                    # one partial per SM of the 3 -> 64 layer's dW
     "mlp_fwd_narrow_kernel": (None, lambda w: (12.0 + 4.0 * 64) * _M(w)),               # 3 -> 64: cloud in, y out
     "wgrad_narrow_kernel": (None, lambda w: (12.0 + 8.0 * 64) * _M(w)),
     "dgrad_input_narrow_kernel": (None, lambda w: (8.0 * 64 + 12.0) * _M(w)),
