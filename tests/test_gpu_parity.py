@@ -656,6 +656,47 @@ def test_shared_mlp_tensor_core_backward(chans, relus, B, N):
         assert (a - b).abs().max().item() <= 3e-2 * scale_m, (k, (a - b).abs().max().item() / scale_m)
 
 
+@pytest.mark.parametrize("chans,B,N,cloud", [
+    ([3, 64, 128, 1024], 8, 300, "random"),        # the reference's shape: a few points selected by 100+ channels
+    ([3, 64, 128, 1024], 2, 300, "three_points"),  # three distinct points repeated: ~340 rows each, first-index ties
+    ([3, 64, 128, 1024], 3, 1000, "random"),       # N just below C: ~ one channel per selected point, largest count matrix
+    ([3, 64, 128, 1024], 2, 37, "two_points"),     # two distinct points repeated: two heavy rows cut by every segment
+    ([3, 64, 64, 96], 4, 50, "random"),            # K = 64 (half the lanes idle), C = 96 (3 chunks of 32)
+    ([3, 64, 128, 1000], 2, 129, "random"),        # C not a multiple of 32
+])
+def test_pool_sparse_sorted_equals_one_warp_per_point(chans, B, N, cloud):
+    """The sorted / evenly cut sparse-row kernel of the pooled dgrad (pool_sparse_sorted_kernel: counting sort by
+    selected point, CTA ranges cut at point boundaries, warp segments cut anywhere, partials combined in warp order)
+    against the one-warp-per-point kernel it replaces for N < C (pcuda_tune(10, -1)): same forward, same arg-max, every
+    gradient within fp32 summation-order noise, including selections that put all channels on one or two points."""
+    relus = [True] * (len(chans) - 2) + [False]
+    convs, bns, pts = _tc_stack(chans, relus, B, N, seed=B * 1000 + N)
+    # (a cloud of identical points would put all 1024 channels on point 0, but its BatchNorm variance is 0: invstd =
+    # eps^-1/2 per layer amplifies summation-order noise to 1e-3 and the comparison says nothing)
+    if cloud == "three_points":
+        pts = pts[:, :3, :].repeat(1, (N + 2) // 3, 1)[:, :N, :].contiguous()
+    elif cloud == "two_points":
+        pts = pts[:, :2, :].repeat(1, (N + 1) // 2, 1)[:, :N, :].contiguous()
+    ops.tune(10, -1)
+    try:
+        ref = _tc_run(convs, bns, pts, relus, mask=0)
+    finally:
+        ops.tune(10, 0)
+    got = _tc_run(convs, bns, pts, relus, mask=0)
+    assert torch.equal(got["out"], ref["out"])
+    for k in ref:
+        if k == "out" or k.startswith(("rm", "rv")):
+            continue
+        a, b = got[k].double(), ref[k].double()
+        scale = max(b.abs().max().item(), 1e-30)
+        if k.startswith(("ggamma", "gbeta")):
+            scale = max(scale, 1e-3 * ref["gW" + k.lstrip("gamebt")].abs().max().item())
+        assert torch.isfinite(a).all(), k
+        # (summation order differs for points that span several warps; three BatchNorm layers over 2-8 clouds amplify
+        # it to ~2e-5 of the largest entry — an indexing error would be O(1))
+        assert (a - b).abs().max().item() <= 1e-4 * scale, (k, (a - b).abs().max().item() / scale)
+
+
 def _same_rounding_oracle(params, pts, spec, want_cache=False):
     """Logits of the oracle with the tensor-core path's operand rounding (bf16 operands of the wide
     layers), evaluated in float64, and the tolerance to hold the kernel to: 1e-2, or -- where train-mode
