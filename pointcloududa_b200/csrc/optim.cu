@@ -57,10 +57,13 @@ __global__ void __launch_bounds__(kThreads) grad_sum_pack_kernel(const __grid_co
   }
 }
 
+// The two kernels that WRITE PARAMETERS never release their successor early (pdl_wait() only, no launch_dependents):
+// other kernels stage weights before their own grid-dependency wait on the grounds that nothing in flight writes them
+// (pcuda_common.cuh), which must also hold for a forward pass launched right behind an optimiser step.
 __global__ void __launch_bounds__(kThreads) sgd_momentum_kernel(const __grid_constant__ Table t, const float* __restrict__ flat_grad,
                                                                 float* __restrict__ flat_mom, const float* __restrict__ lr_dev,
                                                                 float momentum, float weight_decay) {
-  pdl_entry();
+  pdl_wait();
   const int i = find_slot(t, blockIdx.x);
   const Slot& s = t.s[i];
   const float lr = __ldg(lr_dev);
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(kThreads) sgd_momentum_kernel(const __grid_con
 __global__ void __launch_bounds__(kThreads) sgd_momentum_sum_kernel(const __grid_constant__ Table t, float scale, float* __restrict__ flat_grad,
                                                                     float* __restrict__ flat_mom, const float* __restrict__ lr_dev,
                                                                     float momentum, float weight_decay) {
-  pdl_entry();
+  pdl_wait();
   const int i = find_slot(t, blockIdx.x);
   const Slot& s = t.s[i];
   const float lr = __ldg(lr_dev);

@@ -51,7 +51,9 @@ __device__ __forceinline__ void pdl_wait() {
 // the programmatic-serialization attribute), THEN let the grid after it start early.  In this order at most two kernels
 // of a stream overlap, and when a dependent starts, everything before its predecessor has completed: code a kernel runs
 // BEFORE pdl_entry() may read anything except what its immediate predecessor writes (parameters, its own shared memory,
-// barrier / TMEM set-up), and must not write global memory.
+// barrier / TMEM set-up), and must not write global memory.  Two kinds of kernel call pdl_wait() alone and so release
+// their successor only when they complete: the optimiser kernels (they write the parameters others stage early) and the
+// kernels that spin on a peer GPU (comm.cu: a successor resident while they wait can deadlock two ranks).
 __device__ __forceinline__ void pdl_entry() {
   pdl_wait();
   pdl_trigger();

@@ -1044,6 +1044,36 @@ def test_fused_sgd_sum_step_equals_pack_then_step():
             assert torch.equal(p, q)
 
 
+def test_forward_right_behind_optimiser_step_sees_updated_weights():
+    """fc_fwd_kernel stages its weight rows BEFORE its grid-dependency wait (programmatic dependent launch) on the grounds
+    that nothing in flight writes parameters; the optimiser kernels therefore never release their successor early.  A
+    forward pass queued right behind an SGD step, no synchronisation in between, must equal the same forward pass run
+    after the device has drained — bit for bit, 30 times."""
+    import torch.nn as nn
+    from pointcloududa_b200.networks.PointNetCls import fc_stack
+    from pointcloududa_b200.optim import FusedSGD
+    torch.manual_seed(11)
+    fc1, fc2 = nn.Linear(1024, 512).to(DEV), nn.Linear(512, 256).to(DEV)
+    bn1 = nn.BatchNorm1d(512).to(DEV).train()
+    params = list(fc1.parameters()) + list(fc2.parameters()) + list(bn1.parameters())
+    opt = FusedSGD(params, lr=0.05, momentum=0.9, weight_decay=0.0)
+    flat = torch.zeros(opt.numel, device=DEV)
+    x = torch.randn(8, 1024, device=DEV)
+    g = torch.Generator().manual_seed(3)
+    for it in range(30):
+        grads = [torch.randn(p.shape, generator=g).to(DEV) for p in params]
+        torch.cuda.synchronize()
+        opt.sum_step(grads, None, flat)
+        with torch.no_grad():
+            y = fc_stack(x, [fc1, fc2], [bn1, None], [True, False]).clone()     # queued right behind the optimiser kernel
+        torch.cuda.synchronize()
+        bn1.reset_running_stats()
+        with torch.no_grad():
+            y_ref = fc_stack(x, [fc1, fc2], [bn1, None], [True, False])
+        bn1.reset_running_stats()
+        assert torch.equal(y, y_ref), it
+
+
 @pytest.mark.parametrize("target,weight,n", [(1.0, 1.0, 8), (0.0, 1.0, 32), (1.0, 0.01, 5), (0.0, 0.3, 70)])
 def test_bce_with_logits_matches_torch(target, weight, n):
     """pcuda_bce_logits against F.binary_cross_entropy_with_logits + autograd + the accuracy expression of
