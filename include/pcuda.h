@@ -76,7 +76,8 @@ int pcuda_sm_count(void);
  * 5 = chamfer seed-pass stride (0 default, < 0 off), 6 = no auxiliary-stream fork / finalise-on-read in the MLP,
  * 7 = CTAs of the peer-memory all-reduce (0 default), 8 = programmatic dependent launch (0 default: every launch; 1: off;
  * 3: launches of >= 2 waves of CTAs; 4: only kernels with a prologue before their wait), 9 = small fp64 sums through NCCL instead of the peer-memory mailbox,
- * 10 = pooled dgrad, sparse rows: < 0 switches the sorted / evenly cut kernel off (one warp per selected point instead). */
+ * 10 = pooled dgrad, sparse rows: < 0 switches the sorted / evenly cut kernel off (one warp per selected point instead),
+ * 11 = Chamfer backward always as memset + scatter + finalise (default: one launch per gradient for clouds of <= 2048 points). */
 int pcuda_tune(int key, int value);
 /* Number of kernels this library has launched in this process (monotone; for bench accounting). */
 uint64_t pcuda_launch_count(void);

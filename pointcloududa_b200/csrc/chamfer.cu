@@ -568,6 +568,50 @@ __global__ void chamfer_bwd_finalize(const float* __restrict__ q, const float* _
   }
 }
 
+// Both of the above for a SMALL cloud in one launch (no memset, no global atomics): one CTA per cloud, the fixed-point
+// accumulators of its np points in shared memory.  Same arithmetic, and integer sums do not depend on their order, so
+// the result equals the two-kernel path bit for bit.  grad_p[i] = scale * ((p_i - o_{ip[i]}) / dp_i +
+// sum_{j : io[j] == i} (p_i - o_j) / do_j).
+constexpr int kSmallBwdPoints = 2048;          // 3 * 8 B * 2048 = 48 KB of shared memory
+__global__ void __launch_bounds__(512)
+chamfer_bwd_small_kernel(const float* __restrict__ p, const float* __restrict__ o, const float* __restrict__ dp,
+                         const int64_t* __restrict__ ip, const float* __restrict__ d_o, const int64_t* __restrict__ io,
+                         const float* __restrict__ grad_loss, int np, int no, double inv_nb, float* __restrict__ grad_p) {
+  pdl_entry();
+  extern __shared__ long long sacc[];          // [np][3]
+  const int64_t b = blockIdx.x;
+  for (int i = threadIdx.x; i < 3 * np; i += blockDim.x) sacc[i] = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < no; j += blockDim.x) {
+    const int64_t g = b * no + j;
+    const int64_t i = io[g];
+    const float d = d_o[g];
+    const float* op = o + g * 3;
+    const float* pp = p + (b * np + i) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float u = __fdiv_rn(__fsub_rn(pp[k], op[k]), d);
+      atomicAdd(reinterpret_cast<unsigned long long*>(sacc + i * 3 + k),
+                static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(u) * kFixScale)));
+    }
+  }
+  __syncthreads();
+  const double scale = static_cast<double>(__ldg(grad_loss)) * inv_nb;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    const int64_t g = b * np + i;
+    const int64_t j = ip[g];
+    const float d = dp[g];
+    const float* pp = p + g * 3;
+    const float* op = o + (b * no + j) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float u = __fdiv_rn(__fsub_rn(pp[k], op[k]), d);
+      const double many = static_cast<double>(sacc[i * 3 + k]) * (1.0 / kFixScale);
+      grad_p[g * 3 + k] = static_cast<float>(scale * (static_cast<double>(u) + many));
+    }
+  }
+}
+
 struct Plan {
   int R, threads, tiles_x, tiles_y;
 };
@@ -699,17 +743,29 @@ extern "C" int pcuda_chamfer_bwd(const float* x, const float* y, const float* d1
     const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
     return static_cast<int>(g < cap ? g : cap);
   };
-  if (grad_x) {
+  int launches = 0;
+  const bool small_ok = !tuning(TUNE_CHAMFER_BWD_TWO_PASS);     // A/B and tests: key 11 forces memset + scatter + finalise
+  if (grad_x && small_ok && N <= kSmallBwdPoints) {
+    PCUDA_LAUNCH(chamfer_bwd_small_kernel, B, 512, sizeof(long long) * 3 * static_cast<size_t>(N), st, x, y, d1, i1, d2, i2, grad_loss, N, M,
+                 inv_nb, grad_x);
+    launches += 1;
+  } else if (grad_x) {
+    launches += 2;
     cudaMemsetAsync(acc_x, 0, sizeof(long long) * 3 * static_cast<size_t>(B) * N, st);
     // y_j -> nearest x_i contributes to grad_x[i2(j)]
     PCUDA_LAUNCH(chamfer_bwd_scatter, blocks(static_cast<int64_t>(B) * M), threads, 0, st, y, x, d2, i2, M, N, B, acc_x);
     PCUDA_LAUNCH(chamfer_bwd_finalize, blocks(static_cast<int64_t>(B) * N), threads, 0, st, x, y, d1, i1, acc_x, grad_loss, N, M, B, inv_nb, grad_x);
   }
-  if (grad_y) {
+  if (grad_y && small_ok && M <= kSmallBwdPoints) {
+    PCUDA_LAUNCH(chamfer_bwd_small_kernel, B, 512, sizeof(long long) * 3 * static_cast<size_t>(M), st, y, x, d2, i2, d1, i1, grad_loss, M, N,
+                 inv_nb, grad_y);
+    launches += 1;
+  } else if (grad_y) {
+    launches += 2;
     cudaMemsetAsync(acc_y, 0, sizeof(long long) * 3 * static_cast<size_t>(B) * M, st);
     PCUDA_LAUNCH(chamfer_bwd_scatter, blocks(static_cast<int64_t>(B) * N), threads, 0, st, x, y, d1, i1, N, M, B, acc_y);
     PCUDA_LAUNCH(chamfer_bwd_finalize, blocks(static_cast<int64_t>(B) * M), threads, 0, st, y, x, d2, i2, acc_y, grad_loss, M, N, B, inv_nb, grad_y);
   }
-  count_launch((grad_x ? 2 : 0) + (grad_y ? 2 : 0));
+  count_launch(launches);
   return check_launch("chamfer_bwd");
 }

@@ -25,7 +25,7 @@ static inline cudaError_t smem_optin(F* fn, int bytes) {
   return smem_optin_impl(reinterpret_cast<const void*>(fn), bytes);
 }
 
-enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_FP32 = 2, TUNE_MLP_TC_MASK = 3, TUNE_MLP_EPI_DEBUG = 4, TUNE_CHAMFER_SEED = 5, TUNE_MLP_NO_FORK = 6, TUNE_COMM_BLOCKS = 7, TUNE_PDL = 8, TUNE_COMM_NO_SMALL_P2P = 9, TUNE_SPARSE_SORTED = 10, TUNE_NKEYS = 12 };
+enum TuneKey { TUNE_ENTROPY_PRECISE = 0, TUNE_CHAMFER_ROWS = 1, TUNE_MLP_FORCE_FP32 = 2, TUNE_MLP_TC_MASK = 3, TUNE_MLP_EPI_DEBUG = 4, TUNE_CHAMFER_SEED = 5, TUNE_MLP_NO_FORK = 6, TUNE_COMM_BLOCKS = 7, TUNE_PDL = 8, TUNE_COMM_NO_SMALL_P2P = 9, TUNE_SPARSE_SORTED = 10, TUNE_CHAMFER_BWD_TWO_PASS = 11, TUNE_NKEYS = 12 };
 
 // ---- programmatic dependent launch -----------------------------------------------------------------
 // The hot path at the reference's shapes is a chain of ~70 dependent launches of 3-20 us per D4 pass: what a step

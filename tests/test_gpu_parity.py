@@ -326,6 +326,28 @@ def test_chamfer_backward(golden_chamfer, case):
     assert max_rel(x.grad.cpu().numpy() / 1.5, g["grad_x"]) < 5e-3
 
 
+@pytest.mark.parametrize("B,N", [(8, 300), (3, 1024), (2, 2048), (5, 1)])
+def test_chamfer_backward_single_launch_equals_two_pass(B, N):
+    """Clouds of <= 2048 points: the backward is ONE launch per gradient (one CTA per cloud, fixed-point accumulators in
+    shared memory) instead of memset + scatter + finalise (pcuda_tune(11, 1)): same arithmetic, integer sums — bit-identical,
+    for both gradients, also with many points sharing one nearest neighbour (clustered clouds)."""
+    g = torch.Generator().manual_seed(B * 7 + N)
+    x = torch.rand(B, N, 3, generator=g).to(DEV)
+    y = (torch.randint(0, 4, (B, N, 3), generator=g).float() / 3.0).to(DEV)      # few distinct points: heavy scatter targets
+    outs = []
+    for two_pass in (1, 0):
+        ops.tune(11, two_pass)
+        try:
+            xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+            loss = ops.chamfer_nn(xr, yr)[0]
+            gx, gy = torch.autograd.grad(loss * 1.7, (xr, yr))
+            outs.append((gx.clone(), gy.clone()))
+        finally:
+            ops.tune(11, 0)
+    assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[0][1]).all()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_chamfer_backward_deterministic_and_no_grad():
     x, y = synth_clouds(4, 512, seed=91, mode="near")
     grads = []
