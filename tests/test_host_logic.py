@@ -68,3 +68,49 @@ def test_step_input_layout_offsets_are_aligned():
     assert views["vertS"].shape == (8, 300, 3) and views["vertT"].data_ptr() - views["vertS"].data_ptr() == 7232 * 4
     with pytest.raises(ValueError):
         obj.input_layout(torch.zeros(total + 1))
+
+
+def test_share_forward_context_nests_and_restores():
+    """share_forward / ForwardMemo (networks/PointNetCls.py): the memo is thread-local state of the fused ops; the context
+    manager installs it, nests, and restores the previous one (also on exceptions).  No CUDA needed."""
+    from pointcloududa_b200.networks import PointNetCls as P
+    assert getattr(P._TLS, "memo", None) is None
+    a, b = P.ForwardMemo(), P.ForwardMemo()
+    with P.share_forward(a):
+        assert P._TLS.memo is a
+        with P.share_forward(b):
+            assert P._TLS.memo is b
+        assert P._TLS.memo is a
+        with P.share_forward(None):           # an inner region that must not share
+            assert P._TLS.memo is None
+        assert P._TLS.memo is a
+        try:
+            with P.share_forward(b):
+                raise RuntimeError("x")
+        except RuntimeError:
+            pass
+        assert P._TLS.memo is a
+    assert P._TLS.memo is None
+    a.entries["k"] = 1
+    a.clear()
+    assert not a.entries
+    t = __import__("torch").zeros(3, 4)[:, 1:]
+    assert P._tkey(t) == (t.data_ptr(), (3, 3), (4, 1)) and P._tkey(None) is None
+
+
+def test_roofline_labels_small_launches_as_latency():
+    """A launch whose whole roofline time is below a microsecond is labelled 'latency' (bench.kernel_roofline): the cfg2-sized
+    FC layer; the same kernel name at a roofline-sized shape keeps its HBM / tensor label."""
+    import bench
+    pk = {"hbm": 6546.2, "tensor": 1666.9, "source": "test"}
+    w = dict(bench.WORKLOADS["cfg2"])
+    r = bench.kernel_roofline("pcuda::fc_fwd_kernel", w, 5.8e-6, pk, traffic=9.4e5)
+    assert r["bound"] == "latency" and r["roofline_time_us"] < 1.0 and 0 < r["frac"] < 0.1
+    big = dict(bench.WORKLOADS["cfg5_rank"])
+    r = bench.kernel_roofline("pcuda::tc::ws_kernel<1>", big, 45e-6, pk, traffic=None)
+    assert r["bound"] == "tensor" and 0.3 < r["frac"] < 0.6
+    r = bench.kernel_roofline("pcuda::entropy_bwd_vec4<1, 5, true, true, false>", big, 170e-6, pk, traffic=None)
+    assert r["bound"] == "hbm"
+    for name in ("pool_sparse_sorted_kernel", "gram_finish_kernel", "reduce_partials_split_kernel<float>", "sgd_momentum_sum_kernel",
+                 "chamfer_bwd_small_kernel", "q_finish_kernel", "pool_q_kernel"):
+        assert any(frag in name for frag in bench.KERNEL_WORK), name
