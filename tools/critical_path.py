@@ -1,6 +1,9 @@
 """Approximate critical path of the graph-replayed adversarial step from CUPTI kernel records: walk back from the
 kernel that ends last, each time to the kernel whose end is the latest one not after the current start (+0.3 us).
-Prints the chain with durations and the gaps between links.   python tools/critical_path.py [cfg2|cfg5_rank]"""
+Prints the chain with durations and the gaps between links.   python tools/critical_path.py [cfg2|cfg5_rank]
+The step is captured WITHOUT programmatic dependent launch (pcuda_tune(8, 1)): with it a kernel's record starts when the
+kernel becomes resident, i.e. includes the time it waits for its predecessor (see tools/stream_chains.py for that view).
+The profiler itself stretches the step (branches overlap less than in an unprofiled replay): read shares, not totals."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,6 +16,8 @@ w = dict(bench.WORKLOADS[wl])
 dev = torch.device("cuda", 0)
 cfg = StepConfig(B=w["B"], C=w["C"], H=w["H"], W=w["W"], N=w["N"], activation=w["activation"], normalize=w["normalize"],
                  return_prob=w["return_prob"])
+from pointcloududa_b200 import ops
+ops.tune(8, 1)
 step = AdversarialStep(cfg, dev, seed=0)
 step.load_inputs(bench.make_host_inputs(w, 0, pinned=False), non_blocking=False)
 for _ in range(3):
