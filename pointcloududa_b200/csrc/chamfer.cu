@@ -582,17 +582,40 @@ chamfer_bwd_small_kernel(const float* __restrict__ p, const float* __restrict__ 
   const int64_t b = blockIdx.x;
   for (int i = threadIdx.x; i < 3 * np; i += blockDim.x) sacc[i] = 0;
   __syncthreads();
-  for (int j = threadIdx.x; j < no; j += blockDim.x) {
-    const int64_t g = b * no + j;
-    const int64_t i = io[g];
-    const float d = d_o[g];
-    const float* op = o + g * 3;
-    const float* pp = p + (b * np + i) * 3;
+  // Ground-truth clouds repeat points (and one cloud per batch is all zeros: every query's nearest neighbour is index
+  // 0), so many lanes hit the same accumulator: a 64-bit shared-memory atomic is a compare-and-swap loop and 300
+  // contenders on one address cost ~25 us.  The lanes of a warp that share a target first add their (integer)
+  // contributions through shuffles; one lane per distinct target issues the atomic.
+  const int lane = threadIdx.x & 31;
+  for (int j0 = threadIdx.x - lane; j0 < no; j0 += blockDim.x) {       // warp-uniform trip count
+    const int j = j0 + lane;
+    const bool valid = j < no;
+    const int64_t g = b * no + (valid ? j : 0);
+    const int i = valid ? static_cast<int>(io[g]) : -1 - lane;          // invalid lanes: unique negative keys
+    long long v[3] = {0, 0, 0};
+    if (valid) {
+      const float d = d_o[g];
+      const float* op = o + g * 3;
+      const float* pp = p + (b * np + i) * 3;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float u = __fdiv_rn(__fsub_rn(pp[k], op[k]), d);
-      atomicAdd(reinterpret_cast<unsigned long long*>(sacc + i * 3 + k),
-                static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(u) * kFixScale)));
+      for (int k = 0; k < 3; ++k) {
+        const float u = __fdiv_rn(__fsub_rn(pp[k], op[k]), d);
+        v[k] = __double2ll_rn(static_cast<double>(u) * kFixScale);
+      }
+    }
+    const unsigned mk = __match_any_sync(0xffffffffu, i);
+    long long sum[3] = {0, 0, 0};
+    for (int src = 0; src < 32; ++src) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const long long t = __shfl_sync(0xffffffffu, v[k], src);
+        if ((mk >> src) & 1u) sum[k] += t;
+      }
+    }
+    if (valid && lane == __ffs(mk) - 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        atomicAdd(reinterpret_cast<unsigned long long*>(sacc + i * 3 + k), static_cast<unsigned long long>(sum[k]));
     }
   }
   __syncthreads();
